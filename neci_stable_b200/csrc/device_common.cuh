@@ -1,0 +1,274 @@
+// Device-side building blocks of the FCIQMC engine: determinant bit-string
+// arithmetic (popc / ffs based, no orbital lists), the counter-based Philox
+// streams, and the parameter block every kernel receives by value.
+//
+// Orbital numbering follows NECI: 1-based spin orbitals, odd = beta,
+// even = alpha (src/macros.h:16,21); orbital o is bit (o-1)%64 of word (o-1)/64
+// (src/BitReps.F90:164-306).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/neci_gpu.h"
+
+namespace ng {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define NG_MAX_BASIS 128
+#define NG_MAX_CLASSES 16
+
+// ---------------------------------------------------------------------------
+// Determinant occupation bits in registers.  NW = nIfD + 1 = 1 or 2 words.
+// ---------------------------------------------------------------------------
+template <int NW> struct Det { u64 w[NW]; };
+
+#define NG_BETA_MASK  0x5555555555555555ull   /* odd orbitals  -> even bit index */
+#define NG_ALPHA_MASK 0xAAAAAAAAAAAAAAAAull   /* even orbitals -> odd bit index  */
+
+template <int NW> __device__ __forceinline__ bool det_eq(const Det<NW> &a, const Det<NW> &b) {
+    bool e = a.w[0] == b.w[0];
+    if (NW > 1) e = e && (a.w[1] == b.w[1]);
+    return e;
+}
+template <int NW> __device__ __forceinline__ bool occ(const Det<NW> &d, int orb) {
+    const int b = orb - 1;
+    if (NW == 1) return (d.w[0] >> b) & 1ull;
+    return (d.w[b >> 6] >> (b & 63)) & 1ull;
+}
+template <int NW> __device__ __forceinline__ void set_orb(Det<NW> &d, int orb) {
+    const int b = orb - 1;
+    if (NW == 1) d.w[0] |= 1ull << b; else d.w[b >> 6] |= 1ull << (b & 63);
+}
+template <int NW> __device__ __forceinline__ void clr_orb(Det<NW> &d, int orb) {
+    const int b = orb - 1;
+    if (NW == 1) d.w[0] &= ~(1ull << b); else d.w[b >> 6] &= ~(1ull << (b & 63));
+}
+template <int NW> __device__ __forceinline__ int popc(const Det<NW> &d) {
+    int n = __popcll(d.w[0]);
+    if (NW > 1) n += __popcll(d.w[1]);
+    return n;
+}
+// FindBitExcitLevel (src/DetBitOps.F90:140-180): popcount(ref & (ref ^ det))
+template <int NW> __device__ __forceinline__ int excit_level(const Det<NW> &ref, const Det<NW> &d) {
+    int n = __popcll(ref.w[0] & (ref.w[0] ^ d.w[0]));
+    if (NW > 1) n += __popcll(ref.w[1] & (ref.w[1] ^ d.w[1]));
+    return n;
+}
+// bit index (0-based) of the n-th (1-based) set bit of a 64-bit word; n <= popc(x)
+__device__ __forceinline__ int select64(u64 x, int n) {
+    const u32 lo = (u32)x, hi = (u32)(x >> 32);
+    const int cl = __popc(lo);
+    if (n <= cl) return __fns(lo, 0, n);
+    return 32 + __fns(hi, 0, n - cl);
+}
+// orbital (1-based) holding the n-th set bit of det & mask
+template <int NW> __device__ __forceinline__ int select_orb(const Det<NW> &d, u64 mask, int n) {
+    const u64 a = d.w[0] & mask;
+    if (NW == 1) return select64(a, n) + 1;
+    const int c = __popcll(a);
+    if (n <= c) return select64(a, n) + 1;
+    return 64 + select64(d.w[NW - 1] & mask, n - c) + 1;
+}
+// number of occupied orbitals with index < orb  (== position in nI, 0-based)
+template <int NW> __device__ __forceinline__ int count_below(const Det<NW> &d, int orb) {
+    const int b = orb - 1;
+    if (NW == 1) return __popcll(d.w[0] & ((1ull << b) - 1ull));
+    if (b < 64) return __popcll(d.w[0] & ((1ull << b) - 1ull));
+    return __popcll(d.w[0]) + __popcll(d.w[NW - 1] & ((1ull << (b - 64)) - 1ull));
+}
+// occupied orbitals strictly between orbitals a and b (a != b)
+template <int NW> __device__ __forceinline__ int count_between(const Det<NW> &d, int a, int b) {
+    const int lo = min(a, b), hi = max(a, b);
+    // below(hi) counts orbitals < hi, below(lo+1) counts orbitals <= lo
+    return count_below(d, hi) - count_below(d, lo + 1);
+}
+// iterate set bits in ascending orbital order: returns next orbital and clears it
+template <int NW> __device__ __forceinline__ int pop_lowest(Det<NW> &d) {
+    if (NW == 1 || d.w[0]) { const int b = __ffsll((long long)d.w[0]) - 1; d.w[0] &= d.w[0] - 1ull; return b + 1; }
+    const int b = __ffsll((long long)d.w[NW - 1]) - 1; d.w[NW - 1] &= d.w[NW - 1] - 1ull; return 64 + b + 1;
+}
+template <int NW> __device__ __forceinline__ bool det_any(const Det<NW> &d) {
+    u64 x = d.w[0]; if (NW > 1) x |= d.w[1]; return x != 0ull;
+}
+
+__device__ __forceinline__ bool is_beta(int orb) { return orb & 1; }
+__device__ __forceinline__ int gtid(int orb) { return (orb + 1) >> 1; }     // spatial index, 1-based
+__device__ __forceinline__ int fuse_index(int x, int y) {                  // src/lib/util_mod.fpp:429-441
+    return (x < y) ? x + y * (y - 1) / 2 : y + x * (x - 1) / 2;
+}
+__device__ __forceinline__ double dsign(double a, double b) { return copysign(a, b); }
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10, counter based; stream keyed by (seed, iteration, determinant
+// hash, attempt, purpose) -- DESIGN.md §RNG.  Draw j of a stream comes from
+// block j/2 (lanes {0,1} or {2,3}), mapped to [0,1) with 53 bits.
+// ---------------------------------------------------------------------------
+enum : u32 { RNG_NSPAWN = 0, RNG_ATTEMPT = 1, RNG_DEATH = 2, RNG_ROUND_SPAWN = 3, RNG_PRUNE = 4 };
+
+__host__ __device__ __forceinline__ u64 mix64(u64 z) {
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+template <int NW> __device__ __forceinline__ u64 det_hash64(const Det<NW> &d) {
+    u64 h = mix64(d.w[0] + 0x9E3779B97F4A7C15ull);
+    if (NW > 1) h = mix64((h ^ (d.w[NW - 1] * 0xC2B2AE3D27D4EB4Full)) + 0x165667B19E3779F9ull);
+    return h;
+}
+
+struct Stream {
+    u32 c0, c1, c2, c3, k0, k1;
+    u32 x2, x3;        // second half of the current block
+    int next;
+    __device__ __forceinline__ Stream(u64 seed, long long iter, u64 h, u32 attempt, u32 purpose) {
+        c0 = (u32)h; c1 = (u32)(h >> 32); c2 = attempt; c3 = purpose << 24;
+        k0 = (u32)seed ^ (u32)(seed >> 32); k1 = (u32)iter; next = 0; x2 = x3 = 0;
+    }
+    __device__ __forceinline__ double draw() {
+        u32 a, b;
+        if ((next & 1) == 0) {
+            u32 v0 = c0, v1 = c1, v2 = c2, v3 = c3 | (u32)(next >> 1);
+            u32 q0 = k0, q1 = k1;
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                if (r) { q0 += 0x9E3779B9u; q1 += 0xBB67AE85u; }
+                const u32 hi0 = __umulhi(0xD2511F53u, v0), lo0 = 0xD2511F53u * v0;
+                const u32 hi1 = __umulhi(0xCD9E8D57u, v2), lo1 = 0xCD9E8D57u * v2;
+                const u32 n0 = hi1 ^ v1 ^ q0, n2 = hi0 ^ v3 ^ q1;
+                v0 = n0; v1 = lo1; v2 = n2; v3 = lo0;
+            }
+            a = v0; b = v1; x2 = v2; x3 = v3;
+        } else { a = x2; b = x3; }
+        ++next;
+        const u64 u = (u64)a | ((u64)b << 32);
+        return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Parameter block (passed by value; lives in the kernel's constant bank).
+// ---------------------------------------------------------------------------
+struct Params {
+    // configuration scalars
+    int nel, nbasis, nocc_alpha, nocc_beta;
+    int nranks, rank, balance_blocks;
+    int system_type;
+    int t_trunc_initiator, t_all_real_coeff, t_real_spawn_cutoff, t_death_before_comms;
+    int t_init_coherent_rule, t_no_brillouin, t_exch, t_semi_stochastic, t_core_inits;
+    double initiator_walk_no, real_spawn_cutoff, occupied_thresh, av_mc_excits;
+    double hii, ecore;
+    u64 seed;
+    u64 ref[2];
+    // hashing tables (global memory copies)
+    const int *random_orb_index;      // [nbasis]
+    const int *lb_mapping;            // [balance_blocks]
+    // FCIDUMP
+    const double *umat, *tmat;
+    // PCHB
+    int n_spat, ij_max, ab_max;
+    const double *probs, *bias, *p_exch;
+    const int *alias;
+    const int2 *tgt_orbs;
+    double p_singles, p_doubles, p_parallel;
+    int n_classes;
+    const unsigned char *class_of_spinorb;          // [nbasis]
+    const int *class_start, *class_orbs;            // CSR of class members
+    u64 class_mask[NG_MAX_CLASSES][2];
+    // r-space Hubbard
+    int max_neigh;
+    const int *neighbours;
+    double uhub;
+    // k-space Hubbard
+    int n_k;
+    const int *ksum, *kdiff;
+    const double *eps_k;
+    double u_over_n;
+};
+
+// main walker list, structure of arrays in HBM
+struct WalkerList {
+    u64 *det0, *det1;        // occupation words (det1 unused for NW = 1)
+    double *sgn;
+    int *flg;
+    double *diagH, *offH;
+    long long cap;
+    // open-addressing hash table: entry = (tag32 << 32) | slot ; EMPTY / TOMB sentinels
+    u64 *ht; u64 ht_mask;
+    // free-slot stacks: A is popped, B is pushed (merged between kernels)
+    int *freeA, *freeB;
+    // device counters: [0] n_list, [1] n_freeA, [2] n_freeB, [3] n_tomb, [4] n_heavy,
+    //                  [5] n_insert, [6] err flags, [7] n_merged
+    long long *ctr;
+};
+enum { C_NLIST = 0, C_NFREEA, C_NFREEB, C_NTOMB, C_NHEAVY, C_NINSERT, C_ERR, C_NMERGED, C_COUNT = 16 };
+
+#define HT_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define HT_TOMB  0xFFFFFFFFFFFFFFFEull
+
+#define F_INIT   (1 << NECI_FLAG_INITIATOR)
+#define F_DETERM (1 << NECI_FLAG_DETERMINISTIC)
+#define F_REMOVED (1 << NECI_FLAG_REMOVED)
+#define F_DPARENT (1 << NECI_FLAG_DETERM_PARENT)
+// engine-internal marker bits inside spawn-record flag words (never leave the device)
+#define SF_MULTI (1ll << 40)   /* record merged from >= 2 spawns */
+#define SF_DEAD  (1ll << 41)   /* record folded into its representative */
+
+template <int NW> __device__ __forceinline__ Det<NW> load_det(const WalkerList &L, long long i) {
+    Det<NW> d; d.w[0] = L.det0[i]; if (NW > 1) d.w[NW - 1] = L.det1[i]; return d;
+}
+template <int NW> __device__ __forceinline__ void store_det(const WalkerList &L, long long i, const Det<NW> &d) {
+    L.det0[i] = d.w[0]; if (NW > 1) L.det1[i] = d.w[NW - 1];
+}
+template <int NW> __device__ __forceinline__ Det<NW> ref_det(const Params &P) {
+    Det<NW> d; d.w[0] = P.ref[0]; if (NW > 1) d.w[NW - 1] = P.ref[1]; return d;
+}
+
+// hash-table probe: returns slot or -1.  If ht_pos is given it receives the
+// table position of the hit (for tombstoning) or of the terminating EMPTY.
+template <int NW>
+__device__ __forceinline__ long long ht_lookup(const WalkerList &L, const Det<NW> &d, u64 h, u64 *ht_pos = nullptr,
+                                               long long *first_tomb = nullptr) {
+    const u32 tag = (u32)(h >> 32);
+    u64 pos = h & L.ht_mask;
+    if (first_tomb) *first_tomb = -1;
+    for (;;) {
+        const u64 e = L.ht[pos];
+        if (e == HT_EMPTY) { if (ht_pos) *ht_pos = pos; return -1; }
+        if (e == HT_TOMB) { if (first_tomb && *first_tomb < 0) *first_tomb = (long long)pos; }
+        else if ((u32)(e >> 32) == tag) {
+            const long long slot = (long long)(e & 0xFFFFFFFFull);
+            if (det_eq(load_det<NW>(L, slot), d)) { if (ht_pos) *ht_pos = pos; return slot; }
+        }
+        pos = (pos + 1) & L.ht_mask;
+    }
+}
+// insert a key known to be absent (unique among concurrent inserters)
+__device__ __forceinline__ void ht_insert(const WalkerList &L, u64 h, long long slot, u64 start_pos) {
+    const u64 entry = ((u64)(u32)(h >> 32) << 32) | (u64)(u32)slot;
+    u64 pos = start_pos;
+    for (;;) {
+        const u64 e = L.ht[pos];
+        if (e == HT_EMPTY || e == HT_TOMB) {
+            const u64 old = atomicCAS((unsigned long long *)&L.ht[pos], e, entry);
+            if (old == e) { if (e == HT_TOMB) atomicAdd((unsigned long long *)&L.ctr[C_NTOMB], (unsigned long long)-1ll); return; }
+            continue;     // re-read this position
+        }
+        pos = (pos + 1) & L.ht_mask;
+    }
+}
+// RemoveHashDet (src/load_balancer.fpp:631-644): tombstone + push the slot on the free stack
+template <int NW>
+__device__ __forceinline__ void ht_remove(const WalkerList &L, const Det<NW> &d, u64 h, long long slot) {
+    u64 pos;
+    const long long s = ht_lookup<NW>(L, d, h, &pos);
+    if (s == slot) {
+        L.ht[pos] = HT_TOMB;
+        atomicAdd((unsigned long long *)&L.ctr[C_NTOMB], 1ull);
+    }
+    const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NFREEB], 1ull);
+    L.freeB[k] = (int)slot;
+}
+
+}  // namespace ng

@@ -1,0 +1,404 @@
+// Device-side Hamiltonian matrix elements and excitation generators, written
+// directly on the occupation bit-strings (no nI lists, no per-thread arrays):
+//   Slater-Condon rules          src/sltcnd.fpp:585-708
+//   UMAT / TMAT access           src/UMatCache.F90:257-296, src/OneEInts.F90:188-226
+//   PCHB doubles + uniform singles
+//        src/gasci_pchb_doubles_spatorb_fastweighted.fpp:155-277,
+//        src/excit_gens_int_weighted.F90:722-840, src/aliasSampling.F90:310-332,
+//        src/GenRandSymExcitNUMod.F90:1118-1286, src/excitation_generators.F90:112-138
+//   real-space Hubbard           src/real_space_hubbard.F90:1938-2142,2303-2321,2425-2457
+//   k-space Hubbard              src/k_space_hubbard.F90:356-374,535-625,1712-1817,2620-2671
+//   DetermineDetNode             src/load_balance_calcnodes.F90:25-117
+#pragma once
+#include "device_common.cuh"
+
+namespace ng {
+
+#define NG_EPS 1e-13   /* src/lib/constants.F90:28 */
+
+template <int NW> struct Excit {
+    bool valid;
+    int ic;
+    int src1, src2, tgt1, tgt2;    // sorted as make_single / make_double return them
+    bool parity;
+    double pgen;
+    Det<NW> detJ;
+    int err;
+};
+
+// ---- integrals ---------------------------------------------------------------
+__device__ __forceinline__ int tri(int a, int b) { return (a > b) ? a * (a - 1) / 2 + b : b * (b - 1) / 2 + a; }
+// <ij|kl> over spatial orbitals (1-based): UMAT(UMatInd(i,j,k,l))
+__device__ __forceinline__ double umat_el(const Params &P, int i, int j, int k, int l) {
+    const int A = tri(i, k), B = tri(j, l);
+    const long long ind = (A > B) ? (long long)A * (A - 1) / 2 + B : (long long)B * (B - 1) / 2 + A;
+    return __ldg(&P.umat[ind - 1]);
+}
+__device__ __forceinline__ double tmat_el(const Params &P, int i, int j) {
+    return __ldg(&P.tmat[(size_t)(i - 1) + (size_t)P.nbasis * (j - 1)]);
+}
+__device__ __forceinline__ double umat_k(const Params &P, int i, int j, int k, int l) {   // get_umat_kspace
+    const int a = __ldg(&P.ksum[(i - 1) * P.n_k + (j - 1)]), b = __ldg(&P.ksum[(k - 1) * P.n_k + (l - 1)]);
+    return (a == b) ? P.u_over_n : 0.0;
+}
+
+// parity of the double excitation {s1<s2} -> {t1<t2} (make_double, src/excit_parity.F90:78-170):
+// orbitals jumped by s1->t1 in D, then by s2->t2 in D - s1 + t1.
+template <int NW>
+__device__ __forceinline__ bool parity_double(const Det<NW> &d, int s1, int s2, int t1, int t2) {
+    int c = count_between(d, s1, t1);
+    Det<NW> d2 = d; clr_orb(d2, s1); set_orb(d2, t1);
+    c += count_between(d2, s2, t2);
+    return c & 1;
+}
+template <int NW>
+__device__ __forceinline__ bool parity_single(const Det<NW> &d, int s, int t) { return count_between(d, s, t) & 1; }
+
+// ---- Slater-Condon -----------------------------------------------------------
+template <int NW>
+__device__ double sltcnd_0(const Params &P, const Det<NW> &d) {
+    double hel_sing = 0.0, hel_doub = 0.0, hel_tmp = 0.0;
+    Det<NW> a = d;
+    while (det_any(a)) {
+        const int oi = pop_lowest(a);
+        hel_sing += tmat_el(P, oi, oi);
+        const int idi = gtid(oi);
+        Det<NW> b = a;
+        double s = 0.0;
+        while (det_any(b)) {
+            const int oj = pop_lowest(b);
+            const int idj = gtid(oj);
+            s += umat_el(P, idi, idj, idi, idj);
+            if (P.t_exch && ((oi ^ oj) & 1) == 0) hel_tmp -= umat_el(P, idi, idj, idj, idi);
+        }
+        hel_doub += s;
+    }
+    return hel_doub + hel_tmp + hel_sing;
+}
+template <int NW>
+__device__ double sltcnd_1(const Params &P, const Det<NW> &d, int src, int tgt) {
+    const int id1 = gtid(src), id2 = gtid(tgt);
+    double hel = 0.0;
+    if (((src ^ tgt) & 1) == 0) {
+        Det<NW> a = d; clr_orb(a, src);
+        while (det_any(a)) { const int id = gtid(pop_lowest(a)); hel += umat_el(P, id1, id, id2, id); }
+        if (P.t_exch) {
+            Det<NW> b = d; clr_orb(b, src);
+            b.w[0] &= (src & 1) ? NG_BETA_MASK : NG_ALPHA_MASK;
+            if (NW > 1) b.w[NW - 1] &= (src & 1) ? NG_BETA_MASK : NG_ALPHA_MASK;
+            while (det_any(b)) { const int id = gtid(pop_lowest(b)); hel -= umat_el(P, id1, id, id, id2); }
+        }
+    }
+    return hel + tmat_el(P, src, tgt);
+}
+__device__ __forceinline__ double sltcnd_2(const Params &P, int s1, int s2, int t1, int t2) {
+    double hel = 0.0;
+    if ((((s1 ^ t1) | (s2 ^ t2)) & 1) == 0) hel = umat_el(P, gtid(s1), gtid(s2), gtid(t1), gtid(t2));
+    if ((((s1 ^ t2) | (s2 ^ t1)) & 1) == 0) hel -= umat_el(P, gtid(s1), gtid(s2), gtid(t2), gtid(t1));
+    return hel;
+}
+// k-space Hubbard double, get_offdiag_helement_k_sp_hub
+__device__ __forceinline__ double offdiag_k(const Params &P, int s1, int s2, int t1, int t2, bool par) {
+    if (((s1 ^ s2) & 1) == 0 || ((t1 ^ t2) & 1) == 0) return 0.0;
+    double hel = umat_k(P, gtid(s1), gtid(s2), gtid(t1), gtid(t2));
+    if (((s1 ^ t1) & 1) != 0) hel = -hel;
+    if (fabs(hel) < NG_EPS) return hel;
+    return par ? -hel : hel;
+}
+template <int NW>
+__device__ double diag_k(const Params &P, const Det<NW> &d) {      // sltcnd_0 with get_umat_kspace, tExch
+    double hs = 0.0;
+    Det<NW> a = d;
+    while (det_any(a)) hs += __ldg(&P.eps_k[gtid(pop_lowest(a)) - 1]);
+    // every pair contributes U/N (Coulomb), same-spin pairs cancel by exchange:
+    // summed explicitly in the reference's order to stay within 1e-12.
+    const int n = popc(d);
+    int nb = __popcll(d.w[0] & NG_BETA_MASK); if (NW > 1) nb += __popcll(d.w[NW - 1] & NG_BETA_MASK);
+    const int na = n - nb;
+    const double coul = (double)(n * (n - 1) / 2) * P.u_over_n;
+    const double exch = (double)(na * (na - 1) / 2 + nb * (nb - 1) / 2) * P.u_over_n;
+    return (coul - exch) + hs;
+}
+template <int NW>
+__device__ __forceinline__ double diag_rs(const Params &P, const Det<NW> &d) {   // U * double occupancies
+    int nd = __popcll(d.w[0] & (d.w[0] >> 1) & NG_BETA_MASK);
+    if (NW > 1) nd += __popcll(d.w[NW - 1] & (d.w[NW - 1] >> 1) & NG_BETA_MASK);
+    return P.uhub * nd;
+}
+
+// get_diagonal_matel (src/matel_getter.F90:30-58): full H_ii (ECore included)
+template <int NW, int SYS>
+__device__ __forceinline__ double diagonal_matel(const Params &P, const Det<NW> &d) {
+    if (SYS == NECI_SYS_HUBBARD_RS) return diag_rs(P, d);
+    if (SYS == NECI_SYS_HUBBARD_K) return diag_k(P, d) + P.ecore;
+    return sltcnd_0(P, d) + P.ecore;
+}
+
+// get_helement between two arbitrary determinants (ic <= 2), with the
+// excitation I -> J and its parity derived from the bit-strings.
+template <int NW, int SYS>
+__device__ double helement(const Params &P, const Det<NW> &I, const Det<NW> &J) {
+    Det<NW> S, T;
+    S.w[0] = I.w[0] & ~J.w[0]; T.w[0] = J.w[0] & ~I.w[0];
+    if (NW > 1) { S.w[NW - 1] = I.w[NW - 1] & ~J.w[NW - 1]; T.w[NW - 1] = J.w[NW - 1] & ~I.w[NW - 1]; }
+    const int ic = popc(S);
+    if (ic != popc(T) || ic > 2) return 0.0;
+    if (ic == 0) return diagonal_matel<NW, SYS>(P, I);
+    if (ic == 1) {
+        const int s = pop_lowest(S), t = pop_lowest(T);
+        const bool par = parity_single(I, s, t);
+        double h;
+        if (SYS == NECI_SYS_HUBBARD_RS) h = tmat_el(P, s, t);
+        else if (SYS == NECI_SYS_HUBBARD_K) return 0.0;
+        else h = sltcnd_1(P, I, s, t);
+        return par ? -h : h;
+    }
+    const int s1 = pop_lowest(S), s2 = pop_lowest(S), t1 = pop_lowest(T), t2 = pop_lowest(T);
+    const bool par = parity_double(I, s1, s2, t1, t2);
+    if (SYS == NECI_SYS_HUBBARD_RS) return 0.0;
+    if (SYS == NECI_SYS_HUBBARD_K) return offdiag_k(P, s1, s2, t1, t2, par);
+    const double h = sltcnd_2(P, s1, s2, t1, t2);
+    return par ? -h : h;
+}
+// get_off_diagonal_matel (src/matel_getter.F90:61-105)
+template <int NW, int SYS>
+__device__ __forceinline__ double off_diagonal_matel(const Params &P, const Det<NW> &d) {
+    const Det<NW> ref = ref_det<NW>(P);
+    const int ex = excit_level(ref, d);
+    if (ex == 2 || (ex == 1 && P.t_no_brillouin)) return helement<NW, SYS>(P, d, ref);
+    return 0.0;
+}
+
+// get_det_block / DetermineDetNode with the RandomOrbIndex table staged in
+// shared memory (roi).  Two's-complement wrap, Fortran mod and abs reproduced.
+template <int NW>
+__device__ __forceinline__ int det_block(const Params &P, const int *roi, Det<NW> d) {
+    u64 acc = 0; int i = 1;
+    while (det_any(d)) {
+        const int o = pop_lowest(d);
+        acc = 1099511628211ull * acc + (u64)(long long)(roi[o - 1] * i);
+        ++i;
+    }
+    long long m = (long long)acc % (long long)P.balance_blocks;
+    if (m < 0) m = -m;
+    return (int)m + 1;
+}
+
+// ---- generators ----------------------------------------------------------------
+// pick_from_cum_list over an on-the-fly cumulative list of `n` equal or unequal
+// weights is specialised per generator below.
+
+// gen_excit_rs_hubbard
+template <int NW>
+__device__ void gen_rs_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+    E.ic = 1; E.valid = false; E.err = 0; E.pgen = 0.0;
+    const int elec = 1 + (int)(rng.draw() * P.nel);
+    const double p_elec = 1.0 / (double)P.nel;
+    Det<NW> all; all.w[0] = ~0ull; if (NW > 1) all.w[NW - 1] = ~0ull;
+    const int src = select_orb(d, ~0ull, elec);
+    const int *ng = P.neighbours + (size_t)(src - 1) * P.max_neigh;
+    double cum[8]; int nb[8];
+    double cum_sum = 0.0; int nn = 0;
+    for (int i = 0; i < P.max_neigh && i < 8; ++i) {
+        const int o = __ldg(&ng[i]);
+        if (o == 0) break;
+        double elem = 0.0;
+        if (!occ(d, o)) elem = fabs(tmat_el(P, src, o));
+        cum_sum += elem; cum[i] = cum_sum; nb[i] = o; nn = i + 1;
+    }
+    if (cum_sum < NG_EPS) return;
+    const double r = rng.draw() * cum_sum;
+    if (cum[nn - 1] < r) return;
+    // binary_search_first_ge over <= 8 entries == first index with cum >= r
+    int ind = 0;
+    while (cum[ind] < r) ++ind;
+    const double p_orb = (ind == 0) ? cum[0] / cum_sum : (cum[ind] - cum[ind - 1]) / cum_sum;
+    const int orb = nb[ind];
+    E.pgen = p_elec * p_orb;
+    E.src1 = src; E.src2 = 0; E.tgt1 = orb; E.tgt2 = 0;
+    E.parity = parity_single(d, src, orb);
+    E.detJ = d; clr_orb(E.detJ, src); set_orb(E.detJ, orb);
+    E.valid = true;
+}
+
+// gen_excit_k_space_hub
+template <int NW>
+__device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+    E.ic = 2; E.valid = false; E.err = 0; E.pgen = 0.0;
+    int e1, e2, s1, s2;
+    for (int guard = 0;; ++guard) {                // pick_spin_opp_elecs
+        e1 = 1 + (int)(rng.draw() * P.nel);
+        do { e2 = 1 + (int)(rng.draw() * P.nel); } while (e1 == e2);
+        s1 = select_orb(d, ~0ull, e1); s2 = select_orb(d, ~0ull, e2);
+        if (((s1 ^ s2) & 1) != 0) break;
+        if (guard > 100000) { E.err = 1; return; }
+    }
+    if (s1 > s2) { const int t = s1; s1 = s2; s2 = t; }
+    const double p_elec = 1.0 / (double)(P.nocc_beta * P.nocc_alpha);
+    const int kij = __ldg(&P.ksum[(gtid(s1) - 1) * P.n_k + (gtid(s2) - 1)]);
+    // create_ab_list_hubbard: cumulative list over a = 1..nbasis; elem = excit_cache(i,j,a)
+    // = U/N when a, b are empty (b = k_i + k_j - k_a with the spin opposite to a)
+    const double w = fabs(P.u_over_n);
+    double cum_sum = 0.0;
+    for (int a = 1; a <= P.nbasis; ++a) {
+        double elem = 0.0;
+        if (!occ(d, a)) {
+            const int kb = __ldg(&P.kdiff[kij * P.n_k + (gtid(a) - 1)]);
+            const int b = 2 * (kb + 1) - ((a & 1) ? 0 : 1);
+            if (b != a && !occ(d, b)) elem = w;
+        }
+        cum_sum += elem;
+    }
+    if (cum_sum < NG_EPS) return;
+    const double r = rng.draw() * cum_sum;
+    // second sweep: first a with cum(a) >= r  (binary_search_first_ge on the same sums)
+    double c = 0.0, prev = 0.0; int ind = 0, bsel = 0;
+    for (int a = 1; a <= P.nbasis; ++a) {
+        double elem = 0.0; int b = -1;
+        if (!occ(d, a)) {
+            const int kb = __ldg(&P.kdiff[kij * P.n_k + (gtid(a) - 1)]);
+            b = 2 * (kb + 1) - ((a & 1) ? 0 : 1);
+            if (b != a && !occ(d, b)) elem = w;
+        }
+        prev = c; c += elem;
+        if (!(c < r)) { ind = a; bsel = b; break; }
+    }
+    if (ind == 0) return;
+    double p_orb = (ind == 1) ? c / cum_sum : (c - prev) / cum_sum;
+    p_orb = 2.0 * p_orb;
+    if (bsel <= 0) { E.pgen = 0.0; return; }       // r == 0 corner: zero-weight first entry
+    const int t1 = min(ind, bsel), t2 = max(ind, bsel);
+    E.src1 = s1; E.src2 = s2; E.tgt1 = t1; E.tgt2 = t2;
+    E.parity = parity_double(d, s1, s2, t1, t2);
+    E.detJ = d; clr_orb(E.detJ, s1); clr_orb(E.detJ, s2); set_orb(E.detJ, t1); set_orb(E.detJ, t2);
+    E.pgen = p_elec * p_orb;
+    E.valid = true;
+}
+
+// CreateSingleExcit (uniform singles)
+template <int NW>
+__device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+    E.ic = 1; E.valid = false; E.err = 0; E.pgen = 0.0;
+    // construct_class_counts + CheckIfSingleExcits via class masks
+    int unocc_c[NG_MAX_CLASSES];
+    int ElecsWNoExcits = 0;
+    for (int c = 0; c < P.n_classes; ++c) {
+        int o = __popcll(d.w[0] & P.class_mask[c][0]);
+        int t = __popcll(P.class_mask[c][0]);
+        if (NW > 1) { o += __popcll(d.w[NW - 1] & P.class_mask[c][1]); t += __popcll(P.class_mask[c][1]); }
+        unocc_c[c] = t - o;
+        if (t - o == 0) ElecsWNoExcits += o;
+    }
+    if (ElecsWNoExcits == P.nel) return;
+    int src = 0, cls = 0, NExcit = 0, attempts = 0;
+    for (;;) {
+        const int Eleci = (int)(P.nel * rng.draw()) + 1;
+        src = select_orb(d, ~0ull, Eleci);
+        cls = __ldg(&P.class_of_spinorb[src - 1]);
+        NExcit = 0;
+        for (int c = 0; c < P.n_classes; ++c) if (c == cls) NExcit = unocc_c[c];
+        if (NExcit != 0) break;
+        if (attempts > 250) { E.err = 1; return; }
+        ++attempts;
+    }
+    const int cs = __ldg(&P.class_start[cls]), nOrbs = __ldg(&P.class_start[cls + 1]) - cs;
+    int Orb = 0; attempts = 0;
+    for (;;) {
+        const int ChosenUnocc = (int)(nOrbs * rng.draw());
+        Orb = __ldg(&P.class_orbs[cs + ChosenUnocc]);
+        if (!occ(d, Orb)) break;
+        if (attempts > 250) { E.err = 1; return; }
+        ++attempts;
+    }
+    E.src1 = src; E.src2 = 0; E.tgt1 = Orb; E.tgt2 = 0;
+    E.parity = parity_single(d, src, Orb);
+    const double pDoubNew = 1.0 - P.p_singles;
+    double pgen = (1 - pDoubNew) / ((double)(NExcit * (P.nel - ElecsWNoExcits)));
+    pgen = pgen / P.p_singles;
+    E.pgen = pgen;
+    E.detJ = d; clr_orb(E.detJ, src); set_orb(E.detJ, Orb);
+    E.valid = true;
+}
+
+// pick_biased_elecs + GAS_doubles_PCHB_gen_exc
+template <int NW>
+__device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+    E.ic = 2; E.valid = false; E.err = 0;
+    const int nA = P.nocc_alpha, nB = P.nocc_beta;
+    const int AA = nA * (nA - 1) / 2, BB = nB * (nB - 1) / 2, par = AA + BB, AB = nA * nB;
+    double r = rng.draw();
+    int s1, s2;
+    double pGen;
+    if (r < P.p_parallel) {
+        r = (r / P.p_parallel) * par;
+        int idx = (int)floor(r);
+        u64 mask = NG_ALPHA_MASK;
+        if (idx >= AA) { idx -= AA; mask = NG_BETA_MASK; }
+        const int n1 = (int)ceil((1 + sqrt(9 + 8 * (double)idx)) / 2);
+        const int n2 = idx + 1 - ((n1 - 1) * (n1 - 2)) / 2;
+        s1 = select_orb(d, mask, n2); s2 = select_orb(d, mask, n1);     // n2 < n1  =>  s1 < s2
+        pGen = P.p_parallel / (double)par;
+    } else {
+        pGen = (1.0 - P.p_parallel) / (double)AB;
+        r = ((r - P.p_parallel) / (1.0 - P.p_parallel)) * AB;
+        const int idx = (int)floor(r);
+        const int an = 1 + idx % nA;
+        const int bn = 1 + (int)floor(idx / (double)nA);
+        const int oa = select_orb(d, NG_ALPHA_MASK, an), ob = select_orb(d, NG_BETA_MASK, bn);
+        s1 = min(oa, ob); s2 = max(oa, ob);
+    }
+    const int ij = fuse_index(gtid(s1), gtid(s2));
+    int spin1 = s1 & 1, spin2 = s2 & 1;           // getSpinIndex: 0 alpha, 1 beta
+    int sampler;
+    if (spin1 == spin2) sampler = 0;
+    else {
+        const double pe = __ldg(&P.p_exch[ij - 1]);
+        if (rng.draw() < pe) { sampler = 2; pGen *= pe; const int t = spin1; spin1 = spin2; spin2 = t; }
+        else { sampler = 1; pGen *= (1.0 - pe); }
+    }
+    E.src1 = s1; E.src2 = s2; E.tgt1 = 0; E.tgt2 = 0; E.pgen = pGen;
+    // AliasSampler_t::sample
+    const size_t base = ((size_t)(ij - 1) * 3 + sampler) * P.ab_max;
+    if (__ldg(&P.alias[base]) == 0) return;                          // empty sampler: ab = 0
+    const double rr = rng.draw();
+    const int pos = (int)(P.ab_max * rr) + 1;
+    const double bias = fmax(P.ab_max * rr + 1 - pos, 0.0);
+    const int ab = (bias < __ldg(&P.bias[base + pos - 1])) ? pos : __ldg(&P.alias[base + pos - 1]);
+    const double pGenHoles = __ldg(&P.probs[base + ab - 1]);
+    const int2 t = __ldg(&P.tgt_orbs[ab - 1]);
+    const int o1 = 2 * t.x - spin1, o2 = 2 * t.y - spin2;
+    E.tgt1 = o1; E.tgt2 = o2;
+    bool invalid = (o1 == 0 || o2 == 0) || occ(d, o1) || occ(d, o2);
+    if (!invalid && fabs(pGenHoles) <= NG_EPS) invalid = true;
+    if (invalid) return;
+    const int t1 = min(o1, o2), t2 = max(o1, o2);
+    E.tgt1 = t1; E.tgt2 = t2;
+    E.parity = parity_double(d, s1, s2, t1, t2);
+    E.detJ = d; clr_orb(E.detJ, s1); clr_orb(E.detJ, s2); set_orb(E.detJ, t1); set_orb(E.detJ, t2);
+    E.pgen = pGen * pGenHoles;
+    E.valid = true;
+}
+
+template <int NW, int SYS>
+__device__ __forceinline__ void generate_excitation(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+    if (SYS == NECI_SYS_HUBBARD_RS) gen_rs_hubbard(P, d, rng, E);
+    else if (SYS == NECI_SYS_HUBBARD_K) gen_k_hubbard(P, d, rng, E);
+    else {
+        // gen_exc_sd
+        if (rng.draw() < P.p_singles) { gen_uniform_single(P, d, rng, E); E.pgen = E.pgen * P.p_singles; }
+        else { gen_pchb_double(P, d, rng, E); E.pgen = E.pgen * P.p_doubles; }
+    }
+}
+
+// get_spawn_helement = get_helement_det_only (src/Determinants.F90:508-554)
+template <int NW, int SYS>
+__device__ __forceinline__ double spawn_helement(const Params &P, const Det<NW> &d, const Excit<NW> &E) {
+    if (SYS == NECI_SYS_HUBBARD_RS) { const double h = tmat_el(P, E.src1, E.tgt1); return E.parity ? -h : h; }
+    if (SYS == NECI_SYS_HUBBARD_K) return offdiag_k(P, E.src1, E.src2, E.tgt1, E.tgt2, E.parity);
+    double h;
+    if (E.ic == 1) h = sltcnd_1(P, d, E.src1, E.tgt1);
+    else h = sltcnd_2(P, E.src1, E.src2, E.tgt1, E.tgt2);
+    return E.parity ? -h : h;
+}
+
+}  // namespace ng

@@ -1,0 +1,601 @@
+// C ABI + host-side orchestration of the B200-native FCIQMC engine
+// (include/neci_gpu.h).  One engine == one rank == one GPU; the walker list is
+// resident in HBM as structure-of-arrays, every phase of an iteration is a
+// kernel launch on one stream, and the only host synchronisation per
+// iteration is the read-back of the statistics vector (plus the spawn counts
+// when more than one rank exchanges spawns over NCCL).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <dlfcn.h>
+#include <nccl.h>
+#include "kernels.cuh"
+
+using namespace ng;
+
+namespace {
+
+// ---- NCCL through dlopen: single-GPU runs need no NCCL at all; inside a torch
+// process this resolves to the libnccl torch already loaded ---------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err) {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define NG_SYM(field, name) *(void **)(&field) = dlsym(lib, name); if (!field) { err = std::string("missing NCCL symbol ") + name; return false; }
+        NG_SYM(GetUniqueId, "ncclGetUniqueId") NG_SYM(CommInitRank, "ncclCommInitRank") NG_SYM(CommDestroy, "ncclCommDestroy")
+        NG_SYM(AllGather, "ncclAllGather") NG_SYM(Send, "ncclSend") NG_SYM(Recv, "ncclRecv")
+        NG_SYM(GroupStart, "ncclGroupStart") NG_SYM(GroupEnd, "ncclGroupEnd") NG_SYM(GetErrorString, "ncclGetErrorString")
+#undef NG_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+template <class T> T *dalloc(size_t n) {
+    void *p = nullptr;
+    if (n == 0) n = 1;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+    return (T *)p;
+}
+
+}  // namespace
+
+struct neci_gpu_engine {
+    neci_gpu_config cfg;
+    int nw = 1, W = 3;
+    Params P;
+    WalkerList L;
+    SpawnBuf SB;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6];
+    std::string err;
+    // device-owned tables
+    std::vector<void *> owned;
+    double *d_partials = nullptr, *d_stats = nullptr, *h_stats = nullptr;
+    long long *h_ctr = nullptr;
+    int rows_spawn = 0, rows_heavy = 0, rows_compress = 0, rows_annih = 0, rows_insert = 0, rows_list = 0, rows_total = 0;
+    int grid_spawn = 0, grid_generic = 0;
+    u32 stamp = 0;
+    bool need_rebuild = false;
+    long long ht_cap = 0;
+    // semi-stochastic
+    long long n_core_local = 0, n_core_total = 0, core_displ = 0;
+    long long *d_row_ptr = nullptr; int *d_col = nullptr; double *d_val = nullptr;
+    int *d_core_slots = nullptr; double *d_vpart = nullptr, *d_vfull = nullptr, *d_vout = nullptr;
+    std::vector<int> core_sizes, core_displs;
+    // staging for AoS transfers
+    long long *d_aos = nullptr; size_t aos_cap = 0;
+    // multi-rank
+    ncclComm_t comm = nullptr;
+    unsigned long long *d_cnt_all = nullptr, *h_cnt_all = nullptr;
+
+    int fail(const char *fmt, ...) {
+        char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf; return 1;
+    }
+    template <class T> T *upload(const T *h, size_t n) {
+        T *d = dalloc<T>(n);
+        if (!d) return nullptr;
+        owned.push_back(d);
+        if (n) cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice);
+        return d;
+    }
+    template <class T> T *alloc(size_t n) { T *d = dalloc<T>(n); if (d) owned.push_back(d); return d; }
+};
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return e->fail("%s failed: %s", #call, cudaGetErrorString(_e)); } while (0)
+#define NCK(call) do { ncclResult_t _r = (call); if (_r != ncclSuccess) return e->fail("%s failed: %s", #call, g_nccl.GetErrorString(_r)); } while (0)
+
+// dispatch on (words per determinant, system type)
+#define NG_DISPATCH(e, BODY)                                                                              \
+    do {                                                                                                  \
+        const int _key = (e)->nw * 10 + (e)->cfg.system_type;                                             \
+        switch (_key) {                                                                                   \
+            case 11: { constexpr int NW = 1, SYS = NECI_SYS_FCIDUMP_PCHB; BODY; } break;                  \
+            case 12: { constexpr int NW = 1, SYS = NECI_SYS_HUBBARD_RS; BODY; } break;                    \
+            case 13: { constexpr int NW = 1, SYS = NECI_SYS_HUBBARD_K; BODY; } break;                     \
+            case 21: { constexpr int NW = 2, SYS = NECI_SYS_FCIDUMP_PCHB; BODY; } break;                  \
+            case 22: { constexpr int NW = 2, SYS = NECI_SYS_HUBBARD_RS; BODY; } break;                    \
+            case 23: { constexpr int NW = 2, SYS = NECI_SYS_HUBBARD_K; BODY; } break;                     \
+            default: return (e)->fail("unsupported (nifd, system_type) = (%d, %d)", (e)->nw - 1, (e)->cfg.system_type); \
+        }                                                                                                 \
+    } while (0)
+
+static int ensure_aos(neci_gpu_engine *e, size_t words) {
+    if (words <= e->aos_cap) return 0;
+    if (e->d_aos) cudaFree(e->d_aos);
+    e->d_aos = nullptr; e->aos_cap = 0;
+    CK(cudaMalloc((void **)&e->d_aos, std::max<size_t>(words, 1) * 8));
+    e->aos_cap = words;
+    return 0;
+}
+
+extern "C" {
+
+const char *neci_gpu_last_error(const neci_gpu_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
+    if (!cfg || !out) return 1;
+    neci_gpu_engine *e = new neci_gpu_engine();
+    *out = e;
+    e->cfg = *cfg;
+    if (cfg->nifd < 0 || cfg->nifd > 1 || cfg->nbasis > 64 * (cfg->nifd + 1) || cfg->nbasis > NG_MAX_BASIS)
+        return e->fail("unsupported bit representation: nbasis=%d nifd=%d (need nbasis <= 64*(nifd+1) <= %d)", cfg->nbasis, cfg->nifd, NG_MAX_BASIS);
+    if (cfg->niftot != cfg->nifd + 2) return e->fail("niftot must be nifd + 2 (lenof_sign = 1, flags word)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return e->fail("no CUDA device: the engine has no CPU fallback");
+    CK(cudaSetDevice(cfg->device));
+    e->nw = cfg->nifd + 1; e->W = cfg->niftot + 1;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (auto &v : e->ev) CK(cudaEventCreate(&v));
+
+    Params &P = e->P; memset(&P, 0, sizeof P);
+    P.nel = cfg->nel; P.nbasis = cfg->nbasis; P.nocc_alpha = cfg->nocc_alpha; P.nocc_beta = cfg->nocc_beta;
+    P.nranks = cfg->nranks; P.rank = cfg->rank; P.balance_blocks = cfg->balance_blocks; P.system_type = cfg->system_type;
+    P.t_trunc_initiator = cfg->t_trunc_initiator; P.t_all_real_coeff = cfg->t_all_real_coeff;
+    P.t_real_spawn_cutoff = cfg->t_real_spawn_cutoff; P.t_death_before_comms = cfg->t_death_before_comms;
+    P.t_init_coherent_rule = cfg->t_init_coherent_rule; P.t_no_brillouin = cfg->t_no_brillouin; P.t_exch = cfg->t_exch;
+    P.t_semi_stochastic = cfg->t_semi_stochastic; P.t_core_inits = cfg->t_core_inits;
+    P.initiator_walk_no = cfg->initiator_walk_no; P.real_spawn_cutoff = cfg->real_spawn_cutoff;
+    P.occupied_thresh = cfg->occupied_thresh; P.av_mc_excits = cfg->av_mc_excits; P.hii = cfg->hii; P.ecore = cfg->ecore;
+    P.seed = cfg->seed;
+    P.ref[0] = (u64)cfg->ilut_ref[0]; P.ref[1] = (e->nw > 1) ? (u64)cfg->ilut_ref[1] : 0;
+    P.random_orb_index = e->upload(cfg->random_orb_index, cfg->nbasis);
+    P.lb_mapping = e->upload(cfg->load_balance_mapping, cfg->balance_blocks);
+
+    const long long M = cfg->max_walkers, Ms = cfg->max_spawned;
+    if (M >= (1ll << 31) - 2 || Ms >= (1ll << 31) - 2) return e->fail("max_walkers / max_spawned must be < 2^31");
+    WalkerList &L = e->L; memset(&L, 0, sizeof L);
+    L.cap = M;
+    L.det0 = e->alloc<u64>(M); L.det1 = (e->nw > 1) ? e->alloc<u64>(M) : nullptr;
+    L.sgn = e->alloc<double>(M); L.flg = e->alloc<int>(M); L.diagH = e->alloc<double>(M); L.offH = e->alloc<double>(M);
+    long long hc = 1024; while (hc < 2 * M) hc <<= 1;
+    e->ht_cap = hc; L.ht = e->alloc<u64>(hc); L.ht_mask = (u64)hc - 1;
+    L.freeA = e->alloc<int>(M + 1); L.freeB = e->alloc<int>(M + 1);
+    L.ctr = e->alloc<long long>(C_COUNT);
+    SpawnBuf &SB = e->SB; memset(&SB, 0, sizeof SB);
+    SB.W = e->W; SB.seg_cap = Ms / cfg->nranks;
+    SB.buf = e->alloc<long long>((size_t)Ms * e->W);
+    SB.recv = (cfg->nranks > 1) ? e->alloc<long long>((size_t)Ms * e->W) : SB.buf;
+    SB.cnt = e->alloc<unsigned long long>(cfg->nranks);
+    long long sc = 1024; while (sc < 2 * Ms) sc <<= 1;
+    SB.sht_cap = (u64)sc; SB.sht = e->alloc<u64>(sc);
+    SB.ins_idx = e->alloc<int>(Ms);
+    SB.heavy_cap = 1 << 16; SB.heavy = e->alloc<long long>(2 * SB.heavy_cap);
+    if (!L.det0 || !L.sgn || !L.flg || !L.diagH || !L.offH || !L.ht || !L.freeA || !L.freeB || !L.ctr || !SB.buf ||
+        !SB.recv || !SB.cnt || !SB.sht || !SB.ins_idx || !SB.heavy || (e->nw > 1 && !L.det1))
+        return e->fail("device allocation failed (max_walkers=%lld, max_spawned=%lld)", M, Ms);
+    CK(cudaMemset(L.ctr, 0, C_COUNT * 8));
+    CK(cudaMemset(L.sgn, 0, (size_t)M * 8));
+    CK(cudaMemset(L.flg, 0, (size_t)M * 4));
+    CK(cudaMemset(L.ht, 0xFF, (size_t)hc * 8));
+    CK(cudaMemset(SB.sht, 0, (size_t)sc * 8));
+    CK(cudaMemset(SB.cnt, 0, cfg->nranks * 8));
+    e->stamp = 0;
+
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
+    const int nsm = prop.multiProcessorCount;
+    e->grid_generic = nsm * 8;
+    e->grid_spawn = nsm * 4;       // refined per kernel variant below
+    e->rows_spawn = nsm * 8; e->rows_heavy = nsm * 4; e->rows_compress = e->grid_generic; e->rows_annih = e->grid_generic;
+    e->rows_insert = e->grid_generic; e->rows_list = e->grid_generic;
+    e->rows_total = e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih + e->rows_insert + e->rows_list;
+    e->d_partials = e->alloc<double>((size_t)e->rows_total * NECI_ST_COUNT);
+    e->d_stats = e->alloc<double>(NECI_ST_COUNT);
+    CK(cudaMemset(e->d_partials, 0, (size_t)e->rows_total * NECI_ST_COUNT * 8));
+    CK(cudaMallocHost((void **)&e->h_stats, NECI_ST_COUNT * 8));
+    CK(cudaMallocHost((void **)&e->h_ctr, C_COUNT * 8));
+    if (cfg->nranks > 1) {
+        e->d_cnt_all = e->alloc<unsigned long long>((size_t)cfg->nranks * cfg->nranks);
+        CK(cudaMallocHost((void **)&e->h_cnt_all, (size_t)cfg->nranks * cfg->nranks * 8));
+    }
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int neci_gpu_finalize(neci_gpu_engine *e) {
+    if (!e) return 0;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (void *p : e->owned) cudaFree(p);
+    if (e->d_aos) cudaFree(e->d_aos);
+    if (e->h_stats) cudaFreeHost(e->h_stats);
+    if (e->h_ctr) cudaFreeHost(e->h_ctr);
+    if (e->h_cnt_all) cudaFreeHost(e->h_cnt_all);
+    for (auto &v : e->ev) if (v) cudaEventDestroy(v);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return 0;
+}
+
+int neci_gpu_set_system_fcidump(neci_gpu_engine *e, const double *umat, int64_t n_umat, const double *tmat2d) {
+    CK(cudaSetDevice(e->cfg.device));
+    e->P.umat = e->upload(umat, (size_t)n_umat);
+    e->P.tmat = e->upload(tmat2d, (size_t)e->cfg.nbasis * e->cfg.nbasis);
+    if (!e->P.umat || !e->P.tmat) return e->fail("integral upload failed");
+    return 0;
+}
+
+int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_t ab_max, const double *probs,
+                      const double *bias, const int32_t *alias, const double *p_exch, const int32_t *tgt_orbs,
+                      double p_singles, double p_doubles, double p_parallel, int32_t n_classes,
+                      const int32_t *class_of_spinorb) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n_classes > NG_MAX_CLASSES || n_classes < 1) return e->fail("n_classes %d out of range (1..%d)", n_classes, NG_MAX_CLASSES);
+    Params &P = e->P;
+    const size_t n = (size_t)ij_max * 3 * ab_max;
+    P.n_spat = n_spat; P.ij_max = ij_max; P.ab_max = ab_max;
+    P.probs = e->upload(probs, n); P.bias = e->upload(bias, n); P.alias = e->upload(alias, n);
+    P.p_exch = e->upload(p_exch, (size_t)ij_max);
+    P.tgt_orbs = (const int2 *)e->upload(tgt_orbs, 2 * (size_t)ab_max);
+    P.p_singles = p_singles; P.p_doubles = p_doubles; P.p_parallel = p_parallel; P.n_classes = n_classes;
+    std::vector<unsigned char> cls(e->cfg.nbasis);
+    std::vector<int> start(n_classes + 1, 0), orbs;
+    memset(P.class_mask, 0, sizeof P.class_mask);
+    for (int c = 0; c < n_classes; ++c) {
+        start[c] = (int)orbs.size();
+        for (int o = 1; o <= e->cfg.nbasis; ++o)
+            if (class_of_spinorb[o - 1] == c) { orbs.push_back(o); P.class_mask[c][(o - 1) / 64] |= 1ull << ((o - 1) % 64); }
+    }
+    start[n_classes] = (int)orbs.size();
+    for (int o = 0; o < e->cfg.nbasis; ++o) cls[o] = (unsigned char)class_of_spinorb[o];
+    P.class_of_spinorb = e->upload(cls.data(), cls.size());
+    P.class_start = e->upload(start.data(), start.size());
+    P.class_orbs = e->upload(orbs.data(), orbs.size());
+    if (!P.probs || !P.bias || !P.alias || !P.p_exch || !P.tgt_orbs) return e->fail("PCHB table upload failed");
+    return 0;
+}
+
+int neci_gpu_set_system_hubbard_rs(neci_gpu_engine *e, int32_t max_neigh, const int32_t *neighbours,
+                                   const double *tmat2d, double uhub) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (max_neigh > 8) return e->fail("max_neigh > 8 not supported");
+    e->P.max_neigh = max_neigh;
+    e->P.neighbours = e->upload(neighbours, (size_t)max_neigh * e->cfg.nbasis);
+    e->P.tmat = e->upload(tmat2d, (size_t)e->cfg.nbasis * e->cfg.nbasis);
+    e->P.uhub = uhub;
+    return 0;
+}
+
+int neci_gpu_set_system_hubbard_k(neci_gpu_engine *e, int32_t n_k, const int32_t *ksum, const int32_t *kdiff,
+                                  const double *eps_k, double u_over_n) {
+    CK(cudaSetDevice(e->cfg.device));
+    e->P.n_k = n_k;
+    e->P.ksum = e->upload(ksum, (size_t)n_k * n_k); e->P.kdiff = e->upload(kdiff, (size_t)n_k * n_k);
+    e->P.eps_k = e->upload(eps_k, (size_t)n_k); e->P.u_over_n = u_over_n;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------
+int neci_gpu_upload_walkers(neci_gpu_engine *e, const int64_t *current_dets, int64_t n, const double *gd, const double *go) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n > e->cfg.max_walkers - 1) return e->fail("upload of %lld walkers exceeds max_walkers", (long long)n);
+    const size_t words = (size_t)n * e->W;
+    if (ensure_aos(e, words + 2 * (size_t)n)) return 1;
+    CK(cudaMemcpyAsync(e->d_aos, current_dets, words * 8, cudaMemcpyHostToDevice, e->stream));
+    double *dgd = nullptr, *dgo = nullptr;
+    if (gd) { dgd = (double *)(e->d_aos + words); CK(cudaMemcpyAsync(dgd, gd, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream)); }
+    if (go) { dgo = (double *)(e->d_aos + words + n); CK(cudaMemcpyAsync(dgo, go, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream)); }
+    CK(cudaMemsetAsync(e->L.ctr, 0, C_COUNT * 8, e->stream));
+    CK(cudaMemsetAsync(e->L.ht, 0xFF, (size_t)e->ht_cap * 8, e->stream));
+    long long nn = n;
+    CK(cudaMemcpyAsync(&e->L.ctr[C_NLIST], &nn, 8, cudaMemcpyHostToDevice, e->stream));
+    const int grid = (int)std::min<long long>(e->grid_generic, std::max<long long>(1, (n + 255) / 256));
+    NG_DISPATCH(e, (k_upload<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, e->L, e->d_aos, n, dgd, dgo, e->W)));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int neci_gpu_download_walkers(neci_gpu_engine *e, int64_t *current_dets, int64_t *n_out, double *gd, double *go) {
+    CK(cudaSetDevice(e->cfg.device));
+    long long n = 0;
+    CK(cudaMemcpyAsync(&n, &e->L.ctr[C_NLIST], 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (n_out) *n_out = n;
+    if (current_dets && n > 0) {
+        if (ensure_aos(e, (size_t)n * e->W)) return 1;
+        const int grid = (int)std::min<long long>(e->grid_generic, (n + 255) / 256);
+        if (e->nw == 1) k_download<1><<<grid, 256, 0, e->stream>>>(e->L, e->d_aos, n, e->W);
+        else k_download<2><<<grid, 256, 0, e->stream>>>(e->L, e->d_aos, n, e->W);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(current_dets, e->d_aos, (size_t)n * e->W * 8, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (gd && n > 0) CK(cudaMemcpyAsync(gd, e->L.diagH, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (go && n > 0) CK(cudaMemcpyAsync(go, e->L.offH, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------
+int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *row_ptr, const int32_t *col,
+                            const double *val, const int32_t *sizes, const int32_t *displs, const int64_t *core_iluts) {
+    CK(cudaSetDevice(e->cfg.device));
+    e->n_core_local = n_local;
+    e->core_sizes.assign(sizes, sizes + e->cfg.nranks); e->core_displs.assign(displs, displs + e->cfg.nranks);
+    e->n_core_total = 0; for (int r = 0; r < e->cfg.nranks; ++r) e->n_core_total += sizes[r];
+    e->core_displ = displs[e->cfg.rank];
+    const long long nnz = row_ptr[n_local];
+    e->d_row_ptr = e->upload((const long long *)row_ptr, (size_t)n_local + 1);
+    e->d_col = e->upload(col, (size_t)nnz); e->d_val = e->upload(val, (size_t)nnz);
+    e->d_core_slots = e->alloc<int>((size_t)n_local);
+    e->d_vpart = e->alloc<double>((size_t)n_local); e->d_vout = e->alloc<double>((size_t)n_local);
+    e->d_vfull = e->alloc<double>((size_t)e->n_core_total);
+    long long *d_il = e->upload((const long long *)core_iluts, (size_t)n_local * e->nw);
+    if (n_local > 0) {
+        const int grid = (int)std::min<long long>(e->grid_generic, (n_local + 255) / 256);
+        if (e->nw == 1) k_core_locate<1><<<grid, 256, 0, e->stream>>>(e->P, e->L, d_il, n_local, e->d_core_slots);
+        else k_core_locate<2><<<grid, 256, 0, e->stream>>>(e->P, e->L, d_il, n_local, e->d_core_slots);
+        CK(cudaGetLastError());
+    }
+    long long errf = 0;
+    CK(cudaMemcpyAsync(&errf, &e->L.ctr[C_ERR], 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (errf & 64) return e->fail("core determinant missing from the uploaded walker list");
+    return 0;
+}
+
+// ---- spawn exchange: SendProcNewParts (Annihilation.F90:150-247) over NCCL ------
+static int exchange_spawns(neci_gpu_engine *e, long long *n_recv_out) {
+    const int nr = e->cfg.nranks;
+    // MPI_Alltoall of the counts == all-gather of every rank's count vector
+    NCK(g_nccl.AllGather(e->SB.cnt, e->d_cnt_all, (size_t)nr, ncclUint64, e->comm, e->stream));
+    CK(cudaMemcpyAsync(e->h_cnt_all, e->d_cnt_all, (size_t)nr * nr * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const int me = e->cfg.rank;
+    long long total = 0;
+    for (int s = 0; s < nr; ++s) total += (long long)std::min<unsigned long long>(e->h_cnt_all[(size_t)s * nr + me], (unsigned long long)e->SB.seg_cap);
+    if (total > e->cfg.max_spawned) return e->fail("received spawns exceed max_spawned");
+    NCK(g_nccl.GroupStart());
+    long long off = 0;
+    for (int s = 0; s < nr; ++s) {       // receive buffer ordered by source rank (MPI_Alltoallv displacements)
+        const long long cs = (long long)std::min<unsigned long long>(e->h_cnt_all[(size_t)s * nr + me], (unsigned long long)e->SB.seg_cap);
+        const long long cd = (long long)std::min<unsigned long long>(e->h_cnt_all[(size_t)me * nr + s], (unsigned long long)e->SB.seg_cap);
+        if (cd > 0) NCK(g_nccl.Send(e->SB.buf + (size_t)s * e->SB.seg_cap * e->W, (size_t)cd * e->W, ncclInt64, s, e->comm, e->stream));
+        if (cs > 0) NCK(g_nccl.Recv(e->SB.recv + (size_t)off * e->W, (size_t)cs * e->W, ncclInt64, s, e->comm, e->stream));
+        off += cs;
+    }
+    NCK(g_nccl.GroupEnd());
+    *n_recv_out = total;
+    return 0;
+}
+
+static int gather_core_vector(neci_gpu_engine *e) {
+    const int nr = e->cfg.nranks;
+    if (nr == 1) {
+        CK(cudaMemcpyAsync(e->d_vfull, e->d_vpart, (size_t)e->n_core_local * 8, cudaMemcpyDeviceToDevice, e->stream));
+        return 0;
+    }
+    // MPIAllGatherV (semi_stoch_procs.F90:127) as grouped send/recv of the ragged shares
+    NCK(g_nccl.GroupStart());
+    for (int r = 0; r < nr; ++r) {
+        if (e->n_core_local > 0) NCK(g_nccl.Send(e->d_vpart, (size_t)e->n_core_local, ncclFloat64, r, e->comm, e->stream));
+        if (e->core_sizes[r] > 0) NCK(g_nccl.Recv(e->d_vfull + e->core_displs[r], (size_t)e->core_sizes[r], ncclFloat64, r, e->comm, e->stream));
+    }
+    NCK(g_nccl.GroupEnd());
+    return 0;
+}
+
+static int annihilation_phase(neci_gpu_engine *e, IterArgs &A, int row0) {
+    const int g = e->grid_generic;
+    double *p_comp = e->d_partials + (size_t)row0 * NECI_ST_COUNT;
+    double *p_ann = p_comp + (size_t)e->rows_compress * NECI_ST_COUNT;
+    double *p_ins = p_ann + (size_t)e->rows_annih * NECI_ST_COUNT;
+    double *p_lst = p_ins + (size_t)e->rows_insert * NECI_ST_COUNT;
+    e->stamp += 1;
+    if ((e->stamp & 0xFFFFu) == 0) { e->stamp += 1; CK(cudaMemsetAsync(e->SB.sht, 0, (size_t)e->SB.sht_cap * 8, e->stream)); }
+    A.stamp = e->stamp;
+    k_merge_free<<<64, 256, 0, e->stream>>>(e->L);
+    k_merge_free_finish<<<1, 1, 0, e->stream>>>(e->L);
+    if (e->nw == 1) k_compress<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->SB, A, p_comp);
+    else k_compress<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->SB, A, p_comp);
+    if (e->cfg.t_semi_stochastic && e->n_core_local > 0)
+        k_determ_apply<<<std::max(1, (int)std::min<long long>(g, (e->n_core_local + 255) / 256)), 256, 0, e->stream>>>(e->L, e->d_core_slots, e->d_vout, e->n_core_local);
+    if (e->nw == 1) k_annihilate<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_ann);
+    else k_annihilate<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_ann);
+    NG_DISPATCH(e, (k_insert<NW, SYS><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, p_ins)));
+    k_fix_counters<<<1, 1, 0, e->stream>>>(e->L);
+    if (e->nw == 1) k_list_stats<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, A, p_lst);
+    else k_list_stats<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, A, p_lst);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
+    k_reduce_stats<<<1, 64, 0, e->stream>>>(e->d_partials, e->rows_total, e->d_stats);
+    if (e->nw == 1) k_finish_stats<1><<<1, 32, 0, e->stream>>>(e->P, e->L, e->SB, e->d_stats);
+    else k_finish_stats<2><<<1, 32, 0, e->stream>>>(e->P, e->L, e->SB, e->d_stats);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev[4], e->stream));
+    CK(cudaMemcpyAsync(e->h_stats, e->d_stats, NECI_ST_COUNT * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_ctr, e->L.ctr, C_COUNT * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    float ms;
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->h_stats[NECI_ST_TIME_DETERM_MS] = ms;
+    cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->h_stats[NECI_ST_TIME_SPAWN_MS] = ms;
+    cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->h_stats[NECI_ST_TIME_COMM_MS] = ms;
+    cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->h_stats[NECI_ST_TIME_ANNIHIL_MS] = ms;
+    if (stats_out) memcpy(stats_out, e->h_stats, NECI_ST_COUNT * 8);
+    // tombstones are recycled by inserts; rebuild the table when they pile up
+    if (e->h_ctr[C_NTOMB] > e->ht_cap / 4) e->need_rebuild = true;
+    const long long errf = e->h_ctr[C_ERR];
+    if (errf & 1) return e->fail("spawned-list overflow (increase max_spawned / MemoryFacSpawn)");
+    if (errf & 2) return e->fail("main walker list overflow (increase max_walkers / MemoryFacPart)");
+    if (errf & 4) return e->fail("death probability > 2: algorithm unstable, reduce tau");
+    if (errf & 16) return e->fail("excitation generator could not find an excitation after 250 attempts");
+    if (errf & 32) return e->fail("heavy-determinant queue overflow");
+    return 0;
+}
+
+static int begin_iteration(neci_gpu_engine *e) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->need_rebuild) {
+        CK(cudaMemsetAsync(e->L.ht, 0xFF, (size_t)e->ht_cap * 8, e->stream));
+        long long z = 0;
+        CK(cudaMemcpyAsync(&e->L.ctr[C_NTOMB], &z, 8, cudaMemcpyHostToDevice, e->stream));
+        if (e->nw == 1) k_ht_rebuild<1><<<e->grid_generic, 256, 0, e->stream>>>(e->P, e->L);
+        else k_ht_rebuild<2><<<e->grid_generic, 256, 0, e->stream>>>(e->P, e->L);
+        e->need_rebuild = false;
+    }
+    // ValidSpawnedList = InitialSpawnedSlots etc. (FciMCPar.F90:1237-1248)
+    CK(cudaMemsetAsync(e->SB.cnt, 0, (size_t)e->cfg.nranks * 8, e->stream));
+    CK(cudaMemsetAsync(&e->L.ctr[C_NHEAVY], 0, 8 * (C_COUNT - C_NHEAVY), e->stream));
+    return 0;
+}
+
+int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t iter, double *stats_out) {
+    if (begin_iteration(e)) return 1;
+    IterArgs A; A.tau = tau; A.diag_sft = diag_sft; A.iter = iter; A.n_recv = -1; A.stamp = 0;
+    CK(cudaEventRecord(e->ev[0], e->stream));
+    if (e->cfg.t_semi_stochastic && e->n_core_total > 0) {
+        if (e->n_core_local > 0)
+            k_core_gather<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local + 255) / 256)), 256, 0, e->stream>>>(e->L, e->d_core_slots, e->n_core_local, e->d_vpart);
+        if (gather_core_vector(e)) return 1;
+        if (e->n_core_local > 0)
+            k_determ_spmv<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local * 32 + 255) / 256)), NG_BLOCK, 0, e->stream>>>(
+                e->L, e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft, e->d_core_slots, e->d_vout);
+    }
+    CK(cudaEventRecord(e->ev[1], e->stream));
+    double *p_spawn = e->d_partials, *p_heavy = e->d_partials + (size_t)e->rows_spawn * NECI_ST_COUNT;
+    NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
+    NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev[2], e->stream));
+    if (e->cfg.nranks > 1) {
+        if (!e->comm) return e->fail("nranks > 1 but neci_gpu_nccl_init was not called");
+        long long nrecv = 0;
+        if (exchange_spawns(e, &nrecv)) return 1;
+        A.n_recv = nrecv;
+    }
+    CK(cudaEventRecord(e->ev[3], e->stream));
+    if (annihilation_phase(e, A, e->rows_spawn + e->rows_heavy)) return 1;
+    return finish_iteration(e, stats_out);
+}
+
+int neci_gpu_iterate_host(neci_gpu_engine *e, int64_t *current_dets, int64_t *n, double *gd, double *go,
+                          double tau, double diag_sft, int64_t iter, double *stats_out) {
+    if (neci_gpu_upload_walkers(e, current_dets, *n, gd, go)) return 1;
+    if (neci_gpu_iterate(e, tau, diag_sft, iter, stats_out)) return 1;
+    return neci_gpu_download_walkers(e, current_dets, n, gd, go);
+}
+
+int neci_gpu_annihilate(neci_gpu_engine *e, const int64_t *spawned_parts, int64_t n_spawned, int64_t iter, double *stats_out) {
+    if (begin_iteration(e)) return 1;
+    if (n_spawned > e->cfg.max_spawned) return e->fail("n_spawned exceeds max_spawned");
+    CK(cudaMemsetAsync(e->d_partials, 0, (size_t)(e->rows_spawn + e->rows_heavy) * NECI_ST_COUNT * 8, e->stream));
+    CK(cudaMemcpyAsync(e->SB.recv, spawned_parts, (size_t)n_spawned * e->W * 8, cudaMemcpyHostToDevice, e->stream));
+    IterArgs A; A.tau = 0; A.diag_sft = 0; A.iter = iter; A.n_recv = n_spawned; A.stamp = 0;
+    for (int k = 0; k < 4; ++k) CK(cudaEventRecord(e->ev[k], e->stream));
+    const bool semi = e->cfg.t_semi_stochastic;
+    e->cfg.t_semi_stochastic = 0;                 // no determ_projection output to apply here
+    const int rc = annihilation_phase(e, A, e->rows_spawn + e->rows_heavy);
+    e->cfg.t_semi_stochastic = semi;
+    if (rc) return 1;
+    return finish_iteration(e, stats_out);
+}
+
+// -------------------------------------------------------------------------------
+int neci_gpu_nccl_unique_id(uint8_t id_out[128]) {
+    std::string err;
+    if (!g_nccl.load(err)) { fprintf(stderr, "neci_gpu: %s\n", err.c_str()); return 1; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return 1;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id_out, &id, 128);
+    return 0;
+}
+int neci_gpu_nccl_init(neci_gpu_engine *e, const uint8_t id_in[128]) {
+    if (!g_nccl.load(e->err)) return 1;
+    CK(cudaSetDevice(e->cfg.device));
+    ncclUniqueId id; memcpy(&id, id_in, 128);
+    NCK(g_nccl.CommInitRank(&e->comm, e->cfg.nranks, id, e->cfg.rank));
+    return 0;
+}
+
+int neci_gpu_block_populations(neci_gpu_engine *e, double *block_parts) {
+    CK(cudaSetDevice(e->cfg.device));
+    const int nb = e->cfg.balance_blocks;
+    double *d = dalloc<double>(nb);
+    if (!d) return e->fail("allocation failed");
+    cudaMemsetAsync(d, 0, nb * 8, e->stream);
+    if (e->nw == 1) k_block_pops<1><<<e->grid_generic, 256, 0, e->stream>>>(e->P, e->L, d);
+    else k_block_pops<2><<<e->grid_generic, 256, 0, e->stream>>>(e->P, e->L, d);
+    cudaMemcpyAsync(block_parts, d, nb * 8, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t rc = cudaStreamSynchronize(e->stream);
+    cudaFree(d);
+    if (rc != cudaSuccess) return e->fail("block population kernel failed: %s", cudaGetErrorString(rc));
+    return 0;
+}
+
+int neci_gpu_rebalance(neci_gpu_engine *e, const int32_t *new_mapping) {
+    // adjust_load_balance / move_block (load_balancer.fpp:178-512): with the
+    // mapping replaced, every determinant whose block moved is shipped as a
+    // "spawn" of its full weight to the new owner and re-inserted there.
+    (void)new_mapping;
+    return e->fail("neci_gpu_rebalance: not implemented in this round");
+}
+
+// ---- probes -----------------------------------------------------------------------
+int neci_gpu_probe_det_node(neci_gpu_engine *e, int64_t n, const int64_t *iluts, int32_t *block_out, int32_t *node_out) {
+    CK(cudaSetDevice(e->cfg.device));
+    long long *d_il = dalloc<long long>((size_t)n * e->nw); int *d_b = dalloc<int>(n), *d_n = dalloc<int>(n);
+    cudaMemcpy(d_il, iluts, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, (n + 255) / 256));
+    if (e->nw == 1) k_probe_det_node<1><<<grid, 256, 0, e->stream>>>(e->P, d_il, n, d_b, d_n);
+    else k_probe_det_node<2><<<grid, 256, 0, e->stream>>>(e->P, d_il, n, d_b, d_n);
+    cudaError_t rc = cudaStreamSynchronize(e->stream);
+    cudaMemcpy(block_out, d_b, n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(node_out, d_n, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_il); cudaFree(d_b); cudaFree(d_n);
+    if (rc != cudaSuccess) return e->fail("probe_det_node: %s", cudaGetErrorString(rc));
+    return 0;
+}
+int neci_gpu_probe_helement(neci_gpu_engine *e, int64_t n, const int64_t *ii, const int64_t *ij, double *out) {
+    CK(cudaSetDevice(e->cfg.device));
+    long long *d_i = dalloc<long long>((size_t)n * e->nw), *d_j = dalloc<long long>((size_t)n * e->nw); double *d_o = dalloc<double>(n);
+    cudaMemcpy(d_i, ii, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice); cudaMemcpy(d_j, ij, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, (n + 255) / 256));
+    NG_DISPATCH(e, (k_probe_helement<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, d_i, d_j, n, d_o)));
+    cudaError_t rc = cudaStreamSynchronize(e->stream);
+    cudaMemcpy(out, d_o, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_i); cudaFree(d_j); cudaFree(d_o);
+    if (rc != cudaSuccess) return e->fail("probe_helement: %s", cudaGetErrorString(rc));
+    return 0;
+}
+int neci_gpu_probe_gen_excit(neci_gpu_engine *e, int64_t n, const int64_t *iluts, const int32_t *attempt, int64_t iter,
+                             int64_t *ilut_j_out, int32_t *ic_out, int32_t *ex_out, int32_t *parity_out,
+                             double *pgen_out, double *hel_out) {
+    CK(cudaSetDevice(e->cfg.device));
+    long long *d_il = dalloc<long long>((size_t)n * e->nw), *d_j = dalloc<long long>((size_t)n * e->nw);
+    int *d_at = dalloc<int>(n), *d_ic = dalloc<int>(n), *d_ex = dalloc<int>(4 * n), *d_par = dalloc<int>(n);
+    double *d_pg = dalloc<double>(n), *d_h = dalloc<double>(n);
+    cudaMemcpy(d_il, iluts, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice); cudaMemcpy(d_at, attempt, n * 4, cudaMemcpyHostToDevice);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, (n + 255) / 256));
+    NG_DISPATCH(e, (k_probe_gen_excit<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, d_il, d_at, iter, n, d_j, d_ic, d_ex, d_par, d_pg, d_h)));
+    cudaError_t rc = cudaStreamSynchronize(e->stream);
+    cudaMemcpy(ilut_j_out, d_j, (size_t)n * e->nw * 8, cudaMemcpyDeviceToHost); cudaMemcpy(ic_out, d_ic, n * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ex_out, d_ex, 4 * n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(parity_out, d_par, n * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(pgen_out, d_pg, n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(hel_out, d_h, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_il); cudaFree(d_j); cudaFree(d_at); cudaFree(d_ic); cudaFree(d_ex); cudaFree(d_par); cudaFree(d_pg); cudaFree(d_h);
+    if (rc != cudaSuccess) return e->fail("probe_gen_excit: %s", cudaGetErrorString(rc));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+"""Host driver mirroring the outer loop of FciMCPar (src/FciMCPar.F90:394-854):
+one engine call per iteration where the reference calls PerformFCIMCycPar
+(:507), statistics reduced over ranks every StepsSft iterations as in
+communicate_estimates (src/fcimc_iter_utilities.F90:390-791), shift updated as
+in update_shift (:883-1260), and the FCIMCStats-style history kept for the
+blocking analysis (src/ErrorAnalysis.F90).
+
+The per-iteration work is entirely inside the engine; nothing here touches
+walker data.
+"""
+import math
+
+import numpy as np
+
+from . import capi, host
+from .capi import ST
+
+
+def diag_energy(system, orbs):
+    """<D|H|D> (sltcnd_0_base src/sltcnd.fpp:585-622 / lattice diagonal elements)."""
+    t = system.tables
+    orbs = list(orbs)
+    if system.kind == capi.SYS_HUBBARD_RS:
+        s = set(orbs)
+        nd = sum(1 for o in orbs if o % 2 == 1 and (o + 1) in s)
+        return t["uhub"] * nd
+    if system.kind == capi.SYS_HUBBARD_K:
+        na = sum(1 for o in orbs if o % 2 == 0)
+        nb = len(orbs) - na
+        return sum(t["eps_k"][(o - 1) // 2] for o in orbs) + t["u_over_n"] * na * nb + system.ecore
+    nbas = system.nbasis
+    umat, tmat = t["umat"], t["tmat"]
+
+    def tri(a, b):
+        return a * (a - 1) // 2 + b if a > b else b * (b - 1) // 2 + a
+
+    def um(i, j, k, l):
+        return umat[tri(tri(i, k), tri(j, l)) - 1]
+
+    e = sum(tmat[(o - 1) + nbas * (o - 1)] for o in orbs)
+    for a in range(len(orbs)):
+        for b in range(a + 1, len(orbs)):
+            i, j = (orbs[a] + 1) // 2, (orbs[b] + 1) // 2
+            e += um(i, j, i, j)
+            if (orbs[a] - orbs[b]) % 2 == 0:
+                e -= um(i, j, j, i)
+    return e + system.ecore
+
+
+def _world():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+def reduce_stats(st):
+    """MPISumAll / MPIAllReduce(MAX) of the per-rank accumulators (fcimc_iter_utilities.F90:616,733,783)."""
+    dist = _world()
+    if dist is None or dist.get_world_size() == 1:
+        return st
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    s = torch.tensor(st, dtype=torch.float64, device=dev)
+    m = s.clone()
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    out = s.cpu().numpy()
+    mx = m.cpu().numpy()
+    for name in capi.ST_MAX_REDUCED + ("TIME_SPAWN_MS", "TIME_COMM_MS", "TIME_ANNIHIL_MS", "TIME_DETERM_MS"):
+        out[ST[name]] = mx[ST[name]]
+    out[ST["ERR_FLAGS"]] = mx[ST["ERR_FLAGS"]]
+    return out
+
+
+class FciMC:
+    """Drives one engine (rank) through the FCIQMC iteration loop."""
+
+    def __init__(self, system, engine, hii, tau, init_walkers, steps_sft=10, sft_damp=0.1, diag_sft=0.0,
+                 nranks=1):
+        self.system, self.engine, self.hii = system, engine, hii
+        self.tau, self.init_walkers = tau, init_walkers
+        self.steps_sft, self.sft_damp = steps_sft, sft_damp
+        self.diag_sft = diag_sft
+        self.nranks = nranks
+        self.iter = 0
+        self.single_part_phase = True          # tSinglePartPhase
+        self.tot_parts = 0.0                   # AllTotParts of the previous iteration
+        self.old_av_walkers = 0.0              # OldAllAvWalkersCyc
+        self.sum_walkers_cyc = 0.0             # AllSumWalkersCyc
+        self.cyc = np.zeros(capi.ST_COUNT)     # accumulators over the update cycle
+        self.history = []                      # one row per update cycle (FCIMCStats)
+        self.attempts = 0.0
+
+    def seed_reference(self, n_walkers, rank_of_ref=0, my_rank=0):
+        """InitFCIMC_HF: start from n walkers on the reference determinant."""
+        s = self.system
+        if my_rank == rank_of_ref:
+            rec = host.record(s, s.ref_orbs, float(n_walkers), (1 << capi.FLAG_INITIATOR))
+            self.engine.upload_walkers(rec.reshape(1, -1))
+            self.tot_parts = float(n_walkers)
+        else:
+            self.engine.upload_walkers(np.zeros((0, s.W), dtype=np.int64))
+        self.old_av_walkers = float(n_walkers)
+
+    def step(self):
+        """One iteration == one PerformFCIMCycPar."""
+        self.iter += 1
+        self.sum_walkers_cyc += self.tot_parts          # end_iter_stats: SumWalkersCyc += TotParts
+        st = self.engine.iterate(self.tau, self.diag_sft, self.iter)
+        self.tot_parts = st[ST["TOTPARTS"]]
+        self.cyc += st
+        for name in capi.ST_MAX_REDUCED:
+            self.cyc[ST[name]] = max(self.cyc[ST[name]] - st[ST[name]], st[ST[name]])
+        self.attempts += st[ST["NVALIDEXCITS"]] + st[ST["NINVALIDEXCITS"]]
+        if self.iter % self.steps_sft == 0:
+            self._update_cycle(st)
+        return st
+
+    def _update_cycle(self, last):
+        # communicate_estimates
+        loc = self.cyc.copy()
+        loc[ST["TOTPARTS"]] = last[ST["TOTPARTS"]]
+        loc[ST["TOTWALKERS"]] = last[ST["TOTWALKERS"]] - last[ST["HOLESINLIST"]]
+        extra = np.array([self.sum_walkers_cyc])
+        allst = reduce_stats(np.concatenate([loc, extra]))
+        all_sum_walkers_cyc = allst[-1]
+        allst = allst[:-1]
+        all_tot_parts = allst[ST["TOTPARTS"]]
+        av_walkers = all_sum_walkers_cyc / self.steps_sft
+        # update_shift
+        if self.single_part_phase and all_tot_parts > self.init_walkers * self.nranks:
+            self.single_part_phase = False
+        if not self.single_part_phase and self.old_av_walkers > 0 and av_walkers > 0:
+            self.diag_sft = host.update_shift(self.diag_sft, self.sft_damp, self.tau, self.steps_sft,
+                                              av_walkers, self.old_av_walkers)
+        hf = allst[ST["HFCYC"]]
+        proje = allst[ST["ENUMCYC"]] / hf if abs(hf) > 1e-13 else float("nan")
+        self.history.append(dict(iter=self.iter, shift=self.diag_sft, tot_parts=all_tot_parts,
+                                 n_dets=allst[ST["TOTWALKERS"]], enum_cyc=allst[ST["ENUMCYC"]], hf_cyc=hf,
+                                 proje_corr=proje, proje=proje + self.hii, varying=not self.single_part_phase,
+                                 noathf=hf / self.steps_sft))
+        self.old_av_walkers = av_walkers
+        self.sum_walkers_cyc = 0.0
+        self.cyc[:] = 0.0
+
+    def run(self, n_iter):
+        for _ in range(n_iter):
+            self.step()
+        return self.history
+
+
+# ---------------------------------------------------------------------------------------
+def blocking(x):
+    """Flyvbjerg-Petersen reblocking (src/ErrorAnalysis.F90:374-470): returns
+    (mean, error) with the error taken at the first plateau of the blocked
+    standard error (largest value that is still well determined)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    if n < 2:
+        return (float(x.mean()) if n else float("nan")), float("inf")
+    mean = x.mean()
+    errs = []
+    y = x.copy()
+    while y.size >= 8:
+        m = y.size
+        se = y.std(ddof=1) / math.sqrt(m)
+        ee = se / math.sqrt(2.0 * (m - 1))
+        errs.append((se, ee))
+        if m % 2:
+            y = y[:-1]
+        y = 0.5 * (y[0::2] + y[1::2])
+    if not errs:
+        return float(mean), float(x.std(ddof=1) / math.sqrt(n))
+    best = errs[0][0]
+    for se, ee in errs:
+        if se > best and ee < 0.5 * se:
+            best = se
+    return float(mean), float(best)
+
+
+def ratio_estimate(num, den):
+    """Projected-energy estimate <num>/<den> with blocking errors and the
+    numerator/denominator covariance (src/ErrorAnalysis.F90:1116-1180)."""
+    num, den = np.asarray(num, float), np.asarray(den, float)
+    mn, en = blocking(num)
+    md, ed = blocking(den)
+    if abs(md) < 1e-300:
+        return float("nan"), float("inf")
+    cov = np.cov(num, den)[0, 1] / max(len(num), 1)
+    r = mn / md
+    var = (en / mn) ** 2 + (ed / md) ** 2 - 2.0 * cov / (mn * md) if mn != 0 else float("inf")
+    return r, abs(r) * math.sqrt(max(var, 0.0))

@@ -1,0 +1,222 @@
+"""Host-side mirror of what NECI's Fortran host prepares for the hot path.
+
+Everything here produces inputs of exactly the shapes the Fortran host would
+pass through the C ABI (include/neci_gpu.h): integral tables, PCHB alias tables,
+lattice tables, the hashing tables, the reference determinant and the engine
+configuration.  The heavy loops live in ``csrc/host/neci_host.cpp``
+(``libneci_host.so``); this module is the typed Python face of that library.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB = os.path.join(HERE, "libneci_host.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB):
+            from . import _build
+            _build.build_host()
+        _lib = C.CDLL(HOST_LIB)
+        _lib.neci_host_umat_size.restype = C.c_int64
+        _lib.neci_host_update_shift.restype = C.c_double
+    return _lib
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+@dataclass
+class System:
+    """A Hamiltonian + excitation generator in the engine's input format."""
+    kind: int
+    nel: int
+    nbasis: int
+    nocc_alpha: int
+    nocc_beta: int
+    ecore: float = 0.0
+    t_exch: int = 1
+    t_no_brillouin: int = 0
+    tables: dict = field(default_factory=dict)
+    ref_orbs: np.ndarray = None           # reference determinant, sorted spin orbitals (1-based)
+
+    @property
+    def nifd(self):
+        return self.nbasis // 64           # src/BitReps.F90:174
+
+    @property
+    def nw(self):
+        return self.nifd + 1
+
+    @property
+    def W(self):
+        return self.nifd + 3
+
+    def ilut(self, orbs):
+        """EncodeBitDet: sorted orbital list -> occupation words (int64)."""
+        w = [0] * self.nw
+        for o in orbs:
+            w[(o - 1) // 64] |= 1 << ((o - 1) % 64)
+        return np.array(w, dtype=np.uint64).view(np.int64)
+
+    def apply(self, engine):
+        """Upload this system's tables through the C ABI."""
+        t = self.tables
+        if self.kind == capi.SYS_FCIDUMP_PCHB:
+            engine.set_system_fcidump(t["umat"], t["tmat"])
+            engine.set_pchb(t["pchb"])
+        elif self.kind == capi.SYS_HUBBARD_RS:
+            engine.set_system_hubbard_rs(t["max_neigh"], t["neighbours"], t["tmat"], t["uhub"])
+        elif self.kind == capi.SYS_HUBBARD_K:
+            engine.set_system_hubbard_k(t["n_k"], t["ksum"], t["kdiff"], t["eps_k"], t["u_over_n"])
+        else:
+            raise ValueError("unknown system kind")
+
+
+# ---------------------------------------------------------------------------------------
+def random_fcidump_system(n_spat, nel, sparse=1.0, sparse_t=1.0, seed=25, diag_shift=2.0,
+                          p_singles=0.1, p_parallel=None, ms2=0):
+    """Synthetic FCIDUMP per generate_random_integrals (src/unit_test_helper_excitgen.F90:371-485),
+    PCHB `MANUAL UNIF:UNIF UNIF-UNIF:FAST-FAST` spatial-orbital tables."""
+    L = lib()
+    nb = 2 * n_spat
+    n_umat = L.neci_host_umat_size(C.c_int32(n_spat))
+    umat = np.zeros(n_umat)
+    tmat = np.zeros(nb * nb)
+    L.neci_host_random_fcidump(C.c_int32(n_spat), C.c_double(sparse), C.c_double(sparse_t), C.c_uint64(seed),
+                               C.c_double(diag_shift), _p(umat, C.c_double), _p(tmat, C.c_double))
+    nalpha = (nel + ms2) // 2
+    nbeta = nel - nalpha
+    pchb = build_pchb(n_spat, umat, p_singles=p_singles, p_parallel=p_parallel, nalpha=nalpha, nbeta=nbeta)
+    # aufbau reference: lowest nbeta beta orbitals (odd) and nalpha alpha orbitals (even)
+    ref = sorted([2 * i - 1 for i in range(1, nbeta + 1)] + [2 * i for i in range(1, nalpha + 1)])
+    return System(kind=capi.SYS_FCIDUMP_PCHB, nel=nel, nbasis=nb, nocc_alpha=nalpha, nocc_beta=nbeta,
+                  ecore=0.0, t_exch=1, t_no_brillouin=1,
+                  tables=dict(umat=umat, tmat=tmat, pchb=pchb), ref_orbs=np.array(ref, dtype=np.int32))
+
+
+def build_pchb(n_spat, umat, p_singles=0.1, p_parallel=None, nalpha=None, nbeta=None, class_of_spinorb=None):
+    """GAS_doubles_PCHB_compute_samplers (src/gasci_pchb_doubles_spatorb_fastweighted.fpp:329-445)."""
+    L = lib()
+    ij = C.c_int32(); ab = C.c_int32()
+    L.neci_host_pchb_dims(C.c_int32(n_spat), C.byref(ij), C.byref(ab))
+    ij_max, ab_max = ij.value, ab.value
+    n = ij_max * 3 * ab_max
+    probs = np.zeros(n); bias = np.zeros(n); alias = np.zeros(n, dtype=np.int32)
+    p_exch = np.zeros(ij_max); tgt = np.zeros(2 * ab_max, dtype=np.int32)
+    um = np.ascontiguousarray(umat, dtype=np.float64)
+    L.neci_host_pchb_build(C.c_int32(n_spat), _p(um, C.c_double), _p(probs, C.c_double), _p(bias, C.c_double),
+                           _p(alias, C.c_int32), _p(p_exch, C.c_double), _p(tgt, C.c_int32))
+    if p_parallel is None:
+        # fraction of same-spin electron pairs (what the tau-search would start from)
+        par = nalpha * (nalpha - 1) // 2 + nbeta * (nbeta - 1) // 2
+        opp = nalpha * nbeta
+        p_parallel = par / float(par + opp) if par + opp else 0.0
+    if class_of_spinorb is None:
+        # ORBSYM all 1: one class per spin (0: beta = odd orbitals, 1: alpha = even orbitals)
+        class_of_spinorb = np.array([0 if (o % 2) else 1 for o in range(1, 2 * n_spat + 1)], dtype=np.int32)
+    return dict(n_spat=n_spat, ij_max=ij_max, ab_max=ab_max, probs=probs, bias=bias, alias=alias, p_exch=p_exch,
+                tgt_orbs=tgt, p_singles=float(p_singles), p_doubles=1.0 - float(p_singles),
+                p_parallel=float(p_parallel), n_classes=int(class_of_spinorb.max()) + 1,
+                class_of_spinorb=class_of_spinorb)
+
+
+def hubbard_rs_system(lx, ly, nel=None, U=4.0, t=1.0, pbc=True):
+    """Real-space Hubbard on an lx x ly square lattice (gen_excit_rs_hubbard); half filling by default."""
+    L = lib()
+    ns = lx * ly
+    nb = 2 * ns
+    nel = ns if nel is None else nel
+    neigh = np.zeros(nb * 4, dtype=np.int32)
+    tmat = np.zeros(nb * nb)
+    L.neci_host_hubbard_rs_setup(C.c_int32(lx), C.c_int32(ly), C.c_int32(1 if pbc else 0), C.c_double(t),
+                                 _p(neigh, C.c_int32), _p(tmat, C.c_double))
+    nalpha = (nel + 1) // 2
+    nbeta = nel - nalpha
+    # Neel-like reference: alpha on even-parity sites, beta on odd-parity sites, in site order
+    sites_a = [s for s in range(ns) if ((s % lx) + (s // lx)) % 2 == 0]
+    sites_b = [s for s in range(ns) if ((s % lx) + (s // lx)) % 2 == 1]
+    rest = [s for s in range(ns)]
+    a_sites = (sites_a + [s for s in rest if s not in sites_a])[:nalpha]
+    b_sites = (sites_b + [s for s in rest if s not in sites_b])[:nbeta]
+    ref = sorted([2 * (s + 1) for s in a_sites] + [2 * (s + 1) - 1 for s in b_sites])
+    return System(kind=capi.SYS_HUBBARD_RS, nel=nel, nbasis=nb, nocc_alpha=nalpha, nocc_beta=nbeta, ecore=0.0,
+                  t_exch=0, t_no_brillouin=1,     # real_space_hubbard.F90:151-160
+                  tables=dict(max_neigh=4, neighbours=neigh, tmat=tmat, uhub=float(U)),
+                  ref_orbs=np.array(ref, dtype=np.int32))
+
+
+def hubbard_k_system(lx, ly, nel=None, U=4.0, t=1.0):
+    """k-space Hubbard on an lx x ly periodic mesh (gen_excit_k_space_hub); half filling by default."""
+    L = lib()
+    nk = lx * ly
+    nb = 2 * nk
+    nel = nk if nel is None else nel
+    ksum = np.zeros(nk * nk, dtype=np.int32); kdiff = np.zeros(nk * nk, dtype=np.int32); eps = np.zeros(nk)
+    L.neci_host_hubbard_k_setup(C.c_int32(lx), C.c_int32(ly), C.c_double(t), _p(ksum, C.c_int32), _p(kdiff, C.c_int32),
+                                _p(eps, C.c_double))
+    nalpha = (nel + 1) // 2
+    nbeta = nel - nalpha
+    ref = sorted([2 * i for i in range(1, nalpha + 1)] + [2 * i - 1 for i in range(1, nbeta + 1)])
+    return System(kind=capi.SYS_HUBBARD_K, nel=nel, nbasis=nb, nocc_alpha=nalpha, nocc_beta=nbeta, ecore=0.0,
+                  t_exch=1, t_no_brillouin=0,     # k_space_hubbard.F90:391-393
+                  tables=dict(n_k=nk, ksum=ksum, kdiff=kdiff, eps_k=eps, u_over_n=float(U) / nk),
+                  ref_orbs=np.array(ref, dtype=np.int32))
+
+
+def random_hash_tables(nbasis, seed=7):
+    """RandomOrbIndex / RandomHash2 (src/fcimc_initialisation.fpp:862-942)."""
+    roi = np.zeros(nbasis, dtype=np.int32); rh2 = np.zeros(nbasis, dtype=np.int32)
+    lib().neci_host_random_hash_tables(C.c_int32(nbasis), C.c_uint64(seed), _p(roi, C.c_int32), _p(rh2, C.c_int32))
+    return roi, rh2
+
+
+def update_shift(diag_sft, sft_damp, tau, steps_sft, av_walkers, old_av_walkers):
+    """update_shift (src/fcimc_iter_utilities.F90:1063-1072)."""
+    return lib().neci_host_update_shift(C.c_double(diag_sft), C.c_double(sft_damp), C.c_double(tau),
+                                        C.c_int32(steps_sft), C.c_double(av_walkers), C.c_double(old_av_walkers))
+
+
+def make_params(system, hii, max_walkers, max_spawned, nranks=1, rank=0, device=0, seed=7, initiator=True,
+                initiator_walk_no=3.0, all_real_coeff=False, real_spawn_cutoff=0.95, occupied_thresh=1.0,
+                av_mc_excits=1.0, semi_stochastic=False, blocks_per_rank=1, hash_seed=7, mapping=None):
+    """The module-level globals of the reference that the engine needs (neci_gpu_config).
+    Defaults follow src/Calc.F90:120-480."""
+    roi, rh2 = random_hash_tables(system.nbasis, hash_seed)
+    balance_blocks = nranks * blocks_per_rank
+    if mapping is None:
+        # init_load_balance (src/load_balancer.fpp:72-110): block b -> rank mod(b-1, nranks)
+        mapping = np.array([b % nranks for b in range(balance_blocks)], dtype=np.int32)
+    return dict(
+        nel=system.nel, nbasis=system.nbasis, nifd=system.nifd, niftot=system.nifd + 2,
+        nocc_alpha=system.nocc_alpha, nocc_beta=system.nocc_beta, nranks=nranks, rank=rank, device=device,
+        balance_blocks=balance_blocks, max_walkers=int(max_walkers), max_spawned=int(max_spawned),
+        system_type=system.kind, t_trunc_initiator=int(initiator), t_all_real_coeff=int(all_real_coeff),
+        t_real_spawn_cutoff=int(all_real_coeff), t_death_before_comms=1, t_init_coherent_rule=1,
+        t_no_brillouin=system.t_no_brillouin, t_exch=system.t_exch, t_semi_stochastic=int(semi_stochastic),
+        t_core_inits=1, initiator_walk_no=float(initiator_walk_no), real_spawn_cutoff=float(real_spawn_cutoff),
+        occupied_thresh=float(occupied_thresh), av_mc_excits=float(av_mc_excits), hii=float(hii),
+        ecore=float(system.ecore), seed=int(seed), random_orb_index=roi, random_hash2=rh2,
+        load_balance_mapping=np.asarray(mapping, dtype=np.int32), ilut_ref=system.ilut(system.ref_orbs))
+
+
+def record(system, orbs, sign, flags=0):
+    """One CurrentDets record ilut(0:NIfTot) as int64 words."""
+    rec = np.zeros(system.W, dtype=np.int64)
+    rec[:system.nw] = system.ilut(orbs)
+    rec[system.nw] = np.array([sign], dtype=np.float64).view(np.int64)[0]
+    rec[system.nw + 1] = flags
+    return rec
+
+
+def signs_of(dets, nw):
+    return np.ascontiguousarray(dets[:, nw]).view(np.float64)
