@@ -136,6 +136,12 @@ static void build_alias(const std::vector<double> &w, double *probs, double *bia
     for (int k = 0; k < cU; ++k) { bias[underfull[k] - 1] = 1.0; alias[underfull[k] - 1] = underfull[k]; }
 }
 
+// one alias table (init_AliasTable_t, src/aliasSampling.F90:209-297), exposed for the sampler tests
+int neci_host_alias_build(int32_t n, const double *w, double *probs, double *bias, int32_t *alias) {
+    build_alias(std::vector<double>(w, w + n), probs, bias, alias);
+    return 0;
+}
+
 int neci_host_pchb_dims(int32_t n_spat, int32_t *ij_max, int32_t *ab_max) {
     *ij_max = (int32_t)fuse(n_spat, n_spat); *ab_max = *ij_max; return 0;
 }

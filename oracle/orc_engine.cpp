@@ -656,6 +656,34 @@ int orc_probe_pchb_pgen(orc_engine *e, int64_t n, const int32_t *ex, double *out
     for (int64_t i = 0; i < n; ++i) out[i] = e->S.p_doubles * pchb_double_get_pgen(e->S, &ex[4 * i]);
     return 0;
 }
+// direct known-answer probes of the lattice elements with an explicit excitation matrix
+// (the shapes the reference's unit tests call: get_offdiag_helement_k_sp_hub(nI, ex, tpar),
+//  get_offdiag_helement_rs_hub(nI, ex, tpar), get_diag_helement_k_sp_hub(nI))
+int orc_probe_offdiag_k(orc_engine *e, const int32_t *ex4, int32_t tpar, double *out) {
+    *out = e->S.offdiag_k_hub(ex4, tpar != 0); return 0;
+}
+int orc_probe_offdiag_rs(orc_engine *e, int32_t src, int32_t tgt, int32_t tpar, double *out) {
+    *out = e->S.offdiag_rs_hub(src, tgt, tpar != 0); return 0;
+}
+int orc_probe_diag(orc_engine *e, const int64_t *ilut, double *out) {
+    *out = get_diagonal_matel(e->S, (const uint64_t *)ilut); return 0;
+}
+// UMatInd (src/UMatCache.F90:257-296) and the alias sampler in isolation
+int64_t orc_probe_umat_ind(int32_t i, int32_t j, int32_t k, int32_t l) { return System::UMatInd(i, j, k, l); }
+// draws n samples from one alias table (probs/bias/alias of length len, 1-based alias) with the
+// stream (seed, iter=0, h=stream_id, attempt = draw index): histogram of the 1-based results.
+int orc_probe_alias_hist(const double *bias, const int32_t *alias, int32_t len, uint64_t seed, int64_t ndraw, int64_t *hist) {
+    for (int i = 0; i < len; ++i) hist[i] = 0;
+    for (int64_t d = 0; d < ndraw; ++d) {
+        Stream rng(seed, d >> 32, 0x1234567ull, (uint32_t)d, RNG_ATTEMPT);
+        const double r = rng.draw();
+        const int pos = (int)(len * r) + 1;
+        const double b = std::max(len * r + 1 - pos, 0.0);
+        const int ind = (b < bias[pos - 1]) ? pos : alias[pos - 1];
+        hist[ind - 1] += 1;
+    }
+    return 0;
+}
 // raw Philox block (known-answer test) and the double stream
 int orc_probe_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { Philox::gen(ctr, key, out); return 0; }
 int orc_probe_stream(uint64_t seed, int64_t iter, const int64_t *ilut, int32_t nwords, int32_t attempt, int32_t purpose, int32_t n, double *out) {

@@ -1,0 +1,396 @@
+"""Pins the CPU oracle (oracle/, test infrastructure) before anything is compared with it:
+
+  * known-answer vectors transcribed from the reference's own unit tests
+    (tests/golden/reference_known_answers.json, file:line cited there),
+  * an independent second-quantised construction of H (tests/bruteforce.py),
+  * the reference's statistical generator tests (alias-table L1 test, PCHB sum 1/pgen test),
+  * exact diagonalisation against energies the reference's regression suite publishes.
+
+CPU only."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import bruteforce
+import helpers
+from neci_stable_b200 import capi, host, driver
+
+with open(os.path.join(helpers.GOLDEN, "reference_known_answers.json")) as f:
+    GOLD = json.load(f)
+
+
+# ---- hand-built lattices in the reference's own orbital order ---------------------------------
+def chain_rs_system(length, periodic, bhub, uhub, nel):
+    """lattice('chain', L, ...) + init_tmat: tmat(i,j) = bhub between neighbouring sites, same spin."""
+    nb = 2 * length
+    neigh = np.zeros((nb, 4), dtype=np.int32)
+    tmat = np.zeros((nb, nb))
+    for s in range(length):
+        cand = []
+        for d in (-1, 1):
+            x = s + d
+            if periodic:
+                x %= length
+            elif x < 0 or x >= length:
+                continue
+            if x != s and x not in cand:
+                cand.append(x)
+        for spin in (0, 1):
+            o = 2 * (s + 1) - spin
+            for q, s2 in enumerate(sorted(cand)):
+                o2 = 2 * (s2 + 1) - spin
+                neigh[o - 1, q] = o2
+                tmat[o - 1, o2 - 1] = bhub
+    return host.System(kind=capi.SYS_HUBBARD_RS, nel=nel, nbasis=nb, nocc_alpha=nel // 2, nocc_beta=nel - nel // 2,
+                       t_exch=0, t_no_brillouin=1,
+                       tables=dict(max_neigh=4, neighbours=neigh.ravel(), tmat=tmat.T.ravel().copy(), uhub=float(uhub)),
+                       ref_orbs=np.arange(1, nel + 1, dtype=np.int32))
+
+
+def square_rs_system(lx, ly, bhub, uhub, nel, t_scale=1.0):
+    s = host.hubbard_rs_system(lx, ly, nel=nel, U=uhub, t=-bhub * t_scale)
+    return s
+
+
+def k_chain_system(kvals, bhub, u_over_n, nel, length):
+    """k-space chain in the reference's orbital order: spatial orbital i has momentum kvals[i-1]."""
+    nk = len(kvals)
+    idx = {k % length: i for i, k in enumerate(kvals)}
+    ksum = np.zeros((nk, nk), dtype=np.int32); kdiff = np.zeros((nk, nk), dtype=np.int32)
+    for a, ka in enumerate(kvals):
+        for b, kb in enumerate(kvals):
+            ksum[a, b] = idx[(ka + kb) % length]
+            kdiff[a, b] = idx[(ka - kb) % length]
+    eps = np.array([2.0 * bhub * np.cos(2 * np.pi * k / length) for k in kvals])
+    return host.System(kind=capi.SYS_HUBBARD_K, nel=nel, nbasis=2 * nk, nocc_alpha=nel // 2, nocc_beta=nel - nel // 2,
+                       t_exch=1, t_no_brillouin=0,
+                       tables=dict(n_k=nk, ksum=ksum.ravel(), kdiff=kdiff.ravel(), eps_k=eps, u_over_n=float(u_over_n)),
+                       ref_orbs=np.arange(1, nel + 1, dtype=np.int32))
+
+
+def oracle_for(system, **kw):
+    hii = 0.0
+    kw.setdefault("max_walkers", 1000)
+    kw.setdefault("max_spawned", 1000)
+    o, params = helpers.make_pair(system, hii, **kw)
+    return o
+
+
+def dbl(lib, name, *args):
+    out = C.c_double(0.0)
+    f = getattr(lib, name); f.restype = C.c_int
+    assert f(*args, C.byref(out)) == 0
+    return out.value
+
+
+# ---- Philox -------------------------------------------------------------------------------------
+def test_philox_known_answers():
+    lib = helpers.oracle_lib()
+    for c in GOLD["philox4x32_10"]["cases"]:
+        ctr = np.array([int(x, 16) for x in c["ctr"]], dtype=np.uint32)
+        key = np.array([int(x, 16) for x in c["key"]], dtype=np.uint32)
+        out = np.zeros(4, dtype=np.uint32)
+        lib.orc_probe_philox(ctr.ctypes.data_as(C.c_void_p), key.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        assert ["%08x" % v for v in out] == c["out"]
+
+
+def test_stream_is_uniform_and_in_range():
+    lib = helpers.oracle_lib()
+    il = np.array([0x5555], dtype=np.int64)
+    out = np.zeros(20000)
+    lib.orc_probe_stream(C.c_uint64(7), C.c_int64(3), il.ctypes.data_as(C.c_void_p), C.c_int32(1), C.c_int32(0),
+                         C.c_int32(1), C.c_int32(out.size), out.ctypes.data_as(C.c_void_p))
+    assert out.min() >= 0.0 and out.max() < 1.0
+    assert abs(out.mean() - 0.5) < 0.01 and abs(out.var() - 1 / 12) < 0.005
+
+
+# ---- make_double / parity conventions --------------------------------------------------------------
+def test_make_double_reference_cases():
+    lib = helpers.oracle_lib()
+    for c in GOLD["make_double"]["cases"]:
+        nI = np.array(c["nI"], dtype=np.int32)
+        nJ = np.zeros_like(nI); ex = np.zeros(4, dtype=np.int32); par = C.c_int32(0)
+        lib.orc_probe_make_double(C.c_int32(nI.size), nI.ctypes.data_as(C.c_void_p), C.c_int32(c["elecs"][0]),
+                                  C.c_int32(c["elecs"][1]), C.c_int32(c["tgt"][0]), C.c_int32(c["tgt"][1]),
+                                  nJ.ctypes.data_as(C.c_void_p), ex.ctypes.data_as(C.c_void_p), C.byref(par))
+        assert list(nJ) == c["nJ"], c
+        assert list(ex) == c["ex"], c
+        assert bool(par.value) == c["tpar"], c
+
+
+# ---- real-space Hubbard known answers -----------------------------------------------------------------
+def _lattice(spec, uhub, nel):
+    if spec["type"] == "chain":
+        return chain_rs_system(spec["length"], spec["periodic"], spec["bhub"], uhub, nel)
+    return square_rs_system(spec["lx"], spec["ly"], spec["bhub"], uhub, nel)
+
+
+def test_rs_hubbard_offdiag_reference_cases():
+    g = GOLD["rs_hubbard_offdiag"]
+    o = oracle_for(_lattice(g["lattice"], 0.0, 2))
+    for c in g["cases"]:
+        v = dbl(o.lib, "orc_probe_offdiag_rs", o.h, C.c_int32(c["ex"][0]), C.c_int32(c["ex"][1]), C.c_int32(int(c["tpar"])))
+        assert v == c["hel"], c
+
+
+def test_rs_hubbard_get_helement_reference_cases():
+    for blk in GOLD["rs_hubbard_get_helement"]["blocks"]:
+        by_nel = {}
+        for c in blk["cases"]:
+            by_nel.setdefault(len(c["nI"]), []).append(c)
+        for nel, cases in by_nel.items():
+            s = _lattice(blk["lattice"], blk["uhub"], nel)
+            assert s.nbasis == blk["nbasis"]
+            o = oracle_for(s)
+            I = np.array([s.ilut(c["nI"]) for c in cases]); J = np.array([s.ilut(c["nJ"]) for c in cases])
+            h = o.probe_helement(I, J)
+            assert list(h) == [c["hel"] for c in cases], (blk["lattice"], cases, h)
+
+
+# ---- k-space Hubbard known answers ----------------------------------------------------------------------
+def test_k_hubbard_reference_cases():
+    g = GOLD["k_hubbard"]
+    lat = g["lattice"]
+    for c in g["diag"]:
+        s = k_chain_system(lat["k_of_spatial_orbital"], lat["bhub"], c["u_over_n"], len(c["nI"]), lat["length"])
+        o = oracle_for(s)
+        il = s.ilut(c["nI"])
+        v = dbl(o.lib, "orc_probe_diag", o.h, il.ctypes.data_as(C.c_void_p))
+        assert abs(v - c["hel"]) < 1e-14, (c, v)
+    s = k_chain_system(lat["k_of_spatial_orbital"], lat["bhub"], g["uhub"] / g["omega"], 2, lat["length"])
+    o = oracle_for(s)
+    for c in g["offdiag"]:
+        ex = np.array(c["ex"], dtype=np.int32)
+        if ex[2] == 0:
+            ex[2:] = [2, 4]
+        v = dbl(o.lib, "orc_probe_offdiag_k", o.h, ex.ctypes.data_as(C.c_void_p), C.c_int32(int(c["tpar"])))
+        assert v == c["hel"], (c, v)
+
+
+# ---- integral indexing ---------------------------------------------------------------------------------------
+def test_umat_ind_eightfold_symmetry_and_packing():
+    """UMatInd (src/UMatCache.F90:257-296): <ij|kl> = <kj|il> = <il|kj> = <ji|lk> ..., dense packing 1..N."""
+    lib = helpers.oracle_lib()
+    lib.orc_probe_umat_ind.restype = C.c_int64
+    f = lambda i, j, k, l: lib.orc_probe_umat_ind(C.c_int32(i), C.c_int32(j), C.c_int32(k), C.c_int32(l))
+    n = 5
+    seen = set()
+    for i in range(1, n + 1):
+        for j in range(1, n + 1):
+            for k in range(1, n + 1):
+                for l in range(1, n + 1):
+                    a = f(i, j, k, l)
+                    assert a == f(k, j, i, l) == f(i, l, k, j) == f(k, l, i, j) == f(j, i, l, k) == f(l, k, j, i)
+                    seen.add(a)
+    npair = n * (n + 1) // 2
+    assert seen == set(range(1, npair * (npair + 1) // 2 + 1))
+    # fixed values: <11|11> = 1, <12|12> -> pairs (1,1),(2,2) = tri 1 and 3 -> 3*2/2+1 = 4
+    assert f(1, 1, 1, 1) == 1 and f(1, 2, 1, 2) == 4 and f(1, 2, 2, 1) == 3
+
+
+# ---- Slater-Condon rules vs. independent second quantisation -----------------------------------------------------
+def _h_oracle(o, s, dets):
+    return helpers.hamiltonian_matrix(o, s, dets)
+
+
+def test_sltcnd_against_second_quantisation():
+    s = host.random_fcidump_system(4, 4, sparse=0.9, sparse_t=0.9, seed=5)
+    o = oracle_for(s)
+    dets = helpers.all_dets(s)
+    H = _h_oracle(o, s, dets)
+    t = s.tables
+    nb = s.nbasis
+
+    def tri(a, b):
+        return a * (a - 1) // 2 + b if a > b else b * (b - 1) // 2 + a
+
+    h1 = lambda p, q: t["tmat"][(p - 1) + nb * (q - 1)]
+    eri = lambda i, j, k, l: t["umat"][tri(tri(i, j), tri(k, l)) - 1]     # chemist (ij|kl) = <ik|jl>
+    Hb = bruteforce.hamiltonian([tuple(d) for d in dets], nb, h1, eri)
+    assert np.allclose(H, H.T, atol=1e-13)
+    assert np.allclose(H, Hb, rtol=1e-12, atol=1e-12)
+    assert np.count_nonzero(np.abs(Hb) > 1e-9) > len(dets) * 5
+
+
+def test_sltcnd_two_word_determinants():
+    """nbasis > 64 (nIfD = 1): same rules across the word boundary, checked on the subspace reachable from the
+    reference via one oracle excitation each (second quantisation on a determinant subset)."""
+    s = host.random_fcidump_system(33, 4, sparse=0.8, sparse_t=0.8, seed=4)
+    o = oracle_for(s)
+    rng = np.random.default_rng(0)
+    dets = [list(s.ref_orbs)]
+    # singles and doubles that straddle bit 64
+    for _ in range(40):
+        a = sorted(rng.choice(33, 2, replace=False) + 1); b = sorted(rng.choice(33, 2, replace=False) + 1)
+        dets.append(sorted([2 * int(i) for i in a] + [2 * int(i) - 1 for i in b]))
+    dets = [list(x) for x in sorted(set(tuple(d) for d in dets))]
+    H = _h_oracle(o, s, dets)
+    t = s.tables; nb = s.nbasis
+
+    def tri(a, b):
+        return a * (a - 1) // 2 + b if a > b else b * (b - 1) // 2 + a
+
+    h1 = lambda p, q: t["tmat"][(p - 1) + nb * (q - 1)]
+    eri = lambda i, j, k, l: t["umat"][tri(tri(i, j), tri(k, l)) - 1]
+    Hb = bruteforce.hamiltonian([tuple(d) for d in dets], nb, h1, eri)
+    assert np.allclose(H, Hb, rtol=1e-12, atol=1e-12)
+
+
+def test_hubbard_hamiltonians_against_second_quantisation():
+    # real space 2x3, 4 electrons
+    s = host.hubbard_rs_system(3, 2, nel=4, U=4.0)
+    o = oracle_for(s)
+    dets = helpers.all_dets(s)
+    t = s.tables; nb = s.nbasis
+    h1 = lambda p, q: t["tmat"][(p - 1) + nb * (q - 1)]
+    eri = lambda i, j, k, l: t["uhub"] if (i == j == k == l) else 0.0
+    H = _h_oracle(o, s, dets)
+    Hb = bruteforce.hamiltonian([tuple(d) for d in dets], nb, h1, eri)
+    assert np.allclose(H, Hb, atol=1e-13)
+    # k space 2x2 and a 4-site chain, 4 electrons
+    for s in (host.hubbard_k_system(2, 2, nel=4, U=2.0), host.hubbard_k_system(4, 1, nel=4, U=3.0)):
+        o = oracle_for(s)
+        dets = helpers.all_dets(s)
+        t = s.tables; nb = s.nbasis; nk = t["n_k"]
+        ks = t["ksum"].reshape(nk, nk)
+        h1 = lambda p, q: t["eps_k"][(p - 1) // 2] if p == q else 0.0
+        # (ij|kl) = <ik|jl> = U/N [k_i + k_k == k_j + k_l]
+        eri = lambda i, j, k, l: t["u_over_n"] if ks[i - 1, k - 1] == ks[j - 1, l - 1] else 0.0
+        H = _h_oracle(o, s, dets)
+        Hb = bruteforce.hamiltonian([tuple(d) for d in dets], nb, h1, eri)
+        assert np.allclose(H, Hb, atol=1e-13)
+
+
+# ---- exact diagonalisation vs. energies published in the reference's regression suite ---------------------------------
+def test_exact_diagonalisation_matches_reference_energies():
+    g = GOLD["end_to_end_energies"]
+    # k-space 2x2, U = 1, 4 electrons (test_suite/neci/parallel/Hubbard_2x2): -7.29750728 +- 2.8e-4
+    k = g["hubbard_2x2_kspace"]
+    s = host.hubbard_k_system(k["lx"], k["ly"], nel=k["nel"], U=k["U"], t=k["t"])
+    o = oracle_for(s)
+    H = _h_oracle(o, s, helpers.all_dets(s))
+    e0 = np.linalg.eigvalsh(H)[0]
+    assert abs(e0 - k["reference_fciqmc"]) < 4 * k["err"], e0
+    # real-space periodic 2x2 of the old lattice code (bonds doubled), U = 16, 4 electrons: shift estimate -2.63628 +- 2.6e-3
+    r = g["hubbard_2x2_realspace"]
+    s = host.hubbard_rs_system(r["lx"], r["ly"], nel=r["nel"], U=r["U"], t=r["t_effective"])
+    o = oracle_for(s)
+    H = _h_oracle(o, s, helpers.all_dets(s))
+    e0 = np.linalg.eigvalsh(H)[0]
+    assert abs(e0 - r["reference_fciqmc"]) < 4 * r["err"], e0
+
+
+# ---- alias tables: the reference's L1 test (unit_tests/sampler/test_aliasTables.F90:45-110) ------------------------------
+def test_alias_table_l1_distance():
+    lib = helpers.oracle_lib()
+    rng = np.random.default_rng(11)
+    n = 10                                              # huge_number-free version of the reference's setup
+    w = rng.random(n)
+    w[3] = 0.0                                          # a zero-weight entry must never be drawn
+    w /= w.sum()
+    pchb = host.lib()
+    probs = np.zeros(n); bias = np.zeros(n); alias = np.zeros(n, dtype=np.int32)
+    pchb.neci_host_alias_build(C.c_int32(n), w.ctypes.data_as(C.c_void_p), probs.ctypes.data_as(C.c_void_p),
+                               bias.ctypes.data_as(C.c_void_p), alias.ctypes.data_as(C.c_void_p))
+    assert np.allclose(probs, w, rtol=1e-14)
+    prev = None
+    for ndraw in (1000, 100000, 2000000):
+        hist = np.zeros(n, dtype=np.int64)
+        lib.orc_probe_alias_hist(bias.ctypes.data_as(C.c_void_p), alias.ctypes.data_as(C.c_void_p), C.c_int32(n),
+                                 C.c_uint64(5), C.c_int64(ndraw), hist.ctypes.data_as(C.c_void_p))
+        l1 = np.abs(hist / ndraw - w).sum()
+        assert hist[3] == 0
+        if prev is not None:
+            assert l1 < prev
+        prev = l1
+    assert prev < 1e-2                                  # the reference's threshold after its 8e6 draws
+
+
+# ---- PCHB: sum(1/pgen) test (unit_tests/excitgen/pchb_excitgen_test_helper.F90:40-118) -------------------------------------
+def test_pchb_generator_sum_inverse_pgen():
+    """det_I = [1,2,3,7,8,10], 10 spatial orbitals, random FCIDUMP (sparse 0.7): for every connected determinant
+    with a non-zero matrix element, sum(1/pgen)/n_iter within [0.85, 1.15]; get_pgen == returned pgen."""
+    s = host.random_fcidump_system(10, 6, sparse=0.7, sparse_t=0.7, seed=25, p_singles=0.3)
+    o = oracle_for(s)
+    det = [1, 2, 3, 7, 8, 10]
+    il = s.ilut(det).reshape(1, -1)
+    n_iter = 1_500_000
+    res = o.probe_gen_excit(np.repeat(il, n_iter, axis=0), np.arange(n_iter, dtype=np.int32), 1)
+    valid = res["ilut_j"][:, 0] != 0
+    assert 0.2 < valid.mean() < 1.0
+    keys, inv, cnt = np.unique(res["ilut_j"][valid, 0], return_inverse=True, return_counts=True)
+    contrib = np.bincount(inv, weights=1.0 / res["pgen"][valid]) / n_iter
+    # matrix elements to all generated determinants
+    h = o.probe_helement(np.repeat(il, keys.size, axis=0), keys.reshape(-1, 1))
+    nz = np.abs(h) > 1e-10
+    assert nz.sum() > 50
+    # the reference draws 5e7 excitations; with 1.5e6 the [0.85, 1.15] window applies to determinants hit
+    # often enough (relative std 1/sqrt(hits) <= 4 %), all others must be within 5 standard deviations
+    often = nz & (cnt >= 600)
+    assert often.sum() > 100
+    assert np.all(np.abs(contrib[often] - 1.0) < 0.15), (contrib[often].min(), contrib[often].max())
+    z = (contrib[nz] - 1.0) * np.sqrt(cnt[nz])
+    assert np.abs(z).max() < 5.0 and 0.7 < z.std() < 1.3, (np.abs(z).max(), z.std())
+    # every connected determinant with non-zero element must be generated
+    all_conn = []
+    occ = set(det)
+    for d in helpers.all_dets(s):
+        ex = len(occ - set(d))
+        if ex in (1, 2):
+            all_conn.append(d)
+    ilc = np.array([s.ilut(d) for d in all_conn]).reshape(-1, 1)
+    hc = o.probe_helement(np.repeat(il, len(all_conn), axis=0), ilc)
+    must = set(int(x) for x in ilc[np.abs(hc) > 1e-10, 0])
+    assert must.issubset(set(int(x) for x in keys))
+    # pgen recomputation for doubles
+    dbl_mask = valid & (res["ic"] == 2)
+    pg = o.probe_pchb_pgen(res["ex"][dbl_mask][:20000])
+    assert np.allclose(pg, res["pgen"][dbl_mask][:20000], rtol=1e-12)
+
+
+def test_hubbard_generators_sum_inverse_pgen():
+    """The reference's stochastic generator tests for the lattice models
+    (test_real_space_hubbard.F90:1599, test_k_space_hubbard.F90:3804) with the same harness criterion."""
+    for s in (host.hubbard_rs_system(3, 2, nel=4, U=4.0), host.hubbard_k_system(3, 2, nel=4, U=4.0)):
+        o = oracle_for(s)
+        rng = np.random.default_rng(1)
+        for det in helpers.random_dets(s, 3, rng):
+            il = s.ilut(det).reshape(1, -1)
+            n_iter = 300_000
+            res = o.probe_gen_excit(np.repeat(il, n_iter, axis=0), np.arange(n_iter, dtype=np.int32), 2)
+            valid = res["ilut_j"][:, 0] != 0
+            if not valid.any():
+                continue
+            keys, inv = np.unique(res["ilut_j"][valid, 0], return_inverse=True)
+            contrib = np.bincount(inv, weights=1.0 / res["pgen"][valid]) / n_iter
+            h = o.probe_helement(np.repeat(il, keys.size, axis=0), keys.reshape(-1, 1))
+            assert np.all(np.abs(h) > 1e-12)
+            assert np.all(np.abs(contrib - 1.0) < 0.05), (s.kind, contrib.min(), contrib.max())
+            # completeness
+            occ = set(det)
+            conn = [d for d in helpers.all_dets(s) if len(occ - set(d)) in (1, 2)]
+            ilc = np.array([s.ilut(d) for d in conn]).reshape(-1, 1)
+            hc = o.probe_helement(np.repeat(il, len(conn), axis=0), ilc)
+            must = set(int(x) for x in ilc[np.abs(hc) > 1e-12, 0])
+            assert must == set(int(x) for x in keys)
+
+
+# ---- FCIQMC on the oracle against exact diagonalisation (small lattice) ------------------------------------------------------
+def test_oracle_fciqmc_energy_matches_exact_diagonalisation():
+    s = host.hubbard_k_system(2, 2, nel=4, U=1.0)
+    dets = helpers.all_dets(s)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=20000, max_spawned=20000, seed=3, initiator=False)
+    e0 = np.linalg.eigvalsh(_h_oracle(o, s, dets))[0]
+    run = driver.FciMC(s, o, hii, tau=0.01, init_walkers=3000, steps_sft=10, sft_damp=0.1)
+    run.seed_reference(10)
+    run.run(6000)
+    hist = [h for h in run.history if h["varying"]][100:]
+    num = np.array([h["enum_cyc"] for h in hist]); den = np.array([h["hf_cyc"] for h in hist])
+    e, err = driver.ratio_estimate(num, den)
+    assert abs(e + hii - e0) < max(5 * err, 2e-3), (e + hii, e0, err)
+    sm, serr = driver.blocking([h["shift"] for h in hist])
+    assert abs(sm + hii - e0) < max(5 * serr, 1e-2), (sm + hii, e0, serr)
