@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- spawn attempts/s and iteration time of the FCIQMC hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA engine (one rank per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference arm: CPU restatement of the reference's
+                                                           algorithm (oracle/) on all host cores, bounded sample
+
+A "step" is one FCIQMC iteration (one PerformFCIMCycPar, src/FciMCPar.F90:1177) over the resident walker
+list.  Workload at N = 1: BASELINE.json configs[1] -- N2 cc-pVDZ-sized synthetic FCIDUMP (14 electrons in 28
+spatial orbitals), i-FCIQMC with the PCHB generator, 1e7 walkers on one B200 (frozen synthetic start list per
+SURVEY.md section 8d: distinct uniformly random determinants, |sign| = round(1 + Exp(1))).  For N > 1 the same
+per-GPU population is hashed over the ranks with DetermineDetNode and spawns are exchanged over NCCL (weak scaling).
+
+One JSON line on stdout (rank 0).  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "spawn_attempts_per_sec"
+UNIT = "attempts/s"
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+WORKLOADS = {
+    # name: (n_spat, nel, tau, description)
+    "n2_14e28o_pchb": (28, 14, 2.0e-5, "N2 cc-pVDZ-sized synthetic FCIDUMP 14e/28o, i-FCIQMC, PCHB (BASELINE configs[1])"),
+    "cr2_24e30o_pchb": (30, 24, 1.0e-5, "Cr2-sized synthetic FCIDUMP 24e/30o, i-FCIQMC, PCHB (BASELINE configs[4])"),
+}
+
+
+def build_system(workload):
+    from neci_stable_b200 import host
+    if workload in WORKLOADS:
+        n_spat, nel, tau, _ = WORKLOADS[workload]
+        return host.random_fcidump_system(n_spat, nel, sparse=1.0, sparse_t=1.0, seed=25), tau
+    if workload == "hubk_6x6":
+        return host.hubbard_k_system(6, 6, U=4.0), 5.0e-4
+    if workload == "hubrs_4x4":
+        return host.hubbard_rs_system(4, 4, U=4.0), 5.0e-3
+    raise SystemExit("unknown workload %s" % workload)
+
+
+def random_walker_records(system, n_dets, seed, keep=None, keep_frac=1.0, chunk=1 << 20):
+    """Distinct uniformly random determinants (n_alpha of n_spat, n_beta of n_spat), signs +-round(1 + Exp(1)).
+    keep(iluts) -> bool mask selects the determinants this rank owns."""
+    rng = np.random.default_rng(seed)
+    ns = system.nbasis // 2
+    nw = system.nw
+    out = []
+    have = 0
+    seen = None
+    while have < n_dets:
+        m = int(min(chunk, max(4096, 1.05 * (n_dets - have) / keep_frac + 1024)))
+        words = np.zeros((m, nw), dtype=np.uint64)
+        for nocc, alpha in ((system.nocc_alpha, True), (system.nocc_beta, False)):
+            pick = np.argpartition(rng.random((m, ns)), nocc - 1, axis=1)[:, :nocc]      # nocc distinct spatial orbitals
+            orb = 2 * (pick + 1) - (0 if alpha else 1)                                    # 1-based spin orbital
+            bit = (orb - 1).astype(np.uint64)
+            for w in range(nw):
+                sel = (bit // 64) == w
+                contrib = np.where(sel, np.uint64(1) << (bit % np.uint64(64)), np.uint64(0))
+                words[:, w] |= np.bitwise_or.reduce(contrib, axis=1)
+        if keep is not None:
+            words = words[keep(words.view(np.int64))]
+        out.append(words)
+        have += words.shape[0]
+    words = np.concatenate(out)
+    # distinct
+    if nw == 1:
+        _, idx = np.unique(words[:, 0], return_index=True)
+    else:
+        _, idx = np.unique(words, axis=0, return_index=True)
+    words = words[np.sort(idx)][:n_dets]
+    n = words.shape[0]
+    mag = np.round(1.0 + rng.exponential(1.0, n))
+    sgn = mag * rng.choice(np.array([-1.0, 1.0]), n)
+    rec = np.zeros((n, nw + 2), dtype=np.int64)
+    rec[:, :nw] = words.view(np.int64)
+    rec[:, nw] = sgn.view(np.int64)
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(pw))}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: oracle (restatement of the reference algorithm), ranks played by host threads
+# ---------------------------------------------------------------------------------------------
+def cpu_run(workload, n_dets_total, steps, warmup, cores, seed=5):
+    """Times `steps` iterations of the CPU restatement on `cores` threads (one NECI 'rank' per thread,
+    determinants partitioned by DetermineDetNode, in-memory all-to-all).  Returns attempts/s etc."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as g
+    g.build_cpu_side()
+    import helpers
+    from neci_stable_b200 import capi, host, driver
+    from neci_stable_b200.capi import ST
+    system, tau = build_system(workload)
+    hii = driver.diag_energy(system, system.ref_orbs)
+    nr = max(1, cores)
+    per = int(n_dets_total * 3 // nr + 1000)
+    oracles = []
+    for r in range(nr):
+        params = host.make_params(system, hii, max_walkers=per, max_spawned=max(per, 200000), nranks=nr, rank=r, seed=11)
+        o = helpers.Oracle(params)
+        system.apply(o)
+        oracles.append(o)
+    rec = random_walker_records(system, n_dets_total, seed)
+    _, node = oracles[0].probe_det_node(rec[:, :system.nw])
+    for r in range(nr):
+        oracles[r].upload_walkers(rec[node == r])
+    tot = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
+    sft = 0.0
+    attempts = 0.0
+    t_used = 0.0
+    for it in range(1, warmup + steps + 1):
+        t0 = time.perf_counter()
+        st = helpers.world_iterate(oracles, tau, sft, it, nthreads=nr)
+        dt = time.perf_counter() - t0
+        new = st[:, ST["TOTPARTS"]].sum()
+        if it <= warmup:
+            if new > 0 and tot > 0:
+                sft -= 0.5 * np.log(new / tot) / tau
+        else:
+            attempts += st[:, ST["NVALIDEXCITS"]].sum() + st[:, ST["NINVALIDEXCITS"]].sum()
+            t_used += dt
+        tot = new
+    for o in oracles:
+        o.close()
+    return dict(value=attempts / t_used, ms_per_step=1e3 * t_used / steps, attempts_per_step=attempts / steps,
+                walkers=tot, cores=nr)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="n2_14e28o_pchb")
+    ap.add_argument("--walkers", type=float, default=1.0e7, help="walkers (sum |sign|) per GPU")
+    ap.add_argument("--cpu-sample-walkers", type=float, default=2.0e6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    desc = WORKLOADS.get(args.workload, (0, 0, 0, args.workload))[3]
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n_dets = int(args.cpu_sample_walkers / 2.0)
+        r = cpu_run(args.workload, n_dets, args.steps, args.warmup, cores)
+        sample = "%d iterations of a %.3g-walker (%d determinants) list of the same system and distribution" % (
+            args.steps, r["walkers"], n_dets)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "walkers": r["walkers"],
+                       "note": "CPU restatement of the reference algorithm (the NECI Fortran/MPI build needs gfortran+MPI, "
+                               "absent from this image); bounded sample of the GPU workload"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    import __graft_entry__ as g
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "neci_stable_b200", "libneci_gpu.so")):
+        g.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from neci_stable_b200 import capi, host, driver
+    from neci_stable_b200.capi import ST
+
+    system, tau = build_system(args.workload)
+    hii = driver.diag_energy(system, system.ref_orbs)
+    n_dets = int(args.walkers / 2.0)                       # mean |sign| of round(1 + Exp(1)) is ~2.0
+    max_walkers = int(3 * n_dets + 100000)
+    max_spawned = int(max(2 * args.walkers, 400000))
+    params = host.make_params(system, hii, max_walkers=max_walkers, max_spawned=max_spawned, nranks=world, rank=rank,
+                              device=local_rank, seed=11, blocks_per_rank=1)
+    eng = capi.Engine(params)
+    system.apply(eng)
+    if world > 1:
+        uid = [eng.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.nccl_init(uid[0])
+
+    keep = None
+    if world > 1:
+        def keep(il):
+            _, node = eng.probe_det_node(il)
+            return node == rank
+    rec = random_walker_records(system, n_dets, seed=1000 + rank, keep=keep, keep_frac=1.0 / world)
+    eng.upload_walkers(rec)
+    tot0 = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: also settles the shift so that the population is stationary (update_shift with damping 0.5/step)
+    sft = 0.0
+    tot = allsum(tot0)
+    it = 0
+    for _ in range(args.warmup):
+        it += 1
+        st = eng.iterate(tau, sft, it)
+        new = allsum(st[ST["TOTPARTS"]])
+        if new > 0 and tot > 0:
+            sft -= 0.5 * np.log(new / tot) / tau
+        tot = new
+
+    # ---- timed region: K iterations, list resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    acc = np.zeros(capi.ST_COUNT)
+    t_spawn = t_ann = t_comm = 0.0
+    bytes_spawn = 0.0
+    launches0 = eng.launch_count()
+    barrier()
+    eng.timer_start()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        it += 1
+        st = eng.iterate(tau, sft, it)
+        acc += st
+        t_spawn += st[ST["TIME_SPAWN_MS"]]; t_ann += st[ST["TIME_ANNIHIL_MS"]]; t_comm += st[ST["TIME_COMM_MS"]]
+        # algorithmic bytes of the spawn/death kernel (DESIGN.md "K1"): SoA record (8*nw + 8 sign + 4 flags) and diagH per
+        # slot, offdiagH per occupied slot, sign+flag write-back per occupied slot, one AoS record per spawn
+        n_slot = st[ST["TOTWALKERS"]]; n_occ = n_slot - st[ST["HOLESINLIST"]]
+        bytes_spawn += n_slot * (8 * system.nw + 12 + 8) + n_occ * 8 + n_occ * 12 + st[ST["NSPAWNED_SENT"]] * 8 * system.W
+    ms_dev = eng.timer_stop()
+    barrier()
+    wall = time.perf_counter() - w0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count() - launches0
+    ms = allmax(ms_dev)
+    attempts = allsum(acc[ST["NVALIDEXCITS"]] + acc[ST["NINVALIDEXCITS"]])
+    value = attempts / (ms * 1e-3)
+    walkers_end = allsum(st[ST["TOTPARTS"]])
+    dets_end = allsum(st[ST["TOTWALKERS"]] - st[ST["HOLESINLIST"]])
+    spawned = allsum(acc[ST["NSPAWNED_SENT"]])
+
+    # ---- roofline of the dominant kernel (k_spawn), measured live with CUDA events on the engine's stream
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = bytes_spawn / (t_spawn * 1e-3) / 1e9 if t_spawn > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("k_spawn_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_spawn", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_launch": bytes_spawn / args.steps, "ms_per_launch": t_spawn / args.steps,
+                "phase_ms_per_step": {"spawn_death": t_spawn / args.steps, "exchange": t_comm / args.steps,
+                                      "annihilation": t_ann / args.steps}}
+
+    # ---- end to end through the C ABI with HOST buffers: CurrentDets + gdata in pinned host memory, uploaded, iterated
+    #      and downloaded inside the timed region (neci_gpu_iterate_host)
+    e2e = None
+    if not args.no_e2e:
+        W = system.W
+        dets_h = eng.alloc_host((max_walkers, W), np.int64)
+        gd_h = eng.alloc_host((max_walkers,), np.float64)
+        go_h = eng.alloc_host((max_walkers,), np.float64)
+        d, gd, go = eng.download_walkers()
+        n = d.shape[0]
+        dets_h[:n] = d; gd_h[:n] = gd; go_h[:n] = go
+        h2d = d2h = 0
+        att = 0.0
+        for k in range(2):                                   # warm-up of the host path
+            it += 1
+            st, n = eng.iterate_host(dets_h, n, gd_h, go_h, tau, sft, it)
+        e_steps = max(3, min(args.steps, 10))
+        barrier()
+        w0 = time.perf_counter()
+        for k in range(e_steps):
+            it += 1
+            h2d += n * (8 * W + 16)
+            st, n = eng.iterate_host(dets_h, n, gd_h, go_h, tau, sft, it)
+            d2h += n * (8 * W + 16) + 8 * capi.ST_COUNT
+            att += st[ST["NVALIDEXCITS"]] + st[ST["NINVALIDEXCITS"]]
+        barrier()
+        e_wall = allmax(time.perf_counter() - w0)
+        e2e = {"value": allsum(att) / e_wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d / e_steps),
+               "d2h_bytes_per_step": int(d2h / e_steps), "ms_per_step": 1e3 * e_wall / e_steps, "steps": e_steps,
+               "api": "neci_gpu_iterate_host (CurrentDets + global_determinant_data in pinned host memory, uploaded and "
+                      "downloaded every iteration)",
+               "resident_api": {"value": attempts / wall, "unit": UNIT, "h2d_bytes_per_step": 24,
+                                "d2h_bytes_per_step": 8 * capi.ST_COUNT + 128,
+                                "note": "neci_gpu_iterate: list stays in HBM, host passes tau/shift/iter and reads the "
+                                        "statistics vector every iteration (wall clock, same K steps as `value`)"}}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nd = int(args.cpu_sample_walkers / 2.0)
+        r = cpu_run(args.workload, nd, 6, 3, cores)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": "6 iterations of a %.3g-walker (%d determinants) list of the same system and distribution, "
+                         "ranks = host threads" % (r["walkers"], nd), "ms_per_step": r["ms_per_step"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "walkers_per_gpu": args.walkers,
+                       "walkers_total_end": walkers_end, "determinants_total_end": dets_end, "tau": tau, "shift": sft,
+                       "initiator": True, "attempts_per_step": attempts / args.steps,
+                       "spawned_per_step": spawned / args.steps, "partition": "DetermineDetNode hash" if world > 1 else "single rank",
+                       "l2": "inputs larger than L2 (walker list %.0f MB per GPU > 126 MB)" % (dets_end / world * (8 * system.nw + 28) / 1e6),
+                       "wall_ms_per_step": 1e3 * wall / args.steps},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -229,6 +229,22 @@ int neci_gpu_rebalance(neci_gpu_engine *e, const int32_t *new_mapping);
  * src/load_balancer.fpp:216-235).                                             */
 int neci_gpu_block_populations(neci_gpu_engine *e, double *block_parts);
 
+/* ---- measurement helpers ----------------------------------------------------- */
+/* CUDA events on the engine's own stream (torch.cuda.Event would only see
+ * torch's current stream): start synchronises the stream and records; stop
+ * records, waits and returns the device time between the two in ms.  This is
+ * the device-side counterpart of the reference's set_timer/halt_timer pair
+ * around the iteration (src/FciMCPar.F90:1226, src/lib/timing.F90:122-223).  */
+int neci_gpu_timer_start(neci_gpu_engine *e);
+int neci_gpu_timer_stop(neci_gpu_engine *e, double *ms_out);
+/* Number of kernels this engine has launched since neci_gpu_init.              */
+int64_t neci_gpu_launch_count(const neci_gpu_engine *e);
+/* Page-locked host memory for CurrentDets / global_determinant_data when the
+ * host keeps the list authoritative (neci_gpu_iterate_host): the Fortran host
+ * maps it with c_f_pointer instead of ALLOCATE (fcimc_initialisation.fpp:1650-1763). */
+int neci_gpu_alloc_host(int64_t bytes, void **out);
+int neci_gpu_free_host(void *p);
+
 /* ---- batch probes (parity tests call the same device functions) ----------- */
 /* get_det_block / DetermineDetNode (src/load_balance_calcnodes.F90:25-117):
  * block is 1-based, node 0-based.                                             */

@@ -196,6 +196,31 @@ class Engine:
                                             _p(st, C.c_double)), "annihilate")
         return st
 
+    # -- measurement -----------------------------------------------------------------------
+    def timer_start(self):
+        self._check(self._fn("timer_start")(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double(0.0)
+        self._check(self._fn("timer_stop")(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def launch_count(self):
+        f = getattr(self.lib, self.prefix + "launch_count"); f.restype = C.c_int64
+        return int(f(self.h))
+
+    def alloc_host(self, shape, dtype):
+        """Page-locked numpy array (neci_gpu_alloc_host); freed with free_host."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        f = getattr(self.lib, self.prefix + "alloc_host"); f.restype = C.c_int
+        if f(C.c_int64(n), C.byref(p)) != 0:
+            raise EngineError("alloc_host(%d bytes) failed" % n)
+        buf = (C.c_uint8 * max(n, 8)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._keep.setdefault("_pinned", []).append((p, buf))
+        return arr
+
     # -- multi-rank ---------------------------------------------------------------------
     def nccl_unique_id(self):
         buf = (C.c_uint8 * 128)()

@@ -248,14 +248,16 @@ __device__ __forceinline__ long long ht_lookup(const WalkerList &L, const Det<NW
 __device__ __forceinline__ void ht_insert(const WalkerList &L, u64 h, long long slot, u64 start_pos) {
     const u64 entry = ((u64)(u32)(h >> 32) << 32) | (u64)(u32)slot;
     u64 pos = start_pos;
+    u64 e = __ldcg(&L.ht[pos]);                 // L2 reads: other CTAs insert concurrently
     for (;;) {
-        const u64 e = L.ht[pos];
         if (e == HT_EMPTY || e == HT_TOMB) {
             const u64 old = atomicCAS((unsigned long long *)&L.ht[pos], e, entry);
             if (old == e) { if (e == HT_TOMB) atomicAdd((unsigned long long *)&L.ctr[C_NTOMB], (unsigned long long)-1ll); return; }
-            continue;     // re-read this position
+            e = old;                            // lost the race: judge the winner's value, no re-read
+            continue;
         }
         pos = (pos + 1) & L.ht_mask;
+        e = __ldcg(&L.ht[pos]);
     }
 }
 // RemoveHashDet (src/load_balancer.fpp:631-644): tombstone + push the slot on the free stack

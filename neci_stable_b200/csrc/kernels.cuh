@@ -414,11 +414,12 @@ __global__ void __launch_bounds__(NG_BLOCK) k_compress(Params P, SpawnBuf SB, It
         const u64 h = det_hash64(d);
         const u64 mine = stamp | ((h >> 48) << 32) | (u64)(u32)i;
         u64 pos = h & mask;
+        u64 e = __ldcg(&SB.sht[pos]);                     // L2 reads: slots are claimed concurrently
         for (;;) {
-            const u64 e = SB.sht[pos];
             if ((e >> 48) != (stamp >> 48)) {
                 const u64 old = atomicCAS((unsigned long long *)&SB.sht[pos], e, mine);
                 if (old == e) break;                      // this record represents its determinant
+                e = old;                                  // lost the race: judge the winner's entry
                 continue;
             }
             if (((e >> 32) & 0xFFFFu) == (h >> 48)) {
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(NG_BLOCK) k_compress(Params P, SpawnBuf SB, It
                 }
             }
             pos = (pos + 1) & mask;
+            e = __ldcg(&SB.sht[pos]);
         }
     }
     const int idx[1] = {NECI_ST_ANNIHILATED};

@@ -73,6 +73,8 @@ struct neci_gpu_engine {
     int grid_spawn = 0, grid_generic = 0;
     u32 stamp = 0;
     bool need_rebuild = false;
+    long long n_launch = 0;            // kernels launched by this engine since init
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     long long ht_cap = 0;
     // semi-stochastic
     long long n_core_local = 0, n_core_total = 0, core_displ = 0;
@@ -145,6 +147,7 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     e->nw = cfg->nifd + 1; e->W = cfg->niftot + 1;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto &v : e->ev) CK(cudaEventCreate(&v));
+    CK(cudaEventCreate(&e->ev_t0)); CK(cudaEventCreate(&e->ev_t1));
 
     Params &P = e->P; memset(&P, 0, sizeof P);
     P.nel = cfg->nel; P.nbasis = cfg->nbasis; P.nocc_alpha = cfg->nocc_alpha; P.nocc_beta = cfg->nocc_beta;
@@ -221,6 +224,8 @@ int neci_gpu_finalize(neci_gpu_engine *e) {
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_cnt_all) cudaFreeHost(e->h_cnt_all);
     for (auto &v : e->ev) if (v) cudaEventDestroy(v);
+    if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+    if (e->ev_t1) cudaEventDestroy(e->ev_t1);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return 0;
@@ -299,6 +304,7 @@ int neci_gpu_upload_walkers(neci_gpu_engine *e, const int64_t *current_dets, int
     long long nn = n;
     CK(cudaMemcpyAsync(&e->L.ctr[C_NLIST], &nn, 8, cudaMemcpyHostToDevice, e->stream));
     const int grid = (int)std::min<long long>(e->grid_generic, std::max<long long>(1, (n + 255) / 256));
+    e->n_launch += 1;
     NG_DISPATCH(e, (k_upload<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, e->L, e->d_aos, n, dgd, dgo, e->W)));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
@@ -314,6 +320,7 @@ int neci_gpu_download_walkers(neci_gpu_engine *e, int64_t *current_dets, int64_t
     if (current_dets && n > 0) {
         if (ensure_aos(e, (size_t)n * e->W)) return 1;
         const int grid = (int)std::min<long long>(e->grid_generic, (n + 255) / 256);
+        e->n_launch += 1;
         if (e->nw == 1) k_download<1><<<grid, 256, 0, e->stream>>>(e->L, e->d_aos, n, e->W);
         else k_download<2><<<grid, 256, 0, e->stream>>>(e->L, e->d_aos, n, e->W);
         CK(cudaGetLastError());
@@ -403,6 +410,7 @@ static int annihilation_phase(neci_gpu_engine *e, IterArgs &A, int row0) {
     e->stamp += 1;
     if ((e->stamp & 0xFFFFu) == 0) { e->stamp += 1; CK(cudaMemsetAsync(e->SB.sht, 0, (size_t)e->SB.sht_cap * 8, e->stream)); }
     A.stamp = e->stamp;
+    e->n_launch += 8 + ((e->cfg.t_semi_stochastic && e->n_core_local > 0) ? 1 : 0);
     k_merge_free<<<64, 256, 0, e->stream>>>(e->L);
     k_merge_free_finish<<<1, 1, 0, e->stream>>>(e->L);
     if (e->nw == 1) k_compress<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->SB, A, p_comp);
@@ -420,6 +428,7 @@ static int annihilation_phase(neci_gpu_engine *e, IterArgs &A, int row0) {
 }
 
 static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
+    e->n_launch += 2;
     k_reduce_stats<<<1, 64, 0, e->stream>>>(e->d_partials, e->rows_total, e->d_stats);
     if (e->nw == 1) k_finish_stats<1><<<1, 32, 0, e->stream>>>(e->P, e->L, e->SB, e->d_stats);
     else k_finish_stats<2><<<1, 32, 0, e->stream>>>(e->P, e->L, e->SB, e->d_stats);
@@ -454,6 +463,7 @@ static int begin_iteration(neci_gpu_engine *e) {
         if (e->nw == 1) k_ht_rebuild<1><<<e->grid_generic, 256, 0, e->stream>>>(e->P, e->L);
         else k_ht_rebuild<2><<<e->grid_generic, 256, 0, e->stream>>>(e->P, e->L);
         e->need_rebuild = false;
+        e->n_launch += 1;
     }
     // ValidSpawnedList = InitialSpawnedSlots etc. (FciMCPar.F90:1237-1248)
     CK(cudaMemsetAsync(e->SB.cnt, 0, (size_t)e->cfg.nranks * 8, e->stream));
@@ -466,6 +476,7 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
     IterArgs A; A.tau = tau; A.diag_sft = diag_sft; A.iter = iter; A.n_recv = -1; A.stamp = 0;
     CK(cudaEventRecord(e->ev[0], e->stream));
     if (e->cfg.t_semi_stochastic && e->n_core_total > 0) {
+        e->n_launch += (e->n_core_local > 0) ? 2 : 0;
         if (e->n_core_local > 0)
             k_core_gather<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local + 255) / 256)), 256, 0, e->stream>>>(e->L, e->d_core_slots, e->n_core_local, e->d_vpart);
         if (gather_core_vector(e)) return 1;
@@ -474,6 +485,7 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
                 e->L, e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft, e->d_core_slots, e->d_vout);
     }
     CK(cudaEventRecord(e->ev[1], e->stream));
+    e->n_launch += 2;
     double *p_spawn = e->d_partials, *p_heavy = e->d_partials + (size_t)e->rows_spawn * NECI_ST_COUNT;
     NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
     NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
@@ -552,6 +564,29 @@ int neci_gpu_rebalance(neci_gpu_engine *e, const int32_t *new_mapping) {
     (void)new_mapping;
     return e->fail("neci_gpu_rebalance: not implemented in this round");
 }
+
+// ---- measurement helpers ------------------------------------------------------------
+int neci_gpu_timer_start(neci_gpu_engine *e) {
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventRecord(e->ev_t0, e->stream));
+    return 0;
+}
+int neci_gpu_timer_stop(neci_gpu_engine *e, double *ms_out) {
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaEventRecord(e->ev_t1, e->stream));
+    CK(cudaEventSynchronize(e->ev_t1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1));
+    if (ms_out) *ms_out = (double)ms;
+    return 0;
+}
+int64_t neci_gpu_launch_count(const neci_gpu_engine *e) { return e ? e->n_launch : 0; }
+int neci_gpu_alloc_host(int64_t bytes, void **out) {
+    if (!out || bytes < 0) return 1;
+    return cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 8)) == cudaSuccess ? 0 : 1;
+}
+int neci_gpu_free_host(void *p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? 0 : 1; }
 
 // ---- probes -----------------------------------------------------------------------
 int neci_gpu_probe_det_node(neci_gpu_engine *e, int64_t n, const int64_t *iluts, int32_t *block_out, int32_t *node_out) {

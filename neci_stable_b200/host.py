@@ -65,6 +65,7 @@ class System:
         """EncodeBitDet: sorted orbital list -> occupation words (int64)."""
         w = [0] * self.nw
         for o in orbs:
+            o = int(o)                     # numpy int32 would overflow in the shift
             w[(o - 1) // 64] |= 1 << ((o - 1) % 64)
         return np.array(w, dtype=np.uint64).view(np.int64)
 

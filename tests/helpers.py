@@ -9,7 +9,7 @@ import numpy as np
 from neci_stable_b200 import capi, host, driver
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+ORACLE_LIB = os.environ.get("ORACLE_LIB_OVERRIDE") or os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -114,7 +114,14 @@ def all_dets(system, sector=True):
 
 
 def random_dets(system, n, rng):
+    """n distinct random determinants (all of them, shuffled, if the sector holds fewer than 2n)."""
+    import math
     ns = system.nbasis // 2
+    total = math.comb(ns, system.nocc_alpha) * math.comb(ns, system.nocc_beta)
+    if total <= 2 * n:
+        dets = all_dets(system)
+        order = rng.permutation(len(dets))[:n]
+        return [dets[i] for i in sorted(order)]
     out = set()
     while len(out) < n:
         a = rng.choice(ns, system.nocc_alpha, replace=False) + 1
