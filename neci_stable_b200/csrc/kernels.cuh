@@ -78,17 +78,24 @@ __device__ __forceinline__ void block_flush_stats(const double (&acc)[N], const 
     }
 }
 
-// final, fixed-order reduction over the partial rows of all kernels
-__global__ void k_reduce_stats(const double *partials, int nrows, double *stats) {
-    const int k = threadIdx.x;
-    if (k >= NECI_ST_COUNT) return;
+// final reduction over the partial rows of all kernels: one CTA per statistic, fixed
+// (launch-independent) summation tree, so results are reproducible run to run
+__global__ void __launch_bounds__(256) k_reduce_stats(const double *partials, int nrows, double *stats) {
+    __shared__ double s_v[256];
+    const int k = blockIdx.x;
     const bool is_max = (k >= NECI_ST_FIRST_MAX && k <= NECI_ST_LAST_MAX) || k == NECI_ST_HIGHEST_POP;
     double v = 0.0;
-    for (int r = 0; r < nrows; ++r) {
+    for (int r = threadIdx.x; r < nrows; r += 256) {
         const double x = partials[(size_t)r * NECI_ST_COUNT + k];
         v = is_max ? fmax(v, x) : v + x;
     }
-    stats[k] = v;
+    s_v[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_v[threadIdx.x] = is_max ? fmax(s_v[threadIdx.x], s_v[threadIdx.x + o]) : s_v[threadIdx.x] + s_v[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stats[k] = s_v[0];
 }
 
 // ---- stochastic_round (src/lib/util_mod.fpp:182-204) ---------------------------

@@ -429,7 +429,7 @@ static int annihilation_phase(neci_gpu_engine *e, IterArgs &A, int row0) {
 
 static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
     e->n_launch += 2;
-    k_reduce_stats<<<1, 64, 0, e->stream>>>(e->d_partials, e->rows_total, e->d_stats);
+    k_reduce_stats<<<NECI_ST_COUNT, 256, 0, e->stream>>>(e->d_partials, e->rows_total, e->d_stats);
     if (e->nw == 1) k_finish_stats<1><<<1, 32, 0, e->stream>>>(e->P, e->L, e->SB, e->d_stats);
     else k_finish_stats<2><<<1, 32, 0, e->stream>>>(e->P, e->L, e->SB, e->d_stats);
     CK(cudaGetLastError());
