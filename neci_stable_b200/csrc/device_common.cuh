@@ -55,12 +55,19 @@ template <int NW> __device__ __forceinline__ int excit_level(const Det<NW> &ref,
     if (NW > 1) n += __popcll(ref.w[1] & (ref.w[1] ^ d.w[1]));
     return n;
 }
-// bit index (0-based) of the n-th (1-based) set bit of a 64-bit word; n <= popc(x)
+// bit index (0-based) of the n-th (1-based) set bit of a 64-bit word; n <= popc(x).
+// Branch-free popcount bisection (the __fns intrinsic is a divergent software loop).
 __device__ __forceinline__ int select64(u64 x, int n) {
-    const u32 lo = (u32)x, hi = (u32)(x >> 32);
-    const int cl = __popc(lo);
-    if (n <= cl) return __fns(lo, 0, n);
-    return 32 + __fns(hi, 0, n - cl);
+    u32 w = (u32)x;
+    int pos = 0;
+    int c = __popc(w);
+    if (n > c) { n -= c; w = (u32)(x >> 32); pos = 32; }
+    c = __popc(w & 0xFFFFu); if (n > c) { n -= c; w >>= 16; pos += 16; }
+    c = __popc(w & 0xFFu);   if (n > c) { n -= c; w >>= 8;  pos += 8; }
+    c = __popc(w & 0xFu);    if (n > c) { n -= c; w >>= 4;  pos += 4; }
+    c = __popc(w & 0x3u);    if (n > c) { n -= c; w >>= 2;  pos += 2; }
+    if (n > (int)(w & 1u)) pos += 1;
+    return pos;
 }
 // orbital (1-based) holding the n-th set bit of det & mask
 template <int NW> __device__ __forceinline__ int select_orb(const Det<NW> &d, u64 mask, int n) {
@@ -122,13 +129,14 @@ struct Stream {
     u32 c0, c1, c2, c3, k0, k1;
     u32 x2, x3;        // second half of the current block
     int next;
-    __device__ __forceinline__ Stream(u64 seed, long long iter, u64 h, u32 attempt, u32 purpose) {
+    bool have;         // x2/x3 hold block next>>1
+    __device__ __forceinline__ Stream(u64 seed, long long iter, u64 h, u32 attempt, u32 purpose, int start = 0) {
         c0 = (u32)h; c1 = (u32)(h >> 32); c2 = attempt; c3 = purpose << 24;
-        k0 = (u32)seed ^ (u32)(seed >> 32); k1 = (u32)iter; next = 0; x2 = x3 = 0;
+        k0 = (u32)seed ^ (u32)(seed >> 32); k1 = (u32)iter; next = start; x2 = x3 = 0; have = false;
     }
     __device__ __forceinline__ double draw() {
         u32 a, b;
-        if ((next & 1) == 0) {
+        if ((next & 1) == 0 || !have) {
             u32 v0 = c0, v1 = c1, v2 = c2, v3 = c3 | (u32)(next >> 1);
             u32 q0 = k0, q1 = k1;
 #pragma unroll
@@ -139,7 +147,8 @@ struct Stream {
                 const u32 n0 = hi1 ^ v1 ^ q0, n2 = hi0 ^ v3 ^ q1;
                 v0 = n0; v1 = lo1; v2 = n2; v3 = lo0;
             }
-            a = v0; b = v1; x2 = v2; x3 = v3;
+            if ((next & 1) == 0) { a = v0; b = v1; } else { a = v2; b = v3; }
+            x2 = v2; x3 = v3; have = true;
         } else { a = x2; b = x3; }
         ++next;
         const u64 u = (u64)a | ((u64)b << 32);

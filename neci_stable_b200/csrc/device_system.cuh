@@ -75,21 +75,32 @@ __device__ double sltcnd_0(const Params &P, const Det<NW> &d) {
     }
     return hel_doub + hel_tmp + hel_sing;
 }
+// sltcnd_1_kernel.  The reference walks the occupied orbitals one by one; here the integral loads of four
+// orbitals are issued together (predicated) so that the L2 round trips overlap, Coulomb and exchange terms
+// are accumulated separately (agrees with the sequential order to ~1 ulp).
 template <int NW>
 __device__ double sltcnd_1(const Params &P, const Det<NW> &d, int src, int tgt) {
     const int id1 = gtid(src), id2 = gtid(tgt);
-    double hel = 0.0;
+    double hc = 0.0, hx = 0.0;
     if (((src ^ tgt) & 1) == 0) {
         Det<NW> a = d; clr_orb(a, src);
-        while (det_any(a)) { const int id = gtid(pop_lowest(a)); hel += umat_el(P, id1, id, id2, id); }
-        if (P.t_exch) {
-            Det<NW> b = d; clr_orb(b, src);
-            b.w[0] &= (src & 1) ? NG_BETA_MASK : NG_ALPHA_MASK;
-            if (NW > 1) b.w[NW - 1] &= (src & 1) ? NG_BETA_MASK : NG_ALPHA_MASK;
-            while (det_any(b)) { const int id = gtid(pop_lowest(b)); hel -= umat_el(P, id1, id, id, id2); }
+        const bool exch = P.t_exch != 0;
+        while (det_any(a)) {
+            double c[4], x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool v = det_any(a);
+                int o = src;
+                if (v) o = pop_lowest(a);
+                const int id = gtid(o);
+                c[u] = v ? umat_el(P, id1, id, id2, id) : 0.0;
+                x[u] = (v && exch && ((o ^ src) & 1) == 0) ? umat_el(P, id1, id, id, id2) : 0.0;
+            }
+            hc += (c[0] + c[1]) + (c[2] + c[3]);
+            hx += (x[0] + x[1]) + (x[2] + x[3]);
         }
     }
-    return hel + tmat_el(P, src, tgt);
+    return (hc - hx) + tmat_el(P, src, tgt);
 }
 __device__ __forceinline__ double sltcnd_2(const Params &P, int s1, int s2, int t1, int t2) {
     double hel = 0.0;
@@ -216,8 +227,6 @@ __device__ void gen_rs_hubbard(const Params &P, const Det<NW> &d, Stream &rng, E
     const int orb = nb[ind];
     E.pgen = p_elec * p_orb;
     E.src1 = src; E.src2 = 0; E.tgt1 = orb; E.tgt2 = 0;
-    E.parity = parity_single(d, src, orb);
-    E.detJ = d; clr_orb(E.detJ, src); set_orb(E.detJ, orb);
     E.valid = true;
 }
 
@@ -269,8 +278,6 @@ __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Ex
     if (bsel <= 0) { E.pgen = 0.0; return; }       // r == 0 corner: zero-weight first entry
     const int t1 = min(ind, bsel), t2 = max(ind, bsel);
     E.src1 = s1; E.src2 = s2; E.tgt1 = t1; E.tgt2 = t2;
-    E.parity = parity_double(d, s1, s2, t1, t2);
-    E.detJ = d; clr_orb(E.detJ, s1); clr_orb(E.detJ, s2); set_orb(E.detJ, t1); set_orb(E.detJ, t2);
     E.pgen = p_elec * p_orb;
     E.valid = true;
 }
@@ -279,14 +286,13 @@ __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Ex
 template <int NW>
 __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
     E.ic = 1; E.valid = false; E.err = 0; E.pgen = 0.0;
-    // construct_class_counts + CheckIfSingleExcits via class masks
-    int unocc_c[NG_MAX_CLASSES];
+    // construct_class_counts + CheckIfSingleExcits via class masks (no per-thread arrays: the count of
+    // empty orbitals of a class is recomputed from the masks in the constant bank when needed)
     int ElecsWNoExcits = 0;
     for (int c = 0; c < P.n_classes; ++c) {
         int o = __popcll(d.w[0] & P.class_mask[c][0]);
         int t = __popcll(P.class_mask[c][0]);
         if (NW > 1) { o += __popcll(d.w[NW - 1] & P.class_mask[c][1]); t += __popcll(P.class_mask[c][1]); }
-        unocc_c[c] = t - o;
         if (t - o == 0) ElecsWNoExcits += o;
     }
     if (ElecsWNoExcits == P.nel) return;
@@ -295,8 +301,8 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
         const int Eleci = (int)(P.nel * rng.draw()) + 1;
         src = select_orb(d, ~0ull, Eleci);
         cls = __ldg(&P.class_of_spinorb[src - 1]);
-        NExcit = 0;
-        for (int c = 0; c < P.n_classes; ++c) if (c == cls) NExcit = unocc_c[c];
+        NExcit = __popcll(P.class_mask[cls][0]) - __popcll(d.w[0] & P.class_mask[cls][0]);
+        if (NW > 1) NExcit += __popcll(P.class_mask[cls][1]) - __popcll(d.w[NW - 1] & P.class_mask[cls][1]);
         if (NExcit != 0) break;
         if (attempts > 250) { E.err = 1; return; }
         ++attempts;
@@ -311,12 +317,10 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
         ++attempts;
     }
     E.src1 = src; E.src2 = 0; E.tgt1 = Orb; E.tgt2 = 0;
-    E.parity = parity_single(d, src, Orb);
     const double pDoubNew = 1.0 - P.p_singles;
     double pgen = (1 - pDoubNew) / ((double)(NExcit * (P.nel - ElecsWNoExcits)));
     pgen = pgen / P.p_singles;
     E.pgen = pgen;
-    E.detJ = d; clr_orb(E.detJ, src); set_orb(E.detJ, Orb);
     E.valid = true;
 }
 
@@ -334,7 +338,10 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
         int idx = (int)floor(r);
         u64 mask = NG_ALPHA_MASK;
         if (idx >= AA) { idx -= AA; mask = NG_BETA_MASK; }
-        const int n1 = (int)ceil((1 + sqrt(9 + 8 * (double)idx)) / 2);
+        // n1 = ceil((1 + sqrt(9 + 8 idx)) / 2) == smallest n with n (n - 1) / 2 > idx, evaluated in integers
+        int n1 = (int)((1.0f + sqrtf(9.0f + 8.0f * (float)idx)) * 0.5f);
+        while (n1 * (n1 - 1) / 2 <= idx) ++n1;
+        while ((n1 - 1) * (n1 - 2) / 2 > idx) --n1;
         const int n2 = idx + 1 - ((n1 - 1) * (n1 - 2)) / 2;
         s1 = select_orb(d, mask, n2); s2 = select_orb(d, mask, n1);     // n2 < n1  =>  s1 < s2
         pGen = P.p_parallel / (double)par;
@@ -373,14 +380,26 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
     if (invalid) return;
     const int t1 = min(o1, o2), t2 = max(o1, o2);
     E.tgt1 = t1; E.tgt2 = t2;
-    E.parity = parity_double(d, s1, s2, t1, t2);
-    E.detJ = d; clr_orb(E.detJ, s1); clr_orb(E.detJ, s2); set_orb(E.detJ, t1); set_orb(E.detJ, t2);
     E.pgen = pGen * pGenHoles;
     E.valid = true;
 }
 
+// make_single / make_double results derived from the bit-strings: parity and the excited determinant
+template <int NW>
+__device__ __forceinline__ void finalize_excit(const Det<NW> &d, Excit<NW> &E) {
+    E.detJ = d;
+    if (E.ic == 1) {
+        E.parity = parity_single(d, E.src1, E.tgt1);
+        clr_orb(E.detJ, E.src1); set_orb(E.detJ, E.tgt1);
+    } else {
+        E.parity = parity_double(d, E.src1, E.src2, E.tgt1, E.tgt2);
+        clr_orb(E.detJ, E.src1); clr_orb(E.detJ, E.src2); set_orb(E.detJ, E.tgt1); set_orb(E.detJ, E.tgt2);
+    }
+}
+
+// generation proper (orbitals + pgen); parity and detJ are added by finalize_excit
 template <int NW, int SYS>
-__device__ __forceinline__ void generate_excitation(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+__device__ __forceinline__ void generate_excitation_core(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
     if (SYS == NECI_SYS_HUBBARD_RS) gen_rs_hubbard(P, d, rng, E);
     else if (SYS == NECI_SYS_HUBBARD_K) gen_k_hubbard(P, d, rng, E);
     else {
@@ -388,6 +407,11 @@ __device__ __forceinline__ void generate_excitation(const Params &P, const Det<N
         if (rng.draw() < P.p_singles) { gen_uniform_single(P, d, rng, E); E.pgen = E.pgen * P.p_singles; }
         else { gen_pchb_double(P, d, rng, E); E.pgen = E.pgen * P.p_doubles; }
     }
+}
+template <int NW, int SYS>
+__device__ __forceinline__ void generate_excitation(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+    generate_excitation_core<NW, SYS>(P, d, rng, E);
+    if (E.valid) finalize_excit(d, E);
 }
 
 // get_spawn_helement = get_helement_det_only (src/Determinants.F90:508-554)

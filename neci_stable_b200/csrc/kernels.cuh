@@ -17,44 +17,11 @@
 //   k_list_stats     CalcHashTableStats (load_balancer.fpp:646-805).
 //   k_determ_spmv    determ_projection (semi_stoch_procs.F90:105-241).
 #pragma once
-#include "device_system.cuh"
+#include "spawn_kernel.cuh"
 
 namespace ng {
 
-#define NG_BLOCK 256
-#define NG_HEAVY 4096        /* attempts per determinant handled inside a tile */
-
-struct SpawnBuf {
-    long long *buf;          // SpawnedParts: nranks segments of seg_cap records (W words each)
-    long long *recv;         // received records (contiguous)
-    unsigned long long *cnt; // ValidSpawnedList - InitialSpawnedSlots, per destination rank
-    long long seg_cap;
-    int W;
-    // spawn-merge hash table, entries [stamp:16][tag:16][index:32]
-    u64 *sht; u64 sht_cap;
-    int *ins_idx;            // records that become new determinants
-    long long *heavy;        // (slot, nspawn) pairs
-    long long heavy_cap;
-};
-
-struct IterArgs {
-    double tau, diag_sft;
-    long long iter;
-    long long n_recv;        // < 0: read SB.cnt[0] on the device (single rank)
-    u32 stamp;
-};
-
 // ---- block-level reduction of per-thread statistics into per-block partials ---
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 // acc[k] for the statistics listed in idx[k]; writes out[blockIdx.x * NECI_ST_COUNT + idx[k]]
 // (all other entries of the block row are zeroed by the caller's prologue).
 template <int N>
@@ -96,288 +63,6 @@ __global__ void __launch_bounds__(256) k_reduce_stats(const double *partials, in
         __syncthreads();
     }
     if (threadIdx.x == 0) stats[k] = s_v[0];
-}
-
-// ---- stochastic_round (src/lib/util_mod.fpp:182-204) ---------------------------
-__device__ __forceinline__ double stochastic_round(double r, Stream &rng) {
-    int i = (int)r;
-    const double res = r - (double)i;
-    if (fabs(res) >= 1.0e-12) {
-        if (fabs(res) > rng.draw()) i += (r < 0.0 || (r == 0.0 && signbit(r))) ? -1 : 1;
-    }
-    return (double)i;
-}
-
-// One spawning attempt: generate_excitation + attempt_create_normal
-// (src/fcimc_pointed_fns.F90:178-491).  Returns the child weight (0 = none).
-enum { A_NOBORN = 0, A_SING, A_ACC, A_VALID, A_INVALID, A_BC1, A_BC2, A_MAXSP, A_BS1, A_BS2, A_COUNT };
-
-template <int NW, int SYS, int NA>
-__device__ __forceinline__ double do_attempt(const Params &P, const WalkerList &L, const IterArgs &A,
-                                             const Det<NW> &d, u64 h, u32 p, bool neg, bool core,
-                                             Det<NW> &detJ, double (&acc)[NA], int &child_extra_flags) {
-    Stream rng(P.seed, A.iter, h, p, RNG_ATTEMPT);
-    Excit<NW> E;
-    generate_excitation<NW, SYS>(P, d, rng, E);
-    if (E.err) atomicOr((unsigned long long *)&L.ctr[C_ERR], 16ull);
-    if (!E.valid) { acc[A_INVALID] += 1.0; return 0.0; }
-    acc[A_VALID] += 1.0;
-    child_extra_flags = 0;
-    if (P.t_semi_stochastic && core) {
-        // core -> core spawning is done by determ_projection (FciMCPar.F90:1651-1670)
-        const long long s = ht_lookup<NW>(L, E.detJ, det_hash64(E.detJ));
-        if (s >= 0 && (L.flg[s] & F_DETERM)) return 0.0;
-        child_extra_flags = F_DPARENT;
-    }
-    const double prob = E.pgen * P.av_mc_excits;
-    const double rh = spawn_helement<NW, SYS>(P, d, E);
-    const double ww = neg ? -1.0 : 1.0;
-    double nSpawn = -A.tau * rh * ww / prob;
-    acc[A_MAXSP] = fmax(acc[A_MAXSP], fabs(nSpawn));
-    if (P.t_all_real_coeff) {
-        if (P.t_real_spawn_cutoff && fabs(nSpawn) < P.real_spawn_cutoff)
-            nSpawn = P.real_spawn_cutoff * stochastic_round(nSpawn / P.real_spawn_cutoff, rng);
-    } else nSpawn = stochastic_round(nSpawn, rng);
-    if (fabs(nSpawn) <= NG_EPS) return 0.0;
-    const double ac = fabs(nSpawn);
-    acc[A_NOBORN] += ac;
-    if (E.ic == 1) acc[A_SING] += ac;
-    if (ac > P.initiator_walk_no) {
-        if (E.ic == 1) { acc[A_BC1] += 1.0; acc[A_BS1] = fmax(acc[A_BS1], ac); }
-        else { acc[A_BC2] += 1.0; acc[A_BS2] = fmax(acc[A_BS2], ac); }
-    }
-    acc[A_ACC] += ac;
-    detJ = E.detJ;
-    return nSpawn;
-}
-
-// create_particle (src/fcimc_helper.F90:152-308): warp-aggregated append of
-// (ilutJ, child, flags) to the destination rank's segment of SpawnedParts.
-template <int NW>
-__device__ __forceinline__ void append_spawn(const Params &P, const SpawnBuf &SB, const WalkerList &L, const int *roi,
-                                             bool has, const Det<NW> &detJ, double child, long long flags) {
-    const u32 lane = threadIdx.x & 31;
-    int proc = 0;
-    if (has && P.nranks > 1) proc = __ldg(&P.lb_mapping[det_block<NW>(P, roi, detJ) - 1]);
-    const u32 active = __ballot_sync(0xffffffffu, has);
-    if (!has) return;
-    u32 peers = active;
-    if (P.nranks > 1) peers = __match_any_sync(active, proc);
-    const int leader = __ffs(peers) - 1;
-    const int rank_in = __popc(peers & ((1u << lane) - 1u));
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(&SB.cnt[proc], (unsigned long long)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const long long pos = (long long)base + rank_in;
-    if (pos >= SB.seg_cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull); return; }
-    long long *rec = SB.buf + ((size_t)proc * SB.seg_cap + pos) * SB.W;
-    rec[0] = (long long)detJ.w[0];
-    if (NW > 1) rec[NW - 1] = (long long)detJ.w[NW - 1];
-    rec[NW] = __double_as_longlong(child);
-    rec[NW + 1] = flags;
-}
-
-enum { S_NODIED = A_COUNT, S_NOBORN_D, S_ABORT, S_HF, S_DOUBS, S_ENUM, S_ENUMABS, S_INITSENUM,
-       S_INITD, S_NINITD, S_INITW, S_NINITW, S_ADDED, S_COUNT };
-
-template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK) k_spawn(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
-    __shared__ int s_roi[NG_MAX_BASIS];
-    __shared__ u64 s_d0[NG_BLOCK];
-    __shared__ u64 s_d1[(NW > 1) ? NG_BLOCK : 1];
-    __shared__ u64 s_h[NG_BLOCK];
-    __shared__ int s_off[NG_BLOCK + 1];
-    __shared__ unsigned char s_info[NG_BLOCK];
-    __shared__ int s_wsum[NG_BLOCK / 32];
-    __shared__ double s_red[S_COUNT * 32];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < P.nbasis; i += NG_BLOCK) s_roi[i] = P.random_orb_index[i];
-    double acc[S_COUNT];
-#pragma unroll
-    for (int k = 0; k < S_COUNT; ++k) acc[k] = 0.0;
-    const Det<NW> ref = ref_det<NW>(P);
-    const long long n_list = L.ctr[C_NLIST];
-    __syncthreads();
-
-    for (long long tile = blockIdx.x; tile * NG_BLOCK < n_list; tile += gridDim.x) {
-        const long long slot = tile * NG_BLOCK + tid;
-        int nsp = 0;
-        unsigned char info = 0;
-        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
-        u64 h = 0;
-        if (slot < n_list) {
-            const double s = L.sgn[slot];
-            if (fabs(s) >= 1.0e-12) {
-                d = load_det<NW>(L, slot);
-                int f = L.flg[slot];
-                const int f0 = f;
-                const double K = L.diagH[slot], O = L.offH[slot];
-                const bool core = (f & F_DETERM) != 0;
-                const int exl = excit_level(ref, d);
-                const double as = fabs(s);
-                // CalcParentFlag / TestInitiator_explicit (fcimc_helper.F90:1036-1243)
-                if (P.t_trunc_initiator) {
-                    bool initiator = (f & F_INIT) != 0;
-                    const bool popInit = as > P.initiator_walk_no;
-                    if (!initiator) { if (popInit) { initiator = true; acc[S_ADDED] += 1.0; } }
-                    else if (exl != 0 && !(core && P.t_core_inits) && !popInit) { initiator = false; acc[S_ADDED] -= 1.0; }
-                    if (initiator) { acc[S_INITD] += 1.0; acc[S_INITW] += as; f |= F_INIT; }
-                    else { acc[S_NINITD] += 1.0; acc[S_NINITW] += as; f &= ~F_INIT; }
-                }
-                // SumEContrib (fcimc_helper.F90:518-802)
-                if (exl == 0) acc[S_HF] += s;
-                if (exl == 2) acc[S_DOUBS] += as;
-                const double dE = O * s;
-                acc[S_ENUM] += dE; acc[S_ENUMABS] += fabs(dE);
-                if (f & F_INIT) acc[S_INITSENUM] += dE;
-                h = det_hash64(d);
-                // decide_num_to_spawn (fcimc_helper.F90:2160-2174)
-                {
-                    const double x = s * P.av_mc_excits;
-                    nsp = abs((int)x);
-                    if (fabs(fabs(x) - (double)nsp) > 1.e-12) {
-                        Stream rng(P.seed, A.iter, h, 0, RNG_NSPAWN);
-                        if ((fabs(x) - (double)nsp) > rng.draw()) ++nsp;
-                    }
-                }
-                info = (unsigned char)((s < 0.0 ? 1 : 0) | ((f & F_INIT) ? 2 : 0) | (core ? 4 : 0));
-                // walker_death / attempt_die_normal (fcimc_helper.F90:2279-2407, fcimc_pointed_fns.F90:573-705)
-                double news = s;
-                if (!core) {
-                    const double fac = A.tau * (K - A.diag_sft);
-                    if (fac > 2.0) atomicOr((unsigned long long *)&L.ctr[C_ERR], 4ull);
-                    double iDie;
-                    if (P.t_all_real_coeff) iDie = fac * as;
-                    else {
-                        double rat = fac * as;
-                        iDie = (double)(long long)rat;
-                        rat = rat - iDie;
-                        Stream rng(P.seed, A.iter, h, 0, RNG_DEATH);
-                        if (fabs(rat) > rng.draw()) iDie += (rat < 0.0 || (rat == 0.0 && signbit(rat))) ? -1.0 : 1.0;
-                    }
-                    acc[S_NODIED] += fmin(iDie, as);
-                    acc[S_NOBORN_D] += fmax(iDie - as, 0.0);
-                    news = s - (iDie * dsign(1.0, s));
-                    if (P.t_trunc_initiator && fabs(news) > 1.0e-12 && ((news > 0.0) != (s > 0.0))) {
-                        acc[S_ABORT] += fabs(news);
-                        if (f & F_INIT) acc[S_ADDED] -= 1.0;
-                        news = 0.0;
-                    }
-                    if (!(fabs(news) > 1.0e-12)) {
-                        if (P.t_trunc_initiator && (f & F_INIT)) acc[S_ADDED] -= 1.0;
-                        ht_remove<NW>(L, d, h, slot);
-                        f |= F_REMOVED;
-                        news = 0.0;
-                    }
-                }
-                if (news != s) L.sgn[slot] = news;
-                if (f != f0) L.flg[slot] = f;
-                if (nsp > NG_HEAVY) {
-                    const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NHEAVY], 1ull);
-                    if (k < SB.heavy_cap) { SB.heavy[2 * k] = slot; SB.heavy[2 * k + 1] = ((long long)nsp << 8) | info; }
-                    else atomicOr((unsigned long long *)&L.ctr[C_ERR], 32ull);
-                    nsp = 0;
-                }
-            }
-        }
-        // ---- distribute the tile's attempts over the CTA -------------------------
-        s_d0[tid] = d.w[0]; if (NW > 1) s_d1[tid] = d.w[NW - 1];
-        s_h[tid] = h; s_info[tid] = info;
-        int incl = nsp;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += s_wsum[w];
-        s_off[tid] = wbase + incl - nsp;
-        if (tid == NG_BLOCK - 1) s_off[NG_BLOCK] = wbase + incl;
-        __syncthreads();
-        const int T = s_off[NG_BLOCK];
-        for (int base = 0; base < T; base += NG_BLOCK) {
-            const int a = base + tid;
-            bool has = false; Det<NW> detJ; double child = 0.0; long long cflags = 0;
-            detJ.w[0] = 0; if (NW > 1) detJ.w[NW - 1] = 0;
-            if (a < T) {
-                int lo = 0, hi = NG_BLOCK - 1;            // last index with s_off[idx] <= a
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= a) lo = mid; else hi = mid - 1; }
-                Det<NW> dp; dp.w[0] = s_d0[lo]; if (NW > 1) dp.w[NW - 1] = s_d1[lo];
-                const unsigned char inf = s_info[lo];
-                int extra = 0;
-                child = do_attempt<NW, SYS>(P, L, A, dp, s_h[lo], (u32)(a - s_off[lo]), inf & 1, (inf & 4) != 0,
-                                            detJ, acc, extra);
-                if (child != 0.0) {
-                    has = true;
-                    cflags = (long long)extra;
-                    if (P.t_trunc_initiator && (inf & 2)) cflags |= F_INIT;
-                }
-            }
-            append_spawn<NW>(P, SB, L, s_roi, has, detJ, child, cflags);
-        }
-        __syncthreads();
-    }
-    // ---- flush statistics -------------------------------------------------------
-    double out[20];
-    out[0] = acc[A_NOBORN] + acc[S_NOBORN_D]; out[1] = acc[S_NODIED]; out[2] = acc[S_ABORT]; out[3] = acc[A_SING];
-    out[4] = acc[A_ACC]; out[5] = acc[S_HF]; out[6] = acc[S_DOUBS]; out[7] = acc[S_ENUM]; out[8] = acc[S_ENUMABS];
-    out[9] = acc[S_INITSENUM]; out[10] = acc[S_INITD]; out[11] = acc[S_NINITD]; out[12] = acc[S_INITW];
-    out[13] = acc[S_NINITW]; out[14] = acc[S_ADDED]; out[15] = acc[A_VALID]; out[16] = acc[A_INVALID];
-    out[17] = acc[A_BC1]; out[18] = acc[A_BC2]; out[19] = acc[A_MAXSP];
-    const int idx[20] = {NECI_ST_NOBORN, NECI_ST_NODIED, NECI_ST_NOABORTED, NECI_ST_SPAWNFROMSING, NECI_ST_ACCEPTANCES,
-                         NECI_ST_HFCYC, NECI_ST_NOATDOUBS, NECI_ST_ENUMCYC, NECI_ST_ENUMCYCABS, NECI_ST_INITSENUMCYC,
-                         NECI_ST_NOINITDETS, NECI_ST_NONONINITDETS, NECI_ST_NOINITWALK, NECI_ST_NONONINITWALK,
-                         NECI_ST_NOADDEDINITIATORS, NECI_ST_NVALIDEXCITS, NECI_ST_NINVALIDEXCITS,
-                         NECI_ST_BLOOM_COUNT_1, NECI_ST_BLOOM_COUNT_2, NECI_ST_MAX_CYC_SPAWN};
-    block_flush_stats<20>(out, idx, partials, s_red);
-    // bloom sizes and error bits: rarely non-zero, merged with atomics
-    if (acc[A_BS1] > 0.0 || acc[A_BS2] > 0.0) {
-        atomicMax((unsigned long long *)&L.ctr[C_COUNT - 2], (unsigned long long)__double_as_longlong(acc[A_BS1]));
-        atomicMax((unsigned long long *)&L.ctr[C_COUNT - 1], (unsigned long long)__double_as_longlong(acc[A_BS2]));
-    }
-}
-
-// Attempts of the deferred heavy determinants, spread over the whole grid.
-template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK) k_spawn_heavy(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
-    __shared__ int s_roi[NG_MAX_BASIS];
-    __shared__ double s_red[A_COUNT * 32];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < P.nbasis; i += NG_BLOCK) s_roi[i] = P.random_orb_index[i];
-    __syncthreads();
-    double acc[A_COUNT];
-#pragma unroll
-    for (int k = 0; k < A_COUNT; ++k) acc[k] = 0.0;
-    long long nh = L.ctr[C_NHEAVY];
-    if (nh > SB.heavy_cap) nh = SB.heavy_cap;
-    for (long long e = 0; e < nh; ++e) {
-        const long long slot = SB.heavy[2 * e];
-        const long long packed = SB.heavy[2 * e + 1];
-        const int nsp = (int)(packed >> 8);
-        const unsigned char inf = (unsigned char)(packed & 0xff);
-        const Det<NW> dp = load_det<NW>(L, slot);
-        const u64 h = det_hash64(dp);
-        const int rounds = (nsp + NG_BLOCK - 1) / NG_BLOCK;
-        for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
-            const int a = rd * NG_BLOCK + tid;
-            bool has = false; Det<NW> detJ; double child = 0.0; long long cflags = 0;
-            detJ.w[0] = 0; if (NW > 1) detJ.w[NW - 1] = 0;
-            if (a < nsp) {
-                int extra = 0;
-                child = do_attempt<NW, SYS>(P, L, A, dp, h, (u32)a, inf & 1, (inf & 4) != 0, detJ, acc, extra);
-                if (child != 0.0) { has = true; cflags = (long long)extra; if (P.t_trunc_initiator && (inf & 2)) cflags |= F_INIT; }
-            }
-            append_spawn<NW>(P, SB, L, s_roi, has, detJ, child, cflags);
-        }
-    }
-    double out[8] = {acc[A_NOBORN], acc[A_SING], acc[A_ACC], acc[A_VALID], acc[A_INVALID], acc[A_BC1], acc[A_BC2], acc[A_MAXSP]};
-    const int idx[8] = {NECI_ST_NOBORN, NECI_ST_SPAWNFROMSING, NECI_ST_ACCEPTANCES, NECI_ST_NVALIDEXCITS,
-                        NECI_ST_NINVALIDEXCITS, NECI_ST_BLOOM_COUNT_1, NECI_ST_BLOOM_COUNT_2, NECI_ST_MAX_CYC_SPAWN};
-    block_flush_stats<8>(out, idx, partials, s_red);
-    if (acc[A_BS1] > 0.0 || acc[A_BS2] > 0.0) {
-        atomicMax((unsigned long long *)&L.ctr[C_COUNT - 2], (unsigned long long)__double_as_longlong(acc[A_BS1]));
-        atomicMax((unsigned long long *)&L.ctr[C_COUNT - 1], (unsigned long long)__double_as_longlong(acc[A_BS2]));
-    }
 }
 
 // freeB -> freeA, clamp counters (runs with one block per 256 entries + 1)

@@ -199,6 +199,18 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     e->grid_spawn = nsm * 4;       // refined per kernel variant below
     e->rows_spawn = nsm * 8; e->rows_heavy = nsm * 4; e->rows_compress = e->grid_generic; e->rows_annih = e->grid_generic;
     e->rows_insert = e->grid_generic; e->rows_list = e->grid_generic;
+    // K1 keeps its stage queues in dynamic shared memory (> 48 KB for two-word determinants); one persistent
+    // CTA per resident slot of every SM
+    {
+        int per_sm = 0;
+        NG_DISPATCH(e, {
+            CK(cudaFuncSetAttribute(k_spawn<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared<NW>)));
+            CK(cudaFuncSetAttribute(k_spawn_heavy<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared<NW>)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spawn<NW, SYS>, NG_BLOCK, sizeof(K1Shared<NW>)));
+        });
+        if (per_sm < 1) per_sm = 1;
+        e->rows_spawn = nsm * per_sm; e->rows_heavy = nsm * per_sm;
+    }
     e->rows_total = e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih + e->rows_insert + e->rows_list;
     e->d_partials = e->alloc<double>((size_t)e->rows_total * NECI_ST_COUNT);
     e->d_stats = e->alloc<double>(NECI_ST_COUNT);
@@ -487,8 +499,8 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
     CK(cudaEventRecord(e->ev[1], e->stream));
     e->n_launch += 2;
     double *p_spawn = e->d_partials, *p_heavy = e->d_partials + (size_t)e->rows_spawn * NECI_ST_COUNT;
-    NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
-    NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
+    NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, NG_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
+    NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, NG_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[2], e->stream));
     if (e->cfg.nranks > 1) {
