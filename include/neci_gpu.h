@@ -176,10 +176,14 @@ int neci_gpu_set_system_hubbard_rs(neci_gpu_engine *e, int32_t max_neigh,
  * (src/Integrals_neci.F90:643).                                               */
 int neci_gpu_set_system_hubbard_k(neci_gpu_engine *e, int32_t n_k, const int32_t *ksum,
                                   const int32_t *kdiff, const double *eps_k, double u_over_n);
-/* Semi-stochastic core space: CSR flattening of sparse_core_ham
+/* Semi-stochastic core space: CSR flattening of this rank's rows of sparse_core_ham
  * (src/fast_determ_hamil.F90:1421-1507; diagonal has Hii subtracted), 0-based
- * columns into the gathered vector; core_iluts are this rank's n_local core
- * determinants (nifd+1 words each) in core-space order.                       */
+ * columns into the gathered vector.  core_iluts holds ALL core determinants
+ * (sum(sizes) entries of nifd+1 words) in core-space order, i.e. rank-major:
+ * rank r owns entries [displs[r], displs[r] + sizes[r]) -- the reference keeps
+ * the whole core space on every rank too (core_space + its hash table,
+ * src/core_space_util.F90:20-90) because is_core_state (src/semi_stoch_procs.F90:547)
+ * must recognise core determinants owned by other ranks.                       */
 int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *row_ptr,
                             const int32_t *col, const double *val,
                             const int32_t *sizes, const int32_t *displs,

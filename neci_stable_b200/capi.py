@@ -149,7 +149,7 @@ class Engine:
 
     def set_core_space(self, row_ptr, col, val, sizes, displs, core_iluts):
         rp, cl, vl, sz, dp, ci = _i64(row_ptr), _i32(col), _f64(val), _i32(sizes), _i32(displs), _i64(core_iluts)
-        n_local = rp.size - 1
+        n_local = rp.size - 1                      # core_iluts: ALL core determinants (replicated), rank-major
         self._check(self._fn("set_core_space")(self.h, C.c_int64(n_local), _p(rp, C.c_int64), _p(cl, C.c_int32),
                                                 _p(vl, C.c_double), _p(sz, C.c_int32), _p(dp, C.c_int32),
                                                 _p(ci, C.c_int64)), "set_core_space")

@@ -194,6 +194,10 @@ struct Params {
     const int *ksum, *kdiff;
     const double *eps_k;
     double u_over_n;
+    // semi-stochastic: the whole core space, replicated (is_core_state, src/semi_stoch_procs.F90:547)
+    const long long *core_iluts;      // [n_core_total][nw]
+    const int *core_ht;               // open addressing, entry = index + 1, 0 = empty
+    u64 core_ht_mask;
 };
 
 // main walker list, structure of arrays in HBM
@@ -251,6 +255,21 @@ __device__ __forceinline__ long long ht_lookup(const WalkerList &L, const Det<NW
             if (det_eq(load_det<NW>(L, slot), d)) { if (ht_pos) *ht_pos = pos; return slot; }
         }
         pos = (pos + 1) & L.ht_mask;
+    }
+}
+// is_core_state: membership in the replicated core space
+template <int NW>
+__device__ __forceinline__ bool is_core_state(const Params &P, const Det<NW> &d) {
+    if (!P.core_ht) return false;
+    u64 pos = det_hash64(d) & P.core_ht_mask;
+    for (;;) {
+        const int e = __ldg(&P.core_ht[pos]);
+        if (e == 0) return false;
+        const long long *il = P.core_iluts + (size_t)(e - 1) * NW;
+        bool same = ((u64)__ldg(&il[0]) == d.w[0]);
+        if (NW > 1) same = same && ((u64)__ldg(&il[NW - 1]) == d.w[NW - 1]);
+        if (same) return true;
+        pos = (pos + 1) & P.core_ht_mask;
     }
 }
 // insert a key known to be absent (unique among concurrent inserters)

@@ -377,6 +377,15 @@ __global__ void k_determ_apply(WalkerList L, const int *core_slots, const double
         L.sgn[core_slots[i]] += out[i];
 }
 
+// hash table over the replicated core space (entry = index + 1)
+template <int NW>
+__global__ void k_core_ht_build(const long long *iluts, long long n, int *ht, u64 mask) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Det<NW> d; d.w[0] = (u64)iluts[i * NW]; if (NW > 1) d.w[NW - 1] = (u64)iluts[i * NW + NW - 1];
+        u64 pos = det_hash64(d) & mask;
+        while (atomicCAS(&ht[pos], 0, (int)i + 1) != 0) pos = (pos + 1) & mask;
+    }
+}
 // locate the core determinants in the list and flag them (check_determ_flag)
 template <int NW>
 __global__ void k_core_locate(Params P, WalkerList L, const long long *iluts, long long n, int *slots) {

@@ -358,7 +358,20 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
     e->d_core_slots = e->alloc<int>((size_t)n_local);
     e->d_vpart = e->alloc<double>((size_t)n_local); e->d_vout = e->alloc<double>((size_t)n_local);
     e->d_vfull = e->alloc<double>((size_t)e->n_core_total);
-    long long *d_il = e->upload((const long long *)core_iluts, (size_t)n_local * e->nw);
+    // the whole core space is replicated on every rank; this rank's determinants are [displ, displ + n_local)
+    long long *d_il_all = e->upload((const long long *)core_iluts, (size_t)e->n_core_total * e->nw);
+    long long *d_il = d_il_all + (size_t)e->core_displ * e->nw;
+    long long hc = 1024; while (hc < 2 * e->n_core_total) hc <<= 1;
+    int *d_cht = e->alloc<int>((size_t)hc);
+    if (!d_il_all || !d_cht) return e->fail("core-space upload failed");
+    CK(cudaMemsetAsync(d_cht, 0, (size_t)hc * 4, e->stream));
+    if (e->n_core_total > 0) {
+        const int grid = (int)std::min<long long>(e->grid_generic, (e->n_core_total + 255) / 256);
+        if (e->nw == 1) k_core_ht_build<1><<<grid, 256, 0, e->stream>>>(d_il_all, e->n_core_total, d_cht, (u64)hc - 1);
+        else k_core_ht_build<2><<<grid, 256, 0, e->stream>>>(d_il_all, e->n_core_total, d_cht, (u64)hc - 1);
+        CK(cudaGetLastError());
+    }
+    e->P.core_iluts = d_il_all; e->P.core_ht = d_cht; e->P.core_ht_mask = (u64)hc - 1;
     if (n_local > 0) {
         const int grid = (int)std::min<long long>(e->grid_generic, (n_local + 255) / 256);
         if (e->nw == 1) k_core_locate<1><<<grid, 256, 0, e->stream>>>(e->P, e->L, d_il, n_local, e->d_core_slots);

@@ -151,8 +151,7 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
         bool cancelled = false;
         if (P.t_semi_stochastic && (info & 4)) {
             // core -> core spawning is done by determ_projection (FciMCPar.F90:1651-1670)
-            const long long s = ht_lookup<NW>(L, E.detJ, det_hash64(E.detJ));
-            if (s >= 0 && (L.flg[s] & F_DETERM)) cancelled = true;
+            if (is_core_state<NW>(P, E.detJ)) cancelled = true;
             cflags = F_DPARENT;
         }
         if (!cancelled) {

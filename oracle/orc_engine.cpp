@@ -6,6 +6,7 @@
 // the prefix orc_ instead of neci_gpu_.
 #include "orc_system.hpp"
 #include <thread>
+#include <unordered_set>
 #include <cstdio>
 
 using namespace orc;
@@ -43,6 +44,8 @@ struct orc_engine {
     std::vector<int64_t> row_ptr; std::vector<int32_t> col; std::vector<double> val;
     std::vector<int32_t> core_sizes, core_displs;
     std::vector<int64_t> indices_of_determ_states;
+    struct KH { size_t operator()(const std::array<uint64_t, 2> &k) const { return (size_t)mix64(k[0] ^ mix64(k[1] + 0x9E3779B97F4A7C15ull)); } };
+    std::unordered_set<std::array<uint64_t, 2>, KH> core_set;      // core_space hash (is_core_state)
     std::vector<double> partial_determ_vecs, full_determ_vecs;
     double stats[NECI_ST_COUNT];
     std::string err;
@@ -186,10 +189,8 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
             e.stats[NECI_ST_NVALIDEXCITS] += 1;
             int64_t child_flags = 0;
             if (c.t_semi_stochastic && tCoreDet) {                           // :1651-1670
-                auto it = e.hash.find(e.key(E.ilutJ));
-                // is_core_state: in this restatement the core space is exactly the
-                // set of list entries carrying flag_deterministic.
-                if (it != e.hash.end() && e.test_flag(it->second, NECI_FLAG_DETERMINISTIC)) continue;
+                // is_core_state (src/semi_stoch_procs.F90:547-587): lookup in the replicated core space
+                if (e.core_set.count({E.ilutJ[0], (e.nwords > 1) ? E.ilutJ[1] : 0ull})) continue;
                 child_flags |= (1ll << NECI_FLAG_DETERM_PARENT);
             }
             // attempt_create_normal, src/fcimc_pointed_fns.F90:178-491
@@ -516,12 +517,14 @@ int orc_set_system_hubbard_k(orc_engine *e, int32_t n_k, const int32_t *ksum, co
 int orc_set_core_space(orc_engine *e, int64_t n_local, const int64_t *row_ptr, const int32_t *col,
                        const double *val, const int32_t *sizes, const int32_t *displs,
                        const int64_t *core_iluts) {
-    (void)core_iluts;
     e->n_core_local = n_local;
     e->row_ptr.assign(row_ptr, row_ptr + n_local + 1);
     e->col.assign(col, col + row_ptr[n_local]); e->val.assign(val, val + row_ptr[n_local]);
     e->core_sizes.assign(sizes, sizes + e->cfg.nranks); e->core_displs.assign(displs, displs + e->cfg.nranks);
     e->n_core_total = 0; for (int r = 0; r < e->cfg.nranks; ++r) e->n_core_total += sizes[r];
+    e->core_set.clear();
+    for (int64_t i = 0; i < e->n_core_total; ++i)
+        e->core_set.insert({(uint64_t)core_iluts[i * e->nwords], (e->nwords > 1) ? (uint64_t)core_iluts[i * e->nwords + 1] : 0ull});
     e->indices_of_determ_states.assign(n_local, 0);
     e->partial_determ_vecs.assign(n_local, 0.0); e->full_determ_vecs.assign(e->n_core_total, 0.0);
     return 0;

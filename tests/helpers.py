@@ -137,3 +137,65 @@ def hamiltonian_matrix(engine, system, dets):
     I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
     h = engine.probe_helement(il[I], il[J])
     return h.reshape(n, n)
+
+
+def build_core_space(oracle, system, core_dets, hii, nranks=1):
+    """Host-side mirror of what init_semi_stochastic hands over (src/semi_stoch_gen.F90:103-350,
+    src/fast_determ_hamil.F90:1421-1507): the core determinants grouped by owner rank (core-space order = rank-major),
+    and per rank the CSR rows of H over the whole core space with Hii subtracted on the diagonal.
+    Returns (ordered_dets, sizes, displs, [dict(row_ptr, col, val, iluts) per rank])."""
+    il = np.array([system.ilut(d) for d in core_dets], dtype=np.int64).reshape(len(core_dets), system.nw)
+    _, node = oracle.probe_det_node(il)
+    if nranks == 1:
+        node = np.zeros(len(core_dets), dtype=np.int32)
+    order = np.argsort(node, kind="stable")
+    dets = [core_dets[i] for i in order]
+    il = il[order]; node = node[order]
+    sizes = np.bincount(node, minlength=nranks).astype(np.int32)
+    displs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32)
+    n = len(dets)
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    H = oracle.probe_helement(il[I], il[J]).reshape(n, n)
+    H[np.arange(n), np.arange(n)] -= hii
+    per_rank = []
+    for r in range(nranks):
+        rows = range(displs[r], displs[r] + sizes[r])
+        row_ptr = [0]; col = []; val = []
+        for i in rows:
+            nz = np.nonzero(np.abs(H[i]) > 0)[0]
+            nz = nz[nz != i]
+            # off-diagonal elements first, the diagonal appended last (fast_determ_hamil.F90:1496-1507)
+            col += list(nz) + [i]; val += list(H[i, nz]) + [H[i, i]]
+            row_ptr.append(len(col))
+        per_rank.append(dict(row_ptr=np.array(row_ptr, dtype=np.int64), col=np.array(col, dtype=np.int32),
+                             val=np.array(val, dtype=np.float64), iluts=il.copy()))   # the whole core space, replicated
+    return dets, sizes, displs, per_rank, H
+
+
+class DistOracle:
+    """One oracle rank inside a torch.distributed job (gloo on CPU): the spawn exchange (SendProcNewParts,
+    src/Annihilation.F90:150-247) and the core-vector gather (src/semi_stoch_procs.F90:127) go through the process
+    group.  Same iterate() interface as capi.Engine, so driver.FciMC drives it unchanged."""
+
+    def __init__(self, oracle, dist):
+        self.o, self.dist = oracle, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def upload_walkers(self, *a, **k):
+        return self.o.upload_walkers(*a, **k)
+
+    def download_walkers(self, *a, **k):
+        return self.o.download_walkers(*a, **k)
+
+    def iterate(self, tau, sft, it):
+        o = self.o
+        o.spawn_phase(tau, sft, it)
+        if o.params["t_semi_stochastic"]:
+            parts = [None] * self.world
+            self.dist.all_gather_object(parts, o.partial_vec())
+            o.determ_projection(np.concatenate(parts), tau, sft)
+        out = [o.spawned(r) for r in range(self.world)]
+        everything = [None] * self.world
+        self.dist.all_gather_object(everything, out)
+        recv = np.concatenate([everything[s][self.rank] for s in range(self.world)])   # ordered by source rank
+        return o.annihilate_phase(recv, it)
