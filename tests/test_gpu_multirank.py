@@ -51,8 +51,8 @@ def _worker(rank, world, port, out_dir, name, semi):
     flags = [((1 << capi.FLAG_DETERMINISTIC) if i < n_core else 0) | (1 << capi.FLAG_INITIATOR) for i in range(len(dets))]
     recs = np.array([host.record(system, d, float(s), f) for d, s, f in zip(dets, signs, flags)])
     if semi:
-        core, sizes, displs, per_rank, H = helpers.build_core_space(helpers.Oracle(params) if rank else orcs[0], system,
-                                                                     dets[:n_core], hii, nranks=world)
+        tmp = helpers.Oracle(params); system.apply(tmp)
+        core, sizes, displs, per_rank, H = helpers.build_core_space(tmp, system, dets[:n_core], hii, nranks=world)
         # core determinants first, in core-space order, on their owner
         core_il = np.array([system.ilut(d) for d in core]).reshape(len(core), system.nw)
         lookup = {tuple(d): r_ for d, r_ in zip(dets, recs)}
