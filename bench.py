@@ -53,26 +53,63 @@ def build_system(workload):
     raise SystemExit("unknown workload %s" % workload)
 
 
-def random_walker_records(system, n_dets, seed, keep=None, keep_frac=1.0, chunk=1 << 20):
+_COMBO_CACHE = {}
+
+
+def _combination_masks(n, k):
+    """All C(n, k) k-subsets of n spatial orbitals as bit masks over spatial orbitals (uint64), built by the
+    Pascal recursion with numpy concatenations."""
+    key = (n, k)
+    if key in _COMBO_CACHE:
+        return _COMBO_CACHE[key]
+    if k == 0:
+        out = np.zeros(1, dtype=np.uint64)
+    elif k == n:
+        out = np.array([(1 << n) - 1], dtype=np.uint64)
+    else:
+        out = np.concatenate([_combination_masks(n - 1, k), _combination_masks(n - 1, k - 1) | np.uint64(1 << (n - 1))])
+    _COMBO_CACHE[key] = out
+    return out
+
+
+def _spread_spin(masks, n_spat, alpha, nw):
+    """Spatial-orbital masks -> spin-orbital occupation words: spatial i (1-based) -> spin orbital 2i (alpha) or 2i-1 (beta)."""
+    words = np.zeros((masks.shape[0], nw), dtype=np.uint64)
+    for i in range(n_spat):
+        orb = 2 * (i + 1) - (0 if alpha else 1)
+        bit = orb - 1
+        has = (masks >> np.uint64(i)) & np.uint64(1)
+        words[:, bit // 64] |= has << np.uint64(bit % 64)
+    return words
+
+
+def random_walker_records(system, n_dets, seed, keep=None, keep_frac=1.0, chunk=1 << 22):
     """Distinct uniformly random determinants (n_alpha of n_spat, n_beta of n_spat), signs +-round(1 + Exp(1)).
     keep(iluts) -> bool mask selects the determinants this rank owns."""
+    import math
     rng = np.random.default_rng(seed)
     ns = system.nbasis // 2
     nw = system.nw
+    use_table = max(math.comb(ns, system.nocc_alpha), math.comb(ns, system.nocc_beta)) <= 30_000_000
+    if use_table:
+        ta = _spread_spin(_combination_masks(ns, system.nocc_alpha), ns, True, nw)
+        tb = _spread_spin(_combination_masks(ns, system.nocc_beta), ns, False, nw)
     out = []
     have = 0
-    seen = None
     while have < n_dets:
         m = int(min(chunk, max(4096, 1.05 * (n_dets - have) / keep_frac + 1024)))
-        words = np.zeros((m, nw), dtype=np.uint64)
-        for nocc, alpha in ((system.nocc_alpha, True), (system.nocc_beta, False)):
-            pick = np.argpartition(rng.random((m, ns)), nocc - 1, axis=1)[:, :nocc]      # nocc distinct spatial orbitals
-            orb = 2 * (pick + 1) - (0 if alpha else 1)                                    # 1-based spin orbital
-            bit = (orb - 1).astype(np.uint64)
-            for w in range(nw):
-                sel = (bit // 64) == w
-                contrib = np.where(sel, np.uint64(1) << (bit % np.uint64(64)), np.uint64(0))
-                words[:, w] |= np.bitwise_or.reduce(contrib, axis=1)
+        if use_table:
+            words = ta[rng.integers(0, ta.shape[0], m)] | tb[rng.integers(0, tb.shape[0], m)]
+        else:
+            words = np.zeros((m, nw), dtype=np.uint64)
+            for nocc, alpha in ((system.nocc_alpha, True), (system.nocc_beta, False)):
+                pick = np.argpartition(rng.random((m, ns)), nocc - 1, axis=1)[:, :nocc]  # nocc distinct spatial orbitals
+                orb = 2 * (pick + 1) - (0 if alpha else 1)                                # 1-based spin orbital
+                bit = (orb - 1).astype(np.uint64)
+                for w in range(nw):
+                    sel = (bit // 64) == w
+                    contrib = np.where(sel, np.uint64(1) << (bit % np.uint64(64)), np.uint64(0))
+                    words[:, w] |= np.bitwise_or.reduce(contrib, axis=1)
         if keep is not None:
             words = words[keep(words.view(np.int64))]
         out.append(words)

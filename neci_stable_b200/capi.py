@@ -238,6 +238,11 @@ class Engine:
         self._check(self._fn("block_populations")(self.h, _p(out, C.c_double)), "block_populations")
         return out
 
+    def rebalance(self, new_mapping):
+        m = _i32(new_mapping)
+        self._check(self._fn("rebalance")(self.h, _p(m, C.c_int32)), "rebalance")
+        self.params["load_balance_mapping"] = m.copy()
+
     # -- probes ---------------------------------------------------------------------------
     def probe_det_node(self, iluts):
         il = _i64(iluts).reshape(-1, self.nw)

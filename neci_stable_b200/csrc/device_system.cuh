@@ -331,8 +331,8 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
     const int nA = P.nocc_alpha, nB = P.nocc_beta;
     const int AA = nA * (nA - 1) / 2, BB = nB * (nB - 1) / 2, par = AA + BB, AB = nA * nB;
     double r = rng.draw();
-    int s1, s2;
     double pGen;
+    u64 m1, m2; int k1, k2;                        // the pair = k1-th orbital of mask m1 and k2-th of mask m2
     if (r < P.p_parallel) {
         r = (r / P.p_parallel) * par;
         int idx = (int)floor(r);
@@ -343,17 +343,18 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
         while (n1 * (n1 - 1) / 2 <= idx) ++n1;
         while ((n1 - 1) * (n1 - 2) / 2 > idx) --n1;
         const int n2 = idx + 1 - ((n1 - 1) * (n1 - 2)) / 2;
-        s1 = select_orb(d, mask, n2); s2 = select_orb(d, mask, n1);     // n2 < n1  =>  s1 < s2
+        m1 = mask; k1 = n2; m2 = mask; k2 = n1;
         pGen = P.p_parallel / (double)par;
     } else {
         pGen = (1.0 - P.p_parallel) / (double)AB;
         r = ((r - P.p_parallel) / (1.0 - P.p_parallel)) * AB;
         const int idx = (int)floor(r);
-        const int an = 1 + idx % nA;
-        const int bn = 1 + (int)floor(idx / (double)nA);
-        const int oa = select_orb(d, NG_ALPHA_MASK, an), ob = select_orb(d, NG_BETA_MASK, bn);
-        s1 = min(oa, ob); s2 = max(oa, ob);
+        m1 = NG_ALPHA_MASK; k1 = 1 + idx % nA;
+        m2 = NG_BETA_MASK;  k2 = 1 + idx / nA;      // == 1 + floor(idx / real(nA))
     }
+    // the two orbital selections are common to both branches (kept out of the divergent part)
+    const int oa = select_orb(d, m1, k1), ob = select_orb(d, m2, k2);
+    const int s1 = min(oa, ob), s2 = max(oa, ob);
     const int ij = fuse_index(gtid(s1), gtid(s2));
     int spin1 = s1 & 1, spin2 = s2 & 1;           // getSpinIndex: 0 alpha, 1 beta
     int sampler;

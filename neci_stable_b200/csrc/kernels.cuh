@@ -439,7 +439,7 @@ __global__ void k_probe_gen_excit(Params P, const long long *iluts, const int *a
     }
 }
 
-// per-block walker populations for adjust_load_balance (load_balancer.fpp:216-235)
+// per-block walker populations for adjust_load_balance (load_balancer.fpp:216-235): sum(ceiling(abs(sgn)))
 template <int NW>
 __global__ void k_block_pops(Params P, WalkerList L, double *block_parts) {
     __shared__ int s_roi[NG_MAX_BASIS];
@@ -450,8 +450,45 @@ __global__ void k_block_pops(Params P, WalkerList L, double *block_parts) {
         const double s = L.sgn[i];
         if (fabs(s) < 1.0e-12) continue;
         const int b = det_block<NW>(P, s_roi, load_det<NW>(L, i));
-        atomicAdd(&block_parts[b - 1], fabs(s));
+        atomicAdd(&block_parts[b - 1], ceil(fabs(s)));
     }
+}
+
+// move_block (load_balancer.fpp:353-512), sender side, for all moved blocks at once: every occupied
+// determinant whose owner under the NEW mapping is another rank is appended to that rank's segment of the
+// spawn buffer (the wire format of the reference's MPISend: ilut incl. sign and flags) and removed here.
+template <int NW>
+__global__ void __launch_bounds__(NG_BLOCK) k_rebalance_pack(Params P, WalkerList L, SpawnBuf SB) {
+    __shared__ int s_roi[NG_MAX_BASIS];
+    for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) s_roi[i] = P.random_orb_index[i];
+    __syncthreads();
+    const long long n = L.ctr[C_NLIST];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n + stride - 1) / stride) * stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
+        bool move = false;
+        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
+        double s = 0.0; int f = 0;
+        if (i < n) {
+            s = L.sgn[i];
+            if (fabs(s) >= 1.0e-12) {
+                d = load_det<NW>(L, i);
+                f = L.flg[i];
+                const int owner = __ldg(&P.lb_mapping[det_block<NW>(P, s_roi, d) - 1]);
+                if (owner != P.rank) {
+                    move = true;
+                    ht_remove<NW>(L, d, det_hash64(d), i);
+                    L.sgn[i] = 0.0; L.flg[i] = f | F_REMOVED;
+                }
+            }
+        }
+        append_spawn<NW>(P, SB, L, s_roi, move, d, s, (long long)(f & ~F_REMOVED));
+    }
+}
+// receiver side: every received record is a new determinant here
+__global__ void k_iota_insert(WalkerList L, SpawnBuf SB, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) SB.ins_idx[i] = (int)i;
+    if (blockIdx.x == 0 && threadIdx.x == 0) L.ctr[C_NINSERT] = n;
 }
 
 }  // namespace ng

@@ -583,11 +583,38 @@ int neci_gpu_block_populations(neci_gpu_engine *e, double *block_parts) {
 }
 
 int neci_gpu_rebalance(neci_gpu_engine *e, const int32_t *new_mapping) {
-    // adjust_load_balance / move_block (load_balancer.fpp:178-512): with the
-    // mapping replaced, every determinant whose block moved is shipped as a
-    // "spawn" of its full weight to the new owner and re-inserted there.
-    (void)new_mapping;
-    return e->fail("neci_gpu_rebalance: not implemented in this round");
+    // adjust_load_balance / move_block (load_balancer.fpp:178-512): install the new LoadBalanceMapping, ship
+    // every determinant whose block changed owner to its new rank (same grouped send/recv as the spawn
+    // exchange) and insert it there (AddNewHashDet recomputes H_ii and H_0i, as the receiver does in move_block).
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->cfg.t_semi_stochastic && e->n_core_total > 0)
+        return e->fail("should not be dynamically load-balancing with a fixed deterministic space (load_balancer.fpp:198-201)");
+    for (int b = 0; b < e->cfg.balance_blocks; ++b)
+        if (new_mapping[b] < 0 || new_mapping[b] >= e->cfg.nranks) return e->fail("new_mapping[%d] = %d out of range", b, new_mapping[b]);
+    CK(cudaMemcpyAsync((void *)e->P.lb_mapping, new_mapping, (size_t)e->cfg.balance_blocks * 4, cudaMemcpyHostToDevice, e->stream));
+    if (e->cfg.nranks == 1) { CK(cudaStreamSynchronize(e->stream)); return 0; }
+    if (!e->comm) return e->fail("nranks > 1 but neci_gpu_nccl_init was not called");
+    if (begin_iteration(e)) return 1;
+    const int g = e->grid_generic;
+    e->n_launch += 5;
+    if (e->nw == 1) k_rebalance_pack<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
+    else k_rebalance_pack<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
+    CK(cudaGetLastError());
+    long long nrecv = 0;
+    if (exchange_spawns(e, &nrecv)) return 1;
+    k_merge_free<<<64, 256, 0, e->stream>>>(e->L);
+    k_merge_free_finish<<<1, 1, 0, e->stream>>>(e->L);
+    k_iota_insert<<<g, 256, 0, e->stream>>>(e->L, e->SB, nrecv);
+    double *p_ins = e->d_partials + (size_t)(e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih) * NECI_ST_COUNT;
+    NG_DISPATCH(e, (k_insert<NW, SYS><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, p_ins)));
+    k_fix_counters<<<1, 1, 0, e->stream>>>(e->L);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_ctr, e->L.ctr, C_COUNT * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const long long errf = e->h_ctr[C_ERR];
+    if (errf & 1) return e->fail("rebalance: moved determinants exceed the spawn buffer segment (move fewer blocks per call or raise max_spawned)");
+    if (errf & 2) return e->fail("rebalance: main walker list overflow on the receiving rank");
+    return 0;
 }
 
 // ---- measurement helpers ------------------------------------------------------------

@@ -347,7 +347,7 @@ __device__ __forceinline__ void k1_flush(const WalkerList &L, K1Shared<NW> &S, c
 }
 
 template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK, 3) k_spawn(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
+__global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     K1Shared<NW> &S = *reinterpret_cast<K1Shared<NW> *>(k1_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -76,6 +76,59 @@ def reduce_stats(st):
     return out
 
 
+def plan_load_balance(block_parts_all, mapping, nranks):
+    """The greedy balancer of adjust_load_balance (src/load_balancer.fpp:239-304): repeatedly move the smallest
+    non-empty block of the fullest rank to the emptiest rank while that brings both closer to the average.
+    block_parts_all: summed block populations (sum(ceiling(abs(sgn)))); mapping: block -> rank (0-based).
+    Returns (new_mapping, movelist[(block, from, to)])."""
+    parts = np.asarray(block_parts_all, dtype=np.int64)
+    mapping = np.array(mapping, dtype=np.int32).copy()
+    moves = []
+    while True:
+        proc_parts = np.bincount(mapping, weights=parts, minlength=nranks).astype(np.int64)
+        avg = proc_parts.sum() / float(nranks)
+        min_proc, max_proc = int(np.argmin(proc_parts)), int(np.argmax(proc_parts))      # first occurrence, as min/maxloc
+        min_parts, max_parts = int(proc_parts[min_proc]), int(proc_parts[max_proc])
+        smallest_block, smallest_size = -1, -1
+        for b in np.nonzero(mapping == max_proc)[0]:
+            if parts[b] > 0 and (parts[b] < smallest_size or smallest_size == -1):
+                smallest_block, smallest_size = int(b), int(parts[b])
+        unbalanced = (smallest_block != -1 and abs(min_parts + smallest_size - avg) < abs(min_parts - avg)
+                      and abs(max_parts - smallest_size - avg) < abs(max_parts - avg))
+        if not unbalanced:
+            break
+        moves.append((smallest_block, max_proc, min_proc))
+        mapping[smallest_block] = min_proc
+    return mapping, moves
+
+
+class LoadBalanceTrigger:
+    """need_load_balancing (src/load_balancer.fpp:836-855) with the imbalance measure of the main loop
+    (src/FciMCPar.F90:564-578, 842-849): over a measuring cycle of 100 iterations, lt_imb = sum_iter (max_rank t - mean_rank t)
+    / sum_iter sum_rank t, i.e. the fraction of loop time lost to imbalance.  Balance when it exceeds
+    max(0.1, 2 x the value logged right after the previous balancing step); never in two consecutive cycles."""
+
+    def __init__(self):
+        self.last_imb = 0.0
+        self.last_t_lb = False
+
+    @staticmethod
+    def imbalance(loop_times):
+        """loop_times: array [n_iter, n_ranks] of per-iteration loop times."""
+        t = np.asarray(loop_times, dtype=np.float64)
+        tot = t.sum()
+        return float((t.max(axis=1) - t.mean(axis=1)).sum() / tot) if tot > 0 else 0.0
+
+    def need(self, lt_imb):
+        if self.last_t_lb:
+            self.last_imb = lt_imb
+            self.last_t_lb = False
+            return False
+        t_lb = lt_imb > max(0.1, 2.0 * self.last_imb)
+        self.last_t_lb = t_lb
+        return t_lb
+
+
 class FciMC:
     """Drives one engine (rank) through the FCIQMC iteration loop."""
 

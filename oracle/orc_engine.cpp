@@ -612,6 +612,57 @@ int orc_iterate(orc_engine *e, double tau, double diag_sft, int64_t iter, double
     return orc_world_iterate(es, 1, tau, diag_sft, iter, stats_out, 1);
 }
 
+// ---- dynamic load balancing -------------------------------------------------
+// block populations, src/load_balancer.fpp:216-235: sum(ceiling(abs(sgn))) per block
+int orc_block_populations(orc_engine *e, double *block_parts) {
+    for (int b = 0; b < e->cfg.balance_blocks; ++b) block_parts[b] = 0.0;
+    int nI[128];
+    for (int64_t j = 0; j < e->TotWalkers; ++j) {
+        const double s = e->sign(j);
+        if (unocc(s)) continue;
+        decode(e->orb(j), e->cfg.nbasis, nI);
+        block_parts[det_block(*e, nI) - 1] += std::ceil(std::fabs(s));
+    }
+    return 0;
+}
+// move_block, src/load_balancer.fpp:353-512, for a whole new mapping at once: determinants whose block now
+// belongs to another rank are removed here (RemoveHashDet + null sign) and added there (AddNewHashDet with
+// recomputed H_ii / H_0i).
+int orc_world_rebalance(orc_engine **es, int32_t n, const int32_t *new_mapping) {
+    std::vector<std::vector<int64_t>> moved(n);
+    int nI[128];
+    for (int r = 0; r < n; ++r) {
+        orc_engine &e = *es[r];
+        e.lb_mapping.assign(new_mapping, new_mapping + e.cfg.balance_blocks);
+        e.iStartFreeSlot = e.iEndFreeSlot = 0;
+        for (int64_t j = 0; j < e.TotWalkers; ++j) {
+            const double s = e.sign(j);
+            if (unocc(s)) { if (!e.test_flag(j, NECI_FLAG_DETERMINISTIC)) e.FreeSlot[e.iEndFreeSlot++] = j; continue; }
+            decode(e.orb(j), e.cfg.nbasis, nI);
+            const int owner = det_node(e, nI);
+            if (owner != r) {
+                const int64_t *rec = &e.dets[(size_t)j * e.W];
+                std::vector<int64_t> tmp(rec, rec + e.W);
+                tmp[e.nwords + 1] &= ~1ll;
+                moved[owner].insert(moved[owner].end(), tmp.begin(), tmp.end());
+                RemoveHashDet(e, j);
+                e.set_sign(j, 0.0);
+            }
+        }
+    }
+    for (int r = 0; r < n; ++r) {
+        orc_engine &e = *es[r];
+        const int64_t m = (int64_t)(moved[r].size() / e.W);
+        for (int64_t i = 0; i < m; ++i) {
+            const int64_t *rec = &moved[r][(size_t)i * e.W];
+            const double diagH = get_diagonal_matel(e.S, (const uint64_t *)rec);
+            const double offdiagH = get_off_diagonal_matel(e.S, (const uint64_t *)rec, e.ilut_ref.data());
+            if (!AddNewHashDet(e, rec, sign_to_double(rec[e.nwords]), diagH, offdiagH)) return 1;
+        }
+    }
+    return 0;
+}
+
 // ---- probes ---------------------------------------------------------------
 int orc_probe_det_node(orc_engine *e, int64_t n, const int64_t *iluts, int32_t *block_out, int32_t *node_out) {
     int nI[128];

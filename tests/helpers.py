@@ -79,6 +79,17 @@ def world_iterate(oracles, tau, sft, it, nthreads=1):
     return st
 
 
+def world_rebalance(oracles, new_mapping):
+    lib = oracles[0].lib
+    n = len(oracles)
+    arr = (C.c_void_p * n)(*[o.h for o in oracles])
+    m = np.ascontiguousarray(new_mapping, dtype=np.int32)
+    rc = lib.orc_world_rebalance(arr, C.c_int32(n), m.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    for o in oracles:
+        o.params["load_balance_mapping"] = m.copy()
+
+
 def make_pair(system, hii, cls_gpu=True, **kw):
     """(oracle, params) for a system; the caller creates the CUDA engine from the same params."""
     params = host.make_params(system, hii, **kw)

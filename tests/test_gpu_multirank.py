@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N_ITER = 30
 
 
-def _worker(rank, world, port, out_dir, name, semi):
+def _worker(rank, world, port, out_dir, name, semi, balance=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -76,6 +76,7 @@ def _worker(rank, world, port, out_dir, name, semi):
                 orcs[r].upload_walkers(recs[node == r])
     ok = True
     msg = ""
+    n_moves = 0
     for it in range(1, N_ITER + 1):
         sg = gpu.iterate(tau, -0.1, it)
         allg = [None] * world
@@ -92,6 +93,21 @@ def _worker(rank, world, port, out_dir, name, semi):
                         ok = False; msg = "stat %s rank %d it %d: gpu %r oracle %r" % (n, r, it, allg[r][ST[n]], so[r][ST[n]])
         if not ok:
             break
+        if balance and it % 10 == 0:
+            # adjust_load_balance: block populations summed over ranks, greedy plan (identical on every rank), block moves
+            allp = [None] * world
+            dist.all_gather_object(allp, gpu.block_populations())
+            parts = np.sum(allp, axis=0)
+            new, moves = driver.plan_load_balance(parts, gpu.params["load_balance_mapping"], world)
+            if rank == 0:
+                op = np.sum([o.block_populations() for o in orcs], axis=0)
+                if not np.array_equal(op, parts):
+                    ok = False; msg = "block populations differ at it %d" % it
+                helpers.world_rebalance(orcs, new)
+            gpu.rebalance(new)
+            n_moves += len(moves)
+    if balance and n_moves == 0:
+        ok = False; msg = "no block was moved"
     lists = [None] * world
     dist.all_gather_object(lists, gpu.download_walkers())
     if rank == 0 and ok:
@@ -115,9 +131,10 @@ def _worker(rank, world, port, out_dir, name, semi):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,semi", [("pchb_14e28o", False), ("hub_k_6x6_2words", False), ("hub_rs_4x4", False),
-                                       ("pchb_6e6o", True)])
-def test_multi_gpu_matches_oracle_world(tmp_path, name, semi):
+@pytest.mark.parametrize("name,semi,balance", [("pchb_14e28o", False, False), ("hub_k_6x6_2words", False, False),
+                                               ("hub_rs_4x4", False, True), ("pchb_14e28o", False, True),
+                                               ("pchb_6e6o", True, False)])
+def test_multi_gpu_matches_oracle_world(tmp_path, name, semi, balance):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -125,7 +142,7 @@ def test_multi_gpu_matches_oracle_world(tmp_path, name, semi):
         pytest.skip("needs >= 2 GPUs")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, str(tmp_path), name, semi), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), name, semi, balance), nprocs=world, join=True)
     res = open(os.path.join(tmp_path, "result.txt")).read()
     assert res.startswith("OK"), res
     assert int(res.split()[1]) > 100
