@@ -159,6 +159,12 @@ struct Stream {
 // ---------------------------------------------------------------------------
 // Parameter block (passed by value; lives in the kernel's constant bank).
 // ---------------------------------------------------------------------------
+// one entry of an alias sampler: probability and bias threshold of pair index ab, its alias and its two
+// spatial target orbitals (tgtOrbs(:, ab)) packed as lo | hi << 16
+struct __align__(32) PchbEntry { double prob, bias; int alias; u32 tgt; };
+// per electron-pair index ij: exchange probability, and bit s set when sampler s of this pair is non-empty
+struct __align__(16) PchbPair { double p_exch; int nonempty; int pad; };
+
 struct Params {
     // configuration scalars
     int nel, nbasis, nocc_alpha, nocc_beta;
@@ -175,12 +181,14 @@ struct Params {
     const int *lb_mapping;            // [balance_blocks]
     // FCIDUMP
     const double *umat, *tmat;
-    // PCHB
+    // PCHB: the host's probs / bias / alias / tgtOrbs arrays interleaved into one 32-byte entry per
+    // (ij, sampler, ab) so that an alias draw costs one L2 sector (two when the alias is taken)
     int n_spat, ij_max, ab_max;
-    const double *probs, *bias, *p_exch;
-    const int *alias;
-    const int2 *tgt_orbs;
+    const struct PchbEntry *pchb;     // [ij_max * 3 * ab_max]
+    const struct PchbPair *pchb_pair; // [ij_max]
     double p_singles, p_doubles, p_parallel;
+    double pgen_pair_par, pgen_pair_opp;            // p_parallel / #parallel pairs, (1 - p_parallel) / #alpha-beta pairs
+    u32 magic_nalpha;                               // floor(2^32 / nocc_alpha) + 1 (exact quotients for idx < 2^32 / nocc_alpha)
     int n_classes;
     const unsigned char *class_of_spinorb;          // [nbasis]
     const int *class_start, *class_orbs;            // CSR of class members

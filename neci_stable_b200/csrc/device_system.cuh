@@ -27,12 +27,16 @@ template <int NW> struct Excit {
 };
 
 // ---- integrals ---------------------------------------------------------------
-__device__ __forceinline__ int tri(int a, int b) { return (a > b) ? a * (a - 1) / 2 + b : b * (b - 1) / 2 + a; }
+// 1-based triangular index in unsigned 32-bit arithmetic (spatial orbitals <= 64 => pair index <= 2080,
+// UMatInd <= 2 164 240: neci_gpu_set_system_fcidump checks n_umat < 2^31)
+__device__ __forceinline__ u32 tri(u32 a, u32 b) {
+    const u32 hi = max(a, b), lo = min(a, b);
+    return ((hi * (hi - 1u)) >> 1) + lo;
+}
 // <ij|kl> over spatial orbitals (1-based): UMAT(UMatInd(i,j,k,l))
 __device__ __forceinline__ double umat_el(const Params &P, int i, int j, int k, int l) {
-    const int A = tri(i, k), B = tri(j, l);
-    const long long ind = (A > B) ? (long long)A * (A - 1) / 2 + B : (long long)B * (B - 1) / 2 + A;
-    return __ldg(&P.umat[ind - 1]);
+    const u32 ind = tri(tri((u32)i, (u32)k), tri((u32)j, (u32)l));
+    return __ldg(&P.umat[ind - 1u]);
 }
 __device__ __forceinline__ double tmat_el(const Params &P, int i, int j) {
     return __ldg(&P.tmat[(size_t)(i - 1) + (size_t)P.nbasis * (j - 1)]);
@@ -344,37 +348,45 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
         while ((n1 - 1) * (n1 - 2) / 2 > idx) --n1;
         const int n2 = idx + 1 - ((n1 - 1) * (n1 - 2)) / 2;
         m1 = mask; k1 = n2; m2 = mask; k2 = n1;
-        pGen = P.p_parallel / (double)par;
+        pGen = P.pgen_pair_par;                     // p_parallel / par, divided once on the host (same IEEE quotient)
     } else {
-        pGen = (1.0 - P.p_parallel) / (double)AB;
+        pGen = P.pgen_pair_opp;                     // (1 - p_parallel) / AB
         r = ((r - P.p_parallel) / (1.0 - P.p_parallel)) * AB;
         const int idx = (int)floor(r);
-        m1 = NG_ALPHA_MASK; k1 = 1 + idx % nA;
-        m2 = NG_BETA_MASK;  k2 = 1 + idx / nA;      // == 1 + floor(idx / real(nA))
+        const int q = (nA == 1) ? idx : (int)__umulhi((u32)idx, P.magic_nalpha);   // idx / nA
+        m1 = NG_ALPHA_MASK; k1 = 1 + idx - q * nA;
+        m2 = NG_BETA_MASK;  k2 = 1 + q;             // == 1 + floor(idx / real(nA))
     }
     // the two orbital selections are common to both branches (kept out of the divergent part)
     const int oa = select_orb(d, m1, k1), ob = select_orb(d, m2, k2);
     const int s1 = min(oa, ob), s2 = max(oa, ob);
-    const int ij = fuse_index(gtid(s1), gtid(s2));
+    const int ij = (int)tri((u32)gtid(s1), (u32)gtid(s2));      // fuse_index
     int spin1 = s1 & 1, spin2 = s2 & 1;           // getSpinIndex: 0 alpha, 1 beta
+    const int4 pi = __ldg(reinterpret_cast<const int4 *>(P.pchb_pair + (ij - 1)));    // {p_exch, nonempty, pad}
     int sampler;
     if (spin1 == spin2) sampler = 0;
     else {
-        const double pe = __ldg(&P.p_exch[ij - 1]);
+        const double pe = __hiloint2double(pi.y, pi.x);
         if (rng.draw() < pe) { sampler = 2; pGen *= pe; const int t = spin1; spin1 = spin2; spin2 = t; }
         else { sampler = 1; pGen *= (1.0 - pe); }
     }
     E.src1 = s1; E.src2 = s2; E.tgt1 = 0; E.tgt2 = 0; E.pgen = pGen;
     // AliasSampler_t::sample
-    const size_t base = ((size_t)(ij - 1) * 3 + sampler) * P.ab_max;
-    if (__ldg(&P.alias[base]) == 0) return;                          // empty sampler: ab = 0
+    if (((pi.z >> sampler) & 1) == 0) return;                        // empty sampler: ab = 0
+    const PchbEntry *tab = P.pchb + ((size_t)(ij - 1) * 3 + sampler) * P.ab_max;
     const double rr = rng.draw();
     const int pos = (int)(P.ab_max * rr) + 1;
     const double bias = fmax(P.ab_max * rr + 1 - pos, 0.0);
-    const int ab = (bias < __ldg(&P.bias[base + pos - 1])) ? pos : __ldg(&P.alias[base + pos - 1]);
-    const double pGenHoles = __ldg(&P.probs[base + ab - 1]);
-    const int2 t = __ldg(&P.tgt_orbs[ab - 1]);
-    const int o1 = 2 * t.x - spin1, o2 = 2 * t.y - spin2;
+    const double2 pb = __ldg(reinterpret_cast<const double2 *>(tab + (pos - 1)));                              // prob, bias
+    const int2 at = __ldg(reinterpret_cast<const int2 *>(reinterpret_cast<const char *>(tab + (pos - 1)) + 16)); // alias, tgt
+    double pGenHoles = pb.x;
+    u32 tg = (u32)at.y;
+    if (!(bias < pb.y)) {                                            // take the alias: its entry holds prob and targets
+        const PchbEntry *e2 = tab + (at.x - 1);
+        pGenHoles = __ldg(&e2->prob);
+        tg = __ldg(&e2->tgt);
+    }
+    const int o1 = 2 * (int)(tg & 0xffffu) - spin1, o2 = 2 * (int)(tg >> 16) - spin2;
     E.tgt1 = o1; E.tgt2 = o2;
     bool invalid = (o1 == 0 || o2 == 0) || occ(d, o1) || occ(d, o2);
     if (!invalid && fabs(pGenHoles) <= NG_EPS) invalid = true;

@@ -245,6 +245,7 @@ int neci_gpu_finalize(neci_gpu_engine *e) {
 
 int neci_gpu_set_system_fcidump(neci_gpu_engine *e, const double *umat, int64_t n_umat, const double *tmat2d) {
     CK(cudaSetDevice(e->cfg.device));
+    if (n_umat >= (1ll << 31)) return e->fail("n_umat must be < 2^31 (32-bit UMatInd arithmetic on the device)");
     e->P.umat = e->upload(umat, (size_t)n_umat);
     e->P.tmat = e->upload(tmat2d, (size_t)e->cfg.nbasis * e->cfg.nbasis);
     if (!e->P.umat || !e->P.tmat) return e->fail("integral upload failed");
@@ -260,10 +261,34 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
     Params &P = e->P;
     const size_t n = (size_t)ij_max * 3 * ab_max;
     P.n_spat = n_spat; P.ij_max = ij_max; P.ab_max = ab_max;
-    P.probs = e->upload(probs, n); P.bias = e->upload(bias, n); P.alias = e->upload(alias, n);
-    P.p_exch = e->upload(p_exch, (size_t)ij_max);
-    P.tgt_orbs = (const int2 *)e->upload(tgt_orbs, 2 * (size_t)ab_max);
+    if (n_spat > 0xffff) return e->fail("n_spat %d too large", n_spat);
+    {
+        // interleave probs / bias / alias / tgtOrbs into one 32-byte entry per (ij, sampler, ab)
+        std::vector<PchbEntry> tab(n);
+        std::vector<PchbPair> pair((size_t)ij_max);
+        for (size_t ij = 0; ij < (size_t)ij_max; ++ij) {
+            pair[ij].p_exch = p_exch[ij]; pair[ij].nonempty = 0; pair[ij].pad = 0;
+            for (int s = 0; s < 3; ++s) {
+                const size_t base = (ij * 3 + s) * ab_max;
+                if (alias[base] != 0) pair[ij].nonempty |= 1 << s;
+                for (int ab = 0; ab < ab_max; ++ab) {
+                    PchbEntry &t = tab[base + ab];
+                    t.prob = probs[base + ab]; t.bias = bias[base + ab]; t.alias = alias[base + ab];
+                    t.tgt = (u32)tgt_orbs[2 * ab] | ((u32)tgt_orbs[2 * ab + 1] << 16);
+                }
+            }
+        }
+        P.pchb = e->upload(tab.data(), n);
+        P.pchb_pair = e->upload(pair.data(), pair.size());
+    }
     P.p_singles = p_singles; P.p_doubles = p_doubles; P.p_parallel = p_parallel; P.n_classes = n_classes;
+    {
+        const int nA = e->cfg.nocc_alpha, nB = e->cfg.nocc_beta;
+        const int par = nA * (nA - 1) / 2 + nB * (nB - 1) / 2, AB = nA * nB;
+        P.pgen_pair_par = p_parallel / (double)par;          // IEEE quotients, as pick_biased_elecs forms them per draw
+        P.pgen_pair_opp = (1.0 - p_parallel) / (double)AB;
+        P.magic_nalpha = (nA > 1) ? (u32)((1ull << 32) / (unsigned)nA) + 1u : 0u;
+    }
     std::vector<unsigned char> cls(e->cfg.nbasis);
     std::vector<int> start(n_classes + 1, 0), orbs;
     memset(P.class_mask, 0, sizeof P.class_mask);
@@ -277,7 +302,7 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
     P.class_of_spinorb = e->upload(cls.data(), cls.size());
     P.class_start = e->upload(start.data(), start.size());
     P.class_orbs = e->upload(orbs.data(), orbs.size());
-    if (!P.probs || !P.bias || !P.alias || !P.p_exch || !P.tgt_orbs) return e->fail("PCHB table upload failed");
+    if (!P.pchb || !P.pchb_pair) return e->fail("PCHB table upload failed");
     return 0;
 }
 

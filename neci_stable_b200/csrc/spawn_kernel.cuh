@@ -11,7 +11,7 @@
 //
 //   stage A  one thread per slot of a 512-slot tile: flags, energy sums, death, attempt count;
 //            parents (det, stream id, info) and the prefix sum of the attempt counts go to shared memory
-//   stage B1 one thread per attempt (binary search in the prefix array): draw the excitation.
+//   stage B1 one thread per attempt (parents expand their index into an attempt -> parent map): draw the excitation.
 //            valid doubles / lattice excitations -> queue QE {parent det, orbitals, pgen, rounding draw}
 //            PCHB singles -> queue QS {parent det, stream id, attempt}        null draws stop here
 //   stage B2 whenever QE holds >= 256 entries: parity (popc), matrix element (2 UMAT loads), spawn
@@ -30,6 +30,7 @@ namespace ng {
 #define K1_SPT 2             /* slots per thread and tile */
 #define K1_TILE (NG_BLOCK * K1_SPT)
 #define K1_QCAP (2 * NG_BLOCK)
+#define K1_MAPW 1024         /* attempts per window of the attempt -> parent map */
 
 struct SpawnBuf {
     long long *buf;          // SpawnedParts: nranks segments of seg_cap records (W words each)
@@ -73,6 +74,7 @@ template <int NW> struct K1Shared {
     u64 p_d1[(NW > 1) ? K1_TILE : 1];
     u64 p_h[K1_TILE];
     int p_off[K1_TILE + 1];
+    unsigned short p_map[K1_MAPW];   // attempt (within the current window) -> parent index in the tile
     unsigned char p_info[K1_TILE];
     // QE: generated excitations waiting for their matrix element
     u64 q_d0[K1_QCAP];
@@ -363,6 +365,19 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
 #pragma unroll
         for (int k = 0; k < W_STAGE_A; ++k) sa[k] = 0.0;
         int nsp_k[K1_SPT];
+        // all five streams of both slots are requested before anything is consumed: one HBM round trip per
+        // tile (empty slots cost bandwidth, which this kernel has to spare, not latency)
+        double ld_s[K1_SPT], ld_K[K1_SPT], ld_O[K1_SPT]; int ld_f[K1_SPT]; Det<NW> ld_d[K1_SPT];
+#pragma unroll
+        for (int kk = 0; kk < K1_SPT; ++kk) {
+            const long long slot = tile * K1_TILE + kk * NG_BLOCK + tid;
+            ld_s[kk] = 0.0; ld_K[kk] = 0.0; ld_O[kk] = 0.0; ld_f[kk] = 0; ld_d[kk].w[0] = 0; if (NW > 1) ld_d[kk].w[NW - 1] = 0;
+            if (slot < n_list) {
+                ld_s[kk] = __ldcs(&L.sgn[slot]); ld_d[kk].w[0] = __ldcs(&L.det0[slot]);
+                if (NW > 1) ld_d[kk].w[NW - 1] = __ldcs(&L.det1[slot]);
+                ld_f[kk] = __ldcs(&L.flg[slot]); ld_K[kk] = __ldcs(&L.diagH[slot]); ld_O[kk] = __ldcs(&L.offH[slot]);
+            }
+        }
 #pragma unroll
         for (int kk = 0; kk < K1_SPT; ++kk) {
             const int idx = kk * NG_BLOCK + tid;
@@ -372,12 +387,12 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
             Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
             u64 h = 0;
             if (slot < n_list) {
-                const double s = L.sgn[slot];
+                const double s = ld_s[kk];
                 if (fabs(s) >= 1.0e-12) {
-                    d = load_det<NW>(L, slot);
-                    int f = L.flg[slot];
+                    d = ld_d[kk];
+                    int f = ld_f[kk];
                     const int f0 = f;
-                    const double K = L.diagH[slot], O = L.offH[slot];
+                    const double K = ld_K[kk], O = ld_O[kk];
                     const bool core = (f & F_DETERM) != 0;
                     const int exl = excit_level(ref, d);
                     const double as = fabs(s);
@@ -458,6 +473,7 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
         }
         // exclusive prefix sum of the attempt counts over the tile (index order kk * 256 + tid)
         int run = 0;
+        int off_k[K1_SPT];
 #pragma unroll
         for (int kk = 0; kk < K1_SPT; ++kk) {
             int incl = nsp_k[kk];
@@ -468,26 +484,45 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
             int wbase = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < NG_BLOCK / 32; ++w) { const int v = S.wsum[w]; if (w < warp) wbase += v; total += v; }
-            S.p_off[kk * NG_BLOCK + tid] = run + wbase + incl - nsp_k[kk];
+            off_k[kk] = run + wbase + incl - nsp_k[kk];
+            S.p_off[kk * NG_BLOCK + tid] = off_k[kk];
             run += total;
             __syncthreads();
         }
-        if (tid == 0) S.p_off[K1_TILE] = run;
         const int T = run;
         // ---------------- stage B1 rounds, queues served at full width in between --------------------
-        for (int base = 0; base < T; base += NG_BLOCK) {
-            serve_queues<NW, SYS>(P, L, SB, A, S, NG_BLOCK, acc);       // starts with a barrier (publishes p_* and counts)
-            const int a = base + tid;
-            const bool active = a < T;
-            Det<NW> dp; dp.w[0] = 0; if (NW > 1) dp.w[NW - 1] = 0;
-            u64 h = 0; int info = 0; u32 p = 0;
-            if (active) {
-                int lo = 0, hi = K1_TILE - 1;            // last index with p_off[idx] <= a
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (S.p_off[mid] <= a) lo = mid; else hi = mid - 1; }
-                dp.w[0] = S.p_d0[lo]; if (NW > 1) dp.w[NW - 1] = S.p_d1[lo];
-                h = S.p_h[lo]; info = S.p_info[lo]; p = (u32)(a - S.p_off[lo]);
+        // Attempts are numbered 0..T-1 over the tile; each parent writes its tile index into the map entries of
+        // its own attempts (window by window), so an attempt finds its parent with one shared-memory load.
+        for (int wb = 0; wb < T; wb += K1_MAPW) {
+            const int we = min(T, wb + K1_MAPW);
+#pragma unroll
+            for (int kk = 0; kk < K1_SPT; ++kk) {
+                const int idx = kk * NG_BLOCK + tid;
+                const int lo = max(off_k[kk], wb), hi = min(off_k[kk] + nsp_k[kk], we);
+                const bool big = hi - lo > 4;
+                if (!big) for (int a = lo; a < hi; ++a) S.p_map[a - wb] = (unsigned short)idx;
+                u32 m = __ballot_sync(0xffffffffu, big);           // long ranges are filled by the whole warp
+                while (m) {
+                    const int src = __ffs(m) - 1; m &= m - 1u;
+                    const int l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
+                    const int i2 = __shfl_sync(0xffffffffu, idx, src);
+                    for (int a = l2 + lane; a < h2; a += 32) S.p_map[a - wb] = (unsigned short)i2;
+                }
             }
-            stage_generate<NW, SYS>(P, L, A, S, active, dp, h, info, p, acc);
+            for (int base = wb; base < we; base += NG_BLOCK) {
+                serve_queues<NW, SYS>(P, L, SB, A, S, NG_BLOCK, acc);       // starts with a barrier (publishes p_* and the map)
+                const int a = base + tid;
+                const bool active = a < we;
+                Det<NW> dp; dp.w[0] = 0; if (NW > 1) dp.w[NW - 1] = 0;
+                u64 h = 0; int info = 0; u32 p = 0;
+                if (active) {
+                    const int lo = S.p_map[a - wb];
+                    dp.w[0] = S.p_d0[lo]; if (NW > 1) dp.w[NW - 1] = S.p_d1[lo];
+                    h = S.p_h[lo]; info = S.p_info[lo]; p = (u32)(a - S.p_off[lo]);
+                }
+                stage_generate<NW, SYS>(P, L, A, S, active, dp, h, info, p, acc);
+            }
+            if (we < T) __syncthreads();   // the map is rewritten for the next window
         }
         __syncthreads();        // parents are overwritten by the next tile
     }
