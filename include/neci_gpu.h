@@ -75,6 +75,11 @@ enum neci_stat_index {
     NECI_ST_MAX_CYC_SPAWN,       /* max-reduced                                 */
     NECI_ST_BLOOM_SIZE_1,        /* max-reduced                                 */
     NECI_ST_BLOOM_SIZE_2,        /* max-reduced                                 */
+    NECI_ST_TAU_GAMMA_SING,      /* tau search: max |H_ij|/(pgen/pSingles) this iteration, max-reduced
+                                    (log_spawn_magnitude, tau/tau_search_conventional.F90:138-260)  */
+    NECI_ST_TAU_GAMMA_DOUB,      /* doubles without the parallel bias, max-reduced */
+    NECI_ST_TAU_GAMMA_PAR,       /* same-spin doubles, max-reduced              */
+    NECI_ST_TAU_GAMMA_OPP,       /* opposite-spin doubles, max-reduced          */
     NECI_ST_TOTPARTS,            /* after CalcHashTableStats load_balancer.fpp:738 */
     NECI_ST_NORM_PSI_SQ,         /* norm_psi_squared                            */
     NECI_ST_NORM_SEMISTOCH_SQ,
@@ -86,6 +91,14 @@ enum neci_stat_index {
     NECI_ST_NSPAWNED_MERGED,     /* unique determinants after CompressSpawnedList */
     NECI_ST_NINSERTED,           /* determinants newly added (AddNewHashDet)    */
     NECI_ST_HIGHEST_POP,         /* iHighestPop, max-reduced                    */
+    NECI_ST_TRIAL_NUMERATOR,     /* trial_numerator   fcimc_helper.F90:586-648  */
+    NECI_ST_TRIAL_DENOM,         /* trial_denom                                 */
+    NECI_ST_INIT_TRIAL_NUMERATOR,/* init_trial_numerator                        */
+    NECI_ST_INIT_TRIAL_DENOM,    /* init_trial_denom                            */
+    NECI_ST_TAU_CNT_SING,        /* spawns logged by log_spawn_magnitude per class (cnt_sing / cnt_doub / cnt_par / cnt_opp) */
+    NECI_ST_TAU_CNT_DOUB,
+    NECI_ST_TAU_CNT_PAR,
+    NECI_ST_TAU_CNT_OPP,
     NECI_ST_ERR_FLAGS,           /* bit0 spawn overflow, bit1 list overflow,
                                     bit2 death prob > 2, bit3 hash overflow     */
     NECI_ST_TIME_SPAWN_MS,       /* device time of the spawn/death pass         */
@@ -94,8 +107,8 @@ enum neci_stat_index {
     NECI_ST_TIME_DETERM_MS,
     NECI_ST_COUNT
 };
-#define NECI_ST_FIRST_MAX NECI_ST_MAX_CYC_SPAWN   /* [FIRST_MAX, BLOOM_SIZE_2] are max-reduced */
-#define NECI_ST_LAST_MAX  NECI_ST_BLOOM_SIZE_2
+#define NECI_ST_FIRST_MAX NECI_ST_MAX_CYC_SPAWN   /* [FIRST_MAX, LAST_MAX] are max-reduced */
+#define NECI_ST_LAST_MAX  NECI_ST_TAU_GAMMA_OPP
 
 /* ---- configuration: the module-level globals the hot path reads ----------
  * (filled at the end of InitFCIMCCalcPar, src/FciMCPar.F90:256)              */
@@ -120,6 +133,8 @@ typedef struct neci_gpu_config {
     int32_t t_exch;               /* tExch           sltcnd.fpp:611            */
     int32_t t_semi_stochastic;    /* tSemiStochastic                           */
     int32_t t_core_inits;         /* t_core_inits    Calc.F90:125              */
+    int32_t t_tau_search;         /* tau_search_method /= OFF: log spawn magnitudes (fcimc_pointed_fns.F90:428-434) */
+    int32_t t_consider_par_bias;  /* consider_par_bias  tau/tau_search_conventional.F90:66-117 */
     double  initiator_walk_no;    /* InitiatorWalkNo                           */
     double  real_spawn_cutoff;    /* RealSpawnCutoff                           */
     double  occupied_thresh;      /* OccupiedThresh                            */
@@ -188,6 +203,17 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
                             const int32_t *col, const double *val,
                             const int32_t *sizes, const int32_t *displs,
                             const int64_t *core_iluts);
+
+/* Trial-wavefunction estimator (init_trial_wf, src/trial_wf_gen.F90): the trial space with the trial vector
+ * (trial_space / trial_wfs) and the connected space with con_space_vecs = sum_j H_ij psiT_j, i.e. the contents of
+ * the two hash tables trial_ht / con_ht that hash_search_trial reads (src/searching.F90:182-223; ntrial_excits = 1).
+ * iluts hold nifd+1 words per determinant.  Sets flag bits 2 (trial) / 3 (connected) and current_trial_amps for
+ * the resident list and for every determinant inserted afterwards (src/load_balancer.fpp:586-611); each iteration
+ * then returns trial_numerator / trial_denom (SumEContrib, src/fcimc_helper.F90:586-648).  A determinant present
+ * in both spaces counts as trial (the trial table is searched first).                                           */
+int neci_gpu_set_trial_space(neci_gpu_engine *e, int64_t n_trial, const int64_t *trial_iluts,
+                             const double *trial_amps, int64_t n_con, const int64_t *con_iluts,
+                             const double *con_amps);
 
 /* ---- walker list transfer -------------------------------------------------- */
 /* CurrentDets(0:NIfTot, 1:n) + global_determinant_data rows diagH (= H_ii - Hii)

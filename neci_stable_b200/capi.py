@@ -19,17 +19,21 @@ ST_NAMES = [
     "NOBORN", "NODIED", "ANNIHILATED", "NOABORTED", "NOREMOVED", "SPAWNFROMSING", "ACCEPTANCES", "HFCYC",
     "NOATDOUBS", "ENUMCYC", "ENUMCYCABS", "INITSENUMCYC", "NOINITDETS", "NONONINITDETS", "NOINITWALK",
     "NONONINITWALK", "NOADDEDINITIATORS", "NVALIDEXCITS", "NINVALIDEXCITS", "BLOOM_COUNT_1", "BLOOM_COUNT_2",
-    "MAX_CYC_SPAWN", "BLOOM_SIZE_1", "BLOOM_SIZE_2", "TOTPARTS", "NORM_PSI_SQ", "NORM_SEMISTOCH_SQ",
+    "MAX_CYC_SPAWN", "BLOOM_SIZE_1", "BLOOM_SIZE_2", "TAU_GAMMA_SING", "TAU_GAMMA_DOUB", "TAU_GAMMA_PAR",
+    "TAU_GAMMA_OPP", "TOTPARTS", "NORM_PSI_SQ", "NORM_SEMISTOCH_SQ",
     "INSTNOATHF", "TOTWALKERS", "HOLESINLIST", "NSPAWNED_SENT", "NSPAWNED_RECV", "NSPAWNED_MERGED",
-    "NINSERTED", "HIGHEST_POP", "ERR_FLAGS", "TIME_SPAWN_MS", "TIME_COMM_MS", "TIME_ANNIHIL_MS",
+    "NINSERTED", "HIGHEST_POP", "TRIAL_NUMERATOR", "TRIAL_DENOM", "INIT_TRIAL_NUMERATOR", "INIT_TRIAL_DENOM",
+    "TAU_CNT_SING", "TAU_CNT_DOUB", "TAU_CNT_PAR", "TAU_CNT_OPP", "ERR_FLAGS", "TIME_SPAWN_MS", "TIME_COMM_MS", "TIME_ANNIHIL_MS",
     "TIME_DETERM_MS",
 ]
 ST = {n: i for i, n in enumerate(ST_NAMES)}
 ST_COUNT = len(ST_NAMES)
-ST_MAX_REDUCED = ("MAX_CYC_SPAWN", "BLOOM_SIZE_1", "BLOOM_SIZE_2", "HIGHEST_POP")
+ST_MAX_REDUCED = ("MAX_CYC_SPAWN", "BLOOM_SIZE_1", "BLOOM_SIZE_2", "TAU_GAMMA_SING", "TAU_GAMMA_DOUB", "TAU_GAMMA_PAR",
+                  "TAU_GAMMA_OPP", "HIGHEST_POP")
 
 SYS_FCIDUMP_PCHB, SYS_HUBBARD_RS, SYS_HUBBARD_K = 1, 2, 3
 FLAG_REMOVED, FLAG_DETERM_PARENT, FLAG_INITIATOR, FLAG_DETERMINISTIC = 0, 1, 13, 19
+FLAG_TRIAL, FLAG_CONNECTED = 2, 3
 
 
 class Config(C.Structure):
@@ -40,7 +44,8 @@ class Config(C.Structure):
         ("max_spawned", C.c_int64), ("system_type", C.c_int32), ("t_trunc_initiator", C.c_int32),
         ("t_all_real_coeff", C.c_int32), ("t_real_spawn_cutoff", C.c_int32), ("t_death_before_comms", C.c_int32),
         ("t_init_coherent_rule", C.c_int32), ("t_no_brillouin", C.c_int32), ("t_exch", C.c_int32),
-        ("t_semi_stochastic", C.c_int32), ("t_core_inits", C.c_int32), ("initiator_walk_no", C.c_double),
+        ("t_semi_stochastic", C.c_int32), ("t_core_inits", C.c_int32), ("t_tau_search", C.c_int32),
+        ("t_consider_par_bias", C.c_int32), ("initiator_walk_no", C.c_double),
         ("real_spawn_cutoff", C.c_double), ("occupied_thresh", C.c_double), ("av_mc_excits", C.c_double),
         ("hii", C.c_double), ("ecore", C.c_double), ("seed", C.c_uint64),
         ("random_orb_index", C.POINTER(C.c_int32)), ("random_hash2", C.POINTER(C.c_int32)),
@@ -153,6 +158,13 @@ class Engine:
         self._check(self._fn("set_core_space")(self.h, C.c_int64(n_local), _p(rp, C.c_int64), _p(cl, C.c_int32),
                                                 _p(vl, C.c_double), _p(sz, C.c_int32), _p(dp, C.c_int32),
                                                 _p(ci, C.c_int64)), "set_core_space")
+
+    def set_trial_space(self, trial_iluts, trial_amps, con_iluts, con_amps):
+        ti, ta = _i64(trial_iluts).reshape(-1, self.nw), _f64(trial_amps)
+        ci, ca = _i64(con_iluts).reshape(-1, self.nw), _f64(con_amps)
+        self._check(self._fn("set_trial_space")(self.h, C.c_int64(ti.shape[0]), _p(ti, C.c_int64), _p(ta, C.c_double),
+                                                 C.c_int64(ci.shape[0]), _p(ci, C.c_int64), _p(ca, C.c_double)),
+                    "set_trial_space")
 
     # -- walkers -------------------------------------------------------------------
     def upload_walkers(self, dets, gdata_diag=None, gdata_offdiag=None):

@@ -172,6 +172,7 @@ struct Params {
     int system_type;
     int t_trunc_initiator, t_all_real_coeff, t_real_spawn_cutoff, t_death_before_comms;
     int t_init_coherent_rule, t_no_brillouin, t_exch, t_semi_stochastic, t_core_inits;
+    int t_tau_search, t_consider_par_bias;
     double initiator_walk_no, real_spawn_cutoff, occupied_thresh, av_mc_excits;
     double hii, ecore;
     u64 seed;
@@ -206,6 +207,12 @@ struct Params {
     const long long *core_iluts;      // [n_core_total][nw]
     const int *core_ht;               // open addressing, entry = index + 1, 0 = empty
     u64 core_ht_mask;
+    // trial wavefunction: trial space followed by connected space (trial_ht / con_ht of src/searching.F90:182-223)
+    const long long *trial_iluts;     // [n_trial + n_con][nw]
+    const double *trial_amps;         // trial_wfs / con_space_vecs
+    const int *trial_ht;              // entry = index + 1, 0 = empty
+    u64 trial_ht_mask;
+    long long n_trial;
 };
 
 // main walker list, structure of arrays in HBM
@@ -214,6 +221,7 @@ struct WalkerList {
     double *sgn;
     int *flg;
     double *diagH, *offH;
+    double *trial_amp;       // current_trial_amps(1, :), allocated by neci_gpu_set_trial_space
     long long cap;
     // open-addressing hash table: entry = (tag32 << 32) | slot ; EMPTY / TOMB sentinels
     u64 *ht; u64 ht_mask;
@@ -232,6 +240,8 @@ enum { C_NLIST = 0, C_NFREEA, C_NFREEB, C_NTOMB, C_NHEAVY, C_NINSERT, C_ERR, C_N
 #define F_DETERM (1 << NECI_FLAG_DETERMINISTIC)
 #define F_REMOVED (1 << NECI_FLAG_REMOVED)
 #define F_DPARENT (1 << NECI_FLAG_DETERM_PARENT)
+#define F_TRIAL (1 << NECI_FLAG_TRIAL)
+#define F_CONNECTED (1 << NECI_FLAG_CONNECTED)
 // engine-internal marker bits inside spawn-record flag words (never leave the device)
 #define SF_MULTI (1ll << 40)   /* record merged from >= 2 spawns */
 #define SF_DEAD  (1ll << 41)   /* record folded into its representative */
@@ -278,6 +288,22 @@ __device__ __forceinline__ bool is_core_state(const Params &P, const Det<NW> &d)
         if (NW > 1) same = same && ((u64)__ldg(&il[NW - 1]) == d.w[NW - 1]);
         if (same) return true;
         pos = (pos + 1) & P.core_ht_mask;
+    }
+}
+// hash_search_trial (src/searching.F90:182-223): flag bit (trial / connected / none) and amplitude of a determinant
+template <int NW>
+__device__ __forceinline__ int trial_lookup(const Params &P, const Det<NW> &d, double *amp) {
+    *amp = 0.0;
+    if (!P.trial_ht) return 0;
+    u64 pos = det_hash64(d) & P.trial_ht_mask;
+    for (;;) {
+        const int e = __ldg(&P.trial_ht[pos]);
+        if (e == 0) return 0;
+        const long long *il = P.trial_iluts + (size_t)(e - 1) * NW;
+        bool same = ((u64)__ldg(&il[0]) == d.w[0]);
+        if (NW > 1) same = same && ((u64)__ldg(&il[NW - 1]) == d.w[NW - 1]);
+        if (same) { *amp = __ldg(&P.trial_amps[e - 1]); return (e - 1 < P.n_trial) ? F_TRIAL : F_CONNECTED; }
+        pos = (pos + 1) & P.trial_ht_mask;
     }
 }
 // insert a key known to be absent (unique among concurrent inserters)

@@ -199,6 +199,14 @@ __device__ __forceinline__ int det_block(const Params &P, const int *roi, Det<NW
     return (int)m + 1;
 }
 
+// TestInitiator_explicit (src/fcimc_helper.F90:1142-1243): the initiator flag of a parent for this iteration
+__device__ __forceinline__ bool parent_is_initiator(const Params &P, bool initiator, double as, int exl, bool core) {
+    const bool popInit = as > P.initiator_walk_no;
+    if (!initiator) return popInit;
+    if (exl != 0 && !(core && P.t_core_inits) && !popInit) return false;
+    return true;
+}
+
 // ---- generators ----------------------------------------------------------------
 // pick_from_cum_list over an on-the-fly cumulative list of `n` equal or unequal
 // weights is specialised per generator below.

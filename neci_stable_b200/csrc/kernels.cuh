@@ -236,8 +236,14 @@ __global__ void __launch_bounds__(NG_BLOCK) k_insert(Params P, WalkerList L, Spa
             slot = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NLIST], 1ull);
             if (slot + 1 >= L.cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 2ull); continue; }
         }
+        int ft = f;
+        if (P.trial_ht) {                                   // hash_search_trial, load_balancer.fpp:586-611
+            double amp;
+            ft = (f & ~(F_TRIAL | F_CONNECTED)) | trial_lookup<NW>(P, d, &amp);
+            L.trial_amp[slot] = amp;
+        }
         store_det<NW>(L, slot, d);
-        L.sgn[slot] = s; L.flg[slot] = f; L.diagH[slot] = hd; L.offH[slot] = ho;
+        L.sgn[slot] = s; L.flg[slot] = ft; L.diagH[slot] = hd; L.offH[slot] = ho;
         const u64 h = det_hash64(d);
         ht_insert(L, h, slot, h & L.ht_mask);
         acc[0] += 1.0;
@@ -327,7 +333,8 @@ __global__ void k_upload(Params P, WalkerList L, const long long *aos, long long
         const long long *rec = aos + (size_t)i * W;
         Det<NW> d; d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
         const double s = __longlong_as_double(rec[NW]);
-        const int f = (int)(rec[NW + 1] & 0x7fffffffll);
+        int f = (int)(rec[NW + 1] & 0x7fffffffll);
+        if (P.trial_ht) { double amp; f = (f & ~(F_TRIAL | F_CONNECTED)) | trial_lookup<NW>(P, d, &amp); L.trial_amp[i] = amp; }
         store_det<NW>(L, i, d);
         L.sgn[i] = s; L.flg[i] = f;
         const bool live = fabs(s) >= 1.0e-12 || (f & F_DETERM);
@@ -357,7 +364,7 @@ __global__ void k_core_gather(WalkerList L, const int *core_slots, long long n, 
 // fused with deterministic_annihilation (Annihilation.F90:930-963): sign += out_i.
 __global__ void __launch_bounds__(NG_BLOCK) k_determ_spmv(WalkerList L, const long long *row_ptr, const int *col, const double *val,
                                                           const double *v_full, long long n_local, long long displ,
-                                                          double tau, double diag_sft, const int *core_slots, double *out) {
+                                                          double tau, double diag_sft, const double *core_ham_diag, double *out) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -367,7 +374,10 @@ __global__ void __launch_bounds__(NG_BLOCK) k_determ_spmv(WalkerList L, const lo
         for (long long k = b + lane; k < e; k += 32) acc -= __ldg(&val[k]) * __ldg(&v_full[__ldg(&col[k])]);
         acc = warp_sum(acc);
         if (lane == 0) {
-            acc = (acc + diag_sft * v_full[i + displ]) * tau;
+            // determ_projection adds the shift; determ_projection_no_death (semi_stoch_procs.F90:285-374) adds the
+            // diagonal element back instead, because death then acts on the core determinants as well
+            const double d = core_ham_diag ? core_ham_diag[i] : diag_sft;
+            acc = (acc + d * v_full[i + displ]) * tau;
             out[i] = acc;
         }
     }
@@ -395,6 +405,53 @@ __global__ void k_core_locate(Params P, WalkerList L, const long long *iluts, lo
         if (s < 0) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 64ull); slots[i] = 0; }
         else { slots[i] = (int)s; L.flg[s] |= F_DETERM; }
     }
+}
+
+// ---- trial wavefunction -----------------------------------------------------------------
+template <int NW>
+__global__ void k_trial_ht_build(const long long *iluts, long long n, int *ht, u64 mask) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Det<NW> d; d.w[0] = (u64)iluts[i * NW]; if (NW > 1) d.w[NW - 1] = (u64)iluts[i * NW + NW - 1];
+        u64 pos = det_hash64(d) & mask;
+        while (atomicCAS(&ht[pos], 0, (int)i + 1) != 0) pos = (pos + 1) & mask;
+    }
+}
+// flags + current_trial_amps for the resident list (what init_trial_wf does for CurrentDets)
+template <int NW>
+__global__ void k_trial_locate(Params P, WalkerList L) {
+    const long long n = L.ctr[C_NLIST];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double amp;
+        const int k = trial_lookup<NW>(P, load_det<NW>(L, i), &amp);
+        L.flg[i] = (L.flg[i] & ~(F_TRIAL | F_CONNECTED)) | k;
+        L.trial_amp[i] = amp;
+    }
+}
+// trial part of SumEContrib (src/fcimc_helper.F90:586-648, ntrial_excits = 1, no qmc_trial_wf): runs before the
+// spawning pass, i.e. on the signs the walker loop sees
+template <int NW>
+__global__ void __launch_bounds__(NG_BLOCK) k_trial_energy(Params P, WalkerList L, double *partials) {
+    __shared__ double s_red[4 * 32];
+    const Det<NW> ref = ref_det<NW>(P);
+    const long long n = L.ctr[C_NLIST];
+    double acc[4] = {0, 0, 0, 0};           // numerator, denominator, initiator numerator, initiator denominator
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int f = L.flg[i];
+        if (!(f & (F_TRIAL | F_CONNECTED))) continue;
+        const double s = L.sgn[i];
+        if (fabs(s) < 1.0e-12) continue;
+        // CalcParentFlag runs before SumEContrib, so the initiator flag is this iteration's
+        bool init = (f & F_INIT) != 0;
+        if (P.t_trunc_initiator) {
+            const int exl = excit_level(ref, load_det<NW>(L, i));
+            init = parent_is_initiator(P, init, fabs(s), exl, (f & F_DETERM) != 0);
+        }
+        const double c = L.trial_amp[i] * s;
+        if (f & F_TRIAL) { acc[1] += c; if (init) acc[3] += c; }
+        else { acc[0] += c; if (init) acc[2] += c; }
+    }
+    const int idx[4] = {NECI_ST_TRIAL_NUMERATOR, NECI_ST_TRIAL_DENOM, NECI_ST_INIT_TRIAL_NUMERATOR, NECI_ST_INIT_TRIAL_DENOM};
+    block_flush_stats<4>(acc, idx, partials, s_red);
 }
 
 // ---- probes ---------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <unordered_set>
 #include <dlfcn.h>
 #include <nccl.h>
 #include "kernels.cuh"
@@ -69,7 +70,7 @@ struct neci_gpu_engine {
     std::vector<void *> owned;
     double *d_partials = nullptr, *d_stats = nullptr, *h_stats = nullptr;
     long long *h_ctr = nullptr;
-    int rows_spawn = 0, rows_heavy = 0, rows_compress = 0, rows_annih = 0, rows_insert = 0, rows_list = 0, rows_total = 0;
+    int rows_spawn = 0, rows_heavy = 0, rows_compress = 0, rows_annih = 0, rows_insert = 0, rows_list = 0, rows_trial = 0, rows_total = 0;
     int grid_spawn = 0, grid_generic = 0;
     u32 stamp = 0;
     bool need_rebuild = false;
@@ -79,7 +80,7 @@ struct neci_gpu_engine {
     // semi-stochastic
     long long n_core_local = 0, n_core_total = 0, core_displ = 0;
     long long *d_row_ptr = nullptr; int *d_col = nullptr; double *d_val = nullptr;
-    int *d_core_slots = nullptr; double *d_vpart = nullptr, *d_vfull = nullptr, *d_vout = nullptr;
+    int *d_core_slots = nullptr; double *d_vpart = nullptr, *d_vfull = nullptr, *d_vout = nullptr, *d_core_diag = nullptr;
     std::vector<int> core_sizes, core_displs;
     // staging for AoS transfers
     long long *d_aos = nullptr; size_t aos_cap = 0;
@@ -156,6 +157,8 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     P.t_real_spawn_cutoff = cfg->t_real_spawn_cutoff; P.t_death_before_comms = cfg->t_death_before_comms;
     P.t_init_coherent_rule = cfg->t_init_coherent_rule; P.t_no_brillouin = cfg->t_no_brillouin; P.t_exch = cfg->t_exch;
     P.t_semi_stochastic = cfg->t_semi_stochastic; P.t_core_inits = cfg->t_core_inits;
+    P.t_tau_search = cfg->t_tau_search; P.t_consider_par_bias = cfg->t_consider_par_bias;
+    P.p_singles = P.p_doubles = P.p_parallel = 1.0;          // lattice models: one excitation class (set_pchb overrides)
     P.initiator_walk_no = cfg->initiator_walk_no; P.real_spawn_cutoff = cfg->real_spawn_cutoff;
     P.occupied_thresh = cfg->occupied_thresh; P.av_mc_excits = cfg->av_mc_excits; P.hii = cfg->hii; P.ecore = cfg->ecore;
     P.seed = cfg->seed;
@@ -211,7 +214,8 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
         if (per_sm < 1) per_sm = 1;
         e->rows_spawn = nsm * per_sm; e->rows_heavy = nsm * per_sm;
     }
-    e->rows_total = e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih + e->rows_insert + e->rows_list;
+    e->rows_trial = e->grid_generic;
+    e->rows_total = e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih + e->rows_insert + e->rows_list + e->rows_trial;
     e->d_partials = e->alloc<double>((size_t)e->rows_total * NECI_ST_COUNT);
     e->d_stats = e->alloc<double>(NECI_ST_COUNT);
     CK(cudaMemset(e->d_partials, 0, (size_t)e->rows_total * NECI_ST_COUNT * 8));
@@ -380,6 +384,14 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
     const long long nnz = row_ptr[n_local];
     e->d_row_ptr = e->upload((const long long *)row_ptr, (size_t)n_local + 1);
     e->d_col = e->upload(col, (size_t)nnz); e->d_val = e->upload(val, (size_t)nnz);
+    {
+        // core_ham_diag (fast_determ_hamil.F90:1494-1507): the diagonal entry of every local row
+        std::vector<double> diag((size_t)n_local, 0.0);
+        for (int64_t i = 0; i < n_local; ++i)
+            for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
+                if (col[k] == i + displs[e->cfg.rank]) diag[i] = val[k];
+        e->d_core_diag = e->upload(diag.data(), diag.size());
+    }
     e->d_core_slots = e->alloc<int>((size_t)n_local);
     e->d_vpart = e->alloc<double>((size_t)n_local); e->d_vout = e->alloc<double>((size_t)n_local);
     e->d_vfull = e->alloc<double>((size_t)e->n_core_total);
@@ -407,6 +419,53 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
     CK(cudaMemcpyAsync(&errf, &e->L.ctr[C_ERR], 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (errf & 64) return e->fail("core determinant missing from the uploaded walker list");
+    return 0;
+}
+
+int neci_gpu_set_trial_space(neci_gpu_engine *e, int64_t n_trial, const int64_t *trial_iluts, const double *trial_amps,
+                             int64_t n_con, const int64_t *con_iluts, const double *con_amps) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n_trial < 0 || n_con < 0 || n_trial + n_con >= (1ll << 31) - 2) return e->fail("trial / connected space size out of range");
+    const int nw = e->nw;
+    // one table for both spaces, trial entries first; a connected determinant that is also a trial determinant is
+    // dropped (hash_search_trial looks in the trial table first, src/searching.F90:198-221)
+    struct KH { size_t operator()(const std::pair<uint64_t, uint64_t> &k) const { return (size_t)mix64(k.first ^ mix64(k.second + 0x9E3779B97F4A7C15ull)); } };
+    std::unordered_set<std::pair<uint64_t, uint64_t>, KH> seen;
+    std::vector<long long> il; std::vector<double> amp;
+    il.reserve((size_t)(n_trial + n_con) * nw); amp.reserve((size_t)(n_trial + n_con));
+    long long nt = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int64_t n = pass ? n_con : n_trial;
+        const int64_t *src = pass ? con_iluts : trial_iluts;
+        const double *a = pass ? con_amps : trial_amps;
+        for (int64_t i = 0; i < n; ++i) {
+            const std::pair<uint64_t, uint64_t> key((uint64_t)src[i * nw], nw > 1 ? (uint64_t)src[i * nw + 1] : 0ull);
+            if (!seen.insert(key).second) continue;
+            for (int w = 0; w < nw; ++w) il.push_back(src[i * nw + w]);
+            amp.push_back(a[i]);
+        }
+        if (!pass) nt = (long long)amp.size();
+    }
+    const long long n_all = (long long)amp.size();
+    long long hc = 1024; while (hc < 2 * n_all) hc <<= 1;
+    long long *d_il = e->upload(il.data(), il.size());
+    double *d_amp = e->upload(amp.data(), amp.size());
+    int *d_ht = e->alloc<int>((size_t)hc);
+    if (!e->L.trial_amp) e->L.trial_amp = e->alloc<double>((size_t)e->cfg.max_walkers);
+    if (!d_il || !d_amp || !d_ht || !e->L.trial_amp) return e->fail("trial-space upload failed");
+    CK(cudaMemsetAsync(d_ht, 0, (size_t)hc * 4, e->stream));
+    CK(cudaMemsetAsync(e->L.trial_amp, 0, (size_t)e->cfg.max_walkers * 8, e->stream));
+    if (n_all > 0) {
+        const int grid = (int)std::min<long long>(e->grid_generic, (n_all + 255) / 256);
+        if (nw == 1) k_trial_ht_build<1><<<grid, 256, 0, e->stream>>>(d_il, n_all, d_ht, (u64)hc - 1);
+        else k_trial_ht_build<2><<<grid, 256, 0, e->stream>>>(d_il, n_all, d_ht, (u64)hc - 1);
+        CK(cudaGetLastError());
+    }
+    e->P.trial_iluts = d_il; e->P.trial_amps = d_amp; e->P.trial_ht = d_ht; e->P.trial_ht_mask = (u64)hc - 1; e->P.n_trial = nt;
+    if (nw == 1) k_trial_locate<1><<<e->grid_generic, 256, 0, e->stream>>>(e->P, e->L);
+    else k_trial_locate<2><<<e->grid_generic, 256, 0, e->stream>>>(e->P, e->L);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
@@ -532,7 +591,15 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
         if (gather_core_vector(e)) return 1;
         if (e->n_core_local > 0)
             k_determ_spmv<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local * 32 + 255) / 256)), NG_BLOCK, 0, e->stream>>>(
-                e->L, e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft, e->d_core_slots, e->d_vout);
+                e->L, e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft,
+                e->cfg.t_death_before_comms ? (const double *)nullptr : (const double *)e->d_core_diag, e->d_vout);
+    }
+    if (e->P.trial_ht) {
+        // trial part of SumEContrib on the signs the walker loop sees (before death)
+        double *p_trial = e->d_partials + (size_t)(e->rows_total - e->rows_trial) * NECI_ST_COUNT;
+        e->n_launch += 1;
+        if (e->nw == 1) k_trial_energy<1><<<e->rows_trial, NG_BLOCK, 0, e->stream>>>(e->P, e->L, p_trial);
+        else k_trial_energy<2><<<e->rows_trial, NG_BLOCK, 0, e->stream>>>(e->P, e->L, p_trial);
     }
     CK(cudaEventRecord(e->ev[1], e->stream));
     e->n_launch += 2;
@@ -563,6 +630,7 @@ int neci_gpu_annihilate(neci_gpu_engine *e, const int64_t *spawned_parts, int64_
     if (begin_iteration(e)) return 1;
     if (n_spawned > e->cfg.max_spawned) return e->fail("n_spawned exceeds max_spawned");
     CK(cudaMemsetAsync(e->d_partials, 0, (size_t)(e->rows_spawn + e->rows_heavy) * NECI_ST_COUNT * 8, e->stream));
+    CK(cudaMemsetAsync(e->d_partials + (size_t)(e->rows_total - e->rows_trial) * NECI_ST_COUNT, 0, (size_t)e->rows_trial * NECI_ST_COUNT * 8, e->stream));
     CK(cudaMemcpyAsync(e->SB.recv, spawned_parts, (size_t)n_spawned * e->W * 8, cudaMemcpyHostToDevice, e->stream));
     IterArgs A; A.tau = 0; A.diag_sft = 0; A.iter = iter; A.n_recv = n_spawned; A.stamp = 0;
     for (int k = 0; k < 4; ++k) CK(cudaEventRecord(e->ev[k], e->stream));

@@ -95,6 +95,9 @@ template <int NW> struct K1Shared {
     int q_count, s_count;
     int bloom_cnt[2];
     unsigned long long bloom_max[2];
+    // tau search (log_spawn_magnitude): classes 0 singles, 1 doubles, 2 parallel doubles, 3 opposite-spin doubles
+    int tau_cnt[4];
+    unsigned long long tau_gamma[4];
 };
 
 // stochastic_round (src/lib/util_mod.fpp:182-204) with the random number drawn by the caller
@@ -148,6 +151,7 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
     bool has = false;
     double child = 0.0;
     long long cflags = 0;
+    int tau_cls = -1;
     if (active) {
         finalize_excit(d, E);
         bool cancelled = false;
@@ -160,6 +164,24 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
             const double prob = E.pgen * P.av_mc_excits;
             const double rh = spawn_helement<NW, SYS>(P, d, E);
             const double ww = (info & 1) ? -1.0 : 1.0;
+            if (P.t_tau_search) {
+                // log_spawn_magnitude (tau/tau_search_conventional.F90:138-260): gamma = |H_ij| / (prob / p_class)
+                double tp;
+                if (E.ic == 1) { tp = prob / P.p_singles; tau_cls = 0; }
+                else {
+                    tp = prob / P.p_doubles; tau_cls = 1;
+                    if (P.t_consider_par_bias) {
+                        if (((E.src1 ^ E.src2) & 1) == 0) { tp = tp / P.p_parallel; tau_cls = 2; }
+                        else { tp = tp / (1.0 - P.p_parallel); tau_cls = 3; }
+                    }
+                }
+                const double g = fabs(rh) / tp;
+                if (tau_cls < 2 && !(g > 0.0)) tau_cls = -1;       // singles / plain doubles are counted when gamma > 0
+                else {
+                    const unsigned long long gb = (unsigned long long)__double_as_longlong(g);
+                    if (gb > S.tau_gamma[tau_cls]) atomicMax(&S.tau_gamma[tau_cls], gb);
+                }
+            }
             double nSpawn = -A.tau * rh * ww / prob;
             acc.maxsp = fmax(acc.maxsp, fabs(nSpawn));
             if (P.t_all_real_coeff) {
@@ -178,6 +200,13 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
                 has = true; child = nSpawn;
                 if (P.t_trunc_initiator && (info & 2)) cflags |= F_INIT;
             }
+        }
+    }
+    if (P.t_tau_search) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const u32 m = __ballot_sync(0xffffffffu, tau_cls == c);
+            if (m && (threadIdx.x & 31) == 0) atomicAdd(&S.tau_cnt[c], __popc(m));
         }
     }
     append_spawn<NW>(P, SB, L, S.roi, has, E.detJ, child, cflags);
@@ -304,6 +333,7 @@ __device__ __forceinline__ void k1_init_shared(const Params &P, K1Shared<NW> &S)
     for (int i = threadIdx.x; i < P.nbasis; i += NG_BLOCK) S.roi[i] = P.random_orb_index[i];
     for (int i = threadIdx.x; i < (NG_BLOCK / 32) * W_COUNT; i += NG_BLOCK) (&S.wacc[0][0])[i] = 0.0;
     if (threadIdx.x == 0) { S.q_count = 0; S.s_count = 0; S.bloom_cnt[0] = S.bloom_cnt[1] = 0; S.bloom_max[0] = S.bloom_max[1] = 0ull; }
+    if (threadIdx.x < 4) { S.tau_cnt[threadIdx.x] = 0; S.tau_gamma[threadIdx.x] = 0ull; }
 }
 
 // end of kernel: per-thread attempt accumulators -> per-warp rows -> one partial row per CTA
@@ -336,6 +366,11 @@ __device__ __forceinline__ void k1_flush(const WalkerList &L, K1Shared<NW> &S, c
         row[NECI_ST_MAX_CYC_SPAWN] = t[W_MAXSP];
         row[NECI_ST_BLOOM_COUNT_1] = (double)S.bloom_cnt[0];
         row[NECI_ST_BLOOM_COUNT_2] = (double)S.bloom_cnt[1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            row[NECI_ST_TAU_GAMMA_SING + c] = __longlong_as_double((long long)S.tau_gamma[c]);
+            row[NECI_ST_TAU_CNT_SING + c] = (double)S.tau_cnt[c];
+        }
         if (with_stage_a) {
             row[NECI_ST_NODIED] = t[W_NODIED]; row[NECI_ST_NOABORTED] = t[W_ABORT]; row[NECI_ST_HFCYC] = t[W_HF];
             row[NECI_ST_NOATDOUBS] = t[W_DOUBS]; row[NECI_ST_ENUMCYC] = t[W_ENUM]; row[NECI_ST_ENUMCYCABS] = t[W_ENUMABS];
@@ -398,10 +433,9 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
                     const double as = fabs(s);
                     // CalcParentFlag / TestInitiator_explicit (fcimc_helper.F90:1036-1243)
                     if (P.t_trunc_initiator) {
-                        bool initiator = (f & F_INIT) != 0;
-                        const bool popInit = as > P.initiator_walk_no;
-                        if (!initiator) { if (popInit) { initiator = true; sa[W_ADDED] += 1.0; } }
-                        else if (exl != 0 && !(core && P.t_core_inits) && !popInit) { initiator = false; sa[W_ADDED] -= 1.0; }
+                        const bool was = (f & F_INIT) != 0;
+                        const bool initiator = parent_is_initiator(P, was, as, exl, core);
+                        if (initiator != was) sa[W_ADDED] += initiator ? 1.0 : -1.0;
                         if (initiator) { sa[W_INITD] += 1.0; sa[W_INITW] += as; f |= F_INIT; }
                         else { sa[W_NINITD] += 1.0; sa[W_NINITW] += as; f &= ~F_INIT; }
                     }
@@ -423,8 +457,11 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
                     }
                     info = (unsigned char)((s < 0.0 ? 1 : 0) | ((f & F_INIT) ? 2 : 0) | (core ? 4 : 0));
                     // walker_death / attempt_die_normal (fcimc_helper.F90:2279-2407, fcimc_pointed_fns.F90:573-705)
+                    // tDeathBeforeComms: here with t_core_die_ = .false. (FciMCPar.F90:1752-1756); otherwise
+                    // perform_death_all_walkers (fcimc_helper.F90:2253-2277) would run it after the loop for every
+                    // determinant, core ones included -- death of slot j touches only slot j, so it is fused here too
                     double news = s;
-                    if (!core) {
+                    if (!core || !P.t_death_before_comms) {
                         const double fac = A.tau * (K - A.diag_sft);
                         if (fac > 2.0) atomicOr((unsigned long long *)&L.ctr[C_ERR], 4ull);
                         double iDie;
@@ -444,7 +481,7 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
                             if (f & F_INIT) sa[W_ADDED] -= 1.0;
                             news = 0.0;
                         }
-                        if (!(fabs(news) > 1.0e-12)) {
+                        if (!(fabs(news) > 1.0e-12) && !core) {
                             if (P.t_trunc_initiator && (f & F_INIT)) sa[W_ADDED] -= 1.0;
                             ht_remove<NW>(L, d, h, slot);
                             f |= F_REMOVED;

@@ -47,6 +47,11 @@ struct orc_engine {
     struct KH { size_t operator()(const std::array<uint64_t, 2> &k) const { return (size_t)mix64(k[0] ^ mix64(k[1] + 0x9E3779B97F4A7C15ull)); } };
     std::unordered_set<std::array<uint64_t, 2>, KH> core_set;      // core_space hash (is_core_state)
     std::vector<double> partial_determ_vecs, full_determ_vecs;
+    std::vector<double> core_ham_diag;                             // fast_determ_hamil.F90:1494-1507
+    // trial wavefunction: trial_ht / con_ht (src/searching.F90:182-223) and current_trial_amps
+    bool t_trial = false;
+    std::unordered_map<std::array<uint64_t, 2>, double, KH> trial_ht, con_ht;
+    std::vector<double> current_trial_amps;
     double stats[NECI_ST_COUNT];
     std::string err;
 
@@ -166,6 +171,17 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
             if (e.test_flag(j, NECI_FLAG_INITIATOR)) e.stats[NECI_ST_INITSENUMCYC] += dE;
         }
 
+        if (e.t_trial) {                                                     // :586-648 (ntrial_excits = 1)
+            const double amp = e.current_trial_amps[j];
+            if (e.test_flag(j, NECI_FLAG_TRIAL)) {
+                e.stats[NECI_ST_TRIAL_DENOM] += amp * SignCurr;
+                if (e.test_flag(j, NECI_FLAG_INITIATOR)) e.stats[NECI_ST_INIT_TRIAL_DENOM] += amp * SignCurr;
+            } else if (e.test_flag(j, NECI_FLAG_CONNECTED)) {
+                e.stats[NECI_ST_TRIAL_NUMERATOR] += amp * SignCurr;
+                if (e.test_flag(j, NECI_FLAG_INITIATOR)) e.stats[NECI_ST_INIT_TRIAL_NUMERATOR] += amp * SignCurr;
+            }
+        }
+
         const uint64_t h = det_hash64(ilut, e.nwords);
         // decide_num_to_spawn, src/fcimc_helper.F90:2160-2174
         int WalkersToSpawn;
@@ -197,6 +213,24 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
             const double prob = E.pgen * c.av_mc_excits;
             const double rh = get_spawn_helement(S, nI, E);
             const double walkerweight = dsign(1.0, SignCurr);
+            if (c.t_tau_search) {
+                // log_spawn_magnitude, src/tau/tau_search_conventional.F90:138-260 (per-iteration maxima and counts; the
+                // host keeps the running maxima and the `enough_*` switches)
+                double tp; int cls;
+                if (E.ic == 1) { tp = prob / S.p_singles; cls = 0; }
+                else {
+                    tp = prob / S.p_doubles; cls = 1;
+                    if (c.t_consider_par_bias) {
+                        if (((E.ex[0] ^ E.ex[1]) & 1) == 0) { tp = tp / S.p_parallel; cls = 2; }
+                        else { tp = tp / (1.0 - S.p_parallel); cls = 3; }
+                    }
+                }
+                const double g = std::fabs(rh) / tp;
+                if (cls >= 2 || g > 0.0) {
+                    e.stats[NECI_ST_TAU_GAMMA_SING + cls] = std::max(e.stats[NECI_ST_TAU_GAMMA_SING + cls], g);
+                    e.stats[NECI_ST_TAU_CNT_SING + cls] += 1;
+                }
+            }
             double nSpawn = -tau * rh * walkerweight / prob;
             e.stats[NECI_ST_MAX_CYC_SPAWN] = std::max(e.stats[NECI_ST_MAX_CYC_SPAWN], std::fabs(nSpawn));
             if (c.t_all_real_coeff) {
@@ -228,8 +262,12 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
             e.stats[NECI_ST_ACCEPTANCES] += std::fabs(child);
         }
 
-        // walker_death, src/fcimc_helper.F90:2279-2407 (always in the tDeathBeforeComms position, t_core_die_ = .false.)
+        // walker_death, src/fcimc_helper.F90:2279-2407.  tDeathBeforeComms: here, with t_core_die_ = .false.
+        // (FciMCPar.F90:1752-1756).  Otherwise perform_death_all_walkers (fcimc_helper.F90:2253-2277) runs it after
+        // the loop with t_core_die = .true.; death of determinant j reads and writes nothing but j's own sign, which
+        // the loop does not touch afterwards, so running it here gives the same list.
         {
+            const bool t_core_die = !c.t_death_before_comms;
             double iDie;
             // attempt_die_normal, src/fcimc_pointed_fns.F90:573-705
             const double fac = tau * (HDiagCurr - DiagSft);
@@ -243,7 +281,7 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
                 const double r = rng.draw();
                 if (std::fabs(rat) > r) iDie += (double)std::lround(dsign(1.0, rat));
             }
-            if (tCoreDet) iDie = 0.0;
+            if (tCoreDet && !t_core_die) iDie = 0.0;
             e.stats[NECI_ST_NODIED] += std::min(iDie, std::fabs(SignCurr));
             e.stats[NECI_ST_NOBORN] += std::max(iDie - std::fabs(SignCurr), 0.0);
             double CopySign = SignCurr - (iDie * dsign(1.0, SignCurr));
@@ -273,7 +311,10 @@ void determ_projection(orc_engine &e, double tau, double DiagSft) {
     for (int64_t i = 0; i < e.n_core_local; ++i) {
         double acc = 0.0;
         for (int64_t k = e.row_ptr[i]; k < e.row_ptr[i + 1]; ++k) acc = acc - e.val[k] * e.full_determ_vecs[e.col[k]];
-        acc = acc + DiagSft * e.full_determ_vecs[i + displ];
+        // determ_projection adds the shift (:171-202); determ_projection_no_death (:285-374, used when death is not
+        // before comms, FciMCPar.F90:1778-1782) adds the diagonal element back instead: death does both later
+        if (e.cfg.t_death_before_comms) acc = acc + DiagSft * e.full_determ_vecs[i + displ];
+        else acc = acc + e.core_ham_diag[i] * e.full_determ_vecs[i + displ];
         e.partial_determ_vecs[i] = acc * tau;
     }
 }
@@ -328,6 +369,18 @@ void compress_spawned(orc_engine &e, std::vector<int64_t> &sp) {
     sp.swap(out);
 }
 
+// hash_search_trial (src/searching.F90:182-223) + the flag / amplitude update of load_balancer.fpp:596-611
+void trial_search_and_flag(orc_engine &e, int64_t pos) {
+    const std::array<uint64_t, 2> k = {e.orb(pos)[0], (e.nwords > 1) ? e.orb(pos)[1] : 0ull};
+    bool tTrial = false, tCon = false; double amp = 0.0;
+    auto it = e.trial_ht.find(k);
+    if (it != e.trial_ht.end()) { tTrial = true; amp = it->second; }
+    else { auto ic = e.con_ht.find(k); if (ic != e.con_ht.end()) { tCon = true; amp = ic->second; } }
+    e.set_flag(pos, NECI_FLAG_TRIAL, tTrial);
+    e.set_flag(pos, NECI_FLAG_CONNECTED, tCon);
+    e.current_trial_amps[pos] = amp;
+}
+
 // AddNewHashDet, src/load_balancer.fpp:514-629
 bool AddNewHashDet(orc_engine &e, const int64_t *rec, double sgn, double HDiag, double HOffDiag) {
     int64_t pos;
@@ -343,6 +396,7 @@ bool AddNewHashDet(orc_engine &e, const int64_t *rec, double sgn, double HDiag, 
     e.offdiagH[pos] = HOffDiag;
     e.set_flag(pos, NECI_FLAG_REMOVED, false);
     e.hash[e.key((const uint64_t *)rec)] = pos;
+    if (e.t_trial) trial_search_and_flag(e, pos);                            // :586-611
     return true;
 }
 
@@ -526,6 +580,10 @@ int orc_set_core_space(orc_engine *e, int64_t n_local, const int64_t *row_ptr, c
     for (int64_t i = 0; i < e->n_core_total; ++i)
         e->core_set.insert({(uint64_t)core_iluts[i * e->nwords], (e->nwords > 1) ? (uint64_t)core_iluts[i * e->nwords + 1] : 0ull});
     e->indices_of_determ_states.assign(n_local, 0);
+    e->core_ham_diag.assign(n_local, 0.0);
+    for (int64_t i = 0; i < n_local; ++i)
+        for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
+            if (col[k] == i + displs[e->cfg.rank]) e->core_ham_diag[i] = val[k];
     e->partial_determ_vecs.assign(n_local, 0.0); e->full_determ_vecs.assign(e->n_core_total, 0.0);
     return 0;
 }
@@ -540,7 +598,22 @@ int orc_upload_walkers(orc_engine *e, const int64_t *current_dets, int64_t n, co
         if (!unocc(e->sign(j)) || core) e->hash[e->key(e->orb(j))] = j;
         if (gd) e->diagH[j] = gd[j]; else e->diagH[j] = get_diagonal_matel(e->S, e->orb(j)) - e->cfg.hii;
         if (go) e->offdiagH[j] = go[j]; else e->offdiagH[j] = get_off_diagonal_matel(e->S, e->orb(j), e->ilut_ref.data());
+        if (e->t_trial) trial_search_and_flag(*e, j);
     }
+    return 0;
+}
+// init_trial_wf (src/trial_wf_gen.F90): install the two hash tables and flag the resident list
+int orc_set_trial_space(orc_engine *e, int64_t n_trial, const int64_t *trial_iluts, const double *trial_amps,
+                        int64_t n_con, const int64_t *con_iluts, const double *con_amps) {
+    const int nw = e->nwords;
+    e->trial_ht.clear(); e->con_ht.clear();
+    for (int64_t i = 0; i < n_trial; ++i)
+        e->trial_ht.insert({{(uint64_t)trial_iluts[i * nw], nw > 1 ? (uint64_t)trial_iluts[i * nw + 1] : 0ull}, trial_amps[i]});
+    for (int64_t i = 0; i < n_con; ++i)
+        e->con_ht.insert({{(uint64_t)con_iluts[i * nw], nw > 1 ? (uint64_t)con_iluts[i * nw + 1] : 0ull}, con_amps[i]});
+    e->t_trial = true;
+    e->current_trial_amps.assign((size_t)e->cfg.max_walkers, 0.0);
+    for (int64_t j = 0; j < e->TotWalkers; ++j) trial_search_and_flag(*e, j);
     return 0;
 }
 int orc_download_walkers(orc_engine *e, int64_t *current_dets, int64_t *n, double *gd, double *go) {

@@ -18,7 +18,7 @@ struct System {
     int n_spat = 0, ij_max = 0, ab_max = 0;
     std::vector<double> probs, bias, p_exch;
     std::vector<int32_t> alias, tgt_orbs;
-    double p_singles = 0, p_doubles = 0, p_parallel = 0;
+    double p_singles = 1.0, p_doubles = 1.0, p_parallel = 1.0;   // lattice models: a single excitation class
     int n_classes = 0;
     std::vector<int32_t> class_of_spinorb;          // 0-based class id per spin orbital (index orb-1)
     std::vector<std::vector<int32_t>> class_orbs;   // members of each class, ascending

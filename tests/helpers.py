@@ -210,3 +210,23 @@ class DistOracle:
         self.dist.all_gather_object(everything, out)
         recv = np.concatenate([everything[s][self.rank] for s in range(self.world)])   # ordered by source rank
         return o.annihilate_phase(recv, it)
+
+
+def build_trial_space(engine, system, dets, trial_dets):
+    """Host-side mirror of init_trial_wf (src/trial_wf_gen.F90): diagonalise H in the trial space, take the lowest
+    eigenvector as the trial vector, and form the connected space = determinants of `dets` outside the trial space
+    with con_space_vecs_i = sum_j H_ij psiT_j != 0.  Returns (trial_iluts, trial_amps, con_iluts, con_amps,
+    trial_energy) with H the full Hamiltonian (ECore included)."""
+    tset = {tuple(d) for d in trial_dets}
+    rest = [d for d in dets if tuple(d) not in tset]
+    Ht = hamiltonian_matrix(engine, system, trial_dets)
+    w, v = np.linalg.eigh(Ht)
+    psi = v[:, 0]
+    il_t = np.array([system.ilut(d) for d in trial_dets], dtype=np.int64).reshape(len(trial_dets), system.nw)
+    il_r = np.array([system.ilut(d) for d in rest], dtype=np.int64).reshape(len(rest), system.nw)
+    nr, nt = len(rest), len(trial_dets)
+    I = np.repeat(np.arange(nr), nt); J = np.tile(np.arange(nt), nr)
+    Hct = engine.probe_helement(il_r[I], il_t[J]).reshape(nr, nt)
+    con = Hct @ psi
+    keep = np.abs(con) > 0
+    return il_t, psi.copy(), il_r[keep], con[keep], float(w[0])

@@ -8,12 +8,12 @@ from neci_stable_b200 import capi, host, driver
 from neci_stable_b200.capi import ST
 
 
-def _setup(system, nranks=1):
+def _setup(system, nranks=1, **kw):
     hii = driver.diag_energy(system, system.ref_orbs)
     orcs = []
     for r in range(nranks):
         o, params = helpers.make_pair(system, hii, max_walkers=20000, max_spawned=20000, nranks=nranks, rank=r,
-                                      semi_stochastic=True, seed=3)
+                                      semi_stochastic=True, seed=3, **kw)
         orcs.append(o)
     return hii, orcs
 
@@ -70,3 +70,30 @@ def test_core_space_split_over_ranks_matches_single_rank():
         results[nr] = helpers.canon(d, nw=s.nw)
     assert np.array_equal(results[1][0], results[3][0])
     assert np.allclose(results[1][1], results[3][1], rtol=1e-13, atol=1e-13)
+
+
+def test_no_death_projection_plus_death_equals_fused_projection():
+    """tDeathBeforeComms = .false. (the reference's default with real coefficients): determ_projection_no_death
+    (src/semi_stoch_procs.F90:285-374) leaves the diagonal and the shift to the death step, which then also acts on
+    the core determinants (perform_death_all_walkers, src/fcimc_helper.F90:2253-2277).  With the whole space as
+    core space both orders are the same exact power iteration."""
+    s = host.hubbard_k_system(2, 2, nel=4, U=2.0)
+    out = {}
+    for dbc in (True, False):
+        hii, (o,) = _setup(s, all_real_coeff=True, death_before_comms=dbc, initiator=False)
+        dets = helpers.all_dets(s)
+        dets, sizes, displs, per_rank, H = helpers.build_core_space(o, s, dets, hii)
+        rng = np.random.default_rng(1)
+        amp = rng.normal(size=len(dets)) + 3.0
+        flags = (1 << capi.FLAG_DETERMINISTIC) | (1 << capi.FLAG_INITIATOR)
+        o.upload_walkers(np.array([host.record(s, d, float(a), flags) for d, a in zip(dets, amp)]))
+        c = per_rank[0]
+        o.set_core_space(c["row_ptr"], c["col"], c["val"], sizes, displs, c["iluts"])
+        v = amp.copy()
+        for it in range(1, 6):
+            o.iterate(0.02, 0.3, it)
+            v = v - 0.02 * (H @ v - 0.3 * v)
+        d, _, _ = o.download_walkers()
+        out[dbc] = host.signs_of(d, s.nw).copy()
+        assert np.allclose(out[dbc], v, rtol=1e-12, atol=1e-12)
+    assert np.allclose(out[True], out[False], rtol=1e-12, atol=1e-12)

@@ -1,0 +1,86 @@
+"""Trial-wavefunction estimator (SumEContrib, src/fcimc_helper.F90:586-648; hash_search_trial,
+src/searching.F90:182-223; AddNewHashDet, src/load_balancer.fpp:586-611) and the tau-search hooks
+(log_spawn_magnitude, src/tau/tau_search_conventional.F90:138-260) on the oracle."""
+import numpy as np
+
+import helpers
+from neci_stable_b200 import capi, host, driver
+from neci_stable_b200.capi import ST
+
+
+def _exact_ground_state(o, s):
+    dets = helpers.all_dets(s)
+    H = helpers.hamiltonian_matrix(o, s, dets)
+    w, v = np.linalg.eigh(H)
+    psi = v[:, 0] * np.sign(v[np.argmax(np.abs(v[:, 0])), 0])
+    return dets, H, w[0], psi
+
+
+def test_trial_estimator_is_exact_on_the_exact_wavefunction():
+    """With walkers = the exact ground state, E = E_T + numerator / denominator = <psi|H|psiT> / <psi|psiT> = E0
+    for ANY trial space, because the connected-space amplitudes are (H psiT)_i."""
+    s = host.hubbard_k_system(2, 2, nel=4, U=2.0)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=20000, max_spawned=20000, all_real_coeff=True, initiator=False, seed=3)
+    dets, H, e0, psi = _exact_ground_state(o, s)
+    order = np.argsort(-np.abs(psi))
+    trial = [dets[i] for i in order[:5]]
+    ti, ta, ci, ca, e_t = helpers.build_trial_space(o, s, dets, trial)
+    recs = np.array([host.record(s, d, 1000.0 * a) for d, a in zip(dets, psi) if abs(a) > 1e-14])
+    o.upload_walkers(recs)
+    o.set_trial_space(ti, ta, ci, ca)
+    st = o.iterate(1e-4, 0.0, 1)
+    e = e_t + st[ST["TRIAL_NUMERATOR"]] / st[ST["TRIAL_DENOM"]]
+    assert abs(e - e0) < 1e-10, (e, e0)
+    # flags: trial and connected are exclusive, and every trial determinant present is flagged
+    d, _, _ = o.download_walkers()
+    f = d[:, s.nw + 1]
+    assert not np.any(((f >> capi.FLAG_TRIAL) & 1) & ((f >> capi.FLAG_CONNECTED) & 1))
+    assert int(((f >> capi.FLAG_TRIAL) & 1).sum()) == len(trial)
+
+
+def test_new_determinants_get_trial_flags_and_amplitudes():
+    """Start from the reference only: every determinant inserted later must be looked up in the two tables."""
+    s = host.hubbard_k_system(2, 2, nel=4, U=2.0)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=20000, max_spawned=20000, initiator=False, seed=5)
+    dets, H, e0, psi = _exact_ground_state(o, s)
+    order = np.argsort(-np.abs(psi))
+    trial = [dets[i] for i in order[:4]]
+    ti, ta, ci, ca, e_t = helpers.build_trial_space(o, s, dets, trial)
+    o.upload_walkers(host.record(s, s.ref_orbs, 200.0).reshape(1, -1))
+    o.set_trial_space(ti, ta, ci, ca)
+    for it in range(1, 60):
+        st = o.iterate(0.02, 0.0, it)
+    d, _, _ = o.download_walkers()
+    c = helpers.canon(d, nw=s.nw)
+    tset = {tuple(int(x) for x in r) for r in ti}; cset = {tuple(int(x) for x in r) for r in ci}
+    assert c[0].shape[0] > 10
+    for orb, fl in zip(c[0], c[2]):
+        key = tuple(int(x) for x in orb)
+        assert bool((fl >> capi.FLAG_TRIAL) & 1) == (key in tset)
+        assert bool((fl >> capi.FLAG_CONNECTED) & 1) == (key in cset and key not in tset)
+    assert st[ST["TRIAL_DENOM"]] != 0.0 and st[ST["TRIAL_NUMERATOR"]] != 0.0
+
+
+def test_tau_search_gamma_bounds_every_spawn():
+    """gamma_class = max |H_ij| / (pgen / p_class), so the largest spawn of the run is tau * max(gamma_class / p_class)
+    (the tau search picks tau = p_class / gamma_class to cap it at one walker); the per-class counts add up to the
+    valid excitations."""
+    s = host.random_fcidump_system(6, 6, sparse=0.9, sparse_t=0.9, seed=3)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=50000, max_spawned=50000, tau_search=True, seed=9)
+    o.upload_walkers(host.record(s, s.ref_orbs, 500.0, 1 << capi.FLAG_INITIATOR).reshape(1, -1))
+    g = np.zeros(4); cnt = np.zeros(4); valid = 0; max_spawn = 0.0
+    tau = 0.001
+    for it in range(1, 30):
+        st = o.iterate(tau, 0.0, it)
+        g = np.maximum(g, st[ST["TAU_GAMMA_SING"]:ST["TAU_GAMMA_SING"] + 4])
+        cnt += st[ST["TAU_CNT_SING"]:ST["TAU_CNT_SING"] + 4]
+        valid += st[ST["NVALIDEXCITS"]]; max_spawn = max(max_spawn, st[ST["MAX_CYC_SPAWN"]])
+    assert g[1] == 0 and cnt[1] == 0                 # PCHB uses the parallel / opposite split
+    assert g[0] > 0 and g[2] > 0 and g[3] > 0
+    assert cnt[2] + cnt[3] + cnt[0] <= valid and cnt[2] + cnt[3] > 0.5 * valid
+    t = s.tables["pchb"]
+    bound = tau * max(g[0] / t["p_singles"], g[2] / (t["p_doubles"] * t["p_parallel"]), g[3] / (t["p_doubles"] * (1 - t["p_parallel"])))
+    assert abs(max_spawn - bound) <= 1e-12 * bound, (max_spawn, bound)
