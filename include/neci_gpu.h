@@ -227,6 +227,15 @@ int neci_gpu_upload_walkers(neci_gpu_engine *e, const int64_t *current_dets, int
 int neci_gpu_download_walkers(neci_gpu_engine *e, int64_t *current_dets, int64_t *n,
                               double *gdata_diag, double *gdata_offdiag);
 
+/* POPSFILE gather (WriteToPopsfileParOneArr / write_pops_det, src/Popsfile.F90:1622-1949,2054-2107;
+ * write_walkers, src/hdf5_popsfile.F90:756): the occupied determinants with |sign| > min_weight
+ * (binarypops_min_weight), compacted on the device in list order.  A record is det(0:NIfD), sign, flags -- the
+ * body of one binary POPSFILE record -- followed in gdata_* by its global_determinant_data rows.  Call with
+ * dets_out = NULL to get the count first.  Reading a POPSFILE back is neci_gpu_upload_walkers (it re-hashes and,
+ * without gdata, recomputes H_ii / H_0i as ReadFromPopsfile's caller does).                                   */
+int neci_gpu_download_occupied(neci_gpu_engine *e, double min_weight, int64_t *dets_out, int64_t *n,
+                               double *gdata_diag, double *gdata_offdiag);
+
 /* ---- the hot path ----------------------------------------------------------- */
 /* One FCIQMC iteration == the body of PerformFCIMCycPar.  stats_out receives
  * NECI_ST_COUNT doubles: this rank's accumulators.                            */

@@ -185,6 +185,17 @@ class Engine:
                                                   _p(go, C.c_double) if with_gdata else None), "download_walkers")
         return dets[:nn], gd[:nn], go[:nn]
 
+    def download_occupied(self, min_weight=0.0):
+        """Occupied determinants (|sign| > min_weight) compacted in list order + their gdata rows: the POPSFILE body."""
+        n = C.c_int64(0)
+        self._check(self._fn("download_occupied")(self.h, C.c_double(min_weight), None, C.byref(n), None, None), "download_occupied")
+        nn = n.value
+        dets = np.zeros((max(nn, 1), self.W), dtype=np.int64); gd = np.zeros(max(nn, 1)); go = np.zeros(max(nn, 1))
+        if nn:
+            self._check(self._fn("download_occupied")(self.h, C.c_double(min_weight), _p(dets, C.c_int64), C.byref(n),
+                                                       _p(gd, C.c_double), _p(go, C.c_double)), "download_occupied")
+        return dets[:nn], gd[:nn], go[:nn]
+
     # -- hot path ---------------------------------------------------------------------
     def iterate(self, tau, diag_sft, it):
         st = np.zeros(ST_COUNT)

@@ -354,6 +354,77 @@ __global__ void k_download(WalkerList L, long long *aos, long long n, int W) {
     }
 }
 
+// ---- POPSFILE gather (write_pops_det, src/Popsfile.F90:2054-2107) ----------------------
+// The binary POPSFILE record of a determinant is det(0:NIfD), sign, flags [, gdata]: the AoS ilut itself.  Occupied
+// determinants above binarypops_min_weight are compacted in slot order: per-CTA counts over fixed chunks, a scan
+// of the counts by one CTA, then the ordered write.
+#define NG_POPS_CHUNK 4096
+__global__ void __launch_bounds__(256) k_pops_count(WalkerList L, double min_weight, int *chunk_cnt) {
+    __shared__ int s_c;
+    const long long n = L.ctr[C_NLIST];
+    const long long nchunks = (n + NG_POPS_CHUNK - 1) / NG_POPS_CHUNK;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        if (threadIdx.x == 0) s_c = 0;
+        __syncthreads();
+        int mine = 0;
+        for (int k = threadIdx.x; k < NG_POPS_CHUNK; k += 256) {
+            const long long i = c * NG_POPS_CHUNK + k;
+            if (i < n && fabs(L.sgn[i]) > min_weight) ++mine;
+        }
+        atomicAdd(&s_c, mine);
+        __syncthreads();
+        if (threadIdx.x == 0) chunk_cnt[c] = s_c;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) k_pops_scan(WalkerList L, int *chunk_cnt, long long *total) {
+    __shared__ long long s_part[1024];
+    const long long n = L.ctr[C_NLIST];
+    const long long nchunks = (n + NG_POPS_CHUNK - 1) / NG_POPS_CHUNK;
+    const long long per = (nchunks + 1023) / 1024, lo = threadIdx.x * per, hi = min(nchunks, lo + per);
+    long long sum = 0;
+    for (long long c = lo; c < hi; ++c) sum += chunk_cnt[c];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { long long run = 0; for (int t = 0; t < 1024; ++t) { const long long v = s_part[t]; s_part[t] = run; run += v; } *total = run; }
+    __syncthreads();
+    long long run = s_part[threadIdx.x];
+    // counts -> exclusive offsets in place (the list holds < 2^31 slots, neci_gpu_init checks max_walkers)
+    for (long long c = lo; c < hi; ++c) { const int v = chunk_cnt[c]; chunk_cnt[c] = (int)run; run += v; }
+}
+template <int NW>
+__global__ void __launch_bounds__(256) k_pops_write(WalkerList L, double min_weight, const int *chunk_off, long long *aos, int W,
+                                                    double *gd, double *go) {
+    __shared__ int s_w[8];
+    const long long n = L.ctr[C_NLIST];
+    const long long nchunks = (n + NG_POPS_CHUNK - 1) / NG_POPS_CHUNK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        long long base = chunk_off[c];
+        for (int k0 = 0; k0 < NG_POPS_CHUNK; k0 += 256) {
+            const long long i = c * NG_POPS_CHUNK + k0 + threadIdx.x;
+            const bool keep = i < n && fabs(L.sgn[i]) > min_weight;
+            const u32 m = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_w[warp] = __popc(m);
+            __syncthreads();
+            int woff = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const int v = s_w[w]; if (w < warp) woff += v; tot += v; }
+            if (keep) {
+                const long long o = base + woff + __popc(m & ((1u << lane) - 1u));
+                long long *rec = aos + (size_t)o * W;
+                rec[0] = (long long)L.det0[i]; if (NW > 1) rec[NW - 1] = (long long)L.det1[i];
+                rec[NW] = __double_as_longlong(L.sgn[i]);
+                rec[NW + 1] = (long long)(L.flg[i] & ~F_REMOVED);
+                if (gd) gd[o] = L.diagH[i];
+                if (go) go[o] = L.offH[i];
+            }
+            base += tot;
+            __syncthreads();
+        }
+    }
+}
+
 // ---- semi-stochastic ---------------------------------------------------------------
 // gather of partial_determ_vecs (FciMCPar.F90:1387-1411)
 __global__ void k_core_gather(WalkerList L, const int *core_slots, long long n, double *v_part) {

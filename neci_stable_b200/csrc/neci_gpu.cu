@@ -373,6 +373,40 @@ int neci_gpu_download_walkers(neci_gpu_engine *e, int64_t *current_dets, int64_t
     return 0;
 }
 
+int neci_gpu_download_occupied(neci_gpu_engine *e, double min_weight, int64_t *dets_out, int64_t *n_out, double *gd, double *go) {
+    CK(cudaSetDevice(e->cfg.device));
+    long long n = 0;
+    CK(cudaMemcpyAsync(&n, &e->L.ctr[C_NLIST], 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const long long nchunks = std::max<long long>(1, (n + NG_POPS_CHUNK - 1) / NG_POPS_CHUNK);
+    int *d_cnt = dalloc<int>((size_t)nchunks); long long *d_tot = dalloc<long long>(1);
+    if (!d_cnt || !d_tot) return e->fail("allocation failed");
+    const int grid = (int)std::min<long long>(e->grid_generic, nchunks);
+    e->n_launch += 2;
+    k_pops_count<<<grid, 256, 0, e->stream>>>(e->L, min_weight, d_cnt);
+    k_pops_scan<<<1, 1024, 0, e->stream>>>(e->L, d_cnt, d_tot);
+    long long tot = 0;
+    CK(cudaMemcpyAsync(&tot, d_tot, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (n_out) *n_out = tot;
+    int rc = 0;
+    if (dets_out && tot > 0) {
+        // staging: records, then the two gdata rows
+        if (ensure_aos(e, (size_t)tot * e->W + 2 * (size_t)tot)) { cudaFree(d_cnt); cudaFree(d_tot); return 1; }
+        double *dgd = gd ? (double *)(e->d_aos + (size_t)tot * e->W) : nullptr;
+        double *dgo = go ? (double *)(e->d_aos + (size_t)tot * e->W + tot) : nullptr;
+        e->n_launch += 1;
+        if (e->nw == 1) k_pops_write<1><<<grid, 256, 0, e->stream>>>(e->L, min_weight, d_cnt, e->d_aos, e->W, dgd, dgo);
+        else k_pops_write<2><<<grid, 256, 0, e->stream>>>(e->L, min_weight, d_cnt, e->d_aos, e->W, dgd, dgo);
+        cudaMemcpyAsync(dets_out, e->d_aos, (size_t)tot * e->W * 8, cudaMemcpyDeviceToHost, e->stream);
+        if (gd) cudaMemcpyAsync(gd, dgd, (size_t)tot * 8, cudaMemcpyDeviceToHost, e->stream);
+        if (go) cudaMemcpyAsync(go, dgo, (size_t)tot * 8, cudaMemcpyDeviceToHost, e->stream);
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = e->fail("download_occupied failed");
+    }
+    cudaFree(d_cnt); cudaFree(d_tot);
+    return rc;
+}
+
 // -------------------------------------------------------------------------------
 int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *row_ptr, const int32_t *col,
                             const double *val, const int32_t *sizes, const int32_t *displs, const int64_t *core_iluts) {

@@ -229,3 +229,33 @@ def record(system, orbs, sign, flags=0):
 
 def signs_of(dets, nw):
     return np.ascontiguousarray(dets[:, nw]).view(np.float64)
+
+
+# ---- POPSFILE body (text form) ---------------------------------------------------------------
+def popsfile_lines(dets, gd=None, go=None, nw=1):
+    """The determinant lines of a text POPSFILE as write_pops_det formats them (src/Popsfile.F90:2095-2107):
+    (i24) per orbital word, (f30.8) sign, (i24) flags, (f30.8) per gdata row."""
+    dets = np.asarray(dets, dtype=np.int64).reshape(-1, nw + 2)
+    sg = signs_of(dets, nw)
+    out = []
+    for j in range(dets.shape[0]):
+        line = "".join("%24d" % int(dets[j, k]) for k in range(nw)) + "%30.8f" % sg[j] + "%24d" % int(dets[j, nw + 1])
+        if gd is not None:
+            line += "%30.8f" % gd[j] + "%30.8f" % go[j]
+        out.append(line)
+    return out
+
+
+def parse_popsfile_lines(lines, nw=1):
+    """Inverse of popsfile_lines: CurrentDets records (and gdata rows if present) for neci_gpu_upload_walkers."""
+    dets = np.zeros((len(lines), nw + 2), dtype=np.int64)
+    gd, go = [], []
+    for j, ln in enumerate(lines):
+        t = ln.split()
+        for k in range(nw):
+            dets[j, k] = int(t[k])
+        dets[j, nw] = np.array([float(t[nw])], dtype=np.float64).view(np.int64)[0]
+        dets[j, nw + 1] = int(t[nw + 1])
+        if len(t) > nw + 2:
+            gd.append(float(t[nw + 2])); go.append(float(t[nw + 3]))
+    return dets, (np.array(gd) if gd else None), (np.array(go) if go else None)

@@ -624,6 +624,23 @@ int orc_download_walkers(orc_engine *e, int64_t *current_dets, int64_t *n, doubl
     return 0;
 }
 
+// write_pops_det, src/Popsfile.F90:2054-2107: occupied determinants above binarypops_min_weight, in list order
+int orc_download_occupied(orc_engine *e, double min_weight, int64_t *dets_out, int64_t *n, double *gd, double *go) {
+    int64_t k = 0;
+    for (int64_t j = 0; j < e->TotWalkers; ++j) {
+        if (!(std::fabs(e->sign(j)) > min_weight)) continue;
+        if (dets_out) {
+            std::memcpy(dets_out + (size_t)k * e->W, &e->dets[(size_t)j * e->W], (size_t)e->W * 8);
+            dets_out[(size_t)k * e->W + e->nwords + 1] &= ~(int64_t)1;
+            if (gd) gd[k] = e->diagH[j];
+            if (go) go[k] = e->offdiagH[j];
+        }
+        ++k;
+    }
+    if (n) *n = k;
+    return 0;
+}
+
 // ---- phases, exposed so that a test harness can play the role of the exchange
 int orc_spawn_phase(orc_engine *e, double tau, double diag_sft, int64_t iter) {
     spawn_phase(*e, tau, diag_sft, iter);
