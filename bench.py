@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--cpu-sample-walkers", type=float, default=2.0e6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="spawn exchange for N > 1: push kernel over NVLink peer memory (default) or NCCL send/recv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -305,6 +307,10 @@ def main():
         uid = [eng.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.nccl_init(uid[0])
+        if args.exchange == "p2p":
+            hs = [None] * world
+            dist.all_gather_object(hs, eng.p2p_handle())
+            eng.p2p_open(hs)
 
     keep = None
     if world > 1:
@@ -453,6 +459,7 @@ def main():
                        "walkers_total_end": walkers_end, "determinants_total_end": dets_end, "tau": tau, "shift": sft,
                        "initiator": True, "attempts_per_step": attempts / args.steps,
                        "spawned_per_step": spawned / args.steps, "partition": "DetermineDetNode hash" if world > 1 else "single rank",
+                       "exchange": ("push kernel over NVLink peer memory" if args.exchange == "p2p" else "NCCL send/recv") if world > 1 else "none",
                        "l2": "inputs larger than L2 (walker list %.0f MB per GPU > 126 MB)" % (dets_end / world * (8 * system.nw + 28) / 1e6),
                        "wall_ms_per_step": 1e3 * wall / args.steps},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -260,6 +260,14 @@ int neci_gpu_annihilate(neci_gpu_engine *e, const int64_t *spawned_parts, int64_
 int neci_gpu_nccl_unique_id(uint8_t id_out[128]);
 int neci_gpu_nccl_init(neci_gpu_engine *e, const uint8_t id[128]);
 
+/* Spawn exchange over NVLink peer memory instead of NCCL send/recv (same result, no host round trip for the
+ * counts): every rank creates its inbox and returns a 64-byte CUDA IPC handle; the host all-gathers the handles
+ * (MPIAllGather / torch.distributed) and every rank opens its peers' inboxes.  One process per GPU, all on one
+ * NVLink/NVSwitch box.  When this has been called neci_gpu_iterate / neci_gpu_rebalance use it for
+ * SendProcNewParts (src/Annihilation.F90:150-247); otherwise they use the NCCL communicator.                  */
+int neci_gpu_p2p_handle(neci_gpu_engine *e, uint8_t handle_out[64]);
+int neci_gpu_p2p_open(neci_gpu_engine *e, const uint8_t *handles /* nranks x 64 bytes, rank order */);
+
 /* adjust_load_balance (src/load_balancer.fpp:178-351): install a new
  * LoadBalanceMapping and move the determinants of the listed blocks
  * (collective over all ranks).                                                */

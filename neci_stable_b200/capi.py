@@ -256,6 +256,17 @@ class Engine:
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._check(self._fn("nccl_init")(self.h, buf), "nccl_init")
 
+    def p2p_handle(self):
+        buf = (C.c_uint8 * 64)()
+        self._check(self._fn("p2p_handle")(self.h, buf), "p2p_handle")
+        return bytes(buf)
+
+    def p2p_open(self, handles):
+        """handles: list of the 64-byte IPC handles of all ranks, in rank order."""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self._fn("p2p_open")(self.h, buf), "p2p_open")
+
     def block_populations(self):
         out = np.zeros(self.cfg.balance_blocks)
         self._check(self._fn("block_populations")(self.h, _p(out, C.c_double)), "block_populations")

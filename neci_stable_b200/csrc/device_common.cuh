@@ -125,6 +125,20 @@ template <int NW> __device__ __forceinline__ u64 det_hash64(const Det<NW> &d) {
     return h;
 }
 
+// One Philox4x32-10 block.  Deliberately NOT inlined: a stream is drawn from at a dozen places of the spawning
+// kernel and twelve inlined copies (~70 instructions each) pushed its code past the instruction cache.
+__device__ __noinline__ uint4 philox4x32_10(u32 v0, u32 v1, u32 v2, u32 v3, u32 q0, u32 q1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        if (r) { q0 += 0x9E3779B9u; q1 += 0xBB67AE85u; }
+        const u32 hi0 = __umulhi(0xD2511F53u, v0), lo0 = 0xD2511F53u * v0;
+        const u32 hi1 = __umulhi(0xCD9E8D57u, v2), lo1 = 0xCD9E8D57u * v2;
+        const u32 n0 = hi1 ^ v1 ^ q0, n2 = hi0 ^ v3 ^ q1;
+        v0 = n0; v1 = lo1; v2 = n2; v3 = lo0;
+    }
+    return make_uint4(v0, v1, v2, v3);
+}
+
 struct Stream {
     u32 c0, c1, c2, c3, k0, k1;
     u32 x2, x3;        // second half of the current block
@@ -137,18 +151,9 @@ struct Stream {
     __device__ __forceinline__ double draw() {
         u32 a, b;
         if ((next & 1) == 0 || !have) {
-            u32 v0 = c0, v1 = c1, v2 = c2, v3 = c3 | (u32)(next >> 1);
-            u32 q0 = k0, q1 = k1;
-#pragma unroll
-            for (int r = 0; r < 10; ++r) {
-                if (r) { q0 += 0x9E3779B9u; q1 += 0xBB67AE85u; }
-                const u32 hi0 = __umulhi(0xD2511F53u, v0), lo0 = 0xD2511F53u * v0;
-                const u32 hi1 = __umulhi(0xCD9E8D57u, v2), lo1 = 0xCD9E8D57u * v2;
-                const u32 n0 = hi1 ^ v1 ^ q0, n2 = hi0 ^ v3 ^ q1;
-                v0 = n0; v1 = lo1; v2 = n2; v3 = lo0;
-            }
-            if ((next & 1) == 0) { a = v0; b = v1; } else { a = v2; b = v3; }
-            x2 = v2; x3 = v3; have = true;
+            const uint4 v = philox4x32_10(c0, c1, c2, c3 | (u32)(next >> 1), k0, k1);
+            if ((next & 1) == 0) { a = v.x; b = v.y; } else { a = v.z; b = v.w; }
+            x2 = v.z; x3 = v.w; have = true;
         } else { a = x2; b = x3; }
         ++next;
         const u64 u = (u64)a | ((u64)b << 32);
@@ -169,6 +174,7 @@ struct Params {
     // configuration scalars
     int nel, nbasis, nocc_alpha, nocc_beta;
     int nranks, rank, balance_blocks;
+    u64 bb_magic;                     // floor((2^64 - 1) / balance_blocks), see det_block
     int system_type;
     int t_trunc_initiator, t_all_real_coeff, t_real_spawn_cutoff, t_death_before_comms;
     int t_init_coherent_rule, t_no_brillouin, t_exch, t_semi_stochastic, t_core_inits;
@@ -182,6 +188,8 @@ struct Params {
     const int *lb_mapping;            // [balance_blocks]
     // FCIDUMP
     const double *umat, *tmat;
+    const double *jmat, *kmat;        // <ij|ij>, <ij|ji> over spatial orbitals, [n_spat_sys][n_spat_sys] (sltcnd_0)
+    int n_spat_sys;
     // PCHB: the host's probs / bias / alias / tgtOrbs arrays interleaved into one 32-byte entry per
     // (ij, sampler, ab) so that an alias draw costs one L2 sector (two when the alias is taken)
     int n_spat, ij_max, ab_max;

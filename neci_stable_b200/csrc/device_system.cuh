@@ -59,21 +59,27 @@ template <int NW>
 __device__ __forceinline__ bool parity_single(const Det<NW> &d, int s, int t) { return count_between(d, s, t) & 1; }
 
 // ---- Slater-Condon -----------------------------------------------------------
+// sltcnd_0 (src/sltcnd.fpp:585-622) in the reference's summation order.  The Coulomb <ij|ij> and exchange <ij|ji>
+// integrals come from two n_spat x n_spat tables gathered from UMAT at upload (same values, so the sums are
+// bit-identical to indexing UMAT through UMatInd) -- they stay in L1 and need one multiply-add of index math.
 template <int NW>
 __device__ double sltcnd_0(const Params &P, const Det<NW> &d) {
     double hel_sing = 0.0, hel_doub = 0.0, hel_tmp = 0.0;
+    const int ns = P.n_spat_sys;
     Det<NW> a = d;
     while (det_any(a)) {
         const int oi = pop_lowest(a);
         hel_sing += tmat_el(P, oi, oi);
         const int idi = gtid(oi);
+        const double *jrow = P.jmat + (size_t)(idi - 1) * ns - 1;
+        const double *krow = P.kmat + (size_t)(idi - 1) * ns - 1;
         Det<NW> b = a;
         double s = 0.0;
         while (det_any(b)) {
             const int oj = pop_lowest(b);
             const int idj = gtid(oj);
-            s += umat_el(P, idi, idj, idi, idj);
-            if (P.t_exch && ((oi ^ oj) & 1) == 0) hel_tmp -= umat_el(P, idi, idj, idj, idi);
+            s += __ldg(&jrow[idj]);
+            if (P.t_exch && ((oi ^ oj) & 1) == 0) hel_tmp -= __ldg(&krow[idj]);
         }
         hel_doub += s;
     }
@@ -194,9 +200,14 @@ __device__ __forceinline__ int det_block(const Params &P, const int *roi, Det<NW
         acc = 1099511628211ull * acc + (u64)(long long)(roi[o - 1] * i);
         ++i;
     }
-    long long m = (long long)acc % (long long)P.balance_blocks;
-    if (m < 0) m = -m;
-    return (int)m + 1;
+    // abs(mod(acc, balance_blocks)) with Fortran's truncating mod == |acc| mod balance_blocks; the 64-bit remainder
+    // is taken with the host-computed reciprocal floor((2^64 - 1) / balance_blocks): q is the quotient or one less
+    const u64 a = ((long long)acc < 0) ? (0ull - acc) : acc;       // |INT64_MIN| = 2^63 fits
+    const u64 B = (u64)P.balance_blocks;
+    const u64 q = __umul64hi(a, P.bb_magic);
+    u64 r = a - q * B;
+    if (r >= B) r -= B;
+    return (int)r + 1;
 }
 
 // TestInitiator_explicit (src/fcimc_helper.F90:1142-1243): the initiator flag of a parent for this iteration
@@ -301,6 +312,7 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
     // construct_class_counts + CheckIfSingleExcits via class masks (no per-thread arrays: the count of
     // empty orbitals of a class is recomputed from the masks in the constant bank when needed)
     int ElecsWNoExcits = 0;
+#pragma unroll 1
     for (int c = 0; c < P.n_classes; ++c) {
         int o = __popcll(d.w[0] & P.class_mask[c][0]);
         int t = __popcll(P.class_mask[c][0]);

@@ -82,7 +82,8 @@ __global__ void k_merge_free_finish(WalkerList L) {
 
 // ---- CompressSpawnedList as an in-place hash merge ------------------------------
 __device__ __forceinline__ long long recv_count(const SpawnBuf &SB, const IterArgs &A) {
-    return (A.n_recv >= 0) ? A.n_recv : (long long)SB.cnt[0];
+    if (A.n_recv >= 0) return A.n_recv;
+    return (A.n_recv == -1) ? (long long)SB.cnt[0] : (long long)*SB.n_recv_dev;
 }
 __device__ __forceinline__ u64 sht_mask_for(long long n, u64 cap) {
     u64 m = 1024;
@@ -615,8 +616,85 @@ __global__ void __launch_bounds__(NG_BLOCK) k_rebalance_pack(Params P, WalkerLis
 }
 // receiver side: every received record is a new determinant here
 __global__ void k_iota_insert(WalkerList L, SpawnBuf SB, long long n) {
+    if (n < 0) n = (long long)*SB.n_recv_dev;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) SB.ins_idx[i] = (int)i;
     if (blockIdx.x == 0 && threadIdx.x == 0) L.ctr[C_NINSERT] = n;
+}
+
+// ---- spawn exchange over NVLink peer memory (SendProcNewParts, src/Annihilation.F90:150-247) -----------------
+// Every rank owns an inbox that its peers can write: per parity (two exchanges can be in flight) and per source rank
+// one segment of seg_cap records plus one 64-bit mailbox word (sequence number << 32 | record count).
+//   k_push    copies this rank's per-destination segments of SpawnedParts straight into the destinations' inbox
+//             segments (coalesced remote stores), then -- once every CTA has fenced its stores -- posts the mailboxes
+//   k_wait    spins until all sources have posted this exchange's sequence number; leaves counts / offsets on the device
+//   k_gather  compacts the inbox segments into the contiguous receive list (source-rank order, like MPI_Alltoallv)
+// No host synchronisation and no count round trip: the kernels that follow read the count from device memory.
+struct PeerBox {
+    long long **peer_seg;            // [nranks] base of rank r's inbox segments  (device array of peer pointers)
+    unsigned long long **peer_mail;  // [nranks] base of rank r's mailboxes
+    long long *my_seg;               // this rank's inbox segments [2][nranks][seg_cap][W]
+    unsigned long long *my_mail;     // this rank's mailboxes [2][nranks]
+    unsigned long long *cnt_in;      // [nranks] counts of the current exchange, [nranks .. 2 nranks) offsets
+    unsigned int *ticket;
+};
+__global__ void __launch_bounds__(256) k_push(SpawnBuf SB, PeerBox X, int nranks, int rank, unsigned int seq) {
+    __shared__ bool s_last;
+    const int par = (int)(seq & 1u);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gstride = (long long)gridDim.x * blockDim.x;
+    for (int dst = 0; dst < nranks; ++dst) {
+        long long n = (long long)SB.cnt[dst]; if (n > SB.seg_cap) n = SB.seg_cap;      // overflow is reported by K1
+        const long long words = n * SB.W;
+        const long long *src = SB.buf + (size_t)dst * SB.seg_cap * SB.W;
+        long long *out = X.peer_seg[dst] + ((size_t)par * nranks + rank) * SB.seg_cap * SB.W;
+        for (long long i = gtid; i < words; i += gstride) out[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(X.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if ((int)threadIdx.x < nranks) {
+            const int dst = threadIdx.x;
+            unsigned long long n = SB.cnt[dst]; if (n > (unsigned long long)SB.seg_cap) n = (unsigned long long)SB.seg_cap;
+            volatile unsigned long long *mail = X.peer_mail[dst] + (size_t)par * nranks + rank;
+            *mail = ((unsigned long long)seq << 32) | n;
+        }
+        if (threadIdx.x == 0) *X.ticket = 0u;
+        __threadfence_system();
+    }
+}
+__global__ void k_wait(WalkerList L, SpawnBuf SB, PeerBox X, int nranks, unsigned int seq, long long timeout_cycles) {
+    __shared__ unsigned long long s_cnt[64];
+    const int par = (int)(seq & 1u);
+    if ((int)threadIdx.x < nranks) {
+        volatile unsigned long long *mail = X.my_mail + (size_t)par * nranks + threadIdx.x;
+        const long long t0 = clock64();
+        unsigned long long v = *mail;
+        while ((unsigned int)(v >> 32) != seq) {
+            if (clock64() - t0 > timeout_cycles) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 256ull); v = (unsigned long long)seq << 32; break; }
+            __nanosleep(200);
+            v = *mail;
+        }
+        s_cnt[threadIdx.x] = v & 0xFFFFFFFFull;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int s = 0; s < nranks; ++s) { X.cnt_in[s] = s_cnt[s]; X.cnt_in[nranks + s] = run; run += s_cnt[s]; }
+        *SB.n_recv_dev = run;
+    }
+}
+__global__ void __launch_bounds__(256) k_gather(SpawnBuf SB, PeerBox X, int nranks, unsigned int seq) {
+    const int par = (int)(seq & 1u);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gstride = (long long)gridDim.x * blockDim.x;
+    for (int s = 0; s < nranks; ++s) {
+        const long long words = (long long)X.cnt_in[s] * SB.W;
+        const long long *src = X.my_seg + ((size_t)par * nranks + s) * SB.seg_cap * SB.W;
+        long long *out = SB.recv + (size_t)X.cnt_in[nranks + s] * SB.W;
+        for (long long i = gtid; i < words; i += gstride) out[i] = src[i];
+    }
 }
 
 }  // namespace ng

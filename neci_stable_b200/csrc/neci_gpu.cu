@@ -87,6 +87,12 @@ struct neci_gpu_engine {
     // multi-rank
     ncclComm_t comm = nullptr;
     unsigned long long *d_cnt_all = nullptr, *h_cnt_all = nullptr;
+    // peer-memory exchange (NVLink): this rank's inbox block, the peers' mapped inboxes
+    bool p2p = false;
+    void *p2p_block = nullptr; size_t p2p_seg_words = 0;
+    std::vector<void *> p2p_peer_base;
+    PeerBox X;
+    unsigned int xseq = 0;
 
     int fail(const char *fmt, ...) {
         char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -153,6 +159,8 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     Params &P = e->P; memset(&P, 0, sizeof P);
     P.nel = cfg->nel; P.nbasis = cfg->nbasis; P.nocc_alpha = cfg->nocc_alpha; P.nocc_beta = cfg->nocc_beta;
     P.nranks = cfg->nranks; P.rank = cfg->rank; P.balance_blocks = cfg->balance_blocks; P.system_type = cfg->system_type;
+    if (cfg->balance_blocks < 1) return e->fail("balance_blocks must be >= 1");
+    P.bb_magic = ~0ull / (u64)cfg->balance_blocks;
     P.t_trunc_initiator = cfg->t_trunc_initiator; P.t_all_real_coeff = cfg->t_all_real_coeff;
     P.t_real_spawn_cutoff = cfg->t_real_spawn_cutoff; P.t_death_before_comms = cfg->t_death_before_comms;
     P.t_init_coherent_rule = cfg->t_init_coherent_rule; P.t_no_brillouin = cfg->t_no_brillouin; P.t_exch = cfg->t_exch;
@@ -234,6 +242,9 @@ int neci_gpu_finalize(neci_gpu_engine *e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (size_t r = 0; r < e->p2p_peer_base.size(); ++r)
+        if ((int)r != e->cfg.rank && e->p2p_peer_base[r]) cudaIpcCloseMemHandle(e->p2p_peer_base[r]);
+    if (e->p2p_block) cudaFree(e->p2p_block);
     for (void *p : e->owned) cudaFree(p);
     if (e->d_aos) cudaFree(e->d_aos);
     if (e->h_stats) cudaFreeHost(e->h_stats);
@@ -252,7 +263,21 @@ int neci_gpu_set_system_fcidump(neci_gpu_engine *e, const double *umat, int64_t 
     if (n_umat >= (1ll << 31)) return e->fail("n_umat must be < 2^31 (32-bit UMatInd arithmetic on the device)");
     e->P.umat = e->upload(umat, (size_t)n_umat);
     e->P.tmat = e->upload(tmat2d, (size_t)e->cfg.nbasis * e->cfg.nbasis);
-    if (!e->P.umat || !e->P.tmat) return e->fail("integral upload failed");
+    {
+        // Coulomb / exchange tables for the diagonal element: J(i,j) = UMAT(UMatInd(i,j,i,j)), K(i,j) = UMAT(UMatInd(i,j,j,i))
+        const int ns = e->cfg.nbasis / 2;
+        auto tri = [](long long a, long long b) { return a > b ? a * (a - 1) / 2 + b : b * (b - 1) / 2 + a; };
+        auto ind = [&](int i, int j, int k, int l) { return tri(tri(i, k), tri(j, l)); };
+        std::vector<double> J((size_t)ns * ns), K((size_t)ns * ns);
+        for (int i = 1; i <= ns; ++i)
+            for (int j = 1; j <= ns; ++j) {
+                const long long a = ind(i, j, i, j), b = ind(i, j, j, i);
+                if (a > n_umat || b > n_umat) return e->fail("UMAT too short for %d spatial orbitals", ns);
+                J[(size_t)(i - 1) * ns + j - 1] = umat[a - 1]; K[(size_t)(i - 1) * ns + j - 1] = umat[b - 1];
+            }
+        e->P.jmat = e->upload(J.data(), J.size()); e->P.kmat = e->upload(K.data(), K.size()); e->P.n_spat_sys = ns;
+    }
+    if (!e->P.umat || !e->P.tmat || !e->P.jmat || !e->P.kmat) return e->fail("integral upload failed");
     return 0;
 }
 
@@ -528,6 +553,25 @@ static int exchange_spawns(neci_gpu_engine *e, long long *n_recv_out) {
     return 0;
 }
 
+// the same exchange over NVLink peer memory: push kernel + mailbox wait + local compaction, no host round trip
+static int exchange_spawns_p2p(neci_gpu_engine *e) {
+    const int nr = e->cfg.nranks;
+    e->xseq += 1;
+    e->n_launch += 3;
+    k_push<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->cfg.rank, e->xseq);
+    k_wait<<<1, 64, 0, e->stream>>>(e->L, e->SB, e->X, nr, e->xseq, 10000000000ll /* ~5 s of SM clocks */);
+    k_gather<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->xseq);
+    CK(cudaGetLastError());
+    return 0;
+}
+// spawn exchange of one iteration: leaves the received records contiguous in SB.recv and the count in A.n_recv
+// (>= 0: known on the host; -2: on the device)
+static int exchange(neci_gpu_engine *e, long long *n_recv) {
+    if (e->p2p) { *n_recv = -2; return exchange_spawns_p2p(e); }
+    if (!e->comm) return e->fail("nranks > 1 but neither neci_gpu_nccl_init nor neci_gpu_p2p_open was called");
+    return exchange_spawns(e, n_recv);
+}
+
 static int gather_core_vector(neci_gpu_engine *e) {
     const int nr = e->cfg.nranks;
     if (nr == 1) {
@@ -594,6 +638,7 @@ static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
     if (errf & 4) return e->fail("death probability > 2: algorithm unstable, reduce tau");
     if (errf & 16) return e->fail("excitation generator could not find an excitation after 250 attempts");
     if (errf & 32) return e->fail("heavy-determinant queue overflow");
+    if (errf & 256) return e->fail("peer-memory spawn exchange timed out waiting for another rank");
     return 0;
 }
 
@@ -643,9 +688,8 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[2], e->stream));
     if (e->cfg.nranks > 1) {
-        if (!e->comm) return e->fail("nranks > 1 but neci_gpu_nccl_init was not called");
         long long nrecv = 0;
-        if (exchange_spawns(e, &nrecv)) return 1;
+        if (exchange(e, &nrecv)) return 1;
         A.n_recv = nrecv;
     }
     CK(cudaEventRecord(e->ev[3], e->stream));
@@ -694,6 +738,54 @@ int neci_gpu_nccl_init(neci_gpu_engine *e, const uint8_t id_in[128]) {
     return 0;
 }
 
+// ---- peer-memory exchange wiring -----------------------------------------------------
+int neci_gpu_p2p_handle(neci_gpu_engine *e, uint8_t handle_out[64]) {
+    CK(cudaSetDevice(e->cfg.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    const int nr = e->cfg.nranks;
+    if (!e->p2p_block) {
+        e->p2p_seg_words = (size_t)2 * nr * e->SB.seg_cap * e->W;
+        const size_t bytes = e->p2p_seg_words * 8 + (size_t)2 * nr * 8;
+        CK(cudaMalloc(&e->p2p_block, bytes));
+        CK(cudaMemset(e->p2p_block, 0, bytes));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->p2p_block));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+int neci_gpu_p2p_open(neci_gpu_engine *e, const uint8_t *handles) {
+    CK(cudaSetDevice(e->cfg.device));
+    const int nr = e->cfg.nranks;
+    if (!e->p2p_block) return e->fail("neci_gpu_p2p_handle must be called first");
+    e->p2p_peer_base.assign(nr, nullptr);
+    std::vector<long long *> seg(nr); std::vector<unsigned long long *> mail(nr);
+    for (int r = 0; r < nr; ++r) {
+        void *base = e->p2p_block;
+        if (r != e->cfg.rank) {
+            cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)r * 64, 64);
+            cudaError_t rc = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+            if (rc != cudaSuccess) return e->fail("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(rc));
+        }
+        e->p2p_peer_base[r] = base;
+        seg[r] = (long long *)base; mail[r] = (unsigned long long *)((long long *)base + e->p2p_seg_words);
+    }
+    e->X.peer_seg = e->upload(seg.data(), seg.size());
+    e->X.peer_mail = e->upload(mail.data(), mail.size());
+    e->X.my_seg = seg[e->cfg.rank]; e->X.my_mail = mail[e->cfg.rank];
+    e->X.cnt_in = e->alloc<unsigned long long>((size_t)2 * nr);
+    e->X.ticket = e->alloc<unsigned int>(1);
+    e->SB.n_recv_dev = e->alloc<unsigned long long>(1);
+    if (!e->X.peer_seg || !e->X.peer_mail || !e->X.cnt_in || !e->X.ticket || !e->SB.n_recv_dev) return e->fail("allocation failed");
+    CK(cudaMemset(e->X.ticket, 0, 4));
+    CK(cudaMemset(e->SB.n_recv_dev, 0, 8));
+    CK(cudaDeviceSynchronize());
+    e->xseq = 0;
+    e->p2p = true;
+    return 0;
+}
+
 int neci_gpu_block_populations(neci_gpu_engine *e, double *block_parts) {
     CK(cudaSetDevice(e->cfg.device));
     const int nb = e->cfg.balance_blocks;
@@ -720,7 +812,6 @@ int neci_gpu_rebalance(neci_gpu_engine *e, const int32_t *new_mapping) {
         if (new_mapping[b] < 0 || new_mapping[b] >= e->cfg.nranks) return e->fail("new_mapping[%d] = %d out of range", b, new_mapping[b]);
     CK(cudaMemcpyAsync((void *)e->P.lb_mapping, new_mapping, (size_t)e->cfg.balance_blocks * 4, cudaMemcpyHostToDevice, e->stream));
     if (e->cfg.nranks == 1) { CK(cudaStreamSynchronize(e->stream)); return 0; }
-    if (!e->comm) return e->fail("nranks > 1 but neci_gpu_nccl_init was not called");
     if (begin_iteration(e)) return 1;
     const int g = e->grid_generic;
     e->n_launch += 5;
@@ -728,7 +819,7 @@ int neci_gpu_rebalance(neci_gpu_engine *e, const int32_t *new_mapping) {
     else k_rebalance_pack<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
     CK(cudaGetLastError());
     long long nrecv = 0;
-    if (exchange_spawns(e, &nrecv)) return 1;
+    if (exchange(e, &nrecv)) return 1;
     k_merge_free<<<64, 256, 0, e->stream>>>(e->L);
     k_merge_free_finish<<<1, 1, 0, e->stream>>>(e->L);
     k_iota_insert<<<g, 256, 0, e->stream>>>(e->L, e->SB, nrecv);

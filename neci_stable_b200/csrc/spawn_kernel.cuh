@@ -43,12 +43,13 @@ struct SpawnBuf {
     int *ins_idx;            // records that become new determinants
     long long *heavy;        // (slot, nspawn) pairs
     long long heavy_cap;
+    unsigned long long *n_recv_dev;   // received-record count left on the device by the peer-memory exchange
 };
 
 struct IterArgs {
     double tau, diag_sft;
     long long iter;
-    long long n_recv;        // < 0: read SB.cnt[0] on the device (single rank)
+    long long n_recv;        // -1: read SB.cnt[0] on the device (single rank); -2: read *SB.n_recv_dev (peer-memory exchange)
     u32 stamp;
 };
 
@@ -330,6 +331,7 @@ __device__ __forceinline__ void serve_queues(const Params &P, const WalkerList &
 
 template <int NW>
 __device__ __forceinline__ void k1_init_shared(const Params &P, K1Shared<NW> &S) {
+#pragma unroll 1
     for (int i = threadIdx.x; i < P.nbasis; i += NG_BLOCK) S.roi[i] = P.random_orb_index[i];
     for (int i = threadIdx.x; i < (NG_BLOCK / 32) * W_COUNT; i += NG_BLOCK) (&S.wacc[0][0])[i] = 0.0;
     if (threadIdx.x == 0) { S.q_count = 0; S.s_count = 0; S.bloom_cnt[0] = S.bloom_cnt[1] = 0; S.bloom_max[0] = S.bloom_max[1] = 0ull; }
@@ -383,23 +385,17 @@ __device__ __forceinline__ void k1_flush(const WalkerList &L, K1Shared<NW> &S, c
     }
 }
 
+// stage A of one tile: flags, energy sums, death and attempt counts of 512 slots; leaves the parents and the
+// exclusive prefix sum of their attempt counts in shared memory.  nsp_k / off_k: this thread's two slots.
 template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
-    extern __shared__ __align__(16) unsigned char k1_smem[];
-    K1Shared<NW> &S = *reinterpret_cast<K1Shared<NW> *>(k1_smem);
+__device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L, const SpawnBuf &SB, const IterArgs &A, K1Shared<NW> &S,
+                                           const Det<NW> &ref, long long tile, long long n_list, int (&nsp_k)[K1_SPT],
+                                           int (&off_k)[K1_SPT], int &T) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    k1_init_shared<NW>(P, S);
-    AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
-    const Det<NW> ref = ref_det<NW>(P);
-    const long long n_list = L.ctr[C_NLIST];
-    __syncthreads();
-
-    for (long long tile = blockIdx.x; tile * K1_TILE < n_list; tile += gridDim.x) {
         // ---------------- stage A: one thread per slot --------------------------------------------
         double sa[W_STAGE_A];
 #pragma unroll
         for (int k = 0; k < W_STAGE_A; ++k) sa[k] = 0.0;
-        int nsp_k[K1_SPT];
         // all five streams of both slots are requested before anything is consumed: one HBM round trip per
         // tile (empty slots cost bandwidth, which this kernel has to spare, not latency)
         double ld_s[K1_SPT], ld_K[K1_SPT], ld_O[K1_SPT]; int ld_f[K1_SPT]; Det<NW> ld_d[K1_SPT];
@@ -510,7 +506,6 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
         }
         // exclusive prefix sum of the attempt counts over the tile (index order kk * 256 + tid)
         int run = 0;
-        int off_k[K1_SPT];
 #pragma unroll
         for (int kk = 0; kk < K1_SPT; ++kk) {
             int incl = nsp_k[kk];
@@ -526,42 +521,83 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
             run += total;
             __syncthreads();
         }
-        const int T = run;
-        // ---------------- stage B1 rounds, queues served at full width in between --------------------
-        // Attempts are numbered 0..T-1 over the tile; each parent writes its tile index into the map entries of
-        // its own attempts (window by window), so an attempt finds its parent with one shared-memory load.
-        for (int wb = 0; wb < T; wb += K1_MAPW) {
-            const int we = min(T, wb + K1_MAPW);
+        T = run;
+}
+
+template <int NW, int SYS>
+__global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
+    extern __shared__ __align__(16) unsigned char k1_smem[];
+    K1Shared<NW> &S = *reinterpret_cast<K1Shared<NW> *>(k1_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    k1_init_shared<NW>(P, S);
+    AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
+    const Det<NW> ref = ref_det<NW>(P);
+    const long long n_list = L.ctr[C_NLIST];
+    __syncthreads();
+
+    // One loop of rounds: a round serves the queues (single call site: the evaluate / singles stages are the bulk
+    // of the kernel's code, and instruction-cache misses showed up in the profile when they were inlined twice) and
+    // then generates up to 256 attempts of the current window of the current tile.  When the tile's attempts are
+    // exhausted the next tile is loaded (stage A); after the last tile one draining round ends the kernel.
+    long long tile = blockIdx.x;
+    int T = 0, wb = 0, we = 0, base = 0;
+    int nsp_k[K1_SPT], off_k[K1_SPT];
 #pragma unroll
-            for (int kk = 0; kk < K1_SPT; ++kk) {
-                const int idx = kk * NG_BLOCK + tid;
-                const int lo = max(off_k[kk], wb), hi = min(off_k[kk] + nsp_k[kk], we);
-                const bool big = hi - lo > 4;
-                if (!big) for (int a = lo; a < hi; ++a) S.p_map[a - wb] = (unsigned short)idx;
-                u32 m = __ballot_sync(0xffffffffu, big);           // long ranges are filled by the whole warp
-                while (m) {
-                    const int src = __ffs(m) - 1; m &= m - 1u;
-                    const int l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
-                    const int i2 = __shfl_sync(0xffffffffu, idx, src);
-                    for (int a = l2 + lane; a < h2; a += 32) S.p_map[a - wb] = (unsigned short)i2;
+    for (int kk = 0; kk < K1_SPT; ++kk) { nsp_k[kk] = 0; off_k[kk] = 0; }
+    for (;;) {
+        bool drain = false;
+        if (base >= we) {
+            bool new_window = false;
+            if (we >= T) {
+                if (tile * K1_TILE >= n_list) drain = true;
+                else {
+                    __syncthreads();        // parents and the map are overwritten
+                    k1_stage_a<NW, SYS>(P, L, SB, A, S, ref, tile, n_list, nsp_k, off_k, T);
+                    tile += gridDim.x;
+                    wb = 0; we = 0; base = 0;
+                    if (T == 0) continue;
+                    new_window = true;
+                }
+            } else { __syncthreads(); wb = we; new_window = true; }
+            if (new_window) {
+                // Attempts are numbered 0..T-1 over the tile; each parent writes its tile index into the map
+                // entries of its own attempts (window by window): an attempt finds its parent with one load.
+                we = min(T, wb + K1_MAPW); base = wb;
+#pragma unroll
+                for (int kk = 0; kk < K1_SPT; ++kk) {
+                    const int idx = kk * NG_BLOCK + tid;
+                    const int lo = max(off_k[kk], wb), hi = min(off_k[kk] + nsp_k[kk], we);
+                    const bool big = hi - lo > 4;
+                    if (!big) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) if (lo + u < hi) S.p_map[lo + u - wb] = (unsigned short)idx;
+                    }
+                    u32 m = __ballot_sync(0xffffffffu, big);           // long ranges are filled by the whole warp
+                    while (m) {
+                        const int src = __ffs(m) - 1; m &= m - 1u;
+                        const int l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
+                        const int i2 = __shfl_sync(0xffffffffu, idx, src);
+#pragma unroll 1
+                        for (int a = l2 + lane; a < h2; a += 32) S.p_map[a - wb] = (unsigned short)i2;
+                    }
                 }
             }
-            for (int base = wb; base < we; base += NG_BLOCK) {
-                serve_queues<NW, SYS>(P, L, SB, A, S, NG_BLOCK, acc);       // starts with a barrier (publishes p_* and the map)
-                const int a = base + tid;
-                const bool active = a < we;
-                Det<NW> dp; dp.w[0] = 0; if (NW > 1) dp.w[NW - 1] = 0;
-                u64 h = 0; int info = 0; u32 p = 0;
-                if (active) {
-                    const int lo = S.p_map[a - wb];
-                    dp.w[0] = S.p_d0[lo]; if (NW > 1) dp.w[NW - 1] = S.p_d1[lo];
-                    h = S.p_h[lo]; info = S.p_info[lo]; p = (u32)(a - S.p_off[lo]);
-                }
-                stage_generate<NW, SYS>(P, L, A, S, active, dp, h, info, p, acc);
-            }
-            if (we < T) __syncthreads();   // the map is rewritten for the next window
         }
-        __syncthreads();        // parents are overwritten by the next tile
+        serve_queues<NW, SYS>(P, L, SB, A, S, drain ? 1 : NG_BLOCK, acc);   // starts with a barrier (publishes p_* and the map)
+        if (drain) break;
+        {
+            const int a = base + tid;
+            const bool active = a < we;
+            Det<NW> dp; dp.w[0] = 0; if (NW > 1) dp.w[NW - 1] = 0;
+            u64 h = 0; int info = 0; u32 p = 0;
+            if (active) {
+                const int lo = S.p_map[a - wb];
+                dp.w[0] = S.p_d0[lo]; if (NW > 1) dp.w[NW - 1] = S.p_d1[lo];
+                h = S.p_h[lo]; info = S.p_info[lo]; p = (u32)(a - S.p_off[lo]);
+            }
+            stage_generate<NW, SYS>(P, L, A, S, active, dp, h, info, p, acc);
+            base += NG_BLOCK;
+        }
     }
     serve_queues<NW, SYS>(P, L, SB, A, S, 1, acc);
     k1_flush<NW>(L, S, acc, partials, true);

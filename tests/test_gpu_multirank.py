@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N_ITER = 30
 
 
-def _worker(rank, world, port, out_dir, name, semi, balance=False):
+def _worker(rank, world, port, out_dir, name, semi, balance=False, p2p=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -26,13 +26,24 @@ def _worker(rank, world, port, out_dir, name, semi, balance=False):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     system, tau = T.get_system(name)
     hii = driver.diag_energy(system, system.ref_orbs)
+    mapping = None
+    if balance:
+        # a deliberately lopsided LoadBalanceMapping (two thirds of the blocks on rank 0) so that the greedy
+        # balancer has blocks to move whatever the world size
+        nb = 10 * world
+        mapping = np.array([0 if b < (2 * nb) // 3 else 1 + (b % (world - 1)) for b in range(nb)], dtype=np.int32)
     params = host.make_params(system, hii, max_walkers=400000, max_spawned=400000, nranks=world, rank=rank, device=rank,
-                              seed=11, blocks_per_rank=10, semi_stochastic=semi)
+                              seed=11, blocks_per_rank=10, semi_stochastic=semi, mapping=mapping)
     gpu = capi.Engine(params)
     system.apply(gpu)
     uid = [gpu.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     gpu.nccl_init(uid[0])
+    if p2p:
+        # spawn exchange over NVLink peer memory: all-gather of the CUDA IPC handles of the inboxes
+        hs = [None] * world
+        dist.all_gather_object(hs, gpu.p2p_handle())
+        gpu.p2p_open(hs)
     # the oracle world lives on rank 0
     orcs = []
     if rank == 0:
@@ -131,10 +142,10 @@ def _worker(rank, world, port, out_dir, name, semi, balance=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,semi,balance", [("pchb_14e28o", False, False), ("hub_k_6x6_2words", False, False),
-                                               ("hub_rs_4x4", False, True), ("pchb_14e28o", False, True),
-                                               ("pchb_6e6o", True, False)])
-def test_multi_gpu_matches_oracle_world(tmp_path, name, semi, balance):
+@pytest.mark.parametrize("name,semi,balance,p2p", [("pchb_14e28o", False, False, False), ("hub_k_6x6_2words", False, False, True),
+                                                   ("hub_rs_4x4", False, True, False), ("pchb_14e28o", False, True, True),
+                                                   ("pchb_6e6o", True, False, True), ("pchb_14e28o", False, False, True)])
+def test_multi_gpu_matches_oracle_world(tmp_path, name, semi, balance, p2p):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -142,7 +153,7 @@ def test_multi_gpu_matches_oracle_world(tmp_path, name, semi, balance):
         pytest.skip("needs >= 2 GPUs")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, str(tmp_path), name, semi, balance), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), name, semi, balance, p2p), nprocs=world, join=True)
     res = open(os.path.join(tmp_path, "result.txt")).read()
     assert res.startswith("OK"), res
     assert int(res.split()[1]) > 100
