@@ -47,7 +47,8 @@ __device__ __forceinline__ void block_flush_stats(const double (&acc)[N], const 
 
 // final reduction over the partial rows of all kernels: one CTA per statistic, fixed
 // (launch-independent) summation tree, so results are reproducible run to run
-__global__ void __launch_bounds__(256) k_reduce_stats(const double *partials, int nrows, double *stats) {
+template <int NW>
+__global__ void __launch_bounds__(256) k_reduce_stats(Params P, WalkerList L, SpawnBuf SB, const double *partials, int nrows, double *stats) {
     __shared__ double s_v[256];
     const int k = blockIdx.x;
     const bool is_max = (k >= NECI_ST_FIRST_MAX && k <= NECI_ST_LAST_MAX) || k == NECI_ST_HIGHEST_POP;
@@ -62,7 +63,20 @@ __global__ void __launch_bounds__(256) k_reduce_stats(const double *partials, in
         if (threadIdx.x < o) s_v[threadIdx.x] = is_max ? fmax(s_v[threadIdx.x], s_v[threadIdx.x + o]) : s_v[threadIdx.x] + s_v[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) stats[k] = s_v[0];
+    if (threadIdx.x != 0) return;
+    double out = s_v[0];
+    // the statistics that are counters or look-ups rather than sums over the list (InstNoatHF, list length, holes, ...)
+    if (k == NECI_ST_INSTNOATHF) {
+        const Det<NW> ref = ref_det<NW>(P);
+        const long long slot = ht_lookup<NW>(L, ref, det_hash64(ref));
+        out = (slot >= 0) ? L.sgn[slot] : 0.0;
+    } else if (k == NECI_ST_TOTWALKERS) out = (double)min(L.ctr[C_NLIST], L.cap - 1);
+    else if (k == NECI_ST_HOLESINLIST) { long long a = L.ctr[C_NFREEA]; if (a < 0) a = 0; out = (double)(a + L.ctr[C_NFREEB]); }
+    else if (k == NECI_ST_NSPAWNED_SENT) { unsigned long long sent = 0; for (int r = 0; r < P.nranks; ++r) sent += SB.cnt[r]; out = (double)sent; }
+    else if (k == NECI_ST_ERR_FLAGS) out = (double)L.ctr[C_ERR];
+    else if (k == NECI_ST_BLOOM_SIZE_1) out = __longlong_as_double(L.ctr[C_COUNT - 2]);
+    else if (k == NECI_ST_BLOOM_SIZE_2) out = __longlong_as_double(L.ctr[C_COUNT - 1]);
+    stats[k] = out;
 }
 
 // freeB -> freeA, clamp counters (runs with one block per 256 entries + 1)
@@ -92,8 +106,18 @@ __device__ __forceinline__ u64 sht_mask_for(long long n, u64 cap) {
 }
 
 template <int NW>
-__global__ void __launch_bounds__(NG_BLOCK) k_compress(Params P, SpawnBuf SB, IterArgs A, double *partials) {
+__global__ void __launch_bounds__(NG_BLOCK) k_compress(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials, unsigned int *ticket) {
     __shared__ double s_red[32];
+    __shared__ bool s_last;
+    // FreeSlot bookkeeping that used to be two launches: the slots freed by the spawning pass (freeB) are appended
+    // to the pop side (freeA) by all CTAs; the CTA that finishes last publishes the new counters.  Nothing in this
+    // kernel touches the free lists otherwise, and the next kernel starts after this one has ended.
+    {
+        long long a = L.ctr[C_NFREEA]; if (a < 0) a = 0;
+        const long long b = L.ctr[C_NFREEB];
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < b; i += (long long)gridDim.x * blockDim.x)
+            L.freeA[a + i] = L.freeB[i];
+    }
     const long long n = recv_count(SB, A);
     const u64 mask = sht_mask_for(n, SB.sht_cap);
     const u64 stamp = (u64)(A.stamp & 0xFFFFu) << 48;
@@ -134,6 +158,16 @@ __global__ void __launch_bounds__(NG_BLOCK) k_compress(Params P, SpawnBuf SB, It
     }
     const int idx[1] = {NECI_ST_ANNIHILATED};
     block_flush_stats<1>(acc, idx, partials, s_red);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        long long a = L.ctr[C_NFREEA]; if (a < 0) a = 0;
+        L.ctr[C_NFREEA] = a + L.ctr[C_NFREEB];
+        L.ctr[C_NFREEB] = 0;
+        *ticket = 0u;
+    }
 }
 
 // ---- AnnihilateSpawnedParts ------------------------------------------------------
@@ -261,53 +295,54 @@ __global__ void k_fix_counters(WalkerList L) {
 template <int NW>
 __global__ void __launch_bounds__(NG_BLOCK) k_list_stats(Params P, WalkerList L, IterArgs A, double *partials) {
     __shared__ double s_red[6 * 32];
-    const long long n = L.ctr[C_NLIST];
+    // k_insert may have overshot the counters when the list overflowed (error already flagged): clamp, as every CTA
+    // does for itself; the stored values are repaired by one thread
+    long long n = L.ctr[C_NLIST]; if (n > L.cap - 1) n = L.cap - 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (L.ctr[C_NFREEA] < 0) L.ctr[C_NFREEA] = 0;
+        if (L.ctr[C_NLIST] > L.cap - 1) L.ctr[C_NLIST] = L.cap - 1;
+    }
     double acc[6] = {0, 0, 0, 0, 0, 0};     // totparts, norm2, norm_ss2, removed, born, highest
     const bool need_flags = P.t_semi_stochastic != 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        double s = L.sgn[i];
-        const bool tDet = need_flags && (L.flg[i] & F_DETERM);
-        if (fabs(s) < 1.0e-12 && !tDet) continue;
-        if (!tDet && fabs(s) > 1.e-12 && fabs(s) < P.occupied_thresh) {
-            const Det<NW> d = load_det<NW>(L, i);
-            const u64 h = det_hash64(d);
-            const double pRemove = (P.occupied_thresh - fabs(s)) / P.occupied_thresh;
-            Stream rng(P.seed, A.iter, h, 0, RNG_PRUNE);
-            if (pRemove > rng.draw()) {
-                acc[3] += fabs(s);
-                s = 0.0; L.sgn[i] = 0.0;
-                ht_remove<NW>(L, d, h, i);
-                L.flg[i] |= F_REMOVED;
-            } else {
-                acc[4] += P.occupied_thresh - fabs(s);
-                s = dsign(P.occupied_thresh, s); L.sgn[i] = s;
-            }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double sv[4]; int fv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                // four independent loads in flight per thread
+            const long long i = i0 + u * stride;
+            sv[u] = (i < n) ? L.sgn[i] : 0.0;
+            fv[u] = (need_flags && i < n) ? L.flg[i] : 0;
         }
-        acc[0] += fabs(s); acc[1] += s * s;
-        if (tDet) acc[2] += s * s;
-        acc[5] = fmax(acc[5], (double)(long long)fabs(s));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= n) continue;
+            double s = sv[u];
+            const bool tDet = need_flags && (fv[u] & F_DETERM);
+            if (fabs(s) < 1.0e-12 && !tDet) continue;
+            if (!tDet && fabs(s) > 1.e-12 && fabs(s) < P.occupied_thresh) {
+                const Det<NW> d = load_det<NW>(L, i);
+                const u64 h = det_hash64(d);
+                const double pRemove = (P.occupied_thresh - fabs(s)) / P.occupied_thresh;
+                Stream rng(P.seed, A.iter, h, 0, RNG_PRUNE);
+                if (pRemove > rng.draw()) {
+                    acc[3] += fabs(s);
+                    s = 0.0; L.sgn[i] = 0.0;
+                    ht_remove<NW>(L, d, h, i);
+                    L.flg[i] |= F_REMOVED;
+                } else {
+                    acc[4] += P.occupied_thresh - fabs(s);
+                    s = dsign(P.occupied_thresh, s); L.sgn[i] = s;
+                }
+            }
+            acc[0] += fabs(s); acc[1] += s * s;
+            if (tDet) acc[2] += s * s;
+            acc[5] = fmax(acc[5], (double)(long long)fabs(s));
+        }
     }
     const int idx[6] = {NECI_ST_TOTPARTS, NECI_ST_NORM_PSI_SQ, NECI_ST_NORM_SEMISTOCH_SQ, NECI_ST_NOREMOVED,
                         NECI_ST_NOBORN, NECI_ST_HIGHEST_POP};
     block_flush_stats<6>(acc, idx, partials, s_red);
-}
-
-// final bookkeeping: InstNoatHF, counters -> stats (single thread)
-template <int NW>
-__global__ void k_finish_stats(Params P, WalkerList L, SpawnBuf SB, double *stats) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const Det<NW> ref = ref_det<NW>(P);
-    const long long slot = ht_lookup<NW>(L, ref, det_hash64(ref));
-    stats[NECI_ST_INSTNOATHF] = (slot >= 0) ? L.sgn[slot] : 0.0;
-    stats[NECI_ST_TOTWALKERS] = (double)L.ctr[C_NLIST];
-    long long a = L.ctr[C_NFREEA]; if (a < 0) a = 0;
-    stats[NECI_ST_HOLESINLIST] = (double)(a + L.ctr[C_NFREEB]);
-    unsigned long long sent = 0;
-    for (int r = 0; r < P.nranks; ++r) sent += SB.cnt[r];
-    stats[NECI_ST_NSPAWNED_SENT] = (double)sent;
-    stats[NECI_ST_ERR_FLAGS] = (double)L.ctr[C_ERR];
-    stats[NECI_ST_BLOOM_SIZE_1] = __longlong_as_double(L.ctr[C_COUNT - 2]);
-    stats[NECI_ST_BLOOM_SIZE_2] = __longlong_as_double(L.ctr[C_COUNT - 1]);
 }
 
 // ---- hash-table maintenance -------------------------------------------------------

@@ -69,6 +69,7 @@ struct neci_gpu_engine {
     // device-owned tables
     std::vector<void *> owned;
     double *d_partials = nullptr, *d_stats = nullptr, *h_stats = nullptr;
+    unsigned int *d_ticket = nullptr;
     long long *h_ctr = nullptr;
     int rows_spawn = 0, rows_heavy = 0, rows_compress = 0, rows_annih = 0, rows_insert = 0, rows_list = 0, rows_trial = 0, rows_total = 0;
     int grid_spawn = 0, grid_generic = 0;
@@ -226,6 +227,8 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     e->rows_total = e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih + e->rows_insert + e->rows_list + e->rows_trial;
     e->d_partials = e->alloc<double>((size_t)e->rows_total * NECI_ST_COUNT);
     e->d_stats = e->alloc<double>(NECI_ST_COUNT);
+    e->d_ticket = e->alloc<unsigned int>(1);
+    CK(cudaMemset(e->d_ticket, 0, 4));
     CK(cudaMemset(e->d_partials, 0, (size_t)e->rows_total * NECI_ST_COUNT * 8));
     CK(cudaMallocHost((void **)&e->h_stats, NECI_ST_COUNT * 8));
     CK(cudaMallocHost((void **)&e->h_ctr, C_COUNT * 8));
@@ -597,17 +600,14 @@ static int annihilation_phase(neci_gpu_engine *e, IterArgs &A, int row0) {
     e->stamp += 1;
     if ((e->stamp & 0xFFFFu) == 0) { e->stamp += 1; CK(cudaMemsetAsync(e->SB.sht, 0, (size_t)e->SB.sht_cap * 8, e->stream)); }
     A.stamp = e->stamp;
-    e->n_launch += 8 + ((e->cfg.t_semi_stochastic && e->n_core_local > 0) ? 1 : 0);
-    k_merge_free<<<64, 256, 0, e->stream>>>(e->L);
-    k_merge_free_finish<<<1, 1, 0, e->stream>>>(e->L);
-    if (e->nw == 1) k_compress<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->SB, A, p_comp);
-    else k_compress<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->SB, A, p_comp);
+    e->n_launch += 4 + ((e->cfg.t_semi_stochastic && e->n_core_local > 0) ? 1 : 0);
+    if (e->nw == 1) k_compress<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_comp, e->d_ticket);
+    else k_compress<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_comp, e->d_ticket);
     if (e->cfg.t_semi_stochastic && e->n_core_local > 0)
         k_determ_apply<<<std::max(1, (int)std::min<long long>(g, (e->n_core_local + 255) / 256)), 256, 0, e->stream>>>(e->L, e->d_core_slots, e->d_vout, e->n_core_local);
     if (e->nw == 1) k_annihilate<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_ann);
     else k_annihilate<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, A, p_ann);
     NG_DISPATCH(e, (k_insert<NW, SYS><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, p_ins)));
-    k_fix_counters<<<1, 1, 0, e->stream>>>(e->L);
     if (e->nw == 1) k_list_stats<1><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, A, p_lst);
     else k_list_stats<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, A, p_lst);
     CK(cudaGetLastError());
@@ -615,10 +615,9 @@ static int annihilation_phase(neci_gpu_engine *e, IterArgs &A, int row0) {
 }
 
 static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
-    e->n_launch += 2;
-    k_reduce_stats<<<NECI_ST_COUNT, 256, 0, e->stream>>>(e->d_partials, e->rows_total, e->d_stats);
-    if (e->nw == 1) k_finish_stats<1><<<1, 32, 0, e->stream>>>(e->P, e->L, e->SB, e->d_stats);
-    else k_finish_stats<2><<<1, 32, 0, e->stream>>>(e->P, e->L, e->SB, e->d_stats);
+    e->n_launch += 1;
+    if (e->nw == 1) k_reduce_stats<1><<<NECI_ST_COUNT, 256, 0, e->stream>>>(e->P, e->L, e->SB, e->d_partials, e->rows_total, e->d_stats);
+    else k_reduce_stats<2><<<NECI_ST_COUNT, 256, 0, e->stream>>>(e->P, e->L, e->SB, e->d_partials, e->rows_total, e->d_stats);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[4], e->stream));
     CK(cudaMemcpyAsync(e->h_stats, e->d_stats, NECI_ST_COUNT * 8, cudaMemcpyDeviceToHost, e->stream));
