@@ -394,9 +394,16 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = bytes_spawn / (t_spawn * 1e-3) / 1e9 if t_spawn > 0 else 0.0
     traffic = None
+    ncu_extra = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_spawn_dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("k_spawn_dram_bytes_per_launch")
+        # the kernel is bound by instruction issue, not by HBM: the committed ncu capture's
+        # issue-slot utilisation and warp-instruction count are repeated here beside the HBM fraction
+        ncu_extra = {"ncu_issue_active_pct": tj.get("k_spawn_issue_active_pct"),
+                     "ncu_warp_instructions_per_launch": tj.get("k_spawn_warp_instructions_per_launch"),
+                     "ncu_source": tj.get("source")}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k_spawn", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -404,6 +411,7 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_spawn / args.steps, "ms_per_launch": t_spawn / args.steps,
                 "phase_ms_per_step": {"spawn_death": t_spawn / args.steps, "exchange": t_comm / args.steps,
                                       "annihilation": t_ann / args.steps}}
+    roofline.update(ncu_extra)
 
     # ---- end to end through the C ABI with HOST buffers: CurrentDets + gdata in pinned host memory, uploaded, iterated
     #      and downloaded inside the timed region (neci_gpu_iterate_host)

@@ -292,8 +292,26 @@ __global__ void k_fix_counters(WalkerList L) {
 }
 
 // ---- CalcHashTableStats ---------------------------------------------------------
+// the stochastic pruning of one under-threshold determinant (rare): kept out of line so that the streaming loop of
+// k_list_stats stays at a register count that allows full occupancy.  Returns the new sign.
 template <int NW>
-__global__ void __launch_bounds__(NG_BLOCK) k_list_stats(Params P, WalkerList L, IterArgs A, double *partials) {
+__device__ __noinline__ double prune_slot(const Params &P, const WalkerList &L, long long iter, long long i, double s) {
+    const Det<NW> d = load_det<NW>(L, i);
+    const u64 h = det_hash64(d);
+    const double pRemove = (P.occupied_thresh - fabs(s)) / P.occupied_thresh;
+    Stream rng(P.seed, iter, h, 0, RNG_PRUNE);
+    if (pRemove > rng.draw()) {
+        L.sgn[i] = 0.0;
+        ht_remove<NW>(L, d, h, i);
+        L.flg[i] |= F_REMOVED;
+        return 0.0;
+    }
+    s = dsign(P.occupied_thresh, s); L.sgn[i] = s;
+    return s;
+}
+template <int NW>
+__global__ void __launch_bounds__(NG_BLOCK, 4) k_list_stats(const __grid_constant__ Params P, const __grid_constant__ WalkerList L, IterArgs A,
+                                                            double *partials) {
     __shared__ double s_red[6 * 32];
     // k_insert may have overshot the counters when the list overflowed (error already flagged): clamp, as every CTA
     // does for itself; the stored values are repaired by one thread
@@ -321,19 +339,9 @@ __global__ void __launch_bounds__(NG_BLOCK) k_list_stats(Params P, WalkerList L,
             const bool tDet = need_flags && (fv[u] & F_DETERM);
             if (fabs(s) < 1.0e-12 && !tDet) continue;
             if (!tDet && fabs(s) > 1.e-12 && fabs(s) < P.occupied_thresh) {
-                const Det<NW> d = load_det<NW>(L, i);
-                const u64 h = det_hash64(d);
-                const double pRemove = (P.occupied_thresh - fabs(s)) / P.occupied_thresh;
-                Stream rng(P.seed, A.iter, h, 0, RNG_PRUNE);
-                if (pRemove > rng.draw()) {
-                    acc[3] += fabs(s);
-                    s = 0.0; L.sgn[i] = 0.0;
-                    ht_remove<NW>(L, d, h, i);
-                    L.flg[i] |= F_REMOVED;
-                } else {
-                    acc[4] += P.occupied_thresh - fabs(s);
-                    s = dsign(P.occupied_thresh, s); L.sgn[i] = s;
-                }
+                const double old = fabs(s);
+                s = prune_slot<NW>(P, L, A.iter, i, s);
+                if (s == 0.0) acc[3] += old; else acc[4] += P.occupied_thresh - old;       // NoRemoved / NoBorn
             }
             acc[0] += fabs(s); acc[1] += s * s;
             if (tDet) acc[2] += s * s;
