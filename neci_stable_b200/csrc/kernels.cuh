@@ -657,6 +657,28 @@ __global__ void __launch_bounds__(NG_BLOCK) k_rebalance_pack(Params P, WalkerLis
         append_spawn<NW>(P, SB, L, s_roi, move, d, s, (long long)(f & ~F_REMOVED));
     }
 }
+// DetermineDetNode for the staged spawns of one iteration (nranks > 1): every lane hashes one spawn and appends it
+// to its destination's segment of SpawnedParts (create_particle's routing, src/fcimc_helper.F90:152-308).
+template <int NW>
+__global__ void __launch_bounds__(NG_BLOCK) k_partition(Params P, WalkerList L, SpawnBuf SB) {
+    __shared__ int s_roi[NG_MAX_BASIS];
+    for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) s_roi[i] = P.random_orb_index[i];
+    __syncthreads();
+    long long n = (long long)*SB.stage_cnt; if (n > SB.stage_cap) n = SB.stage_cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n + stride - 1) / stride) * stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
+        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
+        double s = 0.0; long long f = 0;
+        const bool has = i < n;
+        if (has) {
+            const long long *rec = SB.stage + (size_t)i * SB.W;
+            d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
+            s = __longlong_as_double(rec[NW]); f = rec[NW + 1];
+        }
+        append_spawn<NW>(P, SB, L, s_roi, has, d, s, f);
+    }
+}
 // receiver side: every received record is a new determinant here
 __global__ void k_iota_insert(WalkerList L, SpawnBuf SB, long long n) {
     if (n < 0) n = (long long)*SB.n_recv_dev;

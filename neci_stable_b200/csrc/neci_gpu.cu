@@ -193,6 +193,11 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     long long sc = 1024; while (sc < 2 * Ms) sc <<= 1;
     SB.sht_cap = (u64)sc; SB.sht = e->alloc<u64>(sc);
     SB.ins_idx = e->alloc<int>(Ms);
+    if (cfg->nranks > 1) {
+        SB.stage_cap = Ms; SB.stage = e->alloc<long long>((size_t)Ms * e->W); SB.stage_cnt = e->alloc<unsigned long long>(1);
+        if (!SB.stage || !SB.stage_cnt) return e->fail("device allocation failed (spawn staging list)");
+        CK(cudaMemset(SB.stage_cnt, 0, 8));
+    }
     SB.heavy_cap = 1 << 16; SB.heavy = e->alloc<long long>(2 * SB.heavy_cap);
     if (!L.det0 || !L.sgn || !L.flg || !L.diagH || !L.offH || !L.ht || !L.freeA || !L.freeB || !L.ctr || !SB.buf ||
         !SB.recv || !SB.cnt || !SB.sht || !SB.ins_idx || !SB.heavy || (e->nw > 1 && !L.det1))
@@ -654,6 +659,7 @@ static int begin_iteration(neci_gpu_engine *e) {
     }
     // ValidSpawnedList = InitialSpawnedSlots etc. (FciMCPar.F90:1237-1248)
     CK(cudaMemsetAsync(e->SB.cnt, 0, (size_t)e->cfg.nranks * 8, e->stream));
+    if (e->SB.stage_cnt) CK(cudaMemsetAsync(e->SB.stage_cnt, 0, 8, e->stream));
     CK(cudaMemsetAsync(&e->L.ctr[C_NHEAVY], 0, 8 * (C_COUNT - C_NHEAVY), e->stream));
     return 0;
 }
@@ -684,6 +690,11 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
     double *p_spawn = e->d_partials, *p_heavy = e->d_partials + (size_t)e->rows_spawn * NECI_ST_COUNT;
     NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, NG_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
     NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, NG_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
+    if (e->cfg.nranks > 1) {
+        e->n_launch += 1;
+        if (e->nw == 1) k_partition<1><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
+        else k_partition<2><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[2], e->stream));
     if (e->cfg.nranks > 1) {

@@ -44,6 +44,9 @@ struct SpawnBuf {
     long long *heavy;        // (slot, nspawn) pairs
     long long heavy_cap;
     unsigned long long *n_recv_dev;   // received-record count left on the device by the peer-memory exchange
+    long long *stage;                 // nranks > 1: spawns of the spawning kernel before they are routed (k_partition)
+    unsigned long long *stage_cnt;
+    long long stage_cap;
 };
 
 struct IterArgs {
@@ -136,6 +139,29 @@ __device__ __forceinline__ void append_spawn(const Params &P, const SpawnBuf &SB
     rec[NW] = __double_as_longlong(child);
     rec[NW + 1] = flags;
 }
+// The spawning kernel's own append.  On one rank this is create_particle itself.  On several ranks the spawn goes
+// to a staging list first and k_partition routes it afterwards: DetermineDetNode costs ~230 instructions, and inside
+// the spawning kernel only ~5 of 32 lanes hold a successful spawn, so hashing there wasted 85 % of the issue slots
+// it used (11 % of the kernel); the partition kernel hashes with every lane busy.
+template <int NW>
+__device__ __forceinline__ void append_spawn_k1(const Params &P, const SpawnBuf &SB, const WalkerList &L, const int *roi,
+                                                bool has, const Det<NW> &detJ, double child, long long flags) {
+    if (P.nranks == 1) { append_spawn<NW>(P, SB, L, roi, has, detJ, child, flags); return; }
+    const u32 lane = threadIdx.x & 31;
+    const u32 active = __ballot_sync(0xffffffffu, has);
+    if (!has) return;
+    const int leader = __ffs(active) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(SB.stage_cnt, (unsigned long long)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    const long long pos = (long long)base + __popc(active & ((1u << lane) - 1u));
+    if (pos >= SB.stage_cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull); return; }
+    long long *rec = SB.stage + (size_t)pos * SB.W;
+    rec[0] = (long long)detJ.w[0];
+    if (NW > 1) rec[NW - 1] = (long long)detJ.w[NW - 1];
+    rec[NW] = __double_as_longlong(child);
+    rec[NW + 1] = flags;
+}
 
 // per-thread accumulators of the attempt stages
 struct AttAcc {
@@ -210,7 +236,7 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
             if (m && (threadIdx.x & 31) == 0) atomicAdd(&S.tau_cnt[c], __popc(m));
         }
     }
-    append_spawn<NW>(P, SB, L, S.roi, has, E.detJ, child, cflags);
+    append_spawn_k1<NW>(P, SB, L, S.roi, has, E.detJ, child, cflags);
 }
 
 // push helpers: warp-aggregated reservation in a shared-memory stack
