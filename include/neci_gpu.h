@@ -135,6 +135,11 @@ typedef struct neci_gpu_config {
     int32_t t_core_inits;         /* t_core_inits    Calc.F90:125              */
     int32_t t_tau_search;         /* tau_search_method /= OFF: log spawn magnitudes (fcimc_pointed_fns.F90:428-434) */
     int32_t t_consider_par_bias;  /* consider_par_bias  tau/tau_search_conventional.F90:66-117 */
+    int32_t t_hphf;               /* tHPHF (even S): walkers live on HPHF functions, represented by the determinant
+                                     IsAllowedHPHF accepts (src/DetBitOps.F90:693-718); generate_excitation =
+                                     gen_hphf_excit (src/HPHFRandExcit.F90:175-476), matrix elements from
+                                     src/HPHFIntegrals.fpp.  FCIDUMP/PCHB systems only.                       */
+    int32_t reserved0;            /* keeps the doubles 8-byte aligned; must be 0 */
     double  initiator_walk_no;    /* InitiatorWalkNo                           */
     double  real_spawn_cutoff;    /* RealSpawnCutoff                           */
     double  occupied_thresh;      /* OccupiedThresh                            */

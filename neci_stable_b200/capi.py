@@ -45,7 +45,8 @@ class Config(C.Structure):
         ("t_all_real_coeff", C.c_int32), ("t_real_spawn_cutoff", C.c_int32), ("t_death_before_comms", C.c_int32),
         ("t_init_coherent_rule", C.c_int32), ("t_no_brillouin", C.c_int32), ("t_exch", C.c_int32),
         ("t_semi_stochastic", C.c_int32), ("t_core_inits", C.c_int32), ("t_tau_search", C.c_int32),
-        ("t_consider_par_bias", C.c_int32), ("initiator_walk_no", C.c_double),
+        ("t_consider_par_bias", C.c_int32), ("t_hphf", C.c_int32), ("reserved0", C.c_int32),
+        ("initiator_walk_no", C.c_double),
         ("real_spawn_cutoff", C.c_double), ("occupied_thresh", C.c_double), ("av_mc_excits", C.c_double),
         ("hii", C.c_double), ("ecore", C.c_double), ("seed", C.c_uint64),
         ("random_orb_index", C.POINTER(C.c_int32)), ("random_hash2", C.POINTER(C.c_int32)),

@@ -178,7 +178,7 @@ struct Params {
     int system_type;
     int t_trunc_initiator, t_all_real_coeff, t_real_spawn_cutoff, t_death_before_comms;
     int t_init_coherent_rule, t_no_brillouin, t_exch, t_semi_stochastic, t_core_inits;
-    int t_tau_search, t_consider_par_bias;
+    int t_tau_search, t_consider_par_bias, t_hphf;
     double initiator_walk_no, real_spawn_cutoff, occupied_thresh, av_mc_excits;
     double hii, ecore;
     u64 seed;

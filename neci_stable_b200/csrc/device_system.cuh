@@ -147,9 +147,14 @@ __device__ __forceinline__ double diag_rs(const Params &P, const Det<NW> &d) {  
     return P.uhub * nd;
 }
 
+// (defined with the other HPHF functions below; FCIDUMP systems only)
+template <int NW> __device__ double hphf_diag_dispatch(const Params &P, const Det<NW> &d);
+template <int NW> __device__ double hphf_off_diag_dispatch(const Params &P, const Det<NW> &I, const Det<NW> &J);
+
 // get_diagonal_matel (src/matel_getter.F90:30-58): full H_ii (ECore included)
 template <int NW, int SYS>
 __device__ __forceinline__ double diagonal_matel(const Params &P, const Det<NW> &d) {
+    if (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) return hphf_diag_dispatch<NW>(P, d);
     if (SYS == NECI_SYS_HUBBARD_RS) return diag_rs(P, d);
     if (SYS == NECI_SYS_HUBBARD_K) return diag_k(P, d) + P.ecore;
     return sltcnd_0(P, d) + P.ecore;
@@ -185,8 +190,9 @@ __device__ double helement(const Params &P, const Det<NW> &I, const Det<NW> &J) 
 template <int NW, int SYS>
 __device__ __forceinline__ double off_diagonal_matel(const Params &P, const Det<NW> &d) {
     const Det<NW> ref = ref_det<NW>(P);
-    const int ex = excit_level(ref, d);
-    if (ex == 2 || (ex == 1 && P.t_no_brillouin)) return helement<NW, SYS>(P, d, ref);
+    const int ex = excit_level_ref(P, ref, d);
+    if (ex == 2 || (ex == 1 && P.t_no_brillouin))
+        return (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) ? hphf_off_diag_dispatch<NW>(P, ref, d) : helement<NW, SYS>(P, d, ref);
     return 0.0;
 }
 
@@ -445,6 +451,128 @@ template <int NW, int SYS>
 __device__ __forceinline__ void generate_excitation(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
     generate_excitation_core<NW, SYS>(P, d, rng, E);
     if (E.valid) finalize_excit(d, E);
+}
+
+// ---- HPHF functions (src/HPHFIntegrals.fpp, src/HPHFRandExcit.F90, src/DetBitOps.F90:648-740,819-848), even S ------
+template <int NW> __device__ __forceinline__ Det<NW> spin_sym(const Det<NW> &a) {           // spin_sym_ilut
+    Det<NW> b;
+    b.w[0] = ((a.w[0] & NG_ALPHA_MASK) >> 1) | ((a.w[0] & NG_BETA_MASK) << 1);
+    if (NW > 1) b.w[NW - 1] = ((a.w[NW - 1] & NG_ALPHA_MASK) >> 1) | ((a.w[NW - 1] & NG_BETA_MASK) << 1);
+    return b;
+}
+template <int NW> __device__ __forceinline__ bool closed_shell(const Det<NW> &a) {           // TestClosedShellDet
+    u64 x = ((a.w[0] & NG_ALPHA_MASK) >> 1) ^ (a.w[0] & NG_BETA_MASK);
+    if (NW > 1) x |= ((a.w[NW - 1] & NG_ALPHA_MASK) >> 1) ^ (a.w[NW - 1] & NG_BETA_MASK);
+    return x == 0ull;
+}
+template <int NW> __device__ __forceinline__ int open_orbs(const Det<NW> &a) {                // CalcOpenOrbs
+    int n = __popcll(~((a.w[0] & NG_ALPHA_MASK) >> 1) & (a.w[0] & NG_BETA_MASK));
+    if (NW > 1) n += __popcll(~((a.w[NW - 1] & NG_ALPHA_MASK) >> 1) & (a.w[NW - 1] & NG_BETA_MASK));
+    return n;
+}
+// DetBitLT(a, b) == 1: signed comparison, word 0 first
+template <int NW> __device__ __forceinline__ bool det_less(const Det<NW> &a, const Det<NW> &b) {
+    if ((long long)a.w[0] != (long long)b.w[0] || NW == 1) return (long long)a.w[0] < (long long)b.w[0];
+    return (long long)a.w[NW - 1] < (long long)b.w[NW - 1];
+}
+// FindBitExcitLevel(ref, det, t_hphf_ic = .true.): the smallest level over the spin-flipped partners
+template <int NW> __device__ __forceinline__ int excit_level_ref(const Params &P, const Det<NW> &ref, const Det<NW> &d) {
+    int ic = excit_level(ref, d);
+    if (P.t_hphf && !(closed_shell(ref) && closed_shell(d))) {
+        const Det<NW> r2 = spin_sym(ref), d2 = spin_sym(d);
+        ic = min(min(ic, excit_level(ref, d2)), min(excit_level(r2, d), excit_level(r2, d2)));
+    }
+    return ic;
+}
+// hphf_off_diag_helement_norm (src/HPHFIntegrals.fpp:62-150)
+template <int NW, int SYS>
+__device__ double hphf_off_diag(const Params &P, const Det<NW> &I, const Det<NW> &J) {
+    if (det_eq(I, J)) return 0.0;
+    double hel = helement<NW, SYS>(P, I, J);
+    if (closed_shell(I)) { if (!closed_shell(J)) hel = hel * sqrt(2.0); }
+    else if (closed_shell(J)) hel = hel * sqrt(2.0);
+    else {
+        const Det<NW> I2 = spin_sym(I);
+        if (excit_level(I2, J) <= 2) {
+            const double m2 = helement<NW, SYS>(P, I2, J);
+            hel = (open_orbs(I) % 2 == 0) ? hel + m2 : hel - m2;
+        }
+    }
+    return hel;
+}
+// hphf_diag_helement (src/HPHFIntegrals.fpp:348-411); ECore included
+template <int NW, int SYS>
+__device__ double hphf_diag(const Params &P, const Det<NW> &I) {
+    double hel = sltcnd_0(P, I) + P.ecore;        // the determinant's own diagonal element (not diagonal_matel: that dispatches here)
+    if (!closed_shell(I)) {
+        const Det<NW> I2 = spin_sym(I);
+        if (excit_level(I, I2) <= 2) {
+            const double m2 = helement<NW, SYS>(P, I, I2);
+            hel = (open_orbs(I) % 2 == 1) ? hel - m2 : hel + m2;
+        }
+    }
+    return hel;
+}
+// CalcNonUniPGen for the PCHB class generator (src/HPHFRandExcit.F90:686-821 -> get_pgen_sd,
+// src/excitation_generators.F90:141-158): probability with which I -> K is drawn, K given by its excitation
+template <int NW>
+__device__ double calc_pgen_pchb(const Params &P, const Det<NW> &d, int ic, int s1, int s2, int t1, int t2) {
+    if (ic == 1) {
+        int ElecsWNoExcits = 0, NExcitA = 0;
+        const int cls = __ldg(&P.class_of_spinorb[s1 - 1]);
+#pragma unroll 1
+        for (int c = 0; c < P.n_classes; ++c) {
+            int o = __popcll(d.w[0] & P.class_mask[c][0]), t = __popcll(P.class_mask[c][0]);
+            if (NW > 1) { o += __popcll(d.w[NW - 1] & P.class_mask[c][1]); t += __popcll(P.class_mask[c][1]); }
+            if (t - o == 0) ElecsWNoExcits += o;
+            if (c == cls) NExcitA = t - o;
+        }
+        double pgen = (1 - P.p_doubles) / ((double)(NExcitA * (P.nel - ElecsWNoExcits)));
+        pgen = pgen / P.p_singles;
+        return P.p_singles * pgen;
+    }
+    if (ic != 2) return 0.0;
+    // GAS_doubles_PCHB_get_pgen (src/gasci_pchb_doubles_spatorb_fastweighted.fpp:286-326)
+    const int ij = (int)tri((u32)gtid(s1), (u32)gtid(s2)), ab = (int)tri((u32)gtid(t1), (u32)gtid(t2));
+    const bool same = ((s1 ^ s2) & 1) == 0;
+    double pgen = same ? P.pgen_pair_par : P.pgen_pair_opp;
+    const int4 pi = __ldg(reinterpret_cast<const int4 *>(P.pchb_pair + (ij - 1)));
+    const double pe = __hiloint2double(pi.y, pi.x);
+    int sampler = 0;
+    if (!same) {
+        if (((s1 ^ t1) & 1) == 0 || gtid(t1) == gtid(t2)) { sampler = 1; pgen *= (1.0 - pe); }
+        else { sampler = 2; pgen *= pe; }
+    }
+    if (((pi.z >> sampler) & 1) == 0) return 0.0;
+    const PchbEntry *tab = P.pchb + ((size_t)(ij - 1) * 3 + sampler) * P.ab_max;
+    return (1.0 - P.p_singles) * (pgen * __ldg(&tab[ab - 1].prob));
+}
+// gen_hphf_excit (src/HPHFRandExcit.F90:175-476) applied to an excitation the PCHB generator has produced:
+// replaces detJ by the allowed representative of its HPHF function, adds the probability of having drawn the
+// partner determinant, and returns the HPHF matrix element.  false: the excitation stays inside I's own function.
+template <int NW, int SYS>
+__device__ bool hphf_fixup(const Params &P, const Det<NW> &d, Excit<NW> &E, double &hel) {
+    if (!closed_shell(E.detJ)) {
+        const Det<NW> J2 = spin_sym(E.detJ);                      // ReturnAlphaOpenDet
+        const int exl = excit_level(d, J2);                       // to the determinant that was NOT generated
+        if (exl == 0) return false;
+        if (exl <= 2) {
+            Det<NW> S, T;
+            S.w[0] = d.w[0] & ~J2.w[0]; T.w[0] = J2.w[0] & ~d.w[0];
+            if (NW > 1) { S.w[NW - 1] = d.w[NW - 1] & ~J2.w[NW - 1]; T.w[NW - 1] = J2.w[NW - 1] & ~d.w[NW - 1]; }
+            const int s1 = pop_lowest(S), t1 = pop_lowest(T);
+            const int s2 = (exl == 2) ? pop_lowest(S) : 0, t2 = (exl == 2) ? pop_lowest(T) : 0;
+            E.pgen = E.pgen + calc_pgen_pchb<NW>(P, d, exl, s1, s2, t1, t2);
+        }
+        if (det_less(E.detJ, J2)) E.detJ = J2;
+    }
+    hel = hphf_off_diag<NW, SYS>(P, d, E.detJ);
+    return true;
+}
+
+template <int NW> __device__ double hphf_diag_dispatch(const Params &P, const Det<NW> &d) { return hphf_diag<NW, NECI_SYS_FCIDUMP_PCHB>(P, d); }
+template <int NW> __device__ double hphf_off_diag_dispatch(const Params &P, const Det<NW> &I, const Det<NW> &J) {
+    return hphf_off_diag<NW, NECI_SYS_FCIDUMP_PCHB>(P, I, J);
 }
 
 // get_spawn_helement = get_helement_det_only (src/Determinants.F90:508-554)

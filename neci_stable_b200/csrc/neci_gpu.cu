@@ -166,7 +166,9 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     P.t_real_spawn_cutoff = cfg->t_real_spawn_cutoff; P.t_death_before_comms = cfg->t_death_before_comms;
     P.t_init_coherent_rule = cfg->t_init_coherent_rule; P.t_no_brillouin = cfg->t_no_brillouin; P.t_exch = cfg->t_exch;
     P.t_semi_stochastic = cfg->t_semi_stochastic; P.t_core_inits = cfg->t_core_inits;
-    P.t_tau_search = cfg->t_tau_search; P.t_consider_par_bias = cfg->t_consider_par_bias;
+    P.t_tau_search = cfg->t_tau_search; P.t_consider_par_bias = cfg->t_consider_par_bias; P.t_hphf = cfg->t_hphf;
+    if (cfg->t_hphf && cfg->system_type != NECI_SYS_FCIDUMP_PCHB) return e->fail("t_hphf is implemented for FCIDUMP/PCHB systems only");
+    if (cfg->t_hphf && cfg->nocc_alpha != cfg->nocc_beta) return e->fail("t_hphf needs Ms = 0");
     P.p_singles = P.p_doubles = P.p_parallel = 1.0;          // lattice models: one excitation class (set_pchb overrides)
     P.initiator_walk_no = cfg->initiator_walk_no; P.real_spawn_cutoff = cfg->real_spawn_cutoff;
     P.occupied_thresh = cfg->occupied_thresh; P.av_mc_excits = cfg->av_mc_excits; P.hii = cfg->hii; P.ecore = cfg->ecore;

@@ -182,14 +182,19 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
     if (active) {
         finalize_excit(d, E);
         bool cancelled = false;
-        if (P.t_semi_stochastic && (info & 4)) {
+        double rh_hphf = 0.0;
+        if (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) {
+            // gen_hphf_excit wraps the generator (fcimc_initialisation.fpp:2162-2165): representative, pgen, element
+            if (!hphf_fixup<NW, SYS>(P, d, E, rh_hphf)) { cancelled = true; acc.valid -= 1; acc.invalid += 1; }
+        }
+        if (!cancelled && P.t_semi_stochastic && (info & 4)) {
             // core -> core spawning is done by determ_projection (FciMCPar.F90:1651-1670)
             if (is_core_state<NW>(P, E.detJ)) cancelled = true;
             cflags = F_DPARENT;
         }
         if (!cancelled) {
             const double prob = E.pgen * P.av_mc_excits;
-            const double rh = spawn_helement<NW, SYS>(P, d, E);
+            const double rh = (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) ? rh_hphf : spawn_helement<NW, SYS>(P, d, E);
             const double ww = (info & 1) ? -1.0 : 1.0;
             if (P.t_tau_search) {
                 // log_spawn_magnitude (tau/tau_search_conventional.F90:138-260): gamma = |H_ij| / (prob / p_class)
@@ -451,7 +456,7 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
                     const int f0 = f;
                     const double K = ld_K[kk], O = ld_O[kk];
                     const bool core = (f & F_DETERM) != 0;
-                    const int exl = excit_level(ref, d);
+                    const int exl = excit_level_ref(P, ref, d);        // FindBitExcitLevel(..., t_hphf_ic = .true.)
                     const double as = fabs(s);
                     // CalcParentFlag / TestInitiator_explicit (fcimc_helper.F90:1036-1243)
                     if (P.t_trunc_initiator) {

@@ -190,7 +190,7 @@ def update_shift(diag_sft, sft_damp, tau, steps_sft, av_walkers, old_av_walkers)
 def make_params(system, hii, max_walkers, max_spawned, nranks=1, rank=0, device=0, seed=7, initiator=True,
                 initiator_walk_no=3.0, all_real_coeff=False, real_spawn_cutoff=0.95, occupied_thresh=1.0,
                 av_mc_excits=1.0, semi_stochastic=False, blocks_per_rank=1, hash_seed=7, mapping=None,
-                death_before_comms=None, tau_search=False, consider_par_bias=None):
+                death_before_comms=None, tau_search=False, consider_par_bias=None, hphf=False):
     """The module-level globals of the reference that the engine needs (neci_gpu_config).
     Defaults follow src/Calc.F90:120-480; tDeathBeforeComms is .false. unless the walkers are integers
     (src/Calc.F90:475, src/fcimc_initialisation.fpp:1997-2001) or DEATH-BEFORE-COMMS is given."""
@@ -212,6 +212,7 @@ def make_params(system, hii, max_walkers, max_spawned, nranks=1, rank=0, device=
         # consider_par_bias: true for the PCHB generator with uniform particle selection and for the k-space Hubbard
         # generator's parent class, false for the real-space lattice (tau/tau_search_conventional.F90:80-117)
         t_consider_par_bias=int((system.kind == 1) if consider_par_bias is None else bool(consider_par_bias)),
+        t_hphf=int(bool(hphf)), reserved0=0,
         initiator_walk_no=float(initiator_walk_no), real_spawn_cutoff=float(real_spawn_cutoff),
         occupied_thresh=float(occupied_thresh), av_mc_excits=float(av_mc_excits), hii=float(hii),
         ecore=float(system.ecore), seed=int(seed), random_orb_index=roi, random_hash2=rh2,

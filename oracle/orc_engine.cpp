@@ -128,7 +128,7 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
         const bool tCoreDet = e.test_flag(j, NECI_FLAG_DETERMINISTIC);       // check_determ_flag :1318
         const double SignCurr = e.sign(j);
         decode(ilut, c.nbasis, nI);
-        const int walkExcitLevel = excit_level(e.ilut_ref.data(), ilut, e.nwords);   // :1354
+        const int walkExcitLevel = excit_level_hphf(S, e.ilut_ref.data(), ilut);     // :1354 (t_hphf_ic = .true.)
 
         if (c.t_semi_stochastic && tCoreDet) {                               // :1387-1411
             e.indices_of_determ_states[determ_index] = j;
@@ -199,7 +199,9 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
         for (int p = 0; p < WalkersToSpawn; ++p) {                           // loop_over_walkers :1622
             Stream rng(c.seed, iter, h, (uint32_t)p, RNG_ATTEMPT);
             Excitation E;
-            generate_excitation(S, nI, ilut, rng, E);
+            double HElGen = 0.0;
+            if (S.t_hphf) { E = Excitation(); gen_hphf_excit(S, nI, ilut, rng, E, HElGen); }   // fcimc_initialisation.fpp:2162-2165
+            else generate_excitation(S, nI, ilut, rng, E);
             if (E.err) e.stats[NECI_ST_ERR_FLAGS] = (double)((int)e.stats[NECI_ST_ERR_FLAGS] | 16);
             if (!E.valid) { e.stats[NECI_ST_NINVALIDEXCITS] += 1; continue; }
             e.stats[NECI_ST_NVALIDEXCITS] += 1;
@@ -211,7 +213,7 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
             }
             // attempt_create_normal, src/fcimc_pointed_fns.F90:178-491
             const double prob = E.pgen * c.av_mc_excits;
-            const double rh = get_spawn_helement(S, nI, E);
+            const double rh = S.t_hphf ? HElGen : get_spawn_helement(S, nI, E);          // hphf_spawn_sign
             const double walkerweight = dsign(1.0, SignCurr);
             if (c.t_tau_search) {
                 // log_spawn_magnitude, src/tau/tau_search_conventional.F90:138-260 (per-iteration maxima and counts; the
@@ -492,7 +494,7 @@ void annihilate_phase(orc_engine &e, std::vector<int64_t> &sp, int64_t iter) {
             if (tDet) norm_ss2 += s * s;
             if (std::fabs(s) > highest) highest = (double)(int64_t)std::fabs(s);
         }
-        if (excit_level(e.ilut_ref.data(), e.orb(i), nw) == 0) inst_hf = s;
+        if (excit_level_hphf(e.S, e.ilut_ref.data(), e.orb(i)) == 0) inst_hf = s;
     }
     e.stats[NECI_ST_TOTPARTS] = TotParts;
     e.stats[NECI_ST_NORM_PSI_SQ] = norm2;
@@ -522,6 +524,7 @@ int orc_init(const neci_gpu_config *cfg, orc_engine **out) {
     e->S.type = cfg->system_type; e->S.nel = cfg->nel; e->S.nbasis = cfg->nbasis; e->S.nwords = e->nwords;
     e->S.nocc_alpha = cfg->nocc_alpha; e->S.nocc_beta = cfg->nocc_beta;
     e->S.t_exch = cfg->t_exch != 0; e->S.t_no_brillouin = cfg->t_no_brillouin != 0; e->S.ecore = cfg->ecore;
+    e->S.t_hphf = cfg->t_hphf != 0;
     e->dets.assign((size_t)e->W * cfg->max_walkers, 0);
     e->diagH.assign(cfg->max_walkers, 0.0); e->offdiagH.assign(cfg->max_walkers, 0.0);
     e->FreeSlot.assign(cfg->max_walkers + 1, 0);
@@ -772,8 +775,11 @@ int orc_probe_walker_hash(orc_engine *e, int64_t n, const int64_t *iluts, int32_
     return 0;
 }
 int orc_probe_helement(orc_engine *e, int64_t n, const int64_t *ii, const int64_t *ij, double *out) {
-    for (int64_t i = 0; i < n; ++i)
-        out[i] = get_helement(e->S, (const uint64_t *)&ii[(size_t)i * e->nwords], (const uint64_t *)&ij[(size_t)i * e->nwords]);
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t *a = (const uint64_t *)&ii[(size_t)i * e->nwords], *b = (const uint64_t *)&ij[(size_t)i * e->nwords];
+        if (!e->S.t_hphf) out[i] = get_helement(e->S, a, b);
+        else out[i] = (DetBitLT(a, b, e->nwords) == 0) ? hphf_diag_helement(e->S, a) : hphf_off_diag_helement(e->S, a, b);
+    }
     return 0;
 }
 int orc_probe_gen_excit(orc_engine *e, int64_t n, const int64_t *iluts, const int32_t *attempt, int64_t iter,
@@ -785,13 +791,15 @@ int orc_probe_gen_excit(orc_engine *e, int64_t n, const int64_t *iluts, const in
         decode(il, e->cfg.nbasis, nI);
         Stream rng(e->cfg.seed, iter, det_hash64(il, e->nwords), (uint32_t)attempt[i], RNG_ATTEMPT);
         Excitation E;
-        generate_excitation(e->S, nI, il, rng, E);
+        double HElGen = 0.0;
+        if (e->S.t_hphf) gen_hphf_excit(e->S, nI, il, rng, E, HElGen);
+        else generate_excitation(e->S, nI, il, rng, E);
         for (int w = 0; w < e->nwords; ++w) ilut_j_out[(size_t)i * e->nwords + w] = E.valid ? (int64_t)E.ilutJ[w] : 0;
         ic_out[i] = E.ic;
         for (int k = 0; k < 4; ++k) ex_out[4 * i + k] = E.valid ? E.ex[k] : 0;
         parity_out[i] = E.valid ? (E.parity ? 1 : 0) : 0;
         pgen_out[i] = E.valid ? E.pgen : 0.0;
-        hel_out[i] = E.valid ? get_spawn_helement(e->S, nI, E) : 0.0;
+        hel_out[i] = E.valid ? (e->S.t_hphf ? HElGen : get_spawn_helement(e->S, nI, E)) : 0.0;
     }
     return 0;
 }

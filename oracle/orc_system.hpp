@@ -10,7 +10,7 @@ struct System {
     int type = 0;
     int nel = 0, nbasis = 0, nwords = 1;
     int nocc_alpha = 0, nocc_beta = 0;
-    bool t_exch = true, t_no_brillouin = false;
+    bool t_exch = true, t_no_brillouin = false, t_hphf = false;
     double ecore = 0.0;
     // FCIDUMP
     std::vector<double> umat, tmat;
@@ -537,16 +537,126 @@ inline double get_spawn_helement(const System &S, const int *nI, const Excitatio
     return E.parity ? -h : h;
 }
 
+// ---- HPHF functions (src/HPHFIntegrals.fpp, src/HPHFRandExcit.F90, src/DetBitOps.F90:648-740,819-848) ----------
+// spin_sym_ilut: swap the alpha and beta occupation of every spatial orbital
+inline void spin_sym_ilut(const uint64_t *a, uint64_t *b, int nw) {
+    for (int w = 0; w < nw; ++w) b[w] = ((a[w] & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((a[w] & 0x5555555555555555ull) << 1);
+}
+inline bool TestClosedShellDet(const uint64_t *a, int nw) {
+    for (int w = 0; w < nw; ++w) if (((a[w] & 0xAAAAAAAAAAAAAAAAull) >> 1) ^ (a[w] & 0x5555555555555555ull)) return false;
+    return true;
+}
+// CalcOpenOrbs: beta electrons whose alpha partner is empty (= half the singly occupied orbitals for Ms = 0)
+inline int CalcOpenOrbs(const uint64_t *a, int nw) {
+    int n = 0;
+    for (int w = 0; w < nw; ++w) n += __builtin_popcountll(~((a[w] & 0xAAAAAAAAAAAAAAAAull) >> 1) & (a[w] & 0x5555555555555555ull));
+    return n;
+}
+// DetBitLT (src/DetBitOps.F90:502-534): signed word comparison, word 0 first
+inline int DetBitLT(const uint64_t *a, const uint64_t *b, int nw) {
+    for (int w = 0; w < nw; ++w) {
+        if ((int64_t)a[w] < (int64_t)b[w]) return 1;
+        if ((int64_t)a[w] > (int64_t)b[w]) return -1;
+    }
+    return 0;
+}
+// FindBitExcitLevel(..., t_hphf_ic = .true.) (src/DetBitOps.F90:140-170, 819-848)
+inline int excit_level_hphf(const System &S, const uint64_t *a, const uint64_t *b) {
+    const int nw = S.nwords;
+    if (!S.t_hphf || (TestClosedShellDet(a, nw) && TestClosedShellDet(b, nw))) return excit_level(a, b, nw);
+    uint64_t a2[2], b2[2];
+    spin_sym_ilut(a, a2, nw); spin_sym_ilut(b, b2, nw);
+    return std::min(std::min(excit_level(a, b, nw), excit_level(a, b2, nw)), std::min(excit_level(a2, b, nw), excit_level(a2, b2, nw)));
+}
+// hphf_off_diag_helement_norm (src/HPHFIntegrals.fpp:62-150), even S
+inline double hphf_off_diag_helement(const System &S, const uint64_t *iI, const uint64_t *iJ) {
+    const int nw = S.nwords;
+    if (DetBitLT(iI, iJ, nw) == 0) return 0.0;
+    double hel = get_helement(S, iI, iJ);
+    if (TestClosedShellDet(iI, nw)) {
+        if (!TestClosedShellDet(iJ, nw)) hel = hel * std::sqrt(2.0);
+    } else if (TestClosedShellDet(iJ, nw)) {
+        hel = hel * std::sqrt(2.0);
+    } else {
+        uint64_t iI2[2] = {0, 0};
+        spin_sym_ilut(iI, iI2, nw);                                  // FindExcitBitDetSym
+        if (excit_level(iI2, iJ, nw) <= 2) {
+            const int OpenOrbsI = CalcOpenOrbs(iI, nw);
+            const double MatEl2 = get_helement(S, iI2, iJ);
+            if (OpenOrbsI % 2 == 0) hel = hel + MatEl2; else hel = hel - MatEl2;
+        }
+    }
+    return hel;
+}
+// hphf_diag_helement (src/HPHFIntegrals.fpp:348-411), even S; ECore included by get_helement
+inline double hphf_diag_helement(const System &S, const uint64_t *iI) {
+    const int nw = S.nwords;
+    double hel = get_helement(S, iI, iI);
+    if (!TestClosedShellDet(iI, nw)) {
+        uint64_t iI2[2] = {0, 0};
+        spin_sym_ilut(iI, iI2, nw);
+        if (excit_level(iI, iI2, nw) <= 2) {
+            const double MatEl2 = get_helement(S, iI, iI2);
+            if (CalcOpenOrbs(iI, nw) % 2 == 1) hel = hel - MatEl2; else hel = hel + MatEl2;
+        }
+    }
+    return hel;
+}
+// CalcNonUniPGen (src/HPHFRandExcit.F90:686-821) for the PCHB class generator: get_pgen_sd
+// (src/excitation_generators.F90:141-158) with UniformSingles_get_pgen / calc_pgen_symrandexcit2 and
+// GAS_doubles_PCHB_get_pgen
+inline double calc_pgen_pchb(const System &S, const int *nI, const uint64_t *ilutI, const int *ex, int ic) {
+    if (ic == 1) {
+        int ElecsWNoExcits = 0;
+        std::vector<int> occ(S.n_classes, 0), unocc(S.n_classes, 0);
+        for (int c = 0; c < S.n_classes; ++c) {
+            for (int o : S.class_orbs[c]) { if (is_occ(ilutI, o)) ++occ[c]; else ++unocc[c]; }
+            if (unocc[c] == 0) ElecsWNoExcits += occ[c];
+        }
+        const int NExcitA = unocc[S.class_of_spinorb[ex[0] - 1]];
+        double pgen = (1 - S.p_doubles) / ((double)(NExcitA * (S.nel - ElecsWNoExcits)));
+        pgen = pgen / S.p_singles;
+        return S.p_singles * pgen;
+    }
+    if (ic == 2) return (1.0 - S.p_singles) * pchb_double_get_pgen(S, ex);
+    return 0.0;
+}
+// gen_hphf_excit (src/HPHFRandExcit.F90:175-476) around the PCHB generator.  The matrix element between the two
+// HPHF functions is hphf_off_diag_helement_norm (what get_spawn_helement returns with tGenMatHEl = .false.,
+// src/fcimc_initialisation.fpp:2198-2203; the in-generator evaluation is the same number).
+inline void gen_hphf_excit(const System &S, const int *nI, const uint64_t *ilutI, Stream &rng, Excitation &E, double &HEl) {
+    const int nw = S.nwords;
+    HEl = 0.0;
+    gen_excit_pchb(S, nI, ilutI, rng, E);
+    if (!E.valid) return;
+    if (!TestClosedShellDet(E.ilutJ, nw)) {
+        uint64_t iJ2[2] = {0, 0};
+        spin_sym_ilut(E.ilutJ, iJ2, nw);                             // ReturnAlphaOpenDet
+        const bool tSwapped = DetBitLT(E.ilutJ, iJ2, nw) == 1;
+        const int ExcitLevel = excit_level(ilutI, iJ2, nw);          // to the determinant that was NOT generated
+        if (ExcitLevel == 0) { E.valid = false; return; }            // excitation inside one HPHF function: null
+        if (ExcitLevel <= 2) {
+            int ex2[4]; bool tSign;
+            excitation_between(ilutI, iJ2, S.nbasis, S.nel, ex2, tSign);
+            E.pgen = E.pgen + calc_pgen_pchb(S, nI, ilutI, ex2, ExcitLevel);
+        }
+        if (tSwapped) { E.ilutJ[0] = iJ2[0]; E.ilutJ[1] = iJ2[1]; decode(E.ilutJ, S.nbasis, E.nJ); }
+    }
+    HEl = hphf_off_diag_helement(S, ilutI, E.ilutJ);
+}
+
 // get_diagonal_matel (src/matel_getter.F90:30-58) minus nothing; caller subtracts Hii
 inline double get_diagonal_matel(const System &S, const uint64_t *ilut) {
+    if (S.t_hphf) return hphf_diag_helement(S, ilut);
     if (S.type == NECI_SYS_HUBBARD_RS) return S.diag_rs_hub(ilut);
     int nI[128]; decode(ilut, S.nbasis, nI);
     return S.sltcnd_0(nI) + S.ecore;
 }
 // get_off_diagonal_matel, src/matel_getter.F90:61-105
 inline double get_off_diagonal_matel(const System &S, const uint64_t *ilut, const uint64_t *ilut_ref) {
-    const int exlevel = excit_level(ilut_ref, ilut, S.nwords);
-    if (exlevel == 2 || (exlevel == 1 && S.t_no_brillouin)) return get_helement(S, ilut, ilut_ref);
+    const int exlevel = excit_level_hphf(S, ilut_ref, ilut);
+    if (exlevel == 2 || (exlevel == 1 && S.t_no_brillouin))
+        return S.t_hphf ? hphf_off_diag_helement(S, ilut_ref, ilut) : get_helement(S, ilut, ilut_ref);
     return 0.0;
 }
 

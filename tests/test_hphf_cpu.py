@@ -1,0 +1,114 @@
+"""HPHF functions (src/HPHFIntegrals.fpp, src/HPHFRandExcit.F90) on the oracle, pinned by an independent
+construction: the Hamiltonian in the basis of spin-adapted pairs Phi_I = (|I> + (-1)^open |I_flipped>) / sqrt 2 built
+from the determinant Hamiltonian (itself pinned in test_oracle_golden.py) must equal the oracle's HPHF elements, and
+its spectrum must be the even-S part of the determinant spectrum."""
+import numpy as np
+
+import helpers
+from neci_stable_b200 import capi, host, driver
+from neci_stable_b200.capi import ST
+
+BETA, ALPHA = 0x5555555555555555, 0xAAAAAAAAAAAAAAAA
+
+
+def _flip(w):
+    return ((w & ALPHA) >> 1) | ((w & BETA) << 1)
+
+
+def _open_orbs(w):
+    return bin(~((w & ALPHA) >> 1) & (w & BETA) & ((1 << 64) - 1)).count("1")
+
+
+def _setup(hphf, n_spat=5, nel=4, seed=3, **kw):
+    s = host.random_fcidump_system(n_spat, nel, sparse=0.9, sparse_t=0.9, seed=seed)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=60000, max_spawned=60000, hphf=hphf, **kw)
+    return s, o, hii
+
+
+def _hphf_basis(s):
+    """(unique representatives, index of every determinant's function, sign of the determinant inside it)"""
+    dets = helpers.all_dets(s)
+    words = [int(np.uint64(s.ilut(d)[0])) for d in dets]
+    index = {w: i for i, w in enumerate(words)}
+    reps = []
+    for w in words:
+        f = _flip(w)
+        if f == w or w > f:                 # closed shell, or the member IsAllowedHPHF accepts (the larger one; 1 word, no sign bit)
+            reps.append(w)
+    return dets, words, index, reps
+
+
+def test_hphf_matrix_elements_equal_the_projected_determinant_hamiltonian():
+    s, o_det, _ = _setup(False)
+    _, o_h, _ = _setup(True)
+    dets, words, index, reps = _hphf_basis(s)
+    H = helpers.hamiltonian_matrix(o_det, s, dets)
+    n, m = len(words), len(reps)
+    T = np.zeros((n, m))
+    for k, w in enumerate(reps):
+        f = _flip(w)
+        if f == w:
+            T[index[w], k] = 1.0
+        else:
+            sgn = 1.0 if _open_orbs(w) % 2 == 0 else -1.0
+            T[index[w], k] = 1 / np.sqrt(2); T[index[f], k] = sgn / np.sqrt(2)
+    Hp = T.T @ H @ T
+    il = np.array(reps, dtype=np.uint64).view(np.int64).reshape(-1, 1)
+    I = np.repeat(np.arange(m), m); J = np.tile(np.arange(m), m)
+    Ho = o_h.probe_helement(il[I], il[J]).reshape(m, m)
+    assert np.allclose(Ho, Hp, rtol=1e-12, atol=1e-12)
+    # the HPHF spectrum is a subset of the determinant spectrum, and holds its (singlet) ground state
+    ev_full = np.linalg.eigvalsh(H); ev_h = np.linalg.eigvalsh(Hp)
+    assert abs(ev_h[0] - ev_full[0]) < 1e-10
+    for e in ev_h:
+        assert np.min(np.abs(ev_full - e)) < 1e-9
+
+
+def test_gen_hphf_excit_is_complete_and_unbiased():
+    """The reference's generator criterion (src/unit_test_helpers.F90:438-638) for the HPHF generator: every
+    connected HPHF function is reached, sum 1/pgen / n_draws -> 1 per function, and the returned element is the
+    HPHF matrix element."""
+    s, o, _ = _setup(True, n_spat=5, nel=4, seed=3)
+    dets, words, index, reps = _hphf_basis(s)
+    il = np.array(reps, dtype=np.uint64).view(np.int64).reshape(-1, 1)
+    m = len(reps)
+    for src in (0, m // 2, m - 1):
+        n_draw = 600000
+        out = o.probe_gen_excit(np.repeat(il[src:src + 1], n_draw, axis=0), np.arange(n_draw, dtype=np.int32), 1)
+        valid = out["pgen"] > 0
+        tgt = out["ilut_j"][valid, 0].view(np.uint64)
+        assert set(int(t) for t in tgt) <= set(reps)                   # only allowed representatives come out
+        assert int(np.uint64(il[src, 0])) not in set(int(t) for t in tgt)
+        hrow = o.probe_helement(np.repeat(il[src:src + 1], m, axis=0), il)
+        connected = {reps[k] for k in range(m) if k != src and abs(hrow[k]) > 1e-12}
+        acc, cnt = {}, {}
+        for t, p, h in zip(tgt, out["pgen"][valid], out["hel"][valid]):
+            t = int(t); acc[t] = acc.get(t, 0.0) + 1.0 / p; cnt[t] = cnt.get(t, 0) + 1
+            assert abs(h - hrow[reps.index(t)]) < 1e-12
+        assert connected <= set(acc)
+        for t in connected:                                            # unbiased within 4.5 standard errors of the hit count
+            assert abs(acc[t] / n_draw - 1.0) < 4.5 / np.sqrt(cnt[t]) + 0.01, (t, acc[t] / n_draw, cnt[t])
+
+
+def test_hphf_fciqmc_converges_to_the_ground_state():
+    """FCIQMC on HPHF functions: projected energy and shift within blocking error bars of exact diagonalisation
+    (the north_star criterion), and only allowed representatives are ever occupied."""
+    s, o, hii = _setup(True, n_spat=5, nel=4, seed=3, initiator=False)
+    o_det = _setup(False)[1]
+    e0 = np.linalg.eigvalsh(helpers.hamiltonian_matrix(o_det, s, helpers.all_dets(s)))[0]
+    run = driver.FciMC(s, o, hii, tau=0.002, init_walkers=3000, steps_sft=10, sft_damp=0.1)
+    run.seed_reference(10)
+    run.run(8000)
+    hist = [h for h in run.history if h["varying"]][100:]
+    num = np.array([h["enum_cyc"] for h in hist]); den = np.array([h["hf_cyc"] for h in hist])
+    e, err = driver.ratio_estimate(num, den)
+    assert abs(e + hii - e0) < max(5 * err, 2e-3), (e + hii, e0, err)
+    sm, serr = driver.blocking([h["shift"] for h in hist])
+    assert abs(sm + hii - e0) < max(5 * serr, 2e-2), (sm + hii, e0, serr)
+    d, _, _ = o.download_walkers()
+    w = d[np.abs(host.signs_of(d, s.nw)) > 0][:, 0].view(np.uint64)
+    assert len(w) > 10
+    for x in w:
+        x = int(x); f = _flip(x)
+        assert f == x or x > f
