@@ -16,6 +16,12 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 
 #define NG_MAX_BASIS 128
+// Kernel variant selector: the three system types of the ABI plus the HPHF flavour of the FCIDUMP/PCHB system.  HPHF
+// is a compile-time variant because its code inside the spawning kernel costs the determinant runs 20 % when it is
+// merely present behind a run-time flag (registers and instruction cache).
+#define NG_SYS_PCHB_HPHF 4
+__host__ __device__ constexpr bool sys_pchb(int s) { return s == NECI_SYS_FCIDUMP_PCHB || s == NG_SYS_PCHB_HPHF; }
+__host__ __device__ constexpr bool sys_hphf(int s) { return s == NG_SYS_PCHB_HPHF; }
 #define NG_MAX_CLASSES 16
 
 // ---------------------------------------------------------------------------

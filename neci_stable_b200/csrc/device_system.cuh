@@ -148,13 +148,14 @@ __device__ __forceinline__ double diag_rs(const Params &P, const Det<NW> &d) {  
 }
 
 // (defined with the other HPHF functions below; FCIDUMP systems only)
+template <int NW, bool HPHF> __device__ __forceinline__ int excit_level_ref(const Det<NW> &ref, const Det<NW> &d);
 template <int NW> __device__ double hphf_diag_dispatch(const Params &P, const Det<NW> &d);
 template <int NW> __device__ double hphf_off_diag_dispatch(const Params &P, const Det<NW> &I, const Det<NW> &J);
 
 // get_diagonal_matel (src/matel_getter.F90:30-58): full H_ii (ECore included)
 template <int NW, int SYS>
 __device__ __forceinline__ double diagonal_matel(const Params &P, const Det<NW> &d) {
-    if (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) return hphf_diag_dispatch<NW>(P, d);
+    if (sys_hphf(SYS)) return hphf_diag_dispatch<NW>(P, d);
     if (SYS == NECI_SYS_HUBBARD_RS) return diag_rs(P, d);
     if (SYS == NECI_SYS_HUBBARD_K) return diag_k(P, d) + P.ecore;
     return sltcnd_0(P, d) + P.ecore;
@@ -190,9 +191,9 @@ __device__ double helement(const Params &P, const Det<NW> &I, const Det<NW> &J) 
 template <int NW, int SYS>
 __device__ __forceinline__ double off_diagonal_matel(const Params &P, const Det<NW> &d) {
     const Det<NW> ref = ref_det<NW>(P);
-    const int ex = excit_level_ref(P, ref, d);
+    const int ex = excit_level_ref<NW, sys_hphf(SYS)>(ref, d);
     if (ex == 2 || (ex == 1 && P.t_no_brillouin))
-        return (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) ? hphf_off_diag_dispatch<NW>(P, ref, d) : helement<NW, SYS>(P, d, ref);
+        return sys_hphf(SYS) ? hphf_off_diag_dispatch<NW>(P, ref, d) : helement<NW, SYS>(P, d, ref);
     return 0.0;
 }
 
@@ -476,9 +477,9 @@ template <int NW> __device__ __forceinline__ bool det_less(const Det<NW> &a, con
     return (long long)a.w[NW - 1] < (long long)b.w[NW - 1];
 }
 // FindBitExcitLevel(ref, det, t_hphf_ic = .true.): the smallest level over the spin-flipped partners
-template <int NW> __device__ __forceinline__ int excit_level_ref(const Params &P, const Det<NW> &ref, const Det<NW> &d) {
+template <int NW, bool HPHF> __device__ __forceinline__ int excit_level_ref(const Det<NW> &ref, const Det<NW> &d) {
     int ic = excit_level(ref, d);
-    if (P.t_hphf && !(closed_shell(ref) && closed_shell(d))) {
+    if (HPHF && !(closed_shell(ref) && closed_shell(d))) {
         const Det<NW> r2 = spin_sym(ref), d2 = spin_sym(d);
         ic = min(min(ic, excit_level(ref, d2)), min(excit_level(r2, d), excit_level(r2, d2)));
     }
@@ -570,9 +571,9 @@ __device__ bool hphf_fixup(const Params &P, const Det<NW> &d, Excit<NW> &E, doub
     return true;
 }
 
-template <int NW> __device__ double hphf_diag_dispatch(const Params &P, const Det<NW> &d) { return hphf_diag<NW, NECI_SYS_FCIDUMP_PCHB>(P, d); }
+template <int NW> __device__ double hphf_diag_dispatch(const Params &P, const Det<NW> &d) { return hphf_diag<NW, NG_SYS_PCHB_HPHF>(P, d); }
 template <int NW> __device__ double hphf_off_diag_dispatch(const Params &P, const Det<NW> &I, const Det<NW> &J) {
-    return hphf_off_diag<NW, NECI_SYS_FCIDUMP_PCHB>(P, I, J);
+    return hphf_off_diag<NW, NG_SYS_PCHB_HPHF>(P, I, J);
 }
 
 // get_spawn_helement = get_helement_det_only (src/Determinants.F90:508-554)

@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(NG_BLOCK) k_trial_energy(Params P, WalkerList 
         // CalcParentFlag runs before SumEContrib, so the initiator flag is this iteration's
         bool init = (f & F_INIT) != 0;
         if (P.t_trunc_initiator) {
-            const int exl = excit_level_ref(P, ref, load_det<NW>(L, i));
+            const int exl = P.t_hphf ? excit_level_ref<NW, true>(ref, load_det<NW>(L, i)) : excit_level(ref, load_det<NW>(L, i));
             init = parent_is_initiator(P, init, fabs(s), exl, (f & F_DETERM) != 0);
         }
         const double c = L.trial_amp[i] * s;
@@ -587,7 +587,7 @@ __global__ void k_probe_helement(Params P, const long long *ii, const long long 
         Det<NW> a, b;
         a.w[0] = (u64)ii[i * NW]; b.w[0] = (u64)ij[i * NW];
         if (NW > 1) { a.w[NW - 1] = (u64)ii[i * NW + NW - 1]; b.w[NW - 1] = (u64)ij[i * NW + NW - 1]; }
-        if (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf && !det_eq(a, b)) out[i] = hphf_off_diag<NW, SYS>(P, a, b);
+        if (sys_hphf(SYS) && !det_eq(a, b)) out[i] = hphf_off_diag<NW, SYS>(P, a, b);
         else out[i] = helement<NW, SYS>(P, a, b);
     }
 }
@@ -601,12 +601,12 @@ __global__ void k_probe_gen_excit(Params P, const long long *iluts, const int *a
         generate_excitation<NW, SYS>(P, d, rng, E);
         ic[i] = E.ic;
         double rh_hphf = 0.0;
-        if (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf && E.valid) E.valid = hphf_fixup<NW, SYS>(P, d, E, rh_hphf);
+        if (sys_hphf(SYS) && E.valid) E.valid = hphf_fixup<NW, SYS>(P, d, E, rh_hphf);
         if (E.valid) {
             ilut_j[i * NW] = (long long)E.detJ.w[0]; if (NW > 1) ilut_j[i * NW + NW - 1] = (long long)E.detJ.w[NW - 1];
             ex[4 * i] = E.src1; ex[4 * i + 1] = E.src2; ex[4 * i + 2] = E.tgt1; ex[4 * i + 3] = E.tgt2;
             par[i] = E.parity ? 1 : 0; pgen[i] = E.pgen;
-            hel[i] = (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) ? rh_hphf : spawn_helement<NW, SYS>(P, d, E);
+            hel[i] = sys_hphf(SYS) ? rh_hphf : spawn_helement<NW, SYS>(P, d, E);
         } else {
             for (int w = 0; w < NW; ++w) ilut_j[i * NW + w] = 0;
             ex[4 * i] = ex[4 * i + 1] = ex[4 * i + 2] = ex[4 * i + 3] = 0;

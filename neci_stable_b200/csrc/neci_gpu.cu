@@ -115,14 +115,16 @@ struct neci_gpu_engine {
 // dispatch on (words per determinant, system type)
 #define NG_DISPATCH(e, BODY)                                                                              \
     do {                                                                                                  \
-        const int _key = (e)->nw * 10 + (e)->cfg.system_type;                                             \
+        const int _key = (e)->nw * 10 + (((e)->cfg.t_hphf && (e)->cfg.system_type == NECI_SYS_FCIDUMP_PCHB) ? NG_SYS_PCHB_HPHF : (e)->cfg.system_type); \
         switch (_key) {                                                                                   \
             case 11: { constexpr int NW = 1, SYS = NECI_SYS_FCIDUMP_PCHB; BODY; } break;                  \
             case 12: { constexpr int NW = 1, SYS = NECI_SYS_HUBBARD_RS; BODY; } break;                    \
             case 13: { constexpr int NW = 1, SYS = NECI_SYS_HUBBARD_K; BODY; } break;                     \
+            case 14: { constexpr int NW = 1, SYS = NG_SYS_PCHB_HPHF; BODY; } break;                       \
             case 21: { constexpr int NW = 2, SYS = NECI_SYS_FCIDUMP_PCHB; BODY; } break;                  \
             case 22: { constexpr int NW = 2, SYS = NECI_SYS_HUBBARD_RS; BODY; } break;                    \
             case 23: { constexpr int NW = 2, SYS = NECI_SYS_HUBBARD_K; BODY; } break;                     \
+            case 24: { constexpr int NW = 2, SYS = NG_SYS_PCHB_HPHF; BODY; } break;                       \
             default: return (e)->fail("unsupported (nifd, system_type) = (%d, %d)", (e)->nw - 1, (e)->cfg.system_type); \
         }                                                                                                 \
     } while (0)

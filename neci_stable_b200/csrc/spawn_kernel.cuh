@@ -183,7 +183,7 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
         finalize_excit(d, E);
         bool cancelled = false;
         double rh_hphf = 0.0;
-        if (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) {
+        if (sys_hphf(SYS)) {
             // gen_hphf_excit wraps the generator (fcimc_initialisation.fpp:2162-2165): representative, pgen, element
             if (!hphf_fixup<NW, SYS>(P, d, E, rh_hphf)) { cancelled = true; acc.valid -= 1; acc.invalid += 1; }
         }
@@ -194,7 +194,7 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
         }
         if (!cancelled) {
             const double prob = E.pgen * P.av_mc_excits;
-            const double rh = (SYS == NECI_SYS_FCIDUMP_PCHB && P.t_hphf) ? rh_hphf : spawn_helement<NW, SYS>(P, d, E);
+            const double rh = sys_hphf(SYS) ? rh_hphf : spawn_helement<NW, SYS>(P, d, E);
             const double ww = (info & 1) ? -1.0 : 1.0;
             if (P.t_tau_search) {
                 // log_spawn_magnitude (tau/tau_search_conventional.F90:138-260): gamma = |H_ij| / (prob / p_class)
@@ -265,7 +265,7 @@ __device__ __forceinline__ void stage_generate(const Params &P, const WalkerList
     double r_round = 0.0;
     if (active) {
         Stream rng(P.seed, A.iter, h, p, RNG_ATTEMPT);
-        if (SYS == NECI_SYS_FCIDUMP_PCHB) {
+        if (sys_pchb(SYS)) {
             if (rng.draw() < P.p_singles) push_s = true;                 // gen_exc_sd: single, generated in stage B3
             else { gen_pchb_double(P, d, rng, E); E.pgen = E.pgen * P.p_doubles; }
         } else generate_excitation_core<NW, SYS>(P, d, rng, E);
@@ -282,7 +282,7 @@ __device__ __forceinline__ void stage_generate(const Params &P, const WalkerList
         S.q_orbs[qe] = (u32)E.src1 | ((u32)E.src2 << 8) | ((u32)E.tgt1 << 16) | ((u32)E.tgt2 << 24);
         S.q_misc[qe] = (u32)info | ((u32)E.ic << 8);
     }
-    if (SYS == NECI_SYS_FCIDUMP_PCHB) {
+    if (sys_pchb(SYS)) {
         const int qs = queue_reserve(&S.s_count, push_s);
         if (push_s) {
             S.s_d0[qs] = d.w[0]; if (NW > 1) S.s_d1[qs] = d.w[NW - 1];
@@ -347,7 +347,7 @@ __device__ __forceinline__ void serve_queues(const Params &P, const WalkerList &
         stage_evaluate<NW, SYS>(P, L, SB, A, S, qc - n, n, acc);
         __syncthreads();
     }
-    if (SYS == NECI_SYS_FCIDUMP_PCHB) {
+    if (sys_pchb(SYS)) {
         for (;;) {
             const int sc = S.s_count;
             if (sc < level) break;
@@ -456,7 +456,7 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
                     const int f0 = f;
                     const double K = ld_K[kk], O = ld_O[kk];
                     const bool core = (f & F_DETERM) != 0;
-                    const int exl = excit_level_ref(P, ref, d);        // FindBitExcitLevel(..., t_hphf_ic = .true.)
+                    const int exl = excit_level_ref<NW, sys_hphf(SYS)>(ref, d);        // FindBitExcitLevel(..., t_hphf_ic = .true.)
                     const double as = fabs(s);
                     // CalcParentFlag / TestInitiator_explicit (fcimc_helper.F90:1036-1243)
                     if (P.t_trunc_initiator) {
