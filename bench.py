@@ -398,6 +398,9 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
+        # the capture was taken on the default workload at 1e7 walkers: only that run may quote it
+        if args.workload != "n2_14e28o_pchb" or abs(args.walkers - 1.0e7) > 1.0:
+            raise KeyError("no ncu capture for this configuration")
         traffic = tj.get("k_spawn_dram_bytes_per_launch")
         # the kernel is bound by instruction issue, not by HBM: the committed ncu capture's
         # issue-slot utilisation and warp-instruction count are repeated here beside the HBM fraction
