@@ -227,7 +227,7 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
         NG_DISPATCH(e, {
             CK(cudaFuncSetAttribute(k_spawn<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared<NW>)));
             CK(cudaFuncSetAttribute(k_spawn_heavy<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared<NW>)));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spawn<NW, SYS>, NG_BLOCK, sizeof(K1Shared<NW>)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spawn<NW, SYS>, K1_BLOCK, sizeof(K1Shared<NW>)));
         });
         if (per_sm < 1) per_sm = 1;
         e->rows_spawn = nsm * per_sm; e->rows_heavy = nsm * per_sm;
@@ -692,8 +692,8 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
     CK(cudaEventRecord(e->ev[1], e->stream));
     e->n_launch += 2;
     double *p_spawn = e->d_partials, *p_heavy = e->d_partials + (size_t)e->rows_spawn * NECI_ST_COUNT;
-    NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, NG_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
-    NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, NG_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
+    NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, K1_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
+    NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, K1_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
     if (e->cfg.nranks > 1) {
         e->n_launch += 1;
         if (e->nw == 1) k_partition<1><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);

@@ -25,11 +25,15 @@
 
 namespace ng {
 
-#define NG_BLOCK 256
+#define NG_BLOCK 256         /* block size of the streaming kernels */
+#ifndef K1_BLOCK
+#define K1_BLOCK 256         /* block size of the spawning kernel (measured: 128 -> 0.87 ms, 256 -> 0.78 ms, 512 -> 0.80 ms per launch) */
+#endif
+#define K1_CTAS_PER_SM (1024 / K1_BLOCK)
 #define NG_HEAVY 4096        /* attempts per determinant handled inside a tile */
 #define K1_SPT 2             /* slots per thread and tile */
-#define K1_TILE (NG_BLOCK * K1_SPT)
-#define K1_QCAP (2 * NG_BLOCK)
+#define K1_TILE (K1_BLOCK * K1_SPT)
+#define K1_QCAP (2 * K1_BLOCK)
 #define K1_MAPW 1024         /* attempts per window of the attempt -> parent map */
 
 struct SpawnBuf {
@@ -94,8 +98,8 @@ template <int NW> struct K1Shared {
     u32 s_att[K1_QCAP];
     u32 s_misc[K1_QCAP];
     int roi[NG_MAX_BASIS];
-    double wacc[NG_BLOCK / 32][W_COUNT];
-    int wsum[NG_BLOCK / 32];
+    double wacc[K1_BLOCK / 32][W_COUNT];
+    int wsum[K1_BLOCK / 32];
     int q_count, s_count;
     int bloom_cnt[2];
     unsigned long long bloom_max[2];
@@ -341,7 +345,7 @@ __device__ __forceinline__ void serve_queues(const Params &P, const WalkerList &
     for (;;) {
         const int qc = S.q_count;
         if (qc < level) break;
-        const int n = min(qc, NG_BLOCK);
+        const int n = min(qc, K1_BLOCK);
         __syncthreads();
         if (threadIdx.x == 0) S.q_count = qc - n;
         stage_evaluate<NW, SYS>(P, L, SB, A, S, qc - n, n, acc);
@@ -351,7 +355,7 @@ __device__ __forceinline__ void serve_queues(const Params &P, const WalkerList &
         for (;;) {
             const int sc = S.s_count;
             if (sc < level) break;
-            const int n = min(sc, NG_BLOCK);
+            const int n = min(sc, K1_BLOCK);
             __syncthreads();
             if (threadIdx.x == 0) S.s_count = sc - n;
             stage_singles<NW, SYS>(P, L, SB, A, S, sc - n, n, acc);
@@ -363,8 +367,8 @@ __device__ __forceinline__ void serve_queues(const Params &P, const WalkerList &
 template <int NW>
 __device__ __forceinline__ void k1_init_shared(const Params &P, K1Shared<NW> &S) {
 #pragma unroll 1
-    for (int i = threadIdx.x; i < P.nbasis; i += NG_BLOCK) S.roi[i] = P.random_orb_index[i];
-    for (int i = threadIdx.x; i < (NG_BLOCK / 32) * W_COUNT; i += NG_BLOCK) (&S.wacc[0][0])[i] = 0.0;
+    for (int i = threadIdx.x; i < P.nbasis; i += K1_BLOCK) S.roi[i] = P.random_orb_index[i];
+    for (int i = threadIdx.x; i < (K1_BLOCK / 32) * W_COUNT; i += K1_BLOCK) (&S.wacc[0][0])[i] = 0.0;
     if (threadIdx.x == 0) { S.q_count = 0; S.s_count = 0; S.bloom_cnt[0] = S.bloom_cnt[1] = 0; S.bloom_max[0] = S.bloom_max[1] = 0ull; }
     if (threadIdx.x < 4) { S.tau_cnt[threadIdx.x] = 0; S.tau_gamma[threadIdx.x] = 0ull; }
 }
@@ -380,12 +384,12 @@ __device__ __forceinline__ void k1_flush(const WalkerList &L, K1Shared<NW> &S, c
         S.wacc[warp][W_MAXSP] = mx;
     }
     double *row = partials + (size_t)blockIdx.x * NECI_ST_COUNT;
-    for (int k = threadIdx.x; k < NECI_ST_COUNT; k += NG_BLOCK) row[k] = 0.0;
+    for (int k = threadIdx.x; k < NECI_ST_COUNT; k += K1_BLOCK) row[k] = 0.0;
     __syncthreads();
     if (threadIdx.x < W_COUNT) {
         const int k = threadIdx.x;
         double t = S.wacc[0][k];
-        for (int w = 1; w < NG_BLOCK / 32; ++w) t = (k == W_MAXSP) ? fmax(t, S.wacc[w][k]) : t + S.wacc[w][k];
+        for (int w = 1; w < K1_BLOCK / 32; ++w) t = (k == W_MAXSP) ? fmax(t, S.wacc[w][k]) : t + S.wacc[w][k];
         S.wacc[0][k] = t;
     }
     __syncthreads();
@@ -432,7 +436,7 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
         double ld_s[K1_SPT], ld_K[K1_SPT], ld_O[K1_SPT]; int ld_f[K1_SPT]; Det<NW> ld_d[K1_SPT];
 #pragma unroll
         for (int kk = 0; kk < K1_SPT; ++kk) {
-            const long long slot = tile * K1_TILE + kk * NG_BLOCK + tid;
+            const long long slot = tile * K1_TILE + kk * K1_BLOCK + tid;
             ld_s[kk] = 0.0; ld_K[kk] = 0.0; ld_O[kk] = 0.0; ld_f[kk] = 0; ld_d[kk].w[0] = 0; if (NW > 1) ld_d[kk].w[NW - 1] = 0;
             if (slot < n_list) {
                 ld_s[kk] = __ldcs(&L.sgn[slot]); ld_d[kk].w[0] = __ldcs(&L.det0[slot]);
@@ -442,7 +446,7 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
         }
 #pragma unroll
         for (int kk = 0; kk < K1_SPT; ++kk) {
-            const int idx = kk * NG_BLOCK + tid;
+            const int idx = kk * K1_BLOCK + tid;
             const long long slot = tile * K1_TILE + idx;
             int nsp = 0;
             unsigned char info = 0;
@@ -546,9 +550,9 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
             __syncthreads();
             int wbase = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < NG_BLOCK / 32; ++w) { const int v = S.wsum[w]; if (w < warp) wbase += v; total += v; }
+            for (int w = 0; w < K1_BLOCK / 32; ++w) { const int v = S.wsum[w]; if (w < warp) wbase += v; total += v; }
             off_k[kk] = run + wbase + incl - nsp_k[kk];
-            S.p_off[kk * NG_BLOCK + tid] = off_k[kk];
+            S.p_off[kk * K1_BLOCK + tid] = off_k[kk];
             run += total;
             __syncthreads();
         }
@@ -556,7 +560,7 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
 }
 
 template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
+__global__ void __launch_bounds__(K1_BLOCK, K1_CTAS_PER_SM) k_spawn(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     K1Shared<NW> &S = *reinterpret_cast<K1Shared<NW> *>(k1_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -596,7 +600,7 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
                 we = min(T, wb + K1_MAPW); base = wb;
 #pragma unroll
                 for (int kk = 0; kk < K1_SPT; ++kk) {
-                    const int idx = kk * NG_BLOCK + tid;
+                    const int idx = kk * K1_BLOCK + tid;
                     const int lo = max(off_k[kk], wb), hi = min(off_k[kk] + nsp_k[kk], we);
                     const bool big = hi - lo > 4;
                     if (!big) {
@@ -614,7 +618,7 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
                 }
             }
         }
-        serve_queues<NW, SYS>(P, L, SB, A, S, drain ? 1 : NG_BLOCK, acc);   // starts with a barrier (publishes p_* and the map)
+        serve_queues<NW, SYS>(P, L, SB, A, S, drain ? 1 : K1_BLOCK, acc);   // starts with a barrier (publishes p_* and the map)
         if (drain) break;
         {
             const int a = base + tid;
@@ -627,7 +631,7 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
                 h = S.p_h[lo]; info = S.p_info[lo]; p = (u32)(a - S.p_off[lo]);
             }
             stage_generate<NW, SYS>(P, L, A, S, active, dp, h, info, p, acc);
-            base += NG_BLOCK;
+            base += K1_BLOCK;
         }
     }
     serve_queues<NW, SYS>(P, L, SB, A, S, 1, acc);
@@ -636,7 +640,7 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_spawn(Params P, WalkerList L, S
 
 // Attempts of the deferred heavy determinants (> NG_HEAVY walkers), spread over the whole grid.
 template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK, 3) k_spawn_heavy(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
+__global__ void __launch_bounds__(K1_BLOCK, K1_CTAS_PER_SM) k_spawn_heavy(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     K1Shared<NW> &S = *reinterpret_cast<K1Shared<NW> *>(k1_smem);
     const int tid = threadIdx.x;
@@ -652,10 +656,10 @@ __global__ void __launch_bounds__(NG_BLOCK, 3) k_spawn_heavy(Params P, WalkerLis
         const int info = (int)(packed & 0xff);
         const Det<NW> dp = load_det<NW>(L, slot);
         const u64 h = det_hash64(dp);
-        const int rounds = (nsp + NG_BLOCK - 1) / NG_BLOCK;
+        const int rounds = (nsp + K1_BLOCK - 1) / K1_BLOCK;
         for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
-            serve_queues<NW, SYS>(P, L, SB, A, S, NG_BLOCK, acc);
-            const int a = rd * NG_BLOCK + tid;
+            serve_queues<NW, SYS>(P, L, SB, A, S, K1_BLOCK, acc);
+            const int a = rd * K1_BLOCK + tid;
             stage_generate<NW, SYS>(P, L, A, S, a < nsp, dp, h, info, (u32)a, acc);
         }
     }
