@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(NG_BLOCK) k_annihilate(Params P, WalkerList L,
                     const long long slot = ht_lookup<NW>(L, d, h, &pos);
                     if (slot >= 0) {
                         const double cur = L.sgn[slot];
-                        const int fl = L.flg[slot];
+                        // the flag word is a separate random sector: only semi-stochastic runs need it here (core
+                        // determinants are never removed); a removal below reads it when it happens
+                        int fl = P.t_semi_stochastic ? L.flg[slot] : 0;
                         const bool tDet = (fl & F_DETERM) != 0;
                         if (fabs(cur) >= 1.e-12 || tDet) {
                             if (cur * s < 0.0) acc[0] += 2.0 * fmin(fabs(cur), fabs(s));
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(NG_BLOCK) k_annihilate(Params P, WalkerList L,
                                 atomicAdd((unsigned long long *)&L.ctr[C_NTOMB], 1ull);
                                 const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NFREEB], 1ull);
                                 L.freeB[k] = (int)slot;
+                                if (!P.t_semi_stochastic) fl = L.flg[slot];
                                 L.flg[slot] = fl | F_REMOVED;
                             }
                         }
