@@ -390,18 +390,22 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
     const int ij = (int)tri((u32)gtid(s1), (u32)gtid(s2));      // fuse_index
     int spin1 = s1 & 1, spin2 = s2 & 1;           // getSpinIndex: 0 alpha, 1 beta
     const int4 pi = __ldg(reinterpret_cast<const int4 *>(P.pchb_pair + (ij - 1)));    // {p_exch, nonempty, pad}
+    // The third draw of the stream is the exchange decision of an opposite-spin pair and the alias number of a
+    // parallel pair.  It is drawn before the two cases part, so that the Philox block behind it is computed once by
+    // the whole warp instead of twice by half of it (the numbers each lane sees are the same as in the reference order).
+    const double u2 = rng.draw();
     int sampler;
     if (spin1 == spin2) sampler = 0;
     else {
         const double pe = __hiloint2double(pi.y, pi.x);
-        if (rng.draw() < pe) { sampler = 2; pGen *= pe; const int t = spin1; spin1 = spin2; spin2 = t; }
+        if (u2 < pe) { sampler = 2; pGen *= pe; const int t = spin1; spin1 = spin2; spin2 = t; }
         else { sampler = 1; pGen *= (1.0 - pe); }
     }
     E.src1 = s1; E.src2 = s2; E.tgt1 = 0; E.tgt2 = 0; E.pgen = pGen;
     // AliasSampler_t::sample
     if (((pi.z >> sampler) & 1) == 0) return;                        // empty sampler: ab = 0
     const PchbEntry *tab = P.pchb + ((size_t)(ij - 1) * 3 + sampler) * P.ab_max;
-    const double rr = rng.draw();
+    const double rr = (spin1 == spin2) ? u2 : rng.draw();
     const int pos = (int)(P.ab_max * rr) + 1;
     const double bias = fmax(P.ab_max * rr + 1 - pos, 0.0);
     const double2 pb = __ldg(reinterpret_cast<const double2 *>(tab + (pos - 1)));                              // prob, bias
