@@ -361,12 +361,17 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
     E.ic = 2; E.valid = false; E.err = 0;
     const int nA = P.nocc_alpha, nB = P.nocc_beta;
     const int AA = nA * (nA - 1) / 2, BB = nB * (nB - 1) / 2, par = AA + BB, AB = nA * nB;
-    double r = rng.draw();
-    double pGen;
+    const double r = rng.draw();
     u64 m1, m2; int k1, k2;                        // the pair = k1-th orbital of mask m1 and k2-th of mask m2
-    if (r < P.p_parallel) {
-        r = (r / P.p_parallel) * par;
-        int idx = (int)floor(r);
+    // pick_biased_elecs rescales r to a pair index by (r / pP) * par or ((r - pP) / (1 - pP)) * AB: one division with
+    // selected operands for the whole warp (the operations each lane performs are the reference's)
+    const bool is_par = r < P.p_parallel;
+    const double num = is_par ? r : r - P.p_parallel;
+    const double den = is_par ? P.p_parallel : 1.0 - P.p_parallel;
+    const double scl = is_par ? (double)par : (double)AB;
+    int idx = (int)floor((num / den) * scl);
+    double pGen = is_par ? P.pgen_pair_par : P.pgen_pair_opp;      // p_parallel / par, (1 - p_parallel) / AB: host quotients
+    if (is_par) {
         u64 mask = NG_ALPHA_MASK;
         if (idx >= AA) { idx -= AA; mask = NG_BETA_MASK; }
         // n1 = ceil((1 + sqrt(9 + 8 idx)) / 2) == smallest n with n (n - 1) / 2 > idx, evaluated in integers
@@ -375,11 +380,7 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
         while ((n1 - 1) * (n1 - 2) / 2 > idx) --n1;
         const int n2 = idx + 1 - ((n1 - 1) * (n1 - 2)) / 2;
         m1 = mask; k1 = n2; m2 = mask; k2 = n1;
-        pGen = P.pgen_pair_par;                     // p_parallel / par, divided once on the host (same IEEE quotient)
     } else {
-        pGen = P.pgen_pair_opp;                     // (1 - p_parallel) / AB
-        r = ((r - P.p_parallel) / (1.0 - P.p_parallel)) * AB;
-        const int idx = (int)floor(r);
         const int q = (nA == 1) ? idx : (int)__umulhi((u32)idx, P.magic_nalpha);   // idx / nA
         m1 = NG_ALPHA_MASK; k1 = 1 + idx - q * nA;
         m2 = NG_BETA_MASK;  k2 = 1 + q;             // == 1 + floor(idx / real(nA))
