@@ -195,7 +195,8 @@ class FciMC:
         self.history.append(dict(iter=self.iter, shift=self.diag_sft, tot_parts=all_tot_parts,
                                  n_dets=allst[ST["TOTWALKERS"]], enum_cyc=allst[ST["ENUMCYC"]], hf_cyc=hf,
                                  proje_corr=proje, proje=proje + self.hii, varying=not self.single_part_phase,
-                                 noathf=hf / self.steps_sft))
+                                 noathf=hf / self.steps_sft, trial_num=allst[ST["TRIAL_NUMERATOR"]],
+                                 trial_den=allst[ST["TRIAL_DENOM"]]))
         self.old_av_walkers = av_walkers
         self.sum_walkers_cyc = 0.0
         self.cyc[:] = 0.0

@@ -1,0 +1,98 @@
+"""End-to-end FCIQMC runs of the CUDA engine through the C ABI (driver.FciMC = the outer loop of FciMCPar,
+src/FciMCPar.F90:394-854): projected energy, shift and trial-wavefunction energy must agree with exact
+diagonalisation within blocking-analysis error bars (src/ErrorAnalysis.F90) -- the north_star's energy criterion."""
+import numpy as np
+import pytest
+
+import helpers
+from neci_stable_b200 import capi, host, driver
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(system, **kw):
+    hii = driver.diag_energy(system, system.ref_orbs)
+    kw.setdefault("max_walkers", 400000); kw.setdefault("max_spawned", 400000); kw.setdefault("seed", 3)
+    gpu = capi.Engine(host.make_params(system, hii, **kw))
+    system.apply(gpu)
+    return gpu, hii
+
+
+def _exact(gpu, system):
+    dets = helpers.all_dets(system)
+    return dets, np.linalg.eigh(helpers.hamiltonian_matrix(gpu, system, dets))
+
+
+def _estimates(run, skip=100):
+    hist = [h for h in run.history if h["varying"]][skip:]
+    e, err = driver.ratio_estimate([h["enum_cyc"] for h in hist], [h["hf_cyc"] for h in hist])
+    sm, serr = driver.blocking([h["shift"] for h in hist])
+    return hist, e, err, sm, serr
+
+
+@pytest.mark.parametrize("kind", ["hub_k_2x2", "hub_rs_2x2", "pchb_6e6o"])
+def test_projected_energy_and_shift_match_exact_diagonalisation(kind):
+    if kind == "hub_k_2x2":
+        s, tau = host.hubbard_k_system(2, 2, nel=4, U=1.0), 0.01          # reference suite: -7.29750728 +- 2.8e-4
+    elif kind == "hub_rs_2x2":
+        s, tau = host.hubbard_rs_system(2, 2, U=4.0), 0.01
+    else:
+        s, tau = host.random_fcidump_system(6, 6, sparse=0.9, sparse_t=0.9, seed=3), 0.002
+    gpu, hii = _engine(s, initiator=False)
+    _, (w, _) = _exact(gpu, s)
+    e0 = w[0]
+    run = driver.FciMC(s, gpu, hii, tau=tau, init_walkers=3000, steps_sft=10, sft_damp=0.1)
+    run.seed_reference(10)
+    run.run(8000)
+    hist, e, err, sm, serr = _estimates(run)
+    assert len(hist) > 200
+    assert abs(e + hii - e0) < max(5 * err, 2e-3), (e + hii, e0, err)
+    assert abs(sm + hii - e0) < max(5 * serr, 2e-2), (sm + hii, e0, serr)
+    if kind == "hub_k_2x2":
+        assert abs(e0 - (-7.29750728)) < 2e-3          # the reference's published benchmark energy for this system
+
+
+def test_semi_stochastic_real_coefficient_run_with_trial_energy():
+    """Real coefficients, semi-stochastic core space (death after the walker loop, determ_projection_no_death) and the
+    trial-wavefunction estimator together: E_trial = E_T + numerator / denominator against exact diagonalisation."""
+    s = host.random_fcidump_system(6, 6, sparse=0.9, sparse_t=0.9, seed=3)
+    gpu, hii = _engine(s, initiator=False, all_real_coeff=True, semi_stochastic=True)
+    dets, (w, v) = _exact(gpu, s)
+    e0 = w[0]
+    psi0 = v[:, 0]
+    order = np.argsort(-np.abs(psi0))
+    ref = [int(x) for x in s.ref_orbs]
+    core = [dets[i] for i in order[:40]]
+    if ref not in core:
+        core = [ref] + core[:-1]
+    core, sizes, displs, per_rank, H = helpers.build_core_space(gpu, s, core, hii)
+    flags = (1 << capi.FLAG_DETERMINISTIC) | (1 << capi.FLAG_INITIATOR)
+    recs = np.array([host.record(s, d, 10.0 if d == ref else 0.0, flags) for d in core])
+    gpu.upload_walkers(recs)
+    c = per_rank[0]
+    gpu.set_core_space(c["row_ptr"], c["col"], c["val"], sizes, displs, c["iluts"])
+    trial = [dets[i] for i in order[:12]]
+    ti, ta, ci, ca, e_t = helpers.build_trial_space(gpu, s, dets, trial)
+    gpu.set_trial_space(ti, ta, ci, ca)
+    run = driver.FciMC(s, gpu, hii, tau=0.002, init_walkers=3000, steps_sft=10, sft_damp=0.1)
+    run.tot_parts = 10.0; run.old_av_walkers = 10.0
+    run.run(8000)
+    hist, e, err, sm, serr = _estimates(run)
+    assert abs(e + hii - e0) < max(5 * err, 2e-3), (e + hii, e0, err)
+    et, terr = driver.ratio_estimate([h["trial_num"] for h in hist], [h["trial_den"] for h in hist])
+    assert abs(e_t + et - e0) < max(5 * terr, 2e-3), (e_t + et, e0, terr)
+    # the larger trial space gives the better estimator
+    assert terr <= err * 1.5 + 1e-6
+
+
+def test_hphf_run_matches_exact_diagonalisation():
+    s = host.random_fcidump_system(6, 6, sparse=0.9, sparse_t=0.9, seed=3)
+    gpu_det, _ = _engine(s, initiator=False)
+    _, (w, _) = _exact(gpu_det, s)
+    gpu, hii = _engine(s, initiator=False, hphf=True)
+    run = driver.FciMC(s, gpu, hii, tau=0.002, init_walkers=3000, steps_sft=10, sft_damp=0.1)
+    run.seed_reference(10)
+    run.run(8000)
+    hist, e, err, sm, serr = _estimates(run)
+    assert abs(e + hii - w[0]) < max(5 * err, 2e-3), (e + hii, w[0], err)
+    assert abs(sm + hii - w[0]) < max(5 * serr, 2e-2), (sm + hii, w[0], serr)
