@@ -736,6 +736,64 @@ __global__ void __launch_bounds__(256) k_push(SpawnBuf SB, PeerBox X, int nranks
         __threadfence_system();
     }
 }
+// Routing and pushing in one kernel (the spawning pass on several ranks with the peer-memory exchange): every lane
+// hashes one staged spawn (DetermineDetNode), the warp reserves positions per destination, and the record goes
+// straight into the destination rank's inbox over NVLink -- SpawnedParts' per-destination segments are never
+// materialised locally.  Ends like k_push: the last CTA posts the mailboxes.
+template <int NW>
+__global__ void __launch_bounds__(NG_BLOCK) k_partition_push(Params P, WalkerList L, SpawnBuf SB, PeerBox X, unsigned int seq) {
+    __shared__ int s_roi[NG_MAX_BASIS];
+    __shared__ bool s_last;
+    for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) s_roi[i] = P.random_orb_index[i];
+    __syncthreads();
+    const int par = (int)(seq & 1u), nranks = P.nranks, rank = P.rank;
+    const u32 lane = threadIdx.x & 31;
+    long long n = (long long)*SB.stage_cnt; if (n > SB.stage_cap) n = SB.stage_cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n + stride - 1) / stride) * stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
+        const bool has = i < n;
+        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
+        long long w_sign = 0, w_flag = 0;
+        int proc = 0;
+        if (has) {
+            const long long *rec = SB.stage + (size_t)i * SB.W;
+            d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
+            w_sign = rec[NW]; w_flag = rec[NW + 1];
+            proc = __ldg(&P.lb_mapping[det_block<NW>(P, s_roi, d) - 1]);
+        }
+        const u32 active = __ballot_sync(0xffffffffu, has);
+        if (!has) continue;
+        const u32 peers = __match_any_sync(active, proc);
+        const int leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(&SB.cnt[proc], (unsigned long long)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const long long pos = (long long)base + __popc(peers & ((1u << lane) - 1u));
+        if (pos >= SB.seg_cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull); continue; }
+        long long *out = X.peer_seg[proc] + (((size_t)par * nranks + rank) * SB.seg_cap + pos) * SB.W;
+        out[0] = (long long)d.w[0];
+        if (NW > 1) out[NW - 1] = (long long)d.w[NW - 1];
+        out[NW] = w_sign;
+        out[NW + 1] = w_flag;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(X.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if ((int)threadIdx.x < nranks) {
+            const int dst = threadIdx.x;
+            unsigned long long c = *((volatile unsigned long long *)&SB.cnt[dst]);
+            if (c > (unsigned long long)SB.seg_cap) c = (unsigned long long)SB.seg_cap;
+            volatile unsigned long long *mail = X.peer_mail[dst] + (size_t)par * nranks + rank;
+            *mail = ((unsigned long long)seq << 32) | c;
+        }
+        if (threadIdx.x == 0) *X.ticket = 0u;
+        __threadfence_system();
+    }
+}
 __global__ void k_wait(WalkerList L, SpawnBuf SB, PeerBox X, int nranks, unsigned int seq, long long timeout_cycles) {
     __shared__ unsigned long long s_cnt[64];
     const int par = (int)(seq & 1u);

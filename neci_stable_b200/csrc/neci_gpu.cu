@@ -566,11 +566,14 @@ static int exchange_spawns(neci_gpu_engine *e, long long *n_recv_out) {
 }
 
 // the same exchange over NVLink peer memory: push kernel + mailbox wait + local compaction, no host round trip
-static int exchange_spawns_p2p(neci_gpu_engine *e) {
+static int exchange_spawns_p2p(neci_gpu_engine *e, bool from_stage) {
     const int nr = e->cfg.nranks;
     e->xseq += 1;
     e->n_launch += 3;
-    k_push<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->cfg.rank, e->xseq);
+    if (from_stage) {                       // spawning pass: route the staged spawns and push them in one kernel
+        if (e->nw == 1) k_partition_push<1><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->X, e->xseq);
+        else k_partition_push<2><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->X, e->xseq);
+    } else k_push<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->cfg.rank, e->xseq);
     k_wait<<<1, 64, 0, e->stream>>>(e->L, e->SB, e->X, nr, e->xseq, 10000000000ll /* ~5 s of SM clocks */);
     k_gather<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->xseq);
     CK(cudaGetLastError());
@@ -578,9 +581,15 @@ static int exchange_spawns_p2p(neci_gpu_engine *e) {
 }
 // spawn exchange of one iteration: leaves the received records contiguous in SB.recv and the count in A.n_recv
 // (>= 0: known on the host; -2: on the device)
-static int exchange(neci_gpu_engine *e, long long *n_recv) {
-    if (e->p2p) { *n_recv = -2; return exchange_spawns_p2p(e); }
+static int exchange(neci_gpu_engine *e, long long *n_recv, bool from_stage) {
+    if (e->p2p) { *n_recv = -2; return exchange_spawns_p2p(e, from_stage); }
     if (!e->comm) return e->fail("nranks > 1 but neither neci_gpu_nccl_init nor neci_gpu_p2p_open was called");
+    if (from_stage) {                       // NCCL needs SpawnedParts' per-destination segments: route locally first
+        e->n_launch += 1;
+        if (e->nw == 1) k_partition<1><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
+        else k_partition<2><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
+        CK(cudaGetLastError());
+    }
     return exchange_spawns(e, n_recv);
 }
 
@@ -694,16 +703,11 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
     double *p_spawn = e->d_partials, *p_heavy = e->d_partials + (size_t)e->rows_spawn * NECI_ST_COUNT;
     NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, K1_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
     NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, K1_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
-    if (e->cfg.nranks > 1) {
-        e->n_launch += 1;
-        if (e->nw == 1) k_partition<1><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
-        else k_partition<2><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
-    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[2], e->stream));
     if (e->cfg.nranks > 1) {
         long long nrecv = 0;
-        if (exchange(e, &nrecv)) return 1;
+        if (exchange(e, &nrecv, true)) return 1;
         A.n_recv = nrecv;
     }
     CK(cudaEventRecord(e->ev[3], e->stream));
@@ -833,7 +837,7 @@ int neci_gpu_rebalance(neci_gpu_engine *e, const int32_t *new_mapping) {
     else k_rebalance_pack<2><<<g, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB);
     CK(cudaGetLastError());
     long long nrecv = 0;
-    if (exchange(e, &nrecv)) return 1;
+    if (exchange(e, &nrecv, false)) return 1;
     k_merge_free<<<64, 256, 0, e->stream>>>(e->L);
     k_merge_free_finish<<<1, 1, 0, e->stream>>>(e->L);
     k_iota_insert<<<g, 256, 0, e->stream>>>(e->L, e->SB, nrecv);
