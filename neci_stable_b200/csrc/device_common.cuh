@@ -216,6 +216,7 @@ struct Params {
     int n_k;
     const int *ksum, *kdiff;
     const double *eps_k;
+    const double *kcum;               // [nbasis + 1] running sums k * |U/N| accumulated as the reference does (gen_k_hubbard)
     double u_over_n;
     // semi-stochastic: the whole core space, replicated (is_core_state, src/semi_stoch_procs.F90:547)
     const long long *core_iluts;      // [n_core_total][nw]

@@ -260,19 +260,11 @@ __device__ void gen_rs_hubbard(const Params &P, const Det<NW> &d, Stream &rng, E
     E.valid = true;
 }
 
-// gen_excit_k_space_hub
+// create_ab_list_hubbard + pick_from_cum_list exactly as the reference walks them (two sweeps over all orbitals), for
+// the one case the closed form below does not cover: a random number of exactly zero.
 template <int NW>
-__device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+__device__ __noinline__ void gen_k_hubbard_sweep(const Params &P, const Det<NW> &d, int s1, int s2, double r_draw, Excit<NW> &E) {
     E.ic = 2; E.valid = false; E.err = 0; E.pgen = 0.0;
-    int e1, e2, s1, s2;
-    for (int guard = 0;; ++guard) {                // pick_spin_opp_elecs
-        e1 = 1 + (int)(rng.draw() * P.nel);
-        do { e2 = 1 + (int)(rng.draw() * P.nel); } while (e1 == e2);
-        s1 = select_orb(d, ~0ull, e1); s2 = select_orb(d, ~0ull, e2);
-        if (((s1 ^ s2) & 1) != 0) break;
-        if (guard > 100000) { E.err = 1; return; }
-    }
-    if (s1 > s2) { const int t = s1; s1 = s2; s2 = t; }
     const double p_elec = 1.0 / (double)(P.nocc_beta * P.nocc_alpha);
     const int kij = __ldg(&P.ksum[(gtid(s1) - 1) * P.n_k + (gtid(s2) - 1)]);
     // create_ab_list_hubbard: cumulative list over a = 1..nbasis; elem = excit_cache(i,j,a)
@@ -289,7 +281,7 @@ __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Ex
         cum_sum += elem;
     }
     if (cum_sum < NG_EPS) return;
-    const double r = rng.draw() * cum_sum;
+    const double r = r_draw * cum_sum;
     // second sweep: first a with cum(a) >= r  (binary_search_first_ge on the same sums)
     double c = 0.0, prev = 0.0; int ind = 0, bsel = 0;
     for (int a = 1; a <= P.nbasis; ++a) {
@@ -308,6 +300,66 @@ __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Ex
     if (bsel <= 0) { E.pgen = 0.0; return; }       // r == 0 corner: zero-weight first entry
     const int t1 = min(ind, bsel), t2 = max(ind, bsel);
     E.src1 = s1; E.src2 = s2; E.tgt1 = t1; E.tgt2 = t2;
+    E.pgen = p_elec * p_orb;
+    E.valid = true;
+}
+
+// gen_excit_k_space_hub (src/k_space_hubbard.F90:535-625).  The reference builds a cumulative list over all nBasis
+// orbitals a (weight |U/N| when a and its momentum partner b = k_i + k_j - k_a of the other spin are both empty) and
+// picks from it.  All weights are equal, so the k-th partial sum depends on k alone: the host tabulates the running
+// sums C[k] = C[k-1] + |U/N| in the reference's own order of additions, the allowed orbitals are a bit mask
+// (empty, and not the partner of an occupied orbital: one table look-up per ELECTRON instead of two per ORBITAL), and
+// the pick is "the k-th set bit with C[k] the first partial sum >= r" -- the same orbital and the same probability,
+// bit for bit, in ~400 instead of ~2200 instructions.
+template <int NW>
+__device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+    E.ic = 2; E.valid = false; E.err = 0; E.pgen = 0.0;
+    int e1, e2, s1, s2;
+    for (int guard = 0;; ++guard) {                // pick_spin_opp_elecs
+        e1 = 1 + (int)(rng.draw() * P.nel);
+        do { e2 = 1 + (int)(rng.draw() * P.nel); } while (e1 == e2);
+        s1 = select_orb(d, ~0ull, e1); s2 = select_orb(d, ~0ull, e2);
+        if (((s1 ^ s2) & 1) != 0) break;
+        if (guard > 100000) { E.err = 1; return; }
+    }
+    if (s1 > s2) { const int t = s1; s1 = s2; s2 = t; }
+    const double p_elec = 1.0 / (double)(P.nocc_beta * P.nocc_alpha);
+    const int kij = __ldg(&P.ksum[(gtid(s1) - 1) * P.n_k + (gtid(s2) - 1)]);
+    const int *kd = P.kdiff + (size_t)kij * P.n_k;
+    // orbitals whose partner is occupied: partner(o) for every occupied o (the map a -> b is an involution)
+    Det<NW> blocked; blocked.w[0] = 0; if (NW > 1) blocked.w[NW - 1] = 0;
+    Det<NW> rest = d;
+    while (det_any(rest)) {
+        const int o = pop_lowest(rest);
+        const int kb = __ldg(&kd[gtid(o) - 1]);
+        set_orb(blocked, 2 * (kb + 1) - ((o & 1) ? 0 : 1));
+    }
+    Det<NW> allowed;
+    allowed.w[0] = ~d.w[0] & ~blocked.w[0];
+    if (NW == 1) { if (P.nbasis < 64) allowed.w[0] &= (1ull << P.nbasis) - 1ull; }
+    else {
+        allowed.w[NW - 1] = ~d.w[NW - 1] & ~blocked.w[NW - 1];
+        if (P.nbasis < 128) allowed.w[NW - 1] &= (1ull << (P.nbasis - 64)) - 1ull;
+    }
+    const int n = popc(allowed);
+    if (n == 0) return;
+    const double cum_sum = __ldg(&P.kcum[n]);
+    if (cum_sum < NG_EPS) return;
+    const double u = rng.draw();
+    const double r = u * cum_sum;
+    if (!(r > 0.0)) { gen_k_hubbard_sweep<NW>(P, d, s1, s2, u, E); return; }
+    // smallest k >= 1 with C[k] >= r (binary_search_first_ge on the reference's list)
+    int k = (int)(r / fabs(P.u_over_n));
+    k = max(1, min(k, n));
+    while (k < n && __ldg(&P.kcum[k]) < r) ++k;
+    while (k > 1 && !(__ldg(&P.kcum[k - 1]) < r)) --k;
+    const double c = __ldg(&P.kcum[k]), prev = __ldg(&P.kcum[k - 1]);
+    const int ta = select_orb(allowed, ~0ull, k);
+    const int kb = __ldg(&kd[gtid(ta) - 1]);
+    const int tb = 2 * (kb + 1) - ((ta & 1) ? 0 : 1);
+    double p_orb = (ta == 1) ? c / cum_sum : (c - prev) / cum_sum;
+    p_orb = 2.0 * p_orb;
+    E.src1 = s1; E.src2 = s2; E.tgt1 = min(ta, tb); E.tgt2 = max(ta, tb);
     E.pgen = p_elec * p_orb;
     E.valid = true;
 }

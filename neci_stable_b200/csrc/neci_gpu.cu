@@ -4,6 +4,7 @@
 // kernel launch on one stream, and the only host synchronisation per
 // iteration is the read-back of the statistics vector (plus the spawn counts
 // when more than one rank exchanges spawns over NCCL).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -364,6 +365,14 @@ int neci_gpu_set_system_hubbard_k(neci_gpu_engine *e, int32_t n_k, const int32_t
     e->P.n_k = n_k;
     e->P.ksum = e->upload(ksum, (size_t)n_k * n_k); e->P.kdiff = e->upload(kdiff, (size_t)n_k * n_k);
     e->P.eps_k = e->upload(eps_k, (size_t)n_k); e->P.u_over_n = u_over_n;
+    {
+        // partial sums of create_ab_list_hubbard's cumulative list (src/k_space_hubbard.F90:1795-1817): every allowed
+        // orbital adds |U/N|, so the k-th partial sum is k repeated additions -- tabulated in that order of operations
+        std::vector<double> cum((size_t)e->cfg.nbasis + 1, 0.0);
+        const double w = std::fabs(u_over_n);
+        for (int k = 1; k <= e->cfg.nbasis; ++k) cum[k] = cum[k - 1] + w;
+        e->P.kcum = e->upload(cum.data(), cum.size());
+    }
     return 0;
 }
 
