@@ -37,18 +37,27 @@ template <int NW> __device__ __forceinline__ bool det_eq(const Det<NW> &a, const
     if (NW > 1) e = e && (a.w[1] == b.w[1]);
     return e;
 }
+// Two-word determinants are addressed with selects, never with a run-time word index: d.w[b >> 6] makes the
+// compiler either spill the determinant to local memory or branch, and lanes of one warp routinely sit in different words.
 template <int NW> __device__ __forceinline__ bool occ(const Det<NW> &d, int orb) {
     const int b = orb - 1;
     if (NW == 1) return (d.w[0] >> b) & 1ull;
-    return (d.w[b >> 6] >> (b & 63)) & 1ull;
+    const u64 w = (b < 64) ? d.w[0] : d.w[NW - 1];
+    return (w >> (b & 63)) & 1ull;
 }
 template <int NW> __device__ __forceinline__ void set_orb(Det<NW> &d, int orb) {
     const int b = orb - 1;
-    if (NW == 1) d.w[0] |= 1ull << b; else d.w[b >> 6] |= 1ull << (b & 63);
+    if (NW == 1) { d.w[0] |= 1ull << b; return; }
+    const u64 bit = 1ull << (b & 63);
+    d.w[0] |= (b < 64) ? bit : 0ull;
+    d.w[NW - 1] |= (b < 64) ? 0ull : bit;
 }
 template <int NW> __device__ __forceinline__ void clr_orb(Det<NW> &d, int orb) {
     const int b = orb - 1;
-    if (NW == 1) d.w[0] &= ~(1ull << b); else d.w[b >> 6] &= ~(1ull << (b & 63));
+    if (NW == 1) { d.w[0] &= ~(1ull << b); return; }
+    const u64 bit = 1ull << (b & 63);
+    d.w[0] &= ~((b < 64) ? bit : 0ull);
+    d.w[NW - 1] &= ~((b < 64) ? 0ull : bit);
 }
 template <int NW> __device__ __forceinline__ int popc(const Det<NW> &d) {
     int n = __popcll(d.w[0]);
@@ -80,15 +89,17 @@ template <int NW> __device__ __forceinline__ int select_orb(const Det<NW> &d, u6
     const u64 a = d.w[0] & mask;
     if (NW == 1) return select64(a, n) + 1;
     const int c = __popcll(a);
-    if (n <= c) return select64(a, n) + 1;
-    return 64 + select64(d.w[NW - 1] & mask, n - c) + 1;
+    const bool first = n <= c;                             // one select64 for both words
+    return (first ? 0 : 64) + select64(first ? a : (d.w[NW - 1] & mask), first ? n : n - c) + 1;
 }
 // number of occupied orbitals with index < orb  (== position in nI, 0-based)
 template <int NW> __device__ __forceinline__ int count_below(const Det<NW> &d, int orb) {
     const int b = orb - 1;
     if (NW == 1) return __popcll(d.w[0] & ((1ull << b) - 1ull));
-    if (b < 64) return __popcll(d.w[0] & ((1ull << b) - 1ull));
-    return __popcll(d.w[0]) + __popcll(d.w[NW - 1] & ((1ull << (b - 64)) - 1ull));
+    const u64 low = (1ull << (b & 63)) - 1ull;             // bits below b within its word
+    const u64 m0 = (b < 64) ? low : ~0ull;
+    const u64 m1 = (b < 64) ? 0ull : low;
+    return __popcll(d.w[0] & m0) + __popcll(d.w[NW - 1] & m1);
 }
 // occupied orbitals strictly between orbitals a and b (a != b)
 template <int NW> __device__ __forceinline__ int count_between(const Det<NW> &d, int a, int b) {
@@ -98,8 +109,14 @@ template <int NW> __device__ __forceinline__ int count_between(const Det<NW> &d,
 }
 // iterate set bits in ascending orbital order: returns next orbital and clears it
 template <int NW> __device__ __forceinline__ int pop_lowest(Det<NW> &d) {
-    if (NW == 1 || d.w[0]) { const int b = __ffsll((long long)d.w[0]) - 1; d.w[0] &= d.w[0] - 1ull; return b + 1; }
-    const int b = __ffsll((long long)d.w[NW - 1]) - 1; d.w[NW - 1] &= d.w[NW - 1] - 1ull; return 64 + b + 1;
+    if (NW == 1) { const int b = __ffsll((long long)d.w[0]) - 1; d.w[0] &= d.w[0] - 1ull; return b + 1; }
+    const bool first = d.w[0] != 0ull;                     // branch-free: lanes of a warp are in different words
+    u64 x = first ? d.w[0] : d.w[NW - 1];
+    const int b = __ffsll((long long)x) - 1;
+    x &= x - 1ull;
+    d.w[0] = first ? x : 0ull;
+    d.w[NW - 1] = first ? d.w[NW - 1] : x;
+    return (first ? 0 : 64) + b + 1;
 }
 template <int NW> __device__ __forceinline__ bool det_any(const Det<NW> &d) {
     u64 x = d.w[0]; if (NW > 1) x |= d.w[1]; return x != 0ull;
