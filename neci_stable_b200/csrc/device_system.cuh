@@ -315,13 +315,19 @@ template <int NW>
 __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
     E.ic = 2; E.valid = false; E.err = 0; E.pgen = 0.0;
     int e1, e2, s1, s2;
+    // Rejection loop.  No `return` inside it and an explicit re-convergence after it: with an exit to the end of the
+    // function inside the loop the compiler places the re-convergence point there, and everything below ran with the
+    // warp split into the groups that left the loop together (15.8 of 32 lanes active in the profile).
+    const unsigned conv = __activemask();
+    bool failed = false;
     for (int guard = 0;; ++guard) {                // pick_spin_opp_elecs
         e1 = 1 + (int)(rng.draw() * P.nel);
         do { e2 = 1 + (int)(rng.draw() * P.nel); } while (e1 == e2);
         s1 = select_orb(d, ~0ull, e1); s2 = select_orb(d, ~0ull, e2);
         if (((s1 ^ s2) & 1) != 0) break;
-        if (guard > 100000) { E.err = 1; return; }
+        if (guard > 100000) { failed = true; break; }
     }
+    __syncwarp(conv);
     if (s1 > s2) { const int t = s1; s1 = s2; s2 = t; }
     const double p_elec = 1.0 / (double)(P.nocc_beta * P.nocc_alpha);
     const int kij = __ldg(&P.ksum[(gtid(s1) - 1) * P.n_k + (gtid(s2) - 1)]);
@@ -341,6 +347,7 @@ __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Ex
         allowed.w[NW - 1] = ~d.w[NW - 1] & ~blocked.w[NW - 1];
         if (P.nbasis < 128) allowed.w[NW - 1] &= (1ull << (P.nbasis - 64)) - 1ull;
     }
+    if (failed) { E.err = 1; return; }
     const int n = popc(allowed);
     if (n == 0) return;
     const double cum_sum = __ldg(&P.kcum[n]);
@@ -379,6 +386,9 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
         if (t - o == 0) ElecsWNoExcits += o;
     }
     if (ElecsWNoExcits == P.nel) return;
+    // rejection loops without a `return` inside and with explicit re-convergence (see gen_k_hubbard)
+    const unsigned conv = __activemask();
+    bool failed = false;
     int src = 0, cls = 0, NExcit = 0, attempts = 0;
     for (;;) {
         const int Eleci = (int)(P.nel * rng.draw()) + 1;
@@ -387,18 +397,22 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
         NExcit = __popcll(P.class_mask[cls][0]) - __popcll(d.w[0] & P.class_mask[cls][0]);
         if (NW > 1) NExcit += __popcll(P.class_mask[cls][1]) - __popcll(d.w[NW - 1] & P.class_mask[cls][1]);
         if (NExcit != 0) break;
-        if (attempts > 250) { E.err = 1; return; }
+        if (attempts > 250) { failed = true; break; }
         ++attempts;
     }
+    __syncwarp(conv);
     const int cs = __ldg(&P.class_start[cls]), nOrbs = __ldg(&P.class_start[cls + 1]) - cs;
     int Orb = 0; attempts = 0;
     for (;;) {
+        if (failed) break;
         const int ChosenUnocc = (int)(nOrbs * rng.draw());
         Orb = __ldg(&P.class_orbs[cs + ChosenUnocc]);
         if (!occ(d, Orb)) break;
-        if (attempts > 250) { E.err = 1; return; }
+        if (attempts > 250) { failed = true; break; }
         ++attempts;
     }
+    __syncwarp(conv);
+    if (failed) { E.err = 1; return; }
     E.src1 = src; E.src2 = 0; E.tgt1 = Orb; E.tgt2 = 0;
     const double pDoubNew = 1.0 - P.p_singles;
     double pgen = (1 - pDoubNew) / ((double)(NExcit * (P.nel - ElecsWNoExcits)));
