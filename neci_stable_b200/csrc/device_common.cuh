@@ -233,6 +233,8 @@ struct Params {
     int n_k;
     const int *ksum, *kdiff;
     const double *eps_k;
+    const u64 *kperm;                 // [n_k][kperm_bytes][256]: image of a byte of a k-point mask under k -> kij - k
+    int kperm_bytes;
     const double *kcum;               // [nbasis + 1] running sums k * |U/N| accumulated as the reference does (gen_k_hubbard)
     double u_over_n;
     // semi-stochastic: the whole core space, replicated (is_core_state, src/semi_stoch_procs.F90:547)

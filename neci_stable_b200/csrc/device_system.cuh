@@ -260,6 +260,26 @@ __device__ void gen_rs_hubbard(const Params &P, const Det<NW> &d, Stream &rng, E
     E.valid = true;
 }
 
+// bits at even positions of x gathered into the low 32 bits / the inverse
+__device__ __forceinline__ u64 compress_even(u64 x) {
+    x &= 0x5555555555555555ull;
+    x = (x | (x >> 1)) & 0x3333333333333333ull;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+    return x;
+}
+__device__ __forceinline__ u64 spread_even(u64 x) {
+    x &= 0x00000000FFFFFFFFull;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+
 // create_ab_list_hubbard + pick_from_cum_list exactly as the reference walks them (two sweeps over all orbitals), for
 // the one case the closed form below does not cover: a random number of exactly zero.
 template <int NW>
@@ -332,21 +352,23 @@ __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Ex
     const double p_elec = 1.0 / (double)(P.nocc_beta * P.nocc_alpha);
     const int kij = __ldg(&P.ksum[(gtid(s1) - 1) * P.n_k + (gtid(s2) - 1)]);
     const int *kd = P.kdiff + (size_t)kij * P.n_k;
-    // orbitals whose partner is occupied: partner(o) for every occupied o (the map a -> b is an involution)
-    Det<NW> blocked; blocked.w[0] = 0; if (NW > 1) blocked.w[NW - 1] = 0;
-    Det<NW> rest = d;
-    while (det_any(rest)) {
-        const int o = pop_lowest(rest);
-        const int kb = __ldg(&kd[gtid(o) - 1]);
-        set_orb(blocked, 2 * (kb + 1) - ((o & 1) ? 0 : 1));
+    // Orbitals whose partner is occupied.  In spatial-orbital masks (bit k = k-point k) the beta orbitals blocked are
+    // the image of the occupied ALPHA k-points under k -> k_i + k_j - k, and vice versa; the host tabulates that
+    // permutation per pair momentum and per byte of the mask, so the image is ceil(n_k / 8) table look-ups instead
+    // of one look-up per electron.
+    u64 occB = compress_even(d.w[0]), occA = compress_even(d.w[0] >> 1);
+    if (NW > 1) { occB |= compress_even(d.w[NW - 1]) << 32; occA |= compress_even(d.w[NW - 1] >> 1) << 32; }
+    const u64 *perm = P.kperm + (size_t)kij * P.kperm_bytes * 256;
+    u64 blockedB = 0, blockedA = 0;
+    for (int j = 0; j < P.kperm_bytes; ++j) {
+        blockedB |= __ldg(&perm[j * 256 + (int)((occA >> (8 * j)) & 255ull)]);
+        blockedA |= __ldg(&perm[j * 256 + (int)((occB >> (8 * j)) & 255ull)]);
     }
+    const u64 all_k = (P.n_k < 64) ? ((1ull << P.n_k) - 1ull) : ~0ull;
+    const u64 allowB = ~occB & ~blockedB & all_k, allowA = ~occA & ~blockedA & all_k;
     Det<NW> allowed;
-    allowed.w[0] = ~d.w[0] & ~blocked.w[0];
-    if (NW == 1) { if (P.nbasis < 64) allowed.w[0] &= (1ull << P.nbasis) - 1ull; }
-    else {
-        allowed.w[NW - 1] = ~d.w[NW - 1] & ~blocked.w[NW - 1];
-        if (P.nbasis < 128) allowed.w[NW - 1] &= (1ull << (P.nbasis - 64)) - 1ull;
-    }
+    allowed.w[0] = spread_even(allowB & 0xFFFFFFFFull) | (spread_even(allowA & 0xFFFFFFFFull) << 1);
+    if (NW > 1) allowed.w[NW - 1] = spread_even(allowB >> 32) | (spread_even(allowA >> 32) << 1);
     if (failed) { E.err = 1; return; }
     const int n = popc(allowed);
     if (n == 0) return;

@@ -373,6 +373,24 @@ int neci_gpu_set_system_hubbard_k(neci_gpu_engine *e, int32_t n_k, const int32_t
         for (int k = 1; k <= e->cfg.nbasis; ++k) cum[k] = cum[k - 1] + w;
         e->P.kcum = e->upload(cum.data(), cum.size());
     }
+    {
+        // the momentum reflection k -> k_pair - k as a byte-wise look-up table on k-point bit masks
+        if (n_k > 64) return e->fail("n_k > 64 not supported");
+        const int nb = (n_k + 7) / 8;
+        std::vector<u64> perm((size_t)n_k * nb * 256, 0ull);
+        for (int kij = 0; kij < n_k; ++kij)
+            for (int j = 0; j < nb; ++j)
+                for (int v = 0; v < 256; ++v) {
+                    u64 m = 0;
+                    for (int t = 0; t < 8; ++t) {
+                        const int k = 8 * j + t;
+                        if (((v >> t) & 1) && k < n_k) m |= 1ull << kdiff[(size_t)kij * n_k + k];
+                    }
+                    perm[((size_t)kij * nb + j) * 256 + v] = m;
+                }
+        e->P.kperm = e->upload(perm.data(), perm.size());
+        e->P.kperm_bytes = nb;
+    }
     return 0;
 }
 
