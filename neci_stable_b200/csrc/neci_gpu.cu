@@ -601,7 +601,7 @@ static int exchange_spawns_p2p(neci_gpu_engine *e, bool from_stage) {
         if (e->nw == 1) k_partition_push<1><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->X, e->xseq);
         else k_partition_push<2><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->X, e->xseq);
     } else k_push<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->cfg.rank, e->xseq);
-    k_wait<<<1, 64, 0, e->stream>>>(e->L, e->SB, e->X, nr, e->xseq, 10000000000ll /* ~5 s of SM clocks */);
+    k_wait<<<1, 64, 0, e->stream>>>(e->L, e->SB, e->X, nr, e->xseq, 60000000000ll /* ~30 s of SM clocks: ranks may be skewed by I/O */);
     k_gather<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->xseq);
     CK(cudaGetLastError());
     return 0;
