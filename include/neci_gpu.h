@@ -184,6 +184,9 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
                       const double *p_exch, const int32_t *tgt_orbs,
                       double p_singles, double p_doubles, double p_parallel,
                       int32_t n_classes, const int32_t *class_of_spinorb);
+/* New excitation-class biases from the tau search (update_tau, src/tau/tau_search_conventional.F90:274-499 assigns
+ * pSingles / pDoubles / pParallel); takes effect from the next iteration.  FCIDUMP/PCHB systems.               */
+int neci_gpu_set_excit_probs(neci_gpu_engine *e, double p_singles, double p_doubles, double p_parallel);
 /* Real-space Hubbard: spin-orbital neighbour lists in the order of
  * lat%get_spinorb_neighbors (src/real_space_hubbard.F90:1986), padded with 0;
  * TMAT2D holds the hopping (bhub) and uhub is U.                              */

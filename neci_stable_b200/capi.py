@@ -143,6 +143,10 @@ class Engine:
             C.c_double(t["p_singles"]), C.c_double(t["p_doubles"]), C.c_double(t["p_parallel"]),
             C.c_int32(t["n_classes"]), _p(a["cls"], C.c_int32)), "set_pchb")
 
+    def set_excit_probs(self, p_singles, p_doubles, p_parallel):
+        self._check(self._fn("set_excit_probs")(self.h, C.c_double(p_singles), C.c_double(p_doubles), C.c_double(p_parallel)),
+                    "set_excit_probs")
+
     def set_system_hubbard_rs(self, max_neigh, neighbours, tmat, uhub):
         nb, tm = _i32(neighbours), _f64(tmat)
         self._check(self._fn("set_system_hubbard_rs")(self.h, C.c_int32(max_neigh), _p(nb, C.c_int32), _p(tm, C.c_double),

@@ -348,6 +348,19 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
     return 0;
 }
 
+int neci_gpu_set_excit_probs(neci_gpu_engine *e, double p_singles, double p_doubles, double p_parallel) {
+    if (e->cfg.system_type != NECI_SYS_FCIDUMP_PCHB) return e->fail("set_excit_probs: FCIDUMP/PCHB systems only");
+    if (!(p_singles > 0.0 && p_singles < 1.0 && p_doubles > 0.0 && p_parallel >= 0.0 && p_parallel <= 1.0))
+        return e->fail("set_excit_probs: probabilities out of range");
+    Params &P = e->P;
+    P.p_singles = p_singles; P.p_doubles = p_doubles; P.p_parallel = p_parallel;
+    const int nA = e->cfg.nocc_alpha, nB = e->cfg.nocc_beta;
+    const int par = nA * (nA - 1) / 2 + nB * (nB - 1) / 2, AB = nA * nB;
+    P.pgen_pair_par = p_parallel / (double)par;
+    P.pgen_pair_opp = (1.0 - p_parallel) / (double)AB;
+    return 0;
+}
+
 int neci_gpu_set_system_hubbard_rs(neci_gpu_engine *e, int32_t max_neigh, const int32_t *neighbours,
                                    const double *tmat2d, double uhub) {
     CK(cudaSetDevice(e->cfg.device));

@@ -129,6 +129,76 @@ class LoadBalanceTrigger:
         return t_lb
 
 
+class TauSearch:
+    """The conventional tau search of the host (update_tau, src/tau/tau_search_conventional.F90:274-499), fed by the
+    per-iteration maxima and counts the engine returns (log_spawn_magnitude, :138-260).  Keeps the running maxima
+    gamma_* and the enough_* switches (cnt_threshold = 50), proposes tau = MaxWalkerBloom * p_class / gamma_class and,
+    once every class has been seen often enough, the biases pParallel = gamma_par / (gamma_opp + gamma_par) and
+    pSingles = gamma_sing pParallel / (gamma_par + gamma_sing pParallel).  The death-magnitude cap
+    (max_death_cpt, :425-436) is not applied: the engine does not return it."""
+    CNT_THRESHOLD = 50
+
+    def __init__(self, tau, p_singles, p_doubles, p_parallel, consider_par_bias, max_walker_bloom=1.0,
+                 min_tau=1e-7, max_tau=1.0):
+        self.tau, self.p_singles, self.p_doubles, self.p_parallel = tau, p_singles, p_doubles, p_parallel
+        self.par_bias, self.bloom, self.min_tau, self.max_tau = consider_par_bias, max_walker_bloom, min_tau, max_tau
+        self.gamma = np.zeros(4)                 # sing, doub, par, opp
+        self.cnt = np.zeros(4)
+
+    def log(self, stats):
+        """Accumulate one iteration's statistics vector (after the max / sum reduction over ranks)."""
+        g0 = ST["TAU_GAMMA_SING"]; c0 = ST["TAU_CNT_SING"]
+        self.gamma = np.maximum(self.gamma, stats[g0:g0 + 4])
+        self.cnt += stats[c0:c0 + 4]
+
+    @property
+    def enough(self):
+        e = self.cnt > self.CNT_THRESHOLD
+        sing, doub, par, opp = bool(e[0]), bool(e[1]), bool(e[2]), bool(e[3])
+        if self.par_bias:
+            doub = par and opp
+        return sing, doub, par, opp
+
+    def update(self):
+        """update_tau: returns (tau, p_singles, p_doubles, p_parallel) to use from now on."""
+        eps = 1e-13
+        g_sing, g_doub, g_par, g_opp = self.gamma
+        e_sing, e_doub, e_par, e_opp = self.enough
+        ps_new, pp_new = self.p_singles, self.p_parallel
+        if self.par_bias:
+            if e_sing and e_doub:
+                pp_new = g_par / (g_opp + g_par)
+                ps_new = g_sing * pp_new / (g_par + g_sing * pp_new)
+                tau_new = ps_new * self.bloom / g_sing
+            elif g_sing > eps and g_par > eps and g_opp > eps:
+                tau_new = self.bloom * min(self.p_singles / g_sing, self.p_doubles * self.p_parallel / g_par,
+                                           self.p_doubles * (1.0 - self.p_parallel) / g_opp)
+            else:
+                tau_new = self.tau
+            if e_opp and e_par:
+                self.p_parallel = pp_new
+        else:
+            gsum = g_sing + g_doub
+            if e_sing and e_doub:
+                ps_new = max(g_sing / gsum, 1e-8)
+                tau_new = self.bloom / gsum
+            elif abs(g_doub) > eps and abs(g_sing) > eps:
+                tau_new = self.bloom * min(self.p_singles / g_sing, self.p_doubles / g_doub)
+            elif abs(g_doub) > eps:
+                tau_new = self.bloom * self.p_doubles / g_doub
+            elif abs(g_sing) > eps:
+                tau_new = self.bloom * self.p_singles / g_sing
+            else:
+                tau_new = self.tau
+        tau_new = min(max(tau_new, self.min_tau), self.max_tau)
+        if tau_new < self.tau or (e_sing and e_doub):
+            self.tau = tau_new * 0.99999
+        if e_sing and e_doub and 1e-5 < ps_new < 1.0 - 1e-5:
+            self.p_singles = ps_new
+            self.p_doubles = 1.0 - ps_new
+        return self.tau, self.p_singles, self.p_doubles, self.p_parallel
+
+
 class FciMC:
     """Drives one engine (rank) through the FCIQMC iteration loop."""
 

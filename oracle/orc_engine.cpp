@@ -564,6 +564,10 @@ int orc_set_system_hubbard_rs(orc_engine *e, int32_t max_neigh, const int32_t *n
     e->S.uhub = uhub;
     return 0;
 }
+int orc_set_excit_probs(orc_engine *e, double p_singles, double p_doubles, double p_parallel) {
+    e->S.p_singles = p_singles; e->S.p_doubles = p_doubles; e->S.p_parallel = p_parallel;
+    return 0;
+}
 int orc_set_system_hubbard_k(orc_engine *e, int32_t n_k, const int32_t *ksum, const int32_t *kdiff,
                              const double *eps_k, double u_over_n) {
     e->S.n_k = n_k;

@@ -84,3 +84,35 @@ def test_tau_search_gamma_bounds_every_spawn():
     t = s.tables["pchb"]
     bound = tau * max(g[0] / t["p_singles"], g[2] / (t["p_doubles"] * t["p_parallel"]), g[3] / (t["p_doubles"] * (1 - t["p_parallel"])))
     assert abs(max_spawn - bound) <= 1e-12 * bound, (max_spawn, bound)
+
+
+def test_tau_search_loop_caps_the_spawns():
+    """Host tau search (driver.TauSearch = update_tau) driven by the engine's gamma statistics: starting from a time
+    step ten times too large it settles on tau = p_class / gamma_class, after which no spawn exceeds MaxWalkerBloom,
+    and the class biases move to the gamma ratios (fed back through set_excit_probs)."""
+    s = host.random_fcidump_system(6, 6, sparse=0.9, sparse_t=0.9, seed=3)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=200000, max_spawned=200000, tau_search=True, seed=9, initiator=False)
+    o.upload_walkers(host.record(s, s.ref_orbs, 2000.0, 1 << capi.FLAG_INITIATOR).reshape(1, -1))
+    t = s.tables["pchb"]
+    ts = driver.TauSearch(0.02, t["p_singles"], t["p_doubles"], t["p_parallel"], consider_par_bias=True)
+    tau, sft, it = ts.tau, 0.0, 0
+    probs0 = (ts.p_singles, ts.p_parallel)
+    late_max = 0.0
+    for cyc in range(60):
+        for _ in range(10):
+            it += 1
+            st = o.iterate(tau, sft, it)
+            ts.log(st)
+            if cyc >= 40:
+                late_max = max(late_max, st[ST["MAX_CYC_SPAWN"]])
+        sft = -2.0 if st[ST["TOTPARTS"]] > 20000 else 0.0          # crude population control
+        tau, ps, pd, pp = ts.update()
+        o.set_excit_probs(ps, pd, pp)
+    assert ts.enough[0] and ts.enough[2] and ts.enough[3]
+    assert tau < 0.02 / 3                                             # the search had to cut the time step
+    assert late_max <= 1.0 + 1e-9, late_max                           # MaxWalkerBloom = 1
+    g_sing, _, g_par, g_opp = ts.gamma
+    assert abs(ts.p_parallel - g_par / (g_par + g_opp)) < 1e-12
+    assert (ts.p_singles, ts.p_parallel) != probs0
+    assert abs(ts.p_singles + ts.p_doubles - 1.0) < 1e-15
