@@ -1,21 +1,24 @@
 // The hot-path kernels of one FCIQMC iteration (PerformFCIMCycPar,
 // src/FciMCPar.F90:1177-1920), B200-first:
 //
-//   k_spawn          loop over determinants (:1294-1758): initiator flags
-//                    (CalcParentFlag), energy accumulators (SumEContrib),
-//                    spawning (generate_excitation + attempt_create +
-//                    create_particle) and death (walker_death), fused in one
-//                    pass over the SoA walker list.  Attempts are distributed
-//                    over the threads of a CTA per tile (prefix sum + search),
-//                    very heavy determinants are deferred to k_spawn_heavy.
-//   k_compress       CompressSpawnedList (Annihilation.F90:249-515) as an
-//                    in-place hash merge of the received spawn records.
-//   k_annihilate     AnnihilateSpawnedParts (:965-1352): probe the main hash
-//                    table, merge signs, abort / round, queue new determinants.
-//   k_insert         AddNewHashDet (load_balancer.fpp:514-629) incl.
-//                    get_diagonal_matel / get_off_diagonal_matel.
-//   k_list_stats     CalcHashTableStats (load_balancer.fpp:646-805).
-//   k_determ_spmv    determ_projection (semi_stoch_procs.F90:105-241).
+//   k_spawn            (spawn_kernel.cuh) loop over determinants (:1294-1758): initiator flags, energy
+//                      accumulators, spawning and death, staged through shared-memory queues;
+//                      k_spawn_heavy takes determinants with > 4096 attempts.
+//   k_trial_energy     trial part of SumEContrib (fcimc_helper.F90:586-648).
+//   k_compress         CompressSpawnedList (Annihilation.F90:249-515) as an in-place hash merge of the
+//                      received spawn records; also merges the FreeSlot lists.
+//   k_annihilate       AnnihilateSpawnedParts (:965-1352): probe the main hash table, merge signs,
+//                      abort / round, queue new determinants.
+//   k_insert           AddNewHashDet (load_balancer.fpp:514-629) incl. get_diagonal_matel /
+//                      get_off_diagonal_matel and hash_search_trial.
+//   k_list_stats       CalcHashTableStats (load_balancer.fpp:646-805).
+//   k_reduce_stats     the iteration's statistics vector (communicate_estimates' per-rank inputs).
+//   k_determ_spmv      determ_projection / determ_projection_no_death (semi_stoch_procs.F90:105-374).
+//   k_partition_push, k_partition, k_push, k_wait, k_gather
+//                      DetermineDetNode routing + SendProcNewParts over NVLink peer memory.
+//   k_rebalance_pack   move_block, sender side (load_balancer.fpp:353-512).
+//   k_pops_*           POPSFILE gather (Popsfile.F90:2054-2107).
+//   k_upload / k_download / k_probe_*   list transfer and the parity probes.
 #pragma once
 #include "spawn_kernel.cuh"
 

@@ -18,6 +18,10 @@
 //            weight, stochastic rounding, warp-aggregated append to the destination rank's segment
 //   stage B3 whenever QS holds >= 256 entries: uniform single + sltcnd_1 (loads batched 4 at a time), then as B2
 //
+// The kernel body is one loop of rounds (serve the queues, then generate up to 256 attempts) with a single
+// queue-serving call site.  On several ranks the appends of B2/B3 go to a staging list and k_partition_push routes
+// them afterwards (kernels.cuh).  HPHF runs are their own compile-time variant (NG_SYS_PCHB_HPHF).
+//
 // Random numbers are counter-based (device_common.cuh: Stream), so the result does not depend on the
 // order in which the queues are served.
 #pragma once
