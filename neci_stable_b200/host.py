@@ -105,6 +105,49 @@ def random_fcidump_system(n_spat, nel, sparse=1.0, sparse_t=1.0, seed=25, diag_s
                   tables=dict(umat=umat, tmat=tmat, pchb=pchb), ref_orbs=np.array(ref, dtype=np.int32))
 
 
+def fcidump_system(norb, nelec, h1, eri, ecore=0.0, ms2=0, orbsym=None, eps=None, ref_spatial=None,
+                   p_singles=0.1, p_parallel=None):
+    """A system from FCIDUMP data (what IntInit / readint hand over, src/readint.F90): h1 = [(i, j, value)], eri =
+    [(i, j, k, l, value)] in the FCIDUMP's chemist order (ij|kl) with 1-based spatial orbitals.
+    UMAT is the packed 8-fold array indexed by UMatInd (src/UMatCache.F90:257-296): <pr|qs> = (pq|rs) sits at
+    tri(tri(p,q), tri(r,s)); TMAT2D is spin-orbital, h_pq between equal spins.  ORBSYM gives the (spin, irrep) classes
+    of the uniform singles generator; the reference determinant is the aufbau filling by orbital energy."""
+    L = lib()
+    nb = 2 * norb
+
+    def tri(a, b):
+        return a * (a - 1) // 2 + b if a > b else b * (b - 1) // 2 + a
+    umat = np.zeros(L.neci_host_umat_size(C.c_int32(norb)))
+    for i, j, k, l, v in eri:
+        umat[tri(tri(int(i), int(j)), tri(int(k), int(l))) - 1] = v
+    tmat = np.zeros(nb * nb)
+    for i, j, v in h1:
+        for (a, b) in ((int(i), int(j)), (int(j), int(i))):
+            for spin in (0, 1):                      # beta = odd spin orbital 2a-1, alpha = even 2a
+                so_a, so_b = 2 * a - 1 + spin, 2 * b - 1 + spin
+                tmat[(so_a - 1) + nb * (so_b - 1)] = v
+    nalpha = (nelec + ms2) // 2
+    nbeta = nelec - nalpha
+    cls = None
+    if orbsym is not None:
+        labels = sorted(set(int(x) for x in orbsym))
+        cls = np.zeros(nb, dtype=np.int32)
+        for so in range(1, nb + 1):
+            irr = labels.index(int(orbsym[(so + 1) // 2 - 1]))
+            cls[so - 1] = 2 * irr + (0 if so % 2 else 1)
+    pchb = build_pchb(norb, umat, p_singles=p_singles, p_parallel=p_parallel, nalpha=nalpha, nbeta=nbeta,
+                      class_of_spinorb=cls)
+    if ref_spatial is None:
+        order = np.argsort(np.asarray(eps if eps is not None else [tmat[(2 * a - 2) + nb * (2 * a - 2)] for a in range(1, norb + 1)]),
+                           kind="stable")
+        ref = sorted([2 * int(a) + 1 for a in order[:nbeta]] + [2 * int(a) + 2 for a in order[:nalpha]])
+    else:
+        ref = sorted([2 * a - 1 for a in ref_spatial[:nbeta]] + [2 * a for a in ref_spatial[:nalpha]])
+    return System(kind=capi.SYS_FCIDUMP_PCHB, nel=nelec, nbasis=nb, nocc_alpha=nalpha, nocc_beta=nbeta,
+                  ecore=float(ecore), t_exch=1, t_no_brillouin=0,
+                  tables=dict(umat=umat, tmat=tmat, pchb=pchb), ref_orbs=np.array(ref, dtype=np.int32))
+
+
 def build_pchb(n_spat, umat, p_singles=0.1, p_parallel=None, nalpha=None, nbeta=None, class_of_spinorb=None):
     """GAS_doubles_PCHB_compute_samplers (src/gasci_pchb_doubles_spatorb_fastweighted.fpp:329-445)."""
     L = lib()

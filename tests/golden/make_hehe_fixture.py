@@ -1,0 +1,61 @@
+"""Generates tests/golden/hehe_ss_doubles.json from the reference's own regression case
+test_suite/neci/parallel/HeHe_SS_Doubles: the FCIDUMP integrals (input data of that test) and the numbers the
+reference's CPU run printed into its checked-in benchmark output (reference-determinant energy, energy of the
+highest determinant, final projected energy with its error bar).  Run in the build container, where /root/reference
+exists; the tests only read the JSON."""
+import glob
+import json
+import os
+import re
+import sys
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+CASE = os.path.join(REF, "test_suite", "neci", "parallel", "HeHe_SS_Doubles")
+
+
+def main():
+    txt = open(os.path.join(CASE, "FCIDUMP")).read()
+    head, body = txt.split("&END")
+    norb = int(re.search(r"NORB\s*=\s*(\d+)", head).group(1))
+    nelec = int(re.search(r"NELEC\s*=\s*(\d+)", head).group(1))
+    ms2 = int(re.search(r"MS2\s*=\s*(-?\d+)", head).group(1))
+    orbsym = [int(x) for x in re.search(r"ORBSYM\s*=\s*([\d,\s]+)", head).group(1).replace("\n", "").split(",") if x.strip()]
+    ecore, eps, h1, eri = 0.0, {}, [], []
+    for ln in body.strip().splitlines():
+        t = ln.split()
+        if len(t) != 5:
+            continue
+        v = float(t[0]); i, j, k, l = (int(x) for x in t[1:])
+        if i == 0:
+            ecore = v
+        elif j == 0:
+            eps[i] = v
+        elif k == 0:
+            h1.append([i, j, v])
+        else:
+            eri.append([i, j, k, l, v])
+    bench = open(glob.glob(os.path.join(CASE, "benchmark*"))[0]).read()
+    ref_energy = float(re.search(r"Current reference energy\s+(-?[\d.]+)", bench).group(1))
+    hi = re.search(r"Highest energy determinant is \(approximately\):\s+(-?[\d.Ee+-]+)", bench)
+    hi_det = re.search(r"Highest energy determinant is:\s+([\d\s]+)\n", bench)
+    tot = re.search(r"Total projected energy\s+(-?[\d.]+)\s*\+/-\s*([\d.Ee+-]+)", bench)
+    ref_det = re.search(r"Generated reference determinants:\s*\n\(\s*([\d,\s]+)\)", bench)
+    out = dict(
+        source="test_suite/neci/parallel/HeHe_SS_Doubles (FCIDUMP, neci.inp, benchmark.out...)",
+        input=dict(hphf=True, allrealcoeff=True, realspawncutoff=0.01, tau=0.001, totalwalkers=1000, shiftdamp=0.1,
+                   stepsshift=1, semi_stochastic="doubles-core", startsinglepart=10, diagshift=1.0, nmcyc=6000),
+        norb=norb, nelec=nelec, ms2=ms2, orbsym=orbsym[:norb], ecore=ecore, eps=[eps[i] for i in range(1, norb + 1)],
+        h1=h1, eri=eri,
+        reference_det=[int(x) for x in ref_det.group(1).replace(",", " ").split()],
+        reference_energy=ref_energy,
+        highest_det=[int(x) for x in hi_det.group(1).split()], highest_det_energy=float(hi.group(1)),
+        total_projected_energy=float(tot.group(1)), total_projected_energy_error=float(tot.group(2)),
+    )
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hehe_ss_doubles.json")
+    json.dump(out, open(dst, "w"))
+    print("wrote", dst, "norb", norb, "nelec", nelec, "h1", len(h1), "eri", len(eri), out["reference_energy"],
+          out["highest_det_energy"], out["total_projected_energy"], out["total_projected_energy_error"])
+
+
+if __name__ == "__main__":
+    main()

@@ -230,3 +230,44 @@ def build_trial_space(engine, system, dets, trial_dets):
     con = Hct @ psi
     keep = np.abs(con) > 0
     return il_t, psi.copy(), il_r[keep], con[keep], float(w[0])
+
+
+def hphf_allowed(system, dets):
+    """The determinants IsAllowedHPHF accepts (closed shell, or the larger of a spin-flipped pair; one word)."""
+    A, B = 0xAAAAAAAAAAAAAAAA, 0x5555555555555555
+    out = []
+    for d in dets:
+        w = int(np.uint64(system.ilut(d)[0]))
+        if w >= (((w & A) >> 1) | ((w & B) << 1)):
+            out.append(d)
+    return out
+
+
+def run_with_doubles_core(engine, system, hii, tau, target, n_iter, steps_sft=1, sft_damp=0.1, start=10.0, diag_sft=0.0):
+    """`semi-stochastic doubles-core` + HPHF as the reference's HeHe_SS_Doubles case sets it up: the core space is the
+    reference plus every HPHF function connected to it (singles and doubles), H over it in the HPHF basis; the
+    run starts from `start` walkers on the reference (startsinglepart) and the shift varies once `target` is reached."""
+    ref = [int(x) for x in system.ref_orbs]
+    dets = hphf_allowed(system, all_dets(system))
+    il = np.array([system.ilut(d) for d in dets], dtype=np.int64).reshape(len(dets), system.nw)
+    iref = dets.index(ref)
+    core = [ref] + [d for k, d in enumerate(dets) if k != iref and _hphf_level(system, ref, d) <= 2]
+    core, sizes, displs, per_rank, H = build_core_space(engine, system, core, hii)
+    flags = (1 << capi.FLAG_DETERMINISTIC) | (1 << capi.FLAG_INITIATOR)
+    recs = np.array([host.record(system, d, start if d == ref else 0.0, flags) for d in core])
+    engine.upload_walkers(recs)
+    c = per_rank[0]
+    engine.set_core_space(c["row_ptr"], c["col"], c["val"], sizes, displs, c["iluts"])
+    run = driver.FciMC(system, engine, hii, tau=tau, init_walkers=target, steps_sft=steps_sft, sft_damp=sft_damp,
+                       diag_sft=diag_sft)
+    run.tot_parts = start; run.old_av_walkers = start
+    run.run(n_iter)
+    return run
+
+
+def _hphf_level(system, ref, d):
+    """Excitation level between HPHF functions: the smaller of the levels to the determinant and to its spin flip."""
+    A, B = 0xAAAAAAAAAAAAAAAA, 0x5555555555555555
+    r = int(np.uint64(system.ilut(ref)[0])); w = int(np.uint64(system.ilut(d)[0]))
+    f = ((w & A) >> 1) | ((w & B) << 1)
+    return min(bin(r & ~w).count("1"), bin(r & ~f).count("1"))

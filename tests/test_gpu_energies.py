@@ -96,3 +96,32 @@ def test_hphf_run_matches_exact_diagonalisation():
     hist, e, err, sm, serr = _estimates(run)
     assert abs(e + hii - w[0]) < max(5 * err, 2e-3), (e + hii, w[0], err)
     assert abs(sm + hii - w[0]) < max(5 * serr, 2e-2), (sm + hii, w[0], serr)
+
+
+def test_reference_regression_case_hehe_ss_doubles():
+    """The reference's own regression case test_suite/neci/parallel/HeHe_SS_Doubles run on the CUDA engine with the
+    case's own parameters (HPHF, real coefficients with spawn cutoff 0.01, tau 0.001, semi-stochastic doubles core,
+    1000 walkers, shift updated every iteration with damping 0.1, initial shift 1.0): the determinant energies the
+    reference printed are reproduced to all digits and the projected energy agrees with the reference CPU run's
+    -5.76223713 +- 4.0e-5 within the combined error bars -- the north_star's acceptance criterion, against the
+    reference's own output."""
+    import json, os
+    g = json.load(open(os.path.join(helpers.GOLDEN, "hehe_ss_doubles.json")))
+    s = host.fcidump_system(g["norb"], g["nelec"], g["h1"], g["eri"], ecore=g["ecore"], ms2=g["ms2"],
+                            orbsym=g["orbsym"], eps=g["eps"])
+    inp = g["input"]
+    gpu, hii = _engine(s, initiator=False, hphf=True, all_real_coeff=True, real_spawn_cutoff=inp["realspawncutoff"],
+                       semi_stochastic=True, seed=7, max_walkers=20000, max_spawned=40000)
+    il = lambda d: s.ilut(d).reshape(1, -1)
+    assert abs(gpu.probe_helement(il(g["reference_det"]), il(g["reference_det"]))[0] - g["reference_energy"]) < 5e-12
+    assert abs(gpu.probe_helement(il(g["highest_det"]), il(g["highest_det"]))[0] - g["highest_det_energy"]) < 5e-13
+    run = helpers.run_with_doubles_core(gpu, s, hii, tau=inp["tau"], target=inp["totalwalkers"], n_iter=14000,
+                                        steps_sft=inp["stepsshift"], sft_damp=inp["shiftdamp"],
+                                        start=float(inp["startsinglepart"]), diag_sft=inp["diagshift"])
+    hist = [h for h in run.history if h["varying"]][2000:]
+    assert len(hist) > 4000
+    e, err = driver.ratio_estimate([h["enum_cyc"] for h in hist], [h["hf_cyc"] for h in hist])
+    tol = 5 * np.hypot(err, g["total_projected_energy_error"])
+    assert abs(e + hii - g["total_projected_energy"]) < max(tol, 3e-4), (e + hii, g["total_projected_energy"], err)
+    sm, serr = driver.blocking([h["shift"] for h in hist])
+    assert abs(sm + hii - g["total_projected_energy"]) < max(5 * serr, 2e-2), (sm + hii, serr)
