@@ -203,12 +203,13 @@ class FciMC:
     """Drives one engine (rank) through the FCIQMC iteration loop."""
 
     def __init__(self, system, engine, hii, tau, init_walkers, steps_sft=10, sft_damp=0.1, diag_sft=0.0,
-                 nranks=1):
+                 nranks=1, jump_shift=False):
         self.system, self.engine, self.hii = system, engine, hii
         self.tau, self.init_walkers = tau, init_walkers
         self.steps_sft, self.sft_damp = steps_sft, sft_damp
         self.diag_sft = diag_sft
         self.nranks = nranks
+        self.jump_shift = jump_shift           # tJumpShift (src/fcimc_iter_utilities.F90:1044-1054)
         self.iter = 0
         self.single_part_phase = True          # tSinglePartPhase
         self.tot_parts = 0.0                   # AllTotParts of the previous iteration
@@ -255,9 +256,15 @@ class FciMC:
         all_tot_parts = allst[ST["TOTPARTS"]]
         av_walkers = all_sum_walkers_cyc / self.steps_sft
         # update_shift
+        hf_now = allst[ST["HFCYC"]]
+        defer_update = False
         if self.single_part_phase and all_tot_parts > self.init_walkers * self.nranks:
             self.single_part_phase = False
-        if not self.single_part_phase and self.old_av_walkers > 0 and av_walkers > 0:
+            if self.jump_shift and abs(hf_now) > 1e-13:
+                # jump the shift to the value the projected energy predicts and defer the update by one cycle
+                self.diag_sft = allst[ST["ENUMCYC"]] / hf_now
+                defer_update = True
+        if not self.single_part_phase and not defer_update and self.old_av_walkers > 0 and av_walkers > 0:
             self.diag_sft = host.update_shift(self.diag_sft, self.sft_damp, self.tau, self.steps_sft,
                                               av_walkers, self.old_av_walkers)
         hf = allst[ST["HFCYC"]]

@@ -125,3 +125,30 @@ def test_reference_regression_case_hehe_ss_doubles():
     assert abs(e + hii - g["total_projected_energy"]) < max(tol, 3e-4), (e + hii, g["total_projected_energy"], err)
     sm, serr = driver.blocking([h["shift"] for h in hist])
     assert abs(sm + hii - g["total_projected_energy"]) < max(5 * serr, 2e-2), (sm + hii, serr)
+
+
+def test_reference_regression_case_ne_pchb():
+    """The reference's PCHB regression case test_suite/neci/parallel/Ne_FciMCPar_pchb (Ne, 8 active electrons in 22
+    orbitals after `freeze 2 0`, i-FCIQMC with integer walkers, addtoinitiator 3, 20000 walkers, shift damping 0.03
+    every 25 iterations) on the CUDA engine: reference-determinant energy to the printed digits, and the initiator
+    projected energy against the reference CPU run's -128.70959926 +- 6.8e-4 (the reference picks electron pairs with
+    FULL-FULL weighting, this engine with UNIF-UNIF: different unbiased generators, same estimator)."""
+    import os
+    z = np.load(os.path.join(helpers.GOLDEN, "ne_pchb.npz"))
+    s = host.fcidump_system(int(z["norb"]), int(z["nelec"]), z["h1"], z["eri"], ecore=float(z["ecore"]), ms2=0,
+                            orbsym=[int(x) for x in z["orbsym"]], eps=z["eps"], p_singles=0.2)
+    gpu, hii = _engine(s, initiator=True, initiator_walk_no=float(z["input_addtoinitiator"]), seed=8,
+                       max_walkers=400000, max_spawned=400000)
+    assert [int(x) for x in s.ref_orbs] == [int(x) for x in z["reference_det"]]
+    il = s.ilut(s.ref_orbs).reshape(1, -1)
+    assert abs(gpu.probe_helement(il, il)[0] - float(z["reference_energy"])) < 5e-10
+    run = driver.FciMC(s, gpu, hii, tau=0.01, init_walkers=int(z["input_totalwalkers"]),
+                       steps_sft=int(z["input_stepsshift"]), sft_damp=float(z["input_shiftdamp"]), diag_sft=0.5,
+                       jump_shift=True)                 # the case's `jump-shift`
+    run.seed_reference(100)
+    run.run(16000)
+    hist = [h for h in run.history if h["varying"]][80:]
+    assert len(hist) > 200
+    e, err = driver.ratio_estimate([h["enum_cyc"] for h in hist], [h["hf_cyc"] for h in hist])
+    ref_e, ref_err = float(z["total_projected_energy"]), float(z["total_projected_energy_error"])
+    assert abs(e + hii - ref_e) < max(5 * np.hypot(err, ref_err), 3e-3), (e + hii, ref_e, err)

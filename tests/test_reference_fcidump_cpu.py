@@ -65,3 +65,46 @@ def test_oracle_run_in_the_reference_configuration_reproduces_its_energy():
     e, err = driver.ratio_estimate([h["enum_cyc"] for h in hist], [h["hf_cyc"] for h in hist])
     tol = 5 * np.hypot(err, g["total_projected_energy_error"])
     assert abs(e + hii - g["total_projected_energy"]) < max(tol, 3e-4), (e + hii, g["total_projected_energy"], err)
+
+
+def load_ne_pchb():
+    z = np.load(os.path.join(helpers.GOLDEN, "ne_pchb.npz"))
+    s = host.fcidump_system(int(z["norb"]), int(z["nelec"]), z["h1"], z["eri"], ecore=float(z["ecore"]), ms2=0,
+                            orbsym=[int(x) for x in z["orbsym"]], eps=z["eps"])
+    return z, s
+
+
+def test_ne_pchb_reference_energy_with_frozen_core():
+    """Second regression case of the reference, Ne_FciMCPar_pchb (23 orbitals, `freeze 2 0`, the PCHB generator): the
+    frozen-core folding of tests/golden/make_ne_pchb_fixture.py + the oracle's sltcnd_0 reproduce the reference's
+    `Reference Energy set to: -128.4963497303` and its choice of reference determinant."""
+    z, s = load_ne_pchb()
+    assert [int(x) for x in s.ref_orbs] == [int(x) for x in z["reference_det"]]
+    assert abs(driver.diag_energy(s, s.ref_orbs) - float(z["reference_energy"])) < 5e-10
+
+
+def test_ne_pchb_generator_is_unbiased_from_the_reference_determinant():
+    """PCHB doubles + uniform singles with the case's eight (spin, irrep) classes: sum 1/pgen over the draws that land
+    on a determinant estimates 1 for every connected determinant (the reference's generator criterion)."""
+    z, s = load_ne_pchb()
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, _ = helpers.make_pair(s, hii, max_walkers=10000, max_spawned=10000)
+    il = s.ilut(s.ref_orbs).reshape(1, -1)
+    n_draw = 400000
+    out = o.probe_gen_excit(np.repeat(il, n_draw, axis=0), np.arange(n_draw, dtype=np.int32), 1)
+    ok = out["pgen"] > 0
+    tgt = out["ilut_j"][ok, 0]
+    inv = 1.0 / out["pgen"][ok]
+    keys, idx = np.unique(tgt, return_inverse=True)
+    acc = np.bincount(idx, weights=inv) / n_draw
+    cnt = np.bincount(idx)
+    hel = np.abs(out["hel"][ok])
+    nonzero = np.bincount(idx, weights=(hel > 1e-12)) > 0
+    big = cnt > 400
+    assert big.sum() > 100
+    assert np.all(np.abs(acc[big] - 1.0) < 4.5 / np.sqrt(cnt[big]) + 0.01)
+    # 24 symmetry-allowed singles + 960 doubles from the reference (the reference's own count, benchmark line 230)
+    ic = out["ic"][ok]
+    n_singles = len(np.unique(tgt[(ic == 1) & (hel > 1e-12)]))
+    n_doubles = len(np.unique(tgt[(ic == 2) & (hel > 1e-12)]))
+    assert n_singles <= 24 and n_doubles <= 960 and n_doubles > 800
