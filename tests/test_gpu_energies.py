@@ -152,3 +152,17 @@ def test_reference_regression_case_ne_pchb():
     e, err = driver.ratio_estimate([h["enum_cyc"] for h in hist], [h["hf_cyc"] for h in hist])
     ref_e, ref_err = float(z["total_projected_energy"]), float(z["total_projected_energy_error"])
     assert abs(e + hii - ref_e) < max(5 * np.hypot(err, ref_err), 3e-3), (e + hii, ref_e, err)
+
+
+def test_device_diagonal_elements_match_reference_outputs():
+    """The CUDA sltcnd_0 against `Reference Energy set to` of five of the reference's regression runs
+    (tests/golden/reference_energies.json: C2, H4, Cr2 24e/30o, H2O, Ne)."""
+    import json, os
+    for c in json.load(open(os.path.join(helpers.GOLDEN, "reference_energies.json"))):
+        n = c["n_spat"]
+        s = host.fcidump_system(n, 2 * n, c["h1"], c["eri"], ecore=c["ecore"], ms2=0, ref_spatial=list(range(1, n + 1)))
+        gpu, hii = _engine(s, max_walkers=1000, max_spawned=1000)
+        il = s.ilut(s.ref_orbs).reshape(1, -1)
+        e = gpu.probe_helement(il, il)[0]
+        assert abs(e - c["reference_energy"]) < 5e-10 * max(1.0, abs(e) / 100), (c["case"], e, c["reference_energy"])
+        gpu.close()

@@ -108,3 +108,23 @@ def test_ne_pchb_generator_is_unbiased_from_the_reference_determinant():
     n_singles = len(np.unique(tgt[(ic == 1) & (hel > 1e-12)]))
     n_doubles = len(np.unique(tgt[(ic == 2) & (hel > 1e-12)]))
     assert n_singles <= 24 and n_doubles <= 960 and n_doubles > 800
+
+
+def test_reference_energies_of_five_regression_cases():
+    """`Reference Energy set to` as printed by the reference's own runs of C2_FCIMCPar_CAS (freeze 4), H4, the
+    Cr2 case (freeze 24: the 24-electron / 30-orbital system of BASELINE configs[4]), H2O and Ne (freeze 2):
+    integrals over the occupied orbitals from tests/golden/reference_energies.json (frozen core folded by the
+    generating script), energy from the oracle's UMAT packing + sltcnd_0."""
+    cases = json.load(open(os.path.join(helpers.GOLDEN, "reference_energies.json")))
+    assert len(cases) == 5
+    for c in cases:
+        n = c["n_spat"]
+        assert c["nalpha"] == c["nbeta"] == n and c["det"] == list(range(1, 2 * n + 1))
+        s = host.fcidump_system(n, 2 * n, c["h1"], c["eri"], ecore=c["ecore"], ms2=0, ref_spatial=list(range(1, n + 1)))
+        e = driver.diag_energy(s, s.ref_orbs)                      # host-side Python (what seeds Hii)
+        tol = 5e-10 * max(1.0, abs(e) / 100)
+        assert abs(e - c["reference_energy"]) < tol, (c["case"], e, c["reference_energy"])
+        o, _ = helpers.make_pair(s, e, max_walkers=100, max_spawned=100)
+        il = s.ilut(s.ref_orbs).reshape(1, -1)
+        assert abs(o.probe_helement(il, il)[0] - c["reference_energy"]) < tol        # the oracle's sltcnd_0 + ECore
+        o.close()
