@@ -394,3 +394,31 @@ def test_oracle_fciqmc_energy_matches_exact_diagonalisation():
     assert abs(e + hii - e0) < max(5 * err, 2e-3), (e + hii, e0, err)
     sm, serr = driver.blocking([h["shift"] for h in hist])
     assert abs(sm + hii - e0) < max(5 * serr, 1e-2), (sm + hii, e0, serr)
+
+
+def test_k_hubbard_generator_known_answers():
+    """gen_excit_k_space_hub on the reference's 4-site chain from nI = [1,2,3,4]: exactly the six determinants of
+    test_k_space_hubbard.F90:2781-2852 are reachable, with the probabilities (p_elec = 1/4, halved where two
+    orbital pairs serve one electron pair) and parities asserted there; the pair [3,4] cannot reach [5,6]
+    (calc_pgen_k_space_hubbard_test :2755-2779)."""
+    g = GOLD["k_hubbard"]; lat = g["lattice"]; k = g["gen_excit"]
+    s = k_chain_system(lat["k_of_spatial_orbital"], lat["bhub"], g["uhub"] / g["omega"], 4, lat["length"])
+    o = oracle_for(s)
+    il = s.ilut(k["nI"]).reshape(1, -1)
+    n = 4000
+    out = o.probe_gen_excit(np.repeat(il, n, axis=0), np.arange(n, dtype=np.int32), 3)
+    seen = {}
+    for j in range(n):
+        if out["pgen"][j] <= 0:
+            continue
+        key = int(np.uint64(out["ilut_j"][j, 0]))
+        seen.setdefault(key, set()).add((float(out["pgen"][j]), int(out["parity"][j]), tuple(int(x) for x in out["ex"][j])))
+    want = {int(np.uint64(s.ilut(c["nJ"])[0])): c for c in k["reachable"]}
+    assert set(seen) == set(want)
+    for key, vals in seen.items():
+        for pg, par, ex in vals:
+            assert pg == want[key]["pgen"] and bool(par) == want[key]["tpar"]
+    src_34_to_56 = int(np.uint64(s.ilut([1, 2, 5, 6])[0]))
+    for pg, par, ex in seen[int(np.uint64(s.ilut([3, 4, 5, 6])[0]))]:
+        assert ex[:2] == (1, 2)                       # [3,4,5,6] is reached by exciting the pair (1,2) only
+    assert src_34_to_56 not in seen                   # pgen([3,4] -> [5,6]) = 0
