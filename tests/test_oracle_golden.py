@@ -422,3 +422,31 @@ def test_k_hubbard_generator_known_answers():
     for pg, par, ex in seen[int(np.uint64(s.ilut([3, 4, 5, 6])[0]))]:
         assert ex[:2] == (1, 2)                       # [3,4,5,6] is reached by exciting the pair (1,2) only
     assert src_34_to_56 not in seen                   # pgen([3,4] -> [5,6]) = 0
+
+
+def test_rs_hubbard_generator_known_answers():
+    """gen_excit_rs_hubbard on the reference's periodic 4-site chain: calc_pgen_rs_hubbard_test
+    (test_real_space_hubbard.F90:1808-1860) pins pgen(1->3) = pgen(2->8) = 1/4 from nI = [1,2]; an occupied neighbour
+    adds nothing to the cumulative list (create_cum_list_rs_hubbard_test :1673-1700), so from nI = [1,3] the beta
+    electron on site 1 reaches only site 4, with pgen 1/2."""
+    g = GOLD["rs_hubbard_gen_excit"]
+    s = _lattice(g["lattice"], 0.0, 2)
+    o = oracle_for(s)
+    n = 2000
+    il = s.ilut(g["nI"]).reshape(1, -1)
+    out = o.probe_gen_excit(np.repeat(il, n, axis=0), np.arange(n, dtype=np.int32), 5)
+    want = {int(np.uint64(s.ilut(c["nJ"])[0])): c["pgen"] for c in g["reachable"]}
+    got = {}
+    for j in range(n):
+        assert out["pgen"][j] > 0 and out["ic"][j] == 1
+        got.setdefault(int(np.uint64(out["ilut_j"][j, 0])), set()).add(float(out["pgen"][j]))
+    assert set(got) == set(want)
+    for k, v in got.items():
+        assert v == {want[k]}
+    b = g["blocked"]
+    il = s.ilut(b["nI"]).reshape(1, -1)
+    out = o.probe_gen_excit(np.repeat(il, n, axis=0), np.arange(n, dtype=np.int32), 5)
+    from_1 = out["ex"][:, 0] == 1
+    assert from_1.sum() > 100
+    assert set(int(x) for x in out["ex"][from_1, 2]) == set(b["reachable_from_orb_1"])
+    assert set(float(x) for x in out["pgen"][from_1]) == {b["pgen"]}
