@@ -233,17 +233,21 @@ def update_shift(diag_sft, sft_damp, tau, steps_sft, av_walkers, old_av_walkers)
 def make_params(system, hii, max_walkers, max_spawned, nranks=1, rank=0, device=0, seed=7, initiator=True,
                 initiator_walk_no=3.0, all_real_coeff=False, real_spawn_cutoff=0.95, occupied_thresh=1.0,
                 av_mc_excits=1.0, semi_stochastic=False, blocks_per_rank=1, hash_seed=7, mapping=None,
-                death_before_comms=None, tau_search=False, consider_par_bias=None, hphf=False):
+                death_before_comms=None, tau_search=False, consider_par_bias=None, hphf=False,
+                random_orb_index=None):
     """The module-level globals of the reference that the engine needs (neci_gpu_config).
     Defaults follow src/Calc.F90:120-480; tDeathBeforeComms is .false. unless the walkers are integers
     (src/Calc.F90:475, src/fcimc_initialisation.fpp:1997-2001) or DEATH-BEFORE-COMMS is given."""
     if death_before_comms is None:
         death_before_comms = not all_real_coeff
     roi, rh2 = random_hash_tables(system.nbasis, hash_seed)
+    if random_orb_index is not None:          # the host's own RandomOrbIndex (src/fcimc_initialisation.fpp:862-890)
+        roi = np.asarray(random_orb_index, dtype=np.int32)
     balance_blocks = nranks * blocks_per_rank
     if mapping is None:
-        # init_load_balance (src/load_balancer.fpp:72-110): block b -> rank mod(b-1, nranks)
-        mapping = np.array([b % nranks for b in range(balance_blocks)], dtype=np.int32)
+        # init_load_balance (src/load_balancer.fpp:72-99): LoadBalanceMapping(i) = int((i-1)/oversample_factor),
+        # i.e. contiguous runs of blocks per rank
+        mapping = np.array([b // blocks_per_rank for b in range(balance_blocks)], dtype=np.int32)
     return dict(
         nel=system.nel, nbasis=system.nbasis, nifd=system.nifd, niftot=system.nifd + 2,
         nocc_alpha=system.nocc_alpha, nocc_beta=system.nocc_beta, nranks=nranks, rank=rank, device=device,

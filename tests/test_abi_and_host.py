@@ -152,7 +152,7 @@ def test_det_node_and_walker_hash_properties():
     il = np.array([s.ilut(d) for d in dets]).reshape(len(dets), s.nw)
     blk, node = o.probe_det_node(il)
     assert blk.min() >= 1 and blk.max() <= 800
-    assert np.array_equal(node, (blk - 1) % 8)                      # init_load_balance mapping
+    assert np.array_equal(node, (blk - 1) // 100)                   # init_load_balance: LoadBalanceMapping(i) = int((i-1)/oversample_factor)
     counts = np.bincount(node, minlength=8)
     assert counts.min() > 0.8 * len(dets) / 8 and counts.max() < 1.2 * len(dets) / 8
     # hand evaluation of get_det_block for one determinant (load_balance_calcnodes.F90:92-115)

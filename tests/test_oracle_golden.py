@@ -450,3 +450,25 @@ def test_rs_hubbard_generator_known_answers():
     assert from_1.sum() > 100
     assert set(int(x) for x in out["ex"][from_1, 2]) == set(b["reachable_from_orb_1"])
     assert set(float(x) for x in out["pgen"][from_1]) == {b["pgen"]}
+
+
+def test_det_node_matches_the_reference_processor_of_its_own_runs():
+    """DetermineDetNode / get_det_block (src/load_balance_calcnodes.F90:25-117) + the initial LoadBalanceMapping
+    (src/load_balancer.fpp:96-99) against `Reference processor is: N` as printed by the reference's regression runs
+    (4 MPI ranks; 4 blocks, or 400 with load-balance-blocks).  RandomOrbIndex of every case was rebuilt with the
+    reference's own dSFMT (tests/golden/make_det_node_fixture.py)."""
+    cases = json.load(open(os.path.join(helpers.GOLDEN, "reference_det_nodes.json")))
+    assert len(cases) >= 40
+    assert any(c["balance_blocks"] > c["nprocs"] for c in cases)
+    for c in cases:
+        nb, nel = c["nbasis"], len(c["det"])
+        s = host.System(kind=capi.SYS_HUBBARD_RS, nel=nel, nbasis=nb, nocc_alpha=nel // 2, nocc_beta=nel - nel // 2,
+                        t_exch=0, t_no_brillouin=1,
+                        tables=dict(max_neigh=1, neighbours=np.zeros(nb, dtype=np.int32), tmat=np.zeros(nb * nb), uhub=0.0),
+                        ref_orbs=np.array(c["det"], dtype=np.int32))
+        o, params = helpers.make_pair(s, 0.0, max_walkers=100, max_spawned=100 * c["nprocs"], nranks=c["nprocs"], rank=0,
+                                      blocks_per_rank=c["balance_blocks"] // c["nprocs"],
+                                      random_orb_index=c["random_orb_index"])
+        blk, node = o.probe_det_node(s.ilut(c["det"]).reshape(1, -1))
+        assert int(blk[0]) == c["block"] and int(node[0]) == c["reference_processor"], (c["case"], blk, node)
+        o.close()
