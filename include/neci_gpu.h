@@ -80,6 +80,9 @@ enum neci_stat_index {
     NECI_ST_TAU_GAMMA_DOUB,      /* doubles without the parallel bias, max-reduced */
     NECI_ST_TAU_GAMMA_PAR,       /* same-spin doubles, max-reduced              */
     NECI_ST_TAU_GAMMA_OPP,       /* opposite-spin doubles, max-reduced          */
+    NECI_ST_TAU_MAX_DEATH_CPT,   /* max (K_ii - S) over the determinants that attempted death this iteration
+                                    (log_death_magnitude, tau/tau_main.F90:198-207; fcimc_pointed_fns.F90:640), max-reduced;
+                                    0 when the tau search is off                 */
     NECI_ST_TOTPARTS,            /* after CalcHashTableStats load_balancer.fpp:738 */
     NECI_ST_NORM_PSI_SQ,         /* norm_psi_squared                            */
     NECI_ST_NORM_SEMISTOCH_SQ,
@@ -108,7 +111,7 @@ enum neci_stat_index {
     NECI_ST_COUNT
 };
 #define NECI_ST_FIRST_MAX NECI_ST_MAX_CYC_SPAWN   /* [FIRST_MAX, LAST_MAX] are max-reduced */
-#define NECI_ST_LAST_MAX  NECI_ST_TAU_GAMMA_OPP
+#define NECI_ST_LAST_MAX  NECI_ST_TAU_MAX_DEATH_CPT
 
 /* ---- configuration: the module-level globals the hot path reads ----------
  * (filled at the end of InitFCIMCCalcPar, src/FciMCPar.F90:256)              */

@@ -20,7 +20,7 @@ ST_NAMES = [
     "NOATDOUBS", "ENUMCYC", "ENUMCYCABS", "INITSENUMCYC", "NOINITDETS", "NONONINITDETS", "NOINITWALK",
     "NONONINITWALK", "NOADDEDINITIATORS", "NVALIDEXCITS", "NINVALIDEXCITS", "BLOOM_COUNT_1", "BLOOM_COUNT_2",
     "MAX_CYC_SPAWN", "BLOOM_SIZE_1", "BLOOM_SIZE_2", "TAU_GAMMA_SING", "TAU_GAMMA_DOUB", "TAU_GAMMA_PAR",
-    "TAU_GAMMA_OPP", "TOTPARTS", "NORM_PSI_SQ", "NORM_SEMISTOCH_SQ",
+    "TAU_GAMMA_OPP", "TAU_MAX_DEATH_CPT", "TOTPARTS", "NORM_PSI_SQ", "NORM_SEMISTOCH_SQ",
     "INSTNOATHF", "TOTWALKERS", "HOLESINLIST", "NSPAWNED_SENT", "NSPAWNED_RECV", "NSPAWNED_MERGED",
     "NINSERTED", "HIGHEST_POP", "TRIAL_NUMERATOR", "TRIAL_DENOM", "INIT_TRIAL_NUMERATOR", "INIT_TRIAL_DENOM",
     "TAU_CNT_SING", "TAU_CNT_DOUB", "TAU_CNT_PAR", "TAU_CNT_OPP", "ERR_FLAGS", "TIME_SPAWN_MS", "TIME_COMM_MS", "TIME_ANNIHIL_MS",
@@ -29,7 +29,7 @@ ST_NAMES = [
 ST = {n: i for i, n in enumerate(ST_NAMES)}
 ST_COUNT = len(ST_NAMES)
 ST_MAX_REDUCED = ("MAX_CYC_SPAWN", "BLOOM_SIZE_1", "BLOOM_SIZE_2", "TAU_GAMMA_SING", "TAU_GAMMA_DOUB", "TAU_GAMMA_PAR",
-                  "TAU_GAMMA_OPP", "HIGHEST_POP")
+                  "TAU_GAMMA_OPP", "TAU_MAX_DEATH_CPT", "HIGHEST_POP")
 
 SYS_FCIDUMP_PCHB, SYS_HUBBARD_RS, SYS_HUBBARD_K = 1, 2, 3
 FLAG_REMOVED, FLAG_DETERM_PARENT, FLAG_INITIATOR, FLAG_DETERMINISTIC = 0, 1, 13, 19

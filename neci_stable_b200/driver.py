@@ -134,8 +134,8 @@ class TauSearch:
     per-iteration maxima and counts the engine returns (log_spawn_magnitude, :138-260).  Keeps the running maxima
     gamma_* and the enough_* switches (cnt_threshold = 50), proposes tau = MaxWalkerBloom * p_class / gamma_class and,
     once every class has been seen often enough, the biases pParallel = gamma_par / (gamma_opp + gamma_par) and
-    pSingles = gamma_sing pParallel / (gamma_par + gamma_sing pParallel).  The death-magnitude cap
-    (max_death_cpt, :425-436) is not applied: the engine does not return it."""
+    pSingles = gamma_sing pParallel / (gamma_par + gamma_sing pParallel); tau never exceeds 1 / max_death_cpt
+    (the largest K_ii - S seen at a death attempt, :419-430)."""
     CNT_THRESHOLD = 50
 
     def __init__(self, tau, p_singles, p_doubles, p_parallel, consider_par_bias, max_walker_bloom=1.0,
@@ -144,12 +144,14 @@ class TauSearch:
         self.par_bias, self.bloom, self.min_tau, self.max_tau = consider_par_bias, max_walker_bloom, min_tau, max_tau
         self.gamma = np.zeros(4)                 # sing, doub, par, opp
         self.cnt = np.zeros(4)
+        self.max_death_cpt = 0.0
 
     def log(self, stats):
         """Accumulate one iteration's statistics vector (after the max / sum reduction over ranks)."""
         g0 = ST["TAU_GAMMA_SING"]; c0 = ST["TAU_CNT_SING"]
         self.gamma = np.maximum(self.gamma, stats[g0:g0 + 4])
         self.cnt += stats[c0:c0 + 4]
+        self.max_death_cpt = max(self.max_death_cpt, stats[ST["TAU_MAX_DEATH_CPT"]])
 
     @property
     def enough(self):
@@ -190,6 +192,11 @@ class TauSearch:
                 tau_new = self.bloom * self.p_singles / g_sing
             else:
                 tau_new = self.tau
+        if abs(self.max_death_cpt) > eps:
+            tau_death = 1.0 / self.max_death_cpt
+            if tau_death < tau_new:
+                self.min_tau = min(self.min_tau, tau_death)
+                tau_new = tau_death
         tau_new = min(max(tau_new, self.min_tau), self.max_tau)
         if tau_new < self.tau or (e_sing and e_doub):
             self.tau = tau_new * 0.99999

@@ -274,6 +274,9 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
             // attempt_die_normal, src/fcimc_pointed_fns.F90:573-705
             const double fac = tau * (HDiagCurr - DiagSft);
             if (fac > 2.0) e.stats[NECI_ST_ERR_FLAGS] = (double)((int)e.stats[NECI_ST_ERR_FLAGS] | 4);
+            // log_death_magnitude(Kii - shift), src/fcimc_pointed_fns.F90:640, src/tau/tau_main.F90:198-207
+            if (c.t_tau_search)                          // attempt_die runs (and logs) for core determinants too
+                e.stats[NECI_ST_TAU_MAX_DEATH_CPT] = std::max(e.stats[NECI_ST_TAU_MAX_DEATH_CPT], HDiagCurr - DiagSft);
             if (c.t_all_real_coeff) iDie = fac * std::fabs(SignCurr);
             else {
                 double rat = fac * std::fabs(SignCurr);

@@ -116,3 +116,4 @@ def test_tau_search_loop_caps_the_spawns():
     assert abs(ts.p_parallel - g_par / (g_par + g_opp)) < 1e-12
     assert (ts.p_singles, ts.p_parallel) != probs0
     assert abs(ts.p_singles + ts.p_doubles - 1.0) < 1e-15
+    assert ts.max_death_cpt > 0.0 and tau <= 1.0 / ts.max_death_cpt             # death cap of update_tau
