@@ -575,6 +575,19 @@ __global__ void __launch_bounds__(NG_BLOCK) k_trial_energy(Params P, WalkerList 
     block_flush_stats<4>(acc, idx, partials, s_red);
 }
 
+// log_death_magnitude (src/tau/tau_main.F90:198-207, called from attempt_die for every determinant, core ones
+// included): max (K_ii - S) over the list the walker loop is about to see.  Its own streaming pass, launched only
+// when the tau search is on -- inside the spawning kernel it cost 3 % of every run.
+__global__ void __launch_bounds__(NG_BLOCK) k_death_magnitude(WalkerList L, double diag_sft, double *partials) {
+    __shared__ double s_red[32];
+    const long long n = L.ctr[C_NLIST];
+    double acc[1] = {0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (fabs(L.sgn[i]) >= 1.0e-12) acc[0] = fmax(acc[0], L.diagH[i] - diag_sft);
+    const int idx[1] = {NECI_ST_TAU_MAX_DEATH_CPT};
+    block_flush_stats<1>(acc, idx, partials, s_red);
+}
+
 // ---- probes ---------------------------------------------------------------------------
 template <int NW>
 __global__ void k_probe_det_node(Params P, const long long *iluts, long long n, int *block_out, int *node_out) {

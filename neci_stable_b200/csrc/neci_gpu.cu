@@ -72,7 +72,7 @@ struct neci_gpu_engine {
     double *d_partials = nullptr, *d_stats = nullptr, *h_stats = nullptr;
     unsigned int *d_ticket = nullptr;
     long long *h_ctr = nullptr;
-    int rows_spawn = 0, rows_heavy = 0, rows_compress = 0, rows_annih = 0, rows_insert = 0, rows_list = 0, rows_trial = 0, rows_total = 0;
+    int rows_spawn = 0, rows_heavy = 0, rows_compress = 0, rows_annih = 0, rows_insert = 0, rows_list = 0, rows_trial = 0, rows_tau = 0, rows_total = 0;
     int grid_spawn = 0, grid_generic = 0;
     u32 stamp = 0;
     bool need_rebuild = false;
@@ -234,7 +234,8 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
         e->rows_spawn = nsm * per_sm; e->rows_heavy = nsm * per_sm;
     }
     e->rows_trial = e->grid_generic;
-    e->rows_total = e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih + e->rows_insert + e->rows_list + e->rows_trial;
+    e->rows_tau = e->grid_generic;            // rows of k_death_magnitude, placed before the trial rows
+    e->rows_total = e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih + e->rows_insert + e->rows_list + e->rows_tau + e->rows_trial;
     e->d_partials = e->alloc<double>((size_t)e->rows_total * NECI_ST_COUNT);
     e->d_stats = e->alloc<double>(NECI_ST_COUNT);
     e->d_ticket = e->alloc<unsigned int>(1);
@@ -731,6 +732,11 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
                 e->L, e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft,
                 e->cfg.t_death_before_comms ? (const double *)nullptr : (const double *)e->d_core_diag, e->d_vout);
     }
+    if (e->cfg.t_tau_search) {
+        double *p_tau = e->d_partials + (size_t)(e->rows_total - e->rows_trial - e->rows_tau) * NECI_ST_COUNT;
+        e->n_launch += 1;
+        k_death_magnitude<<<e->rows_tau, NG_BLOCK, 0, e->stream>>>(e->L, diag_sft, p_tau);
+    }
     if (e->P.trial_ht) {
         // trial part of SumEContrib on the signs the walker loop sees (before death)
         double *p_trial = e->d_partials + (size_t)(e->rows_total - e->rows_trial) * NECI_ST_COUNT;
@@ -766,7 +772,8 @@ int neci_gpu_annihilate(neci_gpu_engine *e, const int64_t *spawned_parts, int64_
     if (begin_iteration(e)) return 1;
     if (n_spawned > e->cfg.max_spawned) return e->fail("n_spawned exceeds max_spawned");
     CK(cudaMemsetAsync(e->d_partials, 0, (size_t)(e->rows_spawn + e->rows_heavy) * NECI_ST_COUNT * 8, e->stream));
-    CK(cudaMemsetAsync(e->d_partials + (size_t)(e->rows_total - e->rows_trial) * NECI_ST_COUNT, 0, (size_t)e->rows_trial * NECI_ST_COUNT * 8, e->stream));
+    CK(cudaMemsetAsync(e->d_partials + (size_t)(e->rows_total - e->rows_trial - e->rows_tau) * NECI_ST_COUNT, 0,
+                       (size_t)(e->rows_trial + e->rows_tau) * NECI_ST_COUNT * 8, e->stream));
     CK(cudaMemcpyAsync(e->SB.recv, spawned_parts, (size_t)n_spawned * e->W * 8, cudaMemcpyHostToDevice, e->stream));
     IterArgs A; A.tau = 0; A.diag_sft = 0; A.iter = iter; A.n_recv = n_spawned; A.stamp = 0;
     for (int k = 0; k < 4; ++k) CK(cudaEventRecord(e->ev[k], e->stream));

@@ -77,7 +77,7 @@ __device__ __forceinline__ double warp_max(double v) {
 
 // statistics accumulated by K1, in the order of their rows in K1Shared::wacc
 enum { W_NODIED = 0, W_NOBORN_D, W_ABORT, W_HF, W_DOUBS, W_ENUM, W_ENUMABS, W_INITSENUM, W_INITD, W_NINITD, W_INITW,
-       W_NINITW, W_ADDED, W_CHILD, W_CHILD_SING, W_VALID, W_INVALID, W_MAXSP, W_MAXDIE, W_COUNT };
+       W_NINITW, W_ADDED, W_CHILD, W_CHILD_SING, W_VALID, W_INVALID, W_MAXSP, W_COUNT };
 enum { W_STAGE_A = W_CHILD };   // [0, W_STAGE_A) are flushed once per tile, the rest once per kernel
 
 template <int NW> struct K1Shared {
@@ -393,7 +393,7 @@ __device__ __forceinline__ void k1_flush(const WalkerList &L, K1Shared<NW> &S, c
     if (threadIdx.x < W_COUNT) {
         const int k = threadIdx.x;
         double t = S.wacc[0][k];
-        for (int w = 1; w < K1_BLOCK / 32; ++w) t = (k == W_MAXSP || k == W_MAXDIE) ? fmax(t, S.wacc[w][k]) : t + S.wacc[w][k];
+        for (int w = 1; w < K1_BLOCK / 32; ++w) t = (k == W_MAXSP) ? fmax(t, S.wacc[w][k]) : t + S.wacc[w][k];
         S.wacc[0][k] = t;
     }
     __syncthreads();
@@ -405,7 +405,6 @@ __device__ __forceinline__ void k1_flush(const WalkerList &L, K1Shared<NW> &S, c
         row[NECI_ST_NVALIDEXCITS] = t[W_VALID];
         row[NECI_ST_NINVALIDEXCITS] = t[W_INVALID];
         row[NECI_ST_MAX_CYC_SPAWN] = t[W_MAXSP];
-        if (with_stage_a) row[NECI_ST_TAU_MAX_DEATH_CPT] = t[W_MAXDIE];
         row[NECI_ST_BLOOM_COUNT_1] = (double)S.bloom_cnt[0];
         row[NECI_ST_BLOOM_COUNT_2] = (double)S.bloom_cnt[1];
 #pragma unroll
@@ -434,7 +433,6 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         // ---------------- stage A: one thread per slot --------------------------------------------
         double sa[W_STAGE_A];
-        double sa_maxdie = 0.0;
 #pragma unroll
         for (int k = 0; k < W_STAGE_A; ++k) sa[k] = 0.0;
         // all five streams of both slots are requested before anything is consumed: one HBM round trip per
@@ -498,8 +496,6 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
                     // perform_death_all_walkers (fcimc_helper.F90:2253-2277) would run it after the loop for every
                     // determinant, core ones included -- death of slot j touches only slot j, so it is fused here too
                     double news = s;
-                    // log_death_magnitude: attempt_die evaluates (and logs) K_ii - S for every determinant, core ones too
-                    if (P.t_tau_search) sa_maxdie = fmax(sa_maxdie, K - A.diag_sft);
                     if (!core || !P.t_death_before_comms) {
                         const double fac = A.tau * (K - A.diag_sft);
                         if (fac > 2.0) atomicOr((unsigned long long *)&L.ctr[C_ERR], 4ull);
@@ -546,10 +542,6 @@ __device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L,
         for (int k = 0; k < W_STAGE_A; ++k) {
             const double t = warp_sum(sa[k]);
             if (lane == 0) S.wacc[warp][k] += t;
-        }
-        if (P.t_tau_search) {
-            const double t = warp_max(sa_maxdie);
-            if (lane == 0) S.wacc[warp][W_MAXDIE] = fmax(S.wacc[warp][W_MAXDIE], t);
         }
         // exclusive prefix sum of the attempt counts over the tile (index order kk * 256 + tid)
         int run = 0;
