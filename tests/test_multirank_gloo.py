@@ -19,8 +19,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N_ITER = 300
 
 
-def _system():
-    return host.hubbard_k_system(3, 2, nel=4, U=4.0), 0.03
+def _system(kind="hub_k"):
+    if kind == "pchb_hphf":                    # HPHF functions: spawns are routed by their representative determinant
+        return host.random_fcidump_system(6, 6, sparse=0.9, sparse_t=0.9, seed=3), 0.004, dict(hphf=True)
+    return host.hubbard_k_system(3, 2, nel=4, U=4.0), 0.03, {}
 
 
 def _run(engine, system, hii, tau, nranks, rank, owner_of_ref):
@@ -31,13 +33,13 @@ def _run(engine, system, hii, tau, nranks, rank, owner_of_ref):
     return run
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, kind):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
-    system, tau = _system()
+    system, tau, extra = _system(kind)
     hii = driver.diag_energy(system, system.ref_orbs)
     o, params = helpers.make_pair(system, hii, max_walkers=50000, max_spawned=50000, nranks=world, rank=rank, seed=5,
-                                  blocks_per_rank=4)
+                                  blocks_per_rank=4, **extra)
     _, node = o.probe_det_node(system.ilut(system.ref_orbs).reshape(1, -1))
     eng = helpers.DistOracle(o, dist)
     run = _run(eng, system, hii, tau, world, rank, int(node[0]))
@@ -49,17 +51,18 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_job_reproduces_single_rank(tmp_path):
+@pytest.mark.parametrize("kind", ["hub_k", "pchb_hphf"])
+def test_two_rank_job_reproduces_single_rank(tmp_path, kind):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), kind), nprocs=2, join=True)
     r = [np.load(os.path.join(tmp_path, "rank%d.npz" % k)) for k in range(2)]
     # both ranks saw the same reduced statistics
     assert np.array_equal(r[0]["shift"], r[1]["shift"]) and np.array_equal(r[0]["parts"], r[1]["parts"])
     # single-rank run of the same job
-    system, tau = _system()
+    system, tau, extra = _system(kind)
     hii = driver.diag_energy(system, system.ref_orbs)
-    o, params = helpers.make_pair(system, hii, max_walkers=50000, max_spawned=50000, nranks=1, rank=0, seed=5)
+    o, params = helpers.make_pair(system, hii, max_walkers=50000, max_spawned=50000, nranks=1, rank=0, seed=5, **extra)
     run = _run(o, system, hii, tau, 1, 0, 0)
     assert np.array_equal(r[0]["parts"], np.array([h["tot_parts"] for h in run.history]))
     assert np.allclose(r[0]["shift"], np.array([h["shift"] for h in run.history]), rtol=1e-12, atol=1e-12)
@@ -71,7 +74,7 @@ def test_two_rank_job_reproduces_single_rank(tmp_path):
     for a, b in zip(both[:3], one[:3]):
         assert np.array_equal(a, b)
     # ownership
-    o2, _ = helpers.make_pair(system, hii, max_walkers=100, max_spawned=100, nranks=2, rank=0, seed=5, blocks_per_rank=4)
+    o2, _ = helpers.make_pair(system, hii, max_walkers=100, max_spawned=100, nranks=2, rank=0, seed=5, blocks_per_rank=4, **extra)
     for k in range(2):
         c = helpers.canon(r[k]["dets"], nw=system.nw)
         _, nd = o2.probe_det_node(c[0])
