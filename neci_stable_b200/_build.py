@@ -43,11 +43,11 @@ def build_gpu(force=False, verbose=False):
 
 
 def build_host(force=False):
-    src = os.path.join(CSRC, "host", "neci_host.cpp")
-    if not force and not _newer(HOST_LIB, [src]):
+    srcs = [os.path.join(CSRC, "host", f) for f in ("neci_host.cpp", "core_space.cpp")]
+    if not force and not _newer(HOST_LIB, srcs):
         return HOST_LIB
     cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
-    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", HOST_LIB, src])
+    subprocess.check_call([cxx, "-O3", "-mpopcnt", "-std=c++17", "-fPIC", "-ffp-contract=off", "-pthread", "-shared", "-o", HOST_LIB] + srcs)
     return HOST_LIB
 
 

@@ -4,7 +4,8 @@ Everything here produces inputs of exactly the shapes the Fortran host would
 pass through the C ABI (include/neci_gpu.h): integral tables, PCHB alias tables,
 lattice tables, the hashing tables, the reference determinant and the engine
 configuration.  The heavy loops live in ``csrc/host/neci_host.cpp``
-(``libneci_host.so``); this module is the typed Python face of that library.
+(``libneci_host.so``) and ``csrc/host/core_space.cpp`` (semi-stochastic set-up: core space, its sparse
+Hamiltonian, DetermineDetNode); this module is the typed Python face of that library.
 """
 import ctypes as C
 import os
@@ -28,6 +29,8 @@ def lib():
         _lib = C.CDLL(HOST_LIB)
         _lib.neci_host_umat_size.restype = C.c_int64
         _lib.neci_host_update_shift.restype = C.c_double
+        _lib.neci_host_sd_space.restype = C.c_int64
+        _lib.neci_host_core_ham_build.restype = C.c_void_p
     return _lib
 
 
@@ -307,3 +310,143 @@ def parse_popsfile_lines(lines, nw=1):
         if len(t) > nw + 2:
             gd.append(float(t[nw + 2])); go.append(float(t[nw + 3]))
     return dets, (np.array(gd) if gd else None), (np.array(go) if go else None)
+
+
+# ---------------------------------------------------------------------------------------
+# semi-stochastic set-up (what init_semi_stochastic hands to neci_gpu_set_core_space)
+# ---------------------------------------------------------------------------------------
+def _iluts(system, iluts):
+    return np.ascontiguousarray(np.asarray(iluts, dtype=np.int64).reshape(-1, system.nw))
+
+
+def get_helement(system, iluts_i, iluts_j):
+    """get_helement (src/Determinants.F90:508-554) for pairs of determinants of an FCIDUMP system, on the host."""
+    if system.kind != capi.SYS_FCIDUMP_PCHB:
+        raise ValueError("host get_helement: FCIDUMP systems only")
+    a, b = _iluts(system, iluts_i), _iluts(system, iluts_j)
+    out = np.zeros(a.shape[0])
+    t = system.tables
+    rc = lib().neci_host_get_helement(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
+                                      _p(t["tmat"], C.c_double), C.c_double(system.ecore), _p(a, C.c_int64),
+                                      _p(b, C.c_int64), C.c_int64(a.shape[0]), _p(out, C.c_double))
+    if rc:
+        raise RuntimeError("neci_host_get_helement failed (%d)" % rc)
+    return out
+
+
+def sing_doub_space(system, ref_ilut=None, only_keep_conn=False):
+    """`doubles-core`: the reference determinant and its single and double excitations
+    (generate_sing_doub_determinants, src/semi_stoch_gen.F90:537-604) as n x nw occupation words."""
+    ref = _iluts(system, system.ilut(system.ref_orbs) if ref_ilut is None else ref_ilut)
+    t = system.tables
+    na, nb_ = system.nocc_alpha, system.nocc_beta
+    va, vb = system.nbasis // 2 - na, system.nbasis // 2 - nb_
+    cap = 1 + na * va + nb_ * vb + (na * (na - 1) // 2) * (va * (va - 1) // 2) \
+        + (nb_ * (nb_ - 1) // 2) * (vb * (vb - 1) // 2) + na * va * nb_ * vb
+    out = np.zeros((cap, system.nw), dtype=np.int64)
+    n = lib().neci_host_sd_space(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
+                                 _p(t["tmat"], C.c_double), _p(ref, C.c_int64), C.c_int32(int(only_keep_conn)),
+                                 C.c_int64(cap), _p(out, C.c_int64))
+    if n <= 0:
+        raise RuntimeError("neci_host_sd_space failed (%d)" % n)
+    return out[:n].copy()
+
+
+def det_node(params, iluts, nw):
+    """DetermineDetNode (src/load_balance_calcnodes.F90:25-117) on the host -> (block, node) per determinant."""
+    il = np.ascontiguousarray(np.asarray(iluts, dtype=np.int64).reshape(-1, nw))
+    blocks = np.zeros(il.shape[0], dtype=np.int32)
+    nodes = np.zeros(il.shape[0], dtype=np.int32)
+    roi = np.ascontiguousarray(params["random_orb_index"], dtype=np.int32)
+    mapping = np.ascontiguousarray(params["load_balance_mapping"], dtype=np.int32)
+    rc = lib().neci_host_det_node(C.c_int32(params["nbasis"]), _p(roi, C.c_int32), C.c_int32(params["balance_blocks"]),
+                                  _p(mapping, C.c_int32), _p(il, C.c_int64), C.c_int64(il.shape[0]),
+                                  _p(blocks, C.c_int32), _p(nodes, C.c_int32))
+    if rc:
+        raise RuntimeError("neci_host_det_node failed (%d)" % rc)
+    return blocks, nodes
+
+
+def _ilut_sort_keys(il):
+    """Keys for np.lexsort reproducing ilut_lt (src/DetBitOps.F90:431-473): signed compare, word 0 most significant."""
+    return tuple(il[:, k] for k in range(il.shape[1] - 1, -1, -1))
+
+
+def layout_core_space(core_iluts, nodes, nranks):
+    """Order of the whole core space as store_whole_core_space leaves it (src/semi_stoch_gen.F90:214-243): rank by
+    rank, each rank's determinants sorted with ilut_lt.  Returns (ordered iluts, sizes, displs)."""
+    il = np.asarray(core_iluts, dtype=np.int64)
+    nodes = np.asarray(nodes)
+    order = np.lexsort(_ilut_sort_keys(il) + (nodes,))
+    sizes = np.bincount(nodes, minlength=nranks).astype(np.int32)
+    displs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32)
+    return np.ascontiguousarray(il[order]), sizes, displs
+
+
+def core_hamiltonian(system, core_iluts, hii, displ=0, n_local=None, threads=0):
+    """Sparse core Hamiltonian rows of one rank (calc_determ_hamil_sparse, src/sparse_arrays.F90:426-572; each row:
+    the non-zero off-diagonal elements, then H_ii - Hii last as src/fast_determ_hamil.F90:1494-1507 leaves it).
+    Returns dict(row_ptr int64, col int32, val float64) for neci_gpu_set_core_space."""
+    if system.kind != capi.SYS_FCIDUMP_PCHB:
+        raise ValueError("host core_hamiltonian: FCIDUMP systems only")
+    il = _iluts(system, core_iluts)
+    n_core = il.shape[0]
+    n_local = n_core - displ if n_local is None else int(n_local)
+    t = system.tables
+    nnz = C.c_int64(0)
+    L = lib()
+    h = L.neci_host_core_ham_build(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
+                                   _p(t["tmat"], C.c_double), C.c_double(system.ecore), C.c_double(hii),
+                                   _p(il, C.c_int64), C.c_int64(n_core), C.c_int64(int(displ)), C.c_int64(n_local),
+                                   C.c_int32(int(threads)), C.byref(nnz))
+    if not h:
+        raise RuntimeError("neci_host_core_ham_build failed")
+    row_ptr = np.zeros(n_local + 1, dtype=np.int64)
+    col = np.zeros(nnz.value, dtype=np.int32)
+    val = np.zeros(nnz.value, dtype=np.float64)
+    L.neci_host_core_ham_fetch(C.c_void_p(h), _p(row_ptr, C.c_int64), _p(col, C.c_int32), _p(val, C.c_double))
+    return dict(row_ptr=row_ptr, col=col, val=val)
+
+
+def ham_apply(system, rows, cols, vec, threads=0):
+    """out_i = sum_j <row_i|H|col_j> vec_j on the host (FCIDUMP systems)."""
+    if system.kind != capi.SYS_FCIDUMP_PCHB:
+        raise ValueError("host ham_apply: FCIDUMP systems only")
+    r, c = _iluts(system, rows), _iluts(system, cols)
+    v = np.ascontiguousarray(vec, dtype=np.float64)
+    assert v.shape[0] == c.shape[0]
+    out = np.zeros(r.shape[0])
+    t = system.tables
+    rc = lib().neci_host_ham_apply(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
+                                   _p(t["tmat"], C.c_double), C.c_double(system.ecore), _p(r, C.c_int64),
+                                   C.c_int64(r.shape[0]), _p(c, C.c_int64), C.c_int64(c.shape[0]), _p(v, C.c_double),
+                                   C.c_int32(int(threads)), _p(out, C.c_double))
+    if rc:
+        raise RuntimeError("neci_host_ham_apply failed (%d)" % rc)
+    return out
+
+
+def trial_space(system, trial_iluts):
+    """init_trial_wf (src/trial_wf_gen.F90) for a given trial space: the trial vector is the lowest eigenvector of H
+    in that space; the connected space is every determinant outside it within two excitations of one of its members
+    (generate_connected_space) with con_space_vecs_i = sum_j H_ij psiT_j != 0.
+    Returns (trial_iluts, trial_amps, con_iluts, con_amps, trial_energy) for neci_gpu_set_trial_space."""
+    ti = _iluts(system, trial_iluts)
+    nt = ti.shape[0]
+    I = np.repeat(np.arange(nt), nt); J = np.tile(np.arange(nt), nt)
+    Ht = get_helement(system, ti[I], ti[J]).reshape(nt, nt)
+    w, v = np.linalg.eigh(Ht)
+    psi = v[:, 0].copy()
+    con = np.concatenate([sing_doub_space(system, ref_ilut=ti[k])[1:] for k in range(nt)])
+    con = np.unique(np.concatenate([ti, con]), axis=0)
+    con = np.ascontiguousarray(con[~_rows_in(con, ti)])            # without the trial determinants themselves
+    amps = ham_apply(system, con, ti, psi)
+    keep = np.abs(amps) > 0
+    return ti, psi, np.ascontiguousarray(con[keep]), amps[keep], float(w[0])
+
+
+def _rows_in(a, b):
+    """Boolean mask: which rows of a occur in b (both n x nw int64)."""
+    av = np.ascontiguousarray(a).view([("", a.dtype)] * a.shape[1]).ravel()
+    bv = np.ascontiguousarray(b).view([("", b.dtype)] * b.shape[1]).ravel()
+    return np.isin(av, bv)

@@ -1,0 +1,189 @@
+"""Host-side semi-stochastic set-up (neci_stable_b200/csrc/host/core_space.cpp) against the oracle:
+get_helement (src/Determinants.F90:508-554), generate_sing_doub_determinants (src/semi_stoch_gen.F90:537-604),
+DetermineDetNode (src/load_balance_calcnodes.F90:25-117) and the sparse core Hamiltonian
+(src/sparse_arrays.F90:426-572, src/fast_determ_hamil.F90:1421-1507).  All CPU."""
+import numpy as np
+import pytest
+
+import helpers
+from neci_stable_b200 import capi, host, driver
+from neci_stable_b200.capi import ST
+
+
+def _systems():
+    return {
+        "1word": host.random_fcidump_system(6, 6, sparse=0.7, sparse_t=0.7, seed=3),
+        "odd": host.random_fcidump_system(7, 5, sparse=1.0, sparse_t=1.0, seed=5, ms2=1),
+        "2words": host.random_fcidump_system(33, 8, sparse=0.7, sparse_t=0.7, seed=9),
+    }
+
+
+def _iluts(system, dets):
+    return np.array([system.ilut(d) for d in dets], dtype=np.int64).reshape(len(dets), system.nw)
+
+
+@pytest.mark.parametrize("name", ["1word", "odd", "2words"])
+def test_host_get_helement_equals_oracle(name):
+    s = _systems()[name]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000)
+    rng = np.random.default_rng(1)
+    # the reference, a sample of the sector and everything within two excitations of the reference: all of
+    # sltcnd_0/1/2 and the "more than a double" zero are hit many times
+    sd = host.sing_doub_space(s)
+    pick = rng.choice(sd.shape[0], min(60, sd.shape[0]), replace=False)
+    il = np.concatenate([sd[pick], _iluts(s, helpers.random_dets(s, 40, rng))])
+    n = il.shape[0]
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    h_host = host.get_helement(s, il[I], il[J])
+    h_orc = o.probe_helement(il[I], il[J])
+    assert np.count_nonzero(h_orc) > n                                   # not a trivial comparison
+    assert np.allclose(h_host, h_orc, rtol=1e-12, atol=1e-13)
+    assert np.array_equal(h_host == 0.0, h_orc == 0.0)
+    H = h_host.reshape(n, n)
+    assert np.allclose(H, H.T, rtol=0, atol=1e-13)
+    assert abs(H[0, 0] - host.get_helement(s, il[:1], il[:1])[0]) == 0.0
+
+
+@pytest.mark.parametrize("name", ["1word", "odd", "2words"])
+def test_sing_doub_space_is_exactly_the_sector_within_two_excitations(name):
+    s = _systems()[name]
+    sd = host.sing_doub_space(s)
+    ref = s.ilut(s.ref_orbs)
+    assert np.array_equal(sd[0], ref)
+    keys = {tuple(r) for r in sd.tolist()}
+    assert len(keys) == sd.shape[0]                                      # no determinant twice
+    if name != "2words":
+        want = set()
+        for d in helpers.all_dets(s):
+            il = s.ilut(d)
+            if sum(bin(int(x)).count("1") for x in (il ^ ref).view(np.uint64)) <= 4:
+                want.add(tuple(il.tolist()))
+        assert keys == want
+    else:
+        na, va = s.nocc_alpha, s.nbasis // 2 - s.nocc_alpha
+        nb, vb = s.nocc_beta, s.nbasis // 2 - s.nocc_beta
+        pairs = lambda n: n * (n - 1) // 2
+        assert sd.shape[0] == 1 + na * va + nb * vb + pairs(na) * pairs(va) + pairs(nb) * pairs(vb) + na * va * nb * vb
+        x = (sd ^ ref).view(np.uint64)
+        assert max(sum(bin(int(w)).count("1") for w in row) for row in x) == 4
+    # only_keep_conn drops exactly the determinants with no matrix element to the reference (:585-594)
+    conn = host.sing_doub_space(s, only_keep_conn=True)
+    h = host.get_helement(s, np.repeat(ref[None, :], sd.shape[0], 0), sd)
+    keep = np.abs(h) >= 1e-12
+    keep[0] = True
+    assert np.array_equal(conn, sd[keep])
+
+
+@pytest.mark.parametrize("name,nranks,bpr", [("1word", 1, 1), ("1word", 4, 1), ("2words", 3, 100), ("odd", 8, 100)])
+def test_host_det_node_equals_oracle(name, nranks, bpr):
+    s = _systems()[name]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000, nranks=nranks, rank=0, blocks_per_rank=bpr)
+    il = _iluts(s, helpers.random_dets(s, 500, np.random.default_rng(2)))
+    b_o, n_o = o.probe_det_node(il)
+    b_h, n_h = host.det_node(params, il, s.nw)
+    assert np.array_equal(b_o, b_h) and np.array_equal(n_o, n_h)
+    assert len(set(n_h.tolist())) == nranks
+
+
+@pytest.mark.parametrize("name,nranks", [("1word", 1), ("1word", 3), ("2words", 2)])
+def test_core_hamiltonian_rows(name, nranks):
+    """Same non-zero pattern and values as the dense matrix of the oracle's elements; diagonal (H_ii - Hii) last in
+    its row; off-diagonal columns ascending; rows split over ranks exactly as sizes/displs say."""
+    s = _systems()[name]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000, nranks=nranks, rank=0)
+    rng = np.random.default_rng(4)
+    sd = host.sing_doub_space(s)
+    core = sd[np.sort(rng.choice(sd.shape[0], min(300, sd.shape[0]), replace=False))]
+    _, nodes = host.det_node(params, core, s.nw)
+    il, sizes, displs = host.layout_core_space(core, nodes, nranks)
+    # rank-major, sorted by signed words inside a rank (src/semi_stoch_gen.F90:227)
+    _, nodes_sorted = host.det_node(params, il, s.nw)
+    assert np.all(np.diff(nodes_sorted) >= 0)
+    for r in range(nranks):
+        seg = il[displs[r]:displs[r] + sizes[r]]
+        assert all(tuple(seg[k]) < tuple(seg[k + 1]) for k in range(seg.shape[0] - 1))
+    n = il.shape[0]
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    H = o.probe_helement(il[I], il[J]).reshape(n, n)
+    H[np.arange(n), np.arange(n)] -= hii
+    total = 0
+    for r in range(nranks):
+        c = host.core_hamiltonian(s, il, hii, displ=int(displs[r]), n_local=int(sizes[r]), threads=3)
+        assert c["row_ptr"][0] == 0 and c["row_ptr"][-1] == c["col"].shape[0] == c["val"].shape[0]
+        for k in range(int(sizes[r])):
+            i = int(displs[r]) + k
+            cols = c["col"][c["row_ptr"][k]:c["row_ptr"][k + 1]]
+            vals = c["val"][c["row_ptr"][k]:c["row_ptr"][k + 1]]
+            assert cols[-1] == i and np.all(np.diff(cols[:-1]) > 0) and i not in cols[:-1]
+            row = np.zeros(n); row[cols] = vals
+            want = H[i].copy()
+            assert np.array_equal(np.nonzero(row)[0], np.nonzero(want)[0]) or want[i] == 0.0
+            assert np.allclose(row, want, rtol=1e-12, atol=1e-13)
+        total += int(sizes[r])
+    assert total == n
+    # thread count must not change the result
+    a = host.core_hamiltonian(s, il, hii, threads=1)
+    b = host.core_hamiltonian(s, il, hii, threads=8)
+    assert all(np.array_equal(a[k], b[k]) for k in ("row_ptr", "col", "val"))
+
+
+def test_doubles_core_run_with_host_built_hamiltonian_matches_helper_built_one():
+    """The engine-facing product of this module, end to end on the oracle: a semi-stochastic run whose core
+    Hamiltonian comes from host.core_hamiltonian gives the same walker list as one fed by the test helper's dense
+    construction (tests/helpers.py:build_core_space), to the 1e-12 of a different summation order."""
+    s = host.random_fcidump_system(6, 4, sparse=1.0, sparse_t=1.0, seed=3)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    sd = host.sing_doub_space(s)
+    dets = [[b + 1 for b in range(s.nbasis) if (int(row[0]) >> b) & 1] for row in sd]
+    flags = (1 << capi.FLAG_DETERMINISTIC) | (1 << capi.FLAG_INITIATOR)
+    lists = []
+    for which in ("helper", "host"):
+        o, params = helpers.make_pair(s, hii, max_walkers=20000, max_spawned=20000, semi_stochastic=True, seed=5)
+        if which == "helper":
+            d2, sizes, displs, per_rank, _ = helpers.build_core_space(o, s, dets, hii)
+            c = per_rank[0]; il = c["iluts"]
+        else:
+            il, sizes, displs = host.layout_core_space(sd, np.zeros(sd.shape[0], dtype=np.int64), 1)
+            c = host.core_hamiltonian(s, il, hii)
+        recs = np.array([host.record(s, [b + 1 for b in range(s.nbasis) if (int(row[0]) >> b) & 1],
+                                     10.0 if np.array_equal(row, s.ilut(s.ref_orbs)) else 0.0, flags) for row in il])
+        o.upload_walkers(recs)
+        o.set_core_space(c["row_ptr"], c["col"], c["val"], sizes, displs, il)
+        for it in range(1, 40):
+            st = o.iterate(0.002, 0.0, it)
+        lists.append(helpers.canon(*o.download_walkers(), nw=s.nw))
+        assert st[ST["NORM_SEMISTOCH_SQ"]] > 0
+    a, b = lists
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert np.allclose(a[1], b[1], rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["1word", "odd"])
+def test_trial_space_setup_equals_helper_construction(name):
+    """host.trial_space (init_trial_wf) against the test helper's dense construction on the oracle's elements; the
+    connected space of the helper is restricted to the list it is given, so it gets the whole sector."""
+    s = _systems()[name]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000)
+    dets = helpers.all_dets(s)
+    sd = host.sing_doub_space(s)
+    trial_il = sd[:12]
+    trial = [[b + 1 for b in range(s.nbasis) if (int(row[0]) >> b) & 1] for row in trial_il]
+    ti, ta, ci, ca, e_t = helpers.build_trial_space(o, s, dets, trial)
+    hi, ha, hci, hca, he = host.trial_space(s, trial_il)
+    assert np.array_equal(ti, hi) and abs(e_t - he) < 1e-10
+    sgn = np.sign(np.dot(ta, ha))
+    assert np.allclose(ta, sgn * ha, atol=1e-9)
+    a = {tuple(r): v for r, v in zip(ci.tolist(), ca)}
+    b = {tuple(r): v for r, v in zip(hci.tolist(), sgn * hca)}
+    # determinants whose connected amplitude is zero only to rounding may be in one list and not the other
+    for k in set(a) | set(b):
+        assert abs(a.get(k, 0.0) - b.get(k, 0.0)) < 1e-9, k
+    assert len(set(a) & set(b)) > 50
+    # ham_apply itself: thread count does not matter
+    x = host.ham_apply(s, hci, hi, ha, threads=1)
+    y = host.ham_apply(s, hci, hi, ha, threads=5)
+    assert np.array_equal(x, y) and np.array_equal(x, hca)
