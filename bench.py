@@ -38,7 +38,12 @@ WORKLOADS = {
     # name: (n_spat, nel, tau, description)
     "n2_14e28o_pchb": (28, 14, 2.0e-5, "N2 cc-pVDZ-sized synthetic FCIDUMP 14e/28o, i-FCIQMC, PCHB (BASELINE configs[1])"),
     "cr2_24e30o_pchb": (30, 24, 1.0e-5, "Cr2-sized synthetic FCIDUMP 24e/30o, i-FCIQMC, PCHB (BASELINE configs[4])"),
+    "semistoch_20e40o_pchb": (40, 20, 4.0e-6, "semi-stochastic i-FCIQMC on a synthetic FCIDUMP 20e/40o, PCHB, real "
+                              "coefficients, core space = the --core-size determinants of the reference's singles and "
+                              "doubles with the largest first-order weight, trial wavefunction over the --trial "
+                              "largest of them (BASELINE configs[3])"),
 }
+SEMISTOCH = ("semistoch_20e40o_pchb",)
 
 
 def build_system(workload):
@@ -131,6 +136,64 @@ def random_walker_records(system, n_dets, seed, keep=None, keep_frac=1.0, chunk=
 
 
 # ---------------------------------------------------------------------------------------------
+# semi-stochastic set-up (BASELINE configs[3]): what init_semi_stochastic / init_trial_wf hand to the engine
+# ---------------------------------------------------------------------------------------------
+def semistoch_space(system, hii, params, nranks, core_size, n_trial):
+    """Core space = reference + the singles and doubles with the largest |H_0j| / (H_jj - H_00) ("all
+    singles+doubles truncated"), laid out rank-major as store_whole_core_space does; trial space = its n_trial
+    largest members.  Returns dict(iluts, sizes, displs, weights (signed first-order amplitudes), trial)."""
+    from neci_stable_b200 import host
+    sd = host.sing_doub_space(system)
+    ref = np.repeat(sd[:1], sd.shape[0], 0)
+    h0 = host.get_helement(system, ref, sd)
+    hd = host.get_helement(system, sd, sd)
+    amp = -h0 / np.maximum(hd - hd[0], 1e-9)
+    amp[0] = 1.0
+    a = np.abs(amp)
+    a[0] = np.inf                                           # the reference first
+    pick = np.argsort(-a, kind="stable")[:min(core_size, sd.shape[0])]
+    core, camp = sd[pick], amp[pick]
+    if nranks > 1:
+        _, nodes = host.det_node(params, core, system.nw)
+    else:
+        nodes = np.zeros(core.shape[0], dtype=np.int32)
+    il, sizes, displs = host.layout_core_space(core, nodes, nranks)
+    # amplitudes in the new order
+    key = {tuple(r): a for r, a in zip(core.tolist(), camp)}
+    w = np.array([key[tuple(r)] for r in il.tolist()])
+    trial = core[:n_trial].copy() if n_trial > 0 else None
+    return dict(iluts=il, sizes=sizes, displs=displs, weights=w, trial=trial)
+
+
+def semistoch_records(system, space, rank, l1_total):
+    """CurrentDets records of this rank's core determinants: deterministic + initiator flags, signs = first-order
+    amplitudes scaled so that the whole core space carries l1_total walkers (sum |sign| over all ranks)."""
+    from neci_stable_b200 import capi
+    lo, n = int(space["displs"][rank]), int(space["sizes"][rank])
+    nw = system.nw
+    rec = np.zeros((n, nw + 2), dtype=np.int64)
+    rec[:, :nw] = space["iluts"][lo:lo + n]
+    scale = l1_total / float(np.abs(space["weights"]).sum())
+    rec[:, nw] = (scale * space["weights"][lo:lo + n]).view(np.int64)
+    rec[:, nw + 1] = (1 << capi.FLAG_DETERMINISTIC) | (1 << capi.FLAG_INITIATOR)
+    return rec
+
+
+def semistoch_apply(engine, system, hii, space, rank):
+    """Builds this rank's rows of the sparse core Hamiltonian on the host threads and hands core and trial space
+    over through the C ABI.  Returns (nnz of this rank, seconds spent building)."""
+    from neci_stable_b200 import host
+    t0 = time.perf_counter()
+    c = host.core_hamiltonian(system, space["iluts"], hii, displ=int(space["displs"][rank]), n_local=int(space["sizes"][rank]))
+    dt = time.perf_counter() - t0
+    engine.set_core_space(c["row_ptr"], c["col"], c["val"], space["sizes"], space["displs"], space["iluts"])
+    if space["trial"] is not None:
+        ti, ta, ci, ca, _ = host.trial_space(system, space["trial"])
+        engine.set_trial_space(ti, ta, ci, ca)
+    return int(c["row_ptr"][-1]), dt
+
+
+# ---------------------------------------------------------------------------------------------
 # clocks sampling during the timed region (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -188,7 +251,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: oracle (restatement of the reference algorithm), ranks played by host threads
 # ---------------------------------------------------------------------------------------------
-def cpu_run(workload, n_dets_total, steps, warmup, cores, seed=5):
+def cpu_run(workload, n_dets_total, steps, warmup, cores, seed=5, core_size=0, n_trial=0):
     """Times `steps` iterations of the CPU restatement on `cores` threads (one NECI 'rank' per thread,
     determinants partitioned by DetermineDetNode, in-memory all-to-all).  Returns attempts/s etc."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -202,16 +265,30 @@ def cpu_run(workload, n_dets_total, steps, warmup, cores, seed=5):
     nr = max(1, cores)
     per = int(n_dets_total * 3 // nr + 1000)
     oracles = []
+    semi = workload in SEMISTOCH
+    per += core_size if semi else 0
     for r in range(nr):
-        params = host.make_params(system, hii, max_walkers=per, max_spawned=max(per, 200000), nranks=nr, rank=r, seed=11)
+        params = host.make_params(system, hii, max_walkers=per, max_spawned=max(per, 200000), nranks=nr, rank=r, seed=11,
+                                  semi_stochastic=semi, all_real_coeff=semi)
         o = helpers.Oracle(params)
         system.apply(o)
         oracles.append(o)
     rec = random_walker_records(system, n_dets_total, seed)
+    space = None
+    if semi:
+        space = semistoch_space(system, hii, params, nr, core_size, n_trial)
+        rec = rec[~host.rows_in(rec[:, :system.nw], space["iluts"])]
     _, node = oracles[0].probe_det_node(rec[:, :system.nw])
+    tot = tot_rand = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
     for r in range(nr):
-        oracles[r].upload_walkers(rec[node == r])
-    tot = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
+        mine = rec[node == r]
+        if semi:
+            crec = semistoch_records(system, space, r, l1_total=tot_rand)
+            tot += float(np.abs(crec[:, system.nw].view(np.float64)).sum())
+            mine = np.concatenate([crec, mine])
+        oracles[r].upload_walkers(mine)
+        if semi:
+            semistoch_apply(oracles[r], system, hii, space, r)
     sft = 0.0
     attempts = 0.0
     t_used = 0.0
@@ -245,6 +322,8 @@ def main():
     ap.add_argument("--cpu-sample-walkers", type=float, default=2.0e6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--core-size", type=int, default=100000, help="semi-stochastic workloads: determinants in the core space")
+    ap.add_argument("--trial", type=int, default=10, help="semi-stochastic workloads: determinants in the trial space (0 = none)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="spawn exchange for N > 1: push kernel over NVLink peer memory (default) or NCCL send/recv")
     args = ap.parse_args()
@@ -261,7 +340,7 @@ def main():
         if rank != 0:
             return 0
         n_dets = int(args.cpu_sample_walkers / 2.0)
-        r = cpu_run(args.workload, n_dets, args.steps, args.warmup, cores)
+        r = cpu_run(args.workload, n_dets, args.steps, args.warmup, cores, core_size=args.core_size, n_trial=args.trial)
         sample = "%d iterations of a %.3g-walker (%d determinants) list of the same system and distribution" % (
             args.steps, r["walkers"], n_dets)
         line = {
@@ -299,8 +378,15 @@ def main():
     n_dets = int(args.walkers / 2.0)                       # mean |sign| of round(1 + Exp(1)) is ~2.0
     max_walkers = int(3 * n_dets + 100000)
     max_spawned = int(max(2 * args.walkers, 400000))
+    semi = args.workload in SEMISTOCH
+    if semi:
+        # real coefficients (readinput.F90:569 makes them mandatory with a core space): a third of the attempts leave a
+        # spawn of RealSpawnCutoff walkers on a new determinant, so the list of this far-from-equilibrium start grows
+        # by ~0.2 n_dets per iteration
+        max_walkers = int(16 * n_dets + args.core_size + 100000)
+        max_spawned *= 2
     params = host.make_params(system, hii, max_walkers=max_walkers, max_spawned=max_spawned, nranks=world, rank=rank,
-                              device=local_rank, seed=11, blocks_per_rank=1)
+                              device=local_rank, seed=11, blocks_per_rank=1, semi_stochastic=semi, all_real_coeff=semi)
     eng = capi.Engine(params)
     system.apply(eng)
     if world > 1:
@@ -318,7 +404,21 @@ def main():
             _, node = eng.probe_det_node(il)
             return node == rank
     rec = random_walker_records(system, n_dets, seed=1000 + rank, keep=keep, keep_frac=1.0 / world)
+    core_info = None
+    if semi:
+        # the core determinants join the list with their flags; the sparse core Hamiltonian (this rank's rows) and
+        # the trial / connected spaces are built by the host library, as the Fortran host would, before the loop
+        space = semistoch_space(system, hii, params, world, args.core_size, args.trial)
+        rec = rec[~host.rows_in(rec[:, :system.nw], space["iluts"])]
+        tot_rand = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
+        # half of the population sits in the core space, as in a converged semi-stochastic run
+        rec = np.concatenate([semistoch_records(system, space, rank, l1_total=tot_rand * world), rec])
     eng.upload_walkers(rec)
+    if semi:
+        nnz, t_build = semistoch_apply(eng, system, hii, space, rank)
+        core_info = {"core_size": int(space["iluts"].shape[0]), "core_local": int(space["sizes"][rank]), "nnz_local": nnz,
+                     "trial_size": 0 if space["trial"] is None else int(space["trial"].shape[0]),
+                     "host_build_s": t_build}
     tot0 = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
 
     def allsum(x):
@@ -357,7 +457,7 @@ def main():
     if rank == 0:
         sampler.start()
     acc = np.zeros(capi.ST_COUNT)
-    t_spawn = t_ann = t_comm = 0.0
+    t_spawn = t_ann = t_comm = t_det = 0.0
     bytes_spawn = 0.0
     launches0 = eng.launch_count()
     barrier()
@@ -368,6 +468,7 @@ def main():
         st = eng.iterate(tau, sft, it)
         acc += st
         t_spawn += st[ST["TIME_SPAWN_MS"]]; t_ann += st[ST["TIME_ANNIHIL_MS"]]; t_comm += st[ST["TIME_COMM_MS"]]
+        t_det += st[ST["TIME_DETERM_MS"]]
         # algorithmic bytes of the spawn/death kernel (DESIGN.md "K1"): SoA record (8*nw + 8 sign + 4 flags) and diagH per
         # slot, offdiagH per occupied slot, sign+flag write-back per occupied slot, one AoS record per spawn
         n_slot = st[ST["TOTWALKERS"]]; n_occ = n_slot - st[ST["HOLESINLIST"]]
@@ -415,11 +516,31 @@ def main():
                 "phase_ms_per_step": {"spawn_death": t_spawn / args.steps, "exchange": t_comm / args.steps,
                                       "annihilation": t_ann / args.steps}}
     roofline.update(ncu_extra)
+    if semi:
+        # K3 determ_projection: 12 bytes per non-zero (fp64 value + int32 column), the local
+        # slices of the in/out vectors and one read of the gathered vector; its time is the device span from the
+        # start of the iteration to the start of the spawning kernel (core gather + SpMV + trial-energy pass)
+        b3 = 12.0 * core_info["nnz_local"] + 16.0 * core_info["core_local"] + 8.0 * core_info["core_size"]
+        ach3 = b3 / (t_det / args.steps * 1e-3) / 1e9 if t_det > 0 else 0.0
+        k3 = {"bound": "hbm", "kernel": "k_determ_spmv", "achieved": ach3, "peak": peak, "unit": "GB/s", "frac": ach3 / peak,
+              "traffic": None, "algorithmic_bytes_per_launch": b3, "ms_per_launch": t_det / args.steps}
+        roofline["phase_ms_per_step"]["determ_projection"] = t_det / args.steps
+        k1 = {k: roofline[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic",
+                                       "algorithmic_bytes_per_launch", "ms_per_launch")}
+        roofline["kernels"] = {"k_spawn": k1, "k_determ_spmv": k3}
+        if t_det > t_spawn:                                   # the dominant kernel heads the object
+            roofline.update(k3)
 
     # ---- end to end through the C ABI with HOST buffers: CurrentDets + gdata in pinned host memory, uploaded, iterated
     #      and downloaded inside the timed region (neci_gpu_iterate_host)
     e2e = None
-    if not args.no_e2e:
+    if semi:
+        # the host-buffer path re-uploads the list every iteration, which would also re-locate the core space; for
+        # this workload only the resident API (the deployment path) is timed end to end
+        e2e = {"value": attempts / wall, "unit": UNIT, "h2d_bytes_per_step": 24, "d2h_bytes_per_step": 8 * capi.ST_COUNT + 128,
+               "api": "neci_gpu_iterate: list, core Hamiltonian and trial tables resident in HBM; host passes tau/shift/iter "
+                      "and reads the statistics vector every iteration (wall clock over the same K steps)"}
+    elif not args.no_e2e:
         W = system.W
         dets_h = eng.alloc_host((max_walkers, W), np.int64)
         gd_h = eng.alloc_host((max_walkers,), np.float64)
@@ -456,7 +577,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         nd = int(args.cpu_sample_walkers / 2.0)
-        r = cpu_run(args.workload, nd, 6, 3, cores)
+        r = cpu_run(args.workload, nd, 6, 3, cores, core_size=args.core_size, n_trial=args.trial)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": "6 iterations of a %.3g-walker (%d determinants) list of the same system and distribution, "
                          "ranks = host threads" % (r["walkers"], nd), "ms_per_step": r["ms_per_step"]}
@@ -472,7 +593,7 @@ def main():
                        "spawned_per_step": spawned / args.steps, "partition": "DetermineDetNode hash" if world > 1 else "single rank",
                        "exchange": ("push kernel over NVLink peer memory" if args.exchange == "p2p" else "NCCL send/recv") if world > 1 else "none",
                        "l2": "inputs larger than L2 (walker list %.0f MB per GPU > 126 MB)" % (dets_end / world * (8 * system.nw + 28) / 1e6),
-                       "wall_ms_per_step": 1e3 * wall / args.steps},
+                       "wall_ms_per_step": 1e3 * wall / args.steps, **({"semi_stochastic": core_info} if semi else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -439,13 +439,13 @@ def trial_space(system, trial_iluts):
     psi = v[:, 0].copy()
     con = np.concatenate([sing_doub_space(system, ref_ilut=ti[k])[1:] for k in range(nt)])
     con = np.unique(np.concatenate([ti, con]), axis=0)
-    con = np.ascontiguousarray(con[~_rows_in(con, ti)])            # without the trial determinants themselves
+    con = np.ascontiguousarray(con[~rows_in(con, ti)])            # without the trial determinants themselves
     amps = ham_apply(system, con, ti, psi)
     keep = np.abs(amps) > 0
     return ti, psi, np.ascontiguousarray(con[keep]), amps[keep], float(w[0])
 
 
-def _rows_in(a, b):
+def rows_in(a, b):
     """Boolean mask: which rows of a occur in b (both n x nw int64)."""
     av = np.ascontiguousarray(a).view([("", a.dtype)] * a.shape[1]).ravel()
     bv = np.ascontiguousarray(b).view([("", b.dtype)] * b.shape[1]).ravel()

@@ -187,3 +187,73 @@ def test_trial_space_setup_equals_helper_construction(name):
     x = host.ham_apply(s, hci, hi, ha, threads=1)
     y = host.ham_apply(s, hci, hi, ha, threads=5)
     assert np.array_equal(x, y) and np.array_equal(x, hca)
+
+
+def test_bench_semistoch_setup_runs_on_the_oracle():
+    """bench.py's semi-stochastic workload set-up (two-word determinants, leading singles+doubles as core space,
+    trial space of its largest members) through the oracle: the deterministic projection with the host-built rows
+    equals the dense mat-vec over the core space, and the trial estimator sums equal sum_i con_i v_i and
+    sum_i psiT_i v_i evaluated directly."""
+    import bench
+    s = host.random_fcidump_system(40, 20, sparse=0.9, sparse_t=0.9, seed=6)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, params = helpers.make_pair(s, hii, max_walkers=50000, max_spawned=50000, semi_stochastic=True, all_real_coeff=True,
+                                  death_before_comms=True)
+    space = bench.semistoch_space(s, hii, params, 1, 1500, 4)
+    il = space["iluts"]
+    assert il.shape == (1500, 2) and np.array_equal(space["trial"][0], s.ilut(s.ref_orbs))
+    rec = bench.semistoch_records(s, space, 0, l1_total=5000.0)
+    v = rec[:, s.nw].view(np.float64).copy()
+    assert abs(np.abs(v).sum() - 5000.0) < 1e-9
+    o.upload_walkers(rec)
+    nnz, _ = bench.semistoch_apply(o, s, hii, space, 0)
+    n = il.shape[0]
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    H = host.get_helement(s, il[I], il[J]).reshape(n, n)
+    assert nnz == np.count_nonzero(H)
+    tau, S = 1e-5, 0.3
+    st = o.iterate(tau, S, 1)
+    # trial estimator on the signs the walker loop saw: every trial determinant is a core determinant here
+    ti, ta, ci, ca, e_t = host.trial_space(s, space["trial"])
+    idx = {tuple(r): k for k, r in enumerate(il.tolist())}
+    denom = sum(a * v[idx[tuple(r)]] for r, a in zip(ti.tolist(), ta))
+    numer = sum(a * v[idx[tuple(r)]] for r, a in zip(ci.tolist(), ca) if tuple(r) in idx)
+    # (the trial determinants' own share is E_T * denom, added by the caller: fcimc_helper.F90:600-613)
+    assert np.isclose(st[ST["TRIAL_DENOM"]], denom, rtol=1e-11)
+    assert np.isclose(st[ST["TRIAL_NUMERATOR"]], numer, rtol=1e-10)
+    # one step of the projection: v <- v - tau (H - Hii - S) v on the core space; stochastic spawns onto core
+    # determinants are cancelled, those leaving the core space do not touch it
+    d, _, _ = o.download_walkers()
+    got = {tuple(r[:2]): x for r, x in zip(d.tolist(), host.signs_of(d, s.nw))}
+    Hs = H - hii * np.eye(n)
+    want = v - tau * (Hs @ v - S * v)
+    have = np.array([got[tuple(r)] for r in il.tolist()])
+    assert np.allclose(have, want, rtol=1e-11, atol=1e-11)
+
+
+def test_bench_semistoch_setup_split_over_ranks_matches_single_rank():
+    """The same workload set-up hashed over three ranks with DetermineDetNode (rank-major core order, each rank
+    building only its rows): after several iterations the union of the ranks' lists equals the single-rank list
+    (the iteration is a function of the walker set)."""
+    import bench
+    s = host.random_fcidump_system(9, 6, sparse=1.0, sparse_t=1.0, seed=4)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    results = {}
+    for nr in (1, 3):
+        orcs = []
+        for r in range(nr):
+            o, params = helpers.make_pair(s, hii, max_walkers=40000, max_spawned=40000, nranks=nr, rank=r,
+                                          semi_stochastic=True, all_real_coeff=True, seed=3)
+            orcs.append(o)
+        space = bench.semistoch_space(s, hii, params, nr, 400, 0)
+        assert int(space["sizes"].sum()) == 400 and (nr == 1 or np.all(space["sizes"] > 0))
+        for r in range(nr):
+            orcs[r].upload_walkers(bench.semistoch_records(s, space, r, l1_total=3000.0))
+            bench.semistoch_apply(orcs[r], s, hii, space, r)
+        for it in range(1, 8):
+            st = helpers.world_iterate(orcs, 2e-4, 0.1, it, nthreads=1)
+        assert st[:, ST["NSPAWNED_SENT"]].sum() > 0
+        d = np.concatenate([o.download_walkers()[0] for o in orcs])
+        results[nr] = helpers.canon(d, nw=s.nw)
+    assert np.array_equal(results[1][0], results[3][0]) and np.array_equal(results[1][2], results[3][2])
+    assert np.allclose(results[1][1], results[3][1], rtol=1e-12, atol=1e-12)
