@@ -324,6 +324,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--core-size", type=int, default=100000, help="semi-stochastic workloads: determinants in the core space")
     ap.add_argument("--trial", type=int, default=10, help="semi-stochastic workloads: determinants in the trial space (0 = none)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --walkers per GPU (default, the driver's scaling run); strong: --walkers in total, "
+                         "split over the GPUs (BASELINE configs[4])")
+    ap.add_argument("--load-balance", action="store_true",
+                    help="100 balancing blocks per rank (load-balance-blocks) and one adjust_load_balance pass "
+                         "(block populations -> greedy plan -> device-to-device block moves) during warm-up")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="spawn exchange for N > 1: push kernel over NVLink peer memory (default) or NCCL send/recv")
     args = ap.parse_args()
@@ -375,6 +381,8 @@ def main():
 
     system, tau = build_system(args.workload)
     hii = driver.diag_energy(system, system.ref_orbs)
+    if args.scaling == "strong":
+        args.walkers = args.walkers / world                # total fixed: each GPU holds its 1/N share
     n_dets = int(args.walkers / 2.0)                       # mean |sign| of round(1 + Exp(1)) is ~2.0
     max_walkers = int(3 * n_dets + 100000)
     max_spawned = int(max(2 * args.walkers, 400000))
@@ -386,7 +394,8 @@ def main():
         max_walkers = int(16 * n_dets + args.core_size + 100000)
         max_spawned *= 2
     params = host.make_params(system, hii, max_walkers=max_walkers, max_spawned=max_spawned, nranks=world, rank=rank,
-                              device=local_rank, seed=11, blocks_per_rank=1, semi_stochastic=semi, all_real_coeff=semi)
+                              device=local_rank, seed=11, blocks_per_rank=100 if args.load_balance else 1,
+                              semi_stochastic=semi, all_real_coeff=semi)
     eng = capi.Engine(params)
     system.apply(eng)
     if world > 1:
@@ -444,6 +453,7 @@ def main():
     sft = 0.0
     tot = allsum(tot0)
     it = 0
+    lb_moves = None
     for _ in range(args.warmup):
         it += 1
         st = eng.iterate(tau, sft, it)
@@ -451,6 +461,16 @@ def main():
         if new > 0 and tot > 0:
             sft -= 0.5 * np.log(new / tot) / tau
         tot = new
+        if args.load_balance and world > 1 and not semi and it == 2:
+            # adjust_load_balance (src/load_balancer.fpp:178-351): block populations summed over the ranks, the greedy
+            # plan (identical on every rank), then the block moves through the spawn exchange.  Not with a core
+            # space: the reference switches balancing off then (load_balancer.fpp:198-201)
+            allp = [None] * world
+            dist.all_gather_object(allp, eng.block_populations())
+            new_map, moves = driver.plan_load_balance(np.sum(allp, axis=0), params["load_balance_mapping"], world)
+            eng.rebalance(new_map)
+            params["load_balance_mapping"] = np.asarray(new_map, dtype=np.int32)
+            lb_moves = len(moves)
 
     # ---- timed region: K iterations, list resident in HBM
     sampler = ClockSampler(local_rank)
@@ -585,7 +605,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "walkers_per_gpu": args.walkers,
                        "walkers_total_end": walkers_end, "determinants_total_end": dets_end, "tau": tau, "shift": sft,
@@ -593,7 +613,8 @@ def main():
                        "spawned_per_step": spawned / args.steps, "partition": "DetermineDetNode hash" if world > 1 else "single rank",
                        "exchange": ("push kernel over NVLink peer memory" if args.exchange == "p2p" else "NCCL send/recv") if world > 1 else "none",
                        "l2": "inputs larger than L2 (walker list %.0f MB per GPU > 126 MB)" % (dets_end / world * (8 * system.nw + 28) / 1e6),
-                       "wall_ms_per_step": 1e3 * wall / args.steps, **({"semi_stochastic": core_info} if semi else {})},
+                       "wall_ms_per_step": 1e3 * wall / args.steps, **({"semi_stochastic": core_info} if semi else {}),
+                       **({"load_balance": {"blocks_per_rank": 100, "blocks_moved_in_warmup": lb_moves}} if args.load_balance else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
