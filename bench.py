@@ -179,14 +179,20 @@ def semistoch_records(system, space, rank, l1_total):
     return rec
 
 
-def semistoch_apply(engine, system, hii, space, rank):
-    """Builds this rank's rows of the sparse core Hamiltonian on the host threads and hands core and trial space
-    over through the C ABI.  Returns (nnz of this rank, seconds spent building)."""
+def semistoch_apply(engine, system, hii, space, rank, build="host"):
+    """Hands core and trial space over through the C ABI.  build = "host": this rank's rows of the sparse core
+    Hamiltonian come from the host library's threads (neci_gpu_set_core_space); "device": the engine builds them
+    itself (neci_gpu_build_core_space).  Returns (nnz of this rank, seconds spent building)."""
     from neci_stable_b200 import host
     t0 = time.perf_counter()
-    c = host.core_hamiltonian(system, space["iluts"], hii, displ=int(space["displs"][rank]), n_local=int(space["sizes"][rank]))
-    dt = time.perf_counter() - t0
-    engine.set_core_space(c["row_ptr"], c["col"], c["val"], space["sizes"], space["displs"], space["iluts"])
+    if build == "device":
+        nnz = engine.build_core_space(space["sizes"], space["displs"], space["iluts"])
+        dt = time.perf_counter() - t0
+        c = {"row_ptr": [nnz]}
+    else:
+        c = host.core_hamiltonian(system, space["iluts"], hii, displ=int(space["displs"][rank]), n_local=int(space["sizes"][rank]))
+        dt = time.perf_counter() - t0
+        engine.set_core_space(c["row_ptr"], c["col"], c["val"], space["sizes"], space["displs"], space["iluts"])
     if space["trial"] is not None:
         ti, ta, ci, ca, _ = host.trial_space(system, space["trial"])
         engine.set_trial_space(ti, ta, ci, ca)
@@ -323,6 +329,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--core-size", type=int, default=100000, help="semi-stochastic workloads: determinants in the core space")
+    ap.add_argument("--core-build", default="host", choices=["host", "device"],
+                    help="semi-stochastic workloads: who builds the sparse core Hamiltonian")
     ap.add_argument("--trial", type=int, default=10, help="semi-stochastic workloads: determinants in the trial space (0 = none)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --walkers per GPU (default, the driver's scaling run); strong: --walkers in total, "
@@ -424,10 +432,10 @@ def main():
         rec = np.concatenate([semistoch_records(system, space, rank, l1_total=tot_rand * world), rec])
     eng.upload_walkers(rec)
     if semi:
-        nnz, t_build = semistoch_apply(eng, system, hii, space, rank)
-        core_info = {"core_size": int(space["iluts"].shape[0]), "core_local": int(space["sizes"][rank]), "nnz_local": nnz,
+        nnz, t_build = semistoch_apply(eng, system, hii, space, rank, build=args.core_build)
+        core_info = {"core_build": args.core_build,"core_size": int(space["iluts"].shape[0]), "core_local": int(space["sizes"][rank]), "nnz_local": nnz,
                      "trial_size": 0 if space["trial"] is None else int(space["trial"].shape[0]),
-                     "host_build_s": t_build}
+                     "build_s": t_build}
     tot0 = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
 
     def allsum(x):

@@ -215,6 +215,20 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
                             const int32_t *sizes, const int32_t *displs,
                             const int64_t *core_iluts);
 
+/* The same hand-over with the sparse core Hamiltonian built ON THE DEVICE instead of by the host: replaces
+ * calc_determ_hamil_sparse / calc_determ_hamil_opt (src/sparse_arrays.F90:426-572,
+ * src/fast_determ_hamil.F90:892-1548) for this rank's rows.  sizes / displs / core_iluts as in
+ * neci_gpu_set_core_space (the whole core space, rank-major, nifd+1 words per determinant); every row holds its
+ * non-zero off-diagonal elements in ascending column order and H_ii - Hii as its last entry; Hii is
+ * neci_gpu_config.hii.  The rows never cross the host link.  *nnz_out = number of stored elements of this rank.
+ * The walker list must already hold this rank's core determinants (neci_gpu_upload_walkers).               */
+int neci_gpu_build_core_space(neci_gpu_engine *e, const int32_t *sizes, const int32_t *displs,
+                              const int64_t *core_iluts, int64_t *nnz_out);
+
+/* Copies this rank's sparse core Hamiltonian out (write_core_space-style dumps, tests): row_ptr[n_local + 1],
+ * then col / val with row_ptr[n_local] entries each (either may be NULL to fetch the row offsets only).     */
+int neci_gpu_get_core_hamiltonian(neci_gpu_engine *e, int64_t *row_ptr, int32_t *col, double *val);
+
 /* Trial-wavefunction estimator (init_trial_wf, src/trial_wf_gen.F90): the trial space with the trial vector
  * (trial_space / trial_wfs) and the connected space with con_space_vecs = sum_j H_ij psiT_j, i.e. the contents of
  * the two hash tables trial_ht / con_ht that hash_search_trial reads (src/searching.F90:182-223; ntrial_excits = 1).

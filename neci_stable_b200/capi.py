@@ -164,6 +164,22 @@ class Engine:
                                                 _p(vl, C.c_double), _p(sz, C.c_int32), _p(dp, C.c_int32),
                                                 _p(ci, C.c_int64)), "set_core_space")
 
+    def build_core_space(self, sizes, displs, core_iluts):
+        """Core space with the sparse core Hamiltonian built on the device; returns this rank's nnz."""
+        sz, dp, ci = _i32(sizes), _i32(displs), _i64(core_iluts)
+        nnz = C.c_int64(0)
+        self._check(self._fn("build_core_space")(self.h, _p(sz, C.c_int32), _p(dp, C.c_int32), _p(ci, C.c_int64),
+                                                  C.byref(nnz)), "build_core_space")
+        return int(nnz.value)
+
+    def get_core_hamiltonian(self, n_local):
+        rp = np.zeros(n_local + 1, dtype=np.int64)
+        self._check(self._fn("get_core_hamiltonian")(self.h, _p(rp, C.c_int64), None, None), "get_core_hamiltonian")
+        col = np.zeros(int(rp[-1]), dtype=np.int32); val = np.zeros(int(rp[-1]))
+        self._check(self._fn("get_core_hamiltonian")(self.h, _p(rp, C.c_int64), _p(col, C.c_int32), _p(val, C.c_double)),
+                    "get_core_hamiltonian")
+        return dict(row_ptr=rp, col=col, val=val)
+
     def set_trial_space(self, trial_iluts, trial_amps, con_iluts, con_amps):
         ti, ta = _i64(trial_iluts).reshape(-1, self.nw), _f64(trial_amps)
         ci, ca = _i64(con_iluts).reshape(-1, self.nw), _f64(con_amps)

@@ -528,6 +528,50 @@ __global__ void k_core_locate(Params P, WalkerList L, const long long *iluts, lo
     }
 }
 
+// Sparse core Hamiltonian on the device (calc_determ_hamil_sparse, src/sparse_arrays.F90:426-572; row contents as
+// calc_determ_hamil_opt leaves them, src/fast_determ_hamil.F90:1421-1507): one warp per local row, the lanes sweep
+// the replicated core space 32 determinants at a time (coalesced), a popcount test drops everything more than a
+// double excitation away, the survivors get their matrix element, and a ballot keeps the row in ascending column
+// order.  FILL = false counts the non-zero elements of every row (+1 for the diagonal), FILL = true writes them at
+// row_ptr[i] and closes the row with H_ii - Hii (also stored in core_ham_diag).
+template <int NW, int SYS, bool FILL>
+__global__ void __launch_bounds__(NG_BLOCK) k_core_ham(Params P, const long long *iluts, long long n_core, long long displ,
+                                                       long long n_local, double hii, long long *row_ptr, int *col,
+                                                       double *val, double *core_ham_diag) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < n_local; i += nwarps) {
+        const long long gi = displ + i;
+        Det<NW> I; I.w[0] = (u64)iluts[gi * NW]; if (NW > 1) I.w[NW - 1] = (u64)iluts[gi * NW + NW - 1];
+        long long pos = FILL ? row_ptr[i] : 0;
+        for (long long j0 = 0; j0 < n_core; j0 += 32) {
+            const long long j = j0 + lane;
+            double h = 0.0;
+            if (j < n_core && j != gi) {
+                Det<NW> J; J.w[0] = (u64)iluts[j * NW]; if (NW > 1) J.w[NW - 1] = (u64)iluts[j * NW + NW - 1];
+                if (sys_hphf(SYS)) h = hphf_off_diag<NW, SYS>(P, I, J);     // partner determinants: no cheap prefilter
+                else {
+                    int x = __popcll(I.w[0] ^ J.w[0]); if (NW > 1) x += __popcll(I.w[NW - 1] ^ J.w[NW - 1]);
+                    if (x <= 4) h = helement<NW, SYS>(P, I, J);
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, h != 0.0);
+            if (FILL && h != 0.0) {
+                const long long k = pos + __popc(m & ((1u << lane) - 1u));
+                col[k] = (int)j; val[k] = h;
+            }
+            pos += __popc(m);
+        }
+        if (lane == 0) {
+            if (FILL) {
+                const double d = diagonal_matel<NW, SYS>(P, I) - hii;
+                col[pos] = (int)gi; val[pos] = d; core_ham_diag[i] = d;
+            } else row_ptr[i] = pos + 1;
+        }
+    }
+}
+
 // ---- trial wavefunction -----------------------------------------------------------------
 template <int NW>
 __global__ void k_trial_ht_build(const long long *iluts, long long n, int *ht, u64 mask) {

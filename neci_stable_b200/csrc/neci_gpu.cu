@@ -486,24 +486,18 @@ int neci_gpu_download_occupied(neci_gpu_engine *e, double min_weight, int64_t *d
 }
 
 // -------------------------------------------------------------------------------
-int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *row_ptr, const int32_t *col,
-                            const double *val, const int32_t *sizes, const int32_t *displs, const int64_t *core_iluts) {
-    CK(cudaSetDevice(e->cfg.device));
-    e->n_core_local = n_local;
+// Shared part of the two ways a core space arrives (neci_gpu_set_core_space: rows built by the host;
+// neci_gpu_build_core_space: rows built here): sizes/displacements, the replicated core determinants with their hash
+// table, the vectors of determ_projection and the slots of this rank's core determinants in the walker list.
+static int core_space_layout(neci_gpu_engine *e, const int32_t *sizes, const int32_t *displs) {
     e->core_sizes.assign(sizes, sizes + e->cfg.nranks); e->core_displs.assign(displs, displs + e->cfg.nranks);
     e->n_core_total = 0; for (int r = 0; r < e->cfg.nranks; ++r) e->n_core_total += sizes[r];
+    e->n_core_local = sizes[e->cfg.rank];
     e->core_displ = displs[e->cfg.rank];
-    const long long nnz = row_ptr[n_local];
-    e->d_row_ptr = e->upload((const long long *)row_ptr, (size_t)n_local + 1);
-    e->d_col = e->upload(col, (size_t)nnz); e->d_val = e->upload(val, (size_t)nnz);
-    {
-        // core_ham_diag (fast_determ_hamil.F90:1494-1507): the diagonal entry of every local row
-        std::vector<double> diag((size_t)n_local, 0.0);
-        for (int64_t i = 0; i < n_local; ++i)
-            for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
-                if (col[k] == i + displs[e->cfg.rank]) diag[i] = val[k];
-        e->d_core_diag = e->upload(diag.data(), diag.size());
-    }
+    return 0;
+}
+static int core_space_tables(neci_gpu_engine *e, const int64_t *core_iluts) {
+    const int64_t n_local = e->n_core_local;
     e->d_core_slots = e->alloc<int>((size_t)n_local);
     e->d_vpart = e->alloc<double>((size_t)n_local); e->d_vout = e->alloc<double>((size_t)n_local);
     e->d_vfull = e->alloc<double>((size_t)e->n_core_total);
@@ -531,6 +525,72 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
     CK(cudaMemcpyAsync(&errf, &e->L.ctr[C_ERR], 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (errf & 64) return e->fail("core determinant missing from the uploaded walker list");
+    return 0;
+}
+int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *row_ptr, const int32_t *col,
+                            const double *val, const int32_t *sizes, const int32_t *displs, const int64_t *core_iluts) {
+    CK(cudaSetDevice(e->cfg.device));
+    core_space_layout(e, sizes, displs);
+    if (n_local != e->n_core_local) return e->fail("set_core_space: n_local = %lld but sizes[rank] = %lld", (long long)n_local, (long long)e->n_core_local);
+    const long long nnz = row_ptr[n_local];
+    e->d_row_ptr = e->upload((const long long *)row_ptr, (size_t)n_local + 1);
+    e->d_col = e->upload(col, (size_t)nnz); e->d_val = e->upload(val, (size_t)nnz);
+    {
+        // core_ham_diag (fast_determ_hamil.F90:1494-1507): the diagonal entry of every local row
+        std::vector<double> diag((size_t)n_local, 0.0);
+        for (int64_t i = 0; i < n_local; ++i)
+            for (int64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
+                if (col[k] == i + displs[e->cfg.rank]) diag[i] = val[k];
+        e->d_core_diag = e->upload(diag.data(), diag.size());
+    }
+    return core_space_tables(e, core_iluts);
+}
+
+int neci_gpu_build_core_space(neci_gpu_engine *e, const int32_t *sizes, const int32_t *displs, const int64_t *core_iluts,
+                              int64_t *nnz_out) {
+    CK(cudaSetDevice(e->cfg.device));
+    core_space_layout(e, sizes, displs);
+    if (e->n_core_total >= (1ll << 31)) return e->fail("build_core_space: core space too large for int32 columns");
+    if (core_space_tables(e, core_iluts)) return 1;
+    const long long n_local = e->n_core_local, n_core = e->n_core_total;
+    e->d_row_ptr = e->alloc<long long>((size_t)n_local + 1);
+    e->d_core_diag = e->alloc<double>((size_t)n_local);
+    if (!e->d_row_ptr || !e->d_core_diag) return e->fail("build_core_space: allocation failed");
+    const long long *d_il = e->P.core_iluts;
+    const double hii = e->cfg.hii;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, (n_local * 32 + NG_BLOCK - 1) / NG_BLOCK));
+    // pass 1: row lengths; the prefix sum over n_local numbers is taken on the host (set-up code, 8 bytes per row)
+    NG_DISPATCH(e, (k_core_ham<NW, SYS, false><<<grid, NG_BLOCK, 0, e->stream>>>(e->P, d_il, n_core, e->core_displ, n_local, hii,
+                                                                                e->d_row_ptr, nullptr, nullptr, nullptr)));
+    CK(cudaGetLastError());
+    std::vector<long long> rp((size_t)n_local + 1, 0);
+    CK(cudaMemcpyAsync(rp.data(), e->d_row_ptr, (size_t)n_local * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    long long run = 0;
+    for (long long i = 0; i < n_local; ++i) { const long long len = rp[i]; rp[i] = run; run += len; }
+    rp[n_local] = run;
+    CK(cudaMemcpyAsync(e->d_row_ptr, rp.data(), (size_t)(n_local + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    e->d_col = e->alloc<int>((size_t)run); e->d_val = e->alloc<double>((size_t)run);
+    if (!e->d_col || !e->d_val) return e->fail("build_core_space: no memory for %lld non-zero elements", run);
+    // pass 2: the elements again, written in place
+    NG_DISPATCH(e, (k_core_ham<NW, SYS, true><<<grid, NG_BLOCK, 0, e->stream>>>(e->P, d_il, n_core, e->core_displ, n_local, hii,
+                                                                               e->d_row_ptr, e->d_col, e->d_val, e->d_core_diag)));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    e->n_launch += 2;
+    if (nnz_out) *nnz_out = run;
+    return 0;
+}
+
+int neci_gpu_get_core_hamiltonian(neci_gpu_engine *e, int64_t *row_ptr, int32_t *col, double *val) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->d_row_ptr) return e->fail("get_core_hamiltonian: no core space set");
+    const long long n_local = e->n_core_local;
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(row_ptr, e->d_row_ptr, (size_t)(n_local + 1) * 8, cudaMemcpyDeviceToHost));
+    const long long nnz = row_ptr[n_local];
+    if (col) CK(cudaMemcpy(col, e->d_col, (size_t)nnz * 4, cudaMemcpyDeviceToHost));
+    if (val) CK(cudaMemcpy(val, e->d_val, (size_t)nnz * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 
