@@ -29,7 +29,7 @@ def _nvcc():
 
 
 def build_gpu(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("neci_gpu.cu", "kernels.cuh", "device_system.cuh", "device_common.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("neci_gpu.cu", "kernels.cuh", "spawn_kernel.cuh", "device_system.cuh", "device_common.cuh")]
     srcs.append(os.path.join(ROOT, "include", "neci_gpu.h"))
     if not force and not _newer(GPU_LIB, srcs):
         return GPU_LIB
@@ -40,6 +40,19 @@ def build_gpu(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)
     return GPU_LIB
+
+
+def build_gpu_variant(tag, defines, verbose=False):
+    """A tuning variant of the engine beside the shipped one: libneci_gpu_<tag>.so compiled with extra -D macros
+    (K1_BLOCK, K1_CTAS_PER_SM, K1_SPT ...).  Select it at run time with NECI_GPU_LIB=<path> (capi.GPU_LIB).
+    Used by profiles/tools/round2_first_call.sh to compare launch configurations in one GPU call."""
+    out = os.path.join(HERE, "libneci_gpu_%s.so" % tag)
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+           "-shared", "-Xcompiler", "-fPIC"] + ["-D%s" % d for d in defines] + ["-o", out, os.path.join(CSRC, "neci_gpu.cu"), "-ldl"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return out
 
 
 def build_host(force=False):

@@ -79,7 +79,8 @@ class Engine:
 
     def __init__(self, params, lib_path=None, prefix="neci_gpu_"):
         """params: dict with the Config fields (arrays as numpy)."""
-        lib_path = lib_path or GPU_LIB
+        # NECI_GPU_LIB selects a tuning variant of the CUDA library (_build.build_gpu_variant); never a CPU library
+        lib_path = lib_path or os.environ.get("NECI_GPU_LIB") or GPU_LIB
         if not os.path.exists(lib_path):
             raise EngineError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(the engine has no CPU fallback)" % lib_path)

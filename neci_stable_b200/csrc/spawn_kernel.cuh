@@ -33,9 +33,13 @@ namespace ng {
 #ifndef K1_BLOCK
 #define K1_BLOCK 256         /* block size of the spawning kernel (measured: 128 -> 0.87 ms, 256 -> 0.78 ms, 512 -> 0.80 ms per launch) */
 #endif
+#ifndef K1_CTAS_PER_SM       /* launch bound: resident CTAs per SM the register allocation must allow (variant builds: _build.build_gpu_variant) */
 #define K1_CTAS_PER_SM (1024 / K1_BLOCK)
+#endif
 #define NG_HEAVY 4096        /* attempts per determinant handled inside a tile */
+#ifndef K1_SPT
 #define K1_SPT 2             /* slots per thread and tile */
+#endif
 #define K1_TILE (K1_BLOCK * K1_SPT)
 #define K1_QCAP (2 * K1_BLOCK)
 #define K1_MAPW 1024         /* attempts per window of the attempt -> parent map */
