@@ -209,7 +209,8 @@ int neci_gpu_set_system_hubbard_k(neci_gpu_engine *e, int32_t n_k, const int32_t
  * rank r owns entries [displs[r], displs[r] + sizes[r]) -- the reference keeps
  * the whole core space on every rank too (core_space + its hash table,
  * src/core_space_util.F90:20-90) because is_core_state (src/semi_stoch_procs.F90:547)
- * must recognise core determinants owned by other ranks.                       */
+ * must recognise core determinants owned by other ranks.  n_local must equal
+ * sizes[rank] (anything else is an error).                                     */
 int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *row_ptr,
                             const int32_t *col, const double *val,
                             const int32_t *sizes, const int32_t *displs,
