@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N_ITER = 30
 
 
-def _worker(rank, world, port, out_dir, name, semi, balance=False, p2p=False):
+def _worker(rank, world, port, out_dir, name, semi, balance=False, p2p=False, devbuild=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -72,7 +72,11 @@ def _worker(rank, world, port, out_dir, name, semi, balance=False, p2p=False):
         my = np.array(mine + rest).reshape(-1, system.W)
         gpu.upload_walkers(my)
         c = per_rank[rank]
-        gpu.set_core_space(c["row_ptr"], c["col"], c["val"], sizes, displs, c["iluts"])
+        if devbuild:       # this rank's rows built on its own device (neci_gpu_build_core_space)
+            nnz = gpu.build_core_space(sizes, displs, c["iluts"])
+            assert nnz == c["row_ptr"][-1], (nnz, c["row_ptr"][-1])
+        else:
+            gpu.set_core_space(c["row_ptr"], c["col"], c["val"], sizes, displs, c["iluts"])
         if rank == 0:
             for r in range(world):
                 mine_r = [lookup[tuple(d)] for d in core[displs[r]:displs[r] + sizes[r]]]
@@ -142,10 +146,16 @@ def _worker(rank, world, port, out_dir, name, semi, balance=False, p2p=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,semi,balance,p2p", [("pchb_14e28o", False, False, False), ("hub_k_6x6_2words", False, False, True),
-                                                   ("hub_rs_4x4", False, True, False), ("pchb_14e28o", False, True, True),
-                                                   ("pchb_6e6o", True, False, True), ("pchb_14e28o", False, False, True)])
-def test_multi_gpu_matches_oracle_world(tmp_path, name, semi, balance, p2p):
+_UNVERIFIED = pytest.mark.skipif(os.environ.get("NECI_GPU_UNVERIFIED") != "1",
+                                 reason="written after the round's GPU budget was spent: first run on hardware pending")
+
+
+@pytest.mark.parametrize("name,semi,balance,p2p,devbuild", [
+    ("pchb_14e28o", False, False, False, False), ("hub_k_6x6_2words", False, False, True, False),
+    ("hub_rs_4x4", False, True, False, False), ("pchb_14e28o", False, True, True, False),
+    ("pchb_6e6o", True, False, True, False), ("pchb_14e28o", False, False, True, False),
+    pytest.param("pchb_6e6o", True, False, True, True, marks=_UNVERIFIED)])
+def test_multi_gpu_matches_oracle_world(tmp_path, name, semi, balance, p2p, devbuild):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -153,7 +163,7 @@ def test_multi_gpu_matches_oracle_world(tmp_path, name, semi, balance, p2p):
         pytest.skip("needs >= 2 GPUs")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, str(tmp_path), name, semi, balance, p2p), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), name, semi, balance, p2p, devbuild), nprocs=world, join=True)
     res = open(os.path.join(tmp_path, "result.txt")).read()
     assert res.startswith("OK"), res
     assert int(res.split()[1]) > 100
