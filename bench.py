@@ -427,9 +427,9 @@ def main():
         # the trial / connected spaces are built by the host library, as the Fortran host would, before the loop
         space = semistoch_space(system, hii, params, world, args.core_size, args.trial)
         rec = rec[~host.rows_in(rec[:, :system.nw], space["iluts"])]
-        tot_rand = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
-        # half of the population sits in the core space, as in a converged semi-stochastic run
-        rec = np.concatenate([semistoch_records(system, space, rank, l1_total=tot_rand * world), rec])
+        # half of the population sits in the core space, as in a converged semi-stochastic run (the nominal figure,
+        # so that every rank scales the core amplitudes alike)
+        rec = np.concatenate([semistoch_records(system, space, rank, l1_total=args.walkers * world), rec])
     eng.upload_walkers(rec)
     if semi:
         nnz, t_build = semistoch_apply(eng, system, hii, space, rank, build=args.core_build)
