@@ -172,13 +172,16 @@ int neci_host_get_helement(int32_t nel, int32_t nbasis, const double *umat, cons
     return 0;
 }
 
-// generate_sing_doub_determinants: the reference determinant, then its spin-conserving single and double
-// excitations (all irreps equal, as in the synthetic FCIDUMPs; symmetry-forbidden ones have H = 0 and can be
-// dropped with only_keep_conn as the reference does, :585-594).  Returns the number of determinants written, or
+// generate_sing_doub_determinants: the reference determinant, then its spin- and symmetry-conserving single and
+// double excitations, which is what GenExcitations3 enumerates.  orbsym: the FCIDUMP's ORBSYM label of every spatial
+// orbital (abelian point groups: labels 1..8, product = ((a-1) xor (b-1)) + 1), or NULL when all irreps are equal as
+// in the synthetic FCIDUMPs.  only_keep_conn additionally drops determinants without a matrix element to the
+// reference (:585-594).  Returns the number of determinants written, or
 // -(needed) if `capacity` is too small.  Order: ascending hole (pair), ascending particle (pair); the caller
 // sorts per rank as init_semi_stochastic does (:227).
 int64_t neci_host_sd_space(int32_t nel, int32_t nbasis, const double *umat, const double *tmat,
-                           const int64_t *ilut_ref, int32_t only_keep_conn, int64_t capacity, int64_t *out) {
+                           const int64_t *ilut_ref, int32_t only_keep_conn, const int32_t *orbsym,
+                           int64_t capacity, int64_t *out) {
     if (nbasis > 128) return 0;
     const Ham H{nel, nbasis, nbasis / 64 + 1, umat, tmat, 0.0};
     const Det2 R = H.load(ilut_ref);
@@ -190,9 +193,10 @@ int64_t neci_host_sd_space(int32_t nel, int32_t nbasis, const double *umat, cons
         ++n;
     };
     put(R);
+    auto irr = [&](int b) { return orbsym ? (orbsym[b >> 1] - 1) : 0; };
     for (int i : occ)
         for (int a : vir) {
-            if (!Ham::same_spin(i, a)) continue;
+            if (!Ham::same_spin(i, a) || irr(i) != irr(a)) continue;
             if (only_keep_conn && std::fabs(H.single(R, i, a)) < 1e-12) continue;
             Det2 d = R; flip(d, i); flip(d, a); put(d);
         }
@@ -202,6 +206,7 @@ int64_t neci_host_sd_space(int32_t nel, int32_t nbasis, const double *umat, cons
                 for (size_t q = p + 1; q < vir.size(); ++q) {
                     const int i = occ[x], j = occ[y], a = vir[p], b = vir[q];
                     if (((i & 1) + (j & 1)) != ((a & 1) + (b & 1))) continue;          // Ms conserved
+                    if ((irr(i) ^ irr(j)) != (irr(a) ^ irr(b))) continue;              // total irrep conserved
                     if (only_keep_conn && std::fabs(H.dbl(R, i, j, a, b)) < 1e-12) continue;
                     Det2 d = R; flip(d, i); flip(d, j); flip(d, a); flip(d, b); put(d);
                 }

@@ -334,9 +334,10 @@ def get_helement(system, iluts_i, iluts_j):
     return out
 
 
-def sing_doub_space(system, ref_ilut=None, only_keep_conn=False):
+def sing_doub_space(system, ref_ilut=None, only_keep_conn=False, orbsym=None):
     """`doubles-core`: the reference determinant and its single and double excitations
-    (generate_sing_doub_determinants, src/semi_stoch_gen.F90:537-604) as n x nw occupation words."""
+    (generate_sing_doub_determinants, src/semi_stoch_gen.F90:537-604) as n x nw occupation words.
+    orbsym: ORBSYM labels of the spatial orbitals (abelian groups); None = all irreps equal."""
     ref = _iluts(system, system.ilut(system.ref_orbs) if ref_ilut is None else ref_ilut)
     t = system.tables
     na, nb_ = system.nocc_alpha, system.nocc_beta
@@ -344,9 +345,11 @@ def sing_doub_space(system, ref_ilut=None, only_keep_conn=False):
     cap = 1 + na * va + nb_ * vb + (na * (na - 1) // 2) * (va * (va - 1) // 2) \
         + (nb_ * (nb_ - 1) // 2) * (vb * (vb - 1) // 2) + na * va * nb_ * vb
     out = np.zeros((cap, system.nw), dtype=np.int64)
+    sym = None if orbsym is None else np.ascontiguousarray(orbsym, dtype=np.int32)
+    assert sym is None or sym.shape[0] == system.nbasis // 2
     n = lib().neci_host_sd_space(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
                                  _p(t["tmat"], C.c_double), _p(ref, C.c_int64), C.c_int32(int(only_keep_conn)),
-                                 C.c_int64(cap), _p(out, C.c_int64))
+                                 None if sym is None else _p(sym, C.c_int32), C.c_int64(cap), _p(out, C.c_int64))
     if n <= 0:
         raise RuntimeError("neci_host_sd_space failed (%d)" % n)
     return out[:n].copy()

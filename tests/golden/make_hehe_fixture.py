@@ -40,7 +40,15 @@ def main():
     hi_det = re.search(r"Highest energy determinant is:\s+([\d\s]+)\n", bench)
     tot = re.search(r"Total projected energy\s+(-?[\d.]+)\s*\+/-\s*([\d.Ee+-]+)", bench)
     ref_det = re.search(r"Generated reference determinants:\s*\n\(\s*([\d,\s]+)\)", bench)
+    # `Total size of deterministic space` printed by this case (HPHF functions) and by the determinant-basis twin on
+    # the same FCIDUMP, test_suite/neci/determ_and_trial_spaces/determ_doubles (semi-stochastic doubles-core)
+    core_hphf = int(re.search(r"Total size of deterministic space:\s+(\d+)", bench).group(1))
+    twin = os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", "determ_doubles")
+    assert open(os.path.join(twin, "FCIDUMP")).read() == txt
+    bench2 = open(glob.glob(os.path.join(twin, "benchmark*"))[0]).read()
+    core_dets = int(re.search(r"Total size of deterministic space:\s+(\d+)", bench2).group(1))
     out = dict(
+        doubles_core_size_hphf=core_hphf, doubles_core_size_determinants=core_dets,
         source="test_suite/neci/parallel/HeHe_SS_Doubles (FCIDUMP, neci.inp, benchmark.out...)",
         input=dict(hphf=True, allrealcoeff=True, realspawncutoff=0.01, tau=0.001, totalwalkers=1000, shiftdamp=0.1,
                    stepsshift=1, semi_stochastic="doubles-core", startsinglepart=10, diagshift=1.0, nmcyc=6000),

@@ -257,3 +257,31 @@ def test_bench_semistoch_setup_split_over_ranks_matches_single_rank():
         results[nr] = helpers.canon(d, nw=s.nw)
     assert np.array_equal(results[1][0], results[3][0]) and np.array_equal(results[1][2], results[3][2])
     assert np.allclose(results[1][1], results[3][1], rtol=1e-12, atol=1e-12)
+
+
+def test_doubles_core_size_matches_the_reference_runs():
+    """`Total size of deterministic space` printed by two of the reference's regression runs on the same FCIDUMP
+    (10 orbitals, 4 electrons, D2h labels): 69 determinants for `semi-stochastic doubles-core` in the determinant basis
+    (test_suite/neci/determ_and_trial_spaces/determ_doubles) and 43 HPHF functions for the HPHF run
+    (test_suite/neci/parallel/HeHe_SS_Doubles) -- generate_sing_doub_determinants with the point-group symmetry of
+    GenExcitations3, then one representative per spin-flipped pair."""
+    import json
+    import os
+    from neci_stable_b200 import fcidump
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hehe_ss_doubles.json")))
+    d = fcidump.FciDump(norb=g["norb"], nelec=g["nelec"], ms2=g["ms2"], orbsym=g["orbsym"], ecore=g["ecore"], eps=g["eps"],
+                        h1=[tuple(x) for x in g["h1"]], eri=[tuple(x) for x in g["eri"]])
+    s = d.system()
+    assert [int(x) for x in s.ref_orbs] == g["reference_det"]
+    sd = host.sing_doub_space(s, orbsym=g["orbsym"])
+    assert sd.shape[0] == g["doubles_core_size_determinants"] == 69
+    A, B = 0xAAAAAAAAAAAAAAAA, 0x5555555555555555
+    reps = [w for w in (int(np.uint64(r[0])) for r in sd) if w >= (((w & A) >> 1) | ((w & B) << 1))]
+    assert len(reps) == g["doubles_core_size_hphf"] == 43
+    # symmetry-forbidden excitations carry no matrix element to the reference, and every determinant the symmetry
+    # keeps is within the unrestricted space
+    full = host.sing_doub_space(s)
+    keep = host.rows_in(full, sd)
+    assert keep.sum() == 69
+    h0 = host.get_helement(s, np.repeat(full[:1], full.shape[0], 0), full)
+    assert np.all(np.abs(h0[~keep]) < 1e-10)
