@@ -47,7 +47,25 @@ def main():
     assert open(os.path.join(twin, "FCIDUMP")).read() == txt
     bench2 = open(glob.glob(os.path.join(twin, "benchmark*"))[0]).read()
     core_dets = int(re.search(r"Total size of deterministic space:\s+(\d+)", bench2).group(1))
+    # that run also prints the lowest eigenvalue of its core Hamiltonian (Davidson) and starts from the core ground
+    # state scaled to `startsinglepart` walkers: the first line of the iteration table holds its weight on the
+    # reference and on the doubles, and the projected energy of that state
+    sd_counts = re.search(r"(\d+) double excitations, and\s+(\d+) single excitations found from reference", bench2)
+    e_core = float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench2).group(1))
+    table = bench2[bench2.index("Step    Shift"):]
+    row1 = re.search(r"\n\s+1\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+", table)
+    f = [float(x) for x in row1.groups()]
+    rows = {}
+    for k in (2, 3):
+        m = re.search(r"\n\s+%d\s+(\S+)" % k + r"\s+(\S+)" * 11 + r"\s+", table)
+        rows[k] = [float(x) for x in m.groups()]
     out = dict(
+        determ_doubles=dict(source="test_suite/neci/determ_and_trial_spaces/determ_doubles (same FCIDUMP; benchmark.out...)",
+                            n_doubles_from_reference=int(sd_counts.group(1)), n_singles_from_reference=int(sd_counts.group(2)),
+                            core_correlation_energy=e_core, start_walkers=10000.0, tau=0.01,
+                            step1_proj_e=f[7], step1_no_at_hf=f[10], step1_no_at_doubs=f[11],
+                            shift_damp=0.5, step2_shift=rows[2][0], step2_no_at_hf=rows[2][10], step2_no_at_doubs=rows[2][11],
+                            step3_no_at_hf=rows[3][10]),
         doubles_core_size_hphf=core_hphf, doubles_core_size_determinants=core_dets,
         source="test_suite/neci/parallel/HeHe_SS_Doubles (FCIDUMP, neci.inp, benchmark.out...)",
         input=dict(hphf=True, allrealcoeff=True, realspawncutoff=0.01, tau=0.001, totalwalkers=1000, shiftdamp=0.1,

@@ -285,3 +285,73 @@ def test_doubles_core_size_matches_the_reference_runs():
     assert keep.sum() == 69
     h0 = host.get_helement(s, np.repeat(full[:1], full.shape[0], 0), full)
     assert np.all(np.abs(h0[~keep]) < 1e-10)
+
+
+def _hehe_system():
+    import json
+    import os
+    from neci_stable_b200 import fcidump
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hehe_ss_doubles.json")))
+    d = fcidump.FciDump(norb=g["norb"], nelec=g["nelec"], ms2=g["ms2"], orbsym=g["orbsym"], ecore=g["ecore"], eps=g["eps"],
+                        h1=[tuple(x) for x in g["h1"]], eri=[tuple(x) for x in g["eri"]])
+    return g, d.system()
+
+
+def test_core_hamiltonian_and_first_iteration_match_the_reference_run():
+    """Numbers the reference printed for its `determ_doubles` regression run (semi-stochastic doubles-core on the HeHe
+    FCIDUMP, started from the core ground state scaled to 10000 walkers):
+      * 60 doubles and 8 singles found from the reference determinant;
+      * `Deterministic subspace correlation energy` -0.0646316671 = lowest eigenvalue of the core Hamiltonian
+        (host library: symmetry-adapted doubles-core space + sparse core Hamiltonian) to all printed digits;
+      * first line of the iteration table: NoatHF 5827.059, NoatDoubs 4147.905 (the weights of that eigenvector at
+        10000 walkers) and Proj.E -0.6463167E-01, reproduced by the eigenvector and by the oracle's SumEContrib in
+        an iteration started from it."""
+    g, s = _hehe_system()
+    ref = g["determ_doubles"]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    sd = host.sing_doub_space(s, orbsym=g["orbsym"])
+    refw = s.ilut(s.ref_orbs)
+    level = np.array([bin(int(np.uint64(w[0] ^ refw[0]))).count("1") // 2 for w in sd])
+    assert (level == 2).sum() == ref["n_doubles_from_reference"] and (level == 1).sum() == ref["n_singles_from_reference"]
+    il, sizes, displs = host.layout_core_space(sd, np.zeros(sd.shape[0], dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il, hii)
+    n = il.shape[0]
+    H = np.zeros((n, n))
+    for i in range(n):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        H[i, c["col"][sl]] = c["val"][sl]
+    assert np.allclose(H, H.T, atol=1e-13)
+    w, v = np.linalg.eigh(H)
+    assert abs(w[0] - ref["core_correlation_energy"]) < 6e-11                      # printed with 10 decimals
+    psi = v[:, 0]
+    iref = int(np.nonzero((il == refw).all(axis=1))[0][0])
+    psi = psi * np.sign(psi[iref]) * ref["start_walkers"] / np.abs(psi).sum()      # scaled to `startsinglepart` walkers
+    lvl = np.array([bin(int(np.uint64(x[0] ^ refw[0]))).count("1") // 2 for x in il])
+    assert abs(psi[iref] - ref["step1_no_at_hf"]) < 6e-4                           # printed with 7 significant digits
+    assert abs(np.abs(psi[lvl == 2]).sum() - ref["step1_no_at_doubs"]) < 6e-4
+    # the same through the oracle: one iteration from that state
+    o, _ = helpers.make_pair(s, hii, max_walkers=20000, max_spawned=20000, semi_stochastic=True, all_real_coeff=True,
+                             real_spawn_cutoff=0.01, initiator_walk_no=2.0, seed=7)
+    flags = (1 << capi.FLAG_DETERMINISTIC) | (1 << capi.FLAG_INITIATOR)
+    recs = np.zeros((n, s.nw + 2), dtype=np.int64)
+    recs[:, :s.nw] = il
+    recs[:, s.nw] = psi.view(np.int64)
+    recs[:, s.nw + 1] = flags
+    o.upload_walkers(recs)
+    o.set_core_space(c["row_ptr"], c["col"], c["val"], sizes, displs, il)
+    st = o.iterate(ref["tau"], 0.0, 1)
+    assert abs(st[ST["HFCYC"]] - ref["step1_no_at_hf"]) < 6e-4
+    assert abs(st[ST["NOATDOUBS"]] - ref["step1_no_at_doubs"]) < 6e-4
+    assert abs(st[ST["ENUMCYC"]] / st[ST["HFCYC"]] - ref["step1_proj_e"]) < 6e-9  # -0.6463167E-01
+    # Second and third line of the table.  Every determinant connected to the reference is a core determinant, so
+    # the reference amplitude evolves deterministically; the doubles do too during the first iteration (nothing
+    # outside the core space exists yet).  The shift printed in line k is the one computed at the END of iteration k,
+    # so iterations 1 and 2 both run at S = 0 (real coefficients: determ_projection_no_death + death of every
+    # determinant, FciMCPar.F90:1778-1782, 1842-1846).
+    st2 = o.iterate(ref["tau"], 0.0, 2)
+    assert abs(st2[ST["HFCYC"]] - ref["step2_no_at_hf"]) < 6e-4                    # 5830.825
+    assert abs(st2[ST["NOATDOUBS"]] - ref["step2_no_at_doubs"]) < 6e-4            # 4150.586
+    st3 = o.iterate(ref["tau"], ref["step2_shift"], 3)
+    assert abs(st3[ST["HFCYC"]] - ref["step3_no_at_hf"]) < 6e-4                    # 5834.594
+    # and the closed form behind them: one step multiplies the core ground state by 1 - tau (E_core - S)
+    assert abs(ref["step1_no_at_hf"] * (1.0 - ref["tau"] * w[0]) - ref["step2_no_at_hf"]) < 1e-3
