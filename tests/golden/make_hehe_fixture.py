@@ -59,7 +59,17 @@ def main():
     for k in (2, 3):
         m = re.search(r"\n\s+%d\s+(\S+)" % k + r"\s+(\S+)" * 11 + r"\s+", table)
         rows[k] = [float(x) for x in m.groups()]
+    # the HPHF run itself: core correlation energy and the first two lines of its iteration table
+    tab = bench[bench.index("Step    Shift"):]
+    hrows = {}
+    for k in (1, 2):
+        m = re.search(r"\n\s+%d\s+(\S+)" % k + r"\s+(\S+)" * 11 + r"\s+", tab)
+        hrows[k] = [float(x) for x in m.groups()]
+    hphf_run = dict(core_correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench).group(1)),
+                    start_walkers=10.0, tau=0.001, diagshift=1.0,
+                    step1_no_at_hf=hrows[1][10], step1_no_at_doubs=hrows[1][11], step2_no_at_hf=hrows[2][10])
     out = dict(
+        hphf_run=hphf_run,
         determ_doubles=dict(source="test_suite/neci/determ_and_trial_spaces/determ_doubles (same FCIDUMP; benchmark.out...)",
                             n_doubles_from_reference=int(sd_counts.group(1)), n_singles_from_reference=int(sd_counts.group(2)),
                             core_correlation_energy=e_core, start_walkers=10000.0, tau=0.01,

@@ -112,3 +112,35 @@ def test_hphf_fciqmc_converges_to_the_ground_state():
     for x in w:
         x = int(x); f = _flip(x)
         assert f == x or x > f
+
+
+def test_hphf_core_hamiltonian_matches_the_reference_hehe_ss_doubles_run():
+    """Numbers the reference printed for its HPHF regression run HeHe_SS_Doubles (semi-stochastic doubles-core over
+    43 HPHF functions, started from the core ground state at 10 walkers): the lowest eigenvalue of the core
+    Hamiltonian built from the oracle's hphf_diag_helement / hphf_off_diag_helement is the printed
+    `Deterministic subspace correlation energy` -0.0646316671, and the eigenvector's weights on the reference and on
+    the doubles are the NoatHF / NoatDoubs of the first line of the iteration table (6.249123, 3.731892)."""
+    import test_core_space_cpu as TC
+    g, s = TC._hehe_system()
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000, hphf=True)
+    sd = host.sing_doub_space(s, orbsym=g["orbsym"])
+    A, B = 0xAAAAAAAAAAAAAAAA, 0x5555555555555555
+    flip = lambda w: ((w & A) >> 1) | ((w & B) << 1)
+    reps = np.array([[r[0]] for r in sd if int(np.uint64(r[0])) >= flip(int(np.uint64(r[0])))], dtype=np.int64)
+    n = reps.shape[0]
+    assert n == g["doubles_core_size_hphf"] == 43
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    H = o.probe_helement(reps[I], reps[J]).reshape(n, n)
+    assert np.allclose(H, H.T, atol=1e-12)
+    w, v = np.linalg.eigh(H - hii * np.eye(n))
+    ref = g["hphf_run"]
+    assert abs(w[0] - ref["core_correlation_energy"]) < 6e-11            # -0.0646316671, printed with 10 decimals
+    refw = int(np.uint64(s.ilut(s.ref_orbs)[0]))
+    words = [int(np.uint64(r[0])) for r in reps]
+    iref = words.index(refw)
+    psi = v[:, 0] * np.sign(v[iref, 0]) * ref["start_walkers"] / np.abs(v[:, 0]).sum()       # startsinglepart 10
+    level = np.array([min(bin(refw & ~x).count("1"), bin(refw & ~flip(x)).count("1")) for x in words])
+    assert abs(psi[iref] - ref["step1_no_at_hf"]) < 6e-7 and abs(np.abs(psi[level == 2]).sum() - ref["step1_no_at_doubs"]) < 6e-7
+    # one deterministic step at the run's tau = 0.001 and diagshift 1.0 gives the second line's NoatHF 6.255776
+    assert abs(psi[iref] * (1.0 - ref["tau"] * (w[0] - ref["diagshift"])) - ref["step2_no_at_hf"]) < 2e-6
