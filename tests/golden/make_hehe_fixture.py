@@ -68,7 +68,16 @@ def main():
     hphf_run = dict(core_correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench).group(1)),
                     start_walkers=10.0, tau=0.001, diagshift=1.0,
                     step1_no_at_hf=hrows[1][10], step1_no_at_doubs=hrows[1][11], step2_no_at_hf=hrows[2][10])
+    # `semi-stochastic fci-core` on the same FCIDUMP (test_suite/neci/rdm_singlerun/parallel/HeHe_determ): the whole
+    # symmetry sector as core space, so the printed core correlation energy is the exact FCI correlation energy
+    fci = os.path.join(REF, "test_suite", "neci", "rdm_singlerun", "parallel", "HeHe_determ")
+    assert open(os.path.join(fci, "FCIDUMP")).read() == txt
+    bench3 = open(glob.glob(os.path.join(fci, "benchmark*"))[0]).read()
+    fci_core = dict(source="test_suite/neci/rdm_singlerun/parallel/HeHe_determ (same FCIDUMP; benchmark.out...)",
+                    size=int(re.search(r"Total size of deterministic space:\s+(\d+)", bench3).group(1)),
+                    correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench3).group(1)))
     out = dict(
+        fci_core=fci_core,
         hphf_run=hphf_run,
         determ_doubles=dict(source="test_suite/neci/determ_and_trial_spaces/determ_doubles (same FCIDUMP; benchmark.out...)",
                             n_doubles_from_reference=int(sd_counts.group(1)), n_singles_from_reference=int(sd_counts.group(2)),

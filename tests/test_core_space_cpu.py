@@ -355,3 +355,36 @@ def test_core_hamiltonian_and_first_iteration_match_the_reference_run():
     assert abs(st3[ST["HFCYC"]] - ref["step3_no_at_hf"]) < 6e-4                    # 5834.594
     # and the closed form behind them: one step multiplies the core ground state by 1 - tau (E_core - S)
     assert abs(ref["step1_no_at_hf"] * (1.0 - ref["tau"] * w[0]) - ref["step2_no_at_hf"]) < 1e-3
+
+
+def test_fci_core_space_gives_the_reference_fci_correlation_energy():
+    """`semi-stochastic fci-core` of the reference on the HeHe FCIDUMP (HeHe_determ): 309 determinants = the Ms = 0
+    sector restricted to the irrep of the reference determinant, and `Deterministic subspace correlation energy`
+    -0.0650928511 = the exact ground-state energy of that block minus the reference energy.  Reproduced from the
+    host library's sparse Hamiltonian over the symmetry-filtered sector: every matrix element of the system takes
+    part, to the 10 printed decimals."""
+    g, s = _hehe_system()
+    ref = g["fci_core"]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    irr = lambda orbs: int(np.bitwise_xor.reduce([g["orbsym"][(o + 1) // 2 - 1] - 1 for o in orbs]))
+    target = irr([int(x) for x in s.ref_orbs])
+    dets = [d for d in helpers.all_dets(s) if irr(d) == target]
+    assert len(dets) == ref["size"] == 309
+    il = np.array([s.ilut(d) for d in dets], dtype=np.int64).reshape(len(dets), s.nw)
+    il, sizes, displs = host.layout_core_space(il, np.zeros(len(dets), dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il, hii)
+    n = il.shape[0]
+    H = np.zeros((n, n))
+    for i in range(n):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        H[i, c["col"][sl]] = c["val"][sl]
+    w = np.linalg.eigvalsh(H)
+    assert abs(w[0] - ref["correlation_energy"]) < 6e-11
+    # the oracle's own elements (the checker of the CUDA path) give the same number
+    o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000)
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    Ho = o.probe_helement(il[I], il[J]).reshape(n, n) - hii * np.eye(n)
+    assert abs(np.linalg.eigvalsh(Ho)[0] - ref["correlation_energy"]) < 6e-11
+    assert np.allclose(Ho, H, rtol=1e-12, atol=1e-13)
+    # consistent with the projected energy the HPHF run of the same system converged to (statistical)
+    assert abs(hii + w[0] - g["total_projected_energy"]) < 5 * g["total_projected_energy_error"] + 1e-4
