@@ -472,3 +472,39 @@ def test_det_node_matches_the_reference_processor_of_its_own_runs():
         blk, node = o.probe_det_node(s.ilut(c["det"]).reshape(1, -1))
         assert int(blk[0]) == c["block"] and int(node[0]) == c["reference_processor"], (c["case"], blk, node)
         o.close()
+
+
+@pytest.mark.parametrize("which,ref_orbs", [("total_momentum_6", list(range(1, 13))),
+                                            ("total_momentum_0", list(range(1, 11)) + [11, 14])])
+def test_k_hubbard_doubles_core_matches_the_reference_runs(which, ref_orbs):
+    """Two reference runs on the 12-site k-space Hubbard chain (U = 1, half filling) with `doubles-core`: the
+    deterministic space has 205 determinants (reference + every spin- and momentum-conserving double excitation,
+    same-spin ones included) and the lowest eigenvalue of H over it, relative to the reference energy, is the printed
+    `Deterministic subspace correlation energy` (-0.2580331648 with both open-shell electrons in one eps = 0 orbital,
+    -0.2274848837 with one in each); the reference energy -11.9282032303 as printed.  Oracle's
+    get_diag_helement_k_sp_hub / get_offdiag_helement_k_sp_hub on a lattice the unit tests do not reach."""
+    import itertools
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hubbard_doubles_core.json")))[which]
+    assert g["cell"] == [12, 1, 1] and g["b"] == -1.0
+    s = host.hubbard_k_system(g["cell"][0], g["cell"][1], nel=g["electrons"], U=g["u"])
+    t = s.tables
+    nk = t["n_k"]
+    ksum = np.array(t["ksum"]).reshape(nk, nk)
+    kidx = lambda o: (o + 1) // 2 - 1
+    hii = driver.diag_energy(s, ref_orbs)
+    assert abs(hii - g["reference_energy"]) < 6e-11
+    vir = [o for o in range(1, s.nbasis + 1) if o not in ref_orbs]
+    dets = [ref_orbs]
+    for i, j in itertools.combinations(ref_orbs, 2):
+        for a, b in itertools.combinations(vir, 2):
+            if (i & 1) + (j & 1) == (a & 1) + (b & 1) and ksum[kidx(i), kidx(j)] == ksum[kidx(a), kidx(b)]:
+                dets.append(sorted([o for o in ref_orbs if o not in (i, j)] + [a, b]))
+    n = len(dets)
+    assert n == g["core_size"] == 205
+    o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000)
+    il = np.array([s.ilut(d) for d in dets], dtype=np.int64).reshape(n, s.nw)
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    H = o.probe_helement(il[I], il[J]).reshape(n, n) - hii * np.eye(n)
+    assert np.allclose(H, H.T, atol=1e-13)
+    assert abs(np.linalg.eigvalsh(H)[0] - g["core_correlation_energy"]) < 6e-11
