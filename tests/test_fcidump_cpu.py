@@ -82,3 +82,40 @@ def test_frozen_core_leaves_the_hamiltonian_of_the_valence_space_unchanged():
     # the frozen electrons sit below / between the valence orbitals: moving a valence electron past an even number
     # of them never changes a parity
     assert np.allclose(hz, hf, rtol=1e-12, atol=1e-12)
+
+
+def test_frozen_core_open_shell_case_matches_the_reference_run():
+    """The reference's BeH_open_shell_explicit regression run (19 orbitals, 5 electrons, Ms = -1/2, C2v labels,
+    `freeze 2 0`, `semi-stochastic doubles-core`): after fcidump.freeze_core the reference determinant (1, 2, 3) has
+    the printed `Reference Energy` -15.1493554282, the symmetry-adapted singles and doubles are the printed 234
+    determinants and the lowest eigenvalue of the host library's sparse Hamiltonian over them is the printed
+    `Deterministic subspace correlation energy` -0.0383128036 -- frozen-core folding, open-shell Slater-Condon rules
+    and the doubles-core generator on a system with unequal alpha and beta occupations."""
+    import helpers
+    z = np.load(os.path.join(GOLD, "beh_open_shell.npz"))
+    d = fcidump.FciDump(norb=int(z["norb"]), nelec=int(z["nelec"]), ms2=int(z["input_spin_restrict"]),
+                        orbsym=[int(x) for x in z["orbsym"]], ecore=float(z["ecore"]), eps=[float(x) for x in z["eps"]],
+                        h1=[(int(a), int(b), float(v)) for a, b, v in z["h1"]],
+                        eri=[(int(a), int(b), int(c), int(e), float(v)) for a, b, c, e, v in z["eri"]])
+    assert list(z["input_freeze"]) == [2, 0]
+    f = fcidump.freeze_core(d, [int(np.argmin(d.eps)) + 1])          # the two lowest spin orbitals
+    s = f.system()
+    assert (f.norb, f.nelec, s.nocc_alpha, s.nocc_beta) == (18, 3, 1, 2)
+    assert [int(x) for x in s.ref_orbs] == [int(x) for x in z["reference_det"]]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    assert abs(hii - float(z["reference_energy"])) < 6e-11
+    sd = host.sing_doub_space(s, orbsym=f.orbsym)
+    assert sd.shape[0] == int(z["core_size"]) == 234
+    il, sizes, displs = host.layout_core_space(sd, np.zeros(sd.shape[0], dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il, hii)
+    n = il.shape[0]
+    H = np.zeros((n, n))
+    for i in range(n):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        H[i, c["col"][sl]] = c["val"][sl]
+    assert abs(np.linalg.eigvalsh(H)[0] - float(z["core_correlation_energy"])) < 6e-11
+    # and from the oracle's elements
+    o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000)
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    Ho = o.probe_helement(il[I], il[J]).reshape(n, n) - hii * np.eye(n)
+    assert np.allclose(Ho, H, rtol=1e-12, atol=1e-13)
