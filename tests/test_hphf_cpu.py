@@ -144,3 +144,54 @@ def test_hphf_core_hamiltonian_matches_the_reference_hehe_ss_doubles_run():
     assert abs(psi[iref] - ref["step1_no_at_hf"]) < 6e-7 and abs(np.abs(psi[level == 2]).sum() - ref["step1_no_at_doubs"]) < 6e-7
     # one deterministic step at the run's tau = 0.001 and diagshift 1.0 gives the second line's NoatHF 6.255776
     assert abs(psi[iref] * (1.0 - ref["tau"] * (w[0] - ref["diagshift"])) - ref["step2_no_at_hf"]) < 2e-6
+
+
+def test_mp1_core_and_trial_spaces_match_the_reference_ne_run():
+    """The reference's Ne_SS_Trial_Pops run (22 orbitals and 8 electrons after `freeze 2 0`, HPHF, `mp1-core 50`,
+    `mp1-trial 200`; tests/golden/ne_ss_trial.json) against the oracle's HPHF matrix elements:
+      * the 985 symmetry-allowed singles and doubles of the reference reduce to 529 HPHF functions;
+      * ranked by the first-order amplitude |<D_0|H|D_j> / (F_00 - F_jj)| (return_mp1_amp_and_mp2_energy,
+        src/semi_stoch_procs.F90:2143-2218, orbital energies from the FCIDUMP), the first 50 span a space whose lowest
+        eigenvalue is the printed `Deterministic subspace correlation energy` -0.1088456879;
+      * the 200-function trial space: 188 functions lie above the cut-off and 14 share the cut-off amplitude to all
+        digits, so the reference's choice among them depends on its enumeration order; one of the 91 ways of taking 12
+        of the 14 gives the printed `Energy eigenvalue(s) of the trial space` -128.68457855852768 to 1e-12."""
+    import itertools
+    import json
+    import os
+    import test_reference_fcidump_cpu as TR
+    z, s = TR.load_ne_pchb()
+    g = json.load(open(os.path.join(helpers.GOLDEN, "ne_ss_trial.json")))
+    hii = driver.diag_energy(s, s.ref_orbs)
+    assert abs(hii - g["reference_energy"]) < 6e-11
+    o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000, hphf=True)
+    sd = host.sing_doub_space(s, orbsym=[int(x) for x in z["orbsym"]])
+    assert sd.shape[0] == 985
+    A, B = 0xAAAAAAAAAAAAAAAA, 0x5555555555555555
+    flip = lambda w: ((w & A) >> 1) | ((w & B) << 1)
+    reps = np.array([[r[0]] for r in sd if int(np.uint64(r[0])) >= flip(int(np.uint64(r[0])))], dtype=np.int64)
+    assert reps.shape[0] == 529
+    eps = np.asarray(z["eps"], dtype=float)
+    h0 = lambda w: sum(eps[b >> 1] for b in range(64) if (int(np.uint64(w)) >> b) & 1)
+    ref = s.ilut(s.ref_orbs)
+    hel = o.probe_helement(np.repeat(ref.reshape(1, 1), reps.shape[0], 0), reps)
+    den = np.array([h0(ref[0]) - h0(r[0]) for r in reps])
+    a = np.abs(hel / np.where(den == 0, 1.0, den))
+    a[int(np.nonzero(reps[:, 0] == ref[0])[0][0])] = np.inf           # the reference heads the list
+    order = np.argsort(-a, kind="stable")
+
+    def lowest(idx):
+        il = reps[list(idx)]
+        n = il.shape[0]
+        I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+        return np.linalg.eigvalsh(o.probe_helement(il[I], il[J]).reshape(n, n))[0]
+    nc = g["core_size"]
+    assert a[order[nc - 1]] - a[order[nc]] > 1e-5                       # no tie at the core cut-off
+    assert abs(lowest(order[:nc]) - hii - g["core_correlation_energy"]) < 6e-11
+    nt = g["trial_size"]
+    cut = a[order[nt - 1]]
+    above = [i for i in order if a[i] > cut + 1e-8]
+    tied = [i for i in order if abs(a[i] - cut) <= 1e-8]
+    assert (len(above), len(tied)) == (188, 14)
+    best = min(abs(lowest(above + list(c)) - g["trial_energy"]) for c in itertools.combinations(tied, nt - len(above)))
+    assert best < 1e-12
