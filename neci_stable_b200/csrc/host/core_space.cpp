@@ -7,8 +7,8 @@
 //   neci_host_det_node          DetermineDetNode / get_det_block (src/load_balance_calcnodes.F90:25-117)
 //   neci_host_ham_apply         sum_j H_ij v_j over two determinant lists (con_space_vecs of init_trial_wf,
 //                               src/trial_wf_gen.F90)
-//   neci_host_core_ham_*        the sparse core Hamiltonian of one rank (calc_determ_hamil_sparse,
-//                               src/sparse_arrays.F90:426-572; row contents as calc_determ_hamil_opt,
+//   neci_host_core_ham_*        the sparse core Hamiltonian of one rank (calc_determ_hamil_sparse and
+//                               calc_determ_hamil_sparse_hphf, src/sparse_arrays.F90:426-690; row contents as calc_determ_hamil_opt,
 //                               src/fast_determ_hamil.F90:1421-1507: non-zero off-diagonal elements, then the
 //                               diagonal H_ii - Hii as the last entry of the row)
 //
@@ -134,6 +134,47 @@ struct Ham {
         p += between(t, j, b);
         return (p & 1) ? -h : h;
     }
+    // ---- HPHF functions, even S (src/HPHFIntegrals.fpp:62-150, 348-411) ----
+    static inline Det2 spin_flip(const Det2 &d) {
+        Det2 f;
+        for (int w = 0; w < 2; ++w) f.w[w] = ((d.w[w] & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((d.w[w] & 0x5555555555555555ull) << 1);
+        return f;
+    }
+    static inline bool closed_shell(const Det2 &d) { const Det2 f = spin_flip(d); return f.w[0] == d.w[0] && f.w[1] == d.w[1]; }
+    // CalcOpenOrbs: beta electrons without their alpha partner
+    static inline int open_orbs(const Det2 &d) {
+        int n = 0;
+        for (int w = 0; w < 2; ++w) n += popc(~((d.w[w] & 0xAAAAAAAAAAAAAAAAull) >> 1) & (d.w[w] & 0x5555555555555555ull));
+        return n;
+    }
+    static inline int level(const Det2 &a, const Det2 &b) { return (popc(a.w[0] ^ b.w[0]) + popc(a.w[1] ^ b.w[1])) / 2; }
+    // hphf_off_diag_helement_norm
+    double hphf_off_diag(const Det2 &I, const Det2 &J) const {
+        if (I.w[0] == J.w[0] && I.w[1] == J.w[1]) return 0.0;
+        double hel = element(I, J);
+        const bool ci = closed_shell(I), cj = closed_shell(J);
+        if (ci != cj) return hel * std::sqrt(2.0);
+        if (ci) return hel;
+        const Det2 I2 = spin_flip(I);
+        if (level(I2, J) <= 2) {
+            const double m2 = element(I2, J);
+            hel = (open_orbs(I) % 2 == 0) ? hel + m2 : hel - m2;
+        }
+        return hel;
+    }
+    // hphf_diag_helement
+    double hphf_diag(const Det2 &I) const {
+        double hel = diag(I);
+        if (!closed_shell(I)) {
+            const Det2 I2 = spin_flip(I);
+            if (level(I, I2) <= 2) {
+                const double m2 = element(I, I2);
+                hel = (open_orbs(I) % 2 == 1) ? hel - m2 : hel + m2;
+            }
+        }
+        return hel;
+    }
+
     // get_helement(nI, nJ, iLutI, iLutJ)
     double element(const Det2 &I, const Det2 &J) const {
         Det2 hole, part;
@@ -169,6 +210,18 @@ int neci_host_get_helement(int32_t nel, int32_t nbasis, const double *umat, cons
     if (nbasis > 128) return 1;
     const Ham H{nel, nbasis, nbasis / 64 + 1, umat, tmat, ecore};
     for (int64_t k = 0; k < n; ++k) out[k] = H.element(H.load(iluts_i + k * H.nw), H.load(iluts_j + k * H.nw));
+    return 0;
+}
+// the same between HPHF functions given by their allowed representatives (hphf_diag_helement when both are equal,
+// hphf_off_diag_helement otherwise)
+int neci_host_get_helement_hphf(int32_t nel, int32_t nbasis, const double *umat, const double *tmat, double ecore,
+                                const int64_t *iluts_i, const int64_t *iluts_j, int64_t n, double *out) {
+    if (nbasis > 128) return 1;
+    const Ham H{nel, nbasis, nbasis / 64 + 1, umat, tmat, ecore};
+    for (int64_t k = 0; k < n; ++k) {
+        const Det2 I = H.load(iluts_i + k * H.nw), J = H.load(iluts_j + k * H.nw);
+        out[k] = (I.w[0] == J.w[0] && I.w[1] == J.w[1]) ? H.hphf_diag(I) : H.hphf_off_diag(I, J);
+    }
     return 0;
 }
 
@@ -241,7 +294,7 @@ int neci_host_det_node(int32_t nbasis, const int32_t *random_orb_index, int32_t 
 // copied out and the job freed by neci_host_core_ham_fetch.  n_threads <= 0: all hardware threads.
 void *neci_host_core_ham_build(int32_t nel, int32_t nbasis, const double *umat, const double *tmat, double ecore,
                                double hii, const int64_t *iluts, int64_t n_core, int64_t displ, int64_t n_local,
-                               int32_t n_threads, int64_t *nnz_out) {
+                               int32_t n_threads, int32_t hphf, int64_t *nnz_out) {
     if (nbasis > 128 || displ < 0 || n_local < 0 || displ + n_local > n_core || n_core > 0x7fffffffll) return nullptr;
     Ham H{nel, nbasis, nbasis / 64 + 1, umat, tmat, ecore};
     H.build_single_tables();
@@ -263,14 +316,16 @@ void *neci_host_core_ham_build(int32_t nel, int32_t nbasis, const double *umat, 
             for (int64_t r = r0; r < r1; ++r) {
                 const int64_t gi = displ + r;
                 const Det2 I = D[gi];
+                const Det2 I2 = hphf ? Ham::spin_flip(I) : I;
                 const size_t start = cc.size();
                 for (int64_t j = 0; j < n_core; ++j) {
-                    const uint64_t x0 = I.w[0] ^ D[j].w[0], x1 = I.w[1] ^ D[j].w[1];
-                    if (popc(x0) + popc(x1) > 4 || j == gi) continue;     // more than a double excitation apart
-                    const double h = H.element(I, D[j]);
+                    if (j == gi) continue;
+                    // more than a double excitation apart (for HPHF functions: from the determinant and from its partner)
+                    if (Ham::level(I, D[j]) > 2 && (!hphf || Ham::level(I2, D[j]) > 2)) continue;
+                    const double h = hphf ? H.hphf_off_diag(I, D[j]) : H.element(I, D[j]);
                     if (std::fabs(h) > 0.0) { cc.push_back((int32_t)j); vv.push_back(h); }
                 }
-                cc.push_back((int32_t)gi); vv.push_back(H.diag(I) - hii);  // the diagonal closes the row
+                cc.push_back((int32_t)gi); vv.push_back((hphf ? H.hphf_diag(I) : H.diag(I)) - hii);  // the diagonal closes the row
                 job->row_len[r] = (int64_t)(cc.size() - start);
             }
             job->col[c].assign(cc.begin(), cc.end());

@@ -319,14 +319,16 @@ def _iluts(system, iluts):
     return np.ascontiguousarray(np.asarray(iluts, dtype=np.int64).reshape(-1, system.nw))
 
 
-def get_helement(system, iluts_i, iluts_j):
-    """get_helement (src/Determinants.F90:508-554) for pairs of determinants of an FCIDUMP system, on the host."""
+def get_helement(system, iluts_i, iluts_j, hphf=False):
+    """get_helement (src/Determinants.F90:508-554) for pairs of determinants of an FCIDUMP system, on the host;
+    hphf: between HPHF functions given by their allowed representatives (src/HPHFIntegrals.fpp)."""
     if system.kind != capi.SYS_FCIDUMP_PCHB:
         raise ValueError("host get_helement: FCIDUMP systems only")
     a, b = _iluts(system, iluts_i), _iluts(system, iluts_j)
     out = np.zeros(a.shape[0])
     t = system.tables
-    rc = lib().neci_host_get_helement(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
+    fn = lib().neci_host_get_helement_hphf if hphf else lib().neci_host_get_helement
+    rc = fn(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
                                       _p(t["tmat"], C.c_double), C.c_double(system.ecore), _p(a, C.c_int64),
                                       _p(b, C.c_int64), C.c_int64(a.shape[0]), _p(out, C.c_double))
     if rc:
@@ -386,8 +388,8 @@ def layout_core_space(core_iluts, nodes, nranks):
     return np.ascontiguousarray(il[order]), sizes, displs
 
 
-def core_hamiltonian(system, core_iluts, hii, displ=0, n_local=None, threads=0):
-    """Sparse core Hamiltonian rows of one rank (calc_determ_hamil_sparse, src/sparse_arrays.F90:426-572; each row:
+def core_hamiltonian(system, core_iluts, hii, displ=0, n_local=None, threads=0, hphf=False):
+    """Sparse core Hamiltonian rows of one rank (calc_determ_hamil_sparse / _hphf, src/sparse_arrays.F90:426-690; each row:
     the non-zero off-diagonal elements, then H_ii - Hii last as src/fast_determ_hamil.F90:1494-1507 leaves it).
     Returns dict(row_ptr int64, col int32, val float64) for neci_gpu_set_core_space."""
     if system.kind != capi.SYS_FCIDUMP_PCHB:
@@ -401,7 +403,7 @@ def core_hamiltonian(system, core_iluts, hii, displ=0, n_local=None, threads=0):
     h = L.neci_host_core_ham_build(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
                                    _p(t["tmat"], C.c_double), C.c_double(system.ecore), C.c_double(hii),
                                    _p(il, C.c_int64), C.c_int64(n_core), C.c_int64(int(displ)), C.c_int64(n_local),
-                                   C.c_int32(int(threads)), C.byref(nnz))
+                                   C.c_int32(int(threads)), C.c_int32(int(bool(hphf))), C.byref(nnz))
     if not h:
         raise RuntimeError("neci_host_core_ham_build failed")
     row_ptr = np.zeros(n_local + 1, dtype=np.int64)

@@ -195,3 +195,54 @@ def test_mp1_core_and_trial_spaces_match_the_reference_ne_run():
     assert (len(above), len(tied)) == (188, 14)
     best = min(abs(lowest(above + list(c)) - g["trial_energy"]) for c in itertools.combinations(tied, nt - len(above)))
     assert best < 1e-12
+
+
+def test_host_hphf_elements_and_core_hamiltonian():
+    """The host library's HPHF elements (calc_determ_hamil_sparse_hphf for the stand-alone host) equal the oracle's for
+    random pairs of representatives (one- and two-word determinants), and its sparse core Hamiltonian over the 43
+    HPHF functions of the reference's HeHe_SS_Doubles core space has the printed lowest eigenvalue -0.0646316671."""
+    import test_core_space_cpu as TC
+    A, B = 0xAAAAAAAAAAAAAAAA, 0x5555555555555555
+    for s in (host.random_fcidump_system(6, 6, sparse=0.9, sparse_t=0.9, seed=3),
+              host.random_fcidump_system(33, 8, sparse=0.7, sparse_t=0.7, seed=9)):
+        hii = driver.diag_energy(s, s.ref_orbs)
+        o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000, hphf=True)
+        rng = np.random.default_rng(3)
+        sd = host.sing_doub_space(s)
+        pick = sd[rng.choice(sd.shape[0], min(120, sd.shape[0]), replace=False)]
+        reps = {}
+        for row in pick:
+            w = row.view(np.uint64)
+            f = ((w & np.uint64(A)) >> np.uint64(1)) | ((w & np.uint64(B)) << np.uint64(1))
+            r = row if tuple(int(x) for x in row) >= tuple(int(x) for x in f.view(np.int64)) else f.view(np.int64)
+            reps[tuple(int(x) for x in r)] = r.copy()
+        il = np.array(list(reps.values()), dtype=np.int64).reshape(-1, s.nw)
+        n = il.shape[0]
+        I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+        hh = host.get_helement(s, il[I], il[J], hphf=True)
+        ho = o.probe_helement(il[I], il[J])
+        assert np.count_nonzero(ho) > 2 * n
+        assert np.allclose(hh, ho, rtol=1e-12, atol=1e-13)
+        il2, sizes, displs = host.layout_core_space(il, np.zeros(n, dtype=np.int32), 1)
+        c = host.core_hamiltonian(s, il2, hii, hphf=True)
+        H = np.zeros((n, n))
+        for i in range(n):
+            sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+            assert c["col"][sl][-1] == i
+            H[i, c["col"][sl]] = c["val"][sl]
+        I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+        want = o.probe_helement(il2[I], il2[J]).reshape(n, n) - hii * np.eye(n)
+        assert np.allclose(H, want, rtol=1e-12, atol=1e-13)
+    g, s = TC._hehe_system()
+    hii = driver.diag_energy(s, s.ref_orbs)
+    sd = host.sing_doub_space(s, orbsym=g["orbsym"])
+    flip = lambda w: ((w & A) >> 1) | ((w & B) << 1)
+    reps = np.array([[r[0]] for r in sd if int(np.uint64(r[0])) >= flip(int(np.uint64(r[0])))], dtype=np.int64)
+    il, sizes, displs = host.layout_core_space(reps, np.zeros(reps.shape[0], dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il, hii, hphf=True)
+    n = il.shape[0]
+    H = np.zeros((n, n))
+    for i in range(n):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        H[i, c["col"][sl]] = c["val"][sl]
+    assert n == 43 and abs(np.linalg.eigvalsh(H)[0] - g["hphf_run"]["core_correlation_energy"]) < 6e-11
