@@ -155,7 +155,8 @@ def test_mp1_core_and_trial_spaces_match_the_reference_ne_run():
         eigenvalue is the printed `Deterministic subspace correlation energy` -0.1088456879;
       * the 200-function trial space: 188 functions lie above the cut-off and 14 share the cut-off amplitude to all
         digits, so the reference's choice among them depends on its enumeration order; one of the 91 ways of taking 12
-        of the 14 gives the printed `Energy eigenvalue(s) of the trial space` -128.68457855852768 to 1e-12."""
+        of the 14 gives the printed `Energy eigenvalue(s) of the trial space` -128.68457855852768 to 1e-12;
+      * the space connected to that trial space has the printed 59726 members."""
     import itertools
     import json
     import os
@@ -193,8 +194,21 @@ def test_mp1_core_and_trial_spaces_match_the_reference_ne_run():
     above = [i for i in order if a[i] > cut + 1e-8]
     tied = [i for i in order if abs(a[i] - cut) <= 1e-8]
     assert (len(above), len(tied)) == (188, 14)
-    best = min(abs(lowest(above + list(c)) - g["trial_energy"]) for c in itertools.combinations(tied, nt - len(above)))
-    assert best < 1e-12
+    choice = min(itertools.combinations(tied, nt - len(above)), key=lambda c: abs(lowest(above + list(c)) - g["trial_energy"]))
+    assert abs(lowest(above + list(choice)) - g["trial_energy"]) < 1e-12
+    # `Total size of connected space` 59726 (generate_connected_space_normal, src/enumerate_excitations.F90:158-277, then
+    # remove_repeated_states): every symmetry-allowed single and double excitation of each trial representative, mapped
+    # to its allowed HPHF representative, duplicates removed -- the trial functions themselves are still in it
+    trial = reps[above + list(choice)]
+    con = [trial[:, 0].view(np.uint64)]
+    for r in trial:
+        x = host.sing_doub_space(s, ref_ilut=r, orbsym=[int(v) for v in z["orbsym"]])[1:, 0].view(np.uint64)
+        f = ((x & np.uint64(A)) >> np.uint64(1)) | ((x & np.uint64(B)) << np.uint64(1))
+        con.append(np.where(x.view(np.int64) >= f.view(np.int64), x, f))
+    assert np.unique(np.concatenate(con)).shape[0] == g["connected_size"] == 59726
+    # the host library's HPHF elements rank the functions the same way
+    hel_h = host.get_helement(s, np.repeat(ref.reshape(1, 1), reps.shape[0], 0), reps, hphf=True)
+    assert np.allclose(hel_h, hel, rtol=1e-12, atol=1e-14)
 
 
 def test_host_hphf_elements_and_core_hamiltonian():
