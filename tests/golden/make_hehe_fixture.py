@@ -76,7 +76,17 @@ def main():
     fci_core = dict(source="test_suite/neci/rdm_singlerun/parallel/HeHe_determ (same FCIDUMP; benchmark.out...)",
                     size=int(re.search(r"Total size of deterministic space:\s+(\d+)", bench3).group(1)),
                     correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench3).group(1)))
+    # `semi-stochastic read-core`: the determinants of the checked-in CORESPACE file (occupation words) and the lowest
+    # eigenvalue the reference printed for them
+    rd = os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", "determ_read")
+    assert open(os.path.join(rd, "FCIDUMP")).read() == txt
+    bench4 = open(glob.glob(os.path.join(rd, "benchmark*"))[0]).read()
+    read_core = dict(source="test_suite/neci/determ_and_trial_spaces/determ_read (same FCIDUMP; CORESPACE, benchmark.out...)",
+                     iluts=[int(x) for x in open(os.path.join(rd, "CORESPACE")).read().split()],
+                     size=int(re.search(r"Total size of deterministic space:\s+(\d+)", bench4).group(1)),
+                     correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench4).group(1)))
     out = dict(
+        read_core=read_core,
         fci_core=fci_core,
         hphf_run=hphf_run,
         determ_doubles=dict(source="test_suite/neci/determ_and_trial_spaces/determ_doubles (same FCIDUMP; benchmark.out...)",

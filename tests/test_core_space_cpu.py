@@ -388,3 +388,25 @@ def test_fci_core_space_gives_the_reference_fci_correlation_energy():
     assert np.allclose(Ho, H, rtol=1e-12, atol=1e-13)
     # consistent with the projected energy the HPHF run of the same system converged to (statistical)
     assert abs(hii + w[0] - g["total_projected_energy"]) < 5 * g["total_projected_energy_error"] + 1e-4
+
+
+def test_read_core_space_gives_the_reference_core_energy():
+    """`semi-stochastic read-core` of the reference on the HeHe FCIDUMP (determ_read): the 100 determinants of its
+    checked-in CORESPACE file -- up to quadruple excitations of the reference, so the "more than a double excitation
+    apart" branch of the builder is exercised -- and the printed lowest eigenvalue -0.0650248789."""
+    g, s = _hehe_system()
+    ref = g["read_core"]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    il = np.array(ref["iluts"], dtype=np.int64).reshape(-1, 1)
+    assert il.shape[0] == ref["size"] == 100 and len(set(ref["iluts"])) == 100
+    assert all(bin(x).count("1") == s.nel for x in ref["iluts"])
+    refw = int(s.ilut(s.ref_orbs)[0])
+    levels = {bin(x & ~refw).count("1") for x in ref["iluts"]}
+    assert max(levels) > 2
+    il, sizes, displs = host.layout_core_space(il, np.zeros(100, dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il, hii)
+    H = np.zeros((100, 100))
+    for i in range(100):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        H[i, c["col"][sl]] = c["val"][sl]
+    assert abs(np.linalg.eigvalsh(H)[0] - ref["correlation_energy"]) < 6e-11
