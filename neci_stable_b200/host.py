@@ -431,10 +431,11 @@ def ham_apply(system, rows, cols, vec, threads=0):
     return out
 
 
-def trial_space(system, trial_iluts):
+def trial_space(system, trial_iluts, orbsym=None):
     """init_trial_wf (src/trial_wf_gen.F90) for a given trial space: the trial vector is the lowest eigenvector of H
     in that space; the connected space is every determinant outside it within two excitations of one of its members
     (generate_connected_space) with con_space_vecs_i = sum_j H_ij psiT_j != 0.
+    orbsym: ORBSYM labels (symmetry-allowed excitations only, as GenExcitations3 enumerates them); None = all equal.
     Returns (trial_iluts, trial_amps, con_iluts, con_amps, trial_energy) for neci_gpu_set_trial_space."""
     ti = _iluts(system, trial_iluts)
     nt = ti.shape[0]
@@ -442,7 +443,7 @@ def trial_space(system, trial_iluts):
     Ht = get_helement(system, ti[I], ti[J]).reshape(nt, nt)
     w, v = np.linalg.eigh(Ht)
     psi = v[:, 0].copy()
-    con = np.concatenate([sing_doub_space(system, ref_ilut=ti[k])[1:] for k in range(nt)])
+    con = np.concatenate([sing_doub_space(system, ref_ilut=ti[k], orbsym=orbsym)[1:] for k in range(nt)])
     con = np.unique(np.concatenate([ti, con]), axis=0)
     con = np.ascontiguousarray(con[~rows_in(con, ti)])            # without the trial determinants themselves
     amps = ham_apply(system, con, ti, psi)

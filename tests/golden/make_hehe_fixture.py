@@ -85,7 +85,20 @@ def main():
                      iluts=[int(x) for x in open(os.path.join(rd, "CORESPACE")).read().split()],
                      size=int(re.search(r"Total size of deterministic space:\s+(\d+)", bench4).group(1)),
                      correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench4).group(1)))
+    # trial-wavefunction twins: `doubles-trial` and `read-trial` (TRIALSPACE = the CORESPACE file above)
+    trial = {}
+    for name in ("trial_doubles", "trial_read"):
+        td = os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", name)
+        assert open(os.path.join(td, "FCIDUMP")).read() == txt
+        b = open(glob.glob(os.path.join(td, "benchmark*"))[0]).read()
+        trial[name] = dict(source="test_suite/neci/determ_and_trial_spaces/%s (same FCIDUMP; benchmark.out...)" % name,
+                           trial_size=int(re.search(r"Total size of the trial space:\s+(\d+)", b).group(1)),
+                           connected_size=int(re.search(r"Total size of connected space:\s+(\d+)", b).group(1)),
+                           trial_energy=float(re.search(r"Energy eigenvalue\(s\) of the trial space:\s+(-?[\d.]+)", b).group(1)))
+    assert open(os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", "trial_read", "TRIALSPACE")).read() == \
+        open(os.path.join(rd, "CORESPACE")).read()
     out = dict(
+        trial_runs=trial,
         read_core=read_core,
         fci_core=fci_core,
         hphf_run=hphf_run,

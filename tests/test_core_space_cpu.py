@@ -410,3 +410,32 @@ def test_read_core_space_gives_the_reference_core_energy():
         sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
         H[i, c["col"][sl]] = c["val"][sl]
     assert abs(np.linalg.eigvalsh(H)[0] - ref["correlation_energy"]) < 6e-11
+
+
+@pytest.mark.parametrize("which", ["trial_doubles", "trial_read"])
+def test_trial_space_setup_matches_the_reference_runs(which):
+    """init_trial_wf of the reference on the HeHe FCIDUMP: `doubles-trial` (69 determinants) and `read-trial` (the 100
+    determinants of the TRIALSPACE file).  host.trial_space gives the printed `Energy eigenvalue(s) of the trial
+    space` (-5.7617147894252971 / -5.7621080012308328) to 1e-12; the trial determinants together with their
+    symmetry-allowed singles and doubles are the printed 309 members of the connected space (here the whole symmetry
+    sector); and the connected-space vector is H psi_T restricted to it."""
+    g, s = _hehe_system()
+    ref = g["trial_runs"][which]
+    if which == "trial_doubles":
+        trial = host.sing_doub_space(s, orbsym=g["orbsym"])
+    else:
+        trial = np.array(g["read_core"]["iluts"], dtype=np.int64).reshape(-1, 1)
+    assert trial.shape[0] == ref["trial_size"]
+    ti, ta, ci, ca, e_t = host.trial_space(s, trial, orbsym=g["orbsym"])
+    assert abs(e_t - ref["trial_energy"]) < 1e-12
+    union = np.unique(np.concatenate([trial] + [host.sing_doub_space(s, ref_ilut=r, orbsym=g["orbsym"]) for r in trial]), axis=0)
+    assert union.shape[0] == ref["connected_size"] == 309
+    # con_space_vecs = sum_j H_ij psiT_j for every connected determinant outside the trial space
+    assert not host.rows_in(ci, ti).any() and ci.shape[0] <= 309 - trial.shape[0]
+    I = np.repeat(np.arange(ci.shape[0]), ti.shape[0]); J = np.tile(np.arange(ti.shape[0]), ci.shape[0])
+    Hct = host.get_helement(s, ci[I], ti[J]).reshape(ci.shape[0], ti.shape[0])
+    assert np.allclose(Hct @ ta, ca, rtol=1e-12, atol=1e-14)
+    # <psiT|H|psiT> = E_T and (H psiT)_i = E_T psiT_i inside the trial space
+    I = np.repeat(np.arange(ti.shape[0]), ti.shape[0]); J = np.tile(np.arange(ti.shape[0]), ti.shape[0])
+    Htt = host.get_helement(s, ti[I], ti[J]).reshape(ti.shape[0], ti.shape[0])
+    assert np.allclose(Htt @ ta, e_t * ta, atol=1e-11)
