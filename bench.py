@@ -39,9 +39,9 @@ WORKLOADS = {
     "n2_14e28o_pchb": (28, 14, 2.0e-5, "N2 cc-pVDZ-sized synthetic FCIDUMP 14e/28o, i-FCIQMC, PCHB (BASELINE configs[1])"),
     "cr2_24e30o_pchb": (30, 24, 1.0e-5, "Cr2-sized synthetic FCIDUMP 24e/30o, i-FCIQMC, PCHB (BASELINE configs[4])"),
     "semistoch_20e40o_pchb": (40, 20, 4.0e-6, "semi-stochastic i-FCIQMC on a synthetic FCIDUMP 20e/40o, PCHB, real "
-                              "coefficients, core space = the --core-size determinants of the reference's singles and "
-                              "doubles with the largest first-order weight, trial wavefunction over the --trial "
-                              "largest of them (BASELINE configs[3])"),
+                              "coefficients, core space = mp1-core <--core-size> (largest first-order amplitudes among "
+                              "the reference's singles and doubles), trial wavefunction = mp1-trial <--trial> "
+                              "(BASELINE configs[3])"),
 }
 SEMISTOCH = ("semistoch_20e40o_pchb",)
 
@@ -139,15 +139,20 @@ def random_walker_records(system, n_dets, seed, keep=None, keep_frac=1.0, chunk=
 # semi-stochastic set-up (BASELINE configs[3]): what init_semi_stochastic / init_trial_wf hand to the engine
 # ---------------------------------------------------------------------------------------------
 def semistoch_space(system, hii, params, nranks, core_size, n_trial):
-    """Core space = reference + the singles and doubles with the largest |H_0j| / (H_jj - H_00) ("all
-    singles+doubles truncated"), laid out rank-major as store_whole_core_space does; trial space = its n_trial
-    largest members.  Returns dict(iluts, sizes, displs, weights (signed first-order amplitudes), trial)."""
+    """Core space = `mp1-core <core_size>`: the reference and the singles and doubles with the largest first-order
+    amplitudes ("all singles+doubles truncated"), laid out rank-major as store_whole_core_space does; trial
+    space = `mp1-trial <n_trial>`, its largest members.  Returns dict(iluts, sizes, displs, weights (signed first-order amplitudes), trial)."""
     from neci_stable_b200 import host
     sd = host.sing_doub_space(system)
     ref = np.repeat(sd[:1], sd.shape[0], 0)
     h0 = host.get_helement(system, ref, sd)
-    hd = host.get_helement(system, sd, sd)
-    amp = -h0 / np.maximum(hd - hd[0], 1e-9)
+    # `mp1-core`: first-order amplitude H_0j / (F_00 - F_jj) with the Fock orbital energies of the reference
+    # (return_mp1_amp_and_mp2_energy, src/semi_stoch_procs.F90:2143-2218)
+    eps = fock_orbital_energies(system)
+    occ = ((sd.view(np.uint64)[:, :, None] >> np.arange(64, dtype=np.uint64)[None, None, :]) & np.uint64(1)).astype(np.float64)
+    occ = occ.reshape(sd.shape[0], -1)[:, :system.nbasis]
+    f = occ @ np.repeat(eps, 2)
+    amp = h0 / np.where(np.abs(f[0] - f) > 1e-9, f[0] - f, -1e-9)
     amp[0] = 1.0
     a = np.abs(amp)
     a[0] = np.inf                                           # the reference first
@@ -163,6 +168,25 @@ def semistoch_space(system, hii, params, nranks, core_size, n_trial):
     w = np.array([key[tuple(r)] for r in il.tolist()])
     trial = core[:n_trial].copy() if n_trial > 0 else None
     return dict(iluts=il, sizes=sizes, displs=displs, weights=w, trial=trial)
+
+
+def fock_orbital_energies(system):
+    """Diagonal Fock elements over spatial orbitals for the closed-shell reference of a synthetic FCIDUMP system:
+    eps_p = h_pp + sum_{j occupied} [2 (pp|jj) - (pj|jp)] -- what the reference takes as Arr when the FCIDUMP carries no
+    orbital energies."""
+    ns = system.nbasis // 2
+    umat, tmat, nb = system.tables["umat"], system.tables["tmat"], system.nbasis
+    tri = lambda a, b: a * (a - 1) // 2 + b if a > b else b * (b - 1) // 2 + a
+    um = lambda i, j, k, l: umat[tri(tri(i, k), tri(j, l)) - 1]          # <ij|kl>
+    nocc = system.nocc_alpha
+    assert system.nocc_alpha == system.nocc_beta
+    eps = np.zeros(ns)
+    for p in range(1, ns + 1):
+        e = tmat[(2 * p - 2) + nb * (2 * p - 2)]
+        for j in range(1, nocc + 1):
+            e += 2.0 * um(p, j, p, j) - um(p, j, j, p)
+        eps[p - 1] = e
+    return eps
 
 
 def semistoch_records(system, space, rank, l1_total):
