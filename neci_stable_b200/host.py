@@ -456,3 +456,27 @@ def rows_in(a, b):
     av = np.ascontiguousarray(a).view([("", a.dtype)] * a.shape[1]).ravel()
     bv = np.ascontiguousarray(b).view([("", b.dtype)] * b.shape[1]).ravel()
     return np.isin(av, bv)
+
+
+def cas_space(system, eps, occ_cas, virt_cas, orbsym=None):
+    """`cas-core OccCASOrbs VirtCASOrbs` / `cas-trial` (generate_cas, src/semi_stoch_gen.F90): the highest occ_cas
+    occupied and the lowest virt_cas virtual SPIN orbitals of the energy-ordered reference are active, everything below
+    stays doubly occupied; all determinants of the reference's Ms and (with orbsym) irrep.  Closed-shell references,
+    even occ_cas / virt_cas.  Returns n x nw occupation words."""
+    import itertools
+    if system.nocc_alpha != system.nocc_beta or occ_cas % 2 or virt_cas % 2:
+        raise ValueError("cas_space: closed-shell reference and even active-orbital counts only")
+    order = [int(x) + 1 for x in np.argsort(np.asarray(eps, dtype=float), kind="stable")]
+    nocc, na = system.nocc_alpha, occ_cas // 2
+    core = order[:nocc - na]
+    act = order[nocc - na: nocc + virt_cas // 2]
+    irr = (lambda orbs: 0) if orbsym is None else \
+        (lambda orbs: int(np.bitwise_xor.reduce([int(orbsym[(o + 1) // 2 - 1]) - 1 for o in orbs])))
+    target = irr([int(x) for x in system.ref_orbs])
+    out = []
+    for a in itertools.combinations(act, na):
+        for b in itertools.combinations(act, na):
+            d = sorted([2 * c for c in core] + [2 * c - 1 for c in core] + [2 * x for x in a] + [2 * x - 1 for x in b])
+            if irr(d) == target:
+                out.append(system.ilut(d))
+    return np.array(out, dtype=np.int64).reshape(len(out), system.nw)

@@ -87,7 +87,7 @@ def main():
                      correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench4).group(1)))
     # trial-wavefunction twins: `doubles-trial` and `read-trial` (TRIALSPACE = the CORESPACE file above)
     trial = {}
-    for name in ("trial_doubles", "trial_read"):
+    for name in ("trial_doubles", "trial_read", "trial_cas"):
         td = os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", name)
         assert open(os.path.join(td, "FCIDUMP")).read() == txt
         b = open(glob.glob(os.path.join(td, "benchmark*"))[0]).read()
@@ -97,7 +97,17 @@ def main():
                            trial_energy=float(re.search(r"Energy eigenvalue\(s\) of the trial space:\s+(-?[\d.]+)", b).group(1)))
     assert open(os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", "trial_read", "TRIALSPACE")).read() == \
         open(os.path.join(rd, "CORESPACE")).read()
+    # `cas-core 2 6` / `cas-trial 2 6`
+    cd = os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", "determ_cas")
+    assert open(os.path.join(cd, "FCIDUMP")).read() == txt
+    b5 = open(glob.glob(os.path.join(cd, "benchmark*"))[0]).read()
+    inp5 = open(os.path.join(cd, "neci.inp")).read()
+    cas_core = dict(source="test_suite/neci/determ_and_trial_spaces/determ_cas (same FCIDUMP; benchmark.out...)",
+                    cas=[int(x) for x in re.search(r"cas-core\s+(\d+)\s+(\d+)", inp5).groups()],
+                    size=int(re.search(r"Total size of deterministic space:\s+(\d+)", b5).group(1)),
+                    correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", b5).group(1)))
     out = dict(
+        cas_core=cas_core,
         trial_runs=trial,
         read_core=read_core,
         fci_core=fci_core,

@@ -439,3 +439,26 @@ def test_trial_space_setup_matches_the_reference_runs(which):
     I = np.repeat(np.arange(ti.shape[0]), ti.shape[0]); J = np.tile(np.arange(ti.shape[0]), ti.shape[0])
     Htt = host.get_helement(s, ti[I], ti[J]).reshape(ti.shape[0], ti.shape[0])
     assert np.allclose(Htt @ ta, e_t * ta, atol=1e-11)
+
+
+def test_cas_core_and_cas_trial_match_the_reference_runs():
+    """`cas-core 2 6` and `cas-trial 2 6` of the reference on the HeHe FCIDUMP: 8 determinants, printed core
+    correlation energy -0.0095421747, printed trial energy -5.7066252970297464 (to 1e-12) and 187 members of the
+    connected space."""
+    g, s = _hehe_system()
+    ref, tref = g["cas_core"], g["trial_runs"]["trial_cas"]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    cas = host.cas_space(s, g["eps"], ref["cas"][0], ref["cas"][1], orbsym=g["orbsym"])
+    assert cas.shape[0] == ref["size"] == tref["trial_size"] == 8
+    assert host.rows_in(s.ilut(s.ref_orbs).reshape(1, -1), cas)[0]
+    il, sizes, displs = host.layout_core_space(cas, np.zeros(8, dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il, hii)
+    H = np.zeros((8, 8))
+    for i in range(8):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        H[i, c["col"][sl]] = c["val"][sl]
+    assert abs(np.linalg.eigvalsh(H)[0] - ref["correlation_energy"]) < 6e-11
+    ti, ta, ci, ca, e_t = host.trial_space(s, cas, orbsym=g["orbsym"])
+    assert abs(e_t - tref["trial_energy"]) < 1e-12
+    union = np.unique(np.concatenate([cas] + [host.sing_doub_space(s, ref_ilut=r, orbsym=g["orbsym"]) for r in cas]), axis=0)
+    assert union.shape[0] == tref["connected_size"] == 187
