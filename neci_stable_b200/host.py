@@ -480,3 +480,22 @@ def cas_space(system, eps, occ_cas, virt_cas, orbsym=None):
             if irr(d) == target:
                 out.append(system.ilut(d))
     return np.array(out, dtype=np.int64).reshape(len(out), system.nw)
+
+
+def optimised_space(system, cutoff_num=None, cutoff_amp=None, orbsym=None):
+    """`optimised-core` / `optimised-trial` (generate_optimised_space, src/semi_stoch_gen.F90:824-1029): starting from
+    the reference, each loop takes the space connected to the current one (its determinants and their allowed singles
+    and doubles), finds the ground state of H in it and keeps the cutoff_num[k] determinants of largest amplitude, or
+    those with |amplitude| above cutoff_amp[k] (eigenvector normalised to 1).  Returns n x nw occupation words."""
+    if (cutoff_num is None) == (cutoff_amp is None):
+        raise ValueError("optimised_space: give cutoff_num or cutoff_amp")
+    space = _iluts(system, system.ilut(system.ref_orbs))
+    for k in range(len(cutoff_num if cutoff_num is not None else cutoff_amp)):
+        con = np.unique(np.concatenate([space] + [sing_doub_space(system, ref_ilut=r, orbsym=orbsym) for r in space]), axis=0)
+        n = con.shape[0]
+        I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+        w, v = np.linalg.eigh(get_helement(system, con[I], con[J]).reshape(n, n))
+        a = np.abs(v[:, 0])
+        keep = np.argsort(-a, kind="stable")[:int(cutoff_num[k])] if cutoff_num is not None else np.nonzero(a > cutoff_amp[k])[0]
+        space = np.ascontiguousarray(con[np.sort(keep)])
+    return space

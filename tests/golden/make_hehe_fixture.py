@@ -87,11 +87,14 @@ def main():
                      correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", bench4).group(1)))
     # trial-wavefunction twins: `doubles-trial` and `read-trial` (TRIALSPACE = the CORESPACE file above)
     trial = {}
-    for name in ("trial_doubles", "trial_read", "trial_cas"):
+    for name in ("trial_doubles", "trial_read", "trial_cas", "trial_opt_num", "trial_opt_amp"):
         td = os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", name)
         assert open(os.path.join(td, "FCIDUMP")).read() == txt
         b = open(glob.glob(os.path.join(td, "benchmark*"))[0]).read()
-        trial[name] = dict(source="test_suite/neci/determ_and_trial_spaces/%s (same FCIDUMP; benchmark.out...)" % name,
+        ti = open(os.path.join(td, "neci.inp")).read()
+        cut = re.search(r"optimised-trial-cutoff-(num|amp)\s+([\d.\s]+)\n", ti)
+        trial[name] = dict(cutoff=None if not cut else [cut.group(1)] + [float(x) for x in cut.group(2).split()],
+                           source="test_suite/neci/determ_and_trial_spaces/%s (same FCIDUMP; benchmark.out...)" % name,
                            trial_size=int(re.search(r"Total size of the trial space:\s+(\d+)", b).group(1)),
                            connected_size=int(re.search(r"Total size of connected space:\s+(\d+)", b).group(1)),
                            trial_energy=float(re.search(r"Energy eigenvalue\(s\) of the trial space:\s+(-?[\d.]+)", b).group(1)))
@@ -106,7 +109,19 @@ def main():
                     cas=[int(x) for x in re.search(r"cas-core\s+(\d+)\s+(\d+)", inp5).groups()],
                     size=int(re.search(r"Total size of deterministic space:\s+(\d+)", b5).group(1)),
                     correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", b5).group(1)))
+    # `optimised-core` with cut-offs by number and by amplitude
+    opt = {}
+    for name in ("determ_opt_num", "determ_opt_amp"):
+        od = os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", name)
+        assert open(os.path.join(od, "FCIDUMP")).read() == txt
+        b = open(glob.glob(os.path.join(od, "benchmark*"))[0]).read()
+        cut = re.search(r"optimised-core-cutoff-(num|amp)\s+([\d.\s]+)\n", open(os.path.join(od, "neci.inp")).read())
+        opt[name] = dict(source="test_suite/neci/determ_and_trial_spaces/%s (same FCIDUMP; benchmark.out...)" % name,
+                         cutoff=[cut.group(1)] + [float(x) for x in cut.group(2).split()],
+                         size=int(re.search(r"Total size of deterministic space:\s+(\d+)", b).group(1)),
+                         correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", b).group(1)))
     out = dict(
+        optimised_core=opt,
         cas_core=cas_core,
         trial_runs=trial,
         read_core=read_core,

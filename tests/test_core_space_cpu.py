@@ -462,3 +462,31 @@ def test_cas_core_and_cas_trial_match_the_reference_runs():
     assert abs(e_t - tref["trial_energy"]) < 1e-12
     union = np.unique(np.concatenate([cas] + [host.sing_doub_space(s, ref_ilut=r, orbsym=g["orbsym"]) for r in cas]), axis=0)
     assert union.shape[0] == tref["connected_size"] == 187
+
+
+@pytest.mark.parametrize("which", ["determ_opt_num", "determ_opt_amp", "trial_opt_num", "trial_opt_amp"])
+def test_optimised_spaces_match_the_reference_runs(which):
+    """`optimised-core` / `optimised-trial` of the reference on the HeHe FCIDUMP (connected space -> ground state ->
+    keep by number 3/6/60 and 4/20/80, or by amplitude 0.02/0.002 and 0.001): sizes 60 / 44 / 80 / 53 and the printed
+    core correlation energies (-0.0647917270, -0.0646041982) and trial energies (-5.7620482067956624,
+    -5.7617005825505965, to 1e-12) from host.optimised_space + core_hamiltonian / trial_space."""
+    g, s = _hehe_system()
+    hii = driver.diag_energy(s, s.ref_orbs)
+    ref = g["optimised_core"][which] if which.startswith("determ") else g["trial_runs"][which]
+    kind, cuts = ref["cutoff"][0], ref["cutoff"][1:]
+    space = host.optimised_space(s, cutoff_num=[int(x) for x in cuts] if kind == "num" else None,
+                                 cutoff_amp=cuts if kind == "amp" else None, orbsym=g["orbsym"])
+    if which.startswith("determ"):
+        assert space.shape[0] == ref["size"]
+        il, sizes, displs = host.layout_core_space(space, np.zeros(space.shape[0], dtype=np.int32), 1)
+        c = host.core_hamiltonian(s, il, hii)
+        n = il.shape[0]
+        H = np.zeros((n, n))
+        for i in range(n):
+            sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+            H[i, c["col"][sl]] = c["val"][sl]
+        assert abs(np.linalg.eigvalsh(H)[0] - ref["correlation_energy"]) < 6e-11
+    else:
+        assert space.shape[0] == ref["trial_size"]
+        e_t = host.trial_space(s, space, orbsym=g["orbsym"])[4]
+        assert abs(e_t - ref["trial_energy"]) < 1e-12
