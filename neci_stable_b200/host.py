@@ -499,3 +499,30 @@ def optimised_space(system, cutoff_num=None, cutoff_amp=None, orbsym=None):
         keep = np.argsort(-a, kind="stable")[:int(cutoff_num[k])] if cutoff_num is not None else np.nonzero(a > cutoff_amp[k])[0]
         space = np.ascontiguousarray(con[np.sort(keep)])
     return space
+
+
+def ras_space(system, eps, ras1, ras2, ras3, min1, max3, orbsym=None):
+    """`ras-core ras1 ras2 ras3 min1 max3` / `ras-trial` (generate_ras, src/semi_stoch_gen.F90): the energy-ordered
+    spatial orbitals are split into RAS1 (the first ras1), RAS2 (the next ras2) and RAS3 (the next ras3); all
+    determinants of the reference's Ms (and irrep, with orbsym) with at least min1 electrons in RAS1 and at most max3 in
+    RAS3.  Plain enumeration of the Ms sector: for the small systems such spaces are used on."""
+    import itertools
+    ns = system.nbasis // 2
+    if ras1 + ras2 + ras3 != ns:
+        raise ValueError("ras_space: the three spaces must cover all %d spatial orbitals" % ns)
+    order = [int(x) + 1 for x in np.argsort(np.asarray(eps, dtype=float), kind="stable")]
+    r1, r3 = set(order[:ras1]), set(order[ras1 + ras2:])
+    irr = (lambda orbs: 0) if orbsym is None else \
+        (lambda orbs: int(np.bitwise_xor.reduce([int(orbsym[(o + 1) // 2 - 1]) - 1 for o in orbs])))
+    target = irr([int(x) for x in system.ref_orbs])
+    out = []
+    for a in itertools.combinations(range(1, ns + 1), system.nocc_alpha):
+        for b in itertools.combinations(range(1, ns + 1), system.nocc_beta):
+            n1 = sum(1 for x in a if x in r1) + sum(1 for x in b if x in r1)
+            n3 = sum(1 for x in a if x in r3) + sum(1 for x in b if x in r3)
+            if n1 < min1 or n3 > max3:
+                continue
+            d = sorted([2 * x for x in a] + [2 * x - 1 for x in b])
+            if irr(d) == target:
+                out.append(system.ilut(d))
+    return np.array(out, dtype=np.int64).reshape(len(out), system.nw)

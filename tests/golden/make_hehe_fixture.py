@@ -120,7 +120,16 @@ def main():
                          cutoff=[cut.group(1)] + [float(x) for x in cut.group(2).split()],
                          size=int(re.search(r"Total size of deterministic space:\s+(\d+)", b).group(1)),
                          correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", b).group(1)))
+    # `ras-core 2 0 8 1 3`
+    rsd = os.path.join(REF, "test_suite", "neci", "determ_and_trial_spaces", "determ_ras")
+    assert open(os.path.join(rsd, "FCIDUMP")).read() == txt
+    b6 = open(glob.glob(os.path.join(rsd, "benchmark*"))[0]).read()
+    ras_core = dict(source="test_suite/neci/determ_and_trial_spaces/determ_ras (same FCIDUMP; benchmark.out...)",
+                    ras=[int(x) for x in re.search(r"ras-core\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d+)", open(os.path.join(rsd, "neci.inp")).read()).groups()],
+                    size=int(re.search(r"Total size of deterministic space:\s+(\d+)", b6).group(1)),
+                    correlation_energy=float(re.search(r"Deterministic subspace correlation energy:\s+(-?[\d.]+)", b6).group(1)))
     out = dict(
+        ras_core=ras_core,
         optimised_core=opt,
         cas_core=cas_core,
         trial_runs=trial,

@@ -490,3 +490,21 @@ def test_optimised_spaces_match_the_reference_runs(which):
         assert space.shape[0] == ref["trial_size"]
         e_t = host.trial_space(s, space, orbsym=g["orbsym"])[4]
         assert abs(e_t - ref["trial_energy"]) < 1e-12
+
+
+def test_ras_core_matches_the_reference_run():
+    """`ras-core 2 0 8 1 3` of the reference on the HeHe FCIDUMP: 197 determinants and the printed core correlation
+    energy -0.0646451087 from host.ras_space + core_hamiltonian."""
+    g, s = _hehe_system()
+    ref = g["ras_core"]
+    hii = driver.diag_energy(s, s.ref_orbs)
+    space = host.ras_space(s, g["eps"], *ref["ras"], orbsym=g["orbsym"])
+    assert space.shape[0] == ref["size"] == 197
+    il, sizes, displs = host.layout_core_space(space, np.zeros(space.shape[0], dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il, hii)
+    n = il.shape[0]
+    H = np.zeros((n, n))
+    for i in range(n):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        H[i, c["col"][sl]] = c["val"][sl]
+    assert abs(np.linalg.eigvalsh(H)[0] - ref["correlation_energy"]) < 6e-11
