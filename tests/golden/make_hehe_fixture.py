@@ -139,6 +139,9 @@ def main():
         determ_doubles=dict(source="test_suite/neci/determ_and_trial_spaces/determ_doubles (same FCIDUMP; benchmark.out...)",
                             n_doubles_from_reference=int(sd_counts.group(1)), n_singles_from_reference=int(sd_counts.group(2)),
                             core_correlation_energy=e_core, start_walkers=10000.0, tau=0.01,
+                            projected_correlation_energy=float(re.search(r"Projected correlation energy\s+(-?[\d.]+)", bench2).group(1)),
+                            projected_correlation_energy_error=float(re.search(r"Estimated error in Projected correlation energy\s+([\d.Ee+-]+)", bench2).group(1)),
+                            nmcyc=400, total_walkers=10000, add_to_initiator=2.0, real_spawn_cutoff=0.01, steps_shift=1,
                             step1_proj_e=f[7], step1_no_at_hf=f[10], step1_no_at_doubs=f[11],
                             shift_damp=0.5, step2_shift=rows[2][0], step2_no_at_hf=rows[2][10], step2_no_at_doubs=rows[2][11],
                             step3_no_at_hf=rows[3][10]),
