@@ -16,4 +16,12 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
     python bench.py $W --no-e2e --steps 3 --warmup 3 > gpurun_out/r02_ncu_launches.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_determ_spmv -s 3 -c 1 -f -o gpurun_out/r02_k3_full \
     python bench.py $W --no-e2e --steps 3 --warmup 3 > gpurun_out/r02_ncu_k3.log 2>&1
+# 4. launch-bound variants of the spawning kernel, if they were built in the container beforehand
+#    (python -c "from neci_stable_b200 import _build; _build.build_gpu_variant('ctas5', ['K1_CTAS_PER_SM=5'])")
+for v in ctas5 ctas6; do
+    if [ -f neci_stable_b200/libneci_gpu_$v.so ]; then
+        NECI_GPU_LIB=$PWD/neci_stable_b200/libneci_gpu_$v.so timeout 300 python bench.py --no-e2e --no-cpu-baseline \
+            > gpurun_out/r02_bench_$v.json 2> gpurun_out/r02_bench_$v.err
+    fi
+done
 for f in gpurun_out/r02_bench*.json; do echo "== $f"; head -c 400 "$f"; echo; done
