@@ -526,3 +526,15 @@ def ras_space(system, eps, ras1, ras2, ras3, min1, max3, orbsym=None):
             if irr(d) == target:
                 out.append(system.ilut(d))
     return np.array(out, dtype=np.int64).reshape(len(out), system.nw)
+
+
+def most_populated_space(dets, n, nw=1):
+    """`pops-core n` / `pops-trial n` (generate_space_most_populated, src/semi_stoch_gen.F90:1031-1221): the n
+    determinants of a walker list (CurrentDets records, e.g. from neci_gpu_download_occupied) with the largest |sign|;
+    determinants below 1e-8 are never taken, fewer than n are returned if the list is shorter.  Returns (n x nw
+    occupation words, their signs)."""
+    d = np.asarray(dets, dtype=np.int64).reshape(-1, nw + 2)
+    sg = signs_of(d, nw)
+    ok = np.nonzero(np.abs(sg) >= 1.e-8)[0]
+    pick = ok[np.argsort(-np.abs(sg[ok]), kind="stable")[:int(n)]]
+    return np.ascontiguousarray(d[pick, :nw]), sg[pick].copy()

@@ -312,6 +312,7 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
 
 // determ_projection, src/semi_stoch_procs.F90:105-241 (after the host-side gather)
 void determ_projection(orc_engine &e, double tau, double DiagSft) {
+    if (e.n_core_total == 0) return;
     const int64_t displ = e.core_displs[e.cfg.rank];
     for (int64_t i = 0; i < e.n_core_local; ++i) {
         double acc = 0.0;
@@ -693,7 +694,7 @@ int orc_world_iterate(orc_engine **es, int32_t n, double tau, double diag_sft, i
         for (auto &t : th) t.join();
     };
     par([&](int r) { spawn_phase(*es[r], tau, diag_sft, iter); });
-    if (es[0]->cfg.t_semi_stochastic) {
+    if (es[0]->cfg.t_semi_stochastic && es[0]->n_core_total > 0) {     // no core space handed over yet: nothing to project
         std::vector<double> full(es[0]->n_core_total);
         for (int r = 0; r < n; ++r)
             std::memcpy(&full[es[r]->core_displs[r]], es[r]->partial_determ_vecs.data(), es[r]->n_core_local * 8);

@@ -549,3 +549,34 @@ def test_determ_doubles_run_on_the_oracle_agrees_with_the_reference_run():
     assert abs(e - ref["projected_correlation_energy"]) < tol, (e, err, ref["projected_correlation_energy"])
     assert abs(e - g["fci_core"]["correlation_energy"]) < tol + 2.5e-5
     assert 0.8 * ref["total_walkers"] < hist[-1]["tot_parts"] < 1.3 * ref["total_walkers"]
+
+
+def test_pops_core_from_a_running_list_and_switch_to_semi_stochastic():
+    """`pops-core`: after a stochastic warm-up on the oracle the most populated determinants become the core space
+    (host.most_populated_space on the downloaded list), their rows are built by the host library and the run continues
+    semi-stochastically -- the dynamic core-space flow of the reference (semistoch-shift-iter) with this repo's host."""
+    s = host.random_fcidump_system(6, 6, sparse=0.9, sparse_t=0.9, seed=3)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, _ = helpers.make_pair(s, hii, max_walkers=50000, max_spawned=50000, semi_stochastic=True, all_real_coeff=True, seed=5)
+    o.upload_walkers(host.record(s, s.ref_orbs, 2000.0, 1 << capi.FLAG_INITIATOR).reshape(1, -1))
+    for it in range(1, 60):
+        o.iterate(0.002, 0.0, it)
+    d, gd, go = o.download_walkers()
+    d = d[np.abs(host.signs_of(d, s.nw)) > 0]
+    core, amps = host.most_populated_space(d, 40, nw=s.nw)
+    assert core.shape[0] == 40 and np.all(np.diff(np.abs(amps)) <= 0)
+    assert np.abs(amps[-1]) >= np.sort(np.abs(host.signs_of(d, s.nw)))[-40]
+    il, sizes, displs = host.layout_core_space(core, np.zeros(40, dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il, hii)
+    # flag the chosen determinants in the list and hand the core space over
+    keys = {tuple(r) for r in il.tolist()}
+    for k in range(d.shape[0]):
+        if tuple(d[k, :s.nw].tolist()) in keys:
+            d[k, s.nw + 1] |= (1 << capi.FLAG_DETERMINISTIC) | (1 << capi.FLAG_INITIATOR)
+    o.upload_walkers(d)
+    o.set_core_space(c["row_ptr"], c["col"], c["val"], sizes, displs, il)
+    tot = np.abs(host.signs_of(d, s.nw)).sum()
+    for it in range(60, 80):
+        st = o.iterate(0.002, 0.0, it)
+    assert st[ST["NORM_SEMISTOCH_SQ"]] > 0.5 * st[ST["NORM_PSI_SQ"]]       # the core space carries most of the norm
+    assert 0.5 * tot < st[ST["TOTPARTS"]] < 3.0 * tot
