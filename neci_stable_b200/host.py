@@ -431,22 +431,49 @@ def ham_apply(system, rows, cols, vec, threads=0):
     return out
 
 
-def trial_space(system, trial_iluts, orbsym=None):
+def hphf_representative(iluts):
+    """The allowed HPHF representative of every determinant (IsAllowedHPHF, src/DetBitOps.F90:693-718): the larger of
+    the determinant and its spin-flipped partner in the signed word order of DetBitLT, word 0 first."""
+    x = np.ascontiguousarray(iluts, dtype=np.int64).view(np.uint64)
+    A, B = np.uint64(0xAAAAAAAAAAAAAAAA), np.uint64(0x5555555555555555)
+    f = ((x & A) >> np.uint64(1)) | ((x & B) << np.uint64(1))
+    xs, fs = x.view(np.int64), f.view(np.int64)
+    take_x = np.ones(x.shape[0], dtype=bool)
+    decided = np.zeros(x.shape[0], dtype=bool)
+    for w in range(x.shape[1]):
+        gt, lt = (xs[:, w] > fs[:, w]) & ~decided, (xs[:, w] < fs[:, w]) & ~decided
+        take_x[lt] = False
+        decided |= gt | lt
+    return np.where(take_x[:, None], xs, fs)
+
+
+def trial_space(system, trial_iluts, orbsym=None, hphf=False):
     """init_trial_wf (src/trial_wf_gen.F90) for a given trial space: the trial vector is the lowest eigenvector of H
     in that space; the connected space is every determinant outside it within two excitations of one of its members
     (generate_connected_space) with con_space_vecs_i = sum_j H_ij psiT_j != 0.
     orbsym: ORBSYM labels (symmetry-allowed excitations only, as GenExcitations3 enumerates them); None = all equal.
+    hphf: trial_iluts are allowed HPHF representatives and H acts between HPHF functions.
     Returns (trial_iluts, trial_amps, con_iluts, con_amps, trial_energy) for neci_gpu_set_trial_space."""
     ti = _iluts(system, trial_iluts)
     nt = ti.shape[0]
     I = np.repeat(np.arange(nt), nt); J = np.tile(np.arange(nt), nt)
-    Ht = get_helement(system, ti[I], ti[J]).reshape(nt, nt)
+    Ht = get_helement(system, ti[I], ti[J], hphf=hphf).reshape(nt, nt)
     w, v = np.linalg.eigh(Ht)
     psi = v[:, 0].copy()
     con = np.concatenate([sing_doub_space(system, ref_ilut=ti[k], orbsym=orbsym)[1:] for k in range(nt)])
+    if hphf:                                  # generate_connection_normal: excitations of the representative, mapped
+        con = hphf_representative(con)        # to their own allowed representatives (enumerate_excitations.F90:310-316)
     con = np.unique(np.concatenate([ti, con]), axis=0)
     con = np.ascontiguousarray(con[~rows_in(con, ti)])            # without the trial determinants themselves
-    amps = ham_apply(system, con, ti, psi)
+    if hphf:
+        amps = np.zeros(con.shape[0])
+        step = max(1, (1 << 22) // max(nt, 1))
+        for lo in range(0, con.shape[0], step):
+            blk = con[lo:lo + step]
+            I = np.repeat(np.arange(blk.shape[0]), nt); J = np.tile(np.arange(nt), blk.shape[0])
+            amps[lo:lo + step] = get_helement(system, blk[I], ti[J], hphf=True).reshape(blk.shape[0], nt) @ psi
+    else:
+        amps = ham_apply(system, con, ti, psi)
     keep = np.abs(amps) > 0
     return ti, psi, np.ascontiguousarray(con[keep]), amps[keep], float(w[0])
 

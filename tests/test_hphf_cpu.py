@@ -206,6 +206,16 @@ def test_mp1_core_and_trial_spaces_match_the_reference_ne_run():
         f = ((x & np.uint64(A)) >> np.uint64(1)) | ((x & np.uint64(B)) << np.uint64(1))
         con.append(np.where(x.view(np.int64) >= f.view(np.int64), x, f))
     assert np.unique(np.concatenate(con)).shape[0] == g["connected_size"] == 59726
+    # the product function for the same set-up: trial vector, connected space and its vector in one call
+    ti, ta, ci, ca, e_t = host.trial_space(s, trial, orbsym=[int(v) for v in z["orbsym"]], hphf=True)
+    assert abs(e_t - g["trial_energy"]) < 1e-12
+    assert not host.rows_in(ci, ti).any() and np.array_equal(host.hphf_representative(ci), ci)
+    n_zero = g["connected_size"] - trial.shape[0] - ci.shape[0]       # connected functions whose vector entry vanishes
+    assert 0 <= n_zero < 0.2 * g["connected_size"]
+    k = np.random.default_rng(1).integers(0, ci.shape[0], 40)
+    I = np.repeat(np.arange(40), ti.shape[0]); J = np.tile(np.arange(ti.shape[0]), 40)
+    want = o.probe_helement(ci[k][I], ti[J]).reshape(40, ti.shape[0]) @ ta
+    assert np.allclose(ca[k], want, rtol=1e-11, atol=1e-13)
     # the host library's HPHF elements rank the functions the same way
     hel_h = host.get_helement(s, np.repeat(ref.reshape(1, 1), reps.shape[0], 0), reps, hphf=True)
     assert np.allclose(hel_h, hel, rtol=1e-12, atol=1e-14)
