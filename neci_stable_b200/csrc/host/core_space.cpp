@@ -58,9 +58,18 @@ struct Ham {
     int nel, nb, nw;
     const double *umat, *tmat;
     double ecore;
+    // k-space Hubbard instead of tabulated integrals (ksum != NULL): <ij|kl> = U/N if k_i + k_j = k_k + k_l
+    // (get_umat_kspace, UMAT(1) = UHUB/OMEGA), h_pp = eps(k_p); spatial orbital s has k index s - 1
+    const int32_t *ksum = nullptr; int nk = 0; double u_over_n = 0.0; const double *eps_k = nullptr;
     // <ij|kl> over 1-based spatial orbitals, UMatInd (src/UMatCache.F90:257-296)
-    inline double um(int i, int j, int k, int l) const { return umat[tri(tri(i, k), tri(j, l)) - 1]; }
-    inline double tm(int a, int b) const { return tmat[(size_t)a + (size_t)nb * b]; }     // 0-based spin orbitals
+    inline double um(int i, int j, int k, int l) const {
+        if (ksum) return (ksum[(i - 1) * nk + (j - 1)] == ksum[(k - 1) * nk + (l - 1)]) ? u_over_n : 0.0;
+        return umat[tri(tri(i, k), tri(j, l)) - 1];
+    }
+    inline double tm(int a, int b) const {                                                // 0-based spin orbitals
+        if (ksum) return (a == b) ? eps_k[a >> 1] : 0.0;
+        return tmat[(size_t)a + (size_t)nb * b];
+    }
     static inline int sp(int b) { return (b >> 1) + 1; }                                 // spatial index of bit b
     static inline bool same_spin(int a, int b) { return ((a ^ b) & 1) == 0; }
 
@@ -292,11 +301,37 @@ int neci_host_det_node(int32_t nbasis, const int32_t *random_orb_index, int32_t 
 // Sparse core Hamiltonian rows [displ, displ + n_local) over the whole core space `iluts` (n_core x nw, the
 // rank-major order of store_whole_core_space).  Returns an opaque job (NULL on error) and its nnz; the rows are
 // copied out and the job freed by neci_host_core_ham_fetch.  n_threads <= 0: all hardware threads.
+static void *core_ham_job(Ham &H, double hii, const int64_t *iluts, int64_t n_core, int64_t displ, int64_t n_local,
+                          int32_t n_threads, int32_t hphf, int64_t *nnz_out);
+
 void *neci_host_core_ham_build(int32_t nel, int32_t nbasis, const double *umat, const double *tmat, double ecore,
                                double hii, const int64_t *iluts, int64_t n_core, int64_t displ, int64_t n_local,
                                int32_t n_threads, int32_t hphf, int64_t *nnz_out) {
     if (nbasis > 128 || displ < 0 || n_local < 0 || displ + n_local > n_core || n_core > 0x7fffffffll) return nullptr;
     Ham H{nel, nbasis, nbasis / 64 + 1, umat, tmat, ecore};
+    return core_ham_job(H, hii, iluts, n_core, displ, n_local, n_threads, hphf, nnz_out);
+}
+
+// the same for the k-space Hubbard Hamiltonian (tables as neci_gpu_set_system_hubbard_k takes them)
+void *neci_host_core_ham_build_hubbard_k(int32_t nel, int32_t nbasis, int32_t n_k, const int32_t *ksum, const double *eps_k,
+                                         double u_over_n, double hii, const int64_t *iluts, int64_t n_core, int64_t displ,
+                                         int64_t n_local, int32_t n_threads, int64_t *nnz_out) {
+    if (nbasis > 128 || nbasis != 2 * n_k || displ < 0 || n_local < 0 || displ + n_local > n_core || n_core > 0x7fffffffll) return nullptr;
+    Ham H{nel, nbasis, nbasis / 64 + 1, nullptr, nullptr, 0.0};
+    H.ksum = ksum; H.nk = n_k; H.u_over_n = u_over_n; H.eps_k = eps_k;
+    return core_ham_job(H, hii, iluts, n_core, displ, n_local, n_threads, 0, nnz_out);
+}
+int neci_host_get_helement_hubbard_k(int32_t nel, int32_t nbasis, int32_t n_k, const int32_t *ksum, const double *eps_k,
+                                     double u_over_n, const int64_t *iluts_i, const int64_t *iluts_j, int64_t n, double *out) {
+    if (nbasis > 128 || nbasis != 2 * n_k) return 1;
+    Ham H{nel, nbasis, nbasis / 64 + 1, nullptr, nullptr, 0.0};
+    H.ksum = ksum; H.nk = n_k; H.u_over_n = u_over_n; H.eps_k = eps_k;
+    for (int64_t k = 0; k < n; ++k) out[k] = H.element(H.load(iluts_i + k * H.nw), H.load(iluts_j + k * H.nw));
+    return 0;
+}
+
+static void *core_ham_job(Ham &H, double hii, const int64_t *iluts, int64_t n_core, int64_t displ, int64_t n_local,
+                          int32_t n_threads, int32_t hphf, int64_t *nnz_out) {
     H.build_single_tables();
     std::vector<Det2> D((size_t)n_core);
     for (int64_t k = 0; k < n_core; ++k) D[k] = H.load(iluts + k * H.nw);

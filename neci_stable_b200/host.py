@@ -319,14 +319,41 @@ def _iluts(system, iluts):
     return np.ascontiguousarray(np.asarray(iluts, dtype=np.int64).reshape(-1, system.nw))
 
 
+def _integral_tables(system):
+    """UMAT / TMAT2D of a system for the host library: as they are for FCIDUMP systems; for the real-space Hubbard
+    model the on-site repulsion <ii|ii> = U in UMatInd packing beside its hopping matrix."""
+    if system.kind == capi.SYS_FCIDUMP_PCHB:
+        return system.tables
+    if system.kind == capi.SYS_HUBBARD_RS:
+        if "umat" not in system.tables:
+            ns = system.nbasis // 2
+            umat = np.zeros(lib().neci_host_umat_size(C.c_int32(ns)))
+            for i in range(1, ns + 1):
+                p = i * (i - 1) // 2 + i                       # tri(i, i)
+                umat[p * (p - 1) // 2 + p - 1] = system.tables["uhub"]
+            system.tables["umat"] = umat
+        return system.tables
+    raise ValueError("no tabulated integrals for this system kind")
+
+
 def get_helement(system, iluts_i, iluts_j, hphf=False):
     """get_helement (src/Determinants.F90:508-554) for pairs of determinants of an FCIDUMP system, on the host;
     hphf: between HPHF functions given by their allowed representatives (src/HPHFIntegrals.fpp)."""
-    if system.kind != capi.SYS_FCIDUMP_PCHB:
-        raise ValueError("host get_helement: FCIDUMP systems only")
     a, b = _iluts(system, iluts_i), _iluts(system, iluts_j)
     out = np.zeros(a.shape[0])
-    t = system.tables
+    if system.kind == capi.SYS_HUBBARD_K:
+        if hphf:
+            raise ValueError("host get_helement: no HPHF functions for the lattice models")
+        t = system.tables
+        ks, ek = np.ascontiguousarray(t["ksum"], dtype=np.int32), np.ascontiguousarray(t["eps_k"], dtype=np.float64)
+        rc = lib().neci_host_get_helement_hubbard_k(C.c_int32(system.nel), C.c_int32(system.nbasis), C.c_int32(t["n_k"]),
+                                                    _p(ks, C.c_int32), _p(ek, C.c_double), C.c_double(t["u_over_n"]),
+                                                    _p(a, C.c_int64), _p(b, C.c_int64), C.c_int64(a.shape[0]),
+                                                    _p(out, C.c_double))
+        if rc:
+            raise RuntimeError("neci_host_get_helement_hubbard_k failed (%d)" % rc)
+        return out
+    t = _integral_tables(system)
     fn = lib().neci_host_get_helement_hphf if hphf else lib().neci_host_get_helement
     rc = fn(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
                                       _p(t["tmat"], C.c_double), C.c_double(system.ecore), _p(a, C.c_int64),
@@ -392,18 +419,25 @@ def core_hamiltonian(system, core_iluts, hii, displ=0, n_local=None, threads=0, 
     """Sparse core Hamiltonian rows of one rank (calc_determ_hamil_sparse / _hphf, src/sparse_arrays.F90:426-690; each row:
     the non-zero off-diagonal elements, then H_ii - Hii last as src/fast_determ_hamil.F90:1494-1507 leaves it).
     Returns dict(row_ptr int64, col int32, val float64) for neci_gpu_set_core_space."""
-    if system.kind != capi.SYS_FCIDUMP_PCHB:
-        raise ValueError("host core_hamiltonian: FCIDUMP systems only")
     il = _iluts(system, core_iluts)
     n_core = il.shape[0]
     n_local = n_core - displ if n_local is None else int(n_local)
-    t = system.tables
     nnz = C.c_int64(0)
     L = lib()
-    h = L.neci_host_core_ham_build(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
-                                   _p(t["tmat"], C.c_double), C.c_double(system.ecore), C.c_double(hii),
-                                   _p(il, C.c_int64), C.c_int64(n_core), C.c_int64(int(displ)), C.c_int64(n_local),
-                                   C.c_int32(int(threads)), C.c_int32(int(bool(hphf))), C.byref(nnz))
+    if system.kind == capi.SYS_HUBBARD_K:
+        t = system.tables
+        ks, ek = np.ascontiguousarray(t["ksum"], dtype=np.int32), np.ascontiguousarray(t["eps_k"], dtype=np.float64)
+        L.neci_host_core_ham_build_hubbard_k.restype = C.c_void_p
+        h = L.neci_host_core_ham_build_hubbard_k(C.c_int32(system.nel), C.c_int32(system.nbasis), C.c_int32(t["n_k"]),
+                                                 _p(ks, C.c_int32), _p(ek, C.c_double), C.c_double(t["u_over_n"]),
+                                                 C.c_double(hii), _p(il, C.c_int64), C.c_int64(n_core), C.c_int64(int(displ)),
+                                                 C.c_int64(n_local), C.c_int32(int(threads)), C.byref(nnz))
+    else:
+        t = _integral_tables(system)
+        h = L.neci_host_core_ham_build(C.c_int32(system.nel), C.c_int32(system.nbasis), _p(t["umat"], C.c_double),
+                                       _p(t["tmat"], C.c_double), C.c_double(system.ecore), C.c_double(hii),
+                                       _p(il, C.c_int64), C.c_int64(n_core), C.c_int64(int(displ)), C.c_int64(n_local),
+                                       C.c_int32(int(threads)), C.c_int32(int(bool(hphf))), C.byref(nnz))
     if not h:
         raise RuntimeError("neci_host_core_ham_build failed")
     row_ptr = np.zeros(n_local + 1, dtype=np.int64)

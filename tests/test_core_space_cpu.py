@@ -580,3 +580,40 @@ def test_pops_core_from_a_running_list_and_switch_to_semi_stochastic():
         st = o.iterate(0.002, 0.0, it)
     assert st[ST["NORM_SEMISTOCH_SQ"]] > 0.5 * st[ST["NORM_PSI_SQ"]]       # the core space carries most of the norm
     assert 0.5 * tot < st[ST["TOTPARTS"]] < 3.0 * tot
+
+
+@pytest.mark.parametrize("kind", ["hub_k", "hub_rs"])
+def test_host_lattice_elements_and_core_hamiltonian(kind):
+    """The host library's elements and sparse Hamiltonian for the lattice models (k-space: get_umat_kspace rule inside
+    the Slater-Condon routines; real space: on-site <ii|ii> = U beside the hopping matrix) equal the oracle's
+    get_helement_lattice for random determinant pairs and over a random determinant list."""
+    s = host.hubbard_k_system(4, 4, U=4.0) if kind == "hub_k" else host.hubbard_rs_system(4, 4, U=4.0)
+    hii = driver.diag_energy(s, s.ref_orbs)
+    o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000)
+    rng = np.random.default_rng(6)
+    dets = helpers.random_dets(s, 150, rng)
+    ref = [int(x) for x in s.ref_orbs]
+    # neighbours of the reference so that singles / doubles occur among the pairs
+    near = []
+    for _ in range(100):
+        d = list(ref)
+        for _k in range(int(rng.integers(1, 3))):
+            i = int(rng.integers(0, len(d)))
+            cand = [x for x in range(1, s.nbasis + 1) if x not in d and (x & 1) == (d[i] & 1)]
+            d[i] = int(rng.choice(cand))
+        near.append(sorted(d))
+    il = np.unique(np.array([s.ilut(d) for d in dets + near + [ref]], dtype=np.int64).reshape(-1, s.nw), axis=0)
+    n = il.shape[0]
+    I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
+    hh = host.get_helement(s, il[I], il[J])
+    ho = o.probe_helement(il[I], il[J])
+    assert np.count_nonzero(ho) > n
+    assert np.allclose(hh, ho, rtol=1e-12, atol=1e-13)
+    il2, sizes, displs = host.layout_core_space(il, np.zeros(n, dtype=np.int32), 1)
+    c = host.core_hamiltonian(s, il2, hii)
+    H = np.zeros((n, n))
+    for i in range(n):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        H[i, c["col"][sl]] = c["val"][sl]
+    want = o.probe_helement(il2[I], il2[J]).reshape(n, n) - hii * np.eye(n)
+    assert np.allclose(H, want, rtol=1e-12, atol=1e-13)

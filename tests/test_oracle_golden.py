@@ -508,3 +508,10 @@ def test_k_hubbard_doubles_core_matches_the_reference_runs(which, ref_orbs):
     H = o.probe_helement(il[I], il[J]).reshape(n, n) - hii * np.eye(n)
     assert np.allclose(H, H.T, atol=1e-13)
     assert abs(np.linalg.eigvalsh(H)[0] - g["core_correlation_energy"]) < 6e-11
+    # the host library's sparse rows for the same space (calc_determ_hamil_sparse of the stand-alone host)
+    c = host.core_hamiltonian(s, il, hii)
+    Hh = np.zeros((n, n))
+    for i in range(n):
+        sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
+        Hh[i, c["col"][sl]] = c["val"][sl]
+    assert np.allclose(Hh, H, rtol=1e-12, atol=1e-13)
