@@ -275,6 +275,34 @@ int64_t neci_host_sd_space(int32_t nel, int32_t nbasis, const double *umat, cons
     return (n <= capacity) ? n : -n;
 }
 
+// enumerate_sing_doub_kpnt (src/semi_stoch_gen.F90:1429-1500) for the k-space Hubbard model: the reference determinant
+// and every double excitation conserving spin and total momentum (same-spin pairs included: they are symmetry-allowed
+// although their matrix element to the reference vanishes); momentum conservation leaves no single excitations.
+int64_t neci_host_sd_space_hubbard_k(int32_t nbasis, int32_t n_k, const int32_t *ksum, const int64_t *ilut_ref,
+                                     int64_t capacity, int64_t *out) {
+    if (nbasis > 128 || nbasis != 2 * n_k) return 0;
+    const int nw = nbasis / 64 + 1;
+    Det2 R; R.w[0] = (uint64_t)ilut_ref[0]; R.w[1] = (nw > 1) ? (uint64_t)ilut_ref[1] : 0ull;
+    std::vector<int> occ, vir;
+    for (int b = 0; b < nbasis; ++b) (has(R, b) ? occ : vir).push_back(b);
+    int64_t n = 0;
+    auto put = [&](const Det2 &d) {
+        if (n < capacity) { out[n * nw] = (int64_t)d.w[0]; if (nw > 1) out[n * nw + 1] = (int64_t)d.w[1]; }
+        ++n;
+    };
+    put(R);
+    for (size_t x = 0; x < occ.size(); ++x)
+        for (size_t y = x + 1; y < occ.size(); ++y)
+            for (size_t p = 0; p < vir.size(); ++p)
+                for (size_t q = p + 1; q < vir.size(); ++q) {
+                    const int i = occ[x], j = occ[y], a = vir[p], b = vir[q];
+                    if (((i & 1) + (j & 1)) != ((a & 1) + (b & 1))) continue;
+                    if (ksum[(i >> 1) * n_k + (j >> 1)] != ksum[(a >> 1) * n_k + (b >> 1)]) continue;
+                    Det2 d = R; flip(d, i); flip(d, j); flip(d, a); flip(d, b); put(d);
+                }
+    return (n <= capacity) ? n : -n;
+}
+
 // DetermineDetNode for n determinants (hash_iter = 0, no unique HF node: the defaults).
 // blocks[k] = get_det_block (1-based, as neci_gpu_probe_det_node reports it), nodes[k] = LoadBalanceMapping(block).
 int neci_host_det_node(int32_t nbasis, const int32_t *random_orb_index, int32_t balance_blocks,

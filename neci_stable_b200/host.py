@@ -369,6 +369,19 @@ def sing_doub_space(system, ref_ilut=None, only_keep_conn=False, orbsym=None):
     orbsym: ORBSYM labels of the spatial orbitals (abelian groups); None = all irreps equal."""
     ref = _iluts(system, system.ilut(system.ref_orbs) if ref_ilut is None else ref_ilut)
     t = system.tables
+    if system.kind == capi.SYS_HUBBARD_K:
+        # enumerate_sing_doub_kpnt: spin- and momentum-conserving doubles only
+        ks = np.ascontiguousarray(t["ksum"], dtype=np.int32)
+        L = lib()
+        L.neci_host_sd_space_hubbard_k.restype = C.c_int64
+        need = -L.neci_host_sd_space_hubbard_k(C.c_int32(system.nbasis), C.c_int32(t["n_k"]), _p(ks, C.c_int32),
+                                               _p(ref, C.c_int64), C.c_int64(0), None)
+        out = np.zeros((max(need, 1), system.nw), dtype=np.int64)
+        n = L.neci_host_sd_space_hubbard_k(C.c_int32(system.nbasis), C.c_int32(t["n_k"]), _p(ks, C.c_int32),
+                                           _p(ref, C.c_int64), C.c_int64(out.shape[0]), _p(out, C.c_int64))
+        if n <= 0:
+            raise RuntimeError("neci_host_sd_space_hubbard_k failed (%d)" % n)
+        return out[:n].copy()
     na, nb_ = system.nocc_alpha, system.nocc_beta
     va, vb = system.nbasis // 2 - na, system.nbasis // 2 - nb_
     cap = 1 + na * va + nb_ * vb + (na * (na - 1) // 2) * (va * (va - 1) // 2) \

@@ -502,6 +502,9 @@ def test_k_hubbard_doubles_core_matches_the_reference_runs(which, ref_orbs):
                 dets.append(sorted([o for o in ref_orbs if o not in (i, j)] + [a, b]))
     n = len(dets)
     assert n == g["core_size"] == 205
+    # the host library's enumerate_sing_doub_kpnt gives the same set
+    sd = host.sing_doub_space(s, ref_ilut=s.ilut(ref_orbs))
+    assert sd.shape[0] == n and {tuple(r) for r in sd.tolist()} == {tuple(s.ilut(d).tolist()) for d in dets}
     o, _ = helpers.make_pair(s, hii, max_walkers=1000, max_spawned=1000)
     il = np.array([s.ilut(d) for d in dets], dtype=np.int64).reshape(n, s.nw)
     I = np.repeat(np.arange(n), n); J = np.tile(np.arange(n), n)
