@@ -516,6 +516,17 @@ def test_determ_doubles_run_on_the_oracle_agrees_with_the_reference_run():
     ground state), set up with the host library only and run on the oracle: the projected correlation energy agrees
     with the reference's -0.065081043 +/- 8.8e-6 within the combined blocking errors, and with the exact
     -0.0650928511 of the fci-core run within the initiator bias the reference run itself shows."""
+    e, err, hist, ref, g = determ_doubles_run(lambda s, params: helpers.Oracle(params))
+    tol = 4.0 * np.hypot(err, ref["projected_correlation_energy_error"])
+    assert err < 5e-5
+    assert abs(e - ref["projected_correlation_energy"]) < tol, (e, err, ref["projected_correlation_energy"])
+    assert abs(e - g["fci_core"]["correlation_energy"]) < tol + 2.5e-5
+    assert 0.8 * ref["total_walkers"] < hist[-1]["tot_parts"] < 1.3 * ref["total_walkers"]
+
+
+def determ_doubles_run(make_engine):
+    """The determ_doubles case on an engine made by make_engine(system, params) (oracle here, CUDA engine in
+    tests/test_gpu_energies.py): returns (projected correlation energy, blocking error, history, golden entry, golden)."""
     g, s = _hehe_system()
     ref = g["determ_doubles"]
     hii = driver.diag_energy(s, s.ref_orbs)
@@ -530,8 +541,10 @@ def test_determ_doubles_run_on_the_oracle_agrees_with_the_reference_run():
     w, v = np.linalg.eigh(H)
     iref = int(np.nonzero((il == s.ilut(s.ref_orbs)).all(axis=1))[0][0])
     psi = v[:, 0] * np.sign(v[iref, 0]) * ref["start_walkers"] / np.abs(v[:, 0]).sum()
-    o, _ = helpers.make_pair(s, hii, max_walkers=200000, max_spawned=200000, semi_stochastic=True, all_real_coeff=True,
-                             real_spawn_cutoff=ref["real_spawn_cutoff"], initiator_walk_no=ref["add_to_initiator"], seed=7)
+    params = host.make_params(s, hii, max_walkers=200000, max_spawned=200000, semi_stochastic=True, all_real_coeff=True,
+                              real_spawn_cutoff=ref["real_spawn_cutoff"], initiator_walk_no=ref["add_to_initiator"], seed=7)
+    o = make_engine(s, params)
+    s.apply(o)
     recs = np.zeros((n, s.nw + 2), dtype=np.int64)
     recs[:, :s.nw] = il
     recs[:, s.nw] = psi.view(np.int64)
@@ -544,11 +557,8 @@ def test_determ_doubles_run_on_the_oracle_agrees_with_the_reference_run():
     hist = run.run(4 * ref["nmcyc"])
     rows = [h for h in hist if h["varying"]][100:]
     e, err = driver.ratio_estimate([h["enum_cyc"] for h in rows], [h["hf_cyc"] for h in rows])
-    tol = 4.0 * np.hypot(err, ref["projected_correlation_energy_error"])
-    assert err < 5e-5
-    assert abs(e - ref["projected_correlation_energy"]) < tol, (e, err, ref["projected_correlation_energy"])
-    assert abs(e - g["fci_core"]["correlation_energy"]) < tol + 2.5e-5
-    assert 0.8 * ref["total_walkers"] < hist[-1]["tot_parts"] < 1.3 * ref["total_walkers"]
+    o.close()
+    return e, err, hist, ref, g
 
 
 def test_pops_core_from_a_running_list_and_switch_to_semi_stochastic():
