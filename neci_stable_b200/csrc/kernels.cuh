@@ -100,12 +100,29 @@ __global__ void k_merge_free_finish(WalkerList L) {
 // ---- CompressSpawnedList as an in-place hash merge ------------------------------
 __device__ __forceinline__ long long recv_count(const SpawnBuf &SB, const IterArgs &A) {
     if (A.n_recv >= 0) return A.n_recv;
-    return (A.n_recv == -1) ? (long long)SB.cnt[0] : (long long)*SB.n_recv_dev;
+    // append_spawn keeps counting past seg_cap after an overflow (the error bit reports it): never walk past the buffer
+    if (A.n_recv == -1) return (long long)min(SB.cnt[0], (unsigned long long)SB.seg_cap);
+    return (long long)*SB.n_recv_dev;
 }
 __device__ __forceinline__ u64 sht_mask_for(long long n, u64 cap) {
     u64 m = 1024;
     while (m < 2ull * (u64)n && m < cap) m <<= 1;
     return m - 1;
+}
+
+// Order-independent sum of real-coefficient spawns onto one determinant.  atomicAdd(double) would make the last
+// bits of a merged amplitude depend on the order in which the contributors arrive, i.e. on the schedule.  Instead
+// every contribution is split exactly into a multiple of 2^-24 and a remainder resolved to 2^-64, the two parts are
+// accumulated with 64-bit integer atomics (associative), and the sums are joined once: the same bits whatever the
+// order, within one ulp of the sequential sum (exact split for |s| >= 2^-11; |sum| < 2^39).  Integer amplitudes
+// add exactly in any order and keep the plain fp64 atomic.
+__device__ __forceinline__ void fixed_split(double s, long long &hi, long long &lo) {
+    const double x = s * 16777216.0;
+    hi = (long long)x;
+    lo = (long long)((x - (double)hi) * 1099511627776.0);
+}
+__device__ __forceinline__ double fixed_join(long long hi, long long lo) {
+    return ((double)hi + (double)lo * (1.0 / 1099511627776.0)) * (1.0 / 16777216.0);
 }
 
 template <int NW>
@@ -149,7 +166,11 @@ __global__ void __launch_bounds__(NG_BLOCK) k_compress(Params P, WalkerList L, S
                 if (NW > 1) same = same && ((u64)rj[NW - 1] == d.w[NW - 1]);
                 if (same) {
                     // FindResidualParticle (Annihilation.F90:551-634): sign sum, flag union
-                    atomicAdd((double *)&rj[NW], s);
+                    if (P.t_all_real_coeff) {
+                        long long hi, lo; fixed_split(s, hi, lo);
+                        atomicAdd((unsigned long long *)&SB.acc_hi[j], (unsigned long long)hi);
+                        atomicAdd((unsigned long long *)&SB.acc_lo[j], (unsigned long long)lo);
+                    } else atomicAdd((double *)&rj[NW], s);
                     atomicOr((unsigned long long *)&rj[NW + 1], (unsigned long long)((f & F_INIT) | SF_MULTI));
                     rec[NW + 1] = SF_DEAD;
                     break;
@@ -192,12 +213,23 @@ __global__ void __launch_bounds__(NG_BLOCK) k_annihilate(Params P, WalkerList L,
                 Det<NW> d; d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
                 double s = __longlong_as_double(rec[NW]);
                 const bool multi = (f & SF_MULTI) != 0;
+                if (multi && P.t_all_real_coeff) {
+                    // the representative's own amplitude joins the fixed-point sums of the others; the accumulators
+                    // go back to zero for the next iteration
+                    long long hi, lo; fixed_split(s, hi, lo);
+                    hi += SB.acc_hi[i]; lo += SB.acc_lo[i];
+                    SB.acc_hi[i] = 0; SB.acc_lo[i] = 0;
+                    s = fixed_join(hi, lo);
+                }
                 acc[0] -= fabs(s);                       // Annihilated(compress) = sum|s_i| - |sum s_i|
                 if (fabs(s) > 1.e-12 || (!multi && fabs(s) >= 1.e-12)) {
                     acc[4] += 1.0;
                     bool spawn_init = (f & F_INIT) != 0;
                     if (multi) {
-                        if (P.t_trunc_initiator && P.t_init_coherent_rule) spawn_init = true;
+                        // FindResidualParticle touches the flags of a merged block only under tTruncInitiator
+                        // (Annihilation.F90:576-590); without it cum_det's flag word stays zero
+                        if (!P.t_trunc_initiator) spawn_init = false;
+                        else if (P.t_init_coherent_rule) spawn_init = true;
                         f = spawn_init ? (long long)F_INIT : 0ll;      // cum_det carries initiator flags only
                     } else f &= (long long)(F_INIT | F_DPARENT);
                     const u64 h = det_hash64(d);
@@ -481,25 +513,80 @@ __global__ void k_core_gather(WalkerList L, const int *core_slots, long long n, 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         v_part[i] = L.sgn[core_slots[i]];
 }
-// determ_projection: one warp per row; out_i = tau * (-sum_j H_ij v_j + S * v_{i+displ}),
-// fused with deterministic_annihilation (Annihilation.F90:930-963): sign += out_i.
-__global__ void __launch_bounds__(NG_BLOCK) k_determ_spmv(WalkerList L, const long long *row_ptr, const int *col, const double *val,
-                                                          const double *v_full, long long n_local, long long displ,
-                                                          double tau, double diag_sft, const double *core_ham_diag, double *out) {
+// determ_projection: out_i = tau * (-sum_j H_ij v_j + S * v_{i+displ}), fused with the shift / diagonal term of
+// determ_projection_no_death.  Pure HBM stream (12 bytes per non-zero element, rows of ~2000 elements at 1e5 core
+// determinants), so the design goal is bytes in flight: one warp per row, every lane requests NG_SPMV_QUADS x 4 consecutive
+// elements per trip with 128-bit loads (two double2 + one int4 per quadruple = 1.5 KB per quadruple and warp; the first
+// version's scalar loads kept 384 B per warp in flight and reached 26 % of the HBM roofline), the matrix is read
+// with streaming loads so that the gathered vector (0.8 MB) stays cache-resident.  Row starts are arbitrary, so a
+// row is split into an unaligned head (< 4 elements), the 4-aligned body and a tail (< 4 elements).
+#define NG_SPMV_BLOCK 256
+// The loads are volatile asm so that ptxas keeps them in program order: left to itself it interleaves the gathers of the
+// first quadruple (which wait for its column indices) with the wide loads of the following ones, and the warp then
+// sits on the first scoreboard with a fraction of its bytes requested.
+struct SpmvQuad { double2 a, b; int4 c; };
+__device__ __forceinline__ void spmv_load(SpmvQuad &q, const double *val, const int *col, long long k) {
+    asm volatile("ld.global.cs.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(q.c.x), "=r"(q.c.y), "=r"(q.c.z), "=r"(q.c.w) : "l"(col + k));
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(q.a.x), "=d"(q.a.y) : "l"(val + k));
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(q.b.x), "=d"(q.b.y) : "l"(val + k + 2));
+}
+__device__ __forceinline__ void spmv_gather(double (&g)[4], const SpmvQuad &q, const double *v) {
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(g[0]) : "l"(v + q.c.x));
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(g[1]) : "l"(v + q.c.y));
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(g[2]) : "l"(v + q.c.z));
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(g[3]) : "l"(v + q.c.w));
+}
+__device__ __forceinline__ double spmv_dot(const SpmvQuad &q, const double (&g)[4]) {
+    return (q.a.x * g[0] + q.a.y * g[1]) + (q.b.x * g[2] + q.b.y * g[3]);
+}
+#ifndef NG_SPMV_QUADS
+#define NG_SPMV_QUADS 2          /* quadruples per lane and trip */
+#endif
+#ifndef NG_SPMV_CTAS
+#define NG_SPMV_CTAS 4
+#endif
+__global__ void __launch_bounds__(NG_SPMV_BLOCK, NG_SPMV_CTAS) k_determ_spmv(const long long *__restrict__ row_ptr, const int *__restrict__ col,
+                                                                  const double *__restrict__ val, const double *__restrict__ v_full,
+                                                                  long long n_local, long long displ, double tau, double diag_sft,
+                                                                  const double *__restrict__ core_ham_diag, double *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long i = warp; i < n_local; i += nwarps) {
         const long long b = row_ptr[i], e = row_ptr[i + 1];
-        double acc = 0.0;
-        for (long long k = b + lane; k < e; k += 32) acc -= __ldg(&val[k]) * __ldg(&v_full[__ldg(&col[k])]);
-        acc = warp_sum(acc);
+        const long long k0 = min(e, (b + 3) & ~3ll), k1 = max(k0, e & ~3ll);
+        double acc[NG_SPMV_QUADS];
+#pragma unroll
+        for (int u = 0; u < NG_SPMV_QUADS; ++u) acc[u] = 0.0;
+        if (b + lane < k0) acc[0] = __ldcs(&val[b + lane]) * __ldg(&v_full[__ldcs(&col[b + lane])]);
+        if (k1 + lane < e) acc[NG_SPMV_QUADS - 1] += __ldcs(&val[k1 + lane]) * __ldg(&v_full[__ldcs(&col[k1 + lane])]);
+        long long k = k0 + 4 * lane;
+        for (; k + 128 * (NG_SPMV_QUADS - 1) < k1; k += 128 * NG_SPMV_QUADS) {
+            SpmvQuad q[NG_SPMV_QUADS]; double g[NG_SPMV_QUADS][4];
+#pragma unroll
+            for (int u = 0; u < NG_SPMV_QUADS; ++u) spmv_load(q[u], val, col, k + 128 * u);
+#pragma unroll
+            for (int u = 0; u < NG_SPMV_QUADS; ++u) spmv_gather(g[u], q[u], v_full);
+#pragma unroll
+            for (int u = 0; u < NG_SPMV_QUADS; ++u) acc[u] += spmv_dot(q[u], g[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < NG_SPMV_QUADS - 1; ++u) {          // what is left of this lane's share: < NG_SPMV_QUADS quadruples
+            if (k + 128 * u < k1) {
+                SpmvQuad q; double g[4];
+                spmv_load(q, val, col, k + 128 * u); spmv_gather(g, q, v_full);
+                acc[u] += spmv_dot(q, g);
+            }
+        }
+        double t = acc[0];
+#pragma unroll
+        for (int u = 1; u < NG_SPMV_QUADS; ++u) t += acc[u];
+        t = -warp_sum(t);
         if (lane == 0) {
             // determ_projection adds the shift; determ_projection_no_death (semi_stoch_procs.F90:285-374) adds the
             // diagonal element back instead, because death then acts on the core determinants as well
             const double d = core_ham_diag ? core_ham_diag[i] : diag_sft;
-            acc = (acc + d * v_full[i + displ]) * tau;
-            out[i] = acc;
+            out[i] = (t + d * v_full[i + displ]) * tau;
         }
     }
 }

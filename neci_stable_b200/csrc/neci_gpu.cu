@@ -73,7 +73,7 @@ struct neci_gpu_engine {
     unsigned int *d_ticket = nullptr;
     long long *h_ctr = nullptr;
     int rows_spawn = 0, rows_heavy = 0, rows_compress = 0, rows_annih = 0, rows_insert = 0, rows_list = 0, rows_trial = 0, rows_tau = 0, rows_total = 0;
-    int grid_spawn = 0, grid_generic = 0;
+    int grid_spawn = 0, grid_generic = 0, grid_spmv = 0;
     u32 stamp = 0;
     bool need_rebuild = false;
     long long n_launch = 0;            // kernels launched by this engine since init
@@ -198,6 +198,11 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     long long sc = 1024; while (sc < 2 * Ms) sc <<= 1;
     SB.sht_cap = (u64)sc; SB.sht = e->alloc<u64>(sc);
     SB.ins_idx = e->alloc<int>(Ms);
+    if (cfg->t_all_real_coeff) {
+        SB.acc_hi = e->alloc<long long>(Ms); SB.acc_lo = e->alloc<long long>(Ms);
+        if (!SB.acc_hi || !SB.acc_lo) return e->fail("device allocation failed (merge accumulators)");
+        CK(cudaMemset(SB.acc_hi, 0, (size_t)Ms * 8)); CK(cudaMemset(SB.acc_lo, 0, (size_t)Ms * 8));
+    }
     if (cfg->nranks > 1) {
         SB.stage_cap = Ms; SB.stage = e->alloc<long long>((size_t)Ms * e->W); SB.stage_cnt = e->alloc<unsigned long long>(1);
         if (!SB.stage || !SB.stage_cnt) return e->fail("device allocation failed (spawn staging list)");
@@ -219,6 +224,11 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     const int nsm = prop.multiProcessorCount;
     e->grid_generic = nsm * 8;
     e->grid_spawn = nsm * 4;       // refined per kernel variant below
+    {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_determ_spmv, NG_SPMV_BLOCK, 0));
+        e->grid_spmv = nsm * std::max(1, per_sm);
+    }
     e->rows_spawn = nsm * 8; e->rows_heavy = nsm * 4; e->rows_compress = e->grid_generic; e->rows_annih = e->grid_generic;
     e->rows_insert = e->grid_generic; e->rows_list = e->grid_generic;
     // K1 keeps its stage queues in dynamic shared memory (> 48 KB for two-word determinants); one persistent
@@ -701,6 +711,7 @@ static int gather_core_vector(neci_gpu_engine *e) {
         return 0;
     }
     // MPIAllGatherV (semi_stoch_procs.F90:127) as grouped send/recv of the ragged shares
+    if (!e->comm) return e->fail("semi-stochastic run on several ranks needs neci_gpu_nccl_init (the core vector is gathered with NCCL)");
     NCK(g_nccl.GroupStart());
     for (int r = 0; r < nr; ++r) {
         if (e->n_core_local > 0) NCK(g_nccl.Send(e->d_vpart, (size_t)e->n_core_local, ncclFloat64, r, e->comm, e->stream));
@@ -783,15 +794,23 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
     IterArgs A; A.tau = tau; A.diag_sft = diag_sft; A.iter = iter; A.n_recv = -1; A.stamp = 0;
     CK(cudaEventRecord(e->ev[0], e->stream));
     if (e->cfg.t_semi_stochastic && e->n_core_total > 0) {
+        // determ_projection (semi_stoch_procs.F90:105-241): gather of partial_determ_vecs, MPIAllGatherV, multiplication.
+        // The phase time between ev[0] and ev[1] is exactly that routine.
         e->n_launch += (e->n_core_local > 0) ? 2 : 0;
+        const bool single = e->cfg.nranks == 1;
         if (e->n_core_local > 0)
-            k_core_gather<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local + 255) / 256)), 256, 0, e->stream>>>(e->L, e->d_core_slots, e->n_core_local, e->d_vpart);
-        if (gather_core_vector(e)) return 1;
-        if (e->n_core_local > 0)
-            k_determ_spmv<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local * 32 + 255) / 256)), NG_BLOCK, 0, e->stream>>>(
-                e->L, e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft,
+            k_core_gather<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local + 255) / 256)), 256, 0, e->stream>>>(
+                e->L, e->d_core_slots, e->n_core_local, single ? e->d_vfull : e->d_vpart);
+        if (!single && gather_core_vector(e)) return 1;
+        if (e->n_core_local > 0) {
+            const int warps_per_cta = NG_SPMV_BLOCK / 32;
+            const int grid = (int)std::max<long long>(1, std::min<long long>((long long)e->grid_spmv, (e->n_core_local + warps_per_cta - 1) / warps_per_cta));
+            k_determ_spmv<<<grid, NG_SPMV_BLOCK, 0, e->stream>>>(
+                e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft,
                 e->cfg.t_death_before_comms ? (const double *)nullptr : (const double *)e->d_core_diag, e->d_vout);
+        }
     }
+    CK(cudaEventRecord(e->ev[1], e->stream));
     if (e->cfg.t_tau_search) {
         double *p_tau = e->d_partials + (size_t)(e->rows_total - e->rows_trial - e->rows_tau) * NECI_ST_COUNT;
         e->n_launch += 1;
@@ -804,7 +823,6 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
         if (e->nw == 1) k_trial_energy<1><<<e->rows_trial, NG_BLOCK, 0, e->stream>>>(e->P, e->L, p_trial);
         else k_trial_energy<2><<<e->rows_trial, NG_BLOCK, 0, e->stream>>>(e->P, e->L, p_trial);
     }
-    CK(cudaEventRecord(e->ev[1], e->stream));
     e->n_launch += 2;
     double *p_spawn = e->d_partials, *p_heavy = e->d_partials + (size_t)e->rows_spawn * NECI_ST_COUNT;
     NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, K1_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));

@@ -52,6 +52,8 @@ struct SpawnBuf {
     int W;
     // spawn-merge hash table, entries [stamp:16][tag:16][index:32]
     u64 *sht; u64 sht_cap;
+    long long *acc_hi, *acc_lo;       // real coefficients: order-independent fixed-point sums of the records merged into
+                                      // a representative (k_compress adds, k_annihilate reads and re-zeroes)
     int *ins_idx;            // records that become new determinants
     long long *heavy;        // (slot, nspawn) pairs
     long long heavy_cap;

@@ -334,6 +334,20 @@ struct SpawnLess {
     }
 };
 
+// Merged amplitude of a block of real-coefficient spawns.  The reference adds them in the order its (unstable)
+// quicksort leaves them, so its last bits depend on the arrival order.  The engine fixes a canonical value that no
+// order can change: every contribution is split exactly into a multiple of 2^-24 and a remainder resolved to 2^-64,
+// both parts are summed as 64-bit integers, and the two sums are joined once.  For amplitudes of at least 2^-11 the
+// split is exact, so the result is the exact sum rounded twice (within one ulp of the sequential sum).
+static inline void fixed_split(double s, int64_t &hi, int64_t &lo) {
+    const double x = s * 16777216.0;                   // 2^24, exact
+    hi = (int64_t)x;                                   // truncation
+    lo = (int64_t)((x - (double)hi) * 1099511627776.0);  // 2^40; x - trunc(x) is exact
+}
+static inline double fixed_join(int64_t hi, int64_t lo) {
+    return ((double)hi + (double)lo * (1.0 / 1099511627776.0)) * (1.0 / 16777216.0);
+}
+
 // CompressSpawnedList + FindResidualParticle, src/Annihilation.F90:249-515,551-634
 void compress_spawned(orc_engine &e, std::vector<int64_t> &sp) {
     const int W = e.W, nw = e.nwords;
@@ -351,8 +365,10 @@ void compress_spawned(orc_engine &e, std::vector<int64_t> &sp) {
             if (std::fabs(s) >= 1.e-12) out.insert(out.end(), idx[b], idx[b] + W);
         } else {
             int64_t cum_flags = 0; double cum_sgn = 0.0;
+            int64_t fx_hi = 0, fx_lo = 0;
             for (int64_t i = b; i < c; ++i) {
                 const double new_sgn = sign_to_double(idx[i][nw]);
+                { int64_t h, l; fixed_split(new_sgn, h, l); fx_hi += h; fx_lo += l; }
                 const bool new_init = (idx[i][nw + 1] >> NECI_FLAG_INITIATOR) & 1;
                 if (e.cfg.t_trunc_initiator) {
                     if (e.cfg.t_init_coherent_rule) {
@@ -364,6 +380,8 @@ void compress_spawned(orc_engine &e, std::vector<int64_t> &sp) {
                     e.stats[NECI_ST_ANNIHILATED] += 2 * std::min(std::fabs(cum_sgn), std::fabs(new_sgn));
                 cum_sgn = cum_sgn + new_sgn;
             }
+            // integer amplitudes add exactly in any order; real ones take the order-independent sum
+            if (e.cfg.t_all_real_coeff) cum_sgn = fixed_join(fx_hi, fx_lo);
             if (std::fabs(cum_sgn) > 1.e-12) {
                 for (int w = 0; w < nw; ++w) out.push_back(idx[b][w]);
                 out.push_back(double_to_sign(cum_sgn));

@@ -7,7 +7,7 @@
 # Numbers printed under ncu are never bench values; the bench lines come from the separate runs of step 2.
 mkdir -p gpurun_out
 W="--workload semistoch_20e40o_pchb --no-cpu-baseline"
-NECI_GPU_UNVERIFIED=1 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gpu_tests.log 2>&1
+NECI_GPU_UNVERIFIED=1 timeout 600 python -m pytest tests -m gpu -q > gpurun_out/r02_gpu_tests.log 2>&1
 tail -3 gpurun_out/r02_gpu_tests.log
 timeout 400 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
 timeout 300 python bench.py $W > gpurun_out/r02_bench_semistoch.json 2> gpurun_out/r02_bench_semistoch.err

@@ -168,8 +168,6 @@ def test_device_diagonal_elements_match_reference_outputs():
         gpu.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("NECI_GPU_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: first run on hardware pending")
 def test_reference_regression_case_determ_doubles():
     """The reference's determ_doubles run (semi-stochastic doubles-core in the determinant basis, set up with the host
     library) on the CUDA engine: projected correlation energy within the combined blocking errors of the reference

@@ -146,15 +146,13 @@ def _worker(rank, world, port, out_dir, name, semi, balance=False, p2p=False, de
     dist.destroy_process_group()
 
 
-_UNVERIFIED = pytest.mark.skipif(os.environ.get("NECI_GPU_UNVERIFIED") != "1",
-                                 reason="written after the round's GPU budget was spent: first run on hardware pending")
 
 
 @pytest.mark.parametrize("name,semi,balance,p2p,devbuild", [
     ("pchb_14e28o", False, False, False, False), ("hub_k_6x6_2words", False, False, True, False),
     ("hub_rs_4x4", False, True, False, False), ("pchb_14e28o", False, True, True, False),
     ("pchb_6e6o", True, False, True, False), ("pchb_14e28o", False, False, True, False),
-    pytest.param("pchb_6e6o", True, False, True, True, marks=_UNVERIFIED)])
+    pytest.param("pchb_6e6o", True, False, True, True)])
 def test_multi_gpu_matches_oracle_world(tmp_path, name, semi, balance, p2p, devbuild):
     import torch
     import torch.multiprocessing as mp
