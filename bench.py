@@ -352,6 +352,8 @@ def main():
     ap.add_argument("--cpu-sample-walkers", type=float, default=2.0e6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="default workload only: skip the short runs of the other BASELINE configurations")
     ap.add_argument("--core-size", type=int, default=100000, help="semi-stochastic workloads: determinants in the core space")
     ap.add_argument("--core-build", default="host", choices=["host", "device"],
                     help="semi-stochastic workloads: who builds the sparse core Hamiltonian")
@@ -408,6 +410,52 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
+    ctx = dict(rank=rank, local_rank=local_rank, world=world, cores=cores, dist=dist, torch=torch)
+    line = run_workload(args, ctx, primary=True)
+
+    # ---- short runs of the other BASELINE configurations, so that the driver's one default command leaves evidence
+    #      for all of them (value, ms per step, phase split, roofline fractions); no e2e / CPU legs there
+    if args.secondary and args.workload == "n2_14e28o_pchb":
+        sec = {}
+        for wl, extra in (("hubk_6x6", {}), ("cr2_24e30o_pchb", {}), ("semistoch_20e40o_pchb", {"core_build": "device"})):
+            a2 = argparse.Namespace(**vars(args))
+            a2.workload = wl; a2.steps = max(3, min(args.steps, 8)); a2.warmup = 4
+            a2.no_e2e = True; a2.no_cpu_baseline = True; a2.walkers = min(args.walkers, 1.0e7)
+            a2.scaling = "weak"; a2.load_balance = False
+            for k, v in extra.items():
+                setattr(a2, k, v)
+            try:
+                r = run_workload(a2, ctx, primary=False)
+            except Exception as exc:                         # a failed secondary run must not cost the headline line
+                r = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            if rank == 0:
+                if "error" in r:
+                    sec[wl] = r
+                else:
+                    sec[wl] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "selfcheck") if k in r}
+                    sec[wl]["config"] = {k: r["config"][k] for k in ("description", "walkers_per_gpu", "walkers_total_end",
+                                                                       "determinants_total_end", "attempts_per_step",
+                                                                       "spawned_per_step", "semi_stochastic") if k in r["config"]}
+                    rf = r["roofline"]
+                    sec[wl]["phase_ms_per_step"] = rf["phase_ms_per_step"]
+                    sec[wl]["roofline"] = {kk: {x: kv[x] for x in ("achieved", "peak", "frac", "ms_per_launch", "algorithmic_bytes_per_launch")}
+                                           for kk, kv in rf.get("kernels", {"k_spawn": rf}).items()}
+        if rank == 0:
+            line["secondary"] = sec
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_workload(args, ctx, primary=True):
+    """One workload on the CUDA engine: set-up, warm-up, K timed iterations with the list resident, then (primary
+    only) the host-buffer e2e leg and the CPU leg.  Returns the JSON line as a dict on rank 0."""
+    rank, local_rank, world, cores, dist, torch = (ctx[k] for k in ("rank", "local_rank", "world", "cores", "dist", "torch"))
+    desc = WORKLOADS.get(args.workload, (0, 0, 0, args.workload))[3]
+    args = argparse.Namespace(**vars(args))
     from neci_stable_b200 import capi, host, driver
     from neci_stable_b200.capi import ST
 
@@ -504,12 +552,15 @@ def main():
             params["load_balance_mapping"] = np.asarray(new_map, dtype=np.int32)
             lb_moves = len(moves)
 
+    tot_before_timed = tot                                 # global TotParts entering the timed region
     # ---- timed region: K iterations, list resident in HBM
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     acc = np.zeros(capi.ST_COUNT)
     t_spawn = t_ann = t_comm = t_det = 0.0
+    cons = []                                              # per iteration: (TotParts after, net change the counters claim)
+    tot_prev_local = None
     bytes_spawn = 0.0
     launches0 = eng.launch_count()
     barrier()
@@ -519,6 +570,8 @@ def main():
         it += 1
         st = eng.iterate(tau, sft, it)
         acc += st
+        cons.append((st[ST["TOTPARTS"]], st[ST["NOBORN"]] - st[ST["NODIED"]] - st[ST["ANNIHILATED"]] - st[ST["NOABORTED"]]
+                     - st[ST["NOREMOVED"]], st[ST["NSPAWNED_SENT"]], st[ST["NSPAWNED_RECV"]]))
         t_spawn += st[ST["TIME_SPAWN_MS"]]; t_ann += st[ST["TIME_ANNIHIL_MS"]]; t_comm += st[ST["TIME_COMM_MS"]]
         t_det += st[ST["TIME_DETERM_MS"]]
         # algorithmic bytes of the spawn/death kernel (DESIGN.md "K1"): SoA record (8*nw + 8 sign + 4 flags) and diagH per
@@ -536,6 +589,32 @@ def main():
     walkers_end = allsum(st[ST["TOTPARTS"]])
     dets_end = allsum(st[ST["TOTWALKERS"]] - st[ST["HOLESINLIST"]])
     spawned = allsum(acc[ST["NSPAWNED_SENT"]])
+
+    # ---- self-check (the device-side analogue of the reference's per-iteration consistency checks,
+    #      src/FciMCPar.F90:1764,1851): over the timed iterations and summed over the ranks, every spawn record sent was
+    #      received; the population changed by exactly born - died - annihilated - aborted - removed (exact for integer
+    #      walkers without a core space; determ_projection moves amplitude without counters); a sample of every rank's
+    #      list hashes to that rank (DetermineDetNode)
+    selfcheck = None
+    if cons:
+        c = np.array(cons)
+        if world > 1:
+            t = torch.tensor(c, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            c = t.cpu().numpy()
+        prev = np.concatenate([[tot_before_timed], c[:-1, 0]])
+        resid = np.abs((c[:, 0] - prev) - c[:, 1])
+        owner_ok = None
+        if world > 1:
+            d, _, _ = eng.download_walkers()
+            occ = d[np.abs(d[:, system.nw].view(np.float64)) > 0][:200000]
+            _, node = eng.probe_det_node(occ[:, :system.nw])
+            owner_ok = allsum(float(np.count_nonzero(node != rank))) == 0.0
+        selfcheck = {"iterations": int(c.shape[0]), "spawns_sent": float(c[:, 2].sum()), "spawns_received": float(c[:, 3].sum()),
+                     "sent_equals_received": bool(np.array_equal(c[:, 2], c[:, 3])),
+                     "population_residual_max": float(resid.max()),
+                     "population_conserved": (bool(resid.max() <= 1e-9 * max(1.0, c[:, 0].max())) if not semi else None),
+                     "sampled_owner_is_rank": owner_ok}
 
     # ---- roofline of the dominant kernel (k_spawn), measured live with CUDA events on the engine's stream
     peaks = {}
@@ -592,7 +671,7 @@ def main():
         e2e = {"value": attempts / wall, "unit": UNIT, "h2d_bytes_per_step": 24, "d2h_bytes_per_step": 8 * capi.ST_COUNT + 128,
                "api": "neci_gpu_iterate: list, core Hamiltonian and trial tables resident in HBM; host passes tau/shift/iter "
                       "and reads the statistics vector every iteration (wall clock over the same K steps)"}
-    elif not args.no_e2e:
+    elif not args.no_e2e and primary:
         W = system.W
         dets_h = eng.alloc_host((max_walkers, W), np.int64)
         gd_h = eng.alloc_host((max_walkers,), np.float64)
@@ -627,7 +706,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on the host cores, bounded sample
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and primary:
         nd = int(args.cpu_sample_walkers / 2.0)
         r = cpu_run(args.workload, nd, 6, 3, cores, core_size=args.core_size, n_trial=args.trial)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -648,13 +727,10 @@ def main():
                        "wall_ms_per_step": 1e3 * wall / args.steps, **({"semi_stochastic": core_info} if semi else {}),
                        **({"load_balance": {"blocks_per_rank": 100, "blocks_moved_in_warmup": lb_moves}} if args.load_balance else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "selfcheck": selfcheck,
         }
-        print(json.dumps(line))
     eng.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":

@@ -130,11 +130,15 @@ __device__ __forceinline__ int fuse_index(int x, int y) {                  // sr
 __device__ __forceinline__ double dsign(double a, double b) { return copysign(a, b); }
 
 // ---------------------------------------------------------------------------
-// Philox4x32-10, counter based; stream keyed by (seed, iteration, determinant
-// hash, attempt, purpose) -- DESIGN.md §RNG.  Draw j of a stream comes from
-// block j/2 (lanes {0,1} or {2,3}), mapped to [0,1) with 53 bits.
+// Philox4x32, counter based; stream keyed by (seed, iteration, determinant hash, attempt, purpose) -- DESIGN.md
+// §RNG.  A stream is a sequence of 32-bit words, four per Philox block; draw53() takes two consecutive words and
+// maps them to [0,1) with 53 bits, draw32() takes one word (coarse choices: an electron, an orbital of a class).
+// Seven rounds: the smallest count for which Philox4x32 passes BigCrush (Salmon et al., SC'11, table 2; ten is that
+// paper's default with a safety margin) -- the engine draws ~4e10 blocks per second, so the rounds are paid for.
+// The ten-round function is kept for the Random123 known-answer test.
 // ---------------------------------------------------------------------------
-enum : u32 { RNG_NSPAWN = 0, RNG_ATTEMPT = 1, RNG_DEATH = 2, RNG_ROUND_SPAWN = 3, RNG_PRUNE = 4 };
+enum : u32 { RNG_NSPAWN = 0, RNG_ATTEMPT = 1, RNG_DEATH = 2, RNG_ROUND_SPAWN = 3, RNG_PRUNE = 4, RNG_ATT_ROUND = 5 };
+#define NG_PHILOX_ROUNDS 7
 
 __host__ __device__ __forceinline__ u64 mix64(u64 z) {
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
@@ -148,11 +152,10 @@ template <int NW> __device__ __forceinline__ u64 det_hash64(const Det<NW> &d) {
     return h;
 }
 
-// One Philox4x32-10 block.  Deliberately NOT inlined: a stream is drawn from at a dozen places of the spawning
-// kernel and twelve inlined copies (~70 instructions each) pushed its code past the instruction cache.
-__device__ __noinline__ uint4 philox4x32_10(u32 v0, u32 v1, u32 v2, u32 v3, u32 q0, u32 q1) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32_rounds(u32 v0, u32 v1, u32 v2, u32 v3, u32 q0, u32 q1) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         if (r) { q0 += 0x9E3779B9u; q1 += 0xBB67AE85u; }
         const u32 hi0 = __umulhi(0xD2511F53u, v0), lo0 = 0xD2511F53u * v0;
         const u32 hi1 = __umulhi(0xCD9E8D57u, v2), lo1 = 0xCD9E8D57u * v2;
@@ -161,27 +164,33 @@ __device__ __noinline__ uint4 philox4x32_10(u32 v0, u32 v1, u32 v2, u32 v3, u32 
     }
     return make_uint4(v0, v1, v2, v3);
 }
+// One block of the engine's generator.  Deliberately NOT inlined: a stream is drawn from at a dozen places of the
+// spawning kernel and a dozen inlined copies pushed its code past the instruction cache.
+__device__ __noinline__ uint4 philox_block(u32 v0, u32 v1, u32 v2, u32 v3, u32 q0, u32 q1) {
+    return philox4x32_rounds<NG_PHILOX_ROUNDS>(v0, v1, v2, v3, q0, q1);
+}
 
 struct Stream {
     u32 c0, c1, c2, c3, k0, k1;
-    u32 x2, x3;        // second half of the current block
-    int next;
-    bool have;         // x2/x3 hold block next>>1
-    __device__ __forceinline__ Stream(u64 seed, long long iter, u64 h, u32 attempt, u32 purpose, int start = 0) {
+    uint4 blk;         // block `cur` when cur >= 0
+    int cur, pos;      // pos: index of the next word
+    __device__ __forceinline__ Stream(u64 seed, long long iter, u64 h, u32 attempt, u32 purpose, int start_word = 0) {
         c0 = (u32)h; c1 = (u32)(h >> 32); c2 = attempt; c3 = purpose << 24;
-        k0 = (u32)seed ^ (u32)(seed >> 32); k1 = (u32)iter; next = start; x2 = x3 = 0; have = false;
+        k0 = (u32)seed ^ (u32)(seed >> 32); k1 = (u32)iter; pos = start_word; cur = -1; blk = make_uint4(0, 0, 0, 0);
     }
-    __device__ __forceinline__ double draw() {
-        u32 a, b;
-        if ((next & 1) == 0 || !have) {
-            const uint4 v = philox4x32_10(c0, c1, c2, c3 | (u32)(next >> 1), k0, k1);
-            if ((next & 1) == 0) { a = v.x; b = v.y; } else { a = v.z; b = v.w; }
-            x2 = v.z; x3 = v.w; have = true;
-        } else { a = x2; b = x3; }
-        ++next;
+    __device__ __forceinline__ u32 next_u32() {
+        const int b = pos >> 2, w = pos & 3;
+        if (b != cur) { blk = philox_block(c0, c1, c2, c3 | (u32)b, k0, k1); cur = b; }
+        ++pos;
+        return (w == 0) ? blk.x : (w == 1) ? blk.y : (w == 2) ? blk.z : blk.w;
+    }
+    __device__ __forceinline__ double draw32() { return (double)next_u32() * (1.0 / 4294967296.0); }
+    __device__ __forceinline__ double draw53() {
+        const u32 a = next_u32(), b = next_u32();
         const u64 u = (u64)a | ((u64)b << 32);
         return (double)(u >> 11) * (1.0 / 9007199254740992.0);
     }
+    __device__ __forceinline__ double draw() { return draw53(); }
 };
 
 // ---------------------------------------------------------------------------
@@ -220,6 +229,10 @@ struct Params {
     const struct PchbPair *pchb_pair; // [ij_max]
     double p_singles, p_doubles, p_parallel;
     double pgen_pair_par, pgen_pair_opp;            // p_parallel / #parallel pairs, (1 - p_parallel) / #alpha-beta pairs
+    // host-computed rescaling constants of the first draw of an attempt (see gen_pchb_double): 1 / (1 - p_singles),
+    // #parallel pairs / p_parallel, #alpha-beta pairs / (1 - p_parallel)
+    double inv_1m_ps, c_par, c_opp;
+    const unsigned short *tri_tab;                  // pair index -> n1 | n2 << 8 of a same-spin electron pair
     u32 magic_nalpha;                               // floor(2^32 / nocc_alpha) + 1 (exact quotients for idx < 2^32 / nocc_alpha)
     int n_classes;
     const unsigned char *class_of_spinorb;          // [nbasis]

@@ -233,9 +233,8 @@ __device__ __forceinline__ bool parent_is_initiator(const Params &P, bool initia
 template <int NW>
 __device__ void gen_rs_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
     E.ic = 1; E.valid = false; E.err = 0; E.pgen = 0.0;
-    const int elec = 1 + (int)(rng.draw() * P.nel);
+    const int elec = 1 + (int)(rng.draw32() * P.nel);
     const double p_elec = 1.0 / (double)P.nel;
-    Det<NW> all; all.w[0] = ~0ull; if (NW > 1) all.w[NW - 1] = ~0ull;
     const int src = select_orb(d, ~0ull, elec);
     const int *ng = P.neighbours + (size_t)(src - 1) * P.max_neigh;
     double cum[8]; int nb[8];
@@ -248,7 +247,7 @@ __device__ void gen_rs_hubbard(const Params &P, const Det<NW> &d, Stream &rng, E
         cum_sum += elem; cum[i] = cum_sum; nb[i] = o; nn = i + 1;
     }
     if (cum_sum < NG_EPS) return;
-    const double r = rng.draw() * cum_sum;
+    const double r = rng.draw53() * cum_sum;
     if (cum[nn - 1] < r) return;
     // binary_search_first_ge over <= 8 entries == first index with cum >= r
     int ind = 0;
@@ -341,8 +340,8 @@ __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Ex
     const unsigned conv = __activemask();
     bool failed = false;
     for (int guard = 0;; ++guard) {                // pick_spin_opp_elecs
-        e1 = 1 + (int)(rng.draw() * P.nel);
-        do { e2 = 1 + (int)(rng.draw() * P.nel); } while (e1 == e2);
+        e1 = 1 + (int)(rng.draw32() * P.nel);
+        do { e2 = 1 + (int)(rng.draw32() * P.nel); } while (e1 == e2);
         s1 = select_orb(d, ~0ull, e1); s2 = select_orb(d, ~0ull, e2);
         if (((s1 ^ s2) & 1) != 0) break;
         if (guard > 100000) { failed = true; break; }
@@ -374,7 +373,7 @@ __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Ex
     if (n == 0) return;
     const double cum_sum = __ldg(&P.kcum[n]);
     if (cum_sum < NG_EPS) return;
-    const double u = rng.draw();
+    const double u = rng.draw53();
     const double r = u * cum_sum;
     if (!(r > 0.0)) { gen_k_hubbard_sweep<NW>(P, d, s1, s2, u, E); return; }
     // smallest k >= 1 with C[k] >= r (binary_search_first_ge on the reference's list)
@@ -413,7 +412,7 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
     bool failed = false;
     int src = 0, cls = 0, NExcit = 0, attempts = 0;
     for (;;) {
-        const int Eleci = (int)(P.nel * rng.draw()) + 1;
+        const int Eleci = (int)(P.nel * rng.draw32()) + 1;
         src = select_orb(d, ~0ull, Eleci);
         cls = __ldg(&P.class_of_spinorb[src - 1]);
         NExcit = __popcll(P.class_mask[cls][0]) - __popcll(d.w[0] & P.class_mask[cls][0]);
@@ -427,7 +426,7 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
     int Orb = 0; attempts = 0;
     for (;;) {
         if (failed) break;
-        const int ChosenUnocc = (int)(nOrbs * rng.draw());
+        const int ChosenUnocc = (int)(nOrbs * rng.draw32());
         Orb = __ldg(&P.class_orbs[cs + ChosenUnocc]);
         if (!occ(d, Orb)) break;
         if (attempts > 250) { failed = true; break; }
@@ -443,31 +442,31 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
     E.valid = true;
 }
 
-// pick_biased_elecs + GAS_doubles_PCHB_gen_exc
+// pick_biased_elecs + GAS_doubles_PCHB_gen_exc.
+// Random numbers.  The reference draws four numbers per double excitation (single or double, the electron pair,
+// exchange or not, the alias sample).  Here one attempt takes ONE Philox block: the first 53-bit number decides
+// single / double and, rescaled to [0,1) by the caller (r = (u - pSingles) / (1 - pSingles)), picks the pair --
+// the rescaling pick_biased_elecs itself applies to its own number, (r / pParallel) * nPairs -- and the fraction
+// left over after the pair index has been taken off decides exchange; the second 53-bit number is the alias sample
+// (position and bias from one number, as AliasSampler_t does it).  Every choice keeps the reference's probabilities
+// (resolution 2^-53 / 2^-45 / 2^-53), pgen is unchanged.  The CPU checker of the test suite draws the same way.
 template <int NW>
-__device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
+__device__ void gen_pchb_double(const Params &P, const Det<NW> &d, double r, Stream &rng, Excit<NW> &E) {
     E.ic = 2; E.valid = false; E.err = 0;
     const int nA = P.nocc_alpha, nB = P.nocc_beta;
     const int AA = nA * (nA - 1) / 2, BB = nB * (nB - 1) / 2, par = AA + BB, AB = nA * nB;
-    const double r = rng.draw();
     u64 m1, m2; int k1, k2;                        // the pair = k1-th orbital of mask m1 and k2-th of mask m2
-    // pick_biased_elecs rescales r to a pair index by (r / pP) * par or ((r - pP) / (1 - pP)) * AB: one division with
-    // selected operands for the whole warp (the operations each lane performs are the reference's)
     const bool is_par = r < P.p_parallel;
-    const double num = is_par ? r : r - P.p_parallel;
-    const double den = is_par ? P.p_parallel : 1.0 - P.p_parallel;
-    const double scl = is_par ? (double)par : (double)AB;
-    int idx = (int)floor((num / den) * scl);
+    const double x = is_par ? r * P.c_par : (r - P.p_parallel) * P.c_opp;
+    int idx = min((int)x, (is_par ? par : AB) - 1);
+    const double u2 = x - (double)idx;             // uniform on [0,1), independent of idx
     double pGen = is_par ? P.pgen_pair_par : P.pgen_pair_opp;      // p_parallel / par, (1 - p_parallel) / AB: host quotients
     if (is_par) {
         u64 mask = NG_ALPHA_MASK;
         if (idx >= AA) { idx -= AA; mask = NG_BETA_MASK; }
-        // n1 = ceil((1 + sqrt(9 + 8 idx)) / 2) == smallest n with n (n - 1) / 2 > idx, evaluated in integers
-        int n1 = (int)((1.0f + sqrtf(9.0f + 8.0f * (float)idx)) * 0.5f);
-        while (n1 * (n1 - 1) / 2 <= idx) ++n1;
-        while ((n1 - 1) * (n1 - 2) / 2 > idx) --n1;
-        const int n2 = idx + 1 - ((n1 - 1) * (n1 - 2)) / 2;
-        m1 = mask; k1 = n2; m2 = mask; k2 = n1;
+        // n1 = ceil((1 + sqrt(9 + 8 idx)) / 2), n2 = idx + 1 - (n1 - 1)(n1 - 2) / 2, tabulated by the host
+        const u32 t = __ldg(&P.tri_tab[idx]);
+        m1 = mask; k1 = (int)(t >> 8); m2 = mask; k2 = (int)(t & 0xffu);
     } else {
         const int q = (nA == 1) ? idx : (int)__umulhi((u32)idx, P.magic_nalpha);   // idx / nA
         m1 = NG_ALPHA_MASK; k1 = 1 + idx - q * nA;
@@ -479,10 +478,6 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
     const int ij = (int)tri((u32)gtid(s1), (u32)gtid(s2));      // fuse_index
     int spin1 = s1 & 1, spin2 = s2 & 1;           // getSpinIndex: 0 alpha, 1 beta
     const int4 pi = __ldg(reinterpret_cast<const int4 *>(P.pchb_pair + (ij - 1)));    // {p_exch, nonempty, pad}
-    // The third draw of the stream is the exchange decision of an opposite-spin pair and the alias number of a
-    // parallel pair.  It is drawn before the two cases part, so that the Philox block behind it is computed once by
-    // the whole warp instead of twice by half of it (the numbers each lane sees are the same as in the reference order).
-    const double u2 = rng.draw();
     int sampler;
     if (spin1 == spin2) sampler = 0;
     else {
@@ -494,7 +489,7 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, Stream &rng, 
     // AliasSampler_t::sample
     if (((pi.z >> sampler) & 1) == 0) return;                        // empty sampler: ab = 0
     const PchbEntry *tab = P.pchb + ((size_t)(ij - 1) * 3 + sampler) * P.ab_max;
-    const double rr = (spin1 == spin2) ? u2 : rng.draw();
+    const double rr = rng.draw53();
     const int pos = (int)(P.ab_max * rr) + 1;
     const double bias = fmax(P.ab_max * rr + 1 - pos, 0.0);
     const double2 pb = __ldg(reinterpret_cast<const double2 *>(tab + (pos - 1)));                              // prob, bias
@@ -536,9 +531,10 @@ __device__ __forceinline__ void generate_excitation_core(const Params &P, const 
     if (SYS == NECI_SYS_HUBBARD_RS) gen_rs_hubbard(P, d, rng, E);
     else if (SYS == NECI_SYS_HUBBARD_K) gen_k_hubbard(P, d, rng, E);
     else {
-        // gen_exc_sd
-        if (rng.draw() < P.p_singles) { gen_uniform_single(P, d, rng, E); E.pgen = E.pgen * P.p_singles; }
-        else { gen_pchb_double(P, d, rng, E); E.pgen = E.pgen * P.p_doubles; }
+        // gen_exc_sd: the first number of the attempt's block; singles continue in the second block (word 4)
+        const double u = rng.draw53();
+        if (u < P.p_singles) { rng.pos = 4; gen_uniform_single(P, d, rng, E); E.pgen = E.pgen * P.p_singles; }
+        else { gen_pchb_double(P, d, (u - P.p_singles) * P.inv_1m_ps, rng, E); E.pgen = E.pgen * P.p_doubles; }
     }
 }
 template <int NW, int SYS>

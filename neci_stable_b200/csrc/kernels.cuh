@@ -590,6 +590,123 @@ __global__ void __launch_bounds__(NG_SPMV_BLOCK, NG_SPMV_CTAS) k_determ_spmv(con
         }
     }
 }
+// ---- determ_projection through bulk-copy (TMA) staging ------------------------------------------------------
+// The register version above tops out at ~55 % of the HBM roofline: a warp cannot hold more than a few KB of loads
+// in its registers, and the occupancy that would make up for it costs the registers.  Here the bytes in flight live
+// in shared memory instead.  Every warp is its own pipeline: it owns a contiguous run of rows holding 1/N-th of the
+// matrix elements (balanced in bytes, found by bisection of row_ptr), streams that run of `val` and `col` through a
+// private ring of NG_SPMV_STAGES tiles with cp.async.bulk (one elected lane arms the tile's mbarrier with the byte
+// count and issues two bulk copies), and consumes tile after tile: lanes read consecutive elements from shared memory
+// (conflict-free), gather v_full from L1/L2 and accumulate; a row's sum is reduced across the warp when its last
+// element has been consumed.  Tiles are aligned to 4 elements (16-byte rule of the bulk copy) and ignore row
+// boundaries, so a tile is fetched once even when several rows share it.  In flight per SM: CTAs x warps x stages x
+// 6 KB (3 x 4 x 3 x 6 KB = 216 KB), an order of magnitude above what the register version sustains.
+#ifndef NG_SPMV_TILE
+#define NG_SPMV_TILE 512
+#endif
+#ifndef NG_SPMV_STAGES
+#define NG_SPMV_STAGES 3
+#endif
+#ifndef NG_SPMV_WARPS
+#define NG_SPMV_WARPS 4
+#endif
+struct __align__(128) SpmvRing {
+    double val[NG_SPMV_STAGES][NG_SPMV_TILE];
+    int col[NG_SPMV_STAGES][NG_SPMV_TILE];
+    unsigned long long bar[NG_SPMV_STAGES];
+};
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// first row r in [0, n] with row_ptr[r] >= x
+__device__ __forceinline__ long long spmv_lower_bound(const long long *row_ptr, long long n, long long x) {
+    long long lo = 0, hi = n;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (__ldg(&row_ptr[mid]) < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(NG_SPMV_WARPS * 32) k_determ_spmv_tma(const long long *__restrict__ row_ptr, const int *__restrict__ col,
+                                                                    const double *__restrict__ val, const double *__restrict__ v_full,
+                                                                    long long n_local, long long displ, double tau, double diag_sft,
+                                                                    const double *__restrict__ core_ham_diag, double *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char spmv_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    SpmvRing &R = reinterpret_cast<SpmvRing *>(spmv_smem)[wib];
+    const long long w = (long long)blockIdx.x * NG_SPMV_WARPS + wib, nwarp = (long long)gridDim.x * NG_SPMV_WARPS;
+    const long long nnz = __ldg(&row_ptr[n_local]);
+    // rows whose first element lies in this warp's share of the element range
+    const long long e_lo = (nnz * w) / nwarp, e_hi = (nnz * (w + 1)) / nwarp;
+    const long long r0 = (w == 0) ? 0 : spmv_lower_bound(row_ptr, n_local, e_lo);
+    const long long r1 = (w == nwarp - 1) ? n_local : spmv_lower_bound(row_ptr, n_local, e_hi);
+    if (r0 >= r1) return;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NG_SPMV_STAGES; ++s) mbar_init(&R.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const long long S0 = __ldg(&row_ptr[r0]) & ~3ll, SE = (__ldg(&row_ptr[r1]) + 3) & ~3ll;
+    const long long ntiles = (SE - S0 + NG_SPMV_TILE - 1) / NG_SPMV_TILE;
+    auto issue = [&](long long t) {
+        const int s = (int)(t % NG_SPMV_STAGES);
+        const long long start = S0 + t * NG_SPMV_TILE;
+        const u32 cnt = (u32)min((long long)NG_SPMV_TILE, SE - start);
+        mbar_expect_tx(&R.bar[s], cnt * 12u);
+        bulk_g2s(R.val[s], val + start, cnt * 8u, &R.bar[s]);
+        bulk_g2s(R.col[s], col + start, cnt * 4u, &R.bar[s]);
+    };
+    if (lane == 0) for (long long t = 0; t < ntiles && t < NG_SPMV_STAGES; ++t) issue(t);
+    long long waited = -1;
+    for (long long i = r0; i < r1; ++i) {
+        const long long b = __ldg(&row_ptr[i]), e = __ldg(&row_ptr[i + 1]);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        long long pos = b;
+        while (pos < e) {
+            const long long t = (pos - S0) / NG_SPMV_TILE;
+            const int s = (int)(t % NG_SPMV_STAGES);
+            if (t > waited) { mbar_wait(&R.bar[s], (u32)((t / NG_SPMV_STAGES) & 1)); waited = t; }
+            const long long tstart = S0 + t * NG_SPMV_TILE;
+            const long long hi = min(e, tstart + NG_SPMV_TILE);
+            const double *vs = R.val[s] - tstart;
+            const int *cs = R.col[s] - tstart;
+            long long k = pos + lane;
+            for (; k + 96 < hi; k += 128) {
+                const int c0 = cs[k], c1 = cs[k + 32], c2 = cs[k + 64], c3 = cs[k + 96];
+                const double g0 = __ldg(&v_full[c0]), g1 = __ldg(&v_full[c1]), g2 = __ldg(&v_full[c2]), g3 = __ldg(&v_full[c3]);
+                a0 += vs[k] * g0; a1 += vs[k + 32] * g1; a2 += vs[k + 64] * g2; a3 += vs[k + 96] * g3;
+            }
+            {
+                const bool p0 = k < hi, p1 = k + 32 < hi, p2 = k + 64 < hi;
+                const int c0 = p0 ? cs[k] : 0, c1 = p1 ? cs[k + 32] : 0, c2 = p2 ? cs[k + 64] : 0;
+                const double g0 = __ldg(&v_full[c0]), g1 = __ldg(&v_full[c1]), g2 = __ldg(&v_full[c2]);
+                if (p0) a0 += vs[k] * g0;
+                if (p1) a1 += vs[k + 32] * g1;
+                if (p2) a2 += vs[k + 64] * g2;
+            }
+            pos = hi;
+            if (hi == tstart + NG_SPMV_TILE) {          // tile consumed: its stage is refilled with tile t + STAGES
+                __syncwarp();
+                if (lane == 0 && t + NG_SPMV_STAGES < ntiles) issue(t + NG_SPMV_STAGES);
+            }
+        }
+        const double acc = -warp_sum((a0 + a1) + (a2 + a3));
+        if (lane == 0) {
+            const double d = core_ham_diag ? core_ham_diag[i] : diag_sft;
+            out[i] = (acc + d * v_full[i + displ]) * tau;
+        }
+    }
+}
 __global__ void k_determ_apply(WalkerList L, const int *core_slots, const double *out, long long n_local) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (long long)gridDim.x * blockDim.x)
         L.sgn[core_slots[i]] += out[i];

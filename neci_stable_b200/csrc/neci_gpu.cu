@@ -15,6 +15,9 @@
 #include <unordered_set>
 #include <dlfcn.h>
 #include <nccl.h>
+#ifndef NG_SPMV_TMA
+#define NG_SPMV_TMA 1      /* determ_projection through bulk-copy staging (0: the register-staged kernel) */
+#endif
 #include "kernels.cuh"
 
 using namespace ng;
@@ -226,7 +229,12 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     e->grid_spawn = nsm * 4;       // refined per kernel variant below
     {
         int per_sm = 0;
+#if NG_SPMV_TMA
+        CK(cudaFuncSetAttribute(k_determ_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NG_SPMV_WARPS * sizeof(SpmvRing))));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_determ_spmv_tma, NG_SPMV_WARPS * 32, NG_SPMV_WARPS * sizeof(SpmvRing)));
+#else
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_determ_spmv, NG_SPMV_BLOCK, 0));
+#endif
         e->grid_spmv = nsm * std::max(1, per_sm);
     }
     e->rows_spawn = nsm * 8; e->rows_heavy = nsm * 4; e->rows_compress = e->grid_generic; e->rows_annih = e->grid_generic;
@@ -341,6 +349,20 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
         P.pgen_pair_par = p_parallel / (double)par;          // IEEE quotients, as pick_biased_elecs forms them per draw
         P.pgen_pair_opp = (1.0 - p_parallel) / (double)AB;
         P.magic_nalpha = (nA > 1) ? (u32)((1ull << 32) / (unsigned)nA) + 1u : 0u;
+        P.inv_1m_ps = 1.0 / (1.0 - p_singles);
+        P.c_par = (p_parallel > 0.0) ? (double)par / p_parallel : 0.0;
+        P.c_opp = (p_parallel < 1.0) ? (double)AB / (1.0 - p_parallel) : 0.0;
+        // same-spin pair index -> (n1, n2): n1 = ceil((1 + sqrt(9 + 8 idx)) / 2), n2 = idx + 1 - (n1 - 1)(n1 - 2) / 2
+        // (pick_biased_elecs, src/excit_gens_int_weighted.F90:770-790)
+        const int nmax = std::max(nA, nB), ntri = std::max(1, nmax * (nmax - 1) / 2);
+        if (nmax > 255) return e->fail("more than 255 electrons of one spin are not supported");
+        std::vector<unsigned short> tt((size_t)ntri);
+        for (int idx = 0; idx < ntri; ++idx) {
+            const int n1 = (int)std::ceil((1.0 + std::sqrt(9.0 + 8.0 * (double)idx)) / 2.0);
+            const int n2 = idx + 1 - ((n1 - 1) * (n1 - 2)) / 2;
+            tt[idx] = (unsigned short)(n1 | (n2 << 8));
+        }
+        P.tri_tab = e->upload(tt.data(), tt.size());
     }
     std::vector<unsigned char> cls(e->cfg.nbasis);
     std::vector<int> start(n_classes + 1, 0), orbs;
@@ -369,6 +391,9 @@ int neci_gpu_set_excit_probs(neci_gpu_engine *e, double p_singles, double p_doub
     const int par = nA * (nA - 1) / 2 + nB * (nB - 1) / 2, AB = nA * nB;
     P.pgen_pair_par = p_parallel / (double)par;
     P.pgen_pair_opp = (1.0 - p_parallel) / (double)AB;
+    P.inv_1m_ps = 1.0 / (1.0 - p_singles);
+    P.c_par = (p_parallel > 0.0) ? (double)par / p_parallel : 0.0;
+    P.c_opp = (p_parallel < 1.0) ? (double)AB / (1.0 - p_parallel) : 0.0;
     return 0;
 }
 
@@ -544,7 +569,11 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
     if (n_local != e->n_core_local) return e->fail("set_core_space: n_local = %lld but sizes[rank] = %lld", (long long)n_local, (long long)e->n_core_local);
     const long long nnz = row_ptr[n_local];
     e->d_row_ptr = e->upload((const long long *)row_ptr, (size_t)n_local + 1);
-    e->d_col = e->upload(col, (size_t)nnz); e->d_val = e->upload(val, (size_t)nnz);
+    // + 4 elements of slack: the last tile of the bulk-copy SpMV is rounded up to the 16-byte rule
+    e->d_col = e->alloc<int>((size_t)nnz + 4); e->d_val = e->alloc<double>((size_t)nnz + 4);
+    if (!e->d_col || !e->d_val) return e->fail("set_core_space: no memory for %lld non-zero elements", nnz);
+    CK(cudaMemset(e->d_col + nnz, 0, 16)); CK(cudaMemset(e->d_val + nnz, 0, 32));
+    CK(cudaMemcpy(e->d_col, col, (size_t)nnz * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(e->d_val, val, (size_t)nnz * 8, cudaMemcpyHostToDevice));
     {
         // core_ham_diag (fast_determ_hamil.F90:1494-1507): the diagonal entry of every local row
         std::vector<double> diag((size_t)n_local, 0.0);
@@ -580,8 +609,9 @@ int neci_gpu_build_core_space(neci_gpu_engine *e, const int32_t *sizes, const in
     for (long long i = 0; i < n_local; ++i) { const long long len = rp[i]; rp[i] = run; run += len; }
     rp[n_local] = run;
     CK(cudaMemcpyAsync(e->d_row_ptr, rp.data(), (size_t)(n_local + 1) * 8, cudaMemcpyHostToDevice, e->stream));
-    e->d_col = e->alloc<int>((size_t)run); e->d_val = e->alloc<double>((size_t)run);
+    e->d_col = e->alloc<int>((size_t)run + 4); e->d_val = e->alloc<double>((size_t)run + 4);
     if (!e->d_col || !e->d_val) return e->fail("build_core_space: no memory for %lld non-zero elements", run);
+    CK(cudaMemsetAsync(e->d_col + run, 0, 16, e->stream)); CK(cudaMemsetAsync(e->d_val + run, 0, 32, e->stream));
     // pass 2: the elements again, written in place
     NG_DISPATCH(e, (k_core_ham<NW, SYS, true><<<grid, NG_BLOCK, 0, e->stream>>>(e->P, d_il, n_core, e->core_displ, n_local, hii,
                                                                                e->d_row_ptr, e->d_col, e->d_val, e->d_core_diag)));
@@ -803,11 +833,18 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
                 e->L, e->d_core_slots, e->n_core_local, single ? e->d_vfull : e->d_vpart);
         if (!single && gather_core_vector(e)) return 1;
         if (e->n_core_local > 0) {
+#if NG_SPMV_TMA
+            const int grid = (int)std::max<long long>(1, std::min<long long>((long long)e->grid_spmv, (e->n_core_local + NG_SPMV_WARPS - 1) / NG_SPMV_WARPS));
+            k_determ_spmv_tma<<<grid, NG_SPMV_WARPS * 32, NG_SPMV_WARPS * sizeof(SpmvRing), e->stream>>>(
+                e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft,
+                e->cfg.t_death_before_comms ? (const double *)nullptr : (const double *)e->d_core_diag, e->d_vout);
+#else
             const int warps_per_cta = NG_SPMV_BLOCK / 32;
             const int grid = (int)std::max<long long>(1, std::min<long long>((long long)e->grid_spmv, (e->n_core_local + warps_per_cta - 1) / warps_per_cta));
             k_determ_spmv<<<grid, NG_SPMV_BLOCK, 0, e->stream>>>(
                 e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft,
                 e->cfg.t_death_before_comms ? (const double *)nullptr : (const double *)e->d_core_diag, e->d_vout);
+#endif
         }
     }
     CK(cudaEventRecord(e->ev[1], e->stream));

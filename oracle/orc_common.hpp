@@ -21,7 +21,7 @@
 // CalcHashTableStats.  The reference holds no test for those.
 //
 // The random stream is NOT the reference's dSFMT: both the oracle and the CUDA
-// engine draw from the same counter-based Philox4x32-10 streams keyed by
+// engine draw from the same counter-based Philox4x32 streams (seven rounds) keyed by
 // (seed, iteration, determinant, attempt, purpose) -- see DESIGN.md §RNG -- so
 // a whole iteration of the engine can be compared with the oracle bit for bit.
 #pragma once
@@ -50,10 +50,13 @@ struct Philox {
         const uint32_t n2 = hi0 ^ c[3] ^ k[1];
         c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
     }
-    static inline void gen(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    // rounds = 10 is the Random123 default (known-answer test); the streams of the engine and of this oracle use
+    // ROUNDS = 7, the smallest count that passes BigCrush (Salmon et al., SC'11)
+    static constexpr int ROUNDS = 7;
+    static inline void gen(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds = 10) {
         uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
         uint32_t k[2] = {key[0], key[1]};
-        for (int r = 0; r < 10; ++r) {
+        for (int r = 0; r < rounds; ++r) {
             if (r) { k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
             round(c, k);
         }
@@ -62,7 +65,7 @@ struct Philox {
 };
 
 // purposes of a random stream
-enum : uint32_t { RNG_NSPAWN = 0, RNG_ATTEMPT = 1, RNG_DEATH = 2, RNG_ROUND_SPAWN = 3, RNG_PRUNE = 4 };
+enum : uint32_t { RNG_NSPAWN = 0, RNG_ATTEMPT = 1, RNG_DEATH = 2, RNG_ROUND_SPAWN = 3, RNG_PRUNE = 4, RNG_ATT_ROUND = 5 };
 
 inline uint64_t mix64(uint64_t z) {
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
@@ -77,26 +80,34 @@ inline uint64_t det_hash64(const uint64_t *w, int nwords) {
     return h;
 }
 
-// Sequential [0,1) doubles of one (determinant, attempt, purpose, iteration)
-// stream; draw j comes from Philox block j/2, lanes {0,1} or {2,3}.
+// One (determinant, attempt, purpose, iteration) stream: a sequence of 32-bit words, four per Philox block.
+// draw53() takes two consecutive words and maps them to [0,1) with 53 bits; draw32() takes one word (coarse
+// choices: an electron, an orbital of a class).  draw() == draw53().
 struct Stream {
     uint32_t ctr[4], key[2];
     uint32_t cache[4];
-    int next = 0;
-    Stream(uint64_t seed, int64_t iter, uint64_t h, uint32_t attempt, uint32_t purpose) {
+    int cur = -1, pos = 0;
+    Stream(uint64_t seed, int64_t iter, uint64_t h, uint32_t attempt, uint32_t purpose, int start_word = 0) {
         ctr[0] = (uint32_t)h; ctr[1] = (uint32_t)(h >> 32); ctr[2] = attempt; ctr[3] = purpose << 24;
         key[0] = (uint32_t)seed ^ (uint32_t)(seed >> 32); key[1] = (uint32_t)iter;
+        pos = start_word;
     }
-    double draw() {
-        if ((next & 1) == 0) {
-            uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3] | (uint32_t)(next >> 1)};
-            Philox::gen(c, key, cache);
+    uint32_t next_u32() {
+        const int b = pos >> 2;
+        if (b != cur) {
+            uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3] | (uint32_t)b};
+            Philox::gen(c, key, cache, Philox::ROUNDS);
+            cur = b;
         }
-        const int o = (next & 1) * 2;
-        const uint64_t u = (uint64_t)cache[o] | ((uint64_t)cache[o + 1] << 32);
-        ++next;
+        return cache[(pos++) & 3];
+    }
+    double draw32() { return (double)next_u32() * (1.0 / 4294967296.0); }
+    double draw53() {
+        const uint32_t a = next_u32(), b = next_u32();
+        const uint64_t u = (uint64_t)a | ((uint64_t)b << 32);
         return (double)(u >> 11) * (1.0 / 9007199254740992.0);
     }
+    double draw() { return draw53(); }
 };
 
 // ----------------------------------------------------------------------------

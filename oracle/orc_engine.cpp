@@ -235,11 +235,14 @@ void spawn_phase(orc_engine &e, double tau, double DiagSft, int64_t iter) {
             }
             double nSpawn = -tau * rh * walkerweight / prob;
             e.stats[NECI_ST_MAX_CYC_SPAWN] = std::max(e.stats[NECI_ST_MAX_CYC_SPAWN], std::fabs(nSpawn));
+            // the rounding number is the first of the attempt's own RNG_ATT_ROUND stream (the engine evaluates the
+            // spawn in a later stage than it draws the excitation)
+            Stream rng_round(c.seed, iter, h, (uint32_t)p, RNG_ATT_ROUND);
             if (c.t_all_real_coeff) {
                 if (c.t_real_spawn_cutoff && std::fabs(nSpawn) < c.real_spawn_cutoff)
-                    nSpawn = c.real_spawn_cutoff * stochastic_round(nSpawn / c.real_spawn_cutoff, rng);
+                    nSpawn = c.real_spawn_cutoff * stochastic_round(nSpawn / c.real_spawn_cutoff, rng_round);
             } else {
-                nSpawn = (double)stochastic_round(nSpawn, rng);
+                nSpawn = (double)stochastic_round(nSpawn, rng_round);
             }
             const double child = nSpawn;
             if (near_zero(child)) continue;                                  // is_child_created :1706

@@ -269,7 +269,7 @@ struct Excitation {
 // + binary_search_first_ge, src/lib/util_mod_numerical.F90.template:35-85
 inline int pick_from_cum_list(const double *cum_arr, int n, double cum_sum, Stream &rng, double &pgen) {
     if (cum_sum < EPS) { pgen = 0.0; return -1; }
-    const double r = rng.draw() * cum_sum;
+    const double r = rng.draw53() * cum_sum;
     int lo = 1, hi = n, pos = -1;
     if (cum_arr[hi - 1] < r) { pgen = 0.0; return -1; }
     while (hi != lo) {
@@ -284,7 +284,7 @@ inline int pick_from_cum_list(const double *cum_arr, int n, double cum_sum, Stre
 // gen_excit_rs_hubbard, src/real_space_hubbard.F90:1938-2033
 inline void gen_excit_rs_hubbard(const System &S, const int *nI, const uint64_t *ilutI, Stream &rng, Excitation &E) {
     E.ic = 1;
-    const int elec = 1 + (int)(rng.draw() * S.nel);
+    const int elec = 1 + (int)(rng.draw32() * S.nel);
     const double p_elec = 1.0 / (double)S.nel;
     const int src = nI[elec - 1];
     const int32_t *neigh = &S.neighbours[(size_t)(src - 1) * S.max_neigh];
@@ -316,8 +316,8 @@ inline void gen_excit_k_space_hub(const System &S, const int *nI, const uint64_t
     // pick_spin_opp_elecs, src/lattice_models_utils.F90:123-148
     int elecs[2];
     for (int guard = 0;; ++guard) {
-        elecs[0] = 1 + (int)(rng.draw() * S.nel);
-        do { elecs[1] = 1 + (int)(rng.draw() * S.nel); } while (elecs[0] == elecs[1]);
+        elecs[0] = 1 + (int)(rng.draw32() * S.nel);
+        do { elecs[1] = 1 + (int)(rng.draw32() * S.nel); } while (elecs[0] == elecs[1]);
         if (is_beta(nI[elecs[0] - 1]) != is_beta(nI[elecs[1] - 1])) break;
         if (guard > 100000) { E.valid = false; E.err = 1; return; }
     }
@@ -354,15 +354,23 @@ inline void gen_excit_k_space_hub(const System &S, const int *nI, const uint64_t
     E.valid = true;
 }
 
-// pick_biased_elecs, src/excit_gens_int_weighted.F90:722-840 (no pAA bias)
-inline void pick_biased_elecs(const System &S, const int *nI, Stream &rng, int *elecs, int *src, double &pgen) {
+// pick_biased_elecs, src/excit_gens_int_weighted.F90:722-840 (no pAA bias).
+// Random numbers: the reference draws its own number here and rescales it to a pair index,
+// (r / pParallel) * nPairs or ((r - pParallel) / (1 - pParallel)) * nPairs.  The engine hands in the number that
+// decided "double" in gen_exc_sd, rescaled to [0,1) by the caller in the same way, and multiplies by the
+// host-computed constants nPairs / pParallel and nPairs / (1 - pParallel); the fraction left after the pair index
+// has been taken off is returned as `rest`, a uniform number independent of the index, which decides exchange in
+// GAS_doubles_PCHB_gen_exc.  Same probabilities, one Philox block per attempt instead of two.
+inline void pick_biased_elecs(const System &S, const int *nI, double r, int *elecs, int *src, double &pgen, double &rest) {
     const int nA = S.nocc_alpha, nB = S.nocc_beta;
     const int AA = nA * (nA - 1) / 2, BB = nB * (nB - 1) / 2, par = AA + BB, AB = nA * nB;
-    double r = rng.draw();
+    const double c_par = (S.p_parallel > 0.0) ? (double)par / S.p_parallel : 0.0;
+    const double c_opp = (S.p_parallel < 1.0) ? (double)AB / (1.0 - S.p_parallel) : 0.0;
     int al_req, be_req, al_num[2] = {0, 0}, be_num[2] = {0, 0};
     if (r < S.p_parallel) {
-        r = (r / S.p_parallel) * par;
-        int idx = (int)std::floor(r);
+        r = r * c_par;
+        int idx = std::min((int)r, par - 1);
+        rest = r - (double)idx;
         if (idx < AA) {
             al_req = 2; be_req = 0;
             al_num[0] = (int)std::ceil((1 + std::sqrt(9 + 8 * (double)idx)) / 2);
@@ -377,8 +385,9 @@ inline void pick_biased_elecs(const System &S, const int *nI, Stream &rng, int *
     } else {
         al_req = 1; be_req = 1;
         pgen = (1.0 - S.p_parallel) / (double)AB;
-        r = ((r - S.p_parallel) / (1.0 - S.p_parallel)) * AB;
-        const int idx = (int)std::floor(r);
+        r = (r - S.p_parallel) * c_opp;
+        const int idx = std::min((int)r, AB - 1);
+        rest = r - (double)idx;
         al_num[0] = 1 + idx % nA;
         be_num[0] = 1 + (int)std::floor(idx / (double)nA);
     }
@@ -403,7 +412,7 @@ inline int alias_sample(const System &S, int ij, int sampler, Stream &rng, doubl
     const size_t base = ((size_t)(ij - 1) * 3 + sampler) * S.ab_max;
     if (S.alias[base] == 0) { prob = 1.0; return 0; }
     const int sizeArr = S.ab_max;
-    const double r = rng.draw();
+    const double r = rng.draw53();
     const int pos = (int)(sizeArr * r) + 1;
     const double b = std::max(sizeArr * r + 1 - pos, 0.0);
     const int ind = (b < S.bias[base + pos - 1]) ? pos : S.alias[base + pos - 1];
@@ -423,7 +432,7 @@ inline void gen_uniform_single(const System &S, const int *nI, const uint64_t *i
     if (ElecsWNoExcits == S.nel) { E.valid = false; E.pgen = 0.0; return; }
     int Eleci = 0, cls = 0, NExcit = 0, attempts = 0;
     for (;;) {
-        const double r = rng.draw();
+        const double r = rng.draw32();
         Eleci = (int)(S.nel * r) + 1;
         cls = S.class_of_spinorb[nI[Eleci - 1] - 1];
         NExcit = unocc[cls];
@@ -434,7 +443,7 @@ inline void gen_uniform_single(const System &S, const int *nI, const uint64_t *i
     const int nOrbs = (int)S.class_orbs[cls].size();
     int Orb = 0; attempts = 0;
     for (;;) {
-        const double r = rng.draw();
+        const double r = rng.draw32();
         const int ChosenUnocc = (int)(nOrbs * r);
         Orb = S.class_orbs[cls][ChosenUnocc];
         if (!is_occ(ilutI, Orb)) break;
@@ -454,18 +463,18 @@ inline void gen_uniform_single(const System &S, const int *nI, const uint64_t *i
 }
 
 // GAS_doubles_PCHB_gen_exc, src/gasci_pchb_doubles_spatorb_fastweighted.fpp:155-277
-inline void gen_pchb_double(const System &S, const int *nI, const uint64_t *ilutI, Stream &rng, Excitation &E) {
+inline void gen_pchb_double(const System &S, const int *nI, const uint64_t *ilutI, double r_pair, Stream &rng, Excitation &E) {
     E.ic = 2;
     int elecs[2], src[2];
-    double pGen;
-    pick_biased_elecs(S, nI, rng, elecs, src, pGen);
+    double pGen, rest;
+    pick_biased_elecs(S, nI, r_pair, elecs, src, pGen, rest);
     const int ij = (int)fuseIndex(gtID(src[0]), gtID(src[1]));
     int spin[2] = {is_beta(src[0]) ? 1 : 0, is_beta(src[1]) ? 1 : 0};   // getSpinIndex: 0 alpha, 1 beta
     int sampler;
     if (spin[0] == spin[1]) sampler = 0;                                  // SAME_SPIN
     else {
         const double pe = S.p_exch[ij - 1];
-        if (rng.draw() < pe) { sampler = 2; pGen *= pe; std::swap(spin[0], spin[1]); }   // OPP_SPIN_EXCH
+        if (rest < pe) { sampler = 2; pGen *= pe; std::swap(spin[0], spin[1]); }          // OPP_SPIN_EXCH
         else { sampler = 1; pGen *= (1.0 - pe); }                                          // OPP_SPIN_NO_EXCH
     }
     double pGenHoles;
@@ -507,12 +516,17 @@ inline double pchb_double_get_pgen(const System &S, const int *ex) {
 }
 
 // gen_exc_sd, src/excitation_generators.F90:112-138
+// One number decides single / double; a double re-uses it, rescaled to [0,1), for the electron pair (see
+// pick_biased_elecs); a single continues with the second block of the attempt's stream (word 4).
 inline void gen_excit_pchb(const System &S, const int *nI, const uint64_t *ilutI, Stream &rng, Excitation &E) {
-    if (rng.draw() < S.p_singles) {
+    const double u = rng.draw53();
+    if (u < S.p_singles) {
+        rng.pos = 4;
         gen_uniform_single(S, nI, ilutI, rng, E);
         E.pgen = E.pgen * S.p_singles;
     } else {
-        gen_pchb_double(S, nI, ilutI, rng, E);
+        const double inv_1m_ps = 1.0 / (1.0 - S.p_singles);
+        gen_pchb_double(S, nI, ilutI, (u - S.p_singles) * inv_1m_ps, rng, E);
         E.pgen = E.pgen * S.p_doubles;
     }
 }
