@@ -353,21 +353,36 @@ __device__ __forceinline__ int trial_lookup(const Params &P, const Det<NW> &d, d
         pos = (pos + 1) & P.trial_ht_mask;
     }
 }
-// insert a key known to be absent (unique among concurrent inserters)
-__device__ __forceinline__ void ht_insert(const WalkerList &L, u64 h, long long slot, u64 start_pos) {
+// insert a key known to be absent (unique among concurrent inserters).  Returns true when a tombstone was recycled:
+// the caller counts those and lowers L.ctr[C_NTOMB] once per warp (a per-insert atomic on one address serialises).
+__device__ __forceinline__ bool ht_insert(const WalkerList &L, u64 h, long long slot, u64 start_pos) {
     const u64 entry = ((u64)(u32)(h >> 32) << 32) | (u64)(u32)slot;
     u64 pos = start_pos;
     u64 e = __ldcg(&L.ht[pos]);                 // L2 reads: other CTAs insert concurrently
     for (;;) {
         if (e == HT_EMPTY || e == HT_TOMB) {
             const u64 old = atomicCAS((unsigned long long *)&L.ht[pos], e, entry);
-            if (old == e) { if (e == HT_TOMB) atomicAdd((unsigned long long *)&L.ctr[C_NTOMB], (unsigned long long)-1ll); return; }
+            if (old == e) return e == HT_TOMB;
             e = old;                            // lost the race: judge the winner's value, no re-read
             continue;
         }
         pos = (pos + 1) & L.ht_mask;
         e = __ldcg(&L.ht[pos]);
     }
+}
+// RemoveHashDet, table part only: tombstones the entry; returns true when an entry was tombstoned.  The caller
+// pushes the slot on the free stack and counts the tombstone (k_walk aggregates both per CTA).
+template <int NW>
+__device__ __forceinline__ bool ht_tombstone(const WalkerList &L, const Det<NW> &d, u64 h, long long slot) {
+    u64 pos;
+    const long long s = ht_lookup<NW>(L, d, h, &pos);
+    if (s == slot) { L.ht[pos] = HT_TOMB; return true; }
+    return false;
+}
+// tombstones recycled by the inserts of this thread -> L.ctr[C_NTOMB], one atomic per warp (call with all lanes)
+__device__ __forceinline__ void ht_settle_tombs(const WalkerList &L, int delta) {
+    const int t = __reduce_add_sync(0xffffffffu, delta);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd((unsigned long long *)&L.ctr[C_NTOMB], (unsigned long long)(long long)t);
 }
 // RemoveHashDet (src/load_balancer.fpp:631-644): tombstone + push the slot on the free stack
 template <int NW>

@@ -1,9 +1,10 @@
 // The hot-path kernels of one FCIQMC iteration (PerformFCIMCycPar,
 // src/FciMCPar.F90:1177-1920), B200-first:
 //
-//   k_spawn            (spawn_kernel.cuh) loop over determinants (:1294-1758): initiator flags, energy
-//                      accumulators, spawning and death, staged through shared-memory queues;
-//                      k_spawn_heavy takes determinants with > 4096 attempts.
+//   k_walk, k_generate, k_evaluate, k_singles
+//                      (spawn_kernel.cuh) loop over determinants (:1294-1758): initiator flags, energy
+//                      accumulators, death; spawning attempts staged through global-memory queues;
+//                      k_generate_heavy takes determinants with > 4096 attempts.
 //   k_trial_energy     trial part of SumEContrib (fcimc_helper.F90:586-648).
 //   k_compress         CompressSpawnedList (Annihilation.F90:249-515) as an in-place hash merge of the
 //                      received spawn records; also merges the FreeSlot lists.
@@ -23,30 +24,6 @@
 #include "spawn_kernel.cuh"
 
 namespace ng {
-
-// ---- block-level reduction of per-thread statistics into per-block partials ---
-// acc[k] for the statistics listed in idx[k]; writes out[blockIdx.x * NECI_ST_COUNT + idx[k]]
-// (all other entries of the block row are zeroed by the caller's prologue).
-template <int N>
-__device__ __forceinline__ void block_flush_stats(const double (&acc)[N], const int (&idx)[N], double *out, double *s_red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int k = threadIdx.x; k < NECI_ST_COUNT; k += blockDim.x) out[(size_t)blockIdx.x * NECI_ST_COUNT + k] = 0.0;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const bool is_max = (idx[k] >= NECI_ST_FIRST_MAX && idx[k] <= NECI_ST_LAST_MAX) || idx[k] == NECI_ST_HIGHEST_POP;
-        const double v = is_max ? warp_max(acc[k]) : warp_sum(acc[k]);
-        if (lane == 0) s_red[k * 32 + warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < N) {
-        const int k = threadIdx.x;
-        const bool is_max = (idx[k] >= NECI_ST_FIRST_MAX && idx[k] <= NECI_ST_LAST_MAX) || idx[k] == NECI_ST_HIGHEST_POP;
-        double v = s_red[k * 32];
-        for (int w = 1; w < nw; ++w) v = is_max ? fmax(v, s_red[k * 32 + w]) : v + s_red[k * 32 + w];
-        out[(size_t)blockIdx.x * NECI_ST_COUNT + idx[k]] = v;
-    }
-}
 
 // final reduction over the partial rows of all kernels: one CTA per statistic, fixed
 // (launch-independent) summation tree, so results are reproducible run to run
@@ -198,13 +175,15 @@ __global__ void __launch_bounds__(NG_BLOCK) k_compress(Params P, WalkerList L, S
 template <int NW>
 __global__ void __launch_bounds__(NG_BLOCK) k_annihilate(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
     __shared__ double s_red[6 * 32];
+    __shared__ CtaReserveScratch<2> R;
+    int parity = 0, n_tomb = 0;
     const long long n = recv_count(SB, A);
     double acc[6] = {0, 0, 0, 0, 0, 0};     // annihilated, aborted, removed, born(round), merged, recv
-    const u32 lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long nloop = ((n + stride - 1) / stride) * stride;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
         bool ins = false;
+        long long freed = -1;                // slot emptied by this record (RemoveHashDet)
         if (i < n) {
             long long *rec = SB.recv + (size_t)i * SB.W;
             long long f = rec[NW + 1];
@@ -247,9 +226,8 @@ __global__ void __launch_bounds__(NG_BLOCK) k_annihilate(Params P, WalkerList L,
                             L.sgn[slot] = ns;
                             if (!tDet && fabs(ns) < 1.0e-12) {
                                 L.ht[pos] = HT_TOMB;
-                                atomicAdd((unsigned long long *)&L.ctr[C_NTOMB], 1ull);
-                                const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NFREEB], 1ull);
-                                L.freeB[k] = (int)slot;
+                                ++n_tomb;
+                                freed = slot;
                                 if (!P.t_semi_stochastic) fl = L.flg[slot];
                                 L.flg[slot] = fl | F_REMOVED;
                             }
@@ -274,15 +252,15 @@ __global__ void __launch_bounds__(NG_BLOCK) k_annihilate(Params P, WalkerList L,
                 }
             }
         }
-        const u32 m = __ballot_sync(0xffffffffu, ins);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd((unsigned long long *)&L.ctr[C_NINSERT], (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (ins) SB.ins_idx[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
-        }
+        // queue of new determinants and FreeSlot stack: one reservation per CTA and trip for both
+        unsigned long long *const counter[2] = {(unsigned long long *)&L.ctr[C_NINSERT], (unsigned long long *)&L.ctr[C_NFREEB]};
+        const bool push[2] = {ins, freed >= 0};
+        long long q[2];
+        cta_reserve<2>(R, parity, counter, push, q);
+        if (ins) SB.ins_idx[q[0]] = (int)i;
+        if (freed >= 0) L.freeB[q[1]] = (int)freed;
     }
+    ht_settle_tombs(L, n_tomb);
     const int idx[6] = {NECI_ST_ANNIHILATED, NECI_ST_NOABORTED, NECI_ST_NOREMOVED, NECI_ST_NOBORN,
                         NECI_ST_NSPAWNED_MERGED, NECI_ST_NSPAWNED_RECV};
     block_flush_stats<6>(acc, idx, partials, s_red);
@@ -292,9 +270,44 @@ __global__ void __launch_bounds__(NG_BLOCK) k_annihilate(Params P, WalkerList L,
 template <int NW, int SYS>
 __global__ void __launch_bounds__(NG_BLOCK) k_insert(Params P, WalkerList L, SpawnBuf SB, double *partials) {
     __shared__ double s_red[32];
+    __shared__ int s_cnt[2][32];
+    __shared__ long long s_old[2], s_new[2];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const long long n = L.ctr[C_NINSERT];
     double acc[1] = {0.0};
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    int n_reused = 0, parity = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n + stride - 1) / stride) * stride;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nloop; k += stride) {
+        const bool active = k < n;
+        // slots for the determinants of this trip: from the top of the FreeSlot stack while it lasts, then from the
+        // end of the list -- one pop and one extension per CTA instead of one atomic per determinant
+        const u32 m = __ballot_sync(0xffffffffu, active);
+        if (lane == 0) s_cnt[parity][warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long tot = 0;
+            for (u32 w = 0; w < nwarp; ++w) tot += s_cnt[parity][w];
+            long long old = 0, base_new = 0;
+            if (tot) {
+                old = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NFREEA], (unsigned long long)(-tot));
+                const long long avail = min(max(old, 0ll), tot);
+                if (tot > avail) base_new = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NLIST], (unsigned long long)(tot - avail));
+            }
+            s_old[parity] = old; s_new[parity] = base_new;
+        }
+        __syncthreads();
+        const int par = parity; parity ^= 1;
+        if (!active) continue;
+        long long rank = __popc(m & ((1u << lane) - 1u));
+        for (u32 w = 0; w < warp; ++w) rank += s_cnt[par][w];
+        const long long old = s_old[par], avail = max(old, 0ll);
+        long long slot;
+        if (rank < avail) slot = L.freeA[old - 1 - rank];
+        else {
+            slot = s_new[par] + (rank - avail);
+            if (slot + 1 >= L.cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 2ull); continue; }
+        }
         const long long i = SB.ins_idx[k];
         const long long *rec = SB.recv + (size_t)i * SB.W;
         Det<NW> d; d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
@@ -302,13 +315,6 @@ __global__ void __launch_bounds__(NG_BLOCK) k_insert(Params P, WalkerList L, Spa
         const int f = (int)(rec[NW + 1] & 0x7fffffffll) & ~F_REMOVED;
         const double hd = diagonal_matel<NW, SYS>(P, d) - P.hii;
         const double ho = off_diagonal_matel<NW, SYS>(P, d);
-        long long slot;
-        const long long fi = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NFREEA], (unsigned long long)-1ll) - 1;
-        if (fi >= 0) slot = L.freeA[fi];
-        else {
-            slot = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NLIST], 1ull);
-            if (slot + 1 >= L.cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 2ull); continue; }
-        }
         int ft = f;
         if (P.trial_ht) {                                   // hash_search_trial, load_balancer.fpp:586-611
             double amp;
@@ -318,9 +324,10 @@ __global__ void __launch_bounds__(NG_BLOCK) k_insert(Params P, WalkerList L, Spa
         store_det<NW>(L, slot, d);
         L.sgn[slot] = s; L.flg[slot] = ft; L.diagH[slot] = hd; L.offH[slot] = ho;
         const u64 h = det_hash64(d);
-        ht_insert(L, h, slot, h & L.ht_mask);
+        if (ht_insert(L, h, slot, h & L.ht_mask)) --n_reused;
         acc[0] += 1.0;
     }
+    ht_settle_tombs(L, n_reused);
     const int idx[1] = {NECI_ST_NINSERTED};
     block_flush_stats<1>(acc, idx, partials, s_red);
 }
@@ -403,27 +410,67 @@ __global__ void k_ht_rebuild(Params P, WalkerList L) {
         const int f = L.flg[i];
         if (fabs(s) >= 1.0e-12 || (f & F_DETERM)) {
             const u64 h = det_hash64(load_det<NW>(L, i));
-            ht_insert(L, h, i, h & L.ht_mask);
+            ht_insert(L, h, i, h & L.ht_mask);              // the table was cleared: no tombstones to recycle
         }
     }
 }
 
 // ---- upload / download (AoS ilut(0:NIfTot) <-> SoA) ------------------------------
 template <int NW, int SYS>
-__global__ void k_upload(Params P, WalkerList L, const long long *aos, long long n, const double *gd, const double *go, int W) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long *rec = aos + (size_t)i * W;
-        Det<NW> d; d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
-        const double s = __longlong_as_double(rec[NW]);
-        int f = (int)(rec[NW + 1] & 0x7fffffffll);
-        if (P.trial_ht) { double amp; f = (f & ~(F_TRIAL | F_CONNECTED)) | trial_lookup<NW>(P, d, &amp); L.trial_amp[i] = amp; }
-        store_det<NW>(L, i, d);
-        L.sgn[i] = s; L.flg[i] = f;
-        const bool live = fabs(s) >= 1.0e-12 || (f & F_DETERM);
-        L.diagH[i] = gd ? gd[i] : (live ? diagonal_matel<NW, SYS>(P, d) - P.hii : 0.0);
-        L.offH[i] = go ? go[i] : (live ? off_diagonal_matel<NW, SYS>(P, d) : 0.0);
-        if (live) { const u64 h = det_hash64(d); ht_insert(L, h, i, h & L.ht_mask); }
-        else { const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NFREEA], 1ull); L.freeA[k] = (int)i; }
+__global__ void __launch_bounds__(256) k_upload(Params P, WalkerList L, const long long *aos, long long n, const double *gd, const double *go, int W,
+                                                long long n_prev) {
+    // empty slots go to the FreeSlot stack through a per-warp stage: one global atomic per ~100 holes, not one per hole
+    __shared__ WarpStage<1, 128> s_free[8];
+    WarpStage<1, 128> &FB = s_free[threadIdx.x >> 5];
+    const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    int n_free = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n + stride - 1) / stride) * stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
+        bool hole = false;
+        if (i < n) {
+            const long long *rec = aos + (size_t)i * W;
+            Det<NW> d; d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
+            const double s = __longlong_as_double(rec[NW]);
+            int f = (int)(rec[NW + 1] & 0x7fffffffll);
+            if (P.trial_ht) { double amp; f = (f & ~(F_TRIAL | F_CONNECTED)) | trial_lookup<NW>(P, d, &amp); L.trial_amp[i] = amp; }
+            const bool live = fabs(s) >= 1.0e-12 || (f & F_DETERM);
+            // global_determinant_data: taken from the host when it passes it; otherwise kept when this slot already
+            // holds the same determinant from an earlier call (H_ii and H_0i are functions of the determinant), else
+            // recomputed (get_diagonal_matel / get_off_diagonal_matel)
+            double hd = 0.0, ho = 0.0;
+            if (gd && go) { hd = gd[i]; ho = go[i]; }
+            else if (live) {
+                const bool same = L.det0[i] == d.w[0] && (NW == 1 || L.det1[i] == d.w[NW - 1]) && (L.flg[i] & F_REMOVED) == 0 &&
+                                  i < n_prev;
+                hd = gd ? gd[i] : (same ? L.diagH[i] : diagonal_matel<NW, SYS>(P, d) - P.hii);
+                ho = go ? go[i] : (same ? L.offH[i] : off_diagonal_matel<NW, SYS>(P, d));
+            }
+            store_det<NW>(L, i, d);
+            L.sgn[i] = s; L.flg[i] = f; L.diagH[i] = hd; L.offH[i] = ho;
+            if (live) { const u64 h = det_hash64(d); ht_insert(L, h, i, h & L.ht_mask); }      // fresh table: no tombstones
+            else hole = true;
+        }
+        const u32 m = __ballot_sync(0xffffffffu, hole);
+        if (m) {
+            if (hole) FB.w[n_free + __popc(m & lt)][0] = (unsigned long long)i;
+            n_free += __popc(m);
+            __syncwarp();
+            if (n_free >= 96) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd((unsigned long long *)&L.ctr[C_NFREEA], (unsigned long long)n_free);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int j = lane; j < n_free; j += 32) L.freeA[base + j] = (int)FB.w[j][0];
+                n_free = 0;
+                __syncwarp();
+            }
+        }
+    }
+    if (n_free) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd((unsigned long long *)&L.ctr[C_NFREEA], (unsigned long long)n_free);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int j = lane; j < n_free; j += 32) L.freeA[base + j] = (int)FB.w[j][0];
     }
 }
 template <int NW>
@@ -897,12 +944,46 @@ __global__ void k_block_pops(Params P, WalkerList L, double *block_parts) {
     }
 }
 
+// Reservation of positions in per-destination segments for a CTA's records: the counts per destination are taken in
+// shared memory (one shared atomic per warp and destination) and ONE thread per destination reserves in the global
+// counter.  A global atomic per warp and destination -- eight of them on one cache line per warp at N = 8 -- is what
+// made the round-1 exchange grow with the number of ranks (0.08 / 0.14 / 0.21 ms at 2 / 4 / 8 GPUs): the L2 atomic unit
+// serialises them.  Records of one CTA and destination also become one contiguous run (~32 records at N = 8).
+// All threads of the CTA must call.  Returns the position, or -1 without a record.
+#define NG_MAX_PUSH_RANKS 64
+struct DestReserveScratch { int hist[NG_MAX_PUSH_RANKS]; unsigned long long base[NG_MAX_PUSH_RANKS]; };
+__device__ __forceinline__ long long dest_reserve(DestReserveScratch &R, unsigned long long *cnt, int nranks, bool has, int proc) {
+    const u32 lane = threadIdx.x & 31;
+    if ((int)threadIdx.x < nranks) R.hist[threadIdx.x] = 0;
+    __syncthreads();
+    int rank_in = 0;
+    {
+        const u32 active = __ballot_sync(0xffffffffu, has);
+        if (has) {
+            const u32 peers = __match_any_sync(active, proc);
+            const int leader = __ffs(peers) - 1;
+            int wbase = 0;
+            if ((int)lane == leader) wbase = atomicAdd(&R.hist[proc], __popc(peers));
+            wbase = __shfl_sync(peers, wbase, leader);
+            rank_in = wbase + __popc(peers & ((1u << lane) - 1u));
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nranks) {
+        const int c = R.hist[threadIdx.x];
+        R.base[threadIdx.x] = c ? atomicAdd(&cnt[threadIdx.x], (unsigned long long)c) : 0ull;
+    }
+    __syncthreads();
+    return has ? (long long)R.base[proc] + rank_in : -1;
+}
+
 // move_block (load_balancer.fpp:353-512), sender side, for all moved blocks at once: every occupied
 // determinant whose owner under the NEW mapping is another rank is appended to that rank's segment of the
 // spawn buffer (the wire format of the reference's MPISend: ilut incl. sign and flags) and removed here.
 template <int NW>
 __global__ void __launch_bounds__(NG_BLOCK) k_rebalance_pack(Params P, WalkerList L, SpawnBuf SB) {
     __shared__ int s_roi[NG_MAX_BASIS];
+    __shared__ DestReserveScratch R;
     for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) s_roi[i] = P.random_orb_index[i];
     __syncthreads();
     const long long n = L.ctr[C_NLIST];
@@ -925,7 +1006,17 @@ __global__ void __launch_bounds__(NG_BLOCK) k_rebalance_pack(Params P, WalkerLis
                 }
             }
         }
-        append_spawn<NW>(P, SB, L, s_roi, move, d, s, (long long)(f & ~F_REMOVED));
+        int proc = 0;
+        if (move) proc = __ldg(&P.lb_mapping[det_block<NW>(P, s_roi, d) - 1]);
+        const long long pos = dest_reserve(R, SB.cnt, P.nranks, move, proc);
+        if (move) {
+            if (pos >= SB.seg_cap) atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull);
+            else {
+                long long *rec = SB.buf + ((size_t)proc * SB.seg_cap + pos) * SB.W;
+                rec[0] = (long long)d.w[0]; if (NW > 1) rec[NW - 1] = (long long)d.w[NW - 1];
+                rec[NW] = __double_as_longlong(s); rec[NW + 1] = (long long)(f & ~F_REMOVED);
+            }
+        }
     }
 }
 // DetermineDetNode for the staged spawns of one iteration (nranks > 1): every lane hashes one spawn and appends it
@@ -933,6 +1024,7 @@ __global__ void __launch_bounds__(NG_BLOCK) k_rebalance_pack(Params P, WalkerLis
 template <int NW>
 __global__ void __launch_bounds__(NG_BLOCK) k_partition(Params P, WalkerList L, SpawnBuf SB) {
     __shared__ int s_roi[NG_MAX_BASIS];
+    __shared__ DestReserveScratch R;
     for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) s_roi[i] = P.random_orb_index[i];
     __syncthreads();
     long long n = (long long)*SB.stage_cnt; if (n > SB.stage_cap) n = SB.stage_cap;
@@ -947,7 +1039,17 @@ __global__ void __launch_bounds__(NG_BLOCK) k_partition(Params P, WalkerList L, 
             d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
             s = __longlong_as_double(rec[NW]); f = rec[NW + 1];
         }
-        append_spawn<NW>(P, SB, L, s_roi, has, d, s, f);
+        int proc = 0;
+        if (has) proc = __ldg(&P.lb_mapping[det_block<NW>(P, s_roi, d) - 1]);
+        const long long pos = dest_reserve(R, SB.cnt, P.nranks, has, proc);
+        if (has) {
+            if (pos >= SB.seg_cap) atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull);
+            else {
+                long long *rec = SB.buf + ((size_t)proc * SB.seg_cap + pos) * SB.W;
+                rec[0] = (long long)d.w[0]; if (NW > 1) rec[NW - 1] = (long long)d.w[NW - 1];
+                rec[NW] = __double_as_longlong(s); rec[NW + 1] = f;
+            }
+        }
     }
 }
 // receiver side: every received record is a new determinant here
@@ -1001,17 +1103,17 @@ __global__ void __launch_bounds__(256) k_push(SpawnBuf SB, PeerBox X, int nranks
     }
 }
 // Routing and pushing in one kernel (the spawning pass on several ranks with the peer-memory exchange): every lane
-// hashes one staged spawn (DetermineDetNode), the warp reserves positions per destination, and the record goes
+// hashes one staged spawn (DetermineDetNode), the CTA reserves positions per destination, and the record goes
 // straight into the destination rank's inbox over NVLink -- SpawnedParts' per-destination segments are never
 // materialised locally.  Ends like k_push: the last CTA posts the mailboxes.
 template <int NW>
 __global__ void __launch_bounds__(NG_BLOCK) k_partition_push(Params P, WalkerList L, SpawnBuf SB, PeerBox X, unsigned int seq) {
     __shared__ int s_roi[NG_MAX_BASIS];
+    __shared__ DestReserveScratch R;
     __shared__ bool s_last;
     for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) s_roi[i] = P.random_orb_index[i];
     __syncthreads();
     const int par = (int)(seq & 1u), nranks = P.nranks, rank = P.rank;
-    const u32 lane = threadIdx.x & 31;
     long long n = (long long)*SB.stage_cnt; if (n > SB.stage_cap) n = SB.stage_cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long nloop = ((n + stride - 1) / stride) * stride;
@@ -1026,14 +1128,8 @@ __global__ void __launch_bounds__(NG_BLOCK) k_partition_push(Params P, WalkerLis
             w_sign = rec[NW]; w_flag = rec[NW + 1];
             proc = __ldg(&P.lb_mapping[det_block<NW>(P, s_roi, d) - 1]);
         }
-        const u32 active = __ballot_sync(0xffffffffu, has);
+        const long long pos = dest_reserve(R, SB.cnt, nranks, has, proc);
         if (!has) continue;
-        const u32 peers = __match_any_sync(active, proc);
-        const int leader = __ffs(peers) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(&SB.cnt[proc], (unsigned long long)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const long long pos = (long long)base + __popc(peers & ((1u << lane) - 1u));
         if (pos >= SB.seg_cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull); continue; }
         long long *out = X.peer_seg[proc] + (((size_t)par * nranks + rank) * SB.seg_cap + pos) * SB.W;
         out[0] = (long long)d.w[0];

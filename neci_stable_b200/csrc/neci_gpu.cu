@@ -67,6 +67,7 @@ struct neci_gpu_engine {
     Params P;
     WalkerList L;
     SpawnBuf SB;
+    K1Queues K;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6];
     std::string err;
@@ -75,11 +76,13 @@ struct neci_gpu_engine {
     double *d_partials = nullptr, *d_stats = nullptr, *h_stats = nullptr;
     unsigned int *d_ticket = nullptr;
     long long *h_ctr = nullptr;
+    int rows_walk = 0, rows_gen = 0, rows_eval = 0, rows_sing = 0;   // K1 kernels (rows_spawn = their sum + rows_heavy)
     int rows_spawn = 0, rows_heavy = 0, rows_compress = 0, rows_annih = 0, rows_insert = 0, rows_list = 0, rows_trial = 0, rows_tau = 0, rows_total = 0;
     int grid_spawn = 0, grid_generic = 0, grid_spmv = 0;
     u32 stamp = 0;
     bool need_rebuild = false;
     long long n_launch = 0;            // kernels launched by this engine since init
+    long long n_resident = 0;          // length of the list in HBM (slots holding valid determinant data)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     long long ht_cap = 0;
     // semi-stochastic
@@ -212,6 +215,24 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
         CK(cudaMemset(SB.stage_cnt, 0, 8));
     }
     SB.heavy_cap = 1 << 16; SB.heavy = e->alloc<long long>(2 * SB.heavy_cap);
+    {
+        // queues between the K1 kernels: one parent per occupied determinant, one QE / QS entry per spawning attempt.
+        // Attempts per iteration = walkers (x AvMCExcits) on this rank, which MaxWalkersPart bounds the way it bounds
+        // the list (MemoryFacPart x InitWalkers, fcimc_initialisation.fpp:1650); an overflow is reported, not ignored.
+        K1Queues &K = e->K; memset(&K, 0, sizeof K);
+        K.qe_cap = std::max<long long>(M, 1 << 20); K.qs_cap = std::max<long long>(M, 1 << 20);
+        // the parent list is cut into one segment per CTA of k_walk (sized once the launch shape is known, below)
+        const long long par_cap = M + 256ll * NG_MAX_PAR_SEG;
+        K.par_d0 = e->alloc<u64>(par_cap); K.par_meta = e->alloc<u32>(par_cap);
+        if (e->nw > 1) K.par_d1 = e->alloc<u64>(par_cap);
+        K.par_cnt = e->alloc<u32>(NG_MAX_PAR_SEG);
+        K.qe = e->alloc<u64>((size_t)K.qe_cap * (e->nw + 3)); K.qs = e->alloc<u64>((size_t)K.qs_cap * (e->nw + 1));
+        K.cnt = e->alloc<unsigned long long>(4);
+        if (!K.par_d0 || !K.par_meta || !K.par_cnt || !K.qe || !K.qs || !K.cnt || (e->nw > 1 && !K.par_d1))
+            return e->fail("device allocation failed (attempt queues, max_walkers=%lld)", M);
+        CK(cudaMemset(K.par_cnt, 0, NG_MAX_PAR_SEG * 4));
+        CK(cudaMemset(K.cnt, 0, 32));
+    }
     if (!L.det0 || !L.sgn || !L.flg || !L.diagH || !L.offH || !L.ht || !L.freeA || !L.freeB || !L.ctr || !SB.buf ||
         !SB.recv || !SB.cnt || !SB.sht || !SB.ins_idx || !SB.heavy || (e->nw > 1 && !L.det1))
         return e->fail("device allocation failed (max_walkers=%lld, max_spawned=%lld)", M, Ms);
@@ -226,7 +247,6 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     const int nsm = prop.multiProcessorCount;
     e->grid_generic = nsm * 8;
-    e->grid_spawn = nsm * 4;       // refined per kernel variant below
     {
         int per_sm = 0;
 #if NG_SPMV_TMA
@@ -237,19 +257,25 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
 #endif
         e->grid_spmv = nsm * std::max(1, per_sm);
     }
-    e->rows_spawn = nsm * 8; e->rows_heavy = nsm * 4; e->rows_compress = e->grid_generic; e->rows_annih = e->grid_generic;
+    e->rows_compress = e->grid_generic; e->rows_annih = e->grid_generic;
     e->rows_insert = e->grid_generic; e->rows_list = e->grid_generic;
-    // K1 keeps its stage queues in dynamic shared memory (> 48 KB for two-word determinants); one persistent
-    // CTA per resident slot of every SM
+    // the K1 kernels run as persistent grids: one CTA per resident slot of every SM
     {
-        int per_sm = 0;
+        int w = 0, g = 0, ev = 0, sg = 0;
         NG_DISPATCH(e, {
-            CK(cudaFuncSetAttribute(k_spawn<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared<NW>)));
-            CK(cudaFuncSetAttribute(k_spawn_heavy<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared<NW>)));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spawn<NW, SYS>, K1_BLOCK, sizeof(K1Shared<NW>)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w, k_walk<NW, SYS>, NG_BLOCK, 0));
+            CK(cudaFuncSetAttribute(k_generate<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem_bytes<NW>()));
+            CK(cudaFuncSetAttribute(k_generate_heavy<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K1_GEN_BLOCK / 32) * sizeof(GenStage<NW>))));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g, k_generate<NW, SYS>, K1_GEN_BLOCK, gen_smem_bytes<NW>()));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ev, k_evaluate<NW, SYS>, NG_BLOCK, 0));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sg, k_singles<NW, SYS>, NG_BLOCK, 0));
         });
-        if (per_sm < 1) per_sm = 1;
-        e->rows_spawn = nsm * per_sm; e->rows_heavy = nsm * per_sm;
+        e->rows_walk = std::min(NG_MAX_PAR_SEG, nsm * std::max(1, w)); e->rows_gen = nsm * std::max(1, g); e->rows_heavy = e->rows_gen;
+        // every CTA of k_walk sees at most ceil(n_list / grid) + 256 slots: its segment of the parent list
+        e->K.par_nseg = e->rows_walk;
+        e->K.par_seg_cap = (M + e->rows_walk - 1) / e->rows_walk + 256;
+        e->rows_eval = nsm * std::max(1, ev); e->rows_sing = nsm * std::max(1, sg);
+        e->rows_spawn = e->rows_walk + e->rows_gen + e->rows_eval + e->rows_sing;
     }
     e->rows_trial = e->grid_generic;
     e->rows_tau = e->grid_generic;            // rows of k_death_magnitude, placed before the trial rows
@@ -459,7 +485,8 @@ int neci_gpu_upload_walkers(neci_gpu_engine *e, const int64_t *current_dets, int
     CK(cudaMemcpyAsync(&e->L.ctr[C_NLIST], &nn, 8, cudaMemcpyHostToDevice, e->stream));
     const int grid = (int)std::min<long long>(e->grid_generic, std::max<long long>(1, (n + 255) / 256));
     e->n_launch += 1;
-    NG_DISPATCH(e, (k_upload<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, e->L, e->d_aos, n, dgd, dgo, e->W)));
+    NG_DISPATCH(e, (k_upload<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, e->L, e->d_aos, n, dgd, dgo, e->W, e->n_resident)));
+    e->n_resident = n;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     return 0;
@@ -789,6 +816,7 @@ static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
     cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->h_stats[NECI_ST_TIME_COMM_MS] = ms;
     cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->h_stats[NECI_ST_TIME_ANNIHIL_MS] = ms;
     if (stats_out) memcpy(stats_out, e->h_stats, NECI_ST_COUNT * 8);
+    e->n_resident = std::min<long long>(e->h_ctr[C_NLIST], e->cfg.max_walkers - 1);
     // tombstones are recycled by inserts; rebuild the table when they pile up
     if (e->h_ctr[C_NTOMB] > e->ht_cap / 4) e->need_rebuild = true;
     const long long errf = e->h_ctr[C_ERR];
@@ -797,6 +825,7 @@ static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
     if (errf & 4) return e->fail("death probability > 2: algorithm unstable, reduce tau");
     if (errf & 16) return e->fail("excitation generator could not find an excitation after 250 attempts");
     if (errf & 32) return e->fail("heavy-determinant queue overflow");
+    if (errf & 128) return e->fail("spawning-attempt queue overflow (more walkers than max_walkers: increase MemoryFacPart)");
     if (errf & 256) return e->fail("peer-memory spawn exchange timed out waiting for another rank");
     return 0;
 }
@@ -816,6 +845,7 @@ static int begin_iteration(neci_gpu_engine *e) {
     CK(cudaMemsetAsync(e->SB.cnt, 0, (size_t)e->cfg.nranks * 8, e->stream));
     if (e->SB.stage_cnt) CK(cudaMemsetAsync(e->SB.stage_cnt, 0, 8, e->stream));
     CK(cudaMemsetAsync(&e->L.ctr[C_NHEAVY], 0, 8 * (C_COUNT - C_NHEAVY), e->stream));
+    CK(cudaMemsetAsync(e->K.cnt, 0, 32, e->stream));
     return 0;
 }
 
@@ -860,10 +890,19 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
         if (e->nw == 1) k_trial_energy<1><<<e->rows_trial, NG_BLOCK, 0, e->stream>>>(e->P, e->L, p_trial);
         else k_trial_energy<2><<<e->rows_trial, NG_BLOCK, 0, e->stream>>>(e->P, e->L, p_trial);
     }
-    e->n_launch += 2;
-    double *p_spawn = e->d_partials, *p_heavy = e->d_partials + (size_t)e->rows_spawn * NECI_ST_COUNT;
-    NG_DISPATCH(e, (k_spawn<NW, SYS><<<e->rows_spawn, K1_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_spawn)));
-    NG_DISPATCH(e, (k_spawn_heavy<NW, SYS><<<e->rows_heavy, K1_BLOCK, sizeof(K1Shared<NW>), e->stream>>>(e->P, e->L, e->SB, A, p_heavy)));
+    {
+        // the loop over determinants as four streaming kernels (spawn_kernel.cuh); PCHB singles have their own
+        const bool pchb = e->cfg.system_type == NECI_SYS_FCIDUMP_PCHB;
+        e->n_launch += pchb ? 5 : 4;
+        double *p_walk = e->d_partials, *p_gen = p_walk + (size_t)e->rows_walk * NECI_ST_COUNT,
+               *p_eval = p_gen + (size_t)e->rows_gen * NECI_ST_COUNT, *p_sing = p_eval + (size_t)e->rows_eval * NECI_ST_COUNT,
+               *p_heavy = p_sing + (size_t)e->rows_sing * NECI_ST_COUNT;
+        NG_DISPATCH(e, (k_walk<NW, SYS><<<e->rows_walk, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->K, A, p_walk)));
+        NG_DISPATCH(e, (k_generate<NW, SYS><<<e->rows_gen, K1_GEN_BLOCK, gen_smem_bytes<NW>(), e->stream>>>(e->P, e->L, e->K, A, p_gen)));
+        NG_DISPATCH(e, (k_generate_heavy<NW, SYS><<<e->rows_heavy, K1_GEN_BLOCK, (K1_GEN_BLOCK / 32) * sizeof(GenStage<NW>), e->stream>>>(e->P, e->L, e->SB, e->K, A, p_heavy)));
+        NG_DISPATCH(e, (k_evaluate<NW, SYS><<<e->rows_eval, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->K, A, p_eval)));
+        if (pchb) NG_DISPATCH(e, (k_singles<NW, SYS><<<e->rows_sing, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->K, A, p_sing)));
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[2], e->stream));
     if (e->cfg.nranks > 1) {

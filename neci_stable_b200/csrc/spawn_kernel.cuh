@@ -1,59 +1,46 @@
-// K1: the loop over determinants of PerformFCIMCycPar (src/FciMCPar.F90:1294-1758), fused:
+// K1: the loop over determinants of PerformFCIMCycPar (src/FciMCPar.F90:1294-1758):
 //   CalcParentFlag (fcimc_helper.F90:1036-1243), SumEContrib (:518-802), decide_num_to_spawn (:2160-2174),
 //   generate_excitation + attempt_create_normal (fcimc_pointed_fns.F90:178-491), create_particle
 //   (fcimc_helper.F90:152-308), walker_death / attempt_die_normal (:2279-2407, fcimc_pointed_fns.F90:573-705).
 //
-// B200 design (round 2: every warp is its own pipeline).  Walkers per determinant vary from 1 to 1e5+, a third of
-// the PCHB draws are null excitations and a tenth are singles with an O(nel) matrix element, so attempts -- not
-// determinants -- are the unit of parallelism and work moves between *stages* through queues so that every stage
-// runs with full warps.  In round 1 the queues were shared by a 256-thread CTA: block barriers between the stages
-// (14 % of the stall samples), atomics on the queue counters, a block-wide prefix sum per tile.  Now a warp owns
-// everything it needs -- its chunk of the list, its attempt map, its two queues, all in its private slice of shared
-// memory -- so the stages are separated by __syncwarp only, queue counters are warp-uniform registers (a push is a
-// ballot and a popcount), and no warp ever waits for another:
+// B200 design (round 2).  Walkers per determinant vary from 1 to 1e5+, a third of the PCHB draws are null
+// excitations and a tenth are singles with an O(nel) matrix element, so attempts -- not determinants -- are the unit
+// of parallelism and work moves between *stages* through queues so that every stage runs with full warps.  Round 1
+// ran all stages inside one persistent kernel (shared-memory queues, block barriers); its profile and that of a
+// warp-autonomous rewrite (profiles/r02_k1_*) show what bounds such a kernel on this chip: 110 KB of code against a
+// 32 KB instruction cache (L1.5) -- with the warps of an SM spread over the stages, "no instruction" became the first
+// stall reason (46 % of the samples in the warp-autonomous version).  So the stages are now four small kernels, each
+// with a code footprint that fits the instruction cache, connected by queues in global memory.  The queues are
+// written and read once, coalesced, and what of them does not stay in the 126 MB L2 goes over an HBM link this path
+// uses to a few per cent:
 //
-//   stage A  the warp loads a chunk of 32 x K1_SPT consecutive slots (all SoA streams of all its slots requested up
-//            front), one lane per slot: flags, energy sums, death, attempt count; parents (det, stream id, info)
-//            and the warp-wide prefix sum of the attempt counts go to the warp's shared memory
-//   stage B1 one lane per attempt (parents expand their index into an attempt -> parent map): draw the excitation from
-//            ONE Philox block.  valid doubles / lattice excitations -> queue QE {parent det, stream id, attempt,
-//            orbitals, pgen};  PCHB singles -> queue QS {parent det, stream id, attempt};  null draws stop here
-//   stage B2 whenever QE holds >= 32 entries: parity (popc), matrix element (2 UMAT loads), spawn weight, the
-//            rounding draw (its own Philox block, computed here with every lane busy), stochastic rounding,
-//            warp-aggregated append to the destination rank's segment
-//   stage B3 whenever QS holds >= 32 entries: uniform single + sltcnd_1 (loads batched 4 at a time), then as B2
+//   k_walk      one thread per slot of the list (all SoA streams of its slots requested up front): flags, energy
+//               sums, death, attempt count; occupied determinants -> parent list {det, attempts, info}
+//   k_generate  a CTA takes 512 parents, expands them into attempts (attempt -> parent map in shared memory), one
+//               thread per attempt draws the excitation from ONE Philox block.  valid doubles / lattice excitations ->
+//               queue QE {parent det, orbitals, pgen, attempt, info}; PCHB singles -> queue QS {parent det, attempt,
+//               info}; null draws stop here.  k_generate_heavy does the same for determinants above NG_HEAVY attempts.
+//   k_evaluate  one thread per QE entry: parity (popc), matrix element (2 UMAT loads), spawn weight, the rounding draw
+//               (its own Philox block), stochastic rounding, warp-aggregated append to the destination's segment
+//   k_singles   one thread per QS entry: uniform single + sltcnd_1 (loads batched 4 at a time), then as k_evaluate
 //
-// Statistics of stage A are reduced across the warp only when some lane has something to add (death, energy and
-// sign-flip events are rare per chunk), counts go through the integer reduction instruction.  Determinants above
-// NG_HEAVY attempts go to k_spawn_heavy, which spreads their attempts over all warps of the grid.  On several ranks
-// the appends of B2/B3 go to a staging list and k_partition_push routes them afterwards (kernels.cuh).  HPHF runs are
-// their own compile-time variant (NG_SYS_PCHB_HPHF).
+// Every stage runs with all lanes busy (the queues are compacted), no stage waits for another inside a kernel, and
+// each kernel gets the register allocation and occupancy that suit it.  On several ranks the appends go to a staging
+// list and k_partition_push routes them afterwards (kernels.cuh).  HPHF runs are their own compile-time variant
+// (NG_SYS_PCHB_HPHF).
 //
-// Random numbers are counter-based (device_common.cuh: Stream), so the result does not depend on the order in
-// which the queues are served, nor on which warp handles which chunk.
+// Random numbers are counter-based (device_common.cuh: Stream), so the result does not depend on the order in which
+// queue entries are written or served.
 #pragma once
 #include "device_system.cuh"
 
 namespace ng {
 
 #define NG_BLOCK 256         /* block size of the streaming kernels */
-#ifndef K1_BLOCK
-#define K1_BLOCK 256         /* threads per CTA of the spawning kernel (8 independent warps) */
-#endif
-#define K1_WARPS (K1_BLOCK / 32)
-#ifndef K1_CTAS_PER_SM       /* launch bound: resident CTAs per SM the register allocation must allow */
-#define K1_CTAS_PER_SM (1024 / K1_BLOCK)
-#endif
-#define NG_HEAVY 1024        /* attempts per determinant handled inside a chunk */
-#ifndef K1_SPT1
-#define K1_SPT1 4            /* slots per lane and chunk, one-word determinants */
-#endif
-#ifndef K1_SPT2
-#define K1_SPT2 2            /* slots per lane and chunk, two-word determinants */
-#endif
-template <int NW> __host__ __device__ constexpr int k1_spt() { return NW == 1 ? K1_SPT1 : K1_SPT2; }
-#define K1_QCAP 64           /* queue capacity per warp: < 32 entries before a push of at most 32 */
-#define K1_MAPW 128          /* attempts per window of the attempt -> parent map */
+#define NG_HEAVY 4096        /* attempts per determinant expanded inside a tile of k_generate */
+#define K1_GEN_BLOCK 256     /* threads per CTA of k_generate */
+#define K1_GEN_TILE 512      /* parents per tile */
+#define K1_MAPW 1024         /* attempts per window of the attempt -> parent map */
 
 struct SpawnBuf {
     long long *buf;          // SpawnedParts: nranks segments of seg_cap records (W words each)
@@ -92,47 +79,57 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// statistics accumulated by K1, in the order of their rows in K1Shared::wacc
-enum { W_NODIED = 0, W_NOBORN_D, W_ABORT, W_HF, W_DOUBS, W_ENUM, W_ENUMABS, W_INITSENUM, W_INITD, W_NINITD, W_INITW,
-       W_NINITW, W_ADDED, W_CHILD, W_CHILD_SING, W_VALID, W_INVALID, W_MAXSP, W_COUNT };
-
-// a warp's private slice of shared memory
-template <int NW> struct K1Warp {
-    static constexpr int CHUNK = 32 * k1_spt<NW>();
-    // parents of the current chunk
-    u64 p_d0[CHUNK];
-    u64 p_d1[(NW > 1) ? CHUNK : 1];
-    u64 p_h[CHUNK];
-    int p_off[CHUNK + 1];             // exclusive prefix sum of the attempt counts; [CHUNK] = total
-    unsigned char p_info[CHUNK];
-    unsigned char map[K1_MAPW];      // attempt (within the current window) -> parent index in the chunk
-    // QE: generated excitations waiting for their matrix element
-    u64 q_d0[K1_QCAP];
-    u64 q_d1[(NW > 1) ? K1_QCAP : 1];
-    u64 q_h[K1_QCAP];
-    double q_pgen[K1_QCAP];
-    u32 q_att[K1_QCAP];
-    u32 q_orbs[K1_QCAP];     // src1 | src2 << 8 | tgt1 << 16 | tgt2 << 24
-    u32 q_misc[K1_QCAP];     // info | ic << 8
-    // QS: PCHB single excitations still to be generated
-    u64 s_d0[K1_QCAP];
-    u64 s_d1[(NW > 1) ? K1_QCAP : 1];
-    u64 s_h[K1_QCAP];
-    u32 s_att[K1_QCAP];
-    u32 s_misc[K1_QCAP];
+// the queues between the K1 kernels, in global memory
+struct K1Queues {
+    // parent list: occupied determinants with 1 <= attempts <= NG_HEAVY.  Every CTA of k_walk owns the segment
+    // [cta * par_seg_cap, (cta + 1) * par_seg_cap) and leaves its count in par_cnt[cta]: no global atomics at all.
+    u64 *par_d0, *par_d1; u32 *par_meta;            // meta = attempts << 8 | info
+    u32 *par_cnt; int par_nseg; long long par_seg_cap;
+    // QE: generated excitations waiting for their matrix element, records of qe_rec<NW>() words:
+    //   det word(s), pgen, orbitals | attempt << 32 (orbitals = src1 | src2 << 8 | tgt1 << 16 | tgt2 << 24), info
+    u64 *qe;
+    // QS: PCHB single excitations still to be generated, records of qs_rec<NW>() words: det word(s), attempt | info << 32
+    u64 *qs;
+    long long qe_cap, qs_cap;
+    unsigned long long *cnt;                        // [Q_NQE], [Q_NQS]
 };
-template <int NW> struct K1Shared {
-    K1Warp<NW> w[K1_WARPS];
-    double wacc[K1_WARPS][W_COUNT];
-    int roi[NG_MAX_BASIS];           // RandomOrbIndex (append_spawn's DetermineDetNode; unused on one rank)
+enum { Q_NQE = 0, Q_NQS };
+template <int NW> __host__ __device__ constexpr int qe_rec() { return NW + 3; }
+template <int NW> __host__ __device__ constexpr int qs_rec() { return NW + 1; }
+// info bits of a parent: 1 negative sign, 2 initiator, 4 core determinant
+
+// shared-memory scratch of the attempt kernels: bloom and tau-search statistics (rare atomics)
+struct AttShared {
     int bloom_cnt[2];
     unsigned long long bloom_max[2];
     // tau search (log_spawn_magnitude): classes 0 singles, 1 doubles, 2 parallel doubles, 3 opposite-spin doubles
     int tau_cnt[4];
     unsigned long long tau_gamma[4];
 };
-// a warp's queue fill levels: identical in all lanes, kept in registers
-struct K1Queues { int qe, qs; };
+
+// ---- block-level reduction of per-thread statistics into per-block partials ---
+// acc[k] for the statistics listed in idx[k]; writes out[blockIdx.x * NECI_ST_COUNT + idx[k]]
+// (all other entries of the block row are zeroed here).  Fixed tree: reproducible for a fixed launch shape.
+template <int N>
+__device__ __forceinline__ void block_flush_stats(const double (&acc)[N], const int (&idx)[N], double *out, double *s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = threadIdx.x; k < NECI_ST_COUNT; k += blockDim.x) out[(size_t)blockIdx.x * NECI_ST_COUNT + k] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const bool is_max = (idx[k] >= NECI_ST_FIRST_MAX && idx[k] <= NECI_ST_LAST_MAX) || idx[k] == NECI_ST_HIGHEST_POP;
+        const double v = is_max ? warp_max(acc[k]) : warp_sum(acc[k]);
+        if (lane == 0) s_red[k * 32 + warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        const int k = threadIdx.x;
+        const bool is_max = (idx[k] >= NECI_ST_FIRST_MAX && idx[k] <= NECI_ST_LAST_MAX) || idx[k] == NECI_ST_HIGHEST_POP;
+        double v = s_red[k * 32];
+        for (int w = 1; w < nw; ++w) v = is_max ? fmax(v, s_red[k * 32 + w]) : v + s_red[k * 32 + w];
+        out[(size_t)blockIdx.x * NECI_ST_COUNT + idx[k]] = v;
+    }
+}
 
 // stochastic_round (src/lib/util_mod.fpp:182-204) with the random number drawn by the caller
 __device__ __forceinline__ double stochastic_round_r(double r, double u) {
@@ -169,27 +166,91 @@ __device__ __forceinline__ void append_spawn(const Params &P, const SpawnBuf &SB
     rec[NW] = __double_as_longlong(child);
     rec[NW + 1] = flags;
 }
-// The spawning kernel's own append.  On one rank this is create_particle itself.  On several ranks the spawn goes
-// to a staging list first and k_partition_push routes it afterwards: DetermineDetNode costs ~230 instructions, and
-// the partition kernel hashes with every lane busy and the record already on its way over NVLink.
-template <int NW>
-__device__ __forceinline__ void append_spawn_k1(const Params &P, const SpawnBuf &SB, const WalkerList &L, const int *roi,
-                                                bool has, const Det<NW> &detJ, double child, long long flags) {
-    if (P.nranks == 1) { append_spawn<NW>(P, SB, L, roi, has, detJ, child, flags); return; }
+
+// CTA-wide reservation of queue entries.  The L2 atomic unit serialises atomics on one address (~1 ns each): a
+// reservation per warp and round made k_generate a 0.5 ms queue for its two counters.  Here the warps of a CTA post
+// their counts in shared memory and ONE thread reserves for all of them; up to NQ queues are served by the same two
+// barriers.  All threads of the CTA must call, the same number of times (the scratch is double-buffered by call
+// parity, so a fast warp entering the next call cannot overwrite what a slow one still reads).
+template <int NQ> struct CtaReserveScratch {
+    int cnt[2][NQ][32];
+    unsigned long long off[2][NQ][32];       // global position of the first entry of every warp
+};
+template <int NQ>
+__device__ __forceinline__ void cta_reserve(CtaReserveScratch<NQ> &R, int &parity, unsigned long long *const (&counter)[NQ],
+                                            const bool (&push)[NQ], long long (&index)[NQ]) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    u32 m[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        m[q] = __ballot_sync(0xffffffffu, push[q]);
+        if (lane == 0) R.cnt[parity][q][warp] = __popc(m[q]);
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        const int q = threadIdx.x;
+        int tot = 0;
+        for (u32 w = 0; w < nwarp; ++w) tot += R.cnt[parity][q][w];
+        unsigned long long run = tot ? atomicAdd(counter[q], (unsigned long long)tot) : 0ull;
+        for (u32 w = 0; w < nwarp; ++w) { R.off[parity][q][w] = run; run += (unsigned long long)R.cnt[parity][q][w]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+        index[q] = push[q] ? (long long)R.off[parity][q][warp] + __popc(m[q] & ((1u << lane) - 1u)) : -1;
+    parity ^= 1;
+}
+
+// Warp-private staging of output records in shared memory.  A warp collects what its lanes produce and writes it out
+// in bulk: one global atomic per FLUSH records instead of one per trip, no block barrier, and the records of a
+// flush are contiguous (coalesced 8-byte stores).  The fill level is identical in all lanes (a register).
+//   REC: 64-bit words per record, CAP: records the buffer holds (>= FLUSH + 31).
+template <int REC, int CAP> struct WarpStage { unsigned long long w[CAP][REC]; };
+template <int REC, int CAP>
+__device__ __forceinline__ void warp_stage_flush(WarpStage<REC, CAP> &B, int &fill, unsigned long long *counter, long long cap,
+                                                 unsigned long long *dst, const WalkerList &L, unsigned long long err_bit) {
     const u32 lane = threadIdx.x & 31;
-    const u32 active = __ballot_sync(0xffffffffu, has);
-    if (!has) return;
-    const int leader = __ffs(active) - 1;
+    if (fill == 0) return;
     unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(SB.stage_cnt, (unsigned long long)__popc(active));
-    base = __shfl_sync(active, base, leader);
-    const long long pos = (long long)base + __popc(active & ((1u << lane) - 1u));
-    if (pos >= SB.stage_cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull); return; }
-    long long *rec = SB.stage + (size_t)pos * SB.W;
-    rec[0] = (long long)detJ.w[0];
-    if (NW > 1) rec[NW - 1] = (long long)detJ.w[NW - 1];
-    rec[NW] = __double_as_longlong(child);
-    rec[NW + 1] = flags;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)fill);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    int n = fill;
+    if ((long long)base + n > cap) { if (lane == 0) atomicOr((unsigned long long *)&L.ctr[C_ERR], err_bit); n = (int)max(0ll, cap - (long long)base); }
+    const unsigned long long *src = &B.w[0][0];
+    unsigned long long *out = dst + (size_t)base * REC;
+    for (int j = lane; j < n * REC; j += 32) out[j] = src[j];
+    fill = 0;
+    __syncwarp();
+}
+
+// The attempt kernels' own append (all lanes of the warp must call).  On one rank this is create_particle itself:
+// the record goes to SpawnedParts.  On several ranks the spawn goes to a staging list first and k_partition_push
+// routes it afterwards: DetermineDetNode costs ~230 instructions, and the partition kernel hashes with every lane busy
+// and the record already on its way over NVLink.  Records are staged per warp and written 32 or more at a time.
+#define NG_SPAWN_STAGE_CAP 64
+template <int NW> using SpawnStage = WarpStage<NW + 2, NG_SPAWN_STAGE_CAP>;
+template <int NW>
+__device__ __forceinline__ void spawn_stage_flush(const Params &P, const SpawnBuf &SB, const WalkerList &L, SpawnStage<NW> &B, int &fill) {
+    const bool staged = P.nranks > 1;
+    warp_stage_flush<NW + 2, NG_SPAWN_STAGE_CAP>(B, fill, staged ? SB.stage_cnt : &SB.cnt[0], staged ? SB.stage_cap : SB.seg_cap,
+                                                 (unsigned long long *)(staged ? SB.stage : SB.buf), L, 1ull);
+}
+template <int NW>
+__device__ __forceinline__ void append_spawn_k1(const Params &P, const SpawnBuf &SB, const WalkerList &L, SpawnStage<NW> &B, int &fill,
+                                                bool has, const Det<NW> &detJ, double child, long long flags) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 m = __ballot_sync(0xffffffffu, has);
+    if (m == 0) return;
+    if (has) {
+        unsigned long long *rec = B.w[fill + __popc(m & ((1u << lane) - 1u))];
+        rec[0] = detJ.w[0];
+        if (NW > 1) rec[NW - 1] = detJ.w[NW - 1];
+        rec[NW] = (unsigned long long)__double_as_longlong(child);
+        rec[NW + 1] = (unsigned long long)flags;
+    }
+    fill += __popc(m);
+    __syncwarp();
+    if (fill >= 32) spawn_stage_flush<NW>(P, SB, L, B, fill);
 }
 
 // per-thread accumulators of the attempt stages
@@ -198,17 +259,44 @@ struct AttAcc {
     int valid, invalid;
 };
 
-// attempt_create_normal (fcimc_pointed_fns.F90:178-491) for an excitation whose orbitals and pgen are known, followed
-// by create_particle.  `active` lanes hold a real entry; all lanes must call.  (h, att) name the attempt's stream:
-// the rounding number is the first of its RNG_ATT_ROUND stream.
-template <int NW, int SYS>
+__device__ __forceinline__ void att_shared_init(const Params &P, AttShared &S) {
+    if (threadIdx.x == 0) { S.bloom_cnt[0] = S.bloom_cnt[1] = 0; S.bloom_max[0] = S.bloom_max[1] = 0ull; }
+    if (threadIdx.x < 4) { S.tau_cnt[threadIdx.x] = 0; S.tau_gamma[threadIdx.x] = 0ull; }
+    __syncthreads();
+}
+// end of an attempt kernel: per-thread accumulators and the shared bloom / tau statistics -> this CTA's partial row
+__device__ __forceinline__ void att_flush(const WalkerList &L, AttShared &S, const AttAcc &a, double *partials, double *s_red) {
+    const double acc[6] = {a.child, a.child, a.child_sing, (double)a.valid, (double)a.invalid, a.maxsp};
+    const int idx[6] = {NECI_ST_NOBORN, NECI_ST_ACCEPTANCES, NECI_ST_SPAWNFROMSING, NECI_ST_NVALIDEXCITS, NECI_ST_NINVALIDEXCITS,
+                        NECI_ST_MAX_CYC_SPAWN};
+    block_flush_stats<6>(acc, idx, partials, s_red);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *row = partials + (size_t)blockIdx.x * NECI_ST_COUNT;
+        row[NECI_ST_BLOOM_COUNT_1] = (double)S.bloom_cnt[0];
+        row[NECI_ST_BLOOM_COUNT_2] = (double)S.bloom_cnt[1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            row[NECI_ST_TAU_GAMMA_SING + c] = __longlong_as_double((long long)S.tau_gamma[c]);
+            row[NECI_ST_TAU_CNT_SING + c] = (double)S.tau_cnt[c];
+        }
+        if (S.bloom_max[0]) atomicMax((unsigned long long *)&L.ctr[C_COUNT - 2], S.bloom_max[0]);
+        if (S.bloom_max[1]) atomicMax((unsigned long long *)&L.ctr[C_COUNT - 1], S.bloom_max[1]);
+    }
+}
+
+// attempt_create_normal (fcimc_pointed_fns.F90:178-491) for an excitation of level IC whose orbitals and pgen are
+// known, followed by create_particle.  `active` lanes hold a real entry; all lanes must call.  (h, att) name the
+// attempt's stream: the rounding number is the first of its RNG_ATT_ROUND stream.  B / fill: the warp's spawn stage.
+template <int NW, int SYS, int IC>
 __device__ __forceinline__ void evaluate_and_append(const Params &P, const WalkerList &L, const SpawnBuf &SB, const IterArgs &A,
-                                                    K1Shared<NW> &S, bool active, const Det<NW> &d, Excit<NW> &E, int info,
-                                                    u64 h, u32 att, AttAcc &acc) {
+                                                    AttShared &S, SpawnStage<NW> &B, int &fill, bool active, const Det<NW> &d,
+                                                    Excit<NW> &E, int info, u64 h, u32 att, AttAcc &acc) {
     bool has = false;
     double child = 0.0;
     long long cflags = 0;
     int tau_cls = -1;
+    E.ic = IC;
     if (active) {
         finalize_excit(d, E);
         bool cancelled = false;
@@ -229,7 +317,7 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
             if (P.t_tau_search) {
                 // log_spawn_magnitude (tau/tau_search_conventional.F90:138-260): gamma = |H_ij| / (prob / p_class)
                 double tp;
-                if (E.ic == 1) { tp = prob / P.p_singles; tau_cls = 0; }
+                if (IC == 1) { tp = prob / P.p_singles; tau_cls = 0; }
                 else {
                     tp = prob / P.p_doubles; tau_cls = 1;
                     if (P.t_consider_par_bias) {
@@ -258,9 +346,9 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
             if (fabs(nSpawn) > NG_EPS) {
                 const double ac = fabs(nSpawn);
                 acc.child += ac;                               // NoBorn and acceptances
-                if (E.ic == 1) acc.child_sing += ac;           // SpawnFromSing
+                if (IC == 1) acc.child_sing += ac;             // SpawnFromSing
                 if (ac > P.initiator_walk_no) {                // bloom statistics (rare)
-                    const int b = (E.ic == 1) ? 0 : 1;
+                    const int b = (IC == 1) ? 0 : 1;
                     atomicAdd(&S.bloom_cnt[b], 1);
                     atomicMax(&S.bloom_max[b], (unsigned long long)__double_as_longlong(ac));
                 }
@@ -276,13 +364,190 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
             if (m && (threadIdx.x & 31) == 0) atomicAdd(&S.tau_cnt[c], __popc(m));
         }
     }
-    append_spawn_k1<NW>(P, SB, L, S.roi, has, E.detJ, child, cflags);
+    append_spawn_k1<NW>(P, SB, L, B, fill, has, E.detJ, child, cflags);
 }
 
-// stage B1: one spawning attempt of parent (d, h, info), attempt index p.  All lanes must call.
+// ---------------------------------------------------------------------------------------------------------------
+// k_walk: CalcParentFlag, SumEContrib, decide_num_to_spawn and walker_death of every slot; the parents of this
+// iteration's attempts go to the parent list.  One thread per slot, two slots per trip (ten loads in flight).
+// ---------------------------------------------------------------------------------------------------------------
 template <int NW, int SYS>
-__device__ __forceinline__ void stage_generate(const Params &P, const WalkerList &L, const IterArgs &A, K1Warp<NW> &W,
-                                               K1Queues &Q, bool active, const Det<NW> &d, u64 h, int info, u32 p, AttAcc &acc) {
+__global__ void __launch_bounds__(NG_BLOCK, 4) k_walk(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
+    __shared__ double s_red[13 * 32];
+    __shared__ int s_npar;                                  // parents written by this CTA so far
+    __shared__ WarpStage<1, 128> s_free[NG_BLOCK / 32];     // slots emptied by this warp, flushed to the FreeSlot stack in bulk
+    WarpStage<1, 128> &FB = s_free[threadIdx.x >> 5];
+    const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    int n_free = 0, n_tomb = 0;
+    if (threadIdx.x == 0) s_npar = 0;
+    __syncthreads();
+    const long long seg0 = (long long)blockIdx.x * K.par_seg_cap;
+    const Det<NW> ref = ref_det<NW>(P);
+    const long long n_list = L.ctr[C_NLIST];
+    double c_died = 0.0, c_bornd = 0.0, c_abort = 0.0, c_hf = 0.0, c_doubs = 0.0, c_enum = 0.0, c_enumabs = 0.0,
+           c_initsenum = 0.0, c_initw = 0.0, c_ninitw = 0.0, c_initd = 0.0, c_ninitd = 0.0, c_added = 0.0;
+    constexpr int G = 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n_list + G * stride - 1) / (G * stride)) * (G * stride);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nloop; i0 += G * stride) {
+        double ld_s[G], ld_K[G], ld_O[G]; int ld_f[G]; Det<NW> ld_d[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const long long slot = i0 + g * stride;
+            ld_s[g] = 0.0; ld_K[g] = 0.0; ld_O[g] = 0.0; ld_f[g] = 0; ld_d[g].w[0] = 0; if (NW > 1) ld_d[g].w[NW - 1] = 0;
+            if (slot < n_list) {
+                ld_s[g] = __ldcs(&L.sgn[slot]); ld_d[g].w[0] = __ldcs(&L.det0[slot]);
+                if (NW > 1) ld_d[g].w[NW - 1] = __ldcs(&L.det1[slot]);
+                ld_f[g] = __ldcs(&L.flg[slot]); ld_K[g] = __ldcs(&L.diagH[slot]); ld_O[g] = __ldcs(&L.offH[slot]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const long long slot = i0 + g * stride;
+            int nsp = 0, info = 0;
+            bool removed = false;
+            Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
+            const double s = ld_s[g];
+            if (slot < n_list && fabs(s) >= 1.0e-12) {
+                d = ld_d[g];
+                int f = ld_f[g];
+                const int f0 = f;
+                const double Kd = ld_K[g], O = ld_O[g];
+                const bool core = (f & F_DETERM) != 0;
+                const int exl = excit_level_ref<NW, sys_hphf(SYS)>(ref, d);        // FindBitExcitLevel(..., t_hphf_ic = .true.)
+                const double as = fabs(s);
+                // CalcParentFlag / TestInitiator_explicit (fcimc_helper.F90:1036-1243)
+                if (P.t_trunc_initiator) {
+                    const bool was = (f & F_INIT) != 0;
+                    const bool initiator = parent_is_initiator(P, was, as, exl, core);
+                    if (initiator != was) c_added += initiator ? 1.0 : -1.0;
+                    if (initiator) { c_initd += 1.0; c_initw += as; f |= F_INIT; }
+                    else { c_ninitd += 1.0; c_ninitw += as; f &= ~F_INIT; }
+                }
+                // SumEContrib (fcimc_helper.F90:518-802)
+                if (exl == 0) c_hf += s;
+                if (exl == 2) c_doubs += as;
+                const double dE = O * s;
+                c_enum += dE; c_enumabs += fabs(dE);
+                if (f & F_INIT) c_initsenum += dE;
+                const u64 h = det_hash64(d);
+                // decide_num_to_spawn (fcimc_helper.F90:2160-2174)
+                {
+                    const double x = s * P.av_mc_excits;
+                    nsp = abs((int)x);
+                    if (fabs(fabs(x) - (double)nsp) > 1.e-12) {
+                        Stream rng(P.seed, A.iter, h, 0, RNG_NSPAWN);
+                        if ((fabs(x) - (double)nsp) > rng.draw53()) ++nsp;
+                    }
+                }
+                info = (s < 0.0 ? 1 : 0) | ((f & F_INIT) ? 2 : 0) | (core ? 4 : 0);
+                // walker_death / attempt_die_normal (fcimc_helper.F90:2279-2407, fcimc_pointed_fns.F90:573-705)
+                // tDeathBeforeComms: here with t_core_die_ = .false. (FciMCPar.F90:1752-1756); otherwise
+                // perform_death_all_walkers (fcimc_helper.F90:2253-2277) would run it after the loop for every
+                // determinant, core ones included -- death of slot j touches only slot j, so it is fused here too
+                double news = s;
+                if (!core || !P.t_death_before_comms) {
+                    const double fac = A.tau * (Kd - A.diag_sft);
+                    if (fac > 2.0) atomicOr((unsigned long long *)&L.ctr[C_ERR], 4ull);
+                    double iDie;
+                    if (P.t_all_real_coeff) iDie = fac * as;
+                    else {
+                        double rat = fac * as;
+                        iDie = (double)(long long)rat;
+                        rat = rat - iDie;
+                        Stream rng(P.seed, A.iter, h, 0, RNG_DEATH);
+                        if (fabs(rat) > rng.draw53()) iDie += (rat < 0.0 || (rat == 0.0 && signbit(rat))) ? -1.0 : 1.0;
+                    }
+                    c_died += fmin(iDie, as);
+                    c_bornd += fmax(iDie - as, 0.0);
+                    news = s - (iDie * dsign(1.0, s));
+                    if (P.t_trunc_initiator && fabs(news) > 1.0e-12 && ((news > 0.0) != (s > 0.0))) {
+                        c_abort += fabs(news);
+                        if (f & F_INIT) c_added -= 1.0;
+                        news = 0.0;
+                    }
+                    if (!(fabs(news) > 1.0e-12) && !core) {
+                        if (P.t_trunc_initiator && (f & F_INIT)) c_added -= 1.0;
+                        if (ht_tombstone<NW>(L, d, h, slot)) ++n_tomb;     // RemoveHashDet; the free-slot push follows below
+                        removed = true;
+                        f |= F_REMOVED;
+                        news = 0.0;
+                    }
+                }
+                if (news != s) L.sgn[slot] = news;
+                if (f != f0) L.flg[slot] = f;
+                if (nsp > NG_HEAVY) {
+                    const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NHEAVY], 1ull);
+                    if (k < SB.heavy_cap) { SB.heavy[2 * k] = slot; SB.heavy[2 * k + 1] = ((long long)nsp << 8) | info; }
+                    else atomicOr((unsigned long long *)&L.ctr[C_ERR], 32ull);
+                    nsp = 0;
+                }
+            }
+            // parent list: the CTA's own segment, one shared-memory atomic per warp
+            {
+                const u32 m = __ballot_sync(0xffffffffu, nsp > 0);
+                if (m) {
+                    int base = 0;
+                    if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(&s_npar, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                    if (nsp > 0) {
+                        const long long ql = base + __popc(m & lt);
+                        if (ql >= K.par_seg_cap) atomicOr((unsigned long long *)&L.ctr[C_ERR], 128ull);
+                        else {
+                            const long long q = seg0 + ql;
+                            K.par_d0[q] = d.w[0]; if (NW > 1) K.par_d1[q] = d.w[NW - 1];
+                            K.par_meta[q] = ((u32)nsp << 8) | (u32)info;
+                        }
+                    }
+                }
+            }
+            // FreeSlot stack: staged per warp
+            {
+                const u32 m = __ballot_sync(0xffffffffu, removed);
+                if (m) {
+                    if (removed) FB.w[n_free + __popc(m & lt)][0] = (unsigned long long)slot;
+                    n_free += __popc(m);
+                    __syncwarp();
+                    if (n_free >= 96) {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd((unsigned long long *)&L.ctr[C_NFREEB], (unsigned long long)n_free);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        for (int j = lane; j < n_free; j += 32) L.freeB[base + j] = (int)FB.w[j][0];
+                        n_free = 0;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    if (n_free) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd((unsigned long long *)&L.ctr[C_NFREEB], (unsigned long long)n_free);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int j = lane; j < n_free; j += 32) L.freeB[base + j] = (int)FB.w[j][0];
+    }
+    ht_settle_tombs(L, n_tomb);
+    __syncthreads();
+    if (threadIdx.x == 0) K.par_cnt[blockIdx.x] = (u32)min((long long)s_npar, K.par_seg_cap);
+    const double acc[13] = {c_died, c_bornd, c_abort, c_hf, c_doubs, c_enum, c_enumabs, c_initsenum, c_initd, c_ninitd, c_initw,
+                            c_ninitw, c_added};
+    const int idx[13] = {NECI_ST_NODIED, NECI_ST_NOBORN, NECI_ST_NOABORTED, NECI_ST_HFCYC, NECI_ST_NOATDOUBS, NECI_ST_ENUMCYC,
+                         NECI_ST_ENUMCYCABS, NECI_ST_INITSENUMCYC, NECI_ST_NOINITDETS, NECI_ST_NONONINITDETS, NECI_ST_NOINITWALK,
+                         NECI_ST_NONONINITWALK, NECI_ST_NOADDEDINITIATORS};
+    block_flush_stats<13>(acc, idx, partials, s_red);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_generate: one spawning attempt per thread
+// ---------------------------------------------------------------------------------------------------------------
+// stage B1: attempt index p of parent (d, h, info): draw the excitation, stage it for QE / QS.  All lanes must call.
+#define NG_QE_STAGE_CAP 128      /* flushed at >= 96 */
+#define NG_QS_STAGE_CAP 64       /* flushed at >= 32 */
+template <int NW> struct GenStage { WarpStage<qe_rec<NW>(), NG_QE_STAGE_CAP> e; WarpStage<qs_rec<NW>(), NG_QS_STAGE_CAP> s; };
+template <int NW, int SYS>
+__device__ __forceinline__ void generate_and_push(const Params &P, const WalkerList &L, const K1Queues &K, const IterArgs &A,
+                                                  GenStage<NW> &G, int &fill_e, int &fill_s, bool active,
+                                                  const Det<NW> &d, u64 h, int info, u32 p, AttAcc &acc) {
     const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     bool push_e = false, push_s = false;
     Excit<NW> E;
@@ -291,7 +556,7 @@ __device__ __forceinline__ void stage_generate(const Params &P, const WalkerList
         Stream rng(P.seed, A.iter, h, p, RNG_ATTEMPT);
         if (sys_pchb(SYS)) {
             const double u = rng.draw53();                               // gen_exc_sd
-            if (u < P.p_singles) push_s = true;                          // single: generated in stage B3
+            if (u < P.p_singles) push_s = true;                          // single: generated by k_singles
             else { gen_pchb_double(P, d, (u - P.p_singles) * P.inv_1m_ps, rng, E); E.pgen = E.pgen * P.p_doubles; }
         } else generate_excitation_core<NW, SYS>(P, d, rng, E);
         if (!push_s) {
@@ -300,424 +565,266 @@ __device__ __forceinline__ void stage_generate(const Params &P, const WalkerList
             else acc.invalid += 1;
         }
     }
-    const u32 me = __ballot_sync(0xffffffffu, push_e);
-    if (push_e) {
-        const int q = Q.qe + __popc(me & lt);
-        W.q_d0[q] = d.w[0]; if (NW > 1) W.q_d1[q] = d.w[NW - 1];
-        W.q_h[q] = h; W.q_att[q] = p; W.q_pgen[q] = E.pgen;
-        W.q_orbs[q] = (u32)E.src1 | ((u32)E.src2 << 8) | ((u32)E.tgt1 << 16) | ((u32)E.tgt2 << 24);
-        W.q_misc[q] = (u32)info | ((u32)E.ic << 8);
-    }
-    Q.qe += __popc(me);
-    if (sys_pchb(SYS)) {
-        const u32 ms = __ballot_sync(0xffffffffu, push_s);
-        if (push_s) {
-            const int q = Q.qs + __popc(ms & lt);
-            W.s_d0[q] = d.w[0]; if (NW > 1) W.s_d1[q] = d.w[NW - 1];
-            W.s_h[q] = h; W.s_att[q] = p; W.s_misc[q] = (u32)info;
-        }
-        Q.qs += __popc(ms);
-    }
-    __syncwarp();
-}
-
-// stage B2: serve n <= 32 entries from the top of QE
-template <int NW, int SYS>
-__device__ __forceinline__ void stage_evaluate(const Params &P, const WalkerList &L, const SpawnBuf &SB, const IterArgs &A,
-                                               K1Shared<NW> &S, K1Warp<NW> &W, int first, int n, AttAcc &acc) {
-    const int lane = threadIdx.x & 31;
-    const int i = first + lane;
-    const bool active = lane < n;
-    Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
-    Excit<NW> E; E.ic = 2; E.src1 = E.src2 = E.tgt1 = E.tgt2 = 1; E.pgen = 1.0; E.valid = active; E.err = 0; E.detJ = d; E.parity = false;
-    int info = 0; u64 h = 0; u32 att = 0;
-    if (active) {
-        d.w[0] = W.q_d0[i]; if (NW > 1) d.w[NW - 1] = W.q_d1[i];
-        const u32 o = W.q_orbs[i], m = W.q_misc[i];
-        E.src1 = o & 0xff; E.src2 = (o >> 8) & 0xff; E.tgt1 = (o >> 16) & 0xff; E.tgt2 = o >> 24;
-        E.ic = (m >> 8) & 0xff; info = m & 0xff;
-        E.pgen = W.q_pgen[i]; h = W.q_h[i]; att = W.q_att[i];
-    }
-    __syncwarp();                                           // the entries are in registers: the queue may be refilled
-    evaluate_and_append<NW, SYS>(P, L, SB, A, S, active, d, E, info, h, att, acc);
-}
-
-// stage B3 (PCHB only): serve n <= 32 deferred singles from the top of QS
-template <int NW, int SYS>
-__device__ __forceinline__ void stage_singles(const Params &P, const WalkerList &L, const SpawnBuf &SB, const IterArgs &A,
-                                              K1Shared<NW> &S, K1Warp<NW> &W, int first, int n, AttAcc &acc) {
-    const int lane = threadIdx.x & 31;
-    const int i = first + lane;
-    bool active = lane < n;
-    Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
-    Excit<NW> E; E.ic = 1; E.src1 = E.src2 = E.tgt1 = E.tgt2 = 1; E.pgen = 1.0; E.valid = false; E.err = 0; E.detJ = d; E.parity = false;
-    int info = 0; u64 h = 0; u32 att = 0;
-    if (active) {
-        d.w[0] = W.s_d0[i]; if (NW > 1) d.w[NW - 1] = W.s_d1[i];
-        info = (int)W.s_misc[i]; h = W.s_h[i]; att = W.s_att[i];
-    }
-    __syncwarp();
-    if (active) {
-        Stream rng(P.seed, A.iter, h, att, RNG_ATTEMPT, 4);     // the first block chose "single"; singles draw from word 4
-        gen_uniform_single(P, d, rng, E);
-        E.pgen = E.pgen * P.p_singles;
-        if (E.err) atomicOr((unsigned long long *)&L.ctr[C_ERR], 16ull);
-        if (E.valid) acc.valid += 1;
-        else { acc.invalid += 1; active = false; }
-    }
-    evaluate_and_append<NW, SYS>(P, L, SB, A, S, active, d, E, info, h, att, acc);
-}
-
-// serve the queues while they hold at least `level` entries (level = 32 keeps every stage at full width,
-// level = 1 drains).  Must be called by the whole warp.
-template <int NW, int SYS>
-__device__ __forceinline__ void serve_queues(const Params &P, const WalkerList &L, const SpawnBuf &SB, const IterArgs &A,
-                                             K1Shared<NW> &S, K1Warp<NW> &W, K1Queues &Q, int level, AttAcc &acc) {
-    while (Q.qe >= level) {
-        const int n = min(Q.qe, 32);
-        Q.qe -= n;
-        stage_evaluate<NW, SYS>(P, L, SB, A, S, W, Q.qe, n, acc);
-    }
-    if (sys_pchb(SYS)) {
-        while (Q.qs >= level) {
-            const int n = min(Q.qs, 32);
-            Q.qs -= n;
-            stage_singles<NW, SYS>(P, L, SB, A, S, W, Q.qs, n, acc);
-        }
-    }
-}
-
-template <int NW>
-__device__ __forceinline__ void k1_init_shared(const Params &P, K1Shared<NW> &S) {
-#pragma unroll 1
-    for (int i = threadIdx.x; i < P.nbasis; i += K1_BLOCK) S.roi[i] = P.random_orb_index[i];
-    for (int i = threadIdx.x; i < K1_WARPS * W_COUNT; i += K1_BLOCK) (&S.wacc[0][0])[i] = 0.0;
-    if (threadIdx.x == 0) { S.bloom_cnt[0] = S.bloom_cnt[1] = 0; S.bloom_max[0] = S.bloom_max[1] = 0ull; }
-    if (threadIdx.x < 4) { S.tau_cnt[threadIdx.x] = 0; S.tau_gamma[threadIdx.x] = 0ull; }
-}
-
-// end of kernel: per-thread attempt accumulators -> per-warp rows -> one partial row per CTA
-template <int NW>
-__device__ __forceinline__ void k1_flush(const WalkerList &L, K1Shared<NW> &S, const AttAcc &acc, double *partials, bool with_stage_a) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double c = warp_sum(acc.child), cs = warp_sum(acc.child_sing), mx = warp_max(acc.maxsp);
-    const int v = __reduce_add_sync(0xffffffffu, acc.valid), iv = __reduce_add_sync(0xffffffffu, acc.invalid);
-    if (lane == 0) {
-        S.wacc[warp][W_CHILD] = c; S.wacc[warp][W_CHILD_SING] = cs; S.wacc[warp][W_VALID] = (double)v; S.wacc[warp][W_INVALID] = (double)iv;
-        S.wacc[warp][W_MAXSP] = mx;
-    }
-    double *row = partials + (size_t)blockIdx.x * NECI_ST_COUNT;
-    for (int k = threadIdx.x; k < NECI_ST_COUNT; k += K1_BLOCK) row[k] = 0.0;
-    __syncthreads();
-    if (threadIdx.x < W_COUNT) {
-        const int k = threadIdx.x;
-        double t = S.wacc[0][k];
-        for (int w = 1; w < K1_WARPS; ++w) t = (k == W_MAXSP) ? fmax(t, S.wacc[w][k]) : t + S.wacc[w][k];
-        S.wacc[0][k] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double *t = S.wacc[0];
-        row[NECI_ST_NOBORN] = t[W_CHILD] + (with_stage_a ? t[W_NOBORN_D] : 0.0);
-        row[NECI_ST_ACCEPTANCES] = t[W_CHILD];
-        row[NECI_ST_SPAWNFROMSING] = t[W_CHILD_SING];
-        row[NECI_ST_NVALIDEXCITS] = t[W_VALID];
-        row[NECI_ST_NINVALIDEXCITS] = t[W_INVALID];
-        row[NECI_ST_MAX_CYC_SPAWN] = t[W_MAXSP];
-        row[NECI_ST_BLOOM_COUNT_1] = (double)S.bloom_cnt[0];
-        row[NECI_ST_BLOOM_COUNT_2] = (double)S.bloom_cnt[1];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            row[NECI_ST_TAU_GAMMA_SING + c] = __longlong_as_double((long long)S.tau_gamma[c]);
-            row[NECI_ST_TAU_CNT_SING + c] = (double)S.tau_cnt[c];
-        }
-        if (with_stage_a) {
-            row[NECI_ST_NODIED] = t[W_NODIED]; row[NECI_ST_NOABORTED] = t[W_ABORT]; row[NECI_ST_HFCYC] = t[W_HF];
-            row[NECI_ST_NOATDOUBS] = t[W_DOUBS]; row[NECI_ST_ENUMCYC] = t[W_ENUM]; row[NECI_ST_ENUMCYCABS] = t[W_ENUMABS];
-            row[NECI_ST_INITSENUMCYC] = t[W_INITSENUM]; row[NECI_ST_NOINITDETS] = t[W_INITD];
-            row[NECI_ST_NONONINITDETS] = t[W_NINITD]; row[NECI_ST_NOINITWALK] = t[W_INITW];
-            row[NECI_ST_NONONINITWALK] = t[W_NINITW]; row[NECI_ST_NOADDEDINITIATORS] = t[W_ADDED];
-        }
-        if (S.bloom_max[0]) atomicMax((unsigned long long *)&L.ctr[C_COUNT - 2], S.bloom_max[0]);
-        if (S.bloom_max[1]) atomicMax((unsigned long long *)&L.ctr[C_COUNT - 1], S.bloom_max[1]);
-    }
-}
-
-// a statistic of stage A summed over the warp into the warp's row -- only when some lane has something to add
-// (the sums are taken in chunk order by one lane, so they are reproducible run to run)
-__device__ __forceinline__ void k1_add_stat(double *row, int k, double v) {
-    if (__any_sync(0xffffffffu, v != 0.0)) {
-        const double t = warp_sum(v);
-        if ((threadIdx.x & 31) == 0) row[k] += t;
-    }
-}
-
-// stage A of one chunk: flags, energy sums, death and attempt counts of 32 x SPT slots; leaves the parents and the
-// exclusive prefix sum of their attempt counts in the warp's shared memory.  nsp_k / off_k: this lane's slots.
-template <int NW, int SYS>
-__device__ __forceinline__ void k1_stage_a(const Params &P, const WalkerList &L, const SpawnBuf &SB, const IterArgs &A, K1Shared<NW> &S,
-                                           K1Warp<NW> &W, const Det<NW> &ref, long long chunk, long long n_list, int &T) {
-    constexpr int SPT = k1_spt<NW>();
-    constexpr int CHUNK = 32 * SPT;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double c_died = 0.0, c_bornd = 0.0, c_abort = 0.0, c_hf = 0.0, c_doubs = 0.0, c_enum = 0.0, c_enumabs = 0.0,
-           c_initsenum = 0.0, c_initw = 0.0, c_ninitw = 0.0;
-    int c_initd = 0, c_ninitd = 0, c_added = 0;
-    // the slots of a lane are taken two at a time: all streams of both are requested before anything is consumed (one
-    // HBM round trip per pair; four slots at once cost 36 live registers and spilled)
-    constexpr int G = (SPT >= 2) ? 2 : 1;
-#pragma unroll 1
-    for (int k0 = 0; k0 < SPT; k0 += G) {
-    double ld_s[G], ld_K[G], ld_O[G]; int ld_f[G]; Det<NW> ld_d[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const long long slot = chunk * CHUNK + (k0 + g) * 32 + lane;
-        ld_s[g] = 0.0; ld_K[g] = 0.0; ld_O[g] = 0.0; ld_f[g] = 0; ld_d[g].w[0] = 0; if (NW > 1) ld_d[g].w[NW - 1] = 0;
-        if (slot < n_list) {
-            ld_s[g] = __ldcs(&L.sgn[slot]); ld_d[g].w[0] = __ldcs(&L.det0[slot]);
-            if (NW > 1) ld_d[g].w[NW - 1] = __ldcs(&L.det1[slot]);
-            ld_f[g] = __ldcs(&L.flg[slot]); ld_K[g] = __ldcs(&L.diagH[slot]); ld_O[g] = __ldcs(&L.offH[slot]);
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const int kk = k0 + g;
-        const int idx = kk * 32 + lane;
-        const long long slot = chunk * CHUNK + idx;
-        int nsp = 0;
-        unsigned char info = 0;
-        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
-        u64 h = 0;
-        const double s = ld_s[g];
-        if (slot < n_list && fabs(s) >= 1.0e-12) {
-            d = ld_d[g];
-            int f = ld_f[g];
-            const int f0 = f;
-            const double K = ld_K[g], O = ld_O[g];
-            const bool core = (f & F_DETERM) != 0;
-            const int exl = excit_level_ref<NW, sys_hphf(SYS)>(ref, d);        // FindBitExcitLevel(..., t_hphf_ic = .true.)
-            const double as = fabs(s);
-            // CalcParentFlag / TestInitiator_explicit (fcimc_helper.F90:1036-1243)
-            if (P.t_trunc_initiator) {
-                const bool was = (f & F_INIT) != 0;
-                const bool initiator = parent_is_initiator(P, was, as, exl, core);
-                if (initiator != was) c_added += initiator ? 1 : -1;
-                if (initiator) { c_initd += 1; c_initw += as; f |= F_INIT; }
-                else { c_ninitd += 1; c_ninitw += as; f &= ~F_INIT; }
-            }
-            // SumEContrib (fcimc_helper.F90:518-802)
-            if (exl == 0) c_hf += s;
-            if (exl == 2) c_doubs += as;
-            const double dE = O * s;
-            c_enum += dE; c_enumabs += fabs(dE);
-            if (f & F_INIT) c_initsenum += dE;
-            h = det_hash64(d);
-            // decide_num_to_spawn (fcimc_helper.F90:2160-2174)
-            {
-                const double x = s * P.av_mc_excits;
-                nsp = abs((int)x);
-                if (fabs(fabs(x) - (double)nsp) > 1.e-12) {
-                    Stream rng(P.seed, A.iter, h, 0, RNG_NSPAWN);
-                    if ((fabs(x) - (double)nsp) > rng.draw53()) ++nsp;
-                }
-            }
-            info = (unsigned char)((s < 0.0 ? 1 : 0) | ((f & F_INIT) ? 2 : 0) | (core ? 4 : 0));
-            // walker_death / attempt_die_normal (fcimc_helper.F90:2279-2407, fcimc_pointed_fns.F90:573-705)
-            // tDeathBeforeComms: here with t_core_die_ = .false. (FciMCPar.F90:1752-1756); otherwise
-            // perform_death_all_walkers (fcimc_helper.F90:2253-2277) would run it after the loop for every
-            // determinant, core ones included -- death of slot j touches only slot j, so it is fused here too
-            double news = s;
-            if (!core || !P.t_death_before_comms) {
-                const double fac = A.tau * (K - A.diag_sft);
-                if (fac > 2.0) atomicOr((unsigned long long *)&L.ctr[C_ERR], 4ull);
-                double iDie;
-                if (P.t_all_real_coeff) iDie = fac * as;
-                else {
-                    double rat = fac * as;
-                    iDie = (double)(long long)rat;
-                    rat = rat - iDie;
-                    Stream rng(P.seed, A.iter, h, 0, RNG_DEATH);
-                    if (fabs(rat) > rng.draw53()) iDie += (rat < 0.0 || (rat == 0.0 && signbit(rat))) ? -1.0 : 1.0;
-                }
-                c_died += fmin(iDie, as);
-                c_bornd += fmax(iDie - as, 0.0);
-                news = s - (iDie * dsign(1.0, s));
-                if (P.t_trunc_initiator && fabs(news) > 1.0e-12 && ((news > 0.0) != (s > 0.0))) {
-                    c_abort += fabs(news);
-                    if (f & F_INIT) c_added -= 1;
-                    news = 0.0;
-                }
-                if (!(fabs(news) > 1.0e-12) && !core) {
-                    if (P.t_trunc_initiator && (f & F_INIT)) c_added -= 1;
-                    ht_remove<NW>(L, d, h, slot);
-                    f |= F_REMOVED;
-                    news = 0.0;
-                }
-            }
-            if (news != s) L.sgn[slot] = news;
-            if (f != f0) L.flg[slot] = f;
-            if (nsp > NG_HEAVY) {
-                const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NHEAVY], 1ull);
-                if (k < SB.heavy_cap) { SB.heavy[2 * k] = slot; SB.heavy[2 * k + 1] = ((long long)nsp << 8) | info; }
-                else atomicOr((unsigned long long *)&L.ctr[C_ERR], 32ull);
-                nsp = 0;
-            }
-        }
-        W.p_d0[idx] = d.w[0]; if (NW > 1) W.p_d1[idx] = d.w[NW - 1];
-        W.p_h[idx] = h; W.p_info[idx] = info;
-        W.p_off[idx] = nsp;                              // attempt count; turned into the prefix sum below
-    }
-    }
-    // statistics of this chunk into the warp's row
     {
-        double *row = S.wacc[warp];
-        k1_add_stat(row, W_NODIED, c_died); k1_add_stat(row, W_NOBORN_D, c_bornd); k1_add_stat(row, W_ABORT, c_abort);
-        k1_add_stat(row, W_HF, c_hf); k1_add_stat(row, W_DOUBS, c_doubs); k1_add_stat(row, W_ENUM, c_enum);
-        k1_add_stat(row, W_ENUMABS, c_enumabs); k1_add_stat(row, W_INITSENUM, c_initsenum);
-        if (P.t_trunc_initiator) {
-            k1_add_stat(row, W_INITW, c_initw); k1_add_stat(row, W_NINITW, c_ninitw);
-            const int a = __reduce_add_sync(0xffffffffu, c_initd), b = __reduce_add_sync(0xffffffffu, c_ninitd),
-                      c = __reduce_add_sync(0xffffffffu, c_added);
-            if (lane == 0) { row[W_INITD] += (double)a; row[W_NINITD] += (double)b; row[W_ADDED] += (double)c; }
+        const u32 m = __ballot_sync(0xffffffffu, push_e);
+        if (push_e) {
+            unsigned long long *rec = G.e.w[fill_e + __popc(m & lt)];
+            rec[0] = d.w[0]; if (NW > 1) rec[NW - 1] = d.w[NW - 1];
+            rec[NW] = (unsigned long long)__double_as_longlong(E.pgen);
+            rec[NW + 1] = (unsigned long long)((u32)E.src1 | ((u32)E.src2 << 8) | ((u32)E.tgt1 << 16) | ((u32)E.tgt2 << 24)) |
+                          ((unsigned long long)p << 32);
+            rec[NW + 2] = (unsigned long long)info;
         }
+        fill_e += __popc(m);
+        __syncwarp();
+        if (fill_e >= 96)
+            warp_stage_flush<qe_rec<NW>(), NG_QE_STAGE_CAP>(G.e, fill_e, &K.cnt[Q_NQE], K.qe_cap, K.qe, L, 128ull);
     }
-    // exclusive prefix sum of the attempt counts over the chunk (index order kk * 32 + lane)
-    int run = 0;
-#pragma unroll
-    for (int kk = 0; kk < SPT; ++kk) {
-        const int mine = W.p_off[kk * 32 + lane];        // written by this lane above
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        W.p_off[kk * 32 + lane] = run + incl - mine;
-        run += __shfl_sync(0xffffffffu, incl, 31);
+    if (sys_pchb(SYS)) {
+        const u32 m = __ballot_sync(0xffffffffu, push_s);
+        if (push_s) {
+            unsigned long long *rec = G.s.w[fill_s + __popc(m & lt)];
+            rec[0] = d.w[0]; if (NW > 1) rec[NW - 1] = d.w[NW - 1];
+            rec[NW] = (unsigned long long)p | ((unsigned long long)info << 32);
+        }
+        fill_s += __popc(m);
+        __syncwarp();
+        if (fill_s >= 32)
+            warp_stage_flush<qs_rec<NW>(), NG_QS_STAGE_CAP>(G.s, fill_s, &K.cnt[Q_NQS], K.qs_cap, K.qs, L, 128ull);
     }
-    T = run;
-    if (lane == 0) W.p_off[CHUNK] = run;
-    __syncwarp();
 }
 
-template <int NW, int SYS>
-__global__ void __launch_bounds__(K1_BLOCK, K1_CTAS_PER_SM) k_spawn(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
-    extern __shared__ __align__(16) unsigned char k1_smem[];
-    K1Shared<NW> &S = *reinterpret_cast<K1Shared<NW> *>(k1_smem);
-    constexpr int SPT = k1_spt<NW>();
-    constexpr int CHUNK = 32 * SPT;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    K1Warp<NW> &W = S.w[warp];
-    k1_init_shared<NW>(P, S);
-    AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
-    K1Queues Q; Q.qe = 0; Q.qs = 0;
-    const Det<NW> ref = ref_det<NW>(P);
-    const long long n_list = L.ctr[C_NLIST];
-    __syncthreads();
+#define NG_MAX_PAR_SEG 1024     /* CTAs of k_walk (segments of the parent list) */
+template <int NW> struct GenShared {
+    u64 p_d0[K1_GEN_TILE];
+    u64 p_d1[(NW > 1) ? K1_GEN_TILE : 1];
+    u64 p_h[K1_GEN_TILE];
+    int p_off[K1_GEN_TILE + 1];          // exclusive prefix sum of the attempt counts; [TILE] = total
+    unsigned short p_map[K1_MAPW];       // attempt (within the current window) -> parent index in the tile
+    unsigned char p_info[K1_GEN_TILE];
+    int wsum[K1_GEN_BLOCK / 32];
+    int seg_tile0[NG_MAX_PAR_SEG + 1];   // first tile of every segment of the parent list
+    int cur_seg;
+};
 
-    // Chunks are dealt to the warps of the grid round-robin (static, so every sum is taken in the same order every run).
-    // One loop of rounds with a single call site for the attempt stages (they are the bulk of the kernel's code, and
-    // every additional inlined copy costs instruction-cache misses): a round generates up to 32 attempts of the
-    // current window of the current chunk and serves the queues; when the window is exhausted the next window's map
-    // is filled, when the chunk is exhausted the next chunk is loaded (stage A); after the last chunk one draining
-    // round ends the loop.
-    const long long n_chunks = (n_list + CHUNK - 1) / CHUNK;
-    const long long gwarp = (long long)blockIdx.x * K1_WARPS + warp, nwarps = (long long)gridDim.x * K1_WARPS;
-    long long chunk = gwarp;
-    int T = 0, wb = 0, we = 0, base = 0;
-    for (;;) {
-        bool drain = false;
-        if (base >= we) {
-            if (we >= T) {                                         // chunk exhausted
-                if (chunk >= n_chunks) drain = true;
-                else {
-                    k1_stage_a<NW, SYS>(P, L, SB, A, S, W, ref, chunk, n_list, T);
-                    chunk += nwarps;
-                    wb = 0; we = 0; base = 0;
-                    if (T == 0) continue;
+template <int NW, int SYS>
+__global__ void __launch_bounds__(K1_GEN_BLOCK) k_generate(Params P, WalkerList L, K1Queues K, IterArgs A, double *partials) {
+    extern __shared__ __align__(16) unsigned char gen_smem[];
+    GenShared<NW> &S = *reinterpret_cast<GenShared<NW> *>(gen_smem);
+    GenStage<NW> *stages = reinterpret_cast<GenStage<NW> *>(gen_smem + ((sizeof(GenShared<NW>) + 15) & ~(size_t)15));
+    __shared__ double s_red[2 * 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    GenStage<NW> &G = stages[warp];
+    int fill_e = 0, fill_s = 0;
+    AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
+    // tiles of K1_GEN_TILE parents inside the segments k_walk's CTAs have written
+    const int nseg = K.par_nseg;
+    for (int sg = tid; sg < nseg; sg += K1_GEN_BLOCK) S.seg_tile0[sg + 1] = ((int)K.par_cnt[sg] + K1_GEN_TILE - 1) / K1_GEN_TILE;
+    __syncthreads();
+    if (tid == 0) { int run = 0; S.seg_tile0[0] = 0; for (int sg = 0; sg < nseg; ++sg) { run += S.seg_tile0[sg + 1]; S.seg_tile0[sg + 1] = run; } }
+    __syncthreads();
+    const int n_tiles = S.seg_tile0[nseg];
+    constexpr int SPT = K1_GEN_TILE / K1_GEN_BLOCK;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tid == 0) {                                          // segment of this tile: last sg with seg_tile0[sg] <= tile
+            int lo_s = 0, hi_s = nseg;
+            while (hi_s - lo_s > 1) { const int mid = (lo_s + hi_s) >> 1; if (S.seg_tile0[mid] <= tile) lo_s = mid; else hi_s = mid; }
+            S.cur_seg = lo_s;
+        }
+        __syncthreads();                                         // also: the previous tile's parents and map are overwritten
+        const int lo_s = S.cur_seg;
+        const long long q0 = (long long)lo_s * K.par_seg_cap + (long long)(tile - S.seg_tile0[lo_s]) * K1_GEN_TILE;
+        const long long q_end = (long long)lo_s * K.par_seg_cap + (long long)K.par_cnt[lo_s];
+        int nsp_k[SPT], off_k[SPT];
+#pragma unroll
+        for (int kk = 0; kk < SPT; ++kk) {
+            const int idx = kk * K1_GEN_BLOCK + tid;
+            const long long q = q0 + idx;
+            Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
+            u32 meta = 0;
+            if (q < q_end) { d.w[0] = __ldcs(&K.par_d0[q]); if (NW > 1) d.w[NW - 1] = __ldcs(&K.par_d1[q]); meta = __ldcs(&K.par_meta[q]); }
+            S.p_d0[idx] = d.w[0]; if (NW > 1) S.p_d1[idx] = d.w[NW - 1];
+            S.p_h[idx] = det_hash64(d); S.p_info[idx] = (unsigned char)(meta & 0xffu);
+            nsp_k[kk] = (int)(meta >> 8);
+        }
+        // exclusive prefix sum of the attempt counts over the tile (index order kk * BLOCK + tid)
+        int run = 0;
+#pragma unroll
+        for (int kk = 0; kk < SPT; ++kk) {
+            int incl = nsp_k[kk];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane == 31) S.wsum[warp] = incl;
+            __syncthreads();
+            int wbase = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < K1_GEN_BLOCK / 32; ++w) { const int v = S.wsum[w]; if (w < warp) wbase += v; total += v; }
+            off_k[kk] = run + wbase + incl - nsp_k[kk];
+            S.p_off[kk * K1_GEN_BLOCK + tid] = off_k[kk];
+            run += total;
+            __syncthreads();
+        }
+        const int T = run;
+        for (int wb = 0; wb < T; wb += K1_MAPW) {
+            // Attempts are numbered 0..T-1 over the tile; each parent writes its tile index into the map entries of
+            // its own attempts (window by window): an attempt finds its parent with one load.
+            const int we = min(T, wb + K1_MAPW);
+            if (wb) __syncthreads();                             // the previous window's map is overwritten
+#pragma unroll
+            for (int kk = 0; kk < SPT; ++kk) {
+                const int idx = kk * K1_GEN_BLOCK + tid;
+                const int lo = max(off_k[kk], wb), hi = min(off_k[kk] + nsp_k[kk], we);
+                const bool big = hi - lo > 4;
+                if (!big) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (lo + u < hi) S.p_map[lo + u - wb] = (unsigned short)idx;
                 }
-            } else { __syncwarp(); wb = we; }                      // next window: the map is overwritten
-            if (!drain) {
-                // Attempts are numbered 0..T-1 over the chunk; each parent writes its chunk index into the map entries
-                // of its own attempts (window by window): an attempt finds its parent with one load.
-                we = min(T, wb + K1_MAPW); base = wb;
-#pragma unroll
-                for (int kk = 0; kk < SPT; ++kk) {
-                    const int idx = kk * 32 + lane;
-                    const int lo = max(W.p_off[idx], wb), hi = min(W.p_off[idx + 1], we);
-                    const bool big = hi - lo > 4;
-                    if (!big) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) if (lo + u < hi) W.map[lo + u - wb] = (unsigned char)idx;
-                    }
-                    u32 m = __ballot_sync(0xffffffffu, big);       // long ranges are filled by the whole warp
-                    while (m) {
-                        const int src = __ffs(m) - 1; m &= m - 1u;
-                        const int l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
-                        const int i2 = __shfl_sync(0xffffffffu, idx, src);
+                u32 m = __ballot_sync(0xffffffffu, big);         // long ranges are filled by the whole warp
+                while (m) {
+                    const int src = __ffs(m) - 1; m &= m - 1u;
+                    const int l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
+                    const int i2 = __shfl_sync(0xffffffffu, idx, src);
 #pragma unroll 1
-                        for (int a = l2 + lane; a < h2; a += 32) W.map[a - wb] = (unsigned char)i2;
-                    }
+                    for (int a = l2 + lane; a < h2; a += 32) S.p_map[a - wb] = (unsigned short)i2;
                 }
-                __syncwarp();
+            }
+            __syncthreads();
+            // one attempt per thread and trip; the warps run through the window independently (no barrier inside)
+#pragma unroll 1
+            for (int base = wb + warp * 32; base < we; base += K1_GEN_BLOCK) {
+                const int a = base + lane;
+                const bool active = a < we;
+                Det<NW> dp; dp.w[0] = 0; if (NW > 1) dp.w[NW - 1] = 0;
+                u64 h = 0; int info = 0; u32 p = 0;
+                if (active) {
+                    const int lo = S.p_map[a - wb];
+                    dp.w[0] = S.p_d0[lo]; if (NW > 1) dp.w[NW - 1] = S.p_d1[lo];
+                    h = S.p_h[lo]; info = S.p_info[lo]; p = (u32)(a - S.p_off[lo]);
+                }
+                generate_and_push<NW, SYS>(P, L, K, A, G, fill_e, fill_s, active, dp, h, info, p, acc);
             }
         }
-        {
-            const int a = base + lane;
-            const bool active = !drain && a < we;
-            Det<NW> dp; dp.w[0] = 0; if (NW > 1) dp.w[NW - 1] = 0;
-            u64 h = 0; int info = 0; u32 p = 0;
-            if (active) {
-                const int lo = W.map[a - wb];
-                dp.w[0] = W.p_d0[lo]; if (NW > 1) dp.w[NW - 1] = W.p_d1[lo];
-                h = W.p_h[lo]; info = W.p_info[lo]; p = (u32)(a - W.p_off[lo]);
-            }
-            if (!drain) { stage_generate<NW, SYS>(P, L, A, W, Q, active, dp, h, info, p, acc); base += 32; }
-        }
-        serve_queues<NW, SYS>(P, L, SB, A, S, W, Q, drain ? 1 : 32, acc);
-        if (drain) break;
     }
-    k1_flush<NW>(L, S, acc, partials, true);
+    warp_stage_flush<qe_rec<NW>(), NG_QE_STAGE_CAP>(G.e, fill_e, &K.cnt[Q_NQE], K.qe_cap, K.qe, L, 128ull);
+    if (sys_pchb(SYS)) warp_stage_flush<qs_rec<NW>(), NG_QS_STAGE_CAP>(G.s, fill_s, &K.cnt[Q_NQS], K.qs_cap, K.qs, L, 128ull);
+    const double a2[2] = {(double)acc.valid, (double)acc.invalid};
+    const int idx[2] = {NECI_ST_NVALIDEXCITS, NECI_ST_NINVALIDEXCITS};
+    block_flush_stats<2>(a2, idx, partials, s_red);
+}
+template <int NW> __host__ __device__ constexpr size_t gen_smem_bytes() {
+    return ((sizeof(GenShared<NW>) + 15) & ~(size_t)15) + (K1_GEN_BLOCK / 32) * sizeof(GenStage<NW>);
 }
 
-// Attempts of the deferred heavy determinants (> NG_HEAVY walkers): rounds of 32 attempts dealt to all warps of the grid.
+// Attempts of the deferred heavy determinants (> NG_HEAVY walkers), spread over the whole grid.
 template <int NW, int SYS>
-__global__ void __launch_bounds__(K1_BLOCK, K1_CTAS_PER_SM) k_spawn_heavy(Params P, WalkerList L, SpawnBuf SB, IterArgs A, double *partials) {
-    extern __shared__ __align__(16) unsigned char k1_smem[];
-    K1Shared<NW> &S = *reinterpret_cast<K1Shared<NW> *>(k1_smem);
+__global__ void __launch_bounds__(K1_GEN_BLOCK) k_generate_heavy(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
+    extern __shared__ __align__(16) unsigned char gen_smem[];
+    GenStage<NW> *stages = reinterpret_cast<GenStage<NW> *>(gen_smem);
+    __shared__ double s_red[2 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    K1Warp<NW> &W = S.w[warp];
-    k1_init_shared<NW>(P, S);
+    GenStage<NW> &G = stages[warp];
+    int fill_e = 0, fill_s = 0;
     AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
-    K1Queues Q; Q.qe = 0; Q.qs = 0;
-    __syncthreads();
     long long nh = L.ctr[C_NHEAVY];
     if (nh > SB.heavy_cap) nh = SB.heavy_cap;
-    const long long gwarp = (long long)blockIdx.x * K1_WARPS + warp, nwarps = (long long)gridDim.x * K1_WARPS;
-    // same shape as k_spawn's loop: one call site for the attempt stages, a last draining round
-    long long e = 0, rd = gwarp, rounds = 0;
-    Det<NW> dp; dp.w[0] = 0; if (NW > 1) dp.w[NW - 1] = 0;
-    u64 h = 0; int nsp = 0, info = 0;
-    bool loaded = false;
-    for (;;) {
-        bool drain = false;
-        while (!loaded || rd >= rounds) {                          // next heavy determinant with a round for this warp
-            if (loaded) { ++e; rd = gwarp; loaded = false; }
-            if (e >= nh) { drain = true; break; }
-            const long long slot = SB.heavy[2 * e];
-            const long long packed = SB.heavy[2 * e + 1];
-            nsp = (int)(packed >> 8); info = (int)(packed & 0xff);
-            dp = load_det<NW>(L, slot);
-            h = det_hash64(dp);
-            rounds = (nsp + 31) / 32;
-            loaded = true;
+    const long long gwarp = (long long)blockIdx.x * (K1_GEN_BLOCK / 32) + warp, nwarps = (long long)gridDim.x * (K1_GEN_BLOCK / 32);
+    for (long long e = 0; e < nh; ++e) {
+        const long long slot = SB.heavy[2 * e];
+        const long long packed = SB.heavy[2 * e + 1];
+        const long long nsp = packed >> 8;
+        const int info = (int)(packed & 0xff);
+        const Det<NW> dp = load_det<NW>(L, slot);
+        const u64 h = det_hash64(dp);
+        const long long rounds = (nsp + 31) / 32;
+#pragma unroll 1
+        for (long long rd = gwarp; rd < rounds; rd += nwarps) {
+            const long long a = rd * 32 + lane;
+            generate_and_push<NW, SYS>(P, L, K, A, G, fill_e, fill_s, a < nsp, dp, h, info, (u32)a, acc);
         }
-        if (!drain) {
-            const int a = (int)(rd * 32) + lane;
-            stage_generate<NW, SYS>(P, L, A, W, Q, a < nsp, dp, h, info, (u32)a, acc);
-            rd += nwarps;
-        }
-        serve_queues<NW, SYS>(P, L, SB, A, S, W, Q, drain ? 1 : 32, acc);
-        if (drain) break;
     }
-    k1_flush<NW>(L, S, acc, partials, false);
+    warp_stage_flush<qe_rec<NW>(), NG_QE_STAGE_CAP>(G.e, fill_e, &K.cnt[Q_NQE], K.qe_cap, K.qe, L, 128ull);
+    if (sys_pchb(SYS)) warp_stage_flush<qs_rec<NW>(), NG_QS_STAGE_CAP>(G.s, fill_s, &K.cnt[Q_NQS], K.qs_cap, K.qs, L, 128ull);
+    const double a2[2] = {(double)acc.valid, (double)acc.invalid};
+    const int idx[2] = {NECI_ST_NVALIDEXCITS, NECI_ST_NINVALIDEXCITS};
+    block_flush_stats<2>(a2, idx, partials, s_red);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_evaluate: one thread per QE entry (stage B2)
+// ---------------------------------------------------------------------------------------------------------------
+template <int NW, int SYS>
+__global__ void __launch_bounds__(NG_BLOCK) k_evaluate(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
+    __shared__ AttShared S;
+    __shared__ SpawnStage<NW> s_stage[NG_BLOCK / 32];
+    __shared__ double s_red[6 * 32];
+    constexpr int IC = (SYS == NECI_SYS_HUBBARD_RS) ? 1 : 2;
+    SpawnStage<NW> &B = s_stage[threadIdx.x >> 5];
+    int fill = 0;
+    att_shared_init(P, S);
+    AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
+    long long n = (long long)K.cnt[Q_NQE]; if (n > K.qe_cap) n = K.qe_cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n + stride - 1) / stride) * stride;
+#pragma unroll 1
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
+        const bool active = i < n;
+        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
+        Excit<NW> E; E.ic = IC; E.src1 = E.src2 = E.tgt1 = E.tgt2 = 1; E.pgen = 1.0; E.valid = active; E.err = 0; E.detJ = d; E.parity = false;
+        int info = 0; u32 att = 0;
+        if (active) {
+            const u64 *rec = K.qe + (size_t)i * qe_rec<NW>();
+            d.w[0] = __ldcs(&rec[0]); if (NW > 1) d.w[NW - 1] = __ldcs(&rec[NW - 1]);
+            E.pgen = __longlong_as_double((long long)__ldcs(&rec[NW]));
+            const u64 oa = __ldcs(&rec[NW + 1]);
+            const u32 o = (u32)oa;
+            E.src1 = o & 0xff; E.src2 = (o >> 8) & 0xff; E.tgt1 = (o >> 16) & 0xff; E.tgt2 = o >> 24;
+            att = (u32)(oa >> 32); info = (int)__ldcs(&rec[NW + 2]);
+        }
+        const u64 h = det_hash64(d);
+        evaluate_and_append<NW, SYS, IC>(P, L, SB, A, S, B, fill, active, d, E, info, h, att, acc);
+    }
+    spawn_stage_flush<NW>(P, SB, L, B, fill);
+    att_flush(L, S, acc, partials, s_red);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_singles: one thread per QS entry (stage B3, PCHB only)
+// ---------------------------------------------------------------------------------------------------------------
+template <int NW, int SYS>
+__global__ void __launch_bounds__(NG_BLOCK) k_singles(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
+    __shared__ AttShared S;
+    __shared__ SpawnStage<NW> s_stage[NG_BLOCK / 32];
+    __shared__ double s_red[6 * 32];
+    SpawnStage<NW> &B = s_stage[threadIdx.x >> 5];
+    int fill = 0;
+    att_shared_init(P, S);
+    AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
+    long long n = (long long)K.cnt[Q_NQS]; if (n > K.qs_cap) n = K.qs_cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n + stride - 1) / stride) * stride;
+#pragma unroll 1
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
+        bool active = i < n;
+        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
+        Excit<NW> E; E.ic = 1; E.src1 = E.src2 = E.tgt1 = E.tgt2 = 1; E.pgen = 1.0; E.valid = false; E.err = 0; E.detJ = d; E.parity = false;
+        int info = 0; u32 att = 0; u64 h = 0;
+        if (active) {
+            const u64 *rec = K.qs + (size_t)i * qs_rec<NW>();
+            d.w[0] = __ldcs(&rec[0]); if (NW > 1) d.w[NW - 1] = __ldcs(&rec[NW - 1]);
+            const u64 pm = __ldcs(&rec[NW]);
+            att = (u32)pm; info = (int)(pm >> 32);
+            h = det_hash64(d);
+            Stream rng(P.seed, A.iter, h, att, RNG_ATTEMPT, 4);     // the first block chose "single"; singles draw from word 4
+            gen_uniform_single(P, d, rng, E);
+            E.pgen = E.pgen * P.p_singles;
+            if (E.err) atomicOr((unsigned long long *)&L.ctr[C_ERR], 16ull);
+            if (E.valid) acc.valid += 1;
+            else { acc.invalid += 1; active = false; }
+        }
+        evaluate_and_append<NW, SYS, 1>(P, L, SB, A, S, B, fill, active, d, E, info, h, att, acc);
+    }
+    spawn_stage_flush<NW>(P, SB, L, B, fill);
+    att_flush(L, S, acc, partials, s_red);
 }
 
 }  // namespace ng
