@@ -122,6 +122,15 @@ class Engine:
         if self.h:
             self._fn("finalize")(self.h)
             self.h = C.c_void_p()
+        self.free_host()
+
+    def free_host(self):
+        """Releases every page-locked array alloc_host handed out (arrays must not be used afterwards)."""
+        pinned = self._keep.pop("_pinned", []) if hasattr(self, "_keep") else []
+        f = getattr(self.lib, self.prefix + "free_host", None)
+        for p, _ in pinned:
+            if f is not None and p.value:
+                f(p)
 
     def __del__(self):
         try:
@@ -229,9 +238,11 @@ class Engine:
         """dets_buf: int64 [max_walkers, W] host buffer holding n records; updated in place."""
         st = np.zeros(ST_COUNT)
         nn = C.c_int64(n)
-        self._check(self._fn("iterate_host")(self.h, _p(dets_buf, C.c_int64), C.byref(nn), _p(gd_buf, C.c_double),
-                                              _p(go_buf, C.c_double), C.c_double(tau), C.c_double(diag_sft),
-                                              C.c_int64(it), _p(st, C.c_double)), "iterate_host")
+        null = C.POINTER(C.c_double)()
+        self._check(self._fn("iterate_host")(self.h, _p(dets_buf, C.c_int64), C.byref(nn),
+                                              _p(gd_buf, C.c_double) if gd_buf is not None else null,
+                                              _p(go_buf, C.c_double) if go_buf is not None else null, C.c_double(tau),
+                                              C.c_double(diag_sft), C.c_int64(it), _p(st, C.c_double)), "iterate_host")
         return st, nn.value
 
     def annihilate(self, spawned, it):

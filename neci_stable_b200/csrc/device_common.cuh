@@ -277,7 +277,28 @@ struct WalkerList {
     // device counters: [0] n_list, [1] n_freeA, [2] n_freeB, [3] n_tomb, [4] n_heavy,
     //                  [5] n_insert, [6] err flags, [7] n_merged
     long long *ctr;
+    // Host mirror (neci_gpu_iterate_host with page-locked host arrays): device pointers of the HOST's CurrentDets and
+    // global_determinant_data rows.  While set, every kernel that changes a slot also writes the change through to
+    // the host arrays over PCIe, so the host list is current when the iteration ends without a bulk download of
+    // the ~85 % of the slots an iteration does not touch.  Null otherwise.
+    long long *h_rec; double *h_gd, *h_go; int h_W;
 };
+// write-through of a slot's sign / flag words (and, for a new determinant, of the whole record) to the host mirror
+template <int NW> __device__ __forceinline__ void mirror_sign(const WalkerList &L, long long slot, double s) {
+    if (L.h_rec) L.h_rec[(size_t)slot * L.h_W + NW] = __double_as_longlong(s);
+}
+template <int NW> __device__ __forceinline__ void mirror_flags(const WalkerList &L, long long slot, int f) {
+    if (L.h_rec) L.h_rec[(size_t)slot * L.h_W + NW + 1] = (long long)f;
+}
+template <int NW> __device__ __forceinline__ void mirror_record(const WalkerList &L, long long slot, const Det<NW> &d, double s, int f,
+                                                               double hd, double ho) {
+    if (!L.h_rec) return;
+    long long *rec = L.h_rec + (size_t)slot * L.h_W;
+    rec[0] = (long long)d.w[0]; if (NW > 1) rec[NW - 1] = (long long)d.w[NW - 1];
+    rec[NW] = __double_as_longlong(s); rec[NW + 1] = (long long)f;
+    if (L.h_gd) L.h_gd[slot] = hd;
+    if (L.h_go) L.h_go[slot] = ho;
+}
 enum { C_NLIST = 0, C_NFREEA, C_NFREEB, C_NTOMB, C_NHEAVY, C_NINSERT, C_ERR, C_NMERGED, C_COUNT = 16 };
 
 #define HT_EMPTY 0xFFFFFFFFFFFFFFFFull

@@ -223,13 +223,13 @@ __global__ void __launch_bounds__(NG_BLOCK) k_annihilate(Params P, WalkerList L,
                         if (fabs(cur) >= 1.e-12 || tDet) {
                             if (cur * s < 0.0) acc[0] += 2.0 * fmin(fabs(cur), fabs(s));
                             const double ns = s + cur;
-                            L.sgn[slot] = ns;
+                            L.sgn[slot] = ns; mirror_sign<NW>(L, slot, ns);
                             if (!tDet && fabs(ns) < 1.0e-12) {
                                 L.ht[pos] = HT_TOMB;
                                 ++n_tomb;
                                 freed = slot;
                                 if (!P.t_semi_stochastic) fl = L.flg[slot];
-                                L.flg[slot] = fl | F_REMOVED;
+                                L.flg[slot] = fl | F_REMOVED; mirror_flags<NW>(L, slot, fl | F_REMOVED);
                             }
                         }
                     } else {
@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(NG_BLOCK) k_insert(Params P, WalkerList L, Spa
         }
         store_det<NW>(L, slot, d);
         L.sgn[slot] = s; L.flg[slot] = ft; L.diagH[slot] = hd; L.offH[slot] = ho;
+        mirror_record<NW>(L, slot, d, s, ft, hd, ho);
         const u64 h = det_hash64(d);
         if (ht_insert(L, h, slot, h & L.ht_mask)) --n_reused;
         acc[0] += 1.0;
@@ -337,27 +338,36 @@ __global__ void k_fix_counters(WalkerList L) {
 }
 
 // ---- CalcHashTableStats ---------------------------------------------------------
-// the stochastic pruning of one under-threshold determinant (rare): kept out of line so that the streaming loop of
-// k_list_stats stays at a register count that allows full occupancy.  Returns the new sign.
+// the stochastic pruning of one under-threshold determinant: kept out of line so that the streaming loop of
+// k_list_stats stays at a register count that allows full occupancy.  Returns the new sign; *removed is set when the
+// determinant left the list (its hash-table entry is a tombstone then; the caller returns the slot to the FreeSlot
+// stack in bulk and counts the tombstone).
 template <int NW>
-__device__ __noinline__ double prune_slot(const Params &P, const WalkerList &L, long long iter, long long i, double s) {
+__device__ __noinline__ double prune_slot(const Params &P, const WalkerList &L, long long iter, long long i, double s, bool *removed,
+                                          int *n_tomb) {
     const Det<NW> d = load_det<NW>(L, i);
     const u64 h = det_hash64(d);
     const double pRemove = (P.occupied_thresh - fabs(s)) / P.occupied_thresh;
     Stream rng(P.seed, iter, h, 0, RNG_PRUNE);
     if (pRemove > rng.draw()) {
-        L.sgn[i] = 0.0;
-        ht_remove<NW>(L, d, h, i);
-        L.flg[i] |= F_REMOVED;
+        L.sgn[i] = 0.0; mirror_sign<NW>(L, i, 0.0);
+        if (ht_tombstone<NW>(L, d, h, i)) *n_tomb += 1;
+        const int f = L.flg[i] | F_REMOVED;
+        L.flg[i] = f; mirror_flags<NW>(L, i, f);
+        *removed = true;
         return 0.0;
     }
-    s = dsign(P.occupied_thresh, s); L.sgn[i] = s;
+    s = dsign(P.occupied_thresh, s); L.sgn[i] = s; mirror_sign<NW>(L, i, s);
     return s;
 }
 template <int NW>
 __global__ void __launch_bounds__(NG_BLOCK, 4) k_list_stats(const __grid_constant__ Params P, const __grid_constant__ WalkerList L, IterArgs A,
                                                             double *partials) {
     __shared__ double s_red[6 * 32];
+    __shared__ WarpStage<1, 128> s_free[NG_BLOCK / 32];     // slots emptied by pruning (real coefficients: many), pushed in bulk
+    WarpStage<1, 128> &FB = s_free[threadIdx.x >> 5];
+    const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    int n_free = 0, n_tomb = 0;
     // k_insert may have overshot the counters when the list overflowed (error already flagged): clamp, as every CTA
     // does for itself; the stored values are repaired by one thread
     long long n = L.ctr[C_NLIST]; if (n > L.cap - 1) n = L.cap - 1;
@@ -368,7 +378,8 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_list_stats(const __grid_constan
     double acc[6] = {0, 0, 0, 0, 0, 0};     // totparts, norm2, norm_ss2, removed, born, highest
     const bool need_flags = P.t_semi_stochastic != 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    const long long nloop = ((n + 4 * stride - 1) / (4 * stride)) * (4 * stride);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nloop; i0 += 4 * stride) {
         double sv[4]; int fv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {                // four independent loads in flight per thread
@@ -379,20 +390,42 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_list_stats(const __grid_constan
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const long long i = i0 + u * stride;
-            if (i >= n) continue;
+            bool removed = false;
             double s = sv[u];
             const bool tDet = need_flags && (fv[u] & F_DETERM);
-            if (fabs(s) < 1.0e-12 && !tDet) continue;
-            if (!tDet && fabs(s) > 1.e-12 && fabs(s) < P.occupied_thresh) {
-                const double old = fabs(s);
-                s = prune_slot<NW>(P, L, A.iter, i, s);
-                if (s == 0.0) acc[3] += old; else acc[4] += P.occupied_thresh - old;       // NoRemoved / NoBorn
+            if (i < n && !(fabs(s) < 1.0e-12 && !tDet)) {
+                if (!tDet && fabs(s) > 1.e-12 && fabs(s) < P.occupied_thresh) {
+                    const double old = fabs(s);
+                    s = prune_slot<NW>(P, L, A.iter, i, s, &removed, &n_tomb);
+                    if (s == 0.0) acc[3] += old; else acc[4] += P.occupied_thresh - old;       // NoRemoved / NoBorn
+                }
+                acc[0] += fabs(s); acc[1] += s * s;
+                if (tDet) acc[2] += s * s;
+                acc[5] = fmax(acc[5], (double)(long long)fabs(s));
             }
-            acc[0] += fabs(s); acc[1] += s * s;
-            if (tDet) acc[2] += s * s;
-            acc[5] = fmax(acc[5], (double)(long long)fabs(s));
+            const u32 m = __ballot_sync(0xffffffffu, removed);
+            if (m) {
+                if (removed) FB.w[n_free + __popc(m & lt)][0] = (unsigned long long)i;
+                n_free += __popc(m);
+                __syncwarp();
+                if (n_free >= 96) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd((unsigned long long *)&L.ctr[C_NFREEB], (unsigned long long)n_free);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    for (int j = lane; j < n_free; j += 32) L.freeB[base + j] = (int)FB.w[j][0];
+                    n_free = 0;
+                    __syncwarp();
+                }
+            }
         }
     }
+    if (n_free) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd((unsigned long long *)&L.ctr[C_NFREEB], (unsigned long long)n_free);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int j = lane; j < n_free; j += 32) L.freeB[base + j] = (int)FB.w[j][0];
+    }
+    ht_settle_tombs(L, n_tomb);
     const int idx[6] = {NECI_ST_TOTPARTS, NECI_ST_NORM_PSI_SQ, NECI_ST_NORM_SEMISTOCH_SQ, NECI_ST_NOREMOVED,
                         NECI_ST_NOBORN, NECI_ST_HIGHEST_POP};
     block_flush_stats<6>(acc, idx, partials, s_red);

@@ -101,6 +101,8 @@ struct neci_gpu_engine {
     std::vector<void *> p2p_peer_base;
     PeerBox X;
     unsigned int xseq = 0;
+    // NECI_GPU_TIMING=1: device time of the three kernels of the peer-memory exchange, printed at finalize
+    bool x_timing = false; cudaEvent_t x_ev[4] = {nullptr, nullptr, nullptr, nullptr}; double x_ms[3] = {0, 0, 0}; long long x_n = 0;
 
     int fail(const char *fmt, ...) {
         char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -299,6 +301,10 @@ int neci_gpu_finalize(neci_gpu_engine *e) {
     if (!e) return 0;
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
+    if (e->x_timing && e->x_n > 1)
+        fprintf(stderr, "neci_gpu[rank %d]: peer-memory exchange, mean over %lld iterations: partition+push %.4f ms, wait %.4f ms, gather %.4f ms\n",
+                e->cfg.rank, e->x_n - 1, e->x_ms[0] / (e->x_n - 1), e->x_ms[1] / (e->x_n - 1), e->x_ms[2] / (e->x_n - 1));
+    for (auto &v : e->x_ev) if (v) cudaEventDestroy(v);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (size_t r = 0; r < e->p2p_peer_base.size(); ++r)
         if ((int)r != e->cfg.rank && e->p2p_peer_base[r]) cudaIpcCloseMemHandle(e->p2p_peer_base[r]);
@@ -738,12 +744,20 @@ static int exchange_spawns_p2p(neci_gpu_engine *e, bool from_stage) {
     const int nr = e->cfg.nranks;
     e->xseq += 1;
     e->n_launch += 3;
+    if (e->x_timing && e->x_n > 0) {                       // the previous exchange has long finished
+        float ms;
+        for (int k = 0; k < 3; ++k) if (cudaEventElapsedTime(&ms, e->x_ev[k], e->x_ev[k + 1]) == cudaSuccess) e->x_ms[k] += ms;
+    }
+    if (e->x_timing) cudaEventRecord(e->x_ev[0], e->stream);
     if (from_stage) {                       // spawning pass: route the staged spawns and push them in one kernel
         if (e->nw == 1) k_partition_push<1><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->X, e->xseq);
         else k_partition_push<2><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->X, e->xseq);
     } else k_push<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->cfg.rank, e->xseq);
+    if (e->x_timing) cudaEventRecord(e->x_ev[1], e->stream);
     k_wait<<<1, 64, 0, e->stream>>>(e->L, e->SB, e->X, nr, e->xseq, 60000000000ll /* ~30 s of SM clocks: ranks may be skewed by I/O */);
+    if (e->x_timing) cudaEventRecord(e->x_ev[2], e->stream);
     k_gather<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->xseq);
+    if (e->x_timing) { cudaEventRecord(e->x_ev[3], e->stream); e->x_n += 1; }
     CK(cudaGetLastError());
     return 0;
 }
@@ -917,9 +931,27 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
 
 int neci_gpu_iterate_host(neci_gpu_engine *e, int64_t *current_dets, int64_t *n, double *gd, double *go,
                           double tau, double diag_sft, int64_t iter, double *stats_out) {
+    CK(cudaSetDevice(e->cfg.device));
     if (neci_gpu_upload_walkers(e, current_dets, *n, gd, go)) return 1;
-    if (neci_gpu_iterate(e, tau, diag_sft, iter, stats_out)) return 1;
-    return neci_gpu_download_walkers(e, current_dets, n, gd, go);
+    // Host mirror: when the host arrays are page-locked and mapped (neci_gpu_alloc_host), the kernels write every
+    // change of the iteration through to them, and nothing is downloaded in bulk.  Not with a core or trial space
+    // (their set-up kernels touch flags outside an iteration) and not for pageable memory: then the whole list
+    // is copied back as before.
+    long long *m_rec = nullptr; double *m_gd = nullptr, *m_go = nullptr;
+    bool mirror = !e->cfg.t_semi_stochastic && !e->P.trial_ht && e->cfg.nranks >= 1;
+    if (mirror && cudaHostGetDevicePointer((void **)&m_rec, (void *)current_dets, 0) != cudaSuccess) { mirror = false; cudaGetLastError(); }
+    if (mirror && gd && cudaHostGetDevicePointer((void **)&m_gd, (void *)gd, 0) != cudaSuccess) { mirror = false; cudaGetLastError(); }
+    if (mirror && go && cudaHostGetDevicePointer((void **)&m_go, (void *)go, 0) != cudaSuccess) { mirror = false; cudaGetLastError(); }
+    if (!mirror) {
+        if (neci_gpu_iterate(e, tau, diag_sft, iter, stats_out)) return 1;
+        return neci_gpu_download_walkers(e, current_dets, n, gd, go);
+    }
+    e->L.h_rec = m_rec; e->L.h_gd = m_gd; e->L.h_go = m_go; e->L.h_W = e->W;
+    const int rc = neci_gpu_iterate(e, tau, diag_sft, iter, stats_out);       // ends with a stream synchronisation
+    e->L.h_rec = nullptr; e->L.h_gd = nullptr; e->L.h_go = nullptr;
+    if (rc) return 1;
+    *n = e->n_resident;
+    return 0;
 }
 
 int neci_gpu_annihilate(neci_gpu_engine *e, const int64_t *spawned_parts, int64_t n_spawned, int64_t iter, double *stats_out) {
@@ -1002,6 +1034,10 @@ int neci_gpu_p2p_open(neci_gpu_engine *e, const uint8_t *handles) {
     CK(cudaDeviceSynchronize());
     e->xseq = 0;
     e->p2p = true;
+    if (const char *t = getenv("NECI_GPU_TIMING")) if (t[0] == '1') {
+        e->x_timing = true;
+        for (auto &v : e->x_ev) CK(cudaEventCreate(&v));
+    }
     return 0;
 }
 

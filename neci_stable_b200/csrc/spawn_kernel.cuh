@@ -474,8 +474,8 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_walk(Params P, WalkerList L, Sp
                         news = 0.0;
                     }
                 }
-                if (news != s) L.sgn[slot] = news;
-                if (f != f0) L.flg[slot] = f;
+                if (news != s) { L.sgn[slot] = news; mirror_sign<NW>(L, slot, news); }
+                if (f != f0) { L.flg[slot] = f; mirror_flags<NW>(L, slot, f); }
                 if (nsp > NG_HEAVY) {
                     const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NHEAVY], 1ull);
                     if (k < SB.heavy_cap) { SB.heavy[2 * k] = slot; SB.heavy[2 * k + 1] = ((long long)nsp << 8) | info; }
