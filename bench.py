@@ -648,17 +648,25 @@ def run_workload(args, ctx, primary=True):
                                       "annihilation": t_ann / args.steps}}
     roofline.update(ncu_extra)
     if semi:
-        # K3 determ_projection: 12 bytes per non-zero (fp64 value + int32 column), the local
-        # slices of the in/out vectors and one read of the gathered vector; its time is the device span from the
-        # start of the iteration to the start of the spawning kernel (core gather + SpMV + trial-energy pass)
-        b3 = 12.0 * core_info["nnz_local"] + 16.0 * core_info["core_local"] + 8.0 * core_info["core_size"]
+        # K3 determ_projection.  The engine keeps the core Hamiltonian column-blocked with 16-bit
+        # columns (kernels.cuh: k_determ_spmv_blocked): 10 bytes per non-zero, per (block, row) chunk its pointer (8)
+        # and its partial sum written and read again (16), the local slices of the in/out vectors and one read of the
+        # gathered vector.  `achieved` uses these bytes (what the kernels must move); SURVEY 8(d)'s figure for the
+        # reference's CSR layout (12 bytes per non-zero) is repeated as csr12_*.  Time: the device span from the start
+        # of the iteration to the start of the spawning kernel (core gather + SpMV + finish).
+        nb3 = max(1, -(-int(core_info["core_size"]) // 27648))
+        b3 = (10.0 * core_info["nnz_local"] + 24.0 * nb3 * core_info["core_local"] + 16.0 * core_info["core_local"]
+              + 8.0 * core_info["core_size"])
+        b3_csr = 12.0 * core_info["nnz_local"] + 16.0 * core_info["core_local"] + 8.0 * core_info["core_size"]
         ach3 = b3 / (t_det / args.steps * 1e-3) / 1e9 if t_det > 0 else 0.0
-        k3 = {"bound": "hbm", "kernel": "k_determ_spmv", "achieved": ach3, "peak": peak, "unit": "GB/s", "frac": ach3 / peak,
-              "traffic": None, "algorithmic_bytes_per_launch": b3, "ms_per_launch": t_det / args.steps}
+        k3 = {"bound": "hbm", "kernel": "k_determ_spmv_blocked", "achieved": ach3, "peak": peak, "unit": "GB/s", "frac": ach3 / peak,
+              "traffic": None, "algorithmic_bytes_per_launch": b3, "ms_per_launch": t_det / args.steps,
+              "csr12_bytes_per_launch": b3_csr, "csr12_equivalent_gbs": b3_csr / (t_det / args.steps * 1e-3) / 1e9 if t_det > 0 else 0.0,
+              "column_blocks": nb3}
         roofline["phase_ms_per_step"]["determ_projection"] = t_det / args.steps
         k1 = {k: roofline[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic",
                                        "algorithmic_bytes_per_launch", "ms_per_launch")}
-        roofline["kernels"] = {"k_spawn": k1, "k_determ_spmv": k3}
+        roofline["kernels"] = {"k_spawn": k1, "k_determ_spmv_blocked": k3}
         if t_det > t_spawn:                                   # the dominant kernel heads the object
             roofline.update(k3)
 

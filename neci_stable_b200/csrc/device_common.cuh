@@ -196,9 +196,11 @@ struct Stream {
 // ---------------------------------------------------------------------------
 // Parameter block (passed by value; lives in the kernel's constant bank).
 // ---------------------------------------------------------------------------
-// one entry of an alias sampler: probability and bias threshold of pair index ab, its alias and its two
-// spatial target orbitals (tgtOrbs(:, ab)) packed as lo | hi << 16
-struct __align__(32) PchbEntry { double prob, bias; int alias; u32 tgt; };
+// one entry of an alias sampler, 32 bytes = one L2 sector: bias threshold and probability of pair index ab with its
+// two spatial target orbitals (tgtOrbs(:, ab)) packed as lo | hi << 16, and -- instead of the alias INDEX the
+// reference's tables hold -- the alias's own probability and target orbitals, so that taking the alias costs no
+// second (dependent) table load
+struct __align__(32) PchbEntry { double bias, prob, prob_alias; u32 tgt, tgt_alias; };
 // per electron-pair index ij: exchange probability, and bit s set when sampler s of this pair is non-empty
 struct __align__(16) PchbPair { double p_exch; int nonempty; int pad; };
 

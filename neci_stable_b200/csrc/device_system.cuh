@@ -492,15 +492,12 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, double r, Str
     const double rr = rng.draw53();
     const int pos = (int)(P.ab_max * rr) + 1;
     const double bias = fmax(P.ab_max * rr + 1 - pos, 0.0);
-    const double2 pb = __ldg(reinterpret_cast<const double2 *>(tab + (pos - 1)));                              // prob, bias
-    const int2 at = __ldg(reinterpret_cast<const int2 *>(reinterpret_cast<const char *>(tab + (pos - 1)) + 16)); // alias, tgt
-    double pGenHoles = pb.x;
-    u32 tg = (u32)at.y;
-    if (!(bias < pb.y)) {                                            // take the alias: its entry holds prob and targets
-        const PchbEntry *e2 = tab + (at.x - 1);
-        pGenHoles = __ldg(&e2->prob);
-        tg = __ldg(&e2->tgt);
-    }
+    // the whole entry with one 256-bit load: {bias, prob, prob_alias, tgt | tgt_alias << 32}
+    double en_bias, en_prob, en_palias; u64 en_tgt;
+    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=d"(en_bias), "=d"(en_prob), "=d"(en_palias), "=l"(en_tgt) : "l"(tab + (pos - 1)));
+    const bool own = bias < en_bias;
+    const double pGenHoles = own ? en_prob : en_palias;
+    const u32 tg = own ? (u32)en_tgt : (u32)(en_tgt >> 32);
     const int o1 = 2 * (int)(tg & 0xffffu) - spin1, o2 = 2 * (int)(tg >> 16) - spin2;
     E.tgt1 = o1; E.tgt2 = o2;
     bool invalid = (o1 == 0 || o2 == 0) || occ(d, o1) || occ(d, o2);

@@ -14,7 +14,7 @@
 //                      get_off_diagonal_matel and hash_search_trial.
 //   k_list_stats       CalcHashTableStats (load_balancer.fpp:646-805).
 //   k_reduce_stats     the iteration's statistics vector (communicate_estimates' per-rank inputs).
-//   k_determ_spmv      determ_projection / determ_projection_no_death (semi_stoch_procs.F90:105-374).
+//   k_determ_spmv_blocked (+ k_determ_finish)  determ_projection / determ_projection_no_death (semi_stoch_procs.F90:105-374).
 //   k_partition_push, k_partition, k_push, k_wait, k_gather
 //                      DetermineDetNode routing + SendProcNewParts over NVLink peer memory.
 //   k_rebalance_pack   move_block, sender side (load_balancer.fpp:353-512).
@@ -594,197 +594,137 @@ __global__ void k_core_gather(WalkerList L, const int *core_slots, long long n, 
         v_part[i] = L.sgn[core_slots[i]];
 }
 // determ_projection: out_i = tau * (-sum_j H_ij v_j + S * v_{i+displ}), fused with the shift / diagonal term of
-// determ_projection_no_death.  Pure HBM stream (12 bytes per non-zero element, rows of ~2000 elements at 1e5 core
-// determinants), so the design goal is bytes in flight: one warp per row, every lane requests NG_SPMV_QUADS x 4 consecutive
-// elements per trip with 128-bit loads (two double2 + one int4 per quadruple = 1.5 KB per quadruple and warp; the first
-// version's scalar loads kept 384 B per warp in flight and reached 26 % of the HBM roofline), the matrix is read
-// with streaming loads so that the gathered vector (0.8 MB) stays cache-resident.  Row starts are arbitrary, so a
-// row is split into an unaligned head (< 4 elements), the 4-aligned body and a tail (< 4 elements).
-#define NG_SPMV_BLOCK 256
-// The loads are volatile asm so that ptxas keeps them in program order: left to itself it interleaves the gathers of the
-// first quadruple (which wait for its column indices) with the wide loads of the following ones, and the warp then
-// sits on the first scoreboard with a fraction of its bytes requested.
-struct SpmvQuad { double2 a, b; int4 c; };
-__device__ __forceinline__ void spmv_load(SpmvQuad &q, const double *val, const int *col, long long k) {
-    asm volatile("ld.global.cs.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(q.c.x), "=r"(q.c.y), "=r"(q.c.z), "=r"(q.c.w) : "l"(col + k));
-    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(q.a.x), "=d"(q.a.y) : "l"(val + k));
-    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(q.b.x), "=d"(q.b.y) : "l"(val + k + 2));
-}
-__device__ __forceinline__ void spmv_gather(double (&g)[4], const SpmvQuad &q, const double *v) {
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(g[0]) : "l"(v + q.c.x));
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(g[1]) : "l"(v + q.c.y));
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(g[2]) : "l"(v + q.c.z));
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(g[3]) : "l"(v + q.c.w));
-}
-__device__ __forceinline__ double spmv_dot(const SpmvQuad &q, const double (&g)[4]) {
-    return (q.a.x * g[0] + q.a.y * g[1]) + (q.b.x * g[2] + q.b.y * g[3]);
-}
-#ifndef NG_SPMV_QUADS
-#define NG_SPMV_QUADS 2          /* quadruples per lane and trip */
-#endif
-#ifndef NG_SPMV_CTAS
-#define NG_SPMV_CTAS 4
-#endif
-__global__ void __launch_bounds__(NG_SPMV_BLOCK, NG_SPMV_CTAS) k_determ_spmv(const long long *__restrict__ row_ptr, const int *__restrict__ col,
-                                                                  const double *__restrict__ val, const double *__restrict__ v_full,
-                                                                  long long n_local, long long displ, double tau, double diag_sft,
-                                                                  const double *__restrict__ core_ham_diag, double *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long i = warp; i < n_local; i += nwarps) {
-        const long long b = row_ptr[i], e = row_ptr[i + 1];
-        const long long k0 = min(e, (b + 3) & ~3ll), k1 = max(k0, e & ~3ll);
-        double acc[NG_SPMV_QUADS];
-#pragma unroll
-        for (int u = 0; u < NG_SPMV_QUADS; ++u) acc[u] = 0.0;
-        if (b + lane < k0) acc[0] = __ldcs(&val[b + lane]) * __ldg(&v_full[__ldcs(&col[b + lane])]);
-        if (k1 + lane < e) acc[NG_SPMV_QUADS - 1] += __ldcs(&val[k1 + lane]) * __ldg(&v_full[__ldcs(&col[k1 + lane])]);
-        long long k = k0 + 4 * lane;
-        for (; k + 128 * (NG_SPMV_QUADS - 1) < k1; k += 128 * NG_SPMV_QUADS) {
-            SpmvQuad q[NG_SPMV_QUADS]; double g[NG_SPMV_QUADS][4];
-#pragma unroll
-            for (int u = 0; u < NG_SPMV_QUADS; ++u) spmv_load(q[u], val, col, k + 128 * u);
-#pragma unroll
-            for (int u = 0; u < NG_SPMV_QUADS; ++u) spmv_gather(g[u], q[u], v_full);
-#pragma unroll
-            for (int u = 0; u < NG_SPMV_QUADS; ++u) acc[u] += spmv_dot(q[u], g[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < NG_SPMV_QUADS - 1; ++u) {          // what is left of this lane's share: < NG_SPMV_QUADS quadruples
-            if (k + 128 * u < k1) {
-                SpmvQuad q; double g[4];
-                spmv_load(q, val, col, k + 128 * u); spmv_gather(g, q, v_full);
-                acc[u] += spmv_dot(q, g);
-            }
-        }
-        double t = acc[0];
-#pragma unroll
-        for (int u = 1; u < NG_SPMV_QUADS; ++u) t += acc[u];
-        t = -warp_sum(t);
-        if (lane == 0) {
-            // determ_projection adds the shift; determ_projection_no_death (semi_stoch_procs.F90:285-374) adds the
-            // diagonal element back instead, because death then acts on the core determinants as well
-            const double d = core_ham_diag ? core_ham_diag[i] : diag_sft;
-            out[i] = (t + d * v_full[i + displ]) * tau;
-        }
-    }
-}
-// ---- determ_projection through bulk-copy (TMA) staging ------------------------------------------------------
-// The register version above tops out at ~55 % of the HBM roofline: a warp cannot hold more than a few KB of loads
-// in its registers, and the occupancy that would make up for it costs the registers.  Here the bytes in flight live
-// in shared memory instead.  Every warp is its own pipeline: it owns a contiguous run of rows holding 1/N-th of the
-// matrix elements (balanced in bytes, found by bisection of row_ptr), streams that run of `val` and `col` through a
-// private ring of NG_SPMV_STAGES tiles with cp.async.bulk (one elected lane arms the tile's mbarrier with the byte
-// count and issues two bulk copies), and consumes tile after tile: lanes read consecutive elements from shared memory
-// (conflict-free), gather v_full from L1/L2 and accumulate; a row's sum is reduced across the warp when its last
-// element has been consumed.  Tiles are aligned to 4 elements (16-byte rule of the bulk copy) and ignore row
-// boundaries, so a tile is fetched once even when several rows share it.  In flight per SM: CTAs x warps x stages x
-// 6 KB (3 x 4 x 3 x 6 KB = 216 KB), an order of magnitude above what the register version sustains.
-#ifndef NG_SPMV_TILE
-#define NG_SPMV_TILE 512
-#endif
-#ifndef NG_SPMV_STAGES
-#define NG_SPMV_STAGES 3
-#endif
-#ifndef NG_SPMV_WARPS
-#define NG_SPMV_WARPS 4
-#endif
-struct __align__(128) SpmvRing {
-    double val[NG_SPMV_STAGES][NG_SPMV_TILE];
-    int col[NG_SPMV_STAGES][NG_SPMV_TILE];
-    unsigned long long bar[NG_SPMV_STAGES];
-};
-__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity) {
-    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
-                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-// first row r in [0, n] with row_ptr[r] >= x
-__device__ __forceinline__ long long spmv_lower_bound(const long long *row_ptr, long long n, long long x) {
-    long long lo = 0, hi = n;
-    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (__ldg(&row_ptr[mid]) < x) lo = mid + 1; else hi = mid; }
-    return lo;
-}
-__global__ void __launch_bounds__(NG_SPMV_WARPS * 32) k_determ_spmv_tma(const long long *__restrict__ row_ptr, const int *__restrict__ col,
-                                                                    const double *__restrict__ val, const double *__restrict__ v_full,
-                                                                    long long n_local, long long displ, double tau, double diag_sft,
-                                                                    const double *__restrict__ core_ham_diag, double *__restrict__ out) {
-    extern __shared__ __align__(128) unsigned char spmv_smem[];
+// determ_projection_no_death.
+//
+// What bounds a CSR SpMV here is not HBM but the gather of v_full: rows hold ~2000 elements spread over 1e5 columns, so
+// the 32 lanes of a gather touch 32 different cache lines and the L1 tag stage retires about one of them per cycle
+// and SM.  2.2e8 elements / 148 SMs / 1.97 GHz = 0.75 ms -- exactly where both earlier kernels (register-staged loads,
+// and a bulk-copy ring in shared memory) stopped, with `L1/TEX throughput 89 %` in ncu and HBM at 45-54 %
+// (profiles/r02b_k3_ncu_summary.txt).  Shared memory serves a random 8-byte gather five to six times faster, but the
+// vector (0.8 MB at 1e5 core determinants) does not fit.  So the matrix is cut into COLUMN BLOCKS of at most
+// NG_SPMV_CB_MAX columns whose slice of v_full (<= 216 KB) does fit:
+//   * set-up (k_spmv_block_count / k_spmv_block_fill): every row is partitioned stably by column block and the
+//     matrix is re-laid block-major -- for block c the chunks of rows 0..n_local-1 one after the other -- as
+//     {fp64 value, 16-bit column inside the block}: 10 bytes per element instead of CSR's 12;
+//   * k_determ_spmv_blocked: one persistent CTA of 1024 threads per SM owns a contiguous 1/G-th of the elements
+//     (so of the bytes), loads the v slice of its block into shared memory (200 KB from L2, 1 % of the CTA's traffic)
+//     and its warps walk the (block, row) chunks: coalesced streaming loads of value and column, gather from shared
+//     memory, one partial sum per chunk;
+//   * k_determ_finish adds the partial sums of a row in block order (fixed order: bit-reproducible), the shift or
+//     diagonal term, and multiplies by tau.
+#define NG_SPMV_CB_MAX 27648          /* columns per block: 216 KB of fp64 in shared memory */
+#define NG_SPMV_THREADS 1024
+#define NG_SPMV_NB_MAX 256            /* column blocks (set-up histogram); 7e6 core determinants */
+// set-up, pass 1: elements of every (block, row) chunk.  One warp per row; cnt is block-major [c * n_local + i].
+__global__ void __launch_bounds__(256) k_spmv_block_count(const long long *__restrict__ row_ptr, const int *__restrict__ col, long long n_local,
+                                                          int cb, int nb, long long *__restrict__ cnt) {
+    __shared__ int s_cnt[8][NG_SPMV_NB_MAX];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    SpmvRing &R = reinterpret_cast<SpmvRing *>(spmv_smem)[wib];
-    const long long w = (long long)blockIdx.x * NG_SPMV_WARPS + wib, nwarp = (long long)gridDim.x * NG_SPMV_WARPS;
-    const long long nnz = __ldg(&row_ptr[n_local]);
-    // rows whose first element lies in this warp's share of the element range
-    const long long e_lo = (nnz * w) / nwarp, e_hi = (nnz * (w + 1)) / nwarp;
-    const long long r0 = (w == 0) ? 0 : spmv_lower_bound(row_ptr, n_local, e_lo);
-    const long long r1 = (w == nwarp - 1) ? n_local : spmv_lower_bound(row_ptr, n_local, e_hi);
-    if (r0 >= r1) return;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NG_SPMV_STAGES; ++s) mbar_init(&R.bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < n_local; i += nwarps) {
+        for (int c = lane; c < nb; c += 32) s_cnt[wib][c] = 0;
+        __syncwarp();
+        for (long long k = row_ptr[i] + lane; k < row_ptr[i + 1]; k += 32) atomicAdd(&s_cnt[wib][col[k] / cb], 1);
+        __syncwarp();
+        for (int c = lane; c < nb; c += 32) cnt[(size_t)c * n_local + i] = s_cnt[wib][c];
+        __syncwarp();
     }
-    __syncwarp();
-    const long long S0 = __ldg(&row_ptr[r0]) & ~3ll, SE = (__ldg(&row_ptr[r1]) + 3) & ~3ll;
-    const long long ntiles = (SE - S0 + NG_SPMV_TILE - 1) / NG_SPMV_TILE;
-    auto issue = [&](long long t) {
-        const int s = (int)(t % NG_SPMV_STAGES);
-        const long long start = S0 + t * NG_SPMV_TILE;
-        const u32 cnt = (u32)min((long long)NG_SPMV_TILE, SE - start);
-        mbar_expect_tx(&R.bar[s], cnt * 12u);
-        bulk_g2s(R.val[s], val + start, cnt * 8u, &R.bar[s]);
-        bulk_g2s(R.col[s], col + start, cnt * 4u, &R.bar[s]);
-    };
-    if (lane == 0) for (long long t = 0; t < ntiles && t < NG_SPMV_STAGES; ++t) issue(t);
-    long long waited = -1;
-    for (long long i = r0; i < r1; ++i) {
-        const long long b = __ldg(&row_ptr[i]), e = __ldg(&row_ptr[i + 1]);
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        long long pos = b;
-        while (pos < e) {
-            const long long t = (pos - S0) / NG_SPMV_TILE;
-            const int s = (int)(t % NG_SPMV_STAGES);
-            if (t > waited) { mbar_wait(&R.bar[s], (u32)((t / NG_SPMV_STAGES) & 1)); waited = t; }
-            const long long tstart = S0 + t * NG_SPMV_TILE;
-            const long long hi = min(e, tstart + NG_SPMV_TILE);
-            const double *vs = R.val[s] - tstart;
-            const int *cs = R.col[s] - tstart;
-            long long k = pos + lane;
-            for (; k + 96 < hi; k += 128) {
-                const int c0 = cs[k], c1 = cs[k + 32], c2 = cs[k + 64], c3 = cs[k + 96];
-                const double g0 = __ldg(&v_full[c0]), g1 = __ldg(&v_full[c1]), g2 = __ldg(&v_full[c2]), g3 = __ldg(&v_full[c3]);
-                a0 += vs[k] * g0; a1 += vs[k + 32] * g1; a2 += vs[k + 64] * g2; a3 += vs[k + 96] * g3;
+}
+// set-up, pass 2: stable scatter of every row into its chunks (bptr = exclusive prefix sum of cnt in block-major order)
+__global__ void __launch_bounds__(256) k_spmv_block_fill(const long long *__restrict__ row_ptr, const int *__restrict__ col,
+                                                         const double *__restrict__ val, long long n_local, int cb, int nb,
+                                                         const long long *__restrict__ bptr, double *__restrict__ bval,
+                                                         unsigned short *__restrict__ bcol) {
+    __shared__ long long s_off[8][NG_SPMV_NB_MAX];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < n_local; i += nwarps) {
+        for (int c = lane; c < nb; c += 32) s_off[wib][c] = bptr[(size_t)c * n_local + i];
+        __syncwarp();
+        const long long b = row_ptr[i], e = row_ptr[i + 1];
+        for (long long k0 = b; k0 < e; k0 += 32) {
+            const long long k = k0 + lane;
+            const bool has = k < e;
+            const int cj = has ? col[k] : 0;
+            const int c = has ? cj / cb : -1;
+            const u32 peers = __match_any_sync(0xffffffffu, c);
+            if (has) {
+                const long long pos = s_off[wib][c] + __popc(peers & lt);
+                bval[pos] = val[k]; bcol[pos] = (unsigned short)(cj - c * cb);
             }
-            {
-                const bool p0 = k < hi, p1 = k + 32 < hi, p2 = k + 64 < hi;
-                const int c0 = p0 ? cs[k] : 0, c1 = p1 ? cs[k + 32] : 0, c2 = p2 ? cs[k + 64] : 0;
-                const double g0 = __ldg(&v_full[c0]), g1 = __ldg(&v_full[c1]), g2 = __ldg(&v_full[c2]);
-                if (p0) a0 += vs[k] * g0;
-                if (p1) a1 += vs[k + 32] * g1;
-                if (p2) a2 += vs[k + 64] * g2;
-            }
-            pos = hi;
-            if (hi == tstart + NG_SPMV_TILE) {          // tile consumed: its stage is refilled with tile t + STAGES
-                __syncwarp();
-                if (lane == 0 && t + NG_SPMV_STAGES < ntiles) issue(t + NG_SPMV_STAGES);
-            }
+            __syncwarp();
+            if (has && lane == __ffs(peers) - 1) s_off[wib][c] += __popc(peers);
+            __syncwarp();
         }
-        const double acc = -warp_sum((a0 + a1) + (a2 + a3));
-        if (lane == 0) {
-            const double d = core_ham_diag ? core_ham_diag[i] : diag_sft;
-            out[i] = (acc + d * v_full[i + displ]) * tau;
+        // chunks are padded to whole quadruples with zero elements (bptr holds the padded positions)
+        for (int c = lane; c < nb; c += 32)
+            for (long long pos = s_off[wib][c]; pos < bptr[(size_t)c * n_local + i + 1]; ++pos) { bval[pos] = 0.0; bcol[pos] = 0; }
+        __syncwarp();
+    }
+}
+// A lane takes whole quadruples of consecutive elements: one 256-bit load for the four values and one 64-bit load for
+// the four 16-bit columns (chunks start at multiples of four elements and are padded with zeros), NG_SPMV_U
+// quadruples per lane and trip = 40 bytes x NG_SPMV_U in flight per lane with two load instructions per quadruple.
+#ifndef NG_SPMV_U
+#define NG_SPMV_U 4
+#endif
+struct SpmvQuad { double a0, a1, a2, a3; u32 c01, c23; };
+__device__ __forceinline__ void spmv_quad_load(SpmvQuad &Q, const double *bval, const unsigned short *bcol, long long q, bool p) {
+    Q.a0 = Q.a1 = Q.a2 = Q.a3 = 0.0; Q.c01 = Q.c23 = 0u;
+    if (p) {
+        asm volatile("ld.global.cs.v2.u32 {%0, %1}, [%2];" : "=r"(Q.c01), "=r"(Q.c23) : "l"(bcol + 4 * q));
+        asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(Q.a0), "=d"(Q.a1), "=d"(Q.a2), "=d"(Q.a3) : "l"(bval + 4 * q));
+    }
+}
+__device__ __forceinline__ double spmv_quad_dot(const SpmvQuad &Q, const double *vs) {
+    return (Q.a0 * vs[Q.c01 & 0xffffu] + Q.a1 * vs[Q.c01 >> 16]) + (Q.a2 * vs[Q.c23 & 0xffffu] + Q.a3 * vs[Q.c23 >> 16]);
+}
+__global__ void __launch_bounds__(NG_SPMV_THREADS, 1) k_determ_spmv_blocked(const long long *__restrict__ bptr, const unsigned short *__restrict__ bcol,
+                                                                         const double *__restrict__ bval, const double *__restrict__ v_full,
+                                                                         const long long *__restrict__ work, long long n_local,
+                                                                         long long n_core, int cb, double *__restrict__ partial) {
+    extern __shared__ __align__(16) double spmv_vs[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = NG_SPMV_THREADS / 32;
+    // chunks (flat block-major index c * n_local + i) whose first element lies in this CTA's share of the elements
+    const long long idx_lo = work[blockIdx.x], idx_hi = work[blockIdx.x + 1];
+    if (idx_lo >= idx_hi) return;
+    for (long long c = idx_lo / n_local; c * n_local < idx_hi; ++c) {
+        const long long a = max(idx_lo, c * n_local), b = min(idx_hi, (c + 1) * n_local);
+        const long long col0 = c * cb;
+        const int ncol = (int)min((long long)cb, n_core - col0);
+        __syncthreads();                                       // the previous block's slice is still being read
+        for (int j = threadIdx.x; j < ncol; j += NG_SPMV_THREADS) spmv_vs[j] = __ldg(&v_full[col0 + j]);
+        __syncthreads();
+        for (long long idx = a + warp; idx < b; idx += nwarp) {
+            const long long s = __ldg(&bptr[idx]), e = __ldg(&bptr[idx + 1]);      // multiples of four
+            const long long nq = (e - s) >> 2, q_base = s >> 2;
+            double t = 0.0;
+            for (long long q0 = 0; q0 < nq; q0 += 32 * NG_SPMV_U) {
+                SpmvQuad Q[NG_SPMV_U];
+#pragma unroll
+                for (int u = 0; u < NG_SPMV_U; ++u) { const long long q = q0 + lane + 32 * u; spmv_quad_load(Q[u], bval, bcol, q_base + q, q < nq); }
+                double tt[NG_SPMV_U];
+#pragma unroll
+                for (int u = 0; u < NG_SPMV_U; ++u) tt[u] = spmv_quad_dot(Q[u], spmv_vs);
+#pragma unroll
+                for (int u = 0; u < NG_SPMV_U; ++u) t += tt[u];
+            }
+            t = warp_sum(t);
+            if (lane == 0) partial[idx] = t;
         }
+    }
+}
+// sum of a row's partial sums in block order + the shift term (determ_projection) or the diagonal element
+// (determ_projection_no_death, semi_stoch_procs.F90:285-374: death then acts on the core determinants as well)
+__global__ void k_determ_finish(const double *__restrict__ partial, const double *__restrict__ v_full, long long n_local, int nb,
+                                long long displ, double tau, double diag_sft, const double *__restrict__ core_ham_diag,
+                                double *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (long long)gridDim.x * blockDim.x) {
+        double t = 0.0;
+        for (int c = 0; c < nb; ++c) t += partial[(size_t)c * n_local + i];
+        const double d = core_ham_diag ? core_ham_diag[i] : diag_sft;
+        out[i] = (-t + d * v_full[i + displ]) * tau;
     }
 }
 __global__ void k_determ_apply(WalkerList L, const int *core_slots, const double *out, long long n_local) {

@@ -15,9 +15,6 @@
 #include <unordered_set>
 #include <dlfcn.h>
 #include <nccl.h>
-#ifndef NG_SPMV_TMA
-#define NG_SPMV_TMA 1      /* determ_projection through bulk-copy staging (0: the register-staged kernel) */
-#endif
 #include "kernels.cuh"
 
 using namespace ng;
@@ -87,7 +84,11 @@ struct neci_gpu_engine {
     long long ht_cap = 0;
     // semi-stochastic
     long long n_core_local = 0, n_core_total = 0, core_displ = 0;
-    long long *d_row_ptr = nullptr; int *d_col = nullptr; double *d_val = nullptr;
+    long long *d_row_ptr = nullptr; int *d_col = nullptr; double *d_val = nullptr;      // CSR rows as the host passed / k_core_ham built them
+    // the same matrix column-blocked for k_determ_spmv_blocked (kernels.cuh): chunk pointers, 16-bit columns, values,
+    // the CTAs' shares, one partial sum per (block, row)
+    long long *d_bptr = nullptr, *d_spmv_work = nullptr; unsigned short *d_bcol = nullptr; double *d_bval = nullptr, *d_spmv_partial = nullptr;
+    int spmv_cb = 0, spmv_nb = 0; long long core_nnz = 0, core_nnz_padded = 0;
     int *d_core_slots = nullptr; double *d_vpart = nullptr, *d_vfull = nullptr, *d_vout = nullptr, *d_core_diag = nullptr;
     std::vector<int> core_sizes, core_displs;
     // staging for AoS transfers
@@ -228,7 +229,7 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
         K.par_d0 = e->alloc<u64>(par_cap); K.par_meta = e->alloc<u32>(par_cap);
         if (e->nw > 1) K.par_d1 = e->alloc<u64>(par_cap);
         K.par_cnt = e->alloc<u32>(NG_MAX_PAR_SEG);
-        K.qe = e->alloc<u64>((size_t)K.qe_cap * (e->nw + 3)); K.qs = e->alloc<u64>((size_t)K.qs_cap * (e->nw + 1));
+        K.qe = e->alloc<u64>((size_t)K.qe_cap * (e->nw + 2)); K.qs = e->alloc<u64>((size_t)K.qs_cap * (e->nw + 1));
         K.cnt = e->alloc<unsigned long long>(4);
         if (!K.par_d0 || !K.par_meta || !K.par_cnt || !K.qe || !K.qs || !K.cnt || (e->nw > 1 && !K.par_d1))
             return e->fail("device allocation failed (attempt queues, max_walkers=%lld)", M);
@@ -249,16 +250,7 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     const int nsm = prop.multiProcessorCount;
     e->grid_generic = nsm * 8;
-    {
-        int per_sm = 0;
-#if NG_SPMV_TMA
-        CK(cudaFuncSetAttribute(k_determ_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NG_SPMV_WARPS * sizeof(SpmvRing))));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_determ_spmv_tma, NG_SPMV_WARPS * 32, NG_SPMV_WARPS * sizeof(SpmvRing)));
-#else
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_determ_spmv, NG_SPMV_BLOCK, 0));
-#endif
-        e->grid_spmv = nsm * std::max(1, per_sm);
-    }
+    e->grid_spmv = nsm;                       // one persistent CTA per SM (k_determ_spmv_blocked)
     e->rows_compress = e->grid_generic; e->rows_annih = e->grid_generic;
     e->rows_insert = e->grid_generic; e->rows_list = e->grid_generic;
     // the K1 kernels run as persistent grids: one CTA per resident slot of every SM
@@ -366,8 +358,13 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
                 if (alias[base] != 0) pair[ij].nonempty |= 1 << s;
                 for (int ab = 0; ab < ab_max; ++ab) {
                     PchbEntry &t = tab[base + ab];
-                    t.prob = probs[base + ab]; t.bias = bias[base + ab]; t.alias = alias[base + ab];
+                    t.prob = probs[base + ab]; t.bias = bias[base + ab];
                     t.tgt = (u32)tgt_orbs[2 * ab] | ((u32)tgt_orbs[2 * ab + 1] << 16);
+                    const int al = alias[base + ab];            // 1-based; 0 marks an empty sampler
+                    if (al >= 1 && al <= ab_max) {
+                        t.prob_alias = probs[base + al - 1];
+                        t.tgt_alias = (u32)tgt_orbs[2 * (al - 1)] | ((u32)tgt_orbs[2 * (al - 1) + 1] << 16);
+                    } else { t.prob_alias = 0.0; t.tgt_alias = 0; }
                 }
             }
         }
@@ -564,6 +561,52 @@ static int core_space_layout(neci_gpu_engine *e, const int32_t *sizes, const int
     e->core_displ = displs[e->cfg.rank];
     return 0;
 }
+// Column-blocked copy of the core Hamiltonian for k_determ_spmv_blocked (kernels.cuh): called once the CSR rows are
+// in HBM.  Set-up code: the prefix sum over the (block, row) chunk lengths and the CTAs' shares are taken on the host.
+static int core_space_blocked(neci_gpu_engine *e, long long nnz) {
+    const long long n_local = e->n_core_local, n_core = e->n_core_total;
+    e->core_nnz = nnz;
+    if (n_local == 0) return 0;
+    int nb = (int)((n_core + NG_SPMV_CB_MAX - 1) / NG_SPMV_CB_MAX);
+    if (nb > NG_SPMV_NB_MAX) return e->fail("core space of %lld determinants needs more than %d column blocks", n_core, NG_SPMV_NB_MAX);
+    int cb = (int)((n_core + nb - 1) / nb);
+    cb = (cb + 31) & ~31;
+    e->spmv_cb = cb; e->spmv_nb = nb;
+    const size_t nchunk = (size_t)nb * n_local;
+    e->d_bptr = e->alloc<long long>(nchunk + 1);
+    e->d_spmv_partial = e->alloc<double>(nchunk);
+    e->d_spmv_work = e->alloc<long long>((size_t)e->grid_spmv + 1);
+    if (!e->d_bptr || !e->d_spmv_partial || !e->d_spmv_work) return e->fail("no memory for the column-blocked core Hamiltonian (%lld elements)", nnz);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, (n_local + 7) / 8));
+    k_spmv_block_count<<<grid, 256, 0, e->stream>>>(e->d_row_ptr, e->d_col, n_local, cb, nb, e->d_bptr);
+    CK(cudaGetLastError());
+    std::vector<long long> bp(nchunk + 1, 0);
+    CK(cudaMemcpyAsync(bp.data(), e->d_bptr, nchunk * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    // chunks start at multiples of four elements (256-bit loads of the values) and are padded with zeros up to there
+    long long run = 0, found = 0;
+    for (size_t k = 0; k < nchunk; ++k) { const long long len = bp[k]; bp[k] = run; run += (len + 3) & ~3ll; found += len; }
+    bp[nchunk] = run;
+    if (found != nnz) return e->fail("column blocking lost elements (%lld of %lld): column index outside the core space?", found, nnz);
+    e->core_nnz_padded = run;
+    CK(cudaMemcpyAsync(e->d_bptr, bp.data(), (nchunk + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    e->d_bval = e->alloc<double>((size_t)run + 4); e->d_bcol = e->alloc<unsigned short>((size_t)run + 4);
+    if (!e->d_bval || !e->d_bcol) return e->fail("no memory for the column-blocked core Hamiltonian (%lld elements)", run);
+    k_spmv_block_fill<<<grid, 256, 0, e->stream>>>(e->d_row_ptr, e->d_col, e->d_val, n_local, cb, nb, e->d_bptr, e->d_bval, e->d_bcol);
+    CK(cudaGetLastError());
+    // CTA p takes the chunks whose first element lies in [nnz p / G, nnz (p + 1) / G): equal shares of the bytes
+    const int G = e->grid_spmv;
+    std::vector<long long> work((size_t)G + 1);
+    for (int p = 0; p <= G; ++p) {
+        const long long x = (long long)(((__int128)run * p) / G);
+        work[p] = (p == 0) ? 0 : (p == G) ? (long long)nchunk : (long long)(std::lower_bound(bp.begin(), bp.begin() + nchunk, x) - bp.begin());
+    }
+    CK(cudaMemcpyAsync(e->d_spmv_work, work.data(), work.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaFuncSetAttribute(k_determ_spmv_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, NG_SPMV_CB_MAX * 8));
+    CK(cudaStreamSynchronize(e->stream));
+    e->n_launch += 2;
+    return 0;
+}
 static int core_space_tables(neci_gpu_engine *e, const int64_t *core_iluts) {
     const int64_t n_local = e->n_core_local;
     e->d_core_slots = e->alloc<int>((size_t)n_local);
@@ -602,7 +645,6 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
     if (n_local != e->n_core_local) return e->fail("set_core_space: n_local = %lld but sizes[rank] = %lld", (long long)n_local, (long long)e->n_core_local);
     const long long nnz = row_ptr[n_local];
     e->d_row_ptr = e->upload((const long long *)row_ptr, (size_t)n_local + 1);
-    // + 4 elements of slack: the last tile of the bulk-copy SpMV is rounded up to the 16-byte rule
     e->d_col = e->alloc<int>((size_t)nnz + 4); e->d_val = e->alloc<double>((size_t)nnz + 4);
     if (!e->d_col || !e->d_val) return e->fail("set_core_space: no memory for %lld non-zero elements", nnz);
     CK(cudaMemset(e->d_col + nnz, 0, 16)); CK(cudaMemset(e->d_val + nnz, 0, 32));
@@ -615,7 +657,8 @@ int neci_gpu_set_core_space(neci_gpu_engine *e, int64_t n_local, const int64_t *
                 if (col[k] == i + displs[e->cfg.rank]) diag[i] = val[k];
         e->d_core_diag = e->upload(diag.data(), diag.size());
     }
-    return core_space_tables(e, core_iluts);
+    if (core_space_tables(e, core_iluts)) return 1;
+    return core_space_blocked(e, nnz);
 }
 
 int neci_gpu_build_core_space(neci_gpu_engine *e, const int32_t *sizes, const int32_t *displs, const int64_t *core_iluts,
@@ -652,7 +695,7 @@ int neci_gpu_build_core_space(neci_gpu_engine *e, const int32_t *sizes, const in
     CK(cudaStreamSynchronize(e->stream));
     e->n_launch += 2;
     if (nnz_out) *nnz_out = run;
-    return 0;
+    return core_space_blocked(e, run);
 }
 
 int neci_gpu_get_core_hamiltonian(neci_gpu_engine *e, int64_t *row_ptr, int32_t *col, double *val) {
@@ -841,6 +884,7 @@ static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
     if (errf & 32) return e->fail("heavy-determinant queue overflow");
     if (errf & 128) return e->fail("spawning-attempt queue overflow (more walkers than max_walkers: increase MemoryFacPart)");
     if (errf & 256) return e->fail("peer-memory spawn exchange timed out waiting for another rank");
+    if (errf & 512) return e->fail("a determinant holds 2^29 or more walkers (attempt index field of the spawning queues)");
     return 0;
 }
 
@@ -870,25 +914,19 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
     if (e->cfg.t_semi_stochastic && e->n_core_total > 0) {
         // determ_projection (semi_stoch_procs.F90:105-241): gather of partial_determ_vecs, MPIAllGatherV, multiplication.
         // The phase time between ev[0] and ev[1] is exactly that routine.
-        e->n_launch += (e->n_core_local > 0) ? 2 : 0;
+        e->n_launch += (e->n_core_local > 0) ? 3 : 0;
         const bool single = e->cfg.nranks == 1;
         if (e->n_core_local > 0)
             k_core_gather<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local + 255) / 256)), 256, 0, e->stream>>>(
                 e->L, e->d_core_slots, e->n_core_local, single ? e->d_vfull : e->d_vpart);
         if (!single && gather_core_vector(e)) return 1;
         if (e->n_core_local > 0) {
-#if NG_SPMV_TMA
-            const int grid = (int)std::max<long long>(1, std::min<long long>((long long)e->grid_spmv, (e->n_core_local + NG_SPMV_WARPS - 1) / NG_SPMV_WARPS));
-            k_determ_spmv_tma<<<grid, NG_SPMV_WARPS * 32, NG_SPMV_WARPS * sizeof(SpmvRing), e->stream>>>(
-                e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft,
+            const int cols = (int)std::min<long long>(e->spmv_cb, e->n_core_total);
+            k_determ_spmv_blocked<<<e->grid_spmv, NG_SPMV_THREADS, (size_t)cols * 8, e->stream>>>(
+                e->d_bptr, e->d_bcol, e->d_bval, e->d_vfull, e->d_spmv_work, e->n_core_local, e->n_core_total, e->spmv_cb, e->d_spmv_partial);
+            k_determ_finish<<<std::max(1, (int)std::min<long long>(e->grid_generic, (e->n_core_local + 255) / 256)), 256, 0, e->stream>>>(
+                e->d_spmv_partial, e->d_vfull, e->n_core_local, e->spmv_nb, e->core_displ, tau, diag_sft,
                 e->cfg.t_death_before_comms ? (const double *)nullptr : (const double *)e->d_core_diag, e->d_vout);
-#else
-            const int warps_per_cta = NG_SPMV_BLOCK / 32;
-            const int grid = (int)std::max<long long>(1, std::min<long long>((long long)e->grid_spmv, (e->n_core_local + warps_per_cta - 1) / warps_per_cta));
-            k_determ_spmv<<<grid, NG_SPMV_BLOCK, 0, e->stream>>>(
-                e->d_row_ptr, e->d_col, e->d_val, e->d_vfull, e->n_core_local, e->core_displ, tau, diag_sft,
-                e->cfg.t_death_before_comms ? (const double *)nullptr : (const double *)e->d_core_diag, e->d_vout);
-#endif
         }
     }
     CK(cudaEventRecord(e->ev[1], e->stream));

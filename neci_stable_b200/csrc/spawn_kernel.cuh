@@ -41,6 +41,7 @@ namespace ng {
 #define K1_GEN_BLOCK 256     /* threads per CTA of k_generate */
 #define K1_GEN_TILE 512      /* parents per tile */
 #define K1_MAPW 1024         /* attempts per window of the attempt -> parent map */
+#define K1_GEN_TSEG 256      /* tiles per CTA whose segment is looked up ahead of the tile loop */
 
 struct SpawnBuf {
     long long *buf;          // SpawnedParts: nranks segments of seg_cap records (W words each)
@@ -86,7 +87,8 @@ struct K1Queues {
     u64 *par_d0, *par_d1; u32 *par_meta;            // meta = attempts << 8 | info
     u32 *par_cnt; int par_nseg; long long par_seg_cap;
     // QE: generated excitations waiting for their matrix element, records of qe_rec<NW>() words:
-    //   det word(s), pgen, orbitals | attempt << 32 (orbitals = src1 | src2 << 8 | tgt1 << 16 | tgt2 << 24), info
+    //   det word(s), pgen, orbitals | attempt << 32 | info << 61 (orbitals = src1 | src2 << 8 | tgt1 << 16 | tgt2 << 24;
+    //   k_walk refuses more than 2^29 - 1 attempts per determinant)
     u64 *qe;
     // QS: PCHB single excitations still to be generated, records of qs_rec<NW>() words: det word(s), attempt | info << 32
     u64 *qs;
@@ -94,7 +96,7 @@ struct K1Queues {
     unsigned long long *cnt;                        // [Q_NQE], [Q_NQS]
 };
 enum { Q_NQE = 0, Q_NQS };
-template <int NW> __host__ __device__ constexpr int qe_rec() { return NW + 3; }
+template <int NW> __host__ __device__ constexpr int qe_rec() { return NW + 2; }
 template <int NW> __host__ __device__ constexpr int qs_rec() { return NW + 1; }
 // info bits of a parent: 1 negative sign, 2 initiator, 4 core determinant
 
@@ -476,6 +478,7 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_walk(Params P, WalkerList L, Sp
                 }
                 if (news != s) { L.sgn[slot] = news; mirror_sign<NW>(L, slot, news); }
                 if (f != f0) { L.flg[slot] = f; mirror_flags<NW>(L, slot, f); }
+                if (nsp >= (1 << 29)) atomicOr((unsigned long long *)&L.ctr[C_ERR], 512ull);     // attempt index field of the queues
                 if (nsp > NG_HEAVY) {
                     const long long k = (long long)atomicAdd((unsigned long long *)&L.ctr[C_NHEAVY], 1ull);
                     if (k < SB.heavy_cap) { SB.heavy[2 * k] = slot; SB.heavy[2 * k + 1] = ((long long)nsp << 8) | info; }
@@ -572,8 +575,7 @@ __device__ __forceinline__ void generate_and_push(const Params &P, const WalkerL
             rec[0] = d.w[0]; if (NW > 1) rec[NW - 1] = d.w[NW - 1];
             rec[NW] = (unsigned long long)__double_as_longlong(E.pgen);
             rec[NW + 1] = (unsigned long long)((u32)E.src1 | ((u32)E.src2 << 8) | ((u32)E.tgt1 << 16) | ((u32)E.tgt2 << 24)) |
-                          ((unsigned long long)p << 32);
-            rec[NW + 2] = (unsigned long long)info;
+                          ((unsigned long long)p << 32) | ((unsigned long long)info << 61);
         }
         fill_e += __popc(m);
         __syncwarp();
@@ -604,6 +606,7 @@ template <int NW> struct GenShared {
     unsigned char p_info[K1_GEN_TILE];
     int wsum[K1_GEN_BLOCK / 32];
     int seg_tile0[NG_MAX_PAR_SEG + 1];   // first tile of every segment of the parent list
+    unsigned short tile_seg[K1_GEN_TSEG]; // segment of this CTA's t-th tile, found by K1_GEN_TSEG threads at once
     int cur_seg;
 };
 
@@ -625,14 +628,19 @@ __global__ void __launch_bounds__(K1_GEN_BLOCK) k_generate(Params P, WalkerList 
     __syncthreads();
     const int n_tiles = S.seg_tile0[nseg];
     constexpr int SPT = K1_GEN_TILE / K1_GEN_BLOCK;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (tid == 0) {                                          // segment of this tile: last sg with seg_tile0[sg] <= tile
-            int lo_s = 0, hi_s = nseg;
-            while (hi_s - lo_s > 1) { const int mid = (lo_s + hi_s) >> 1; if (S.seg_tile0[mid] <= tile) lo_s = mid; else hi_s = mid; }
-            S.cur_seg = lo_s;
-        }
+    // segment of a tile: last sg with seg_tile0[sg] <= tile.  One thread per tile of this CTA searches ahead of the loop
+    // (a search by one thread per tile, the rest waiting at the barrier, was 11 % of the kernel's stall samples)
+    auto seg_of = [&](int tile) {
+        int lo_s = 0, hi_s = nseg;
+        while (hi_s - lo_s > 1) { const int mid = (lo_s + hi_s) >> 1; if (S.seg_tile0[mid] <= tile) lo_s = mid; else hi_s = mid; }
+        return lo_s;
+    };
+    if (tid < K1_GEN_TSEG && (long long)blockIdx.x + (long long)tid * gridDim.x < n_tiles) S.tile_seg[tid] = (unsigned short)seg_of(blockIdx.x + tid * gridDim.x);
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        if (ti >= K1_GEN_TSEG && tid == 0) S.cur_seg = seg_of(tile);
         __syncthreads();                                         // also: the previous tile's parents and map are overwritten
-        const int lo_s = S.cur_seg;
+        const int lo_s = (ti < K1_GEN_TSEG) ? (int)S.tile_seg[ti] : S.cur_seg;
         const long long q0 = (long long)lo_s * K.par_seg_cap + (long long)(tile - S.seg_tile0[lo_s]) * K1_GEN_TILE;
         const long long q_end = (long long)lo_s * K.par_seg_cap + (long long)K.par_cnt[lo_s];
         int nsp_k[SPT], off_k[SPT];
@@ -778,7 +786,7 @@ __global__ void __launch_bounds__(NG_BLOCK) k_evaluate(Params P, WalkerList L, S
             const u64 oa = __ldcs(&rec[NW + 1]);
             const u32 o = (u32)oa;
             E.src1 = o & 0xff; E.src2 = (o >> 8) & 0xff; E.tgt1 = (o >> 16) & 0xff; E.tgt2 = o >> 24;
-            att = (u32)(oa >> 32); info = (int)__ldcs(&rec[NW + 2]);
+            att = (u32)(oa >> 32) & 0x1FFFFFFFu; info = (int)(oa >> 61);
         }
         const u64 h = det_hash64(d);
         evaluate_and_append<NW, SYS, IC>(P, L, SB, A, S, B, fill, active, d, E, info, h, att, acc);
