@@ -200,7 +200,7 @@ __device__ __forceinline__ double off_diagonal_matel(const Params &P, const Det<
 // get_det_block / DetermineDetNode with the RandomOrbIndex table staged in
 // shared memory (roi).  Two's-complement wrap, Fortran mod and abs reproduced.
 template <int NW>
-__device__ __forceinline__ int det_block(const Params &P, const int *roi, Det<NW> d) {
+__device__ __forceinline__ int det_block(int balance_blocks, u64 bb_magic, const int *roi, Det<NW> d) {
     u64 acc = 0; int i = 1;
     while (det_any(d)) {
         const int o = pop_lowest(d);
@@ -210,12 +210,14 @@ __device__ __forceinline__ int det_block(const Params &P, const int *roi, Det<NW
     // abs(mod(acc, balance_blocks)) with Fortran's truncating mod == |acc| mod balance_blocks; the 64-bit remainder
     // is taken with the host-computed reciprocal floor((2^64 - 1) / balance_blocks): q is the quotient or one less
     const u64 a = ((long long)acc < 0) ? (0ull - acc) : acc;       // |INT64_MIN| = 2^63 fits
-    const u64 B = (u64)P.balance_blocks;
-    const u64 q = __umul64hi(a, P.bb_magic);
+    const u64 B = (u64)balance_blocks;
+    const u64 q = __umul64hi(a, bb_magic);
     u64 r = a - q * B;
     if (r >= B) r -= B;
     return (int)r + 1;
 }
+template <int NW>
+__device__ __forceinline__ int det_block(const Params &P, const int *roi, const Det<NW> &d) { return det_block<NW>(P.balance_blocks, P.bb_magic, roi, d); }
 
 // TestInitiator_explicit (src/fcimc_helper.F90:1142-1243): the initiator flag of a parent for this iteration
 __device__ __forceinline__ bool parent_is_initiator(const Params &P, bool initiator, double as, int exl, bool core) {

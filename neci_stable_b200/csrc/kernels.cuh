@@ -15,8 +15,9 @@
 //   k_list_stats       CalcHashTableStats (load_balancer.fpp:646-805).
 //   k_reduce_stats     the iteration's statistics vector (communicate_estimates' per-rank inputs).
 //   k_determ_spmv_blocked (+ k_determ_finish)  determ_projection / determ_projection_no_death (semi_stoch_procs.F90:105-374).
-//   k_partition_push, k_partition, k_push, k_wait, k_gather
-//                      DetermineDetNode routing + SendProcNewParts over NVLink peer memory.
+//   k_partition, k_push, k_wait, k_gather
+//                      SendProcNewParts over NVLink peer memory (the spawning kernels route and push their spawns
+//                      themselves: spawn_stage_push in spawn_kernel.cuh) / routing for the NCCL exchange.
 //   k_rebalance_pack   move_block, sender side (load_balancer.fpp:353-512).
 //   k_pops_*           POPSFILE gather (Popsfile.F90:2054-2107).
 //   k_upload / k_download / k_probe_*   list transfer and the parity probes.
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(256) k_spmv_block_fill(const long long *__rest
 // the four 16-bit columns (chunks start at multiples of four elements and are padded with zeros), NG_SPMV_U
 // quadruples per lane and trip = 40 bytes x NG_SPMV_U in flight per lane with two load instructions per quadruple.
 #ifndef NG_SPMV_U
-#define NG_SPMV_U 4
+#define NG_SPMV_U 2
 #endif
 struct SpmvQuad { double a0, a1, a2, a3; u32 c01, c23; };
 __device__ __forceinline__ void spmv_quad_load(SpmvQuad &Q, const double *bval, const unsigned short *bcol, long long q, bool p) {
@@ -679,6 +680,60 @@ __device__ __forceinline__ void spmv_quad_load(SpmvQuad &Q, const double *bval, 
 }
 __device__ __forceinline__ double spmv_quad_dot(const SpmvQuad &Q, const double *vs) {
     return (Q.a0 * vs[Q.c01 & 0xffffu] + Q.a1 * vs[Q.c01 >> 16]) + (Q.a2 * vs[Q.c23 & 0xffffu] + Q.a3 * vs[Q.c23 >> 16]);
+}
+// A warp's work is a stream of trips (NG_SPMV_U x 32 quadruples each) through its chunks.  The stream is software-
+// pipelined by hand, two register buffers deep: the loads of trip n + 1 are issued before trip n is consumed, so the
+// HBM round trip of one overlaps the shared-memory gathers (4-way bank conflicts on average: random 8-byte reads) and
+// the arithmetic of the other.  Without it the phases of a trip add up in every warp and 32 warps per SM -- all that
+// 200 KB of shared memory per CTA allow -- cannot hide them (ncu: short-scoreboard + MIO-throttle 61 % of the stalls).
+struct SpmvTripMeta { int q, nrem, idx_last; };      // first quadruple (relative to the CTA's first), quadruples left in the chunk, chunk << 1 | last trip
+struct SpmvCursor {
+    const long long *bptr; double *partial;
+    long long idx0, q0;          // first chunk / first quadruple of the CTA's share of this column block
+    int idx, end, qb, nq, qcur;  // relative to idx0 / q0
+    int nqb, nnq;                // the warp's next chunk, prefetched
+};
+__device__ __forceinline__ void spmv_cursor_fetch(const SpmvCursor &C, int idx, int &qb, int &nq) {
+    qb = 0; nq = 0;
+    if (idx < C.end) {
+        const long long s = __ldg(&C.bptr[C.idx0 + idx]), e = __ldg(&C.bptr[C.idx0 + idx + 1]);      // multiples of four
+        qb = (int)((s >> 2) - C.q0); nq = (int)((e - s) >> 2);
+    }
+}
+// moves to the warp's next chunk that holds elements; empty chunks get their zero on the way
+__device__ __forceinline__ void spmv_cursor_advance(SpmvCursor &C, int lane, int nwarp) {
+    for (;;) {
+        C.idx += nwarp; C.qb = C.nqb; C.nq = C.nnq; C.qcur = 0;
+        spmv_cursor_fetch(C, C.idx + nwarp, C.nqb, C.nnq);
+        if (C.idx >= C.end || C.nq > 0) return;
+        if (lane == 0) C.partial[C.idx0 + C.idx] = 0.0;
+    }
+}
+__device__ __forceinline__ bool spmv_cursor_next(SpmvCursor &C, SpmvTripMeta &M, int lane, int nwarp) {
+    if (C.idx >= C.end) return false;
+    M.q = C.qb + C.qcur; M.nrem = C.nq - C.qcur;
+    C.qcur += 32 * NG_SPMV_U;
+    const bool last = C.qcur >= C.nq;
+    M.idx_last = (C.idx << 1) | (last ? 1 : 0);
+    if (last) spmv_cursor_advance(C, lane, nwarp);
+    return true;
+}
+__device__ __forceinline__ void spmv_trip_load(SpmvQuad (&Q)[NG_SPMV_U], const SpmvTripMeta &M, const double *bval4, const unsigned short *bcol4, int lane) {
+#pragma unroll
+    for (int u = 0; u < NG_SPMV_U; ++u) spmv_quad_load(Q[u], bval4, bcol4, (long long)M.q + lane + 32 * u, lane + 32 * u < M.nrem);
+}
+__device__ __forceinline__ void spmv_trip_consume(const SpmvQuad (&Q)[NG_SPMV_U], const SpmvTripMeta &M, const SpmvCursor &C, const double *vs,
+                                                  double &t, int lane) {
+    double tt[NG_SPMV_U];
+#pragma unroll
+    for (int u = 0; u < NG_SPMV_U; ++u) tt[u] = spmv_quad_dot(Q[u], vs);
+#pragma unroll
+    for (int u = 0; u < NG_SPMV_U; ++u) t += tt[u];
+    if (M.idx_last & 1) {
+        const double r = warp_sum(t);
+        if (lane == 0) C.partial[C.idx0 + (M.idx_last >> 1)] = r;
+        t = 0.0;
+    }
 }
 __global__ void __launch_bounds__(NG_SPMV_THREADS, 1) k_determ_spmv_blocked(const long long *__restrict__ bptr, const unsigned short *__restrict__ bcol,
                                                                          const double *__restrict__ bval, const double *__restrict__ v_full,
@@ -696,22 +751,26 @@ __global__ void __launch_bounds__(NG_SPMV_THREADS, 1) k_determ_spmv_blocked(cons
         __syncthreads();                                       // the previous block's slice is still being read
         for (int j = threadIdx.x; j < ncol; j += NG_SPMV_THREADS) spmv_vs[j] = __ldg(&v_full[col0 + j]);
         __syncthreads();
-        for (long long idx = a + warp; idx < b; idx += nwarp) {
-            const long long s = __ldg(&bptr[idx]), e = __ldg(&bptr[idx + 1]);      // multiples of four
-            const long long nq = (e - s) >> 2, q_base = s >> 2;
-            double t = 0.0;
-            for (long long q0 = 0; q0 < nq; q0 += 32 * NG_SPMV_U) {
-                SpmvQuad Q[NG_SPMV_U];
-#pragma unroll
-                for (int u = 0; u < NG_SPMV_U; ++u) { const long long q = q0 + lane + 32 * u; spmv_quad_load(Q[u], bval, bcol, q_base + q, q < nq); }
-                double tt[NG_SPMV_U];
-#pragma unroll
-                for (int u = 0; u < NG_SPMV_U; ++u) tt[u] = spmv_quad_dot(Q[u], spmv_vs);
-#pragma unroll
-                for (int u = 0; u < NG_SPMV_U; ++u) t += tt[u];
-            }
-            t = warp_sum(t);
-            if (lane == 0) partial[idx] = t;
+        SpmvCursor C;
+        C.bptr = bptr; C.partial = partial; C.idx0 = a; C.q0 = __ldg(&bptr[a]) >> 2; C.end = (int)(b - a);
+        C.idx = warp - nwarp;                                  // advance() steps onto the warp's first chunk
+        spmv_cursor_fetch(C, warp, C.nqb, C.nnq);
+        spmv_cursor_advance(C, lane, nwarp);
+        const double *bval4 = bval + 4 * C.q0;
+        const unsigned short *bcol4 = bcol + 4 * C.q0;
+        SpmvQuad QA[NG_SPMV_U], QB[NG_SPMV_U];
+        SpmvTripMeta MA, MB;
+        double t = 0.0;
+        bool hasA = spmv_cursor_next(C, MA, lane, nwarp);
+        if (hasA) spmv_trip_load(QA, MA, bval4, bcol4, lane);
+        while (hasA) {
+            const bool hasB = spmv_cursor_next(C, MB, lane, nwarp);
+            if (hasB) spmv_trip_load(QB, MB, bval4, bcol4, lane);
+            spmv_trip_consume(QA, MA, C, spmv_vs, t, lane);
+            if (!hasB) break;
+            hasA = spmv_cursor_next(C, MA, lane, nwarp);
+            if (hasA) spmv_trip_load(QA, MA, bval4, bcol4, lane);
+            spmv_trip_consume(QB, MB, C, spmv_vs, t, lane);
         }
     }
 }
@@ -923,7 +982,6 @@ __global__ void k_block_pops(Params P, WalkerList L, double *block_parts) {
 // made the round-1 exchange grow with the number of ranks (0.08 / 0.14 / 0.21 ms at 2 / 4 / 8 GPUs): the L2 atomic unit
 // serialises them.  Records of one CTA and destination also become one contiguous run (~32 records at N = 8).
 // All threads of the CTA must call.  Returns the position, or -1 without a record.
-#define NG_MAX_PUSH_RANKS 64
 struct DestReserveScratch { int hist[NG_MAX_PUSH_RANKS]; unsigned long long base[NG_MAX_PUSH_RANKS]; };
 __device__ __forceinline__ long long dest_reserve(DestReserveScratch &R, unsigned long long *cnt, int nranks, bool has, int proc) {
     const u32 lane = threadIdx.x & 31;
@@ -1075,61 +1133,21 @@ __global__ void __launch_bounds__(256) k_push(SpawnBuf SB, PeerBox X, int nranks
         __threadfence_system();
     }
 }
-// Routing and pushing in one kernel (the spawning pass on several ranks with the peer-memory exchange): every lane
-// hashes one staged spawn (DetermineDetNode), the CTA reserves positions per destination, and the record goes
-// straight into the destination rank's inbox over NVLink -- SpawnedParts' per-destination segments are never
-// materialised locally.  Ends like k_push: the last CTA posts the mailboxes.
-template <int NW>
-__global__ void __launch_bounds__(NG_BLOCK) k_partition_push(Params P, WalkerList L, SpawnBuf SB, PeerBox X, unsigned int seq) {
-    __shared__ int s_roi[NG_MAX_BASIS];
-    __shared__ DestReserveScratch R;
-    __shared__ bool s_last;
-    for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) s_roi[i] = P.random_orb_index[i];
-    __syncthreads();
-    const int par = (int)(seq & 1u), nranks = P.nranks, rank = P.rank;
-    long long n = (long long)*SB.stage_cnt; if (n > SB.stage_cap) n = SB.stage_cap;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nloop = ((n + stride - 1) / stride) * stride;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
-        const bool has = i < n;
-        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
-        long long w_sign = 0, w_flag = 0;
-        int proc = 0;
-        if (has) {
-            const long long *rec = SB.stage + (size_t)i * SB.W;
-            d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
-            w_sign = rec[NW]; w_flag = rec[NW + 1];
-            proc = __ldg(&P.lb_mapping[det_block<NW>(P, s_roi, d) - 1]);
-        }
-        const long long pos = dest_reserve(R, SB.cnt, nranks, has, proc);
-        if (!has) continue;
-        if (pos >= SB.seg_cap) { atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull); continue; }
-        long long *out = X.peer_seg[proc] + (((size_t)par * nranks + rank) * SB.seg_cap + pos) * SB.W;
-        out[0] = (long long)d.w[0];
-        if (NW > 1) out[NW - 1] = (long long)d.w[NW - 1];
-        out[NW] = w_sign;
-        out[NW + 1] = w_flag;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(X.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_last) {
-        __threadfence_system();
-        if ((int)threadIdx.x < nranks) {
-            const int dst = threadIdx.x;
-            unsigned long long c = *((volatile unsigned long long *)&SB.cnt[dst]);
-            if (c > (unsigned long long)SB.seg_cap) c = (unsigned long long)SB.seg_cap;
-            volatile unsigned long long *mail = X.peer_mail[dst] + (size_t)par * nranks + rank;
-            *mail = ((unsigned long long)seq << 32) | c;
-        }
-        if (threadIdx.x == 0) *X.ticket = 0u;
-        __threadfence_system();
-    }
-}
-__global__ void k_wait(WalkerList L, SpawnBuf SB, PeerBox X, int nranks, unsigned int seq, long long timeout_cycles) {
+// Mailbox hand-shake of an exchange.  post = true (spawning pass): the spawning kernels have already routed and pushed
+// their spawns into the owners' inboxes (spawn_stage_push, spawn_kernel.cuh), so this rank first posts its counts --
+// the stores of the finished kernels were fenced system-wide by their threads -- and then waits like k_push's partner.
+__global__ void k_wait(WalkerList L, SpawnBuf SB, PeerBox X, int nranks, int rank, unsigned int seq, bool post, long long timeout_cycles) {
     __shared__ unsigned long long s_cnt[64];
     const int par = (int)(seq & 1u);
+    if (post && (int)threadIdx.x < nranks) {
+        const int dst = threadIdx.x;
+        const unsigned long long c = SB.push_cnt[NG_PUSH_CNT_STRIDE * dst];
+        SB.cnt[dst] = c;                                    // ValidSpawnedList - InitialSpawnedSlots, for the statistics
+        if (c > (unsigned long long)SB.seg_cap) atomicOr((unsigned long long *)&L.ctr[C_ERR], 1ull);
+        volatile unsigned long long *mail = X.peer_mail[dst] + (size_t)par * nranks + rank;
+        *mail = ((unsigned long long)seq << 32) | min(c, (unsigned long long)SB.seg_cap);
+        __threadfence_system();
+    }
     if ((int)threadIdx.x < nranks) {
         volatile unsigned long long *mail = X.my_mail + (size_t)par * nranks + threadIdx.x;
         const long long t0 = clock64();

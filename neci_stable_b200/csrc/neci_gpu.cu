@@ -786,18 +786,17 @@ static int exchange_spawns(neci_gpu_engine *e, long long *n_recv_out) {
 static int exchange_spawns_p2p(neci_gpu_engine *e, bool from_stage) {
     const int nr = e->cfg.nranks;
     e->xseq += 1;
-    e->n_launch += 3;
+    e->n_launch += from_stage ? 2 : 3;
     if (e->x_timing && e->x_n > 0) {                       // the previous exchange has long finished
         float ms;
         for (int k = 0; k < 3; ++k) if (cudaEventElapsedTime(&ms, e->x_ev[k], e->x_ev[k + 1]) == cudaSuccess) e->x_ms[k] += ms;
     }
     if (e->x_timing) cudaEventRecord(e->x_ev[0], e->stream);
-    if (from_stage) {                       // spawning pass: route the staged spawns and push them in one kernel
-        if (e->nw == 1) k_partition_push<1><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->X, e->xseq);
-        else k_partition_push<2><<<e->grid_generic, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->X, e->xseq);
-    } else k_push<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->cfg.rank, e->xseq);
+    // spawning pass: the spawning kernels have routed and pushed their spawns already (spawn_stage_push); block moves
+    // arrive packed per destination in SpawnedParts and are copied into the inboxes here
+    if (!from_stage) k_push<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->cfg.rank, e->xseq);
     if (e->x_timing) cudaEventRecord(e->x_ev[1], e->stream);
-    k_wait<<<1, 64, 0, e->stream>>>(e->L, e->SB, e->X, nr, e->xseq, 60000000000ll /* ~30 s of SM clocks: ranks may be skewed by I/O */);
+    k_wait<<<1, 64, 0, e->stream>>>(e->L, e->SB, e->X, nr, e->cfg.rank, e->xseq, from_stage, 60000000000ll /* ~30 s of SM clocks: ranks may be skewed by I/O */);
     if (e->x_timing) cudaEventRecord(e->x_ev[2], e->stream);
     k_gather<<<e->grid_generic, 256, 0, e->stream>>>(e->SB, e->X, nr, e->xseq);
     if (e->x_timing) { cudaEventRecord(e->x_ev[3], e->stream); e->x_n += 1; }
@@ -902,6 +901,11 @@ static int begin_iteration(neci_gpu_engine *e) {
     // ValidSpawnedList = InitialSpawnedSlots etc. (FciMCPar.F90:1237-1248)
     CK(cudaMemsetAsync(e->SB.cnt, 0, (size_t)e->cfg.nranks * 8, e->stream));
     if (e->SB.stage_cnt) CK(cudaMemsetAsync(e->SB.stage_cnt, 0, 8, e->stream));
+    if (e->SB.push_cnt) {
+        CK(cudaMemsetAsync(e->SB.push_cnt, 0, (size_t)e->cfg.nranks * NG_PUSH_CNT_STRIDE * 8, e->stream));
+        // this rank's segment in its peers' inboxes for the exchange that follows the spawning pass
+        e->SB.push_off = ((long long)((e->xseq + 1) & 1u) * e->cfg.nranks + e->cfg.rank) * e->SB.seg_cap;
+    }
     CK(cudaMemsetAsync(&e->L.ctr[C_NHEAVY], 0, 8 * (C_COUNT - C_NHEAVY), e->stream));
     CK(cudaMemsetAsync(e->K.cnt, 0, 32, e->stream));
     return 0;
@@ -1066,7 +1070,10 @@ int neci_gpu_p2p_open(neci_gpu_engine *e, const uint8_t *handles) {
     e->X.cnt_in = e->alloc<unsigned long long>((size_t)2 * nr);
     e->X.ticket = e->alloc<unsigned int>(1);
     e->SB.n_recv_dev = e->alloc<unsigned long long>(1);
-    if (!e->X.peer_seg || !e->X.peer_mail || !e->X.cnt_in || !e->X.ticket || !e->SB.n_recv_dev) return e->fail("allocation failed");
+    e->SB.push_cnt = e->alloc<unsigned long long>((size_t)nr * NG_PUSH_CNT_STRIDE);
+    if (!e->X.peer_seg || !e->X.peer_mail || !e->X.cnt_in || !e->X.ticket || !e->SB.n_recv_dev || !e->SB.push_cnt) return e->fail("allocation failed");
+    CK(cudaMemset(e->SB.push_cnt, 0, (size_t)nr * NG_PUSH_CNT_STRIDE * 8));
+    e->SB.push_seg = e->X.peer_seg;
     CK(cudaMemset(e->X.ticket, 0, 4));
     CK(cudaMemset(e->SB.n_recv_dev, 0, 8));
     CK(cudaDeviceSynchronize());

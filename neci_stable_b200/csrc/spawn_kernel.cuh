@@ -57,10 +57,18 @@ struct SpawnBuf {
     long long *heavy;        // (slot, nspawn) pairs
     long long heavy_cap;
     unsigned long long *n_recv_dev;   // received-record count left on the device by the peer-memory exchange
-    long long *stage;                 // nranks > 1: spawns of the spawning kernel before they are routed (k_partition)
+    long long *stage;                 // nranks > 1, NCCL exchange: spawns of the spawning kernels before they are routed (k_partition)
     unsigned long long *stage_cnt;
     long long stage_cap;
+    // nranks > 1, peer-memory exchange: the spawning kernels route and push their spawns themselves (spawn_stage_push).
+    // push_seg[r] = rank r's inbox mapped here, push_off = first record of this rank's segment there for the
+    // current exchange, push_cnt[16 * r] = records reserved for rank r so far (one counter per 128-byte line: the L2
+    // atomic unit serialises atomics on one line).  Null otherwise.
+    long long *const *push_seg;
+    unsigned long long *push_cnt;
+    long long push_off;
 };
+#define NG_PUSH_CNT_STRIDE 16
 
 struct IterArgs {
     double tau, diag_sft;
@@ -229,17 +237,88 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage<REC, CAP> &B, int &fi
 // the record goes to SpawnedParts.  On several ranks the spawn goes to a staging list first and k_partition_push
 // routes it afterwards: DetermineDetNode costs ~230 instructions, and the partition kernel hashes with every lane busy
 // and the record already on its way over NVLink.  Records are staged per warp and written 32 or more at a time.
-#define NG_SPAWN_STAGE_CAP 64
+#define NG_SPAWN_STAGE_CAP 160     /* flushed at >= 128 */
+#define NG_MAX_PUSH_RANKS 64
 template <int NW> using SpawnStage = WarpStage<NW + 2, NG_SPAWN_STAGE_CAP>;
+// what a warp needs besides its stage to push spawns to their owners
+struct PushScratch { int hist[NG_MAX_PUSH_RANKS]; u32 base[NG_MAX_PUSH_RANKS]; unsigned char proc[NG_SPAWN_STAGE_CAP]; };
+struct PushCtx { PushScratch *R; const int *roi; };
+// create_particle's routing (DetermineDetNode, src/fcimc_helper.F90:152-308) and SendProcNewParts (src/Annihilation.F90:150-247)
+// fused into the flush of a warp's spawn stage: every lane hashes one staged record (all lanes busy, unlike hashing at
+// the point of the spawn where ~5 of 32 lanes hold one), the warp reserves positions in the owners' inbox segments
+// with ONE global atomic per destination and flush (~128 records), and the records go straight over NVLink, in runs
+// of ~128 / nranks consecutive records per destination.  The transfer thus overlaps the spawning kernels; what is
+// left of the exchange afterwards is the mailbox hand-shake.
+// (the arguments are scalars and pointers: a reference to the kernel's Params would make the compiler copy the
+// whole parameter block to the stack for this out-of-line function)
+struct PushArgs {
+    int nranks, balance_blocks, W; u64 bb_magic; const int *lb_mapping;
+    long long *const *push_seg; unsigned long long *push_cnt; long long push_off, seg_cap; long long *err;
+};
 template <int NW>
-__device__ __forceinline__ void spawn_stage_flush(const Params &P, const SpawnBuf &SB, const WalkerList &L, SpawnStage<NW> &B, int &fill) {
+__device__ __noinline__ void spawn_stage_push(const PushArgs A, SpawnStage<NW> *Bp, int fill, PushScratch *Rp, const int *roi) {
+    const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    SpawnStage<NW> &B = *Bp;
+    PushScratch &R = *Rp;
+    for (int d = lane; d < A.nranks; d += 32) R.hist[d] = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (int j0 = 0; j0 < fill; j0 += 32) {                    // owners and their record counts
+        const int j = j0 + lane;
+        int proc = -1;
+        if (j < fill) {
+            Det<NW> d; d.w[0] = B.w[j][0]; if (NW > 1) d.w[NW - 1] = B.w[j][NW - 1];
+            proc = __ldg(&A.lb_mapping[det_block<NW>(A.balance_blocks, A.bb_magic, roi, d) - 1]);
+            R.proc[j] = (unsigned char)proc;
+        }
+        const u32 peers = __match_any_sync(0xffffffffu, proc);
+        if (proc >= 0 && lane == (u32)(__ffs(peers) - 1)) R.hist[proc] += __popc(peers);      // one lane per destination
+        __syncwarp();
+    }
+    for (int d = lane; d < A.nranks; d += 32) {
+        const int c = R.hist[d];
+        R.base[d] = c ? (u32)atomicAdd(&A.push_cnt[NG_PUSH_CNT_STRIDE * d], (unsigned long long)c) : 0u;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int j0 = 0; j0 < fill; j0 += 32) {                    // remote stores
+        const int j = j0 + lane;
+        const int proc = (j < fill) ? (int)R.proc[j] : -1;
+        const u32 peers = __match_any_sync(0xffffffffu, proc);
+        if (proc >= 0) {
+            const long long pos = (long long)R.base[proc] + __popc(peers & lt);
+            if (pos >= A.seg_cap) atomicOr((unsigned long long *)A.err, 1ull);
+            else {
+                long long *out = A.push_seg[proc] + (size_t)(A.push_off + pos) * A.W;
+#pragma unroll
+                for (int w = 0; w < NW + 2; ++w) out[w] = (long long)B.w[j][w];
+            }
+        }
+        __syncwarp();
+        if (proc >= 0 && lane == (u32)(__ffs(peers) - 1)) R.base[proc] += (u32)__popc(peers);
+        __syncwarp();
+    }
+}
+template <int NW>
+__device__ __forceinline__ void spawn_stage_flush(const Params &P, const SpawnBuf &SB, const WalkerList &L, SpawnStage<NW> &B, int &fill,
+                                                  const PushCtx &X) {
+    if (SB.push_seg) {
+        if (fill) {
+            PushArgs A;
+            A.nranks = P.nranks; A.balance_blocks = P.balance_blocks; A.W = SB.W; A.bb_magic = P.bb_magic; A.lb_mapping = P.lb_mapping;
+            A.push_seg = SB.push_seg; A.push_cnt = SB.push_cnt; A.push_off = SB.push_off; A.seg_cap = SB.seg_cap; A.err = &L.ctr[C_ERR];
+            spawn_stage_push<NW>(A, &B, fill, X.R, X.roi);
+        }
+        fill = 0;
+        return;
+    }
     const bool staged = P.nranks > 1;
     warp_stage_flush<NW + 2, NG_SPAWN_STAGE_CAP>(B, fill, staged ? SB.stage_cnt : &SB.cnt[0], staged ? SB.stage_cap : SB.seg_cap,
                                                  (unsigned long long *)(staged ? SB.stage : SB.buf), L, 1ull);
 }
 template <int NW>
 __device__ __forceinline__ void append_spawn_k1(const Params &P, const SpawnBuf &SB, const WalkerList &L, SpawnStage<NW> &B, int &fill,
-                                                bool has, const Det<NW> &detJ, double child, long long flags) {
+                                                const PushCtx &X, bool has, const Det<NW> &detJ, double child, long long flags) {
     const u32 lane = threadIdx.x & 31;
     const u32 m = __ballot_sync(0xffffffffu, has);
     if (m == 0) return;
@@ -252,7 +331,17 @@ __device__ __forceinline__ void append_spawn_k1(const Params &P, const SpawnBuf 
     }
     fill += __popc(m);
     __syncwarp();
-    if (fill >= 32) spawn_stage_flush<NW>(P, SB, L, B, fill);
+    if (fill >= NG_SPAWN_STAGE_CAP - 32) spawn_stage_flush<NW>(P, SB, L, B, fill, X);
+}
+// the CTA's routing scratch: RandomOrbIndex in shared memory and one PushScratch per warp (peer-memory exchange only)
+struct PushShared { int roi[NG_MAX_BASIS]; PushScratch R[NG_BLOCK / 32]; };
+__device__ __forceinline__ PushCtx push_ctx_init(const Params &P, const SpawnBuf &SB, PushShared &S) {
+    if (SB.push_seg) {
+        for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) S.roi[i] = P.random_orb_index[i];
+        __syncthreads();
+    }
+    PushCtx X; X.R = &S.R[threadIdx.x >> 5]; X.roi = S.roi;
+    return X;
 }
 
 // per-thread accumulators of the attempt stages
@@ -292,7 +381,7 @@ __device__ __forceinline__ void att_flush(const WalkerList &L, AttShared &S, con
 // attempt's stream: the rounding number is the first of its RNG_ATT_ROUND stream.  B / fill: the warp's spawn stage.
 template <int NW, int SYS, int IC>
 __device__ __forceinline__ void evaluate_and_append(const Params &P, const WalkerList &L, const SpawnBuf &SB, const IterArgs &A,
-                                                    AttShared &S, SpawnStage<NW> &B, int &fill, bool active, const Det<NW> &d,
+                                                    AttShared &S, SpawnStage<NW> &B, int &fill, const PushCtx &X, bool active, const Det<NW> &d,
                                                     Excit<NW> &E, int info, u64 h, u32 att, AttAcc &acc) {
     bool has = false;
     double child = 0.0;
@@ -366,7 +455,7 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
             if (m && (threadIdx.x & 31) == 0) atomicAdd(&S.tau_cnt[c], __popc(m));
         }
     }
-    append_spawn_k1<NW>(P, SB, L, B, fill, has, E.detJ, child, cflags);
+    append_spawn_k1<NW>(P, SB, L, B, fill, X, has, E.detJ, child, cflags);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -544,7 +633,7 @@ __global__ void __launch_bounds__(NG_BLOCK, 4) k_walk(Params P, WalkerList L, Sp
 // k_generate: one spawning attempt per thread
 // ---------------------------------------------------------------------------------------------------------------
 // stage B1: attempt index p of parent (d, h, info): draw the excitation, stage it for QE / QS.  All lanes must call.
-#define NG_QE_STAGE_CAP 128      /* flushed at >= 96 */
+#define NG_QE_STAGE_CAP 112      /* flushed at >= 80 */
 #define NG_QS_STAGE_CAP 64       /* flushed at >= 32 */
 template <int NW> struct GenStage { WarpStage<qe_rec<NW>(), NG_QE_STAGE_CAP> e; WarpStage<qs_rec<NW>(), NG_QS_STAGE_CAP> s; };
 template <int NW, int SYS>
@@ -579,7 +668,7 @@ __device__ __forceinline__ void generate_and_push(const Params &P, const WalkerL
         }
         fill_e += __popc(m);
         __syncwarp();
-        if (fill_e >= 96)
+        if (fill_e >= NG_QE_STAGE_CAP - 32)
             warp_stage_flush<qe_rec<NW>(), NG_QE_STAGE_CAP>(G.e, fill_e, &K.cnt[Q_NQE], K.qe_cap, K.qe, L, 128ull);
     }
     if (sys_pchb(SYS)) {
@@ -600,7 +689,6 @@ __device__ __forceinline__ void generate_and_push(const Params &P, const WalkerL
 template <int NW> struct GenShared {
     u64 p_d0[K1_GEN_TILE];
     u64 p_d1[(NW > 1) ? K1_GEN_TILE : 1];
-    u64 p_h[K1_GEN_TILE];
     int p_off[K1_GEN_TILE + 1];          // exclusive prefix sum of the attempt counts; [TILE] = total
     unsigned short p_map[K1_MAPW];       // attempt (within the current window) -> parent index in the tile
     unsigned char p_info[K1_GEN_TILE];
@@ -624,7 +712,17 @@ __global__ void __launch_bounds__(K1_GEN_BLOCK) k_generate(Params P, WalkerList 
     const int nseg = K.par_nseg;
     for (int sg = tid; sg < nseg; sg += K1_GEN_BLOCK) S.seg_tile0[sg + 1] = ((int)K.par_cnt[sg] + K1_GEN_TILE - 1) / K1_GEN_TILE;
     __syncthreads();
-    if (tid == 0) { int run = 0; S.seg_tile0[0] = 0; for (int sg = 0; sg < nseg; ++sg) { run += S.seg_tile0[sg + 1]; S.seg_tile0[sg + 1] = run; } }
+    if (warp == 0) {                                             // inclusive prefix sum over the segments: a contiguous share per lane
+        const int per = (nseg + 31) / 32, s0 = min(nseg, lane * per), s1 = min(nseg, s0 + per);
+        int tot = 0;
+        for (int sg = s0; sg < s1; ++sg) tot += S.seg_tile0[sg + 1];
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        int run = incl - tot;
+        for (int sg = s0; sg < s1; ++sg) { run += S.seg_tile0[sg + 1]; S.seg_tile0[sg + 1] = run; }
+        if (lane == 0) S.seg_tile0[0] = 0;
+    }
     __syncthreads();
     const int n_tiles = S.seg_tile0[nseg];
     constexpr int SPT = K1_GEN_TILE / K1_GEN_BLOCK;
@@ -652,7 +750,7 @@ __global__ void __launch_bounds__(K1_GEN_BLOCK) k_generate(Params P, WalkerList 
             u32 meta = 0;
             if (q < q_end) { d.w[0] = __ldcs(&K.par_d0[q]); if (NW > 1) d.w[NW - 1] = __ldcs(&K.par_d1[q]); meta = __ldcs(&K.par_meta[q]); }
             S.p_d0[idx] = d.w[0]; if (NW > 1) S.p_d1[idx] = d.w[NW - 1];
-            S.p_h[idx] = det_hash64(d); S.p_info[idx] = (unsigned char)(meta & 0xffu);
+            S.p_info[idx] = (unsigned char)(meta & 0xffu);
             nsp_k[kk] = (int)(meta >> 8);
         }
         // exclusive prefix sum of the attempt counts over the tile (index order kk * BLOCK + tid)
@@ -707,7 +805,7 @@ __global__ void __launch_bounds__(K1_GEN_BLOCK) k_generate(Params P, WalkerList 
                 if (active) {
                     const int lo = S.p_map[a - wb];
                     dp.w[0] = S.p_d0[lo]; if (NW > 1) dp.w[NW - 1] = S.p_d1[lo];
-                    h = S.p_h[lo]; info = S.p_info[lo]; p = (u32)(a - S.p_off[lo]);
+                    h = det_hash64(dp); info = S.p_info[lo]; p = (u32)(a - S.p_off[lo]);    // the hash again per attempt: 4 KB of shared memory buy a fifth CTA per SM
                 }
                 generate_and_push<NW, SYS>(P, L, K, A, G, fill_e, fill_s, active, dp, h, info, p, acc);
             }
@@ -761,13 +859,15 @@ __global__ void __launch_bounds__(K1_GEN_BLOCK) k_generate_heavy(Params P, Walke
 // k_evaluate: one thread per QE entry (stage B2)
 // ---------------------------------------------------------------------------------------------------------------
 template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK) k_evaluate(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
+__global__ void __launch_bounds__(NG_BLOCK, sys_hphf(SYS) ? 4 : 5) k_evaluate(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
     __shared__ AttShared S;
     __shared__ SpawnStage<NW> s_stage[NG_BLOCK / 32];
     __shared__ double s_red[6 * 32];
     constexpr int IC = (SYS == NECI_SYS_HUBBARD_RS) ? 1 : 2;
+    __shared__ PushShared s_push;
     SpawnStage<NW> &B = s_stage[threadIdx.x >> 5];
     int fill = 0;
+    const PushCtx X = push_ctx_init(P, SB, s_push);
     att_shared_init(P, S);
     AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
     long long n = (long long)K.cnt[Q_NQE]; if (n > K.qe_cap) n = K.qe_cap;
@@ -789,9 +889,10 @@ __global__ void __launch_bounds__(NG_BLOCK) k_evaluate(Params P, WalkerList L, S
             att = (u32)(oa >> 32) & 0x1FFFFFFFu; info = (int)(oa >> 61);
         }
         const u64 h = det_hash64(d);
-        evaluate_and_append<NW, SYS, IC>(P, L, SB, A, S, B, fill, active, d, E, info, h, att, acc);
+        evaluate_and_append<NW, SYS, IC>(P, L, SB, A, S, B, fill, X, active, d, E, info, h, att, acc);
     }
-    spawn_stage_flush<NW>(P, SB, L, B, fill);
+    spawn_stage_flush<NW>(P, SB, L, B, fill, X);
+    if (SB.push_seg) __threadfence_system();                  // the pushed records are visible at their owners before the mailboxes are posted
     att_flush(L, S, acc, partials, s_red);
 }
 
@@ -803,8 +904,10 @@ __global__ void __launch_bounds__(NG_BLOCK) k_singles(Params P, WalkerList L, Sp
     __shared__ AttShared S;
     __shared__ SpawnStage<NW> s_stage[NG_BLOCK / 32];
     __shared__ double s_red[6 * 32];
+    __shared__ PushShared s_push;
     SpawnStage<NW> &B = s_stage[threadIdx.x >> 5];
     int fill = 0;
+    const PushCtx X = push_ctx_init(P, SB, s_push);
     att_shared_init(P, S);
     AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
     long long n = (long long)K.cnt[Q_NQS]; if (n > K.qs_cap) n = K.qs_cap;
@@ -829,9 +932,10 @@ __global__ void __launch_bounds__(NG_BLOCK) k_singles(Params P, WalkerList L, Sp
             if (E.valid) acc.valid += 1;
             else { acc.invalid += 1; active = false; }
         }
-        evaluate_and_append<NW, SYS, 1>(P, L, SB, A, S, B, fill, active, d, E, info, h, att, acc);
+        evaluate_and_append<NW, SYS, 1>(P, L, SB, A, S, B, fill, X, active, d, E, info, h, att, acc);
     }
-    spawn_stage_flush<NW>(P, SB, L, B, fill);
+    spawn_stage_flush<NW>(P, SB, L, B, fill, X);
+    if (SB.push_seg) __threadfence_system();                  // the pushed records are visible at their owners before the mailboxes are posted
     att_flush(L, S, acc, partials, s_red);
 }
 
