@@ -375,6 +375,16 @@ module neci_gpu_interface
             integer(c_int) :: err
         end function
 
+        ! benchmark set-up: this rank's share of a frozen synthetic list generated on the device
+        function neci_gpu_synthetic_list(handle, n_dets_total, seed, n_local_out) result(err) bind(c, name='neci_gpu_synthetic_list')
+            import :: c_int, c_ptr, c_int64_t
+            type(c_ptr), value :: handle
+            integer(c_int64_t), value :: n_dets_total
+            integer(c_int64_t), value :: seed
+            integer(c_int64_t), intent(out) :: n_local_out
+            integer(c_int) :: err
+        end function
+
         ! ---- batch probes -------------------------------------------------------------------------------------------------
         function neci_gpu_probe_det_node(handle, n, iluts, block_out, node_out) result(err) bind(c, name='neci_gpu_probe_det_node')
             import :: c_int, c_ptr, c_int32_t, c_int64_t

@@ -318,6 +318,15 @@ int64_t neci_gpu_launch_count(const neci_gpu_engine *e);
 int neci_gpu_alloc_host(int64_t bytes, void **out);
 int neci_gpu_free_host(void *p);
 
+/* Benchmark set-up ("frozen synthetic list"): replaces the resident list by this rank's share of
+ * a global list of n_dets_total uniformly random determinants (n_alpha of nBasis/2 spatial orbitals for the alpha
+ * electrons, n_beta for the beta electrons; signs +-round(1 + Exp(1))), generated on the device as a function of
+ * (seed, candidate index) alone -- the global list does not depend on the number of ranks; ownership by
+ * DetermineDetNode (src/load_balance_calcnodes.F90:25-117).  H_ii / H_0i are computed as AddNewHashDet does.  No
+ * counterpart in the reference (its runs grow their list); lists of 1e8-1e9 walkers cannot be built on the host in
+ * the time of a benchmark.  n_local_out: records taken in on this rank (duplicates of a determinant are holes). */
+int neci_gpu_synthetic_list(neci_gpu_engine *e, int64_t n_dets_total, uint64_t seed, int64_t *n_local_out);
+
 /* ---- batch probes (parity tests call the same device functions) ----------- */
 /* get_det_block / DetermineDetNode (src/load_balance_calcnodes.F90:25-117):
  * block is 1-based, node 0-based.                                             */

@@ -310,6 +310,13 @@ class Engine:
         self._check(self._fn("rebalance")(self.h, _p(m, C.c_int32)), "rebalance")
         self.params["load_balance_mapping"] = m.copy()
 
+    def synthetic_list(self, n_dets_total, seed):
+        """Benchmark set-up: this rank's share of a frozen synthetic list of n_dets_total random determinants,
+        generated on the device (include/neci_gpu.h).  Returns the number of records taken in on this rank."""
+        n = C.c_int64(0)
+        self._check(self._fn("synthetic_list")(self.h, C.c_int64(int(n_dets_total)), C.c_uint64(int(seed)), C.byref(n)), "synthetic_list")
+        return n.value
+
     # -- probes ---------------------------------------------------------------------------
     def probe_det_node(self, iluts):
         il = _i64(iluts).reshape(-1, self.nw)

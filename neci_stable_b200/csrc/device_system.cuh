@@ -335,21 +335,20 @@ __device__ __noinline__ void gen_k_hubbard_sweep(const Params &P, const Det<NW> 
 template <int NW>
 __device__ void gen_k_hubbard(const Params &P, const Det<NW> &d, Stream &rng, Excit<NW> &E) {
     E.ic = 2; E.valid = false; E.err = 0; E.pgen = 0.0;
-    int e1, e2, s1, s2;
-    // Rejection loop.  No `return` inside it and an explicit re-convergence after it: with an exit to the end of the
-    // function inside the loop the compiler places the re-convergence point there, and everything below ran with the
-    // warp split into the groups that left the loop together (15.8 of 32 lanes active in the profile).
-    const unsigned conv = __activemask();
-    bool failed = false;
-    for (int guard = 0;; ++guard) {                // pick_spin_opp_elecs
-        e1 = 1 + (int)(rng.draw32() * P.nel);
-        do { e2 = 1 + (int)(rng.draw32() * P.nel); } while (e1 == e2);
-        s1 = select_orb(d, ~0ull, e1); s2 = select_orb(d, ~0ull, e2);
-        if (((s1 ^ s2) & 1) != 0) break;
-        if (guard > 100000) { failed = true; break; }
+    // pick_spin_opp_elecs (src/lattice_models_utils.F90:123-148) without its rejection loop: the pair index from one
+    // number, alpha electron = index mod nOccAlpha, beta electron = index / nOccAlpha, counted in orbital order --
+    // the distribution (every opposite-spin pair with 1 / (nOccAlpha nOccBeta)) and p_elec of the reference's loop,
+    // which on a warp ran until the slowest lane had its pair (a third of the lanes active, 60 % of this generator's
+    // instructions in profiles/r02m_hubk_k1_*).  The CPU checker draws the same way.
+    int s1, s2;
+    {
+        const int nA = P.nocc_alpha, npair = nA * P.nocc_beta;
+        const int idx = min((int)(rng.draw32() * (double)npair), npair - 1);
+        const int ib = idx / nA, ia = idx - ib * nA;
+        const int oa = select_orb(d, NG_ALPHA_MASK, ia + 1), ob = select_orb(d, NG_BETA_MASK, ib + 1);
+        s1 = min(oa, ob); s2 = max(oa, ob);
     }
-    __syncwarp(conv);
-    if (s1 > s2) { const int t = s1; s1 = s2; s2 = t; }
+    const bool failed = false;
     const double p_elec = 1.0 / (double)(P.nocc_beta * P.nocc_alpha);
     const int kij = __ldg(&P.ksum[(gtid(s1) - 1) * P.n_k + (gtid(s2) - 1)]);
     const int *kd = P.kdiff + (size_t)kij * P.n_k;

@@ -449,6 +449,84 @@ __global__ void k_ht_rebuild(Params P, WalkerList L) {
     }
 }
 
+// ---- frozen synthetic walker list, generated on the device (benchmark set-up) ------------------
+// Candidate c of the GLOBAL list is a function of (seed, c) alone: n_alpha of the n_spat spatial orbitals for the alpha
+// electrons and n_beta for the beta electrons, uniformly (sequential selection sampling), sign +-round(1 + Exp(1)).
+// Every rank walks all candidates and keeps the determinants it owns (DetermineDetNode), so the global list does not
+// depend on the number of ranks.  Records go to the AoS staging buffer; duplicates are nulled by k_synth_dedupe, and
+// the list is then taken in by k_upload like an uploaded CurrentDets.
+template <int NW>
+__global__ void __launch_bounds__(256) k_synth_records(Params P, u64 seed, long long n_cand, int n_spat, long long *aos, int W, long long cap,
+                                                       unsigned long long *count) {
+    __shared__ int s_roi[NG_MAX_BASIS];
+    for (int i = threadIdx.x; i < P.nbasis; i += blockDim.x) s_roi[i] = P.random_orb_index[i];
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nloop = ((n_cand + stride - 1) / stride) * stride;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < nloop; c += stride) {
+        bool keep = false;
+        Det<NW> d; d.w[0] = 0; if (NW > 1) d.w[NW - 1] = 0;
+        double sgn = 0.0;
+        if (c < n_cand) {
+            Stream rng(seed, 0x5EED, mix64((u64)c + 0x9E3779B97F4A7C15ull), 0, RNG_ATTEMPT);
+#pragma unroll 1
+            for (int spin = 0; spin < 2; ++spin) {              // 0: alpha (even orbitals), 1: beta (odd orbitals)
+                int need = spin ? P.nocc_beta : P.nocc_alpha;
+#pragma unroll 1
+                for (int o = 0; o < n_spat && need > 0; ++o) {
+                    const u32 u = rng.next_u32();
+                    if ((u64)u * (u64)(n_spat - o) < ((u64)need << 32)) { set_orb(d, 2 * (o + 1) - spin); --need; }
+                }
+            }
+            const double mag = rint(1.0 - log(1.0 - rng.draw53()));
+            sgn = (rng.next_u32() & 1u) ? -mag : mag;
+            keep = (P.nranks == 1) || (__ldg(&P.lb_mapping[det_block<NW>(P, s_roi, d) - 1]) == P.rank);
+        }
+        const u32 m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            const long long pos = (long long)base + __popc(m & lt);
+            if (keep && pos < cap) {
+                long long *rec = aos + (size_t)pos * W;
+                rec[0] = (long long)d.w[0]; if (NW > 1) rec[NW - 1] = (long long)d.w[NW - 1];
+                rec[NW] = __double_as_longlong(sgn); rec[NW + 1] = 0;
+            }
+        }
+    }
+}
+// a determinant drawn twice keeps its first-inserted record; the others get a zero sign (holes at upload).  `ht` is the
+// (cleared) main hash table used as a set over record indices.
+template <int NW>
+__global__ void __launch_bounds__(256) k_synth_dedupe(WalkerList L, long long *aos, int W, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long *rec = aos + (size_t)i * W;
+        Det<NW> d; d.w[0] = (u64)rec[0]; if (NW > 1) d.w[NW - 1] = (u64)rec[NW - 1];
+        const u64 h = det_hash64(d);
+        const u64 entry = ((u64)(u32)(h >> 32) << 32) | (u64)(u32)i;
+        u64 pos = h & L.ht_mask;
+        u64 e = __ldcg(&L.ht[pos]);
+        for (;;) {
+            if (e == HT_EMPTY) {
+                const u64 old = atomicCAS((unsigned long long *)&L.ht[pos], e, entry);
+                if (old == e) break;
+                e = old;
+                continue;
+            }
+            if ((u32)(e >> 32) == (u32)(h >> 32)) {
+                const long long *rj = aos + (size_t)(e & 0xFFFFFFFFull) * W;
+                bool same = (u64)rj[0] == d.w[0];
+                if (NW > 1) same = same && (u64)rj[NW - 1] == d.w[NW - 1];
+                if (same) { rec[NW] = 0; break; }
+            }
+            pos = (pos + 1) & L.ht_mask;
+            e = __ldcg(&L.ht[pos]);
+        }
+    }
+}
+
 // ---- upload / download (AoS ilut(0:NIfTot) <-> SoA) ------------------------------
 template <int NW, int SYS>
 __global__ void __launch_bounds__(256) k_upload(Params P, WalkerList L, const long long *aos, long long n, const double *gd, const double *go, int W,
@@ -664,76 +742,43 @@ __global__ void __launch_bounds__(256) k_spmv_block_fill(const long long *__rest
         __syncwarp();
     }
 }
-// A lane takes whole quadruples of consecutive elements: one 256-bit load for the four values and one 64-bit load for
-// the four 16-bit columns (chunks start at multiples of four elements and are padded with zeros), NG_SPMV_U
-// quadruples per lane and trip = 40 bytes x NG_SPMV_U in flight per lane with two load instructions per quadruple.
-#ifndef NG_SPMV_U
-#define NG_SPMV_U 2
-#endif
-struct SpmvQuad { double a0, a1, a2, a3; u32 c01, c23; };
-__device__ __forceinline__ void spmv_quad_load(SpmvQuad &Q, const double *bval, const unsigned short *bcol, long long q, bool p) {
-    Q.a0 = Q.a1 = Q.a2 = Q.a3 = 0.0; Q.c01 = Q.c23 = 0u;
-    if (p) {
-        asm volatile("ld.global.cs.v2.u32 {%0, %1}, [%2];" : "=r"(Q.c01), "=r"(Q.c23) : "l"(bcol + 4 * q));
-        asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(Q.a0), "=d"(Q.a1), "=d"(Q.a2), "=d"(Q.a3) : "l"(bval + 4 * q));
-    }
-}
-__device__ __forceinline__ double spmv_quad_dot(const SpmvQuad &Q, const double *vs) {
-    return (Q.a0 * vs[Q.c01 & 0xffffu] + Q.a1 * vs[Q.c01 >> 16]) + (Q.a2 * vs[Q.c23 & 0xffffu] + Q.a3 * vs[Q.c23 >> 16]);
-}
-// A warp's work is a stream of trips (NG_SPMV_U x 32 quadruples each) through its chunks.  The stream is software-
-// pipelined by hand, two register buffers deep: the loads of trip n + 1 are issued before trip n is consumed, so the
-// HBM round trip of one overlaps the shared-memory gathers (4-way bank conflicts on average: random 8-byte reads) and
-// the arithmetic of the other.  Without it the phases of a trip add up in every warp and 32 warps per SM -- all that
-// 200 KB of shared memory per CTA allow -- cannot hide them (ncu: short-scoreboard + MIO-throttle 61 % of the stalls).
-struct SpmvTripMeta { int q, nrem, idx_last; };      // first quadruple (relative to the CTA's first), quadruples left in the chunk, chunk << 1 | last trip
-struct SpmvCursor {
-    const long long *bptr; double *partial;
-    long long idx0, q0;          // first chunk / first quadruple of the CTA's share of this column block
-    int idx, end, qb, nq, qcur;  // relative to idx0 / q0
-    int nqb, nnq;                // the warp's next chunk, prefetched
-};
-__device__ __forceinline__ void spmv_cursor_fetch(const SpmvCursor &C, int idx, int &qb, int &nq) {
-    qb = 0; nq = 0;
-    if (idx < C.end) {
-        const long long s = __ldg(&C.bptr[C.idx0 + idx]), e = __ldg(&C.bptr[C.idx0 + idx + 1]);      // multiples of four
-        qb = (int)((s >> 2) - C.q0); nq = (int)((e - s) >> 2);
-    }
-}
-// moves to the warp's next chunk that holds elements; empty chunks get their zero on the way
-__device__ __forceinline__ void spmv_cursor_advance(SpmvCursor &C, int lane, int nwarp) {
-    for (;;) {
-        C.idx += nwarp; C.qb = C.nqb; C.nq = C.nnq; C.qcur = 0;
-        spmv_cursor_fetch(C, C.idx + nwarp, C.nqb, C.nnq);
-        if (C.idx >= C.end || C.nq > 0) return;
-        if (lane == 0) C.partial[C.idx0 + C.idx] = 0.0;
-    }
-}
-__device__ __forceinline__ bool spmv_cursor_next(SpmvCursor &C, SpmvTripMeta &M, int lane, int nwarp) {
-    if (C.idx >= C.end) return false;
-    M.q = C.qb + C.qcur; M.nrem = C.nq - C.qcur;
-    C.qcur += 32 * NG_SPMV_U;
-    const bool last = C.qcur >= C.nq;
-    M.idx_last = (C.idx << 1) | (last ? 1 : 0);
-    if (last) spmv_cursor_advance(C, lane, nwarp);
-    return true;
-}
-__device__ __forceinline__ void spmv_trip_load(SpmvQuad (&Q)[NG_SPMV_U], const SpmvTripMeta &M, const double *bval4, const unsigned short *bcol4, int lane) {
+// One trip of a warp = 256 consecutive elements, 8 per lane (lane, lane + 32, ...): sixteen coalesced streaming loads.
+// They are volatile asm so that ptxas keeps them together in program order; trips go in pairs, the loads of the next
+// one issued before the current one is consumed.  (Tried and measured slower on the same matrix, 0.50 ms for this
+// kernel against: 256-bit value loads with packed column pairs, 4 to 8 quadruples per lane, 0.53-0.63 ms; a
+// trip stream pipelined across chunk boundaries, 0.57 ms -- profiles/r02k_*, r02m_*.  What is left is latency: 32 warps
+// per SM is all that 200 KB of shared memory per CTA allow, and the gathers see 4-way bank conflicts on average.)
+struct SpmvTrip { double a[8]; unsigned short c[8]; };
+__device__ __forceinline__ void spmv_trip_load(SpmvTrip &T, const double *bval, const unsigned short *bcol, long long k) {
 #pragma unroll
-    for (int u = 0; u < NG_SPMV_U; ++u) spmv_quad_load(Q[u], bval4, bcol4, (long long)M.q + lane + 32 * u, lane + 32 * u < M.nrem);
+    for (int u = 0; u < 8; ++u) asm volatile("ld.global.cs.u16 %0, [%1];" : "=h"(T.c[u]) : "l"(bcol + k + 32 * u));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(T.a[u]) : "l"(bval + k + 32 * u));
 }
-__device__ __forceinline__ void spmv_trip_consume(const SpmvQuad (&Q)[NG_SPMV_U], const SpmvTripMeta &M, const SpmvCursor &C, const double *vs,
-                                                  double &t, int lane) {
-    double tt[NG_SPMV_U];
+__device__ __forceinline__ double spmv_trip_dot(const SpmvTrip &T, u32 vs_addr) {
+    double g[8];
 #pragma unroll
-    for (int u = 0; u < NG_SPMV_U; ++u) tt[u] = spmv_quad_dot(Q[u], vs);
+    for (int u = 0; u < 8; ++u) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(g[u]) : "r"(vs_addr + 8u * (u32)T.c[u]));
+    double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-    for (int u = 0; u < NG_SPMV_U; ++u) t += tt[u];
-    if (M.idx_last & 1) {
-        const double r = warp_sum(t);
-        if (lane == 0) C.partial[C.idx0 + (M.idx_last >> 1)] = r;
-        t = 0.0;
+    for (int u = 0; u < 8; u += 2) { t0 += T.a[u] * g[u]; t1 += T.a[u + 1] * g[u + 1]; }
+    return t0 + t1;
+}
+// the tail of a chunk (< 256 elements), predicated
+__device__ __forceinline__ double spmv_tail(const double *__restrict__ bval, const unsigned short *__restrict__ bcol, const double *vs,
+                                            long long k, long long e) {
+    double a[8]; int c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const long long kk = k + 32 * u;
+        const bool p = kk < e;
+        a[u] = p ? __ldcs(&bval[kk]) : 0.0;
+        c[u] = p ? (int)__ldcs(&bcol[kk]) : 0;
     }
+    double t = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t += a[u] * vs[c[u]];
+    return t;
 }
 __global__ void __launch_bounds__(NG_SPMV_THREADS, 1) k_determ_spmv_blocked(const long long *__restrict__ bptr, const unsigned short *__restrict__ bcol,
                                                                          const double *__restrict__ bval, const double *__restrict__ v_full,
@@ -741,6 +786,7 @@ __global__ void __launch_bounds__(NG_SPMV_THREADS, 1) k_determ_spmv_blocked(cons
                                                                          long long n_core, int cb, double *__restrict__ partial) {
     extern __shared__ __align__(16) double spmv_vs[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = NG_SPMV_THREADS / 32;
+    const u32 vs_addr = (u32)__cvta_generic_to_shared(spmv_vs);
     // chunks (flat block-major index c * n_local + i) whose first element lies in this CTA's share of the elements
     const long long idx_lo = work[blockIdx.x], idx_hi = work[blockIdx.x + 1];
     if (idx_lo >= idx_hi) return;
@@ -751,26 +797,26 @@ __global__ void __launch_bounds__(NG_SPMV_THREADS, 1) k_determ_spmv_blocked(cons
         __syncthreads();                                       // the previous block's slice is still being read
         for (int j = threadIdx.x; j < ncol; j += NG_SPMV_THREADS) spmv_vs[j] = __ldg(&v_full[col0 + j]);
         __syncthreads();
-        SpmvCursor C;
-        C.bptr = bptr; C.partial = partial; C.idx0 = a; C.q0 = __ldg(&bptr[a]) >> 2; C.end = (int)(b - a);
-        C.idx = warp - nwarp;                                  // advance() steps onto the warp's first chunk
-        spmv_cursor_fetch(C, warp, C.nqb, C.nnq);
-        spmv_cursor_advance(C, lane, nwarp);
-        const double *bval4 = bval + 4 * C.q0;
-        const unsigned short *bcol4 = bcol + 4 * C.q0;
-        SpmvQuad QA[NG_SPMV_U], QB[NG_SPMV_U];
-        SpmvTripMeta MA, MB;
-        double t = 0.0;
-        bool hasA = spmv_cursor_next(C, MA, lane, nwarp);
-        if (hasA) spmv_trip_load(QA, MA, bval4, bcol4, lane);
-        while (hasA) {
-            const bool hasB = spmv_cursor_next(C, MB, lane, nwarp);
-            if (hasB) spmv_trip_load(QB, MB, bval4, bcol4, lane);
-            spmv_trip_consume(QA, MA, C, spmv_vs, t, lane);
-            if (!hasB) break;
-            hasA = spmv_cursor_next(C, MA, lane, nwarp);
-            if (hasA) spmv_trip_load(QA, MA, bval4, bcol4, lane);
-            spmv_trip_consume(QB, MB, C, spmv_vs, t, lane);
+        for (long long idx = a + warp; idx < b; idx += nwarp) {
+            const long long s = __ldg(&bptr[idx]), e = __ldg(&bptr[idx + 1]);
+            const long long nfull = (e - s) >> 8;
+            double t = 0.0;
+            long long k = s + lane;
+            if (nfull > 0) {                                   // trips in pairs: the next one is requested before this one is consumed
+                SpmvTrip A, B;
+                spmv_trip_load(A, bval, bcol, k);
+                long long n = 1;
+                for (; n + 1 < nfull; n += 2) {
+                    spmv_trip_load(B, bval, bcol, k + 256 * n); t += spmv_trip_dot(A, vs_addr);
+                    spmv_trip_load(A, bval, bcol, k + 256 * (n + 1)); t += spmv_trip_dot(B, vs_addr);
+                }
+                if (n < nfull) { spmv_trip_load(B, bval, bcol, k + 256 * n); t += spmv_trip_dot(A, vs_addr); t += spmv_trip_dot(B, vs_addr); }
+                else t += spmv_trip_dot(A, vs_addr);
+                k += 256 * nfull;
+            }
+            if (k - lane < e) t += spmv_tail(bval, bcol, spmv_vs, k, e);
+            t = warp_sum(t);
+            if (lane == 0) partial[idx] = t;
         }
     }
 }

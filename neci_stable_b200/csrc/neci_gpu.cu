@@ -473,6 +473,8 @@ int neci_gpu_set_system_hubbard_k(neci_gpu_engine *e, int32_t n_k, const int32_t
 }
 
 // -------------------------------------------------------------------------------
+// the list in the AoS staging buffer (n records, optionally followed by the two gdata rows) becomes the resident list
+static int take_in_staged_list(neci_gpu_engine *e, int64_t n, double *dgd, double *dgo);
 int neci_gpu_upload_walkers(neci_gpu_engine *e, const int64_t *current_dets, int64_t n, const double *gd, const double *go) {
     CK(cudaSetDevice(e->cfg.device));
     if (n > e->cfg.max_walkers - 1) return e->fail("upload of %lld walkers exceeds max_walkers", (long long)n);
@@ -482,6 +484,9 @@ int neci_gpu_upload_walkers(neci_gpu_engine *e, const int64_t *current_dets, int
     double *dgd = nullptr, *dgo = nullptr;
     if (gd) { dgd = (double *)(e->d_aos + words); CK(cudaMemcpyAsync(dgd, gd, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream)); }
     if (go) { dgo = (double *)(e->d_aos + words + n); CK(cudaMemcpyAsync(dgo, go, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream)); }
+    return take_in_staged_list(e, n, dgd, dgo);
+}
+static int take_in_staged_list(neci_gpu_engine *e, int64_t n, double *dgd, double *dgo) {
     CK(cudaMemsetAsync(e->L.ctr, 0, C_COUNT * 8, e->stream));
     CK(cudaMemsetAsync(e->L.ht, 0xFF, (size_t)e->ht_cap * 8, e->stream));
     long long nn = n;
@@ -493,6 +498,38 @@ int neci_gpu_upload_walkers(neci_gpu_engine *e, const int64_t *current_dets, int
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     return 0;
+}
+
+int neci_gpu_synthetic_list(neci_gpu_engine *e, int64_t n_dets_total, uint64_t seed, int64_t *n_local_out) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n_dets_total < 0) return e->fail("synthetic_list: negative size");
+    // this rank's share with 10 % + 4096 of slack for the fluctuation of the hash partition
+    const long long cap = std::min<long long>(e->cfg.max_walkers - 1, (long long)(1.1 * (double)n_dets_total / e->cfg.nranks) + 4096);
+    if (ensure_aos(e, (size_t)cap * e->W)) return 1;
+    unsigned long long *d_count = dalloc<unsigned long long>(1);
+    if (!d_count) return e->fail("allocation failed");
+    cudaMemsetAsync(d_count, 0, 8, e->stream);
+    const int n_spat = e->cfg.nbasis / 2;
+    if (e->nw == 1) k_synth_records<1><<<e->grid_generic, 256, 0, e->stream>>>(e->P, seed, n_dets_total, n_spat, e->d_aos, e->W, cap, d_count);
+    else k_synth_records<2><<<e->grid_generic, 256, 0, e->stream>>>(e->P, seed, n_dets_total, n_spat, e->d_aos, e->W, cap, d_count);
+    unsigned long long cnt = 0;
+    cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t rc = cudaStreamSynchronize(e->stream);
+    cudaFree(d_count);
+    if (rc != cudaSuccess || cudaGetLastError() != cudaSuccess) return e->fail("synthetic_list: generation failed: %s", cudaGetErrorString(rc));
+    if ((long long)cnt > cap) return e->fail("synthetic_list: this rank owns %llu determinants, more than max_walkers allows (%lld)", cnt, cap);
+    const long long n = (long long)cnt;
+    CK(cudaMemsetAsync(e->L.ht, 0xFF, (size_t)e->ht_cap * 8, e->stream));
+    if (n > 0) {
+        const int grid = (int)std::min<long long>(e->grid_generic, (n + 255) / 256);
+        if (e->nw == 1) k_synth_dedupe<1><<<grid, 256, 0, e->stream>>>(e->L, e->d_aos, e->W, n);
+        else k_synth_dedupe<2><<<grid, 256, 0, e->stream>>>(e->L, e->d_aos, e->W, n);
+        CK(cudaGetLastError());
+    }
+    e->n_launch += 2;
+    e->n_resident = 0;                      // nothing of an earlier list may be reused by k_upload
+    if (n_local_out) *n_local_out = n;
+    return take_in_staged_list(e, n, nullptr, nullptr);
 }
 
 int neci_gpu_download_walkers(neci_gpu_engine *e, int64_t *current_dets, int64_t *n_out, double *gd, double *go) {
