@@ -358,6 +358,12 @@ def main():
     ap.add_argument("--core-build", default="host", choices=["host", "device"],
                     help="semi-stochastic workloads: who builds the sparse core Hamiltonian")
     ap.add_argument("--trial", type=int, default=10, help="semi-stochastic workloads: determinants in the trial space (0 = none)")
+    ap.add_argument("--list", default="auto", choices=["auto", "host", "device"],
+                    help="where the frozen start list is generated: numpy on the host (uploaded), or on the device "
+                         "(neci_gpu_synthetic_list); auto = device on several GPUs and from 5e7 walkers per GPU")
+    ap.add_argument("--ref-fraction", type=float, default=None,
+                    help="fraction of all walkers placed on the reference determinant (a converged FCIQMC wavefunction holds a "
+                         "few per cent there; it is what unbalances the hash partition).  Default: 0.05 with --load-balance, else 0")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --walkers per GPU (default, the driver's scaling run); strong: --walkers in total, "
                          "split over the GPUs (BASELINE configs[4])")
@@ -439,7 +445,7 @@ def main():
                     rf = r["roofline"]
                     sec[wl]["phase_ms_per_step"] = rf["phase_ms_per_step"]
                     sec[wl]["roofline"] = {kk: {x: kv[x] for x in ("achieved", "peak", "frac", "ms_per_launch", "algorithmic_bytes_per_launch")}
-                                           for kk, kv in rf.get("kernels", {"k_spawn": rf}).items()}
+                                           for kk, kv in rf.get("kernels", {"K1": rf}).items()}
         if rank == 0:
             line["secondary"] = sec
     if rank == 0:
@@ -467,6 +473,14 @@ def run_workload(args, ctx, primary=True):
     max_walkers = int(3 * n_dets + 100000)
     max_spawned = int(max(2 * args.walkers, 400000))
     semi = args.workload in SEMISTOCH
+    # multi-GPU runs and lists of 5e7 walkers and more (the 1e8 - 1e9 walker configurations): the list is generated on
+    # the device (neci_gpu_synthetic_list: every rank keeps its share of ONE global list; numpy needs minutes per rank for
+    # the large ones and draws N times the candidates on N ranks), and MemoryFacPart / MemoryFacSpawn are sized for a
+    # stationary list (the frozen start list shrinks; a spawning pass sends ~0.16 spawns per walker)
+    device_list = (args.list == "device") or (args.list == "auto" and not semi and (world > 1 or args.walkers >= 5.0e7))
+    if device_list and args.walkers >= 5.0e7:
+        max_walkers = int(2.2 * n_dets + 100000)
+        max_spawned = int(0.6 * args.walkers)
     if semi:
         # real coefficients (readinput.F90:569 makes them mandatory with a core space): a third of the attempts leave a
         # spawn of RealSpawnCutoff walkers on a new determinant, so the list of this far-from-equilibrium start grows
@@ -492,7 +506,9 @@ def run_workload(args, ctx, primary=True):
         def keep(il):
             _, node = eng.probe_det_node(il)
             return node == rank
-    rec = random_walker_records(system, n_dets, seed=1000 + rank, keep=keep, keep_frac=1.0 / world)
+    rec = None
+    if not device_list:
+        rec = random_walker_records(system, n_dets, seed=1000 + rank, keep=keep, keep_frac=1.0 / world)
     core_info = None
     if semi:
         # the core determinants join the list with their flags; the sparse core Hamiltonian (this rank's rows) and
@@ -502,13 +518,26 @@ def run_workload(args, ctx, primary=True):
         # half of the population sits in the core space, as in a converged semi-stochastic run (the nominal figure,
         # so that every rank scales the core amplitudes alike)
         rec = np.concatenate([semistoch_records(system, space, rank, l1_total=args.walkers * world), rec])
-    eng.upload_walkers(rec)
+    if device_list:
+        eng.synthetic_list(n_dets * world, 1000)
+    else:
+        eng.upload_walkers(rec)
+    ref_fraction = args.ref_fraction if args.ref_fraction is not None else (0.05 if args.load_balance else 0.0)
+    if ref_fraction > 0.0 and not semi:
+        # the reference determinant with its share of the population, on the rank that owns it (merged into the list by
+        # the annihilation step: AnnihilateSpawnedParts / AddNewHashDet)
+        ref_rec = host.record(system, system.ref_orbs, float(round(ref_fraction * args.walkers * world)),
+                              1 << capi.FLAG_INITIATOR).reshape(1, -1)
+        _, node = eng.probe_det_node(ref_rec[:, :system.nw])
+        if world == 1 or int(node[0]) == rank:
+            eng.annihilate(ref_rec, 0)
     if semi:
         nnz, t_build = semistoch_apply(eng, system, hii, space, rank, build=args.core_build)
         core_info = {"core_build": args.core_build,"core_size": int(space["iluts"].shape[0]), "core_local": int(space["sizes"][rank]), "nnz_local": nnz,
                      "trial_size": 0 if space["trial"] is None else int(space["trial"].shape[0]),
                      "build_s": t_build}
-    tot0 = float(np.abs(rec[:, system.nw].view(np.float64)).sum())
+    tot0 = float(np.abs(rec[:, system.nw].view(np.float64)).sum()) if rec is not None else 0.0
+    del rec
 
     def allsum(x):
         if world == 1:
@@ -547,10 +576,17 @@ def run_workload(args, ctx, primary=True):
             # space: the reference switches balancing off then (load_balancer.fpp:198-201)
             allp = [None] * world
             dist.all_gather_object(allp, eng.block_populations())
-            new_map, moves = driver.plan_load_balance(np.sum(allp, axis=0), params["load_balance_mapping"], world)
+            blocks = np.sum(allp, axis=0)
+            old_map = np.asarray(params["load_balance_mapping"], dtype=np.int32)
+            new_map, moves = driver.plan_load_balance(blocks, old_map, world)
             eng.rebalance(new_map)
             params["load_balance_mapping"] = np.asarray(new_map, dtype=np.int32)
-            lb_moves = len(moves)
+            before = np.bincount(old_map, weights=blocks, minlength=world)
+            after = np.bincount(np.asarray(new_map, dtype=np.int32), weights=blocks, minlength=world)
+            lb_moves = {"blocks_moved_in_warmup": len(moves),
+                        "rank_walkers_before": [float(x) for x in before], "rank_walkers_after": [float(x) for x in after],
+                        "imbalance_before": float(before.max() / before.mean() - 1.0),
+                        "imbalance_after": float(after.max() / after.mean() - 1.0)}
 
     tot_before_timed = tot                                 # global TotParts entering the timed region
     # ---- timed region: K iterations, list resident in HBM
@@ -616,7 +652,8 @@ def run_workload(args, ctx, primary=True):
                      "population_conserved": (bool(resid.max() <= 1e-9 * max(1.0, c[:, 0].max())) if not semi else None),
                      "sampled_owner_is_rank": owner_ok}
 
-    # ---- roofline of the dominant kernel (k_spawn), measured live with CUDA events on the engine's stream
+    # ---- roofline of the dominant phase (K1: the four kernels of the loop over determinants), measured live with CUDA
+    #      events on the engine's stream
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -633,15 +670,16 @@ def run_workload(args, ctx, primary=True):
         # the capture was taken on the default workload at 1e7 walkers: only that run may quote it
         if args.workload != "n2_14e28o_pchb" or abs(args.walkers - 1.0e7) > 1.0:
             raise KeyError("no ncu capture for this configuration")
-        traffic = tj.get("k_spawn_dram_bytes_per_launch")
-        # the kernel is bound by instruction issue, not by HBM: the committed ncu capture's
-        # issue-slot utilisation and warp-instruction count are repeated here beside the HBM fraction
-        ncu_extra = {"ncu_issue_active_pct": tj.get("k_spawn_issue_active_pct"),
-                     "ncu_warp_instructions_per_launch": tj.get("k_spawn_warp_instructions_per_launch"),
+        traffic = tj.get("k1_dram_bytes_per_launch")
+        # K1 is bound by instruction issue and L2 latency, not by HBM: the committed ncu capture's
+        # issue-slot utilisation and warp-instruction counts of its four kernels are repeated here beside the HBM fraction
+        ncu_extra = {"ncu_issue_active_pct": tj.get("k1_issue_active_pct"),
+                     "ncu_warp_instructions_per_launch": tj.get("k1_warp_instructions_per_launch"),
+                     "ncu_kernel_us": tj.get("k1_kernel_us"),
                      "ncu_source": tj.get("source")}
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_spawn", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+    roofline = {"bound": "hbm", "kernel": "K1 = k_walk + k_generate + k_evaluate + k_singles", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_launch": bytes_spawn / args.steps, "ms_per_launch": t_spawn / args.steps,
                 "phase_ms_per_step": {"spawn_death": t_spawn / args.steps, "exchange": t_comm / args.steps,
@@ -666,7 +704,7 @@ def run_workload(args, ctx, primary=True):
         roofline["phase_ms_per_step"]["determ_projection"] = t_det / args.steps
         k1 = {k: roofline[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic",
                                        "algorithmic_bytes_per_launch", "ms_per_launch")}
-        roofline["kernels"] = {"k_spawn": k1, "k_determ_spmv_blocked": k3}
+        roofline["kernels"] = {"K1": k1, "k_determ_spmv_blocked": k3}
         if t_det > t_spawn:                                   # the dominant kernel heads the object
             roofline.update(k3)
 
@@ -742,13 +780,15 @@ def run_workload(args, ctx, primary=True):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "walkers_per_gpu": args.walkers,
+                       "start_list": "device (neci_gpu_synthetic_list)" if device_list else "host (numpy, uploaded)",
                        "walkers_total_end": walkers_end, "determinants_total_end": dets_end, "tau": tau, "shift": sft,
                        "initiator": True, "attempts_per_step": attempts / args.steps,
                        "spawned_per_step": spawned / args.steps, "partition": "DetermineDetNode hash" if world > 1 else "single rank",
                        "exchange": ("push kernel over NVLink peer memory" if args.exchange == "p2p" else "NCCL send/recv") if world > 1 else "none",
                        "l2": "inputs larger than L2 (walker list %.0f MB per GPU > 126 MB)" % (dets_end / world * (8 * system.nw + 28) / 1e6),
                        "wall_ms_per_step": 1e3 * wall / args.steps, **({"semi_stochastic": core_info} if semi else {}),
-                       **({"load_balance": {"blocks_per_rank": 100, "blocks_moved_in_warmup": lb_moves}} if args.load_balance else {})},
+                       **({"load_balance": {"blocks_per_rank": 100, **(lb_moves or {})}} if args.load_balance else {}),
+                       **({"reference_fraction": ref_fraction} if ref_fraction > 0.0 else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "selfcheck": selfcheck,
         }

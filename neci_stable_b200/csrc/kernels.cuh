@@ -451,7 +451,8 @@ __global__ void k_ht_rebuild(Params P, WalkerList L) {
 
 // ---- frozen synthetic walker list, generated on the device (benchmark set-up) ------------------
 // Candidate c of the GLOBAL list is a function of (seed, c) alone: n_alpha of the n_spat spatial orbitals for the alpha
-// electrons and n_beta for the beta electrons, uniformly (sequential selection sampling), sign +-round(1 + Exp(1)).
+// electrons and n_beta for the beta electrons, uniformly (sequential selection sampling), sign +-round(1 + Exp(1))
+// drawn from a stream keyed by the determinant.
 // Every rank walks all candidates and keeps the determinants it owns (DetermineDetNode), so the global list does not
 // depend on the number of ranks.  Records go to the AoS staging buffer; duplicates are nulled by k_synth_dedupe, and
 // the list is then taken in by k_upload like an uploaded CurrentDets.
@@ -479,8 +480,11 @@ __global__ void __launch_bounds__(256) k_synth_records(Params P, u64 seed, long 
                     if ((u64)u * (u64)(n_spat - o) < ((u64)need << 32)) { set_orb(d, 2 * (o + 1) - spin); --need; }
                 }
             }
-            const double mag = rint(1.0 - log(1.0 - rng.draw53()));
-            sgn = (rng.next_u32() & 1u) ? -mag : mag;
+            // the sign is a function of the determinant, not of the candidate: whichever record of a determinant drawn
+            // twice survives k_synth_dedupe, the list is the same
+            Stream rs(seed, 0x5EED, det_hash64(d), 1, RNG_ATTEMPT);
+            const double mag = rint(1.0 - log(1.0 - rs.draw53()));
+            sgn = (rs.next_u32() & 1u) ? -mag : mag;
             keep = (P.nranks == 1) || (__ldg(&P.lb_mapping[det_block<NW>(P, s_roi, d) - 1]) == P.rank);
         }
         const u32 m = __ballot_sync(0xffffffffu, keep);
