@@ -237,9 +237,13 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        """Starts the poller.  nvidia-smi's own start-up (NVML initialisation over all GPUs of the box) takes a second
+        on an 8-GPU node and stalls kernel launches of every process while it lasts -- inside a 20 ms timed region that
+        was a factor of ten on ms_per_step -- so the poller is started during set-up, wait_ready() makes sure it is
+        past that point before the timed region begins, and only the samples taken inside the window count."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -248,7 +252,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_ready(self, timeout=10.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def window(self, t_begin, t_end):
+        """Restricts the report to the samples that arrived between the two perf_counter stamps (one polling period of
+        slack at the end: a sample describes the interval before it)."""
+        self.win = (t_begin, t_end + 0.06)
 
     def stop(self):
         if not self.proc:
@@ -261,7 +275,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        win = getattr(self, "win", None)
+        lines = [ln for (t, ln) in self.lines if win is None or win[0] <= t <= win[1]]
+        if not lines and self.lines and win is not None:        # region shorter than the polling period: the nearest sample
+            lines = [min(self.lines, key=lambda tl: abs(tl[0] - 0.5 * (win[0] + win[1])))[1]]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -492,6 +510,9 @@ def run_workload(args, ctx, primary=True):
                               semi_stochastic=semi, all_real_coeff=semi)
     eng = capi.Engine(params)
     system.apply(eng)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                    # polls through set-up and warm-up; see ClockSampler.start
     if world > 1:
         uid = [eng.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -590,9 +611,8 @@ def run_workload(args, ctx, primary=True):
 
     tot_before_timed = tot                                 # global TotParts entering the timed region
     # ---- timed region: K iterations, list resident in HBM
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.wait_ready()
     acc = np.zeros(capi.ST_COUNT)
     t_spawn = t_ann = t_comm = t_det = 0.0
     cons = []                                              # per iteration: (TotParts after, net change the counters claim)
@@ -616,7 +636,10 @@ def run_workload(args, ctx, primary=True):
         bytes_spawn += n_slot * (8 * system.nw + 12 + 8) + n_occ * 8 + n_occ * 12 + st[ST["NSPAWNED_SENT"]] * 8 * system.W
     ms_dev = eng.timer_stop()
     barrier()
-    wall = time.perf_counter() - w0
+    w1 = time.perf_counter()
+    wall = w1 - w0
+    if rank == 0:
+        sampler.window(w0, w1)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launch_count() - launches0
     ms = allmax(ms_dev)

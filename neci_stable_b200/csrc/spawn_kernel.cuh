@@ -37,6 +37,12 @@
 namespace ng {
 
 #define NG_BLOCK 256         /* block size of the streaming kernels */
+#ifndef K1_WALK_CTAS
+#define K1_WALK_CTAS 4       /* resident CTAs per SM the register allocation of k_walk aims at */
+#endif
+#ifndef K1_SING_CTAS
+#define K1_SING_CTAS 4       /* the same for k_singles */
+#endif
 #define NG_HEAVY 4096        /* attempts per determinant expanded inside a tile of k_generate */
 #define K1_GEN_BLOCK 256     /* threads per CTA of k_generate */
 #define K1_GEN_TILE 512      /* parents per tile */
@@ -237,11 +243,19 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage<REC, CAP> &B, int &fi
 // the record goes to SpawnedParts.  On several ranks the spawn goes to a staging list first and k_partition_push
 // routes it afterwards: DetermineDetNode costs ~230 instructions, and the partition kernel hashes with every lane busy
 // and the record already on its way over NVLink.  Records are staged per warp and written 32 or more at a time.
-#define NG_SPAWN_STAGE_CAP 160     /* flushed at >= 128 */
+#define NG_SPAWN_STAGE_CAP 160     /* one-word determinants: flushed at >= 128; two words: 128 records, flushed at >= 96 (48 KB of static shared memory) */
+template <int NW> __host__ __device__ constexpr int spawn_stage_cap() { return NW == 1 ? NG_SPAWN_STAGE_CAP : 128; }
 #define NG_MAX_PUSH_RANKS 64
-template <int NW> using SpawnStage = WarpStage<NW + 2, NG_SPAWN_STAGE_CAP>;
+template <int NW> using SpawnStage = WarpStage<NW + 2, spawn_stage_cap<NW>()>;
 // what a warp needs besides its stage to push spawns to their owners
-struct PushScratch { int hist[NG_MAX_PUSH_RANKS]; u32 base[NG_MAX_PUSH_RANKS]; unsigned char proc[NG_SPAWN_STAGE_CAP]; };
+struct PushScratch {
+    int hist[NG_MAX_PUSH_RANKS];                       // records of this flush per destination
+    u32 base[NG_MAX_PUSH_RANKS];                       // first position reserved in the destination's segment
+    unsigned short start[NG_MAX_PUSH_RANKS];           // first index of the destination's run in `perm`
+    unsigned short fill[NG_MAX_PUSH_RANKS];
+    unsigned char proc[NG_SPAWN_STAGE_CAP];            // owner of staged record j
+    unsigned char perm[NG_SPAWN_STAGE_CAP];            // staged records grouped by destination
+};
 struct PushCtx { PushScratch *R; const int *roi; };
 // create_particle's routing (DetermineDetNode, src/fcimc_helper.F90:152-308) and SendProcNewParts (src/Annihilation.F90:150-247)
 // fused into the flush of a warp's spawn stage: every lane hashes one staged record (all lanes busy, unlike hashing at
@@ -280,24 +294,36 @@ __device__ __noinline__ void spawn_stage_push(const PushArgs A, SpawnStage<NW> *
         R.base[d] = c ? (u32)atomicAdd(&A.push_cnt[NG_PUSH_CNT_STRIDE * d], (unsigned long long)c) : 0u;
     }
     __syncwarp();
+    if (lane == 0) {                                            // runs of the destinations in the grouped order
+        int run = 0;
+        for (int d = 0; d < A.nranks; ++d) { R.start[d] = (unsigned short)run; R.fill[d] = 0; run += R.hist[d]; }
+    }
+    __syncwarp();
 #pragma unroll 1
-    for (int j0 = 0; j0 < fill; j0 += 32) {                    // remote stores
+    for (int j0 = 0; j0 < fill; j0 += 32) {                    // counting sort of the record indices by destination
         const int j = j0 + lane;
         const int proc = (j < fill) ? (int)R.proc[j] : -1;
         const u32 peers = __match_any_sync(0xffffffffu, proc);
-        if (proc >= 0) {
-            const long long pos = (long long)R.base[proc] + __popc(peers & lt);
-            if (pos >= A.seg_cap) atomicOr((unsigned long long *)A.err, 1ull);
-            else {
-                long long *out = A.push_seg[proc] + (size_t)(A.push_off + pos) * A.W;
-#pragma unroll
-                for (int w = 0; w < NW + 2; ++w) out[w] = (long long)B.w[j][w];
-            }
-        }
+        if (proc >= 0) R.perm[R.start[proc] + R.fill[proc] + __popc(peers & lt)] = (unsigned char)j;
         __syncwarp();
-        if (proc >= 0 && lane == (u32)(__ffs(peers) - 1)) R.base[proc] += (u32)__popc(peers);
+        if (proc >= 0 && lane == (u32)(__ffs(peers) - 1)) R.fill[proc] += (unsigned short)__popc(peers);
         __syncwarp();
     }
+    // Remote stores, word by word in the grouped order: consecutive lanes write consecutive 8-byte words of a
+    // destination's run, so a store instruction covers ten records of (mostly) one destination in one or two contiguous
+    // pieces.  A lane storing its own record word by word sent 8-byte fragments 24 bytes apart: three NVLink packets
+    // per record, and at N = 8 the spawning kernels were bound by the packet rate (+0.19 ms).
+    constexpr int RW = NW + 2;
+    const int nwords = fill * RW;
+#pragma unroll 1
+    for (int i = lane; i < nwords; i += 32) {
+        const int k = i / RW, w = i - k * RW;
+        const int j = R.perm[k], d = R.proc[j];
+        const long long pos = (long long)R.base[d] + (k - (int)R.start[d]);
+        if (pos >= A.seg_cap) { if (w == 0) atomicOr((unsigned long long *)A.err, 1ull); continue; }
+        A.push_seg[d][(size_t)(A.push_off + pos) * RW + w] = (long long)B.w[j][w];
+    }
+    __syncwarp();
 }
 template <int NW>
 __device__ __forceinline__ void spawn_stage_flush(const Params &P, const SpawnBuf &SB, const WalkerList &L, SpawnStage<NW> &B, int &fill,
@@ -313,7 +339,7 @@ __device__ __forceinline__ void spawn_stage_flush(const Params &P, const SpawnBu
         return;
     }
     const bool staged = P.nranks > 1;
-    warp_stage_flush<NW + 2, NG_SPAWN_STAGE_CAP>(B, fill, staged ? SB.stage_cnt : &SB.cnt[0], staged ? SB.stage_cap : SB.seg_cap,
+    warp_stage_flush<NW + 2, spawn_stage_cap<NW>()>(B, fill, staged ? SB.stage_cnt : &SB.cnt[0], staged ? SB.stage_cap : SB.seg_cap,
                                                  (unsigned long long *)(staged ? SB.stage : SB.buf), L, 1ull);
 }
 template <int NW>
@@ -331,7 +357,7 @@ __device__ __forceinline__ void append_spawn_k1(const Params &P, const SpawnBuf 
     }
     fill += __popc(m);
     __syncwarp();
-    if (fill >= NG_SPAWN_STAGE_CAP - 32) spawn_stage_flush<NW>(P, SB, L, B, fill, X);
+    if (fill >= spawn_stage_cap<NW>() - 32) spawn_stage_flush<NW>(P, SB, L, B, fill, X);
 }
 // the CTA's routing scratch: RandomOrbIndex in shared memory and one PushScratch per warp (peer-memory exchange only)
 struct PushShared { int roi[NG_MAX_BASIS]; PushScratch R[NG_BLOCK / 32]; };
@@ -463,7 +489,7 @@ __device__ __forceinline__ void evaluate_and_append(const Params &P, const Walke
 // iteration's attempts go to the parent list.  One thread per slot, two slots per trip (ten loads in flight).
 // ---------------------------------------------------------------------------------------------------------------
 template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK, 4) k_walk(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
+__global__ void __launch_bounds__(NG_BLOCK, K1_WALK_CTAS) k_walk(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
     __shared__ double s_red[13 * 32];
     __shared__ int s_npar;                                  // parents written by this CTA so far
     __shared__ WarpStage<1, 128> s_free[NG_BLOCK / 32];     // slots emptied by this warp, flushed to the FreeSlot stack in bulk
@@ -900,7 +926,7 @@ __global__ void __launch_bounds__(NG_BLOCK, sys_hphf(SYS) ? 4 : 5) k_evaluate(Pa
 // k_singles: one thread per QS entry (stage B3, PCHB only)
 // ---------------------------------------------------------------------------------------------------------------
 template <int NW, int SYS>
-__global__ void __launch_bounds__(NG_BLOCK) k_singles(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
+__global__ void __launch_bounds__(NG_BLOCK, K1_SING_CTAS) k_singles(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
     __shared__ AttShared S;
     __shared__ SpawnStage<NW> s_stage[NG_BLOCK / 32];
     __shared__ double s_red[6 * 32];

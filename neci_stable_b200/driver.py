@@ -139,15 +139,22 @@ class TauSearch:
     CNT_THRESHOLD = 50
 
     def __init__(self, tau, p_singles, p_doubles, p_parallel, consider_par_bias, max_walker_bloom=1.0,
-                 min_tau=1e-7, max_tau=1.0):
+                 min_tau=1e-7, max_tau=1.0, t_hub=False, t_k_space_hubbard=False, reduce_or=None, reduce_max=None):
+        """t_hub / t_k_space_hubbard: the reference's tHub and t_k_space_hubbard (lattice models: tau is re-assigned at
+        every update).  reduce_or / reduce_max: the MPIAllLORLogical / MPIAllReduce(MAX) of update_tau for runs on several
+        ranks (callables on a bool / float array; None = one rank)."""
         self.tau, self.p_singles, self.p_doubles, self.p_parallel = tau, p_singles, p_doubles, p_parallel
         self.par_bias, self.bloom, self.min_tau, self.max_tau = consider_par_bias, max_walker_bloom, min_tau, max_tau
+        self.t_hub, self.t_k_hub = bool(t_hub), bool(t_k_space_hubbard)
+        self.reduce_or, self.reduce_max = reduce_or, reduce_max
         self.gamma = np.zeros(4)                 # sing, doub, par, opp
         self.cnt = np.zeros(4)
         self.max_death_cpt = 0.0
 
     def log(self, stats):
-        """Accumulate one iteration's statistics vector (after the max / sum reduction over ranks)."""
+        """Accumulate THIS RANK's statistics vector of one iteration: the reference keeps gamma_*, cnt_* and the
+        enough_* switches per rank (log_spawn_magnitude) and reduces them inside update_tau (maxima with MPI_MAX, the
+        switches with a logical OR: tau_search_conventional.F90:295-312)."""
         g0 = ST["TAU_GAMMA_SING"]; c0 = ST["TAU_CNT_SING"]
         self.gamma = np.maximum(self.gamma, stats[g0:g0 + 4])
         self.cnt += stats[c0:c0 + 4]
@@ -156,6 +163,8 @@ class TauSearch:
     @property
     def enough(self):
         e = self.cnt > self.CNT_THRESHOLD
+        if self.reduce_or is not None:
+            e = np.asarray(self.reduce_or(e), dtype=bool)
         sing, doub, par, opp = bool(e[0]), bool(e[1]), bool(e[2]), bool(e[3])
         if self.par_bias:
             doub = par and opp
@@ -164,6 +173,9 @@ class TauSearch:
     def update(self):
         """update_tau: returns (tau, p_singles, p_doubles, p_parallel) to use from now on."""
         eps = 1e-13
+        if self.reduce_max is not None:
+            red = np.asarray(self.reduce_max(np.concatenate([self.gamma, [self.max_death_cpt]])), dtype=np.float64)
+            self.gamma = red[:4].copy(); self.max_death_cpt = float(red[4])
         g_sing, g_doub, g_par, g_opp = self.gamma
         e_sing, e_doub, e_par, e_opp = self.enough
         ps_new, pp_new = self.p_singles, self.p_parallel
@@ -198,7 +210,9 @@ class TauSearch:
                 self.min_tau = min(self.min_tau, tau_death)
                 tau_new = tau_death
         tau_new = min(max(tau_new, self.min_tau), self.max_tau)
-        if tau_new < self.tau or (e_sing and e_doub):
+        # the reference's condition as Fortran parses it (.and. binds tighter than .or., :445-450; UEG and the
+        # transcorrelated branches are outside this engine): enough_sing alone re-assigns tau, and so does tHub
+        if (tau_new < self.tau or (e_sing and e_doub) or self.t_hub or e_sing or (self.t_k_hub and e_doub)):
             self.tau = tau_new * 0.99999
         if e_sing and e_doub and 1e-5 < ps_new < 1.0 - 1e-5:
             self.p_singles = ps_new

@@ -117,3 +117,26 @@ def test_tau_search_loop_caps_the_spawns():
     assert (ts.p_singles, ts.p_parallel) != probs0
     assert abs(ts.p_singles + ts.p_doubles - 1.0) < 1e-15
     assert ts.max_death_cpt > 0.0 and tau <= 1.0 / ts.max_death_cpt             # death cap of update_tau
+
+
+def test_tau_assignment_condition_follows_the_reference():
+    """update_tau's final condition as Fortran parses it (src/tau/tau_search_conventional.F90:445-450): tau may be RAISED
+    when enough singles have been seen (enough_sing alone), on lattice models (tHub) at every update, on the k-space
+    lattice with enough doubles; otherwise only lowered.  The enough_* switches of several ranks are OR-ed."""
+    def ts(**kw):
+        t = driver.TauSearch(1e-4, 0.1, 0.9, 0.5, consider_par_bias=False, **kw)
+        t.gamma = np.array([0.05, 0.0, 0.0, 0.0])        # singles only: tau_new = bloom * pSingles / gamma_sing = 2.0 -> max_tau
+        return t
+    t = ts(); t.cnt = np.array([10.0, 0, 0, 0])
+    assert t.update()[0] == 1e-4                                         # too few singles: tau is not raised
+    t = ts(); t.cnt = np.array([60.0, 0, 0, 0])
+    assert abs(t.update()[0] - 0.99999) < 1e-12                          # enough_sing alone raises it
+    t = ts(t_hub=True); t.cnt = np.array([1.0, 0, 0, 0])
+    assert abs(t.update()[0] - 0.99999) < 1e-12                          # tHub: always assigned
+    t = ts(); t.cnt = np.array([10.0, 0, 0, 0])
+    t.reduce_or = lambda e: np.logical_or(e, np.array([True, False, False, False]))   # another rank has seen enough singles
+    assert abs(t.update()[0] - 0.99999) < 1e-12
+    t = ts(); t.cnt = np.array([10.0, 0, 0, 0])
+    t.reduce_max = lambda v: np.maximum(v, np.array([0.4, 0, 0, 0, 5.0e4]))   # another rank's larger gamma and death component
+    t.tau = 1.0
+    assert abs(t.update()[0] - 0.99999 / 5.0e4) < 1e-15                  # lowered to 1 / max_death_cpt
