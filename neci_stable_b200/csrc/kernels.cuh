@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(256) k_reduce_stats(Params P, WalkerList L, Sp
         if (threadIdx.x < o) s_v[threadIdx.x] = is_max ? fmax(s_v[threadIdx.x], s_v[threadIdx.x + o]) : s_v[threadIdx.x] + s_v[threadIdx.x + o];
         __syncthreads();
     }
+    // the device counters ride along behind the statistics (one copy to the host instead of two)
+    if (k == 0 && threadIdx.x < C_COUNT) reinterpret_cast<long long *>(stats)[NECI_ST_COUNT + threadIdx.x] = L.ctr[threadIdx.x];
     if (threadIdx.x != 0) return;
     double out = s_v[0];
     // the statistics that are counters or look-ups rather than sums over the list (InstNoatHF, list length, holes, ...)
@@ -58,6 +60,15 @@ __global__ void __launch_bounds__(256) k_reduce_stats(Params P, WalkerList L, Sp
     else if (k == NECI_ST_BLOOM_SIZE_1) out = __longlong_as_double(L.ctr[C_COUNT - 2]);
     else if (k == NECI_ST_BLOOM_SIZE_2) out = __longlong_as_double(L.ctr[C_COUNT - 1]);
     stats[k] = out;
+}
+
+// ValidSpawnedList = InitialSpawnedSlots etc. (FciMCPar.F90:1237-1248): every per-iteration counter in one launch
+__global__ void k_begin_iteration(WalkerList L, SpawnBuf SB, K1Queues K, int nranks) {
+    const int t = threadIdx.x;
+    if (t < nranks) { SB.cnt[t] = 0ull; if (SB.push_cnt) SB.push_cnt[NG_PUSH_CNT_STRIDE * t] = 0ull; }
+    if (t >= C_NHEAVY && t < C_COUNT) L.ctr[t] = 0;
+    if (t < 4) K.cnt[t] = 0ull;
+    if (t == 0 && SB.stage_cnt) *SB.stage_cnt = 0ull;
 }
 
 // freeB -> freeA, clamp counters (runs with one block per 256 entries + 1)

@@ -173,6 +173,8 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     P.nel = cfg->nel; P.nbasis = cfg->nbasis; P.nocc_alpha = cfg->nocc_alpha; P.nocc_beta = cfg->nocc_beta;
     P.nranks = cfg->nranks; P.rank = cfg->rank; P.balance_blocks = cfg->balance_blocks; P.system_type = cfg->system_type;
     if (cfg->balance_blocks < 1) return e->fail("balance_blocks must be >= 1");
+    if (cfg->nranks < 1 || cfg->nranks > NG_MAX_PUSH_RANKS || cfg->rank < 0 || cfg->rank >= cfg->nranks)
+        return e->fail("nranks must be 1..%d and 0 <= rank < nranks (got rank %d of %d)", NG_MAX_PUSH_RANKS, cfg->rank, cfg->nranks);
     P.bb_magic = ~0ull / (u64)cfg->balance_blocks;
     P.t_trunc_initiator = cfg->t_trunc_initiator; P.t_all_real_coeff = cfg->t_all_real_coeff;
     P.t_real_spawn_cutoff = cfg->t_real_spawn_cutoff; P.t_death_before_comms = cfg->t_death_before_comms;
@@ -275,12 +277,12 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     e->rows_tau = e->grid_generic;            // rows of k_death_magnitude, placed before the trial rows
     e->rows_total = e->rows_spawn + e->rows_heavy + e->rows_compress + e->rows_annih + e->rows_insert + e->rows_list + e->rows_tau + e->rows_trial;
     e->d_partials = e->alloc<double>((size_t)e->rows_total * NECI_ST_COUNT);
-    e->d_stats = e->alloc<double>(NECI_ST_COUNT);
+    e->d_stats = e->alloc<double>(NECI_ST_COUNT + C_COUNT);
     e->d_ticket = e->alloc<unsigned int>(1);
     CK(cudaMemset(e->d_ticket, 0, 4));
     CK(cudaMemset(e->d_partials, 0, (size_t)e->rows_total * NECI_ST_COUNT * 8));
-    CK(cudaMallocHost((void **)&e->h_stats, NECI_ST_COUNT * 8));
-    CK(cudaMallocHost((void **)&e->h_ctr, C_COUNT * 8));
+    CK(cudaMallocHost((void **)&e->h_stats, (NECI_ST_COUNT + C_COUNT) * 8));
+    e->h_ctr = reinterpret_cast<long long *>(e->h_stats + NECI_ST_COUNT);
     if (cfg->nranks > 1) {
         e->d_cnt_all = e->alloc<unsigned long long>((size_t)cfg->nranks * cfg->nranks);
         CK(cudaMallocHost((void **)&e->h_cnt_all, (size_t)cfg->nranks * cfg->nranks * 8));
@@ -304,7 +306,6 @@ int neci_gpu_finalize(neci_gpu_engine *e) {
     for (void *p : e->owned) cudaFree(p);
     if (e->d_aos) cudaFree(e->d_aos);
     if (e->h_stats) cudaFreeHost(e->h_stats);
-    if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_cnt_all) cudaFreeHost(e->h_cnt_all);
     for (auto &v : e->ev) if (v) cudaEventDestroy(v);
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -900,8 +901,8 @@ static int finish_iteration(neci_gpu_engine *e, double *stats_out) {
     else k_reduce_stats<2><<<NECI_ST_COUNT, 256, 0, e->stream>>>(e->P, e->L, e->SB, e->d_partials, e->rows_total, e->d_stats);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[4], e->stream));
-    CK(cudaMemcpyAsync(e->h_stats, e->d_stats, NECI_ST_COUNT * 8, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(e->h_ctr, e->L.ctr, C_COUNT * 8, cudaMemcpyDeviceToHost, e->stream));
+    // statistics and device counters in one copy (k_reduce_stats leaves the counters behind the statistics)
+    CK(cudaMemcpyAsync(e->h_stats, e->d_stats, (NECI_ST_COUNT + C_COUNT) * 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     float ms;
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->h_stats[NECI_ST_TIME_DETERM_MS] = ms;
@@ -935,16 +936,11 @@ static int begin_iteration(neci_gpu_engine *e) {
         e->need_rebuild = false;
         e->n_launch += 1;
     }
-    // ValidSpawnedList = InitialSpawnedSlots etc. (FciMCPar.F90:1237-1248)
-    CK(cudaMemsetAsync(e->SB.cnt, 0, (size_t)e->cfg.nranks * 8, e->stream));
-    if (e->SB.stage_cnt) CK(cudaMemsetAsync(e->SB.stage_cnt, 0, 8, e->stream));
-    if (e->SB.push_cnt) {
-        CK(cudaMemsetAsync(e->SB.push_cnt, 0, (size_t)e->cfg.nranks * NG_PUSH_CNT_STRIDE * 8, e->stream));
-        // this rank's segment in its peers' inboxes for the exchange that follows the spawning pass
+    // ValidSpawnedList = InitialSpawnedSlots etc. (FciMCPar.F90:1237-1248): one launch for all per-iteration counters
+    if (e->SB.push_cnt)        // this rank's segment in its peers' inboxes for the exchange that follows the spawning pass
         e->SB.push_off = ((long long)((e->xseq + 1) & 1u) * e->cfg.nranks + e->cfg.rank) * e->SB.seg_cap;
-    }
-    CK(cudaMemsetAsync(&e->L.ctr[C_NHEAVY], 0, 8 * (C_COUNT - C_NHEAVY), e->stream));
-    CK(cudaMemsetAsync(e->K.cnt, 0, 32, e->stream));
+    k_begin_iteration<<<1, 64, 0, e->stream>>>(e->L, e->SB, e->K, e->cfg.nranks);
+    e->n_launch += 1;
     return 0;
 }
 

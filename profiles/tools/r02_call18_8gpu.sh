@@ -3,7 +3,7 @@
 # configs[4] (Cr2-sized 24e/30o, 1e9 walkers, strong-scaling point N = 8 with load balancing)
 mkdir -p gpurun_out
 export PYTHONFAULTHANDLER=1
-T=r02r
+T=r02u
 N=${1:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${T}_gpus_${N}.txt
@@ -25,7 +25,7 @@ echo "hubk 1e8 rc=$? wall ${SECONDS}s"
 fi
 python - <<'PY'
 import json, glob
-for f in sorted(glob.glob("gpurun_out/r02r_*gpu.json")):
+for f in sorted(glob.glob("gpurun_out/r02u_*gpu.json")):
     try:
         d = json.loads([l for l in open(f) if l.startswith("{")][-1]); r = d["roofline"]
         print(f, "value %.3e ms/step %.3f" % (d["value"], d["ms_per_step"]), r["phase_ms_per_step"], d.get("selfcheck"), d["config"].get("walkers_total_end"), d["config"].get("load_balance"))
