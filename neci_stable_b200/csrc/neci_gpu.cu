@@ -56,6 +56,13 @@ template <class T> T *dalloc(size_t n) {
     return (T *)p;
 }
 
+// scratch device buffers of one call: freed on every return path
+struct Scratch {
+    std::vector<void *> ptrs; bool ok = true;
+    template <class T> T *get(size_t n) { T *p = dalloc<T>(n); if (!p) ok = false; else ptrs.push_back(p); return p; }
+    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+};
+
 }  // namespace
 
 struct neci_gpu_engine {
@@ -560,32 +567,33 @@ int neci_gpu_download_occupied(neci_gpu_engine *e, double min_weight, int64_t *d
     CK(cudaMemcpyAsync(&n, &e->L.ctr[C_NLIST], 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     const long long nchunks = std::max<long long>(1, (n + NG_POPS_CHUNK - 1) / NG_POPS_CHUNK);
-    int *d_cnt = dalloc<int>((size_t)nchunks); long long *d_tot = dalloc<long long>(1);
-    if (!d_cnt || !d_tot) return e->fail("allocation failed");
+    Scratch sc;
+    int *d_cnt = sc.get<int>((size_t)nchunks); long long *d_tot = sc.get<long long>(1);
+    if (!sc.ok) return e->fail("download_occupied: device allocation failed");
     const int grid = (int)std::min<long long>(e->grid_generic, nchunks);
     e->n_launch += 2;
     k_pops_count<<<grid, 256, 0, e->stream>>>(e->L, min_weight, d_cnt);
     k_pops_scan<<<1, 1024, 0, e->stream>>>(e->L, d_cnt, d_tot);
+    CK(cudaGetLastError());
     long long tot = 0;
     CK(cudaMemcpyAsync(&tot, d_tot, 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (n_out) *n_out = tot;
-    int rc = 0;
     if (dets_out && tot > 0) {
         // staging: records, then the two gdata rows
-        if (ensure_aos(e, (size_t)tot * e->W + 2 * (size_t)tot)) { cudaFree(d_cnt); cudaFree(d_tot); return 1; }
+        if (ensure_aos(e, (size_t)tot * e->W + 2 * (size_t)tot)) return 1;
         double *dgd = gd ? (double *)(e->d_aos + (size_t)tot * e->W) : nullptr;
         double *dgo = go ? (double *)(e->d_aos + (size_t)tot * e->W + tot) : nullptr;
         e->n_launch += 1;
         if (e->nw == 1) k_pops_write<1><<<grid, 256, 0, e->stream>>>(e->L, min_weight, d_cnt, e->d_aos, e->W, dgd, dgo);
         else k_pops_write<2><<<grid, 256, 0, e->stream>>>(e->L, min_weight, d_cnt, e->d_aos, e->W, dgd, dgo);
-        cudaMemcpyAsync(dets_out, e->d_aos, (size_t)tot * e->W * 8, cudaMemcpyDeviceToHost, e->stream);
-        if (gd) cudaMemcpyAsync(gd, dgd, (size_t)tot * 8, cudaMemcpyDeviceToHost, e->stream);
-        if (go) cudaMemcpyAsync(go, dgo, (size_t)tot * 8, cudaMemcpyDeviceToHost, e->stream);
-        if (cudaStreamSynchronize(e->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = e->fail("download_occupied failed");
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(dets_out, e->d_aos, (size_t)tot * e->W * 8, cudaMemcpyDeviceToHost, e->stream));
+        if (gd) CK(cudaMemcpyAsync(gd, dgd, (size_t)tot * 8, cudaMemcpyDeviceToHost, e->stream));
+        if (go) CK(cudaMemcpyAsync(go, dgo, (size_t)tot * 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
     }
-    cudaFree(d_cnt); cudaFree(d_tot);
-    return rc;
+    return 0;
 }
 
 // -------------------------------------------------------------------------------
@@ -1194,45 +1202,48 @@ int neci_gpu_free_host(void *p) { return (!p || cudaFreeHost(p) == cudaSuccess) 
 // ---- probes -----------------------------------------------------------------------
 int neci_gpu_probe_det_node(neci_gpu_engine *e, int64_t n, const int64_t *iluts, int32_t *block_out, int32_t *node_out) {
     CK(cudaSetDevice(e->cfg.device));
-    long long *d_il = dalloc<long long>((size_t)n * e->nw); int *d_b = dalloc<int>(n), *d_n = dalloc<int>(n);
-    cudaMemcpy(d_il, iluts, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice);
+    Scratch sc;
+    long long *d_il = sc.get<long long>((size_t)n * e->nw); int *d_b = sc.get<int>(n), *d_n = sc.get<int>(n);
+    if (!sc.ok) return e->fail("probe_det_node: device allocation failed (n = %lld)", (long long)n);
+    CK(cudaMemcpy(d_il, iluts, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice));
     const int grid = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, (n + 255) / 256));
     if (e->nw == 1) k_probe_det_node<1><<<grid, 256, 0, e->stream>>>(e->P, d_il, n, d_b, d_n);
     else k_probe_det_node<2><<<grid, 256, 0, e->stream>>>(e->P, d_il, n, d_b, d_n);
-    cudaError_t rc = cudaStreamSynchronize(e->stream);
-    cudaMemcpy(block_out, d_b, n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(node_out, d_n, n * 4, cudaMemcpyDeviceToHost);
-    cudaFree(d_il); cudaFree(d_b); cudaFree(d_n);
-    if (rc != cudaSuccess) return e->fail("probe_det_node: %s", cudaGetErrorString(rc));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(block_out, d_b, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(node_out, d_n, n * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 int neci_gpu_probe_helement(neci_gpu_engine *e, int64_t n, const int64_t *ii, const int64_t *ij, double *out) {
     CK(cudaSetDevice(e->cfg.device));
-    long long *d_i = dalloc<long long>((size_t)n * e->nw), *d_j = dalloc<long long>((size_t)n * e->nw); double *d_o = dalloc<double>(n);
-    cudaMemcpy(d_i, ii, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice); cudaMemcpy(d_j, ij, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice);
+    Scratch sc;
+    long long *d_i = sc.get<long long>((size_t)n * e->nw), *d_j = sc.get<long long>((size_t)n * e->nw); double *d_o = sc.get<double>(n);
+    if (!sc.ok) return e->fail("probe_helement: device allocation failed (n = %lld)", (long long)n);
+    CK(cudaMemcpy(d_i, ii, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_j, ij, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice));
     const int grid = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, (n + 255) / 256));
     NG_DISPATCH(e, (k_probe_helement<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, d_i, d_j, n, d_o)));
-    cudaError_t rc = cudaStreamSynchronize(e->stream);
-    cudaMemcpy(out, d_o, n * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_i); cudaFree(d_j); cudaFree(d_o);
-    if (rc != cudaSuccess) return e->fail("probe_helement: %s", cudaGetErrorString(rc));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, d_o, n * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 int neci_gpu_probe_gen_excit(neci_gpu_engine *e, int64_t n, const int64_t *iluts, const int32_t *attempt, int64_t iter,
                              int64_t *ilut_j_out, int32_t *ic_out, int32_t *ex_out, int32_t *parity_out,
                              double *pgen_out, double *hel_out) {
     CK(cudaSetDevice(e->cfg.device));
-    long long *d_il = dalloc<long long>((size_t)n * e->nw), *d_j = dalloc<long long>((size_t)n * e->nw);
-    int *d_at = dalloc<int>(n), *d_ic = dalloc<int>(n), *d_ex = dalloc<int>(4 * n), *d_par = dalloc<int>(n);
-    double *d_pg = dalloc<double>(n), *d_h = dalloc<double>(n);
-    cudaMemcpy(d_il, iluts, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice); cudaMemcpy(d_at, attempt, n * 4, cudaMemcpyHostToDevice);
+    Scratch sc;
+    long long *d_il = sc.get<long long>((size_t)n * e->nw), *d_j = sc.get<long long>((size_t)n * e->nw);
+    int *d_at = sc.get<int>(n), *d_ic = sc.get<int>(n), *d_ex = sc.get<int>(4 * n), *d_par = sc.get<int>(n);
+    double *d_pg = sc.get<double>(n), *d_h = sc.get<double>(n);
+    if (!sc.ok) return e->fail("probe_gen_excit: device allocation failed (n = %lld)", (long long)n);
+    CK(cudaMemcpy(d_il, iluts, (size_t)n * e->nw * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_at, attempt, n * 4, cudaMemcpyHostToDevice));
     const int grid = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, (n + 255) / 256));
     NG_DISPATCH(e, (k_probe_gen_excit<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, d_il, d_at, iter, n, d_j, d_ic, d_ex, d_par, d_pg, d_h)));
-    cudaError_t rc = cudaStreamSynchronize(e->stream);
-    cudaMemcpy(ilut_j_out, d_j, (size_t)n * e->nw * 8, cudaMemcpyDeviceToHost); cudaMemcpy(ic_out, d_ic, n * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(ex_out, d_ex, 4 * n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(parity_out, d_par, n * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(pgen_out, d_pg, n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(hel_out, d_h, n * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_il); cudaFree(d_j); cudaFree(d_at); cudaFree(d_ic); cudaFree(d_ex); cudaFree(d_par); cudaFree(d_pg); cudaFree(d_h);
-    if (rc != cudaSuccess) return e->fail("probe_gen_excit: %s", cudaGetErrorString(rc));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(ilut_j_out, d_j, (size_t)n * e->nw * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(ic_out, d_ic, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ex_out, d_ex, 4 * n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(parity_out, d_par, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pgen_out, d_pg, n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hel_out, d_h, n * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 
