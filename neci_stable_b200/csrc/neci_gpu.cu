@@ -15,9 +15,6 @@
 #include <unordered_set>
 #include <dlfcn.h>
 #include <nccl.h>
-#ifndef K1_GEN_WARP
-#define K1_GEN_WARP 0      /* 1: k_generate_w (warp-private tiles) instead of k_generate */
-#endif
 #include "kernels.cuh"
 
 using namespace ng;
@@ -270,16 +267,9 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
         int w = 0, g = 0, ev = 0, sg = 0;
         NG_DISPATCH(e, {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w, k_walk<NW, SYS>, NG_BLOCK, 0));
-#if K1_GEN_WARP
-            CK(cudaFuncSetAttribute(k_generate_w<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_w_smem_bytes<NW>()));
-#endif
             CK(cudaFuncSetAttribute(k_generate<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem_bytes<NW>()));
             CK(cudaFuncSetAttribute(k_generate_heavy<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K1_GEN_BLOCK / 32) * sizeof(GenStage<NW>))));
-#if K1_GEN_WARP
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g, k_generate_w<NW, SYS>, K1_GEN_BLOCK, gen_w_smem_bytes<NW>()));
-#else
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g, k_generate<NW, SYS>, K1_GEN_BLOCK, gen_smem_bytes<NW>()));
-#endif
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ev, k_evaluate<NW, SYS>, NG_BLOCK, 0));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sg, k_singles<NW, SYS>, NG_BLOCK, 0));
         });
@@ -1005,11 +995,7 @@ int neci_gpu_iterate(neci_gpu_engine *e, double tau, double diag_sft, int64_t it
                *p_eval = p_gen + (size_t)e->rows_gen * NECI_ST_COUNT, *p_sing = p_eval + (size_t)e->rows_eval * NECI_ST_COUNT,
                *p_heavy = p_sing + (size_t)e->rows_sing * NECI_ST_COUNT;
         NG_DISPATCH(e, (k_walk<NW, SYS><<<e->rows_walk, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->K, A, p_walk)));
-#if K1_GEN_WARP
-        NG_DISPATCH(e, (k_generate_w<NW, SYS><<<e->rows_gen, K1_GEN_BLOCK, gen_w_smem_bytes<NW>(), e->stream>>>(e->P, e->L, e->K, A, p_gen)));
-#else
         NG_DISPATCH(e, (k_generate<NW, SYS><<<e->rows_gen, K1_GEN_BLOCK, gen_smem_bytes<NW>(), e->stream>>>(e->P, e->L, e->K, A, p_gen)));
-#endif
         NG_DISPATCH(e, (k_generate_heavy<NW, SYS><<<e->rows_heavy, K1_GEN_BLOCK, (K1_GEN_BLOCK / 32) * sizeof(GenStage<NW>), e->stream>>>(e->P, e->L, e->SB, e->K, A, p_heavy)));
         NG_DISPATCH(e, (k_evaluate<NW, SYS><<<e->rows_eval, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->K, A, p_eval)));
         if (pchb) NG_DISPATCH(e, (k_singles<NW, SYS><<<e->rows_sing, NG_BLOCK, 0, e->stream>>>(e->P, e->L, e->SB, e->K, A, p_sing)));

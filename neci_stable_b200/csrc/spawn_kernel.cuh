@@ -847,124 +847,6 @@ template <int NW> __host__ __device__ constexpr size_t gen_smem_bytes() {
     return ((sizeof(GenShared<NW>) + 15) & ~(size_t)15) + (K1_GEN_BLOCK / 32) * sizeof(GenStage<NW>);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// k_generate_w: the same expansion with warp-private tiles (K1_GEN_WARP): a warp takes 64 parents (two per lane), takes the
-// prefix sum of their attempt counts with shuffles, fills a 256-attempt window of the attempt -> parent map in its own
-// shared memory and runs through it -- no block barrier after the set-up of the segment table.
-// ---------------------------------------------------------------------------------------------------------------
-#define K1_WTILE 64
-#define K1_WMAP 256
-template <int NW> struct GenWarpShared {
-    u64 d0[K1_WTILE];
-    u64 d1[(NW > 1) ? K1_WTILE : 1];
-    int off[K1_WTILE];
-    unsigned char info[K1_WTILE];
-    unsigned char map[K1_WMAP];
-};
-template <int NW> __host__ __device__ constexpr size_t gen_w_smem_bytes() {
-    return ((sizeof(int) * (NG_MAX_PAR_SEG + 1) + 15) & ~(size_t)15) + (K1_GEN_BLOCK / 32) * (((sizeof(GenWarpShared<NW>) + 15) & ~(size_t)15) + sizeof(GenStage<NW>));
-}
-template <int NW, int SYS>
-__global__ void __launch_bounds__(K1_GEN_BLOCK, (NW == 1 && SYS == NECI_SYS_FCIDUMP_PCHB) ? 5 : 4) k_generate_w(Params P, WalkerList L, K1Queues K, IterArgs A, double *partials) {
-    extern __shared__ __align__(16) unsigned char gen_smem[];
-    constexpr size_t SEG_BYTES = (sizeof(int) * (NG_MAX_PAR_SEG + 1) + 15) & ~(size_t)15;
-    constexpr size_t WS_BYTES = (sizeof(GenWarpShared<NW>) + 15) & ~(size_t)15;
-    int *seg_tile0 = reinterpret_cast<int *>(gen_smem);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    GenWarpShared<NW> &W = *reinterpret_cast<GenWarpShared<NW> *>(gen_smem + SEG_BYTES + warp * WS_BYTES);
-    GenStage<NW> &G = reinterpret_cast<GenStage<NW> *>(gen_smem + SEG_BYTES + (K1_GEN_BLOCK / 32) * WS_BYTES)[warp];
-    __shared__ double s_red[2 * 32];
-    int fill_e = 0, fill_s = 0;
-    AttAcc acc; acc.child = acc.child_sing = acc.maxsp = 0.0; acc.valid = acc.invalid = 0;
-    const int nseg = K.par_nseg;
-    for (int sg = tid; sg < nseg; sg += K1_GEN_BLOCK) seg_tile0[sg + 1] = ((int)K.par_cnt[sg] + K1_WTILE - 1) / K1_WTILE;
-    __syncthreads();
-    if (warp == 0) {                                             // inclusive prefix sum over the segments
-        const int per = (nseg + 31) / 32, s0 = min(nseg, lane * per), s1 = min(nseg, s0 + per);
-        int tot = 0;
-        for (int sg = s0; sg < s1; ++sg) tot += seg_tile0[sg + 1];
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        int run = incl - tot;
-        for (int sg = s0; sg < s1; ++sg) { run += seg_tile0[sg + 1]; seg_tile0[sg + 1] = run; }
-        if (lane == 0) seg_tile0[0] = 0;
-    }
-    __syncthreads();
-    const int n_tiles = seg_tile0[nseg];
-    const int gw = blockIdx.x * (K1_GEN_BLOCK / 32) + warp, nwarps = gridDim.x * (K1_GEN_BLOCK / 32);
-#pragma unroll 1
-    for (int tile = gw; tile < n_tiles; tile += nwarps) {
-        int lo_s = 0, hi_s = nseg;                               // last segment with seg_tile0[sg] <= tile
-        while (hi_s - lo_s > 1) { const int mid = (lo_s + hi_s) >> 1; if (seg_tile0[mid] <= tile) lo_s = mid; else hi_s = mid; }
-        const long long q0 = (long long)lo_s * K.par_seg_cap + (long long)(tile - seg_tile0[lo_s]) * K1_WTILE;
-        const long long q_end = (long long)lo_s * K.par_seg_cap + (long long)K.par_cnt[lo_s];
-        int nsp_k[2], off_k[2];
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-            const int idx = kk * 32 + lane;
-            const long long q = q0 + idx;
-            u64 w0 = 0, w1 = 0; u32 meta = 0;
-            if (q < q_end) { w0 = __ldcs(&K.par_d0[q]); if (NW > 1) w1 = __ldcs(&K.par_d1[q]); meta = __ldcs(&K.par_meta[q]); }
-            W.d0[idx] = w0; if (NW > 1) W.d1[idx] = w1;
-            W.info[idx] = (unsigned char)(meta & 0xffu);
-            nsp_k[kk] = (int)(meta >> 8);
-        }
-        int run = 0;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-            int incl = nsp_k[kk];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            off_k[kk] = run + incl - nsp_k[kk];
-            W.off[kk * 32 + lane] = off_k[kk];
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        const int T = run;
-#pragma unroll 1
-        for (int wb = 0; wb < T; wb += K1_WMAP) {
-            const int we = min(T, wb + K1_WMAP);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const int idx = kk * 32 + lane;
-                const int lo = max(off_k[kk], wb), hi = min(off_k[kk] + nsp_k[kk], we);
-                const bool big = hi - lo > 4;
-                if (!big) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (lo + u < hi) W.map[lo + u - wb] = (unsigned char)idx;
-                }
-                u32 m = __ballot_sync(0xffffffffu, big);         // long ranges are filled by the whole warp
-                while (m) {
-                    const int src = __ffs(m) - 1; m &= m - 1u;
-                    const int l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
-#pragma unroll 1
-                    for (int a = l2 + lane; a < h2; a += 32) W.map[a - wb] = (unsigned char)(kk * 32 + src);
-                }
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int base = wb; base < we; base += 32) {
-                const int a = base + lane;
-                const bool active = a < we;
-                Det<NW> dp; dp.w[0] = 0; if (NW > 1) dp.w[NW - 1] = 0;
-                u64 h = 0; int info = 0; u32 p = 0;
-                if (active) {
-                    const int lo = W.map[a - wb];
-                    dp.w[0] = W.d0[lo]; if (NW > 1) dp.w[NW - 1] = W.d1[lo];
-                    h = det_hash64(dp); info = W.info[lo]; p = (u32)(a - W.off[lo]);
-                }
-                generate_and_push<NW, SYS>(P, L, K, A, G, fill_e, fill_s, active, dp, h, info, p, acc);
-            }
-            __syncwarp();                                        // the next window / tile overwrites map and parents
-        }
-    }
-    warp_stage_flush<qe_rec<NW>(), NG_QE_STAGE_CAP>(G.e, fill_e, &K.cnt[Q_NQE], K.qe_cap, K.qe, L, 128ull);
-    if (sys_pchb(SYS)) warp_stage_flush<qs_rec<NW>(), NG_QS_STAGE_CAP>(G.s, fill_s, &K.cnt[Q_NQS], K.qs_cap, K.qs, L, 128ull);
-    const double a2[2] = {(double)acc.valid, (double)acc.invalid};
-    const int idx[2] = {NECI_ST_NVALIDEXCITS, NECI_ST_NINVALIDEXCITS};
-    block_flush_stats<2>(a2, idx, partials, s_red);
-}
-
 // Attempts of the deferred heavy determinants (> NG_HEAVY walkers), spread over the whole grid.
 template <int NW, int SYS>
 __global__ void __launch_bounds__(K1_GEN_BLOCK) k_generate_heavy(Params P, WalkerList L, SpawnBuf SB, K1Queues K, IterArgs A, double *partials) {
