@@ -25,9 +25,10 @@
 //   k_singles   one thread per QS entry: uniform single + sltcnd_1 (loads batched 4 at a time), then as k_evaluate
 //
 // Every stage runs with all lanes busy (the queues are compacted), no stage waits for another inside a kernel, and
-// each kernel gets the register allocation and occupancy that suit it.  On several ranks the appends go to a staging
-// list and k_partition_push routes them afterwards (kernels.cuh).  HPHF runs are their own compile-time variant
-// (NG_SYS_PCHB_HPHF).
+// each kernel gets the register allocation and occupancy that suit it.  On several ranks every flush of a warp's
+// spawn stage routes its records (DetermineDetNode) and stores them into the owners' inboxes over NVLink
+// (spawn_stage_push); with the NCCL exchange they go to a staging list that k_partition routes (kernels.cuh).  HPHF
+// runs are their own compile-time variant (NG_SYS_PCHB_HPHF).
 //
 // Random numbers are counter-based (device_common.cuh: Stream), so the result does not depend on the order in which
 // queue entries are written or served.
@@ -239,10 +240,9 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage<REC, CAP> &B, int &fi
     __syncwarp();
 }
 
-// The attempt kernels' own append (all lanes of the warp must call).  On one rank this is create_particle itself:
-// the record goes to SpawnedParts.  On several ranks the spawn goes to a staging list first and k_partition_push
-// routes it afterwards: DetermineDetNode costs ~230 instructions, and the partition kernel hashes with every lane busy
-// and the record already on its way over NVLink.  Records are staged per warp and written 32 or more at a time.
+// The attempt kernels' own append (all lanes of the warp must call).  Records are staged per warp in shared memory and
+// leave ~128 at a time: on one rank to SpawnedParts (create_particle itself, one global atomic per flush), on several
+// ranks through spawn_stage_push below (peer-memory exchange) or to the staging list of the NCCL exchange.
 #define NG_SPAWN_STAGE_CAP 160     /* one-word determinants: flushed at >= 128; two words: 128 records, flushed at >= 96 (48 KB of static shared memory) */
 template <int NW> __host__ __device__ constexpr int spawn_stage_cap() { return NW == 1 ? NG_SPAWN_STAGE_CAP : 128; }
 #define NG_MAX_PUSH_RANKS 64
