@@ -706,7 +706,12 @@ __global__ void k_core_gather(WalkerList L, const int *core_slots, long long n, 
 //     memory, one partial sum per chunk;
 //   * k_determ_finish adds the partial sums of a row in block order (fixed order: bit-reproducible), the shift or
 //     diagonal term, and multiplies by tau.
+#ifndef NG_SPMV_CB_MAX
 #define NG_SPMV_CB_MAX 27648          /* columns per block: 216 KB of fp64 in shared memory */
+#endif
+#ifndef NG_SPMV_CTAS
+#define NG_SPMV_CTAS 1                /* resident CTAs per SM (2 needs NG_SPMV_CB_MAX <= 13824) */
+#endif
 #define NG_SPMV_THREADS 1024
 #define NG_SPMV_NB_MAX 256            /* column blocks (set-up histogram); 7e6 core determinants */
 // set-up, pass 1: elements of every (block, row) chunk.  One warp per row; cnt is block-major [c * n_local + i].
@@ -757,6 +762,48 @@ __global__ void __launch_bounds__(256) k_spmv_block_fill(const long long *__rest
         __syncwarp();
     }
 }
+// set-up, pass 3: bank-aware order inside every chunk.  The kernel's gathers read 8 bytes per lane from the vector slice
+// in shared memory; the 16 lanes of a half-warp conflict when their columns agree modulo 16 (same pair of banks), and
+// random columns do so 4-way on average.  Within a chunk the order of the elements is free (only the order of the
+// additions changes, deterministically), so they are dealt out round-robin over the 16 residues: the j-th element of
+// every residue class forms one group of 16 consecutive elements -- conflict-free as long as all classes still have
+// elements -- and a half-warp of a trip reads exactly one such group (trips start at multiples of 16 from the chunk's
+// start).  One warp per chunk; sizes of the residue classes first, then positions.
+__global__ void __launch_bounds__(256) k_spmv_bank_order(const long long *__restrict__ bptr, long long nchunk, const double *__restrict__ bval,
+                                                         const unsigned short *__restrict__ bcol, double *__restrict__ oval,
+                                                         unsigned short *__restrict__ ocol) {
+    __shared__ int s_cnt[8][16], s_run[8][16];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long c = warp; c < nchunk; c += nwarps) {
+        const long long s = bptr[c], e = bptr[c + 1];
+        if (lane < 16) { s_cnt[wib][lane] = 0; s_run[wib][lane] = 0; }
+        __syncwarp();
+        for (long long k = s + lane; k < e; k += 32) atomicAdd(&s_cnt[wib][bcol[k] & 15], 1);
+        __syncwarp();
+        int cnt[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) cnt[r] = s_cnt[wib][r];
+        for (long long k0 = s; k0 < e; k0 += 32) {
+            const long long k = k0 + lane;
+            const bool has = k < e;
+            const unsigned short cj = has ? bcol[k] : 0;
+            const int r = has ? (int)(cj & 15) : -1;
+            const u32 peers = __match_any_sync(0xffffffffu, r);
+            if (has) {
+                const int j = s_run[wib][r] + __popc(peers & lt);     // rank inside the residue class, in chunk order
+                int pos = 0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pos += min(cnt[q], j) + ((q < r && cnt[q] > j) ? 1 : 0);
+                oval[s + pos] = bval[k]; ocol[s + pos] = cj;
+            }
+            __syncwarp();
+            if (has && lane == __ffs(peers) - 1) s_run[wib][r] += __popc(peers);
+            __syncwarp();
+        }
+    }
+}
 // One trip of a warp = 256 consecutive elements, 8 per lane (lane, lane + 32, ...): sixteen coalesced streaming loads.
 // They are volatile asm so that ptxas keeps them together in program order; trips go in pairs, the loads of the next
 // one issued before the current one is consumed.  (Tried and measured slower on the same matrix, 0.50 ms for this
@@ -795,7 +842,7 @@ __device__ __forceinline__ double spmv_tail(const double *__restrict__ bval, con
     for (int u = 0; u < 8; ++u) t += a[u] * vs[c[u]];
     return t;
 }
-__global__ void __launch_bounds__(NG_SPMV_THREADS, 1) k_determ_spmv_blocked(const long long *__restrict__ bptr, const unsigned short *__restrict__ bcol,
+__global__ void __launch_bounds__(NG_SPMV_THREADS, NG_SPMV_CTAS) k_determ_spmv_blocked(const long long *__restrict__ bptr, const unsigned short *__restrict__ bcol,
                                                                          const double *__restrict__ bval, const double *__restrict__ v_full,
                                                                          const long long *__restrict__ work, long long n_local,
                                                                          long long n_core, int cb, double *__restrict__ partial) {

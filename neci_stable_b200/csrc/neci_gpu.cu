@@ -259,7 +259,7 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     const int nsm = prop.multiProcessorCount;
     e->grid_generic = nsm * 8;
-    e->grid_spmv = nsm;                       // one persistent CTA per SM (k_determ_spmv_blocked)
+    e->grid_spmv = nsm * NG_SPMV_CTAS;        // persistent CTAs of k_determ_spmv_blocked: one per SM (200 KB of shared memory each)
     e->rows_compress = e->grid_generic; e->rows_annih = e->grid_generic;
     e->rows_insert = e->grid_generic; e->rows_list = e->grid_generic;
     // the K1 kernels run as persistent grids: one CTA per resident slot of every SM
@@ -638,8 +638,19 @@ static int core_space_blocked(neci_gpu_engine *e, long long nnz) {
     CK(cudaMemcpyAsync(e->d_bptr, bp.data(), (nchunk + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     e->d_bval = e->alloc<double>((size_t)run + 4); e->d_bcol = e->alloc<unsigned short>((size_t)run + 4);
     if (!e->d_bval || !e->d_bcol) return e->fail("no memory for the column-blocked core Hamiltonian (%lld elements)", run);
-    k_spmv_block_fill<<<grid, 256, 0, e->stream>>>(e->d_row_ptr, e->d_col, e->d_val, n_local, cb, nb, e->d_bptr, e->d_bval, e->d_bcol);
-    CK(cudaGetLastError());
+    {
+        // chunk order first (stable scatter of the rows), then the bank-aware order inside every chunk
+        Scratch sc;
+        double *t_val = sc.get<double>((size_t)run + 4); unsigned short *t_col = sc.get<unsigned short>((size_t)run + 4);
+        if (!sc.ok) return e->fail("no memory for the column-blocked core Hamiltonian (%lld elements, set-up copy)", run);
+        k_spmv_block_fill<<<grid, 256, 0, e->stream>>>(e->d_row_ptr, e->d_col, e->d_val, n_local, cb, nb, e->d_bptr, t_val, t_col);
+        CK(cudaGetLastError());
+        const int grid2 = (int)std::max<long long>(1, std::min<long long>(e->grid_generic, ((long long)nchunk + 7) / 8));
+        k_spmv_bank_order<<<grid2, 256, 0, e->stream>>>(e->d_bptr, (long long)nchunk, t_val, t_col, e->d_bval, e->d_bcol);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+        e->n_launch += 1;
+    }
     // CTA p takes the chunks whose first element lies in [nnz p / G, nnz (p + 1) / G): equal shares of the bytes
     const int G = e->grid_spmv;
     std::vector<long long> work((size_t)G + 1);
