@@ -290,7 +290,10 @@ int neci_gpu_nccl_init(neci_gpu_engine *e, const uint8_t id[128]);
  * counts): every rank creates its inbox and returns a 64-byte CUDA IPC handle; the host all-gathers the handles
  * (MPIAllGather / torch.distributed) and every rank opens its peers' inboxes.  One process per GPU, all on one
  * NVLink/NVSwitch box.  When this has been called neci_gpu_iterate / neci_gpu_rebalance use it for
- * SendProcNewParts (src/Annihilation.F90:150-247); otherwise they use the NCCL communicator.                  */
+ * SendProcNewParts (src/Annihilation.F90:150-247); otherwise they use the NCCL communicator.  In neci_gpu_iterate the
+ * spawning kernels then route their spawns themselves (DetermineDetNode) and store them into the owners' inboxes
+ * while they run; the exchange proper is a mailbox hand-shake.  A semi-stochastic run on several ranks needs
+ * neci_gpu_nccl_init as well (the core vector is gathered with NCCL); nranks <= 64.                             */
 int neci_gpu_p2p_handle(neci_gpu_engine *e, uint8_t handle_out[64]);
 int neci_gpu_p2p_open(neci_gpu_engine *e, const uint8_t *handles /* nranks x 64 bytes, rank order */);
 
