@@ -46,11 +46,11 @@ WORKLOADS = {
 SEMISTOCH = ("semistoch_20e40o_pchb",)
 
 
-def build_system(workload):
+def build_system(workload, particle_selection="UNIF-UNIF"):
     from neci_stable_b200 import host
     if workload in WORKLOADS:
         n_spat, nel, tau, _ = WORKLOADS[workload]
-        return host.random_fcidump_system(n_spat, nel, sparse=1.0, sparse_t=1.0, seed=25), tau
+        return host.random_fcidump_system(n_spat, nel, sparse=1.0, sparse_t=1.0, seed=25, particle_selection=particle_selection), tau
     if workload == "hubk_6x6":
         return host.hubbard_k_system(6, 6, U=4.0), 5.0e-4
     if workload == "hubrs_4x4":
@@ -376,6 +376,9 @@ def main():
     ap.add_argument("--core-build", default="host", choices=["host", "device"],
                     help="semi-stochastic workloads: who builds the sparse core Hamiltonian")
     ap.add_argument("--trial", type=int, default=10, help="semi-stochastic workloads: determinants in the trial space (0 = none)")
+    ap.add_argument("--particle-selection", default="UNIF-UNIF", choices=["UNIF-UNIF", "FULL-FULL"],
+                    help="PCHB workloads: PCHB_ParticleSelection of the doubles generator (BASELINE configs quote UNIF-UNIF; "
+                         "FULL-FULL is what the reference's own PCHB regression input selects)")
     ap.add_argument("--list", default="auto", choices=["auto", "host", "device"],
                     help="where the frozen start list is generated: numpy on the host (uploaded), or on the device "
                          "(neci_gpu_synthetic_list); auto = device on several GPUs and from 5e7 walkers per GPU")
@@ -483,7 +486,7 @@ def run_workload(args, ctx, primary=True):
     from neci_stable_b200 import capi, host, driver
     from neci_stable_b200.capi import ST
 
-    system, tau = build_system(args.workload)
+    system, tau = build_system(args.workload, args.particle_selection)
     hii = driver.diag_energy(system, system.ref_orbs)
     if args.scaling == "strong":
         args.walkers = args.walkers / world                # total fixed: each GPU holds its 1/N share
@@ -808,6 +811,7 @@ def run_workload(args, ctx, primary=True):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "walkers_per_gpu": args.walkers,
                        "start_list": "device (neci_gpu_synthetic_list)" if device_list else "host (numpy, uploaded)",
+                       **({"particle_selection": args.particle_selection} if args.particle_selection != "UNIF-UNIF" else {}),
                        "walkers_total_end": walkers_end, "determinants_total_end": dets_end, "tau": tau, "shift": sft,
                        "initiator": True, "attempts_per_step": attempts / args.steps,
                        "spawned_per_step": spawned / args.steps, "partition": "DetermineDetNode hash" if world > 1 else "single rank",

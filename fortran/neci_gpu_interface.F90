@@ -170,6 +170,14 @@ module neci_gpu_interface
             integer(c_int32_t), intent(in) :: class_of_spinorb(*)
             integer(c_int) :: err
         end function
+        function neci_gpu_set_pchb_particles(handle, mode, p_first, p_second) result(err) bind(c, name='neci_gpu_set_pchb_particles')
+            import :: c_int, c_ptr, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: mode
+            real(c_double), intent(in) :: p_first(*)
+            real(c_double), intent(in) :: p_second(*)
+            integer(c_int) :: err
+        end function
         function neci_gpu_set_excit_probs(handle, p_singles, p_doubles, p_parallel) result(err) bind(c, name='neci_gpu_set_excit_probs')
             import :: c_int, c_ptr, c_double
             type(c_ptr), value :: handle

@@ -187,6 +187,15 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
                       const double *p_exch, const int32_t *tgt_orbs,
                       double p_singles, double p_doubles, double p_parallel,
                       int32_t n_classes, const int32_t *class_of_spinorb);
+/* PCHB particle selection (PCHB_ParticleSelection_t, src/gasci_pchb_doubles_select_particles.fpp:38-46): mode 0 =
+ * UNIF-UNIF (pick_biased_elecs, the default after neci_gpu_set_pchb; the tables are ignored), mode 1 = FULL-FULL
+ * (PC_FullyWeightedParticles_t, :330-438): the first particle I is drawn with p_first[I] and the second with
+ * p_second[I][J] = p(J | I), both restricted to the occupied orbitals and renormalised (constrained sampling), and
+ * p({I, J}) sums both orders.  p_first[nBasis] and p_second[nBasis * nBasis] (row I) are the normalised probabilities
+ * of the selector's I_sampler / J_sampler (AliasSampler_t::get_prob), spin orbitals in NECI order.  Call after
+ * neci_gpu_set_pchb; not available together with t_hphf.                                                        */
+int neci_gpu_set_pchb_particles(neci_gpu_engine *e, int32_t mode, const double *p_first, const double *p_second);
+
 /* New excitation-class biases from the tau search (update_tau, src/tau/tau_search_conventional.F90:274-499 assigns
  * pSingles / pDoubles / pParallel); takes effect from the next iteration.  FCIDUMP/PCHB systems.               */
 int neci_gpu_set_excit_probs(neci_gpu_engine *e, double p_singles, double p_doubles, double p_parallel);

@@ -153,6 +153,11 @@ class Engine:
             C.c_double(t["p_singles"]), C.c_double(t["p_doubles"]), C.c_double(t["p_parallel"]),
             C.c_int32(t["n_classes"]), _p(a["cls"], C.c_int32)), "set_pchb")
 
+    def set_pchb_particles(self, mode, p_first, p_second):
+        """PCHB particle selection: 0 UNIF-UNIF (default), 1 FULL-FULL with the probability tables of the particle selector."""
+        a, b = _f64(p_first), _f64(p_second)
+        self._check(self._fn("set_pchb_particles")(self.h, C.c_int32(mode), _p(a, C.c_double), _p(b, C.c_double)), "set_pchb_particles")
+
     def set_excit_probs(self, p_singles, p_doubles, p_parallel):
         self._check(self._fn("set_excit_probs")(self.h, C.c_double(p_singles), C.c_double(p_doubles), C.c_double(p_parallel)),
                     "set_excit_probs")

@@ -20,7 +20,10 @@ typedef unsigned int u32;
 // is a compile-time variant because its code inside the spawning kernel costs the determinant runs 20 % when it is
 // merely present behind a run-time flag (registers and instruction cache).
 #define NG_SYS_PCHB_HPHF 4
-__host__ __device__ constexpr bool sys_pchb(int s) { return s == NECI_SYS_FCIDUMP_PCHB || s == NG_SYS_PCHB_HPHF; }
+// the FCIDUMP/PCHB system with PCHB_ParticleSelection FULL-FULL (neci_gpu_set_pchb_particles): its own variant for the
+// same reason
+#define NG_SYS_PCHB_FULL 5
+__host__ __device__ constexpr bool sys_pchb(int s) { return s == NECI_SYS_FCIDUMP_PCHB || s == NG_SYS_PCHB_HPHF || s == NG_SYS_PCHB_FULL; }
 __host__ __device__ constexpr bool sys_hphf(int s) { return s == NG_SYS_PCHB_HPHF; }
 #define NG_MAX_CLASSES 16
 
@@ -229,6 +232,7 @@ struct Params {
     int n_spat, ij_max, ab_max;
     const struct PchbEntry *pchb;     // [ij_max * 3 * ab_max]
     const struct PchbPair *pchb_pair; // [ij_max]
+    const double *pchb_pfirst, *pchb_psecond;       // FULL-FULL particle selection: p_first[nbasis], p_second[nbasis][nbasis]
     double p_singles, p_doubles, p_parallel;
     double pgen_pair_par, pgen_pair_opp;            // p_parallel / #parallel pairs, (1 - p_parallel) / #alpha-beta pairs
     // host-computed rescaling constants of the first draw of an attempt (see gen_pchb_double): 1 / (1 - p_singles),

@@ -452,6 +452,8 @@ __device__ void gen_uniform_single(const Params &P, const Det<NW> &d, Stream &rn
 // (position and bias from one number, as AliasSampler_t does it).  Every choice keeps the reference's probabilities
 // (resolution 2^-53 / 2^-45 / 2^-53), pgen is unchanged.  The CPU checker of the test suite draws the same way.
 template <int NW>
+__device__ __forceinline__ void pchb_pick_holes(const Params &P, const Det<NW> &d, int s1, int s2, double pGen, double u2, Stream &rng, Excit<NW> &E);
+template <int NW>
 __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, double r, Stream &rng, Excit<NW> &E) {
     E.ic = 2; E.valid = false; E.err = 0;
     const int nA = P.nocc_alpha, nB = P.nocc_beta;
@@ -475,7 +477,12 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, double r, Str
     }
     // the two orbital selections are common to both branches (kept out of the divergent part)
     const int oa = select_orb(d, m1, k1), ob = select_orb(d, m2, k2);
-    const int s1 = min(oa, ob), s2 = max(oa, ob);
+    pchb_pick_holes(P, d, min(oa, ob), max(oa, ob), pGen, u2, rng, E);
+}
+// the part of GAS_doubles_PCHB_gen_exc after the particles are chosen (:204-262): sampler by spin and exchange, alias
+// sample of the hole pair, validity.  u2: the uniform number of the exchange decision.
+template <int NW>
+__device__ __forceinline__ void pchb_pick_holes(const Params &P, const Det<NW> &d, int s1, int s2, double pGen, double u2, Stream &rng, Excit<NW> &E) {
     const int ij = (int)tri((u32)gtid(s1), (u32)gtid(s2));      // fuse_index
     int spin1 = s1 & 1, spin2 = s2 & 1;           // getSpinIndex: 0 alpha, 1 beta
     const int4 pi = __ldg(reinterpret_cast<const int4 *>(P.pchb_pair + (ij - 1)));    // {p_exch, nonempty, pad}
@@ -510,6 +517,58 @@ __device__ void gen_pchb_double(const Params &P, const Det<NW> &d, double r, Str
     E.valid = true;
 }
 
+// CDF_Sampler_t over the occupied orbitals with the weights row[orbital - 1] (src/CDF_sampling.fpp:57-118, as
+// constrained_sample uses it, src/aliasSampling.F90:519-525): the first occupied orbital, in ascending order, whose
+// running sum of weights reaches r * total; the last one with a non-zero weight if rounding leaves the sum below.
+template <int NW>
+__device__ __forceinline__ int cdf_pick_occupied(const Det<NW> &d, const double *row, double total, double r, double &renorm_out) {
+    const double thr = r * total;
+    double cum = 0.0;
+    int chosen = 0, last = 0;
+    Det<NW> a = d;
+    while (det_any(a)) {
+        const int o = pop_lowest(a);
+        const double w = __ldg(&row[o - 1]);
+        cum += w;
+        if (w > 0.0) { last = o; if (chosen == 0 && cum >= thr) chosen = o; }
+    }
+    renorm_out = cum;
+    return chosen ? chosen : last;
+}
+template <int NW>
+__device__ __forceinline__ double sum_occupied(const Det<NW> &d, const double *row) {
+    double s = 0.0;
+    Det<NW> a = d;
+    while (det_any(a)) s += __ldg(&row[pop_lowest(a) - 1]);
+    return s;
+}
+// GAS_doubles_PCHB_gen_exc with PC_FullyWeightedParticles_t (src/gasci_pchb_doubles_select_particles.fpp:330-384):
+// first particle with p_first restricted to the occupied orbitals, second with p(J | I) likewise, p({I, J}) summed over
+// both orders.  Random numbers: r (from the attempt's first number) picks the first particle, the next 53-bit number
+// the second; the exchange decision takes a 32-bit number and the alias sample a 53-bit number of the second block.
+template <int NW>
+__device__ void gen_pchb_double_full(const Params &P, const Det<NW> &d, double r, Stream &rng, Excit<NW> &E) {
+    E.ic = 2; E.valid = false; E.err = 0; E.src1 = E.src2 = E.tgt1 = E.tgt2 = 0; E.pgen = 1.0;
+    const int nb = P.nbasis;
+    const double renorm_first = sum_occupied(d, P.pchb_pfirst);
+    const double r2 = rng.draw53();
+    if (fabs(renorm_first) <= NG_EPS) return;
+    double dummy;
+    const int s1 = cdf_pick_occupied(d, P.pchb_pfirst, renorm_first, r, dummy);
+    const double *row1 = P.pchb_psecond + (size_t)(s1 - 1) * nb;
+    const double renorm_second1 = sum_occupied(d, row1);
+    if (fabs(renorm_second1) <= NG_EPS) return;
+    const int s2 = cdf_pick_occupied(d, row1, renorm_second1, r2, dummy);
+    const double p_first1 = __ldg(&P.pchb_pfirst[s1 - 1]) / renorm_first, p_second1 = __ldg(&row1[s2 - 1]) / renorm_second1;
+    const double p_first2 = __ldg(&P.pchb_pfirst[s2 - 1]) / renorm_first;
+    const double *row2 = P.pchb_psecond + (size_t)(s2 - 1) * nb;
+    const double renorm_second2 = sum_occupied(d, row2);
+    const double p_second2 = (fabs(renorm_second2) <= NG_EPS) ? 0.0 : __ldg(&row2[s1 - 1]) / renorm_second2;
+    const double pGen = p_first1 * p_second1 + p_first2 * p_second2;
+    const double u2 = rng.draw32();
+    pchb_pick_holes(P, d, min(s1, s2), max(s1, s2), pGen, u2, rng, E);
+}
+
 // make_single / make_double results derived from the bit-strings: parity and the excited determinant
 template <int NW>
 __device__ __forceinline__ void finalize_excit(const Det<NW> &d, Excit<NW> &E) {
@@ -532,7 +591,11 @@ __device__ __forceinline__ void generate_excitation_core(const Params &P, const 
         // gen_exc_sd: the first number of the attempt's block; singles continue in the second block (word 4)
         const double u = rng.draw53();
         if (u < P.p_singles) { rng.pos = 4; gen_uniform_single(P, d, rng, E); E.pgen = E.pgen * P.p_singles; }
-        else { gen_pchb_double(P, d, (u - P.p_singles) * P.inv_1m_ps, rng, E); E.pgen = E.pgen * P.p_doubles; }
+        else {
+            if (SYS == NG_SYS_PCHB_FULL) gen_pchb_double_full(P, d, (u - P.p_singles) * P.inv_1m_ps, rng, E);
+            else gen_pchb_double(P, d, (u - P.p_singles) * P.inv_1m_ps, rng, E);
+            E.pgen = E.pgen * P.p_doubles;
+        }
     }
 }
 template <int NW, int SYS>

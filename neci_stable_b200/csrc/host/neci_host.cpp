@@ -206,6 +206,74 @@ int neci_host_pchb_build(int32_t n_spat, const double *umat, double *probs, doub
     return 0;
 }
 
+// Particle-selection tables of PCHB_ParticleSelection FULL-FULL (PC_FullyWeightedParticles_t,
+// src/gasci_pchb_doubles_select_particles.fpp:268-328): IJ_weights(I, J) = sum over the hole pairs of the weights
+// of the samplers of the spin-orbital pair (I, J), accumulated as GAS_doubles_PCHB_compute_samplers does it
+// (src/gasci_pchb_doubles_spatorb_fastweighted.fpp:374-420), then normalised the way AliasSampler_t::setup_entry
+// normalises (probs = w / sum(w)): p_first[I] from sum_J IJ_weights(J, I), p_second[I][J] = p(J | I) from column I.
+// Only the probabilities are needed: the engine draws from them restricted to the occupied orbitals (constrained
+// sampling).  Spin orbitals 1-based as in NECI (2 * spatial = alpha, 2 * spatial - 1 = beta), arrays 0-based.
+int neci_host_pchb_particle_probs(int32_t n_spat, const double *umat, double *p_first, double *p_second) {
+    const int nBI = n_spat, nb = 2 * n_spat;
+    const int abMax = (int)fuse(nBI, nBI);
+    std::vector<double> IJ((size_t)nb * nb, 0.0), w(abMax);
+    auto at = [&](int I, int J) -> double & { return IJ[(size_t)(I - 1) * nb + (J - 1)]; };
+    auto Ms = [](int o) { return is_beta(o) ? -1 : 1; };
+    auto umat_el = [&](int i, int j, int k, int l) { return umat[umat_ind(i, j, k, l) - 1]; };
+    auto weight = [&](const int ex[4]) {
+        double hel = 0.0;
+        if (Ms(ex[0]) == Ms(ex[2]) && Ms(ex[1]) == Ms(ex[3])) hel = umat_el(gtid(ex[0]), gtid(ex[1]), gtid(ex[2]), gtid(ex[3]));
+        if (Ms(ex[0]) == Ms(ex[3]) && Ms(ex[1]) == Ms(ex[2])) hel -= umat_el(gtid(ex[0]), gtid(ex[1]), gtid(ex[3]), gtid(ex[2]));
+        return std::fabs(hel);
+    };
+    auto to_spin_orb = [](int orb, bool alpha) { return alpha ? 2 * orb : 2 * orb - 1; };
+    enum { SAME_SPIN = 1, OPP_SPIN_NO_EXCH = 2, OPP_SPIN_EXCH = 3 };
+    for (int i_exch = 1; i_exch <= 3; ++i_exch)
+        for (int i = 1; i <= nBI; ++i) {
+            int ex[4];
+            ex[0] = to_spin_orb(i, true);
+            for (int j = i; j <= nBI; ++j) {
+                if (i_exch == SAME_SPIN && i == j) continue;
+                std::fill(w.begin(), w.end(), 0.0);
+                ex[1] = to_spin_orb(j, i_exch == SAME_SPIN);
+                for (int a = 1; a <= nBI; ++a) {
+                    ex[2] = to_spin_orb(a, i_exch == SAME_SPIN || i_exch == OPP_SPIN_NO_EXCH);
+                    if (ex[2] == ex[0] || ex[2] == ex[1]) continue;
+                    for (int b = a; b <= nBI; ++b) {
+                        if (i_exch == OPP_SPIN_EXCH && a == b) continue;
+                        ex[3] = to_spin_orb(b, i_exch == SAME_SPIN || i_exch == OPP_SPIN_EXCH);
+                        if (ex[3] == ex[0] || ex[3] == ex[1] || ex[3] == ex[2]) continue;
+                        int c[4] = {std::min(ex[0], ex[1]), std::max(ex[0], ex[1]), std::min(ex[2], ex[3]), std::max(ex[2], ex[3])};
+                        w[fuse(a, b) - 1] = weight(c);
+                    }
+                }
+                double sw = 0.0; for (double x : w) sw += x;
+                {
+                    const int I = ex[0], J = ex[1];
+                    at(I, J) = at(I, J) + sw; at(J, I) = at(I, J);
+                }
+                if (i != j) {                                   // the same pair of spatial orbitals with the spins flipped
+                    const int I = ex[0] - 1, J = (i_exch == SAME_SPIN) ? ex[1] - 1 : ex[1] + 1;
+                    at(I, J) = at(I, J) + sw; at(J, I) = at(I, J);
+                }
+            }
+        }
+    // I_sampler: weights sum(IJ_weights(:, :), dim = 1), i.e. the column sums; J_sampler entry I: IJ_weights(:, I)
+    std::vector<double> col(nb, 0.0);
+    double tot = 0.0;
+    for (int I = 1; I <= nb; ++I) {
+        double c = 0.0;
+        for (int J = 1; J <= nb; ++J) c += at(J, I);
+        col[I - 1] = c; tot += c;
+    }
+    for (int I = 1; I <= nb; ++I) {
+        p_first[I - 1] = (std::fabs(tot) <= 1e-13) ? 0.0 : col[I - 1] / tot;
+        for (int J = 1; J <= nb; ++J)
+            p_second[(size_t)(I - 1) * nb + (J - 1)] = (std::fabs(col[I - 1]) <= 1e-13) ? 0.0 : at(J, I) / col[I - 1];
+    }
+    return 0;
+}
+
 // ----------------------------------------------------------------------------
 // Lattices.  Site s = x + lx*y (0-based) is spatial orbital s+1; spin orbitals
 // 2(s+1)-1 (beta) and 2(s+1) (alpha).

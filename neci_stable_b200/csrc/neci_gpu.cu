@@ -85,6 +85,7 @@ struct neci_gpu_engine {
     int grid_spawn = 0, grid_generic = 0, grid_spmv = 0;
     u32 stamp = 0;
     bool need_rebuild = false;
+    bool pchb_full = false;            // PCHB particle selection FULL-FULL (neci_gpu_set_pchb_particles)
     long long n_launch = 0;            // kernels launched by this engine since init
     long long n_resident = 0;          // length of the list in HBM (slots holding valid determinant data)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
@@ -132,16 +133,19 @@ struct neci_gpu_engine {
 // dispatch on (words per determinant, system type)
 #define NG_DISPATCH(e, BODY)                                                                              \
     do {                                                                                                  \
-        const int _key = (e)->nw * 10 + (((e)->cfg.t_hphf && (e)->cfg.system_type == NECI_SYS_FCIDUMP_PCHB) ? NG_SYS_PCHB_HPHF : (e)->cfg.system_type); \
+        const int _key = (e)->nw * 10 + (((e)->cfg.system_type != NECI_SYS_FCIDUMP_PCHB) ? (e)->cfg.system_type :               \
+                                         (e)->cfg.t_hphf ? NG_SYS_PCHB_HPHF : (e)->pchb_full ? NG_SYS_PCHB_FULL : NECI_SYS_FCIDUMP_PCHB); \
         switch (_key) {                                                                                   \
             case 11: { constexpr int NW = 1, SYS = NECI_SYS_FCIDUMP_PCHB; BODY; } break;                  \
             case 12: { constexpr int NW = 1, SYS = NECI_SYS_HUBBARD_RS; BODY; } break;                    \
             case 13: { constexpr int NW = 1, SYS = NECI_SYS_HUBBARD_K; BODY; } break;                     \
             case 14: { constexpr int NW = 1, SYS = NG_SYS_PCHB_HPHF; BODY; } break;                       \
+            case 15: { constexpr int NW = 1, SYS = NG_SYS_PCHB_FULL; BODY; } break;                       \
             case 21: { constexpr int NW = 2, SYS = NECI_SYS_FCIDUMP_PCHB; BODY; } break;                  \
             case 22: { constexpr int NW = 2, SYS = NECI_SYS_HUBBARD_RS; BODY; } break;                    \
             case 23: { constexpr int NW = 2, SYS = NECI_SYS_HUBBARD_K; BODY; } break;                     \
             case 24: { constexpr int NW = 2, SYS = NG_SYS_PCHB_HPHF; BODY; } break;                       \
+            case 25: { constexpr int NW = 2, SYS = NG_SYS_PCHB_FULL; BODY; } break;                       \
             default: return (e)->fail("unsupported (nifd, system_type) = (%d, %d)", (e)->nw - 1, (e)->cfg.system_type); \
         }                                                                                                 \
     } while (0)
@@ -415,6 +419,36 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
     P.class_start = e->upload(start.data(), start.size());
     P.class_orbs = e->upload(orbs.data(), orbs.size());
     if (!P.pchb || !P.pchb_pair) return e->fail("PCHB table upload failed");
+    return 0;
+}
+
+int neci_gpu_set_pchb_particles(neci_gpu_engine *e, int32_t mode, const double *p_first, const double *p_second) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->cfg.system_type != NECI_SYS_FCIDUMP_PCHB || !e->P.pchb) return e->fail("set_pchb_particles: call neci_gpu_set_pchb first (FCIDUMP/PCHB systems)");
+    if (mode == 0) { e->pchb_full = false; return 0; }
+    if (mode != 1) return e->fail("set_pchb_particles: mode %d is not implemented (0 UNIF-UNIF, 1 FULL-FULL)", mode);
+    if (e->cfg.t_hphf) return e->fail("set_pchb_particles: FULL-FULL particle selection is not available with t_hphf");
+    if (!p_first || !p_second) return e->fail("set_pchb_particles: FULL-FULL needs both probability tables");
+    const size_t nb = (size_t)e->cfg.nbasis;
+    e->P.pchb_pfirst = e->upload(p_first, nb);
+    e->P.pchb_psecond = e->upload(p_second, nb * nb);
+    if (!e->P.pchb_pfirst || !e->P.pchb_psecond) return e->fail("set_pchb_particles: table upload failed");
+    e->pchb_full = true;
+    // the launch shapes of the K1 kernels were taken for the UNIF-UNIF variant: this variant has its own
+    int g = 0, ev = 0, sg = 0;
+    NG_DISPATCH(e, {
+        CK(cudaFuncSetAttribute(k_generate<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem_bytes<NW>()));
+        CK(cudaFuncSetAttribute(k_generate_heavy<NW, SYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K1_GEN_BLOCK / 32) * sizeof(GenStage<NW>))));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g, k_generate<NW, SYS>, K1_GEN_BLOCK, gen_smem_bytes<NW>()));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ev, k_evaluate<NW, SYS>, NG_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sg, k_singles<NW, SYS>, NG_BLOCK, 0));
+    });
+    // grids may only shrink: the rows of the statistics partials were laid out for the original shapes
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, e->cfg.device));
+    const int nsm = prop.multiProcessorCount;
+    e->rows_gen = std::min(e->rows_gen, nsm * std::max(1, g)); e->rows_heavy = std::min(e->rows_heavy, e->rows_gen);
+    e->rows_eval = std::min(e->rows_eval, nsm * std::max(1, ev)); e->rows_sing = std::min(e->rows_sing, nsm * std::max(1, sg));
+    CK(cudaMemset(e->d_partials, 0, (size_t)e->rows_total * NECI_ST_COUNT * 8));      // rows that no kernel writes any more
     return 0;
 }
 

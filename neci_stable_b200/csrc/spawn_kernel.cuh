@@ -675,7 +675,11 @@ __device__ __forceinline__ void generate_and_push(const Params &P, const WalkerL
         if (sys_pchb(SYS)) {
             const double u = rng.draw53();                               // gen_exc_sd
             if (u < P.p_singles) push_s = true;                          // single: generated by k_singles
-            else { gen_pchb_double(P, d, (u - P.p_singles) * P.inv_1m_ps, rng, E); E.pgen = E.pgen * P.p_doubles; }
+            else {
+                if (SYS == NG_SYS_PCHB_FULL) gen_pchb_double_full(P, d, (u - P.p_singles) * P.inv_1m_ps, rng, E);
+                else gen_pchb_double(P, d, (u - P.p_singles) * P.inv_1m_ps, rng, E);
+                E.pgen = E.pgen * P.p_doubles;
+            }
         } else generate_excitation_core<NW, SYS>(P, d, rng, E);
         if (!push_s) {
             if (E.err) atomicOr((unsigned long long *)&L.ctr[C_ERR], 16ull);

@@ -78,6 +78,8 @@ class System:
         if self.kind == capi.SYS_FCIDUMP_PCHB:
             engine.set_system_fcidump(t["umat"], t["tmat"])
             engine.set_pchb(t["pchb"])
+            if t["pchb"].get("particle_selection", "UNIF-UNIF") == "FULL-FULL":
+                engine.set_pchb_particles(1, t["pchb"]["p_first"], t["pchb"]["p_second"])
         elif self.kind == capi.SYS_HUBBARD_RS:
             engine.set_system_hubbard_rs(t["max_neigh"], t["neighbours"], t["tmat"], t["uhub"])
         elif self.kind == capi.SYS_HUBBARD_K:
@@ -88,7 +90,7 @@ class System:
 
 # ---------------------------------------------------------------------------------------
 def random_fcidump_system(n_spat, nel, sparse=1.0, sparse_t=1.0, seed=25, diag_shift=2.0,
-                          p_singles=0.1, p_parallel=None, ms2=0):
+                          p_singles=0.1, p_parallel=None, ms2=0, particle_selection="UNIF-UNIF"):
     """Synthetic FCIDUMP per generate_random_integrals (src/unit_test_helper_excitgen.F90:371-485),
     PCHB `MANUAL UNIF:UNIF UNIF-UNIF:FAST-FAST` spatial-orbital tables."""
     L = lib()
@@ -100,7 +102,8 @@ def random_fcidump_system(n_spat, nel, sparse=1.0, sparse_t=1.0, seed=25, diag_s
                                C.c_double(diag_shift), _p(umat, C.c_double), _p(tmat, C.c_double))
     nalpha = (nel + ms2) // 2
     nbeta = nel - nalpha
-    pchb = build_pchb(n_spat, umat, p_singles=p_singles, p_parallel=p_parallel, nalpha=nalpha, nbeta=nbeta)
+    pchb = build_pchb(n_spat, umat, p_singles=p_singles, p_parallel=p_parallel, nalpha=nalpha, nbeta=nbeta,
+                      particle_selection=particle_selection)
     # aufbau reference: lowest nbeta beta orbitals (odd) and nalpha alpha orbitals (even)
     ref = sorted([2 * i - 1 for i in range(1, nbeta + 1)] + [2 * i for i in range(1, nalpha + 1)])
     return System(kind=capi.SYS_FCIDUMP_PCHB, nel=nel, nbasis=nb, nocc_alpha=nalpha, nocc_beta=nbeta,
@@ -151,8 +154,11 @@ def fcidump_system(norb, nelec, h1, eri, ecore=0.0, ms2=0, orbsym=None, eps=None
                   tables=dict(umat=umat, tmat=tmat, pchb=pchb), ref_orbs=np.array(ref, dtype=np.int32))
 
 
-def build_pchb(n_spat, umat, p_singles=0.1, p_parallel=None, nalpha=None, nbeta=None, class_of_spinorb=None):
-    """GAS_doubles_PCHB_compute_samplers (src/gasci_pchb_doubles_spatorb_fastweighted.fpp:329-445)."""
+def build_pchb(n_spat, umat, p_singles=0.1, p_parallel=None, nalpha=None, nbeta=None, class_of_spinorb=None,
+               particle_selection="UNIF-UNIF"):
+    """GAS_doubles_PCHB_compute_samplers (src/gasci_pchb_doubles_spatorb_fastweighted.fpp:329-445).
+    particle_selection: "UNIF-UNIF" (pick_biased_elecs) or "FULL-FULL" (PC_FullyWeightedParticles_t,
+    src/gasci_pchb_doubles_select_particles.fpp:330-384; adds the tables p_first / p_second)."""
     L = lib()
     ij = C.c_int32(); ab = C.c_int32()
     L.neci_host_pchb_dims(C.c_int32(n_spat), C.byref(ij), C.byref(ab))
@@ -171,10 +177,18 @@ def build_pchb(n_spat, umat, p_singles=0.1, p_parallel=None, nalpha=None, nbeta=
     if class_of_spinorb is None:
         # ORBSYM all 1: one class per spin (0: beta = odd orbitals, 1: alpha = even orbitals)
         class_of_spinorb = np.array([0 if (o % 2) else 1 for o in range(1, 2 * n_spat + 1)], dtype=np.int32)
-    return dict(n_spat=n_spat, ij_max=ij_max, ab_max=ab_max, probs=probs, bias=bias, alias=alias, p_exch=p_exch,
-                tgt_orbs=tgt, p_singles=float(p_singles), p_doubles=1.0 - float(p_singles),
-                p_parallel=float(p_parallel), n_classes=int(class_of_spinorb.max()) + 1,
-                class_of_spinorb=class_of_spinorb)
+    out = dict(n_spat=n_spat, ij_max=ij_max, ab_max=ab_max, probs=probs, bias=bias, alias=alias, p_exch=p_exch,
+               tgt_orbs=tgt, p_singles=float(p_singles), p_doubles=1.0 - float(p_singles),
+               p_parallel=float(p_parallel), n_classes=int(class_of_spinorb.max()) + 1,
+               class_of_spinorb=class_of_spinorb, particle_selection=particle_selection)
+    if particle_selection == "FULL-FULL":
+        nb = 2 * n_spat
+        p_first = np.zeros(nb); p_second = np.zeros(nb * nb)
+        L.neci_host_pchb_particle_probs(C.c_int32(n_spat), _p(um, C.c_double), _p(p_first, C.c_double), _p(p_second, C.c_double))
+        out["p_first"] = p_first; out["p_second"] = p_second
+    elif particle_selection != "UNIF-UNIF":
+        raise ValueError("particle_selection must be UNIF-UNIF or FULL-FULL")
+    return out
 
 
 def hubbard_rs_system(lx, ly, nel=None, U=4.0, t=1.0, pbc=True):

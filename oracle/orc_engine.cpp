@@ -581,6 +581,17 @@ int orc_set_pchb(orc_engine *e, int32_t n_spat, int32_t ij_max, int32_t ab_max, 
     for (int o = 1; o <= e->cfg.nbasis; ++o) S.class_orbs[class_of_spinorb[o - 1]].push_back(o);
     return 0;
 }
+int orc_set_pchb_particles(orc_engine *e, int32_t mode, const double *p_first, const double *p_second) {
+    System &S = e->S;
+    if (mode != 0 && mode != 1) return 1;
+    if (mode == 1 && e->cfg.nbasis > 128) return 1;
+    S.pchb_particles = mode;
+    if (mode == 1) {
+        S.p_first.assign(p_first, p_first + e->cfg.nbasis);
+        S.p_second.assign(p_second, p_second + (size_t)e->cfg.nbasis * e->cfg.nbasis);
+    }
+    return 0;
+}
 int orc_set_system_hubbard_rs(orc_engine *e, int32_t max_neigh, const int32_t *neighbours,
                               const double *tmat2d, double uhub) {
     e->S.max_neigh = max_neigh;
@@ -835,6 +846,15 @@ int orc_probe_gen_excit(orc_engine *e, int64_t n, const int64_t *iluts, const in
 // get_pgen recomputation for PCHB doubles (reference test: get_pgen == returned pgen)
 int orc_probe_pchb_pgen(orc_engine *e, int64_t n, const int32_t *ex, double *out) {
     for (int64_t i = 0; i < n; ++i) out[i] = e->S.p_doubles * pchb_double_get_pgen(e->S, &ex[4 * i]);
+    return 0;
+}
+// the same for a selector whose probability depends on the determinant (FULL-FULL particle selection)
+int orc_probe_pchb_pgen_det(orc_engine *e, int64_t n, const int64_t *iluts, const int32_t *ex, double *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t il[2] = {(uint64_t)iluts[(size_t)i * e->nwords], e->nwords > 1 ? (uint64_t)iluts[(size_t)i * e->nwords + 1] : 0ull};
+        int nI[128]; decode(il, e->cfg.nbasis, nI);
+        out[i] = e->S.p_doubles * pchb_double_get_pgen(e->S, &ex[4 * i], nI);
+    }
     return 0;
 }
 // direct known-answer probes of the lattice elements with an explicit excitation matrix

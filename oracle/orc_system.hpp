@@ -19,6 +19,10 @@ struct System {
     std::vector<double> probs, bias, p_exch;
     std::vector<int32_t> alias, tgt_orbs;
     double p_singles = 1.0, p_doubles = 1.0, p_parallel = 1.0;   // lattice models: a single excitation class
+    // PCHB particle selection: 0 UNIF-UNIF (pick_biased_elecs), 1 FULL-FULL (PC_FullyWeightedParticles_t) with the
+    // normalised probabilities of its I_sampler (p_first[I]) and J_sampler (p_second[I][J] = p(J | I))
+    int pchb_particles = 0;
+    std::vector<double> p_first, p_second;
     int n_classes = 0;
     std::vector<int32_t> class_of_spinorb;          // 0-based class id per spin orbital (index orb-1)
     std::vector<std::vector<int32_t>> class_orbs;   // members of each class, ascending
@@ -473,11 +477,80 @@ inline void gen_uniform_single(const System &S, const int *nI, const uint64_t *i
     E.valid = true;
 }
 
+// CDF_Sampler_t over the probabilities w[k] of the occupied orbitals (src/CDF_sampling.fpp:57-118): p = w / total,
+// cum_p = cumsum(p), the draw is the first position with cum_p >= r (binary_search_first_ge) -- taken here as the
+// first position whose running sum of w reaches r * total (the same condition without a division per element).
+// Returns the 0-based position (the last one with a non-zero weight if rounding leaves the sum below the threshold).
+inline int cdf_pick(const double *w, int n, double total, double r) {
+    const double thr = r * total;
+    double cum = 0.0; int last = 0;
+    for (int k = 0; k < n; ++k) {
+        cum += w[k];
+        if (w[k] > 0.0) { last = k; if (cum >= thr) return k; }
+    }
+    return last;
+}
+// draw_PC_FullyWeightedParticles_t, src/gasci_pchb_doubles_select_particles.fpp:330-384.  The reference's
+// constrained_sample (src/aliasSampling.F90:500-535) draws from the alias table until the result is occupied, or, when
+// the occupied orbitals hold less than redrawing_cutoff = 0.1 of the weight, from a CDF sampler over them; both give
+// p(x) = probs(x) / renormalization.  Engine and checker always take the CDF branch (no data-dependent loop).
+// r_first: the number that picks the first particle; the second particle takes the next 53-bit number of the stream.
+// Returns false when no second particle can be drawn (srcs = 0 in the reference: a null excitation).
+inline bool pick_weighted_elecs(const System &S, const int *nI, double r_first, Stream &rng, int *elecs, int *src, double &pgen) {
+    const int nb = (int)S.p_first.size();
+    double w[128];
+    double renorm_first = 0.0;
+    for (int k = 0; k < S.nel; ++k) { w[k] = S.p_first[nI[k] - 1]; renorm_first += w[k]; }
+    elecs[0] = elecs[1] = 0; src[0] = src[1] = 0; pgen = 1.0;
+    if (near_zero(renorm_first)) return false;
+    const int e1 = cdf_pick(w, S.nel, renorm_first, r_first);
+    const int s1 = nI[e1];
+    const double p_first1 = S.p_first[s1 - 1] / renorm_first;
+    const double *row1 = &S.p_second[(size_t)(s1 - 1) * nb];
+    double renorm_second1 = 0.0;
+    for (int k = 0; k < S.nel; ++k) { w[k] = row1[nI[k] - 1]; renorm_second1 += w[k]; }
+    const double r2 = rng.draw53();
+    if (near_zero(renorm_second1)) return false;
+    const int e2 = cdf_pick(w, S.nel, renorm_second1, r2);
+    const int s2 = nI[e2];
+    const double p_second1 = row1[s2 - 1] / renorm_second1;
+    // the other order (constrained_getProb: 0 when the renormalisation vanishes)
+    const double p_first2 = S.p_first[s2 - 1] / renorm_first;
+    const double *row2 = &S.p_second[(size_t)(s2 - 1) * nb];
+    double renorm_second2 = 0.0;
+    for (int k = 0; k < S.nel; ++k) renorm_second2 += row2[nI[k] - 1];
+    const double p_second2 = near_zero(renorm_second2) ? 0.0 : row2[s1 - 1] / renorm_second2;
+    pgen = p_first1 * p_second1 + p_first2 * p_second2;
+    if (s1 < s2) { elecs[0] = e1 + 1; elecs[1] = e2 + 1; src[0] = s1; src[1] = s2; }
+    else { elecs[0] = e2 + 1; elecs[1] = e1 + 1; src[0] = s2; src[1] = s1; }
+    return true;
+}
+// get_pgen_PC_FullyWeightedParticles_t, :386-438
+inline double weighted_elecs_pgen(const System &S, const int *nI, int I, int J) {
+    const int nb = (int)S.p_first.size();
+    double renorm_first = 0.0, rs1 = 0.0, rs2 = 0.0;
+    const double *row1 = &S.p_second[(size_t)(I - 1) * nb], *row2 = &S.p_second[(size_t)(J - 1) * nb];
+    for (int k = 0; k < S.nel; ++k) { renorm_first += S.p_first[nI[k] - 1]; rs1 += row1[nI[k] - 1]; rs2 += row2[nI[k] - 1]; }
+    if (near_zero(renorm_first)) return 0.0;
+    const double pf1 = S.p_first[I - 1] / renorm_first, pf2 = S.p_first[J - 1] / renorm_first;
+    const double ps1 = near_zero(rs1) ? 0.0 : row1[J - 1] / rs1, ps2 = near_zero(rs2) ? 0.0 : row2[I - 1] / rs2;
+    return pf1 * ps1 + pf2 * ps2;
+}
+
 // GAS_doubles_PCHB_gen_exc, src/gasci_pchb_doubles_spatorb_fastweighted.fpp:155-277
 inline void gen_pchb_double(const System &S, const int *nI, const uint64_t *ilutI, double r_pair, Stream &rng, Excitation &E) {
     E.ic = 2;
     int elecs[2], src[2];
     double pGen, rest;
+    if (S.pchb_particles == 1) {
+        // FULL-FULL: both particles from the selector's tables; the exchange decision takes a 32-bit number of the
+        // attempt's second block, the alias sample the 53-bit number after it (block 0: single / double + first
+        // particle, second particle)
+        if (!pick_weighted_elecs(S, nI, r_pair, rng, elecs, src, pGen)) {
+            E.ex[0] = E.ex[1] = E.ex[2] = E.ex[3] = 0; E.valid = false; E.pgen = 1.0; return;
+        }
+        rest = rng.draw32();
+    } else
     pick_biased_elecs(S, nI, r_pair, elecs, src, pGen, rest);
     const int ij = (int)fuseIndex(gtID(src[0]), gtID(src[1]));
     int spin[2] = {is_beta(src[0]) ? 1 : 0, is_beta(src[1]) ? 1 : 0};   // getSpinIndex: 0 alpha, 1 beta
@@ -510,13 +583,14 @@ inline void gen_pchb_double(const System &S, const int *nI, const uint64_t *ilut
 }
 
 // GAS_doubles_PCHB_get_pgen, :286-326 (+ get_pgen_pick_biased_elecs, excit_gens_int_weighted.F90:849)
-inline double pchb_double_get_pgen(const System &S, const int *ex) {
+inline double pchb_double_get_pgen(const System &S, const int *ex, const int *nI = nullptr) {
     const int nex[4] = {gtID(ex[0]), gtID(ex[1]), gtID(ex[2]), gtID(ex[3])};
     const int ij = (int)fuseIndex(nex[0], nex[1]), ab = (int)fuseIndex(nex[2], nex[3]);
     const int nA = S.nocc_alpha, nB = S.nocc_beta;
     const int par = nA * (nA - 1) / 2 + nB * (nB - 1) / 2, AB = nA * nB;
     const bool same = (is_beta(ex[0]) == is_beta(ex[1]));
     double pgen = same ? S.p_parallel / (double)par : (1.0 - S.p_parallel) / (double)AB;
+    if (S.pchb_particles == 1) pgen = nI ? weighted_elecs_pgen(S, nI, ex[0], ex[1]) : 0.0;   // depends on the determinant
     int sampler;
     if (same) sampler = 0;
     else if ((is_beta(ex[0]) == is_beta(ex[2])) || nex[2] == nex[3]) { sampler = 1; pgen *= (1.0 - S.p_exch[ij - 1]); }

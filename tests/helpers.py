@@ -63,6 +63,19 @@ class Oracle(capi.Engine):
         return out
 
 
+def _probe_pchb_pgen_det(self, iluts, ex):
+    """get_pgen of a PCHB double with a particle selector that depends on the determinant (FULL-FULL)."""
+    ex = np.ascontiguousarray(ex, dtype=np.int32).reshape(-1, 4)
+    il = np.ascontiguousarray(iluts, dtype=np.int64).reshape(ex.shape[0], -1)
+    out = np.zeros(ex.shape[0])
+    self._fn("probe_pchb_pgen_det")(self.h, C.c_int64(ex.shape[0]), il.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    ex.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+Oracle.probe_pchb_pgen_det = _probe_pchb_pgen_det
+
+
 def oracle_lib():
     return C.CDLL(ORACLE_LIB)
 

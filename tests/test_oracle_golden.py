@@ -351,6 +351,70 @@ def test_pchb_generator_sum_inverse_pgen():
     assert np.allclose(pg, res["pgen"][dbl_mask][:20000], rtol=1e-12)
 
 
+def test_pchb_full_full_particle_selection_sum_inverse_pgen():
+    """The same acceptance test with PCHB_ParticleSelection FULL-FULL (PC_FullyWeightedParticles_t,
+    src/gasci_pchb_doubles_select_particles.fpp:330-438), the selection the reference's own PCHB regression input uses:
+    sum(1/pgen)/n_iter within [0.85, 1.15] for every connected determinant with a non-zero element, completeness, and
+    get_pgen (which depends on the determinant here) == returned pgen.  Also the tables themselves: p_first and every
+    row of p_second are normalised, p(I | I) = 0, the pair weights are symmetric."""
+    s = host.random_fcidump_system(10, 6, sparse=0.7, sparse_t=0.7, seed=25, p_singles=0.3, particle_selection="FULL-FULL")
+    t = s.tables["pchb"]
+    nb = s.nbasis
+    p2 = t["p_second"].reshape(nb, nb)
+    assert abs(t["p_first"].sum() - 1.0) < 1e-12 and np.all(t["p_first"] >= 0)
+    assert np.allclose(p2.sum(axis=1)[t["p_first"] > 0], 1.0, atol=1e-12) and np.all(np.diag(p2) == 0.0)
+    wij = p2 * t["p_first"][:, None]                    # p_first[I] p(J | I) is proportional to IJ_weights(J, I): symmetric
+    assert np.allclose(wij, wij.T, rtol=1e-12, atol=1e-15)
+    o = oracle_for(s)
+    det = [1, 2, 3, 7, 8, 10]
+    il = s.ilut(det).reshape(1, -1)
+    n_iter = 1_500_000
+    res = o.probe_gen_excit(np.repeat(il, n_iter, axis=0), np.arange(n_iter, dtype=np.int32), 1)
+    valid = res["ilut_j"][:, 0] != 0
+    assert 0.2 < valid.mean() < 1.0
+    keys, inv, cnt = np.unique(res["ilut_j"][valid, 0], return_inverse=True, return_counts=True)
+    contrib = np.bincount(inv, weights=1.0 / res["pgen"][valid]) / n_iter
+    h = o.probe_helement(np.repeat(il, keys.size, axis=0), keys.reshape(-1, 1))
+    nz = np.abs(h) > 1e-10
+    often = nz & (cnt >= 600)
+    assert often.sum() > 100
+    assert np.all(np.abs(contrib[often] - 1.0) < 0.15), (contrib[often].min(), contrib[often].max())
+    z = (contrib[nz] - 1.0) * np.sqrt(cnt[nz])
+    assert np.abs(z).max() < 5.0 and 0.7 < z.std() < 1.3, (np.abs(z).max(), z.std())
+    # completeness: every connected determinant with a non-zero element whose probability makes it due (30 expected
+    # hits) was generated -- a double with |H_ij| = 2e-4 has p = 1e-7 under weights proportional to |H_ij|
+    occ = set(det)
+    all_conn = [d for d in helpers.all_dets(s) if len(occ - set(d)) in (1, 2)]
+    ilc = np.array([s.ilut(d) for d in all_conn]).reshape(-1, 1)
+    hc = o.probe_helement(np.repeat(il, len(all_conn), axis=0), ilc)
+    got = set(int(x) for x in keys)
+    n_due = 0
+    for d, k, hd in zip(all_conn, ilc[:, 0], hc):
+        if abs(hd) <= 1e-10:
+            continue
+        src, tgt = sorted(occ - set(d)), sorted(set(d) - occ)
+        if len(src) == 2:
+            pg = o.probe_pchb_pgen_det(il, np.array([src + tgt], dtype=np.int32))[0]
+            if pg * n_iter < 30.0:
+                continue
+        n_due += 1
+        assert int(k) in got, (src, tgt, hd)
+    assert n_due > 150
+    dbl_mask = valid & (res["ic"] == 2)
+    m = 20000
+    pg = o.probe_pchb_pgen_det(np.repeat(il, m, axis=0), res["ex"][dbl_mask][:m])
+    assert np.allclose(pg, res["pgen"][dbl_mask][:m], rtol=1e-12)
+    # the weighting does what it is for: the spread of |H_ij| / pgen over the doubles is narrower than with UNIF-UNIF
+    su = host.random_fcidump_system(10, 6, sparse=0.7, sparse_t=0.7, seed=25, p_singles=0.3)
+    ou = oracle_for(su)
+    ru = ou.probe_gen_excit(np.repeat(il, 200000, axis=0), np.arange(200000, dtype=np.int32), 1)
+    def spread(r):
+        d = (r["ilut_j"][:, 0] != 0) & (r["ic"] == 2)
+        x = np.abs(r["hel"][d]) / r["pgen"][d]
+        return x.std() / x.mean()
+    assert spread({k: v[:200000] for k, v in res.items()}) < spread(ru)
+
+
 def test_hubbard_generators_sum_inverse_pgen():
     """The reference's stochastic generator tests for the lattice models
     (test_real_space_hubbard.F90:1599, test_k_space_hubbard.F90:3804) with the same harness criterion."""
