@@ -112,7 +112,7 @@ def random_fcidump_system(n_spat, nel, sparse=1.0, sparse_t=1.0, seed=25, diag_s
 
 
 def fcidump_system(norb, nelec, h1, eri, ecore=0.0, ms2=0, orbsym=None, eps=None, ref_spatial=None,
-                   p_singles=0.1, p_parallel=None):
+                   p_singles=0.1, p_parallel=None, particle_selection="UNIF-UNIF"):
     """A system from FCIDUMP data (what IntInit / readint hand over, src/readint.F90): h1 = [(i, j, value)], eri =
     [(i, j, k, l, value)] in the FCIDUMP's chemist order (ij|kl) with 1-based spatial orbitals.
     UMAT is the packed 8-fold array indexed by UMatInd (src/UMatCache.F90:257-296): <pr|qs> = (pq|rs) sits at
@@ -142,7 +142,7 @@ def fcidump_system(norb, nelec, h1, eri, ecore=0.0, ms2=0, orbsym=None, eps=None
             irr = labels.index(int(orbsym[(so + 1) // 2 - 1]))
             cls[so - 1] = 2 * irr + (0 if so % 2 else 1)
     pchb = build_pchb(norb, umat, p_singles=p_singles, p_parallel=p_parallel, nalpha=nalpha, nbeta=nbeta,
-                      class_of_spinorb=cls)
+                      class_of_spinorb=cls, particle_selection=particle_selection)
     if ref_spatial is None:
         order = np.argsort(np.asarray(eps if eps is not None else [tmat[(2 * a - 2) + nb * (2 * a - 2)] for a in range(1, norb + 1)]),
                            kind="stable")

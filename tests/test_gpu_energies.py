@@ -127,16 +127,19 @@ def test_reference_regression_case_hehe_ss_doubles():
     assert abs(sm + hii - g["total_projected_energy"]) < max(5 * serr, 2e-2), (sm + hii, serr)
 
 
-def test_reference_regression_case_ne_pchb():
+@pytest.mark.parametrize("particle_selection", ["FULL-FULL", "UNIF-UNIF"])
+def test_reference_regression_case_ne_pchb(particle_selection):
     """The reference's PCHB regression case test_suite/neci/parallel/Ne_FciMCPar_pchb (Ne, 8 active electrons in 22
     orbitals after `freeze 2 0`, i-FCIQMC with integer walkers, addtoinitiator 3, 20000 walkers, shift damping 0.03
     every 25 iterations) on the CUDA engine: reference-determinant energy to the printed digits, and the initiator
-    projected energy against the reference CPU run's -128.70959926 +- 6.8e-4 (the reference picks electron pairs with
-    FULL-FULL weighting, this engine with UNIF-UNIF: different unbiased generators, same estimator)."""
+    projected energy against the reference CPU run's -128.70959926 +- 6.8e-4.  The reference run picks electron pairs
+    with FULL-FULL weighting (its input's `PCHB` block): that is the first case; UNIF-UNIF, a different unbiased
+    generator under the same estimator, is the second."""
     import os
     z = np.load(os.path.join(helpers.GOLDEN, "ne_pchb.npz"))
     s = host.fcidump_system(int(z["norb"]), int(z["nelec"]), z["h1"], z["eri"], ecore=float(z["ecore"]), ms2=0,
-                            orbsym=[int(x) for x in z["orbsym"]], eps=z["eps"], p_singles=0.2)
+                            orbsym=[int(x) for x in z["orbsym"]], eps=z["eps"], p_singles=0.2,
+                            particle_selection=particle_selection)
     gpu, hii = _engine(s, initiator=True, initiator_walk_no=float(z["input_addtoinitiator"]), seed=8,
                        max_walkers=400000, max_spawned=400000)
     assert [int(x) for x in s.ref_orbs] == [int(x) for x in z["reference_det"]]
