@@ -159,7 +159,9 @@ typedef struct neci_gpu_config {
 typedef struct neci_gpu_engine neci_gpu_engine;   /* opaque */
 
 /* ---- lifetime ------------------------------------------------------------ */
-/* Called at the end of InitFCIMCCalcPar (src/FciMCPar.F90:256).             */
+/* Called at the end of InitFCIMCCalcPar (src/FciMCPar.F90:256).  On failure (non-zero return) *out still holds a
+ * handle: it carries the message for neci_gpu_last_error and whatever was allocated before the failure, accepts no
+ * other call, and must be released with neci_gpu_finalize.                                                       */
 int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out);
 /* Called from DeallocFCIMCMemPar.                                            */
 int neci_gpu_finalize(neci_gpu_engine *e);

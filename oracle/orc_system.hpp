@@ -221,8 +221,8 @@ inline int excitation_between(const uint64_t *iI, const uint64_t *iJ, int nbasis
                               int *ex, bool &tParity) {
     int nI[128], nJ[128], tmp[128];
     decode(iI, nbasis, nI);
-    int srcs[4], tgts[4], ns = 0, nt = 0, elec[4];
-    for (int i = 0; i < nel; ++i) if (!is_occ(iJ, nI[i])) { if (ns < 4) { srcs[ns] = nI[i]; elec[ns] = i + 1; } ++ns; }
+    int tgts[4], ns = 0, nt = 0, elec[4];
+    for (int i = 0; i < nel; ++i) if (!is_occ(iJ, nI[i])) { if (ns < 4) elec[ns] = i + 1; ++ns; }
     for (int o = 1; o <= nbasis; ++o) if (is_occ(iJ, o) && !is_occ(iI, o)) { if (nt < 4) tgts[nt] = o; ++nt; }
     if (ns != nt || ns > 2) return (ns == nt) ? ns : -1;
     (void)nJ;
