@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--core-build", default="host", choices=["host", "device"],
                     help="semi-stochastic workloads: who builds the sparse core Hamiltonian")
     ap.add_argument("--trial", type=int, default=10, help="semi-stochastic workloads: determinants in the trial space (0 = none)")
-    ap.add_argument("--particle-selection", default="UNIF-UNIF", choices=["UNIF-UNIF", "FULL-FULL"],
+    ap.add_argument("--particle-selection", default="UNIF-UNIF", choices=["UNIF-UNIF", "FULL-FULL", "UNIF-FULL"],
                     help="PCHB workloads: PCHB_ParticleSelection of the doubles generator (BASELINE configs quote UNIF-UNIF; "
                          "FULL-FULL is what the reference's own PCHB regression input selects)")
     ap.add_argument("--list", default="auto", choices=["auto", "host", "device"],

@@ -194,8 +194,9 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
  * (PC_FullyWeightedParticles_t, :330-438): the first particle I is drawn with p_first[I] and the second with
  * p_second[I][J] = p(J | I), both restricted to the occupied orbitals and renormalised (constrained sampling), and
  * p({I, J}) sums both orders.  p_first[nBasis] and p_second[nBasis * nBasis] (row I) are the normalised probabilities
- * of the selector's I_sampler / J_sampler (AliasSampler_t::get_prob), spin orbitals in NECI order.  Call after
- * neci_gpu_set_pchb; not available together with t_hphf.                                                        */
+ * of the selector's I_sampler / J_sampler (AliasSampler_t::get_prob), spin orbitals in NECI order.  mode 2 = UNIF-FULL
+ * (PC_WeightedParticles_t, :440-506): the first particle uniformly among the electrons, the second as above, p = (p(J | I)
+ * + p(I | J)) / nEl.  Call after neci_gpu_set_pchb; not available together with t_hphf.  (UNIF-FAST is not built.) */
 int neci_gpu_set_pchb_particles(neci_gpu_engine *e, int32_t mode, const double *p_first, const double *p_second);
 
 /* New excitation-class biases from the tau search (update_tau, src/tau/tau_search_conventional.F90:274-499 assigns

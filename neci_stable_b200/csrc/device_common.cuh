@@ -232,7 +232,8 @@ struct Params {
     int n_spat, ij_max, ab_max;
     const struct PchbEntry *pchb;     // [ij_max * 3 * ab_max]
     const struct PchbPair *pchb_pair; // [ij_max]
-    const double *pchb_pfirst, *pchb_psecond;       // FULL-FULL particle selection: p_first[nbasis], p_second[nbasis][nbasis]
+    const double *pchb_pfirst, *pchb_psecond;       // FULL-FULL / UNIF-FULL particle selection: p_first[nbasis], p_second[nbasis][nbasis]
+    int pchb_particles;                             // 0 UNIF-UNIF, 1 FULL-FULL, 2 UNIF-FULL
     double p_singles, p_doubles, p_parallel;
     double pgen_pair_par, pgen_pair_opp;            // p_parallel / #parallel pairs, (1 - p_parallel) / #alpha-beta pairs
     // host-computed rescaling constants of the first draw of an attempt (see gen_pchb_double): 1 / (1 - p_singles),

@@ -550,21 +550,27 @@ template <int NW>
 __device__ void gen_pchb_double_full(const Params &P, const Det<NW> &d, double r, Stream &rng, Excit<NW> &E) {
     E.ic = 2; E.valid = false; E.err = 0; E.src1 = E.src2 = E.tgt1 = E.tgt2 = 0; E.pgen = 1.0;
     const int nb = P.nbasis;
+    const bool unif_first = P.pchb_particles == 2;      // UNIF-FULL (draw_PC_WeightedParticles_t, :440-478): the first particle uniformly
     const double renorm_first = sum_occupied(d, P.pchb_pfirst);
     const double r2 = rng.draw53();
-    if (fabs(renorm_first) <= NG_EPS) return;
+    if (!unif_first && fabs(renorm_first) <= NG_EPS) return;
     double dummy;
-    const int s1 = cdf_pick_occupied(d, P.pchb_pfirst, renorm_first, r, dummy);
+    const int s1 = unif_first ? select_orb(d, ~0ull, min((int)(r * P.nel), P.nel - 1) + 1)
+                              : cdf_pick_occupied(d, P.pchb_pfirst, renorm_first, r, dummy);
     const double *row1 = P.pchb_psecond + (size_t)(s1 - 1) * nb;
     const double renorm_second1 = sum_occupied(d, row1);
     if (fabs(renorm_second1) <= NG_EPS) return;
     const int s2 = cdf_pick_occupied(d, row1, renorm_second1, r2, dummy);
-    const double p_first1 = __ldg(&P.pchb_pfirst[s1 - 1]) / renorm_first, p_second1 = __ldg(&row1[s2 - 1]) / renorm_second1;
-    const double p_first2 = __ldg(&P.pchb_pfirst[s2 - 1]) / renorm_first;
+    const double p_second1 = __ldg(&row1[s2 - 1]) / renorm_second1;
     const double *row2 = P.pchb_psecond + (size_t)(s2 - 1) * nb;
     const double renorm_second2 = sum_occupied(d, row2);
     const double p_second2 = (fabs(renorm_second2) <= NG_EPS) ? 0.0 : __ldg(&row2[s1 - 1]) / renorm_second2;
-    const double pGen = p_first1 * p_second1 + p_first2 * p_second2;
+    double pGen;
+    if (unif_first) pGen = (p_second1 + p_second2) / (double)P.nel;
+    else {
+        const double p_first1 = __ldg(&P.pchb_pfirst[s1 - 1]) / renorm_first, p_first2 = __ldg(&P.pchb_pfirst[s2 - 1]) / renorm_first;
+        pGen = p_first1 * p_second1 + p_first2 * p_second2;
+    }
     const double u2 = rng.draw32();
     pchb_pick_holes(P, d, min(s1, s2), max(s1, s2), pGen, u2, rng, E);
 }

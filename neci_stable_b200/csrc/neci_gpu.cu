@@ -425,10 +425,11 @@ int neci_gpu_set_pchb(neci_gpu_engine *e, int32_t n_spat, int32_t ij_max, int32_
 int neci_gpu_set_pchb_particles(neci_gpu_engine *e, int32_t mode, const double *p_first, const double *p_second) {
     CK(cudaSetDevice(e->cfg.device));
     if (e->cfg.system_type != NECI_SYS_FCIDUMP_PCHB || !e->P.pchb) return e->fail("set_pchb_particles: call neci_gpu_set_pchb first (FCIDUMP/PCHB systems)");
-    if (mode == 0) { e->pchb_full = false; return 0; }
-    if (mode != 1) return e->fail("set_pchb_particles: mode %d is not implemented (0 UNIF-UNIF, 1 FULL-FULL)", mode);
-    if (e->cfg.t_hphf) return e->fail("set_pchb_particles: FULL-FULL particle selection is not available with t_hphf");
-    if (!p_first || !p_second) return e->fail("set_pchb_particles: FULL-FULL needs both probability tables");
+    if (mode == 0) { e->pchb_full = false; e->P.pchb_particles = 0; return 0; }
+    if (mode != 1 && mode != 2) return e->fail("set_pchb_particles: mode %d is not implemented (0 UNIF-UNIF, 1 FULL-FULL, 2 UNIF-FULL)", mode);
+    if (e->cfg.t_hphf) return e->fail("set_pchb_particles: weighted particle selection is not available with t_hphf");
+    if (!p_first || !p_second) return e->fail("set_pchb_particles: weighted particle selection needs both probability tables");
+    e->P.pchb_particles = mode;
     const size_t nb = (size_t)e->cfg.nbasis;
     e->P.pchb_pfirst = e->upload(p_first, nb);
     e->P.pchb_psecond = e->upload(p_second, nb * nb);

@@ -78,8 +78,9 @@ class System:
         if self.kind == capi.SYS_FCIDUMP_PCHB:
             engine.set_system_fcidump(t["umat"], t["tmat"])
             engine.set_pchb(t["pchb"])
-            if t["pchb"].get("particle_selection", "UNIF-UNIF") == "FULL-FULL":
-                engine.set_pchb_particles(1, t["pchb"]["p_first"], t["pchb"]["p_second"])
+            sel = t["pchb"].get("particle_selection", "UNIF-UNIF")
+            if sel != "UNIF-UNIF":
+                engine.set_pchb_particles({"FULL-FULL": 1, "UNIF-FULL": 2}[sel], t["pchb"]["p_first"], t["pchb"]["p_second"])
         elif self.kind == capi.SYS_HUBBARD_RS:
             engine.set_system_hubbard_rs(t["max_neigh"], t["neighbours"], t["tmat"], t["uhub"])
         elif self.kind == capi.SYS_HUBBARD_K:
@@ -157,8 +158,9 @@ def fcidump_system(norb, nelec, h1, eri, ecore=0.0, ms2=0, orbsym=None, eps=None
 def build_pchb(n_spat, umat, p_singles=0.1, p_parallel=None, nalpha=None, nbeta=None, class_of_spinorb=None,
                particle_selection="UNIF-UNIF"):
     """GAS_doubles_PCHB_compute_samplers (src/gasci_pchb_doubles_spatorb_fastweighted.fpp:329-445).
-    particle_selection: "UNIF-UNIF" (pick_biased_elecs) or "FULL-FULL" (PC_FullyWeightedParticles_t,
-    src/gasci_pchb_doubles_select_particles.fpp:330-384; adds the tables p_first / p_second)."""
+    particle_selection: "UNIF-UNIF" (pick_biased_elecs), "FULL-FULL" (PC_FullyWeightedParticles_t,
+    src/gasci_pchb_doubles_select_particles.fpp:330-384) or "UNIF-FULL" (PC_WeightedParticles_t, :440-506); the
+    weighted ones add the tables p_first / p_second."""
     L = lib()
     ij = C.c_int32(); ab = C.c_int32()
     L.neci_host_pchb_dims(C.c_int32(n_spat), C.byref(ij), C.byref(ab))
@@ -181,13 +183,13 @@ def build_pchb(n_spat, umat, p_singles=0.1, p_parallel=None, nalpha=None, nbeta=
                tgt_orbs=tgt, p_singles=float(p_singles), p_doubles=1.0 - float(p_singles),
                p_parallel=float(p_parallel), n_classes=int(class_of_spinorb.max()) + 1,
                class_of_spinorb=class_of_spinorb, particle_selection=particle_selection)
-    if particle_selection == "FULL-FULL":
+    if particle_selection in ("FULL-FULL", "UNIF-FULL"):
         nb = 2 * n_spat
         p_first = np.zeros(nb); p_second = np.zeros(nb * nb)
         L.neci_host_pchb_particle_probs(C.c_int32(n_spat), _p(um, C.c_double), _p(p_first, C.c_double), _p(p_second, C.c_double))
         out["p_first"] = p_first; out["p_second"] = p_second
     elif particle_selection != "UNIF-UNIF":
-        raise ValueError("particle_selection must be UNIF-UNIF or FULL-FULL")
+        raise ValueError("particle_selection must be UNIF-UNIF, FULL-FULL or UNIF-FULL")
     return out
 
 

@@ -583,10 +583,10 @@ int orc_set_pchb(orc_engine *e, int32_t n_spat, int32_t ij_max, int32_t ab_max, 
 }
 int orc_set_pchb_particles(orc_engine *e, int32_t mode, const double *p_first, const double *p_second) {
     System &S = e->S;
-    if (mode != 0 && mode != 1) return 1;
-    if (mode == 1 && e->cfg.nbasis > 128) return 1;
+    if (mode < 0 || mode > 2) return 1;
+    if (mode != 0 && e->cfg.nbasis > 128) return 1;
     S.pchb_particles = mode;
-    if (mode == 1) {
+    if (mode != 0) {
         S.p_first.assign(p_first, p_first + e->cfg.nbasis);
         S.p_second.assign(p_second, p_second + (size_t)e->cfg.nbasis * e->cfg.nbasis);
     }

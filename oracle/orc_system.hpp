@@ -502,10 +502,11 @@ inline bool pick_weighted_elecs(const System &S, const int *nI, double r_first, 
     double renorm_first = 0.0;
     for (int k = 0; k < S.nel; ++k) { w[k] = S.p_first[nI[k] - 1]; renorm_first += w[k]; }
     elecs[0] = elecs[1] = 0; src[0] = src[1] = 0; pgen = 1.0;
-    if (near_zero(renorm_first)) return false;
-    const int e1 = cdf_pick(w, S.nel, renorm_first, r_first);
+    const bool unif_first = S.pchb_particles == 2;      // UNIF-FULL (draw_PC_WeightedParticles_t, :440-478): elecs(1) = int(r * nEl) + 1
+    if (!unif_first && near_zero(renorm_first)) return false;
+    const int e1 = unif_first ? std::min((int)(r_first * S.nel), S.nel - 1) : cdf_pick(w, S.nel, renorm_first, r_first);
     const int s1 = nI[e1];
-    const double p_first1 = S.p_first[s1 - 1] / renorm_first;
+    const double p_first1 = unif_first ? 1.0 / (double)S.nel : S.p_first[s1 - 1] / renorm_first;
     const double *row1 = &S.p_second[(size_t)(s1 - 1) * nb];
     double renorm_second1 = 0.0;
     for (int k = 0; k < S.nel; ++k) { w[k] = row1[nI[k] - 1]; renorm_second1 += w[k]; }
@@ -515,12 +516,13 @@ inline bool pick_weighted_elecs(const System &S, const int *nI, double r_first, 
     const int s2 = nI[e2];
     const double p_second1 = row1[s2 - 1] / renorm_second1;
     // the other order (constrained_getProb: 0 when the renormalisation vanishes)
-    const double p_first2 = S.p_first[s2 - 1] / renorm_first;
+    const double p_first2 = unif_first ? p_first1 : S.p_first[s2 - 1] / renorm_first;
     const double *row2 = &S.p_second[(size_t)(s2 - 1) * nb];
     double renorm_second2 = 0.0;
     for (int k = 0; k < S.nel; ++k) renorm_second2 += row2[nI[k] - 1];
     const double p_second2 = near_zero(renorm_second2) ? 0.0 : row2[s1 - 1] / renorm_second2;
-    pgen = p_first1 * p_second1 + p_first2 * p_second2;
+    pgen = unif_first ? (p_second1 + p_second2) / (double)S.nel          // sum(p_second) / nEl
+                      : p_first1 * p_second1 + p_first2 * p_second2;
     if (s1 < s2) { elecs[0] = e1 + 1; elecs[1] = e2 + 1; src[0] = s1; src[1] = s2; }
     else { elecs[0] = e2 + 1; elecs[1] = e1 + 1; src[0] = s2; src[1] = s1; }
     return true;
@@ -531,9 +533,10 @@ inline double weighted_elecs_pgen(const System &S, const int *nI, int I, int J) 
     double renorm_first = 0.0, rs1 = 0.0, rs2 = 0.0;
     const double *row1 = &S.p_second[(size_t)(I - 1) * nb], *row2 = &S.p_second[(size_t)(J - 1) * nb];
     for (int k = 0; k < S.nel; ++k) { renorm_first += S.p_first[nI[k] - 1]; rs1 += row1[nI[k] - 1]; rs2 += row2[nI[k] - 1]; }
+    const double ps1 = near_zero(rs1) ? 0.0 : row1[J - 1] / rs1, ps2 = near_zero(rs2) ? 0.0 : row2[I - 1] / rs2;
+    if (S.pchb_particles == 2) return (ps1 + ps2) / (double)S.nel;           // get_pgen_PC_WeightedParticles_t, :476-506
     if (near_zero(renorm_first)) return 0.0;
     const double pf1 = S.p_first[I - 1] / renorm_first, pf2 = S.p_first[J - 1] / renorm_first;
-    const double ps1 = near_zero(rs1) ? 0.0 : row1[J - 1] / rs1, ps2 = near_zero(rs2) ? 0.0 : row2[I - 1] / rs2;
     return pf1 * ps1 + pf2 * ps2;
 }
 
@@ -542,8 +545,8 @@ inline void gen_pchb_double(const System &S, const int *nI, const uint64_t *ilut
     E.ic = 2;
     int elecs[2], src[2];
     double pGen, rest;
-    if (S.pchb_particles == 1) {
-        // FULL-FULL: both particles from the selector's tables; the exchange decision takes a 32-bit number of the
+    if (S.pchb_particles != 0) {
+        // FULL-FULL / UNIF-FULL: particles from the selector's tables; the exchange decision takes a 32-bit number of the
         // attempt's second block, the alias sample the 53-bit number after it (block 0: single / double + first
         // particle, second particle)
         if (!pick_weighted_elecs(S, nI, r_pair, rng, elecs, src, pGen)) {
@@ -590,7 +593,7 @@ inline double pchb_double_get_pgen(const System &S, const int *ex, const int *nI
     const int par = nA * (nA - 1) / 2 + nB * (nB - 1) / 2, AB = nA * nB;
     const bool same = (is_beta(ex[0]) == is_beta(ex[1]));
     double pgen = same ? S.p_parallel / (double)par : (1.0 - S.p_parallel) / (double)AB;
-    if (S.pchb_particles == 1) pgen = nI ? weighted_elecs_pgen(S, nI, ex[0], ex[1]) : 0.0;   // depends on the determinant
+    if (S.pchb_particles != 0) pgen = nI ? weighted_elecs_pgen(S, nI, ex[0], ex[1]) : 0.0;   // depends on the determinant
     int sampler;
     if (same) sampler = 0;
     else if ((is_beta(ex[0]) == is_beta(ex[2])) || nex[2] == nex[3]) { sampler = 1; pgen *= (1.0 - S.p_exch[ij - 1]); }

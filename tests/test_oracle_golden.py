@@ -351,13 +351,15 @@ def test_pchb_generator_sum_inverse_pgen():
     assert np.allclose(pg, res["pgen"][dbl_mask][:20000], rtol=1e-12)
 
 
-def test_pchb_full_full_particle_selection_sum_inverse_pgen():
+@pytest.mark.parametrize("selection", ["FULL-FULL", "UNIF-FULL"])
+def test_pchb_full_full_particle_selection_sum_inverse_pgen(selection):
     """The same acceptance test with PCHB_ParticleSelection FULL-FULL (PC_FullyWeightedParticles_t,
-    src/gasci_pchb_doubles_select_particles.fpp:330-438), the selection the reference's own PCHB regression input uses:
+    src/gasci_pchb_doubles_select_particles.fpp:330-438), the selection the reference's own PCHB regression input uses,
+    and UNIF-FULL (PC_WeightedParticles_t, :440-506: first particle uniform, second weighted):
     sum(1/pgen)/n_iter within [0.85, 1.15] for every connected determinant with a non-zero element, completeness, and
     get_pgen (which depends on the determinant here) == returned pgen.  Also the tables themselves: p_first and every
     row of p_second are normalised, p(I | I) = 0, the pair weights are symmetric."""
-    s = host.random_fcidump_system(10, 6, sparse=0.7, sparse_t=0.7, seed=25, p_singles=0.3, particle_selection="FULL-FULL")
+    s = host.random_fcidump_system(10, 6, sparse=0.7, sparse_t=0.7, seed=25, p_singles=0.3, particle_selection=selection)
     t = s.tables["pchb"]
     nb = s.nbasis
     p2 = t["p_second"].reshape(nb, nb)
