@@ -544,16 +544,16 @@ __global__ void __launch_bounds__(256) k_synth_dedupe(WalkerList L, long long *a
 
 // ---- upload / download (AoS ilut(0:NIfTot) <-> SoA) ------------------------------
 template <int NW, int SYS>
-__global__ void __launch_bounds__(256) k_upload(Params P, WalkerList L, const long long *aos, long long n, const double *gd, const double *go, int W,
-                                                long long n_prev) {
+__global__ void __launch_bounds__(256) k_upload(Params P, WalkerList L, const long long *aos, long long i_begin, long long n, const double *gd,
+                                                const double *go, int W, long long n_prev) {      // slots [i_begin, n)
     // empty slots go to the FreeSlot stack through a per-warp stage: one global atomic per ~100 holes, not one per hole
     __shared__ WarpStage<1, 128> s_free[8];
     WarpStage<1, 128> &FB = s_free[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     int n_free = 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nloop = ((n + stride - 1) / stride) * stride;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
+    const long long nloop = i_begin + ((n - i_begin + stride - 1) / stride) * stride;
+    for (long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloop; i += stride) {
         bool hole = false;
         if (i < n) {
             const long long *rec = aos + (size_t)i * W;

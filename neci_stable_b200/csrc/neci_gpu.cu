@@ -99,8 +99,10 @@ struct neci_gpu_engine {
     int spmv_cb = 0, spmv_nb = 0; long long core_nnz = 0, core_nnz_padded = 0;
     int *d_core_slots = nullptr; double *d_vpart = nullptr, *d_vfull = nullptr, *d_vout = nullptr, *d_core_diag = nullptr;
     std::vector<int> core_sizes, core_displs;
-    // staging for AoS transfers
+    // staging for AoS transfers; large uploads run chunked on a copy stream (neci_gpu_upload_walkers)
     long long *d_aos = nullptr; size_t aos_cap = 0;
+    cudaStream_t copy_stream = nullptr; cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};
+    long long h_nlist = 0, upload_chunk = 1ll << 21;
     // multi-rank
     ncclComm_t comm = nullptr;
     unsigned long long *d_cnt_all = nullptr, *h_cnt_all = nullptr;
@@ -177,6 +179,7 @@ int neci_gpu_init(const neci_gpu_config *cfg, neci_gpu_engine **out) {
     CK(cudaSetDevice(cfg->device));
     e->nw = cfg->nifd + 1; e->W = cfg->niftot + 1;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    if (const char *c = getenv("NECI_GPU_UPLOAD_CHUNK")) { const long long v = atoll(c); if (v >= 32) e->upload_chunk = v; }
     for (auto &v : e->ev) CK(cudaEventCreate(&v));
     CK(cudaEventCreate(&e->ev_t0)); CK(cudaEventCreate(&e->ev_t1));
 
@@ -316,6 +319,8 @@ int neci_gpu_finalize(neci_gpu_engine *e) {
     if (e->p2p_block) cudaFree(e->p2p_block);
     for (void *p : e->owned) cudaFree(p);
     if (e->d_aos) cudaFree(e->d_aos);
+    for (auto &v : e->copy_ev) if (v) cudaEventDestroy(v);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->h_stats) cudaFreeHost(e->h_stats);
     if (e->h_cnt_all) cudaFreeHost(e->h_cnt_all);
     for (auto &v : e->ev) if (v) cudaEventDestroy(v);
@@ -518,27 +523,65 @@ int neci_gpu_set_system_hubbard_k(neci_gpu_engine *e, int32_t n_k, const int32_t
 // -------------------------------------------------------------------------------
 // the list in the AoS staging buffer (n records, optionally followed by the two gdata rows) becomes the resident list
 static int take_in_staged_list(neci_gpu_engine *e, int64_t n, double *dgd, double *dgo);
+static int take_in_begin(neci_gpu_engine *e, int64_t n);
+static int take_in_range(neci_gpu_engine *e, int64_t i0, int64_t i1, double *dgd, double *dgo);
 int neci_gpu_upload_walkers(neci_gpu_engine *e, const int64_t *current_dets, int64_t n, const double *gd, const double *go) {
     CK(cudaSetDevice(e->cfg.device));
     if (n > e->cfg.max_walkers - 1) return e->fail("upload of %lld walkers exceeds max_walkers", (long long)n);
     const size_t words = (size_t)n * e->W;
     if (ensure_aos(e, words + 2 * (size_t)n)) return 1;
-    CK(cudaMemcpyAsync(e->d_aos, current_dets, words * 8, cudaMemcpyHostToDevice, e->stream));
-    double *dgd = nullptr, *dgo = nullptr;
-    if (gd) { dgd = (double *)(e->d_aos + words); CK(cudaMemcpyAsync(dgd, gd, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream)); }
-    if (go) { dgo = (double *)(e->d_aos + words + n); CK(cudaMemcpyAsync(dgo, go, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream)); }
-    return take_in_staged_list(e, n, dgd, dgo);
+    double *dgd = gd ? (double *)(e->d_aos + words) : nullptr, *dgo = go ? (double *)(e->d_aos + words + n) : nullptr;
+    // Large lists arrive in chunks on a copy stream while the engine's stream clears the hash table and takes in the
+    // chunks that have landed (k_upload per chunk): the SoA conversion and the hash inserts hide behind the host link
+    const long long chunk = e->upload_chunk;                 // 2M records (48 MB at W = 3) unless NECI_GPU_UPLOAD_CHUNK says otherwise
+    if (n <= chunk) {
+        CK(cudaMemcpyAsync(e->d_aos, current_dets, words * 8, cudaMemcpyHostToDevice, e->stream));
+        if (gd) CK(cudaMemcpyAsync(dgd, gd, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+        if (go) CK(cudaMemcpyAsync(dgo, go, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+        return take_in_staged_list(e, n, dgd, dgo);
+    }
+    if (!e->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (auto &v : e->copy_ev) CK(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(e->copy_ev[0], e->stream));           // the staging buffer is free once earlier work has finished
+    CK(cudaStreamWaitEvent(e->copy_stream, e->copy_ev[0], 0));
+    if (take_in_begin(e, n)) return 1;
+    int k = 0;
+    for (long long i0 = 0; i0 < n; i0 += chunk, ++k) {
+        const long long i1 = std::min<long long>(n, i0 + chunk);
+        CK(cudaMemcpyAsync(e->d_aos + (size_t)i0 * e->W, current_dets + (size_t)i0 * e->W, (size_t)(i1 - i0) * e->W * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        if (gd) CK(cudaMemcpyAsync(dgd + i0, gd + i0, (size_t)(i1 - i0) * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        if (go) CK(cudaMemcpyAsync(dgo + i0, go + i0, (size_t)(i1 - i0) * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        cudaEvent_t ev = e->copy_ev[1 + (k & 1)];
+        CK(cudaEventRecord(ev, e->copy_stream));
+        CK(cudaStreamWaitEvent(e->stream, ev, 0));
+        if (take_in_range(e, i0, i1, dgd, dgo)) return 1;
+    }
+    e->n_resident = n;
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
 }
-static int take_in_staged_list(neci_gpu_engine *e, int64_t n, double *dgd, double *dgo) {
+// clears counters and hash table for a list of n records (on the engine's stream)
+static int take_in_begin(neci_gpu_engine *e, int64_t n) {
     CK(cudaMemsetAsync(e->L.ctr, 0, C_COUNT * 8, e->stream));
     CK(cudaMemsetAsync(e->L.ht, 0xFF, (size_t)e->ht_cap * 8, e->stream));
-    long long nn = n;
-    CK(cudaMemcpyAsync(&e->L.ctr[C_NLIST], &nn, 8, cudaMemcpyHostToDevice, e->stream));
-    const int grid = (int)std::min<long long>(e->grid_generic, std::max<long long>(1, (n + 255) / 256));
+    e->h_nlist = n;                                          // pinned: the copy below reads it when it runs
+    CK(cudaMemcpyAsync(&e->L.ctr[C_NLIST], &e->h_nlist, 8, cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+// slots [i0, i1) of the staged list become resident (SoA conversion, gdata, hash inserts, holes to the FreeSlot stack)
+static int take_in_range(neci_gpu_engine *e, int64_t i0, int64_t i1, double *dgd, double *dgo) {
+    const int grid = (int)std::min<long long>(e->grid_generic, std::max<long long>(1, (i1 - i0 + 255) / 256));
     e->n_launch += 1;
-    NG_DISPATCH(e, (k_upload<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, e->L, e->d_aos, n, dgd, dgo, e->W, e->n_resident)));
-    e->n_resident = n;
+    NG_DISPATCH(e, (k_upload<NW, SYS><<<grid, 256, 0, e->stream>>>(e->P, e->L, e->d_aos, i0, i1, dgd, dgo, e->W, e->n_resident)));
     CK(cudaGetLastError());
+    return 0;
+}
+static int take_in_staged_list(neci_gpu_engine *e, int64_t n, double *dgd, double *dgo) {
+    if (take_in_begin(e, n)) return 1;
+    if (take_in_range(e, 0, n, dgd, dgo)) return 1;
+    e->n_resident = n;
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
