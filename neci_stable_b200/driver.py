@@ -76,6 +76,30 @@ def reduce_stats(st):
     return out
 
 
+def dist_reduce_or(flags):
+    """MPIAllLORLogical over the ranks of the initialised process group (identity on one rank)."""
+    dist = _world()
+    if dist is None or dist.get_world_size() == 1:
+        return np.asarray(flags, dtype=bool)
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(np.asarray(flags, dtype=np.int32), device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.cpu().numpy().astype(bool)
+
+
+def dist_reduce_max(values):
+    """MPIAllReduce(MPI_MAX) over the ranks of the initialised process group (identity on one rank)."""
+    dist = _world()
+    if dist is None or dist.get_world_size() == 1:
+        return np.asarray(values, dtype=np.float64)
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(np.asarray(values, dtype=np.float64), device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.cpu().numpy()
+
+
 def plan_load_balance(block_parts_all, mapping, nranks):
     """The greedy balancer of adjust_load_balance (src/load_balancer.fpp:239-304): repeatedly move the smallest
     non-empty block of the fullest rank to the emptiest rank while that brings both closer to the average.

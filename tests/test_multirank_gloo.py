@@ -79,3 +79,48 @@ def test_two_rank_job_reproduces_single_rank(tmp_path, kind):
         c = helpers.canon(r[k]["dets"], nw=system.nw)
         _, nd = o2.probe_det_node(c[0])
         assert np.all(nd == k)
+
+
+def _tau_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    system = host.random_fcidump_system(8, 6, sparse=0.8, sparse_t=0.8, seed=5, p_singles=0.2)
+    hii = driver.diag_energy(system, system.ref_orbs)
+    o, params = helpers.make_pair(system, hii, max_walkers=100000, max_spawned=100000, nranks=world, rank=rank, seed=9,
+                                  blocks_per_rank=4, tau_search=True, initiator=False)
+    _, node = o.probe_det_node(system.ilut(system.ref_orbs).reshape(1, -1))
+    eng = helpers.DistOracle(o, dist)
+    t = system.tables["pchb"]
+    ts = driver.TauSearch(0.02, t["p_singles"], t["p_doubles"], t["p_parallel"], consider_par_bias=True,
+                          reduce_or=driver.dist_reduce_or, reduce_max=driver.dist_reduce_max)
+    rec = host.record(system, system.ref_orbs, 400.0, 1 << capi.FLAG_INITIATOR).reshape(1, -1)
+    o.upload_walkers(rec if rank == int(node[0]) else np.zeros((0, system.W), dtype=np.int64))
+    tau = ts.tau
+    local_gamma = np.zeros(4); trace = []
+    for it in range(1, 61):
+        st = eng.iterate(tau, 0.0, it)                     # this rank's statistics vector
+        ts.log(st)
+        local_gamma = np.maximum(local_gamma, st[capi.ST["TAU_GAMMA_SING"]:capi.ST["TAU_GAMMA_SING"] + 4])
+        if it % 10 == 0:
+            tau, ps, pd, pp = ts.update()                  # collective: every rank calls it
+            o.set_excit_probs(ps, pd, pp)
+            trace.append((tau, ps, pd, pp))
+    np.savez(os.path.join(out_dir, "tau%d.npz" % rank), trace=np.array(trace), local_gamma=local_gamma, gamma=ts.gamma,
+             cnt=ts.cnt)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tau_search_switches_and_maxima_are_reduced_over_the_ranks(tmp_path):
+    """update_tau on two ranks (src/tau/tau_search_conventional.F90:295-312): gamma_* and max_death_cpt are reduced with
+    MPI_MAX and the enough_* switches with a logical OR, so every rank assigns the same tau and biases although their
+    own counters differ."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_tau_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(os.path.join(tmp_path, "tau%d.npz" % k)) for k in range(2)]
+    assert np.array_equal(r[0]["trace"], r[1]["trace"])                    # same tau, pSingles, pDoubles, pParallel on both ranks
+    assert not np.array_equal(r[0]["cnt"], r[1]["cnt"])                     # from different local counters
+    assert np.array_equal(r[0]["gamma"], r[1]["gamma"])
+    assert np.array_equal(r[0]["gamma"], np.maximum(r[0]["local_gamma"], r[1]["local_gamma"]))
+    assert r[0]["trace"][-1, 0] < 0.02 and 0.0 < r[0]["trace"][-1, 1] < 1.0
