@@ -7,23 +7,32 @@
 //
 // Parity pinning: the reference (Fortran + MPI) cannot be built in this image
 // (no gfortran/MPI), so the oracle is pinned against the reference's own
-// known-answer tests and properties instead (tests/test_oracle_*.py):
-//   - Hubbard matrix-element known answers
-//     (unit_tests/real_space_hubbard/test_real_space_hubbard.F90:2434-2436,
-//      unit_tests/k_space_hubbard/test_k_space_hubbard.F90:2534-2560)
+// known-answer tests, fixtures and printed run outputs instead (DESIGN.md section 2 has
+// the whole table; tests/test_oracle_golden.py, test_core_space_cpu.py, test_hphf_cpu.py, ...):
+//   - Hubbard matrix-element and generator known answers
+//     (unit_tests/real_space_hubbard/test_real_space_hubbard.F90, unit_tests/k_space_hubbard/test_k_space_hubbard.F90)
 //   - sltcnd property test  (unit_tests/sltcnd/test_sltcnd.F90:25-67)
 //   - alias-table L1 test   (unit_tests/sampler/test_aliasTables.F90:45-110)
-//   - PCHB sum(1/pgen) test (unit_tests/excitgen/pchb_excitgen_test_helper.F90:40-118)
+//   - PCHB sum(1/pgen) test (unit_tests/excitgen/pchb_excitgen_test_helper.F90:40-118), for the UNIF-UNIF,
+//     FULL-FULL and UNIF-FULL particle selections
+//   - DetermineDetNode: the `Reference processor` 58 reference runs printed, with the reference's own dSFMT
+//     (oracle/_ref, compiled in place from src/lib/dSFMT.cpp)
+//   - reference energies, deterministic-space sizes and core correlation energies printed by the reference's
+//     regression runs; determ_projection and SumEContrib by the first lines of the determ_doubles iteration table
 //   - exact diagonalisation energies of small lattices.
-// Parity UNPINNED by any reference vector (restatement reviewed against the
-// cited lines only): DetermineDetNode / FindWalkerHash values,
-// CompressSpawnedList / AnnihilateSpawnedParts outputs, determ_projection,
-// CalcHashTableStats.  The reference holds no test for those.
+// Parity UNPINNED by any reference vector (restatement reviewed against the cited lines, and checked against a
+// second restatement in the reference's sort-and-merge form, tests/literal_annihilation.py): FindWalkerHash values,
+// CompressSpawnedList / AnnihilateSpawnedParts outputs on a fixed list, CalcHashTableStats.  The reference holds no
+// test for those.
 //
 // The random stream is NOT the reference's dSFMT: both the oracle and the CUDA
 // engine draw from the same counter-based Philox4x32 streams (seven rounds) keyed by
-// (seed, iteration, determinant, attempt, purpose) -- see DESIGN.md §RNG -- so
-// a whole iteration of the engine can be compared with the oracle bit for bit.
+// (seed, iteration, determinant, attempt, purpose) -- see DESIGN.md section 3 -- so
+// a whole iteration of the engine can be compared with the oracle bit for bit.  Where the engine takes a choice
+// from fewer random numbers than the reference (PCHB: single/double, electron pair and exchange from one number;
+// k-space Hubbard: the opposite-spin electron pair from one number instead of a rejection loop; weighted particle
+// selection: the CDF branch of constrained_sample instead of redrawing), the oracle draws the same way; each such
+// place says so and keeps the reference's probabilities, which the acceptance tests above check.
 #pragma once
 #include <cstdint>
 #include <cstring>
