@@ -584,3 +584,49 @@ def test_k_hubbard_doubles_core_matches_the_reference_runs(which, ref_orbs):
         sl = slice(c["row_ptr"][i], c["row_ptr"][i + 1])
         Hh[i, c["col"][sl]] = c["val"][sl]
     assert np.allclose(Hh, H, rtol=1e-12, atol=1e-13)
+
+
+def test_particle_selection_tables_equal_the_brute_force_pair_weights():
+    """p_first / p_second of the weighted PCHB particle selections against an independent evaluation: the weight of a
+    spin-orbital pair (I, J) is the sum of |<IJ||AB>| over all hole pairs (what the reference accumulates sampler by
+    sampler, src/gasci_pchb_doubles_spatorb_fastweighted.fpp:374-420), p(J | I) its column normalised, p(I) the
+    normalised column sums (init_PC_WeightedParticles_t, src/gasci_pchb_doubles_select_particles.fpp:268-328)."""
+    n_spat = 5
+    s = host.random_fcidump_system(n_spat, 4, sparse=0.8, sparse_t=0.8, seed=12, particle_selection="FULL-FULL")
+    umat = s.tables["umat"]
+    nb = 2 * n_spat
+
+    def tri(a, b):
+        return a * (a - 1) // 2 + b if a > b else b * (b - 1) // 2 + a
+
+    def um(i, j, k, l):                                   # <ij|kl> over spatial orbitals, UMatInd
+        return umat[tri(tri(i, k), tri(j, l)) - 1]
+
+    def sp(o):
+        return (o + 1) // 2
+
+    def beta(o):
+        return o % 2 == 1
+
+    W = np.zeros((nb + 1, nb + 1))
+    for I in range(1, nb + 1):
+        for J in range(I + 1, nb + 1):
+            tot = 0.0
+            for A in range(1, nb + 1):
+                for B in range(A + 1, nb + 1):
+                    if A in (I, J) or B in (I, J):
+                        continue
+                    h = 0.0                                # sltcnd_2: <IJ|AB> - <IJ|BA> with spin deltas
+                    if beta(I) == beta(A) and beta(J) == beta(B):
+                        h += um(sp(I), sp(J), sp(A), sp(B))
+                    if beta(I) == beta(B) and beta(J) == beta(A):
+                        h -= um(sp(I), sp(J), sp(B), sp(A))
+                    tot += abs(h)
+            W[I, J] = W[J, I] = tot
+    W = W[1:, 1:]
+    col = W.sum(axis=0)
+    t = s.tables["pchb"]
+    assert np.allclose(t["p_first"], col / col.sum(), rtol=1e-12, atol=1e-15)
+    p2 = t["p_second"].reshape(nb, nb)
+    for I in range(nb):
+        assert np.allclose(p2[I], W[:, I] / col[I], rtol=1e-12, atol=1e-15)
