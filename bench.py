@@ -392,7 +392,7 @@ def main():
                     help="100 balancing blocks per rank (load-balance-blocks) and one adjust_load_balance pass "
                          "(block populations -> greedy plan -> device-to-device block moves) during warm-up")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="spawn exchange for N > 1: push kernel over NVLink peer memory (default) or NCCL send/recv")
+                    help="spawn exchange for N > 1: pushes over NVLink peer memory issued by the spawning kernels (default) or NCCL send/recv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -815,7 +815,7 @@ def run_workload(args, ctx, primary=True):
                        "walkers_total_end": walkers_end, "determinants_total_end": dets_end, "tau": tau, "shift": sft,
                        "initiator": True, "attempts_per_step": attempts / args.steps,
                        "spawned_per_step": spawned / args.steps, "partition": "DetermineDetNode hash" if world > 1 else "single rank",
-                       "exchange": ("push kernel over NVLink peer memory" if args.exchange == "p2p" else "NCCL send/recv") if world > 1 else "none",
+                       "exchange": ("routing + pushes over NVLink peer memory inside the spawning kernels" if args.exchange == "p2p" else "NCCL send/recv") if world > 1 else "none",
                        "l2": "inputs larger than L2 (walker list %.0f MB per GPU > 126 MB)" % (dets_end / world * (8 * system.nw + 28) / 1e6),
                        "wall_ms_per_step": 1e3 * wall / args.steps, **({"semi_stochastic": core_info} if semi else {}),
                        **({"load_balance": {"blocks_per_rank": 100, **(lb_moves or {})}} if args.load_balance else {}),
