@@ -355,7 +355,8 @@ def test_pchb_generator_sum_inverse_pgen():
 def test_pchb_full_full_particle_selection_sum_inverse_pgen(selection):
     """The same acceptance test with PCHB_ParticleSelection FULL-FULL (PC_FullyWeightedParticles_t,
     src/gasci_pchb_doubles_select_particles.fpp:330-438), the selection the reference's own PCHB regression input uses,
-    and UNIF-FULL (PC_WeightedParticles_t, :440-506: first particle uniform, second weighted):
+    and UNIF-FULL (PC_WeightedParticles_t, :440-506: first particle uniform, second weighted); the reference runs the
+    same harness on the same determinant for these particle selections in unit_tests/gasci/gasci_pchb_test_helper.F90:62-125:
     sum(1/pgen)/n_iter within [0.85, 1.15] for every connected determinant with a non-zero element, completeness, and
     get_pgen (which depends on the determinant here) == returned pgen.  Also the tables themselves: p_first and every
     row of p_second are normalised, p(I | I) = 0, the pair weights are symmetric."""
